@@ -1,0 +1,19 @@
+"""oracle/ -- TEST INFRASTRUCTURE, not product code.
+
+CPU restatement (PyTorch fp32 + a small C library) of the reference's algorithm for
+GLASS's per-image dense forward path.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference``
+legs may import anything from here; the product package
+(``glass_text_spotting_b200``) never does.
+
+Parity pinning: the reference ships no tests or golden vectors, and its
+arithmetic below the GLASS modules lives in detectron2 v0.6, which is not vendored and
+not installable offline.  The oracle is therefore pinned by
+  * detectron2's upstream known-answer tests for the restated operators
+    (tests/test_oracle_d2_ops.py), torchvision angle-0 equivalences, and
+  * golden vectors generated in the authoring container by importing the reference's
+    own pure-torch modules from /root/reference (tools/make_golden.py ->
+    tests/golden/*.pt; checked by tests/test_oracle_golden.py).
+The detectron2-recalled parts (backbone wiring, RPN, poolers) have no reference-run
+pin: for them parity is "unpinned beyond the upstream KATs" (see DESIGN.md).
+"""

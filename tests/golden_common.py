@@ -1,0 +1,63 @@
+"""Seeds, inputs and the seeded weight fill shared by tools/make_golden.py (which runs
+the reference's modules in the authoring container) and tests/test_oracle_golden.py
+(which replays the same seeds through oracle/nets.py)."""
+import math
+
+import torch
+from torch import nn
+
+SEEDS = {"hybrid": 11, "fusion": 12, "p2p3": 13, "encoder": 14, "decoder": 15, "decoder_break": 16}
+
+
+def seeded_input(case):
+    g = torch.Generator().manual_seed(1000 + SEEDS[case])
+    if case == "hybrid":
+        return torch.randn(2, 3, 128, 128, generator=g) * 50.0
+    if case == "fusion":
+        return torch.randn(2, 512, 8, 32, generator=g)
+    if case == "p2p3":
+        return torch.randn(1, 256, 16, 16, generator=g), torch.randn(1, 256, 8, 8, generator=g)
+    if case == "encoder":
+        return torch.randn(3, 256, 4, 32, generator=g)
+    if case == "decoder":
+        return torch.randn(3, 32, 256, generator=g)
+    if case == "decoder_break":
+        return torch.randn(2, 32, 256, generator=g)
+    raise KeyError(case)
+
+
+def seeded_fill(module: nn.Module, seed: int):
+    """Deterministic, scale-preserving fill keyed on parameter *names* (sorted), so a
+    reference module and its oracle restatement with equal state_dict keys get equal
+    values."""
+    g = torch.Generator().manual_seed(seed)
+    sd = module.state_dict()
+    for name in sorted(sd.keys()):
+        t = sd[name]
+        if name.endswith("num_batches_tracked"):
+            continue
+        if name.endswith("running_var"):
+            t.copy_(0.5 + torch.rand(t.shape, generator=g))
+        elif name.endswith("running_mean"):
+            t.copy_(0.1 * torch.randn(t.shape, generator=g))
+        elif name.endswith("temperature"):
+            t.fill_(1.0)
+        elif t.dim() >= 2:
+            fan_in = t[0].numel()
+            t.copy_(torch.randn(t.shape, generator=g) * math.sqrt(1.5 / fan_in))
+        elif ("bn" in name or "norm" in name or "downsample.1" in name or "channel_add_conv.1" in name) \
+                and name.endswith("weight"):
+            t.copy_(0.75 + 0.5 * torch.rand(t.shape, generator=g))
+        else:
+            t.copy_(0.1 * torch.randn(t.shape, generator=g))
+    module.load_state_dict(sd)
+
+
+def force_eos_bias(head):
+    """Liven the decoder up (larger embeddings / output weights) and bias class 0 so that the
+    reference's early break `dones.min() != 0` fires mid-sequence (after 6 of 26 steps: word 1
+    emits class 0 at step 0 and keeps decoding, word 0 first emits it at step 5)."""
+    with torch.no_grad():
+        head.decoder.tgt_embedding.weight *= 6.0
+        head.decoder.fc.weight *= 4.0
+        head.decoder.fc.bias[0] += 2.0
