@@ -1,0 +1,394 @@
+// conv_gemm.cu -- persistent, warp-specialised tcgen05 implicit-GEMM (sm_100a).
+//
+// One kernel serves every conv / Linear on GLASS's dense path (see include/glass_b200.h).
+//   A: activations, split-bf16 padded NHWC flattened to rows [pixels, C]; a conv tap (r,s) is a
+//      constant row shift, so each k-block is ONE 2-D TMA box (64 channels x 128 pixels) at row
+//      m0 + shift -- image borders are real zero pixels in memory, tensor edges are TMA OOB zeros.
+//   B: weights packed [Cout, taps*C] K-major.
+//   D: 128 x BN fp32 accumulator in TMEM, double buffered (2 x 256 columns) so the epilogue of tile
+//      i overlaps the main loop of tile i+1.
+// Roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warp 2 = TMEM
+// allocator, warps 4..7 = epilogue (one TMEM lane quadrant each).
+// Precision modes: bf16x3 split (3 MMAs per k-step into the same accumulator: hi*hi, hi*lo, lo*hi)
+// gives fp32-grade results (rel err ~1e-5); mode 1 issues only hi*hi.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "glass_b200.h"
+#include "host_util.h"
+
+namespace glass {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;
+static constexpr int ACC_COLS = 256;  // TMEM columns per accumulator stage
+static constexpr int A_TILE_BYTES = BM * BK * 2;
+static constexpr int NUM_THREADS = 256;
+static constexpr int MAX_STAGES = 8;
+
+struct GemmKernelParams {
+  int64_t rows_m;
+  int32_t tiles_m, tiles_n, bn;
+  int32_t kblocks_per_tap, ntaps;
+  int32_t tap_shift[GLASS_MAX_TAPS];
+  int32_t num_stages, stage_bytes, b_tile_bytes;
+  int32_t m_h, m_w, m_border;
+  const float* scale;
+  const float* bias;
+  int32_t relu_pre, relu_post;
+  const __nv_bfloat16* res_hi;
+  const __nv_bfloat16* res_lo;
+  int32_t res_hp, res_wp, res_border, res_shift;
+  __nv_bfloat16* out_hi;
+  __nv_bfloat16* out_lo;
+  float* out_f32;
+  int32_t out_hp, out_wp, out_border;
+  int32_t ld_out, ld_f32, n_store;
+};
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                 const GemmKernelParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages x (A_hi, A_lo?, B_hi, B_lo?)] then barriers
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.num_stages * p.stage_bytes);
+  uint64_t* full_bar = bars;                      // [MAX_STAGES]
+  uint64_t* empty_bar = bars + MAX_STAGES;        // [MAX_STAGES]
+  uint64_t* tmem_full_bar = bars + 2 * MAX_STAGES;   // [2]
+  uint64_t* tmem_empty_bar = bars + 2 * MAX_STAGES + 2;  // [2]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int kblocks = p.kblocks_per_tap * p.ntaps;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a_hi);
+    tma_prefetch_desc(&map_b_hi);
+    if (SPLIT) {
+      tma_prefetch_desc(&map_a_lo);
+      tma_prefetch_desc(&map_b_lo);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < p.num_stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_holder, 2 * ACC_COLS);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tm = tile / p.tiles_n;
+        const int tn = tile - tm * p.tiles_n;
+        const int m0 = tm * BM;
+        const int n0 = tn * p.bn;
+        for (int t = 0; t < p.ntaps; ++t) {
+          const int arow = m0 + p.tap_shift[t];
+          for (int kb = 0; kb < p.kblocks_per_tap; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* s = smem + (size_t)stage * p.stage_bytes;
+            mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)p.stage_bytes);
+            const int ka = kb * BK;
+            const int kw = (t * p.kblocks_per_tap + kb) * BK;
+            tma_load_2d(s, &map_a_hi, &full_bar[stage], ka, arow);
+            if (SPLIT) {
+              tma_load_2d(s + A_TILE_BYTES, &map_a_lo, &full_bar[stage], ka, arow);
+              tma_load_2d(s + 2 * A_TILE_BYTES, &map_b_hi, &full_bar[stage], kw, n0);
+              tma_load_2d(s + 2 * A_TILE_BYTES + p.b_tile_bytes, &map_b_lo, &full_bar[stage], kw, n0);
+            } else {
+              tma_load_2d(s + A_TILE_BYTES, &map_b_hi, &full_bar[stage], kw, n0);
+            }
+            if (++stage == p.num_stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16_f32(BM, p.bn);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local_tile = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
+        const int acc = local_tile & 1;
+        const uint32_t acc_phase = (uint32_t)(local_tile >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t s = smem_u32(smem + (size_t)stage * p.stage_bytes);
+          const uint64_t da_hi = umma_smem_desc_sw128(s);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t koff = (uint64_t)(k * 2);  // 32 bytes >> 4
+            const uint32_t acc_flag = (kb > 0 || k > 0) ? 1u : 0u;
+            if (SPLIT) {
+              const uint64_t da_lo = umma_smem_desc_sw128(s + A_TILE_BYTES);
+              const uint64_t db_hi = umma_smem_desc_sw128(s + 2 * A_TILE_BYTES);
+              const uint64_t db_lo = umma_smem_desc_sw128(s + 2 * A_TILE_BYTES + p.b_tile_bytes);
+              umma_bf16_ss(d_tmem, da_lo + koff, db_hi + koff, idesc, acc_flag);
+              umma_bf16_ss(d_tmem, da_hi + koff, db_lo + koff, idesc, 1u);
+              umma_bf16_ss(d_tmem, da_hi + koff, db_hi + koff, idesc, 1u);
+            } else {
+              const uint64_t db_hi = umma_smem_desc_sw128(s + A_TILE_BYTES);
+              umma_bf16_ss(d_tmem, da_hi + koff, db_hi + koff, idesc, acc_flag);
+            }
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (kb == kblocks - 1) umma_commit(&tmem_full_bar[acc]);
+          if (++stage == p.num_stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================================== epilogue
+    const int q = warp - 4;  // TMEM lane quadrant == warp % 4
+    const int row_in_tile = q * 32 + lane;
+    const int plane = p.m_h * p.m_w;
+    const int nchunks_full = p.bn / 16;
+    int local_tile = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
+      const int tm = tile / p.tiles_n;
+      const int tn = tile - tm * p.tiles_n;
+      const int n0 = tn * p.bn;
+      const int64_t m = (int64_t)tm * BM + row_in_tile;
+      bool valid = m < p.rows_m;
+      int64_t out_row = 0, res_row = 0;
+      if (valid) {
+        const int img = (int)(m / plane);
+        const int rem = (int)(m - (int64_t)img * plane);
+        const int yy = rem / p.m_w;
+        const int xx = rem - yy * p.m_w;
+        const int y = yy - p.m_border, x = xx - p.m_border;
+        valid = (y >= 0) && (x >= 0) && (yy < p.m_h - p.m_border) && (xx < p.m_w - p.m_border);
+        out_row = ((int64_t)img * p.out_hp + y + p.out_border) * p.out_wp + x + p.out_border;
+        res_row = ((int64_t)img * p.res_hp + (y >> p.res_shift) + p.res_border) * p.res_wp + (x >> p.res_shift) +
+                  p.res_border;
+      }
+      const int acc = local_tile & 1;
+      const uint32_t acc_phase = (uint32_t)(local_tile >> 1) & 1;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t t_row = tmem_base + (uint32_t)(acc * ACC_COLS) + ((uint32_t)(q * 32) << 16);
+      for (int c = 0; c < nchunks_full; ++c) {
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(t_row + (uint32_t)(c * 16), r);
+        tmem_ld_wait();
+        const int n = n0 + c * 16;
+        if (valid && n < p.n_store) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.scale != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + n + j));
+              v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
+            }
+          }
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            }
+          }
+          if (p.relu_pre) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (p.res_hi != nullptr) {
+            const uint4* rh = reinterpret_cast<const uint4*>(p.res_hi + res_row * p.ld_out + n);
+            const uint4* rl = reinterpret_cast<const uint4*>(p.res_lo + res_row * p.ld_out + n);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const uint4 a = __ldg(rh + h);
+              const uint4 b = __ldg(rl + h);
+              const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+              const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                v[h * 8 + 2 * j] += bf16_lo_of(aw[j]) + bf16_lo_of(bw[j]);
+                v[h * 8 + 2 * j + 1] += bf16_hi_of(aw[j]) + bf16_hi_of(bw[j]);
+              }
+            }
+          }
+          if (p.relu_post) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (p.out_f32 != nullptr) {
+            float4* o = reinterpret_cast<float4*>(p.out_f32 + out_row * p.ld_f32 + n);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          if (p.out_hi != nullptr) {
+            uint32_t hw[8], lw[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              __nv_bfloat16 h0, l0, h1, l1;
+              split_bf16(v[2 * j], h0, l0);
+              split_bf16(v[2 * j + 1], h1, l1);
+              hw[j] = pack_bf16x2(h0, h1);
+              lw[j] = pack_bf16x2(l0, l1);
+            }
+            uint4* oh = reinterpret_cast<uint4*>(p.out_hi + out_row * p.ld_out + n);
+            oh[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            oh[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+            if (p.out_lo != nullptr) {
+              uint4* ol = reinterpret_cast<uint4*>(p.out_lo + out_row * p.ld_out + n);
+              ol[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+              ol[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 2 * ACC_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+static int make_map_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint32_t box_inner,
+                       uint32_t box_outer) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (enc == nullptr) return fail("cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {inner * 2};  // bytes, dim 1
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+  return 0;
+}
+
+}  // namespace glass
+
+using namespace glass;
+
+extern "C" int glass_conv_gemm(const GlassConvGemmParams* p, void* stream_v) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  GLASS_CHECK(p != nullptr, "null params");
+  GLASS_CHECK(p->a_hi && p->b_hi, "a_hi / b_hi must be set");
+  const bool split = (p->mode == 0);
+  GLASS_CHECK(p->mode == 0 || p->mode == 1, "mode must be 0 (bf16x3) or 1 (bf16)");
+  if (split) GLASS_CHECK(p->a_lo && p->b_lo, "bf16x3 mode needs a_lo / b_lo");
+  GLASS_CHECK(p->k_per_tap > 0 && p->k_per_tap % BK == 0, "k_per_tap must be a positive multiple of 64");
+  GLASS_CHECK(p->ntaps >= 1 && p->ntaps <= GLASS_MAX_TAPS, "ntaps out of range");
+  GLASS_CHECK(p->n >= 16 && p->n % 16 == 0, "n must be a multiple of 16");
+  int bn = p->n;
+  if (p->n > 256) {
+    GLASS_CHECK(p->n % 128 == 0, "n > 256 must be a multiple of 128");
+    bn = (p->n % 256 == 0) ? 256 : 128;
+  }
+  const int64_t rows_m = (int64_t)p->m_imgs * p->m_h * p->m_w;
+  GLASS_CHECK(rows_m > 0 && rows_m < (int64_t)1 << 31, "bad M space");
+  GLASS_CHECK(p->rows_a > 0 && p->rows_a < (int64_t)1 << 31, "bad rows_a");
+  GLASS_CHECK(p->m_border >= 0 && 2 * p->m_border < p->m_h && 2 * p->m_border < p->m_w, "bad m_border");
+  GLASS_CHECK(p->out_hi || p->out_f32, "no output requested");
+  const int n_store = p->n_store > 0 ? p->n_store : p->n;
+  GLASS_CHECK(n_store <= p->n, "n_store > n");
+  if (p->out_hi || p->res_hi) GLASS_CHECK(p->ld_out >= n_store && p->ld_out % 8 == 0, "ld_out must be >= n_store, multiple of 8");
+  if (p->out_f32) GLASS_CHECK(p->ld_f32 >= n_store && p->ld_f32 % 4 == 0, "ld_f32 must be >= n_store, multiple of 4");
+  GLASS_CHECK(n_store % 16 == 0, "n_store must be a multiple of 16");
+  if (p->res_hi) GLASS_CHECK(p->res_lo != nullptr, "res_lo missing");
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  GLASS_CHECK(al16(p->a_hi) && al16(p->a_lo) && al16(p->b_hi) && al16(p->b_lo) && al16(p->out_hi) &&
+                  al16(p->out_lo) && al16(p->out_f32) && al16(p->res_hi) && al16(p->res_lo) && al16(p->scale) &&
+                  al16(p->bias),
+              "all pointers must be 16-byte aligned");
+
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  const uint64_t ktot = (uint64_t)p->k_per_tap * p->ntaps;
+  if (make_map_2d(&ma_hi, p->a_hi, p->k_per_tap, p->rows_a, BK, BM)) return -1;
+  if (make_map_2d(&mb_hi, p->b_hi, ktot, p->n, BK, bn)) return -1;
+  if (split) {
+    if (make_map_2d(&ma_lo, p->a_lo, p->k_per_tap, p->rows_a, BK, BM)) return -1;
+    if (make_map_2d(&mb_lo, p->b_lo, ktot, p->n, BK, bn)) return -1;
+  } else {
+    ma_lo = ma_hi;
+    mb_lo = mb_hi;
+  }
+
+  GemmKernelParams k{};
+  k.rows_m = rows_m;
+  k.tiles_m = (int)((rows_m + BM - 1) / BM);
+  k.tiles_n = p->n / bn;
+  k.bn = bn;
+  k.kblocks_per_tap = p->k_per_tap / BK;
+  k.ntaps = p->ntaps;
+  for (int i = 0; i < GLASS_MAX_TAPS; ++i) k.tap_shift[i] = p->tap_shift[i];
+  k.b_tile_bytes = bn * BK * 2;
+  k.stage_bytes = (A_TILE_BYTES + k.b_tile_bytes) * (split ? 2 : 1);
+  const int smem_budget = 200 * 1024;
+  k.num_stages = smem_budget / k.stage_bytes;
+  if (k.num_stages > MAX_STAGES) k.num_stages = MAX_STAGES;
+  GLASS_CHECK(k.num_stages >= 2, "stage too large");
+  k.m_h = p->m_h; k.m_w = p->m_w; k.m_border = p->m_border;
+  k.scale = p->scale; k.bias = p->bias;
+  k.relu_pre = p->relu_pre; k.relu_post = p->relu_post;
+  k.res_hi = (const __nv_bfloat16*)p->res_hi; k.res_lo = (const __nv_bfloat16*)p->res_lo;
+  k.res_hp = p->res_hp; k.res_wp = p->res_wp; k.res_border = p->res_border; k.res_shift = p->res_shift;
+  k.out_hi = (__nv_bfloat16*)p->out_hi; k.out_lo = (__nv_bfloat16*)p->out_lo; k.out_f32 = p->out_f32;
+  k.out_hp = p->out_hp; k.out_wp = p->out_wp; k.out_border = p->out_border;
+  k.ld_out = p->ld_out; k.ld_f32 = p->ld_f32; k.n_store = n_store;
+
+  // always ask for > half of the SM's shared memory: exactly one CTA per SM owns all 512 TMEM columns
+  const int smem_bytes = k.num_stages * k.stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  const int smem_req = smem_bytes < 120 * 1024 ? 120 * 1024 : smem_bytes;
+  const int sms = num_sms();
+  GLASS_CHECK(sms > 0, "no CUDA device");
+  const int total_tiles = k.tiles_m * k.tiles_n;
+  const int grid = total_tiles < sms ? total_tiles : sms;
+  if (split) {
+    GLASS_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_req));
+    conv_gemm_kernel<true><<<grid, NUM_THREADS, smem_req, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, k);
+  } else {
+    GLASS_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_req));
+    conv_gemm_kernel<false><<<grid, NUM_THREADS, smem_req, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, k);
+  }
+  count_launch();
+  GLASS_CUDA(cudaGetLastError());
+  return 0;
+}

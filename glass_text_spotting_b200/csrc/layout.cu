@@ -1,0 +1,300 @@
+// layout.cu -- HBM-bound glue kernels around the tcgen05 GEMM: layout conversion between fp32 NCHW
+// (the reference's tensors) and split-bf16 padded NHWC (ours), the stem im2col with fused pixel
+// normalisation, the generic tap gather for strided convs, and max-pooling.
+// All are streaming kernels: 16-byte vector accesses along the channel (innermost) dimension.
+#include "common.cuh"
+#include "glass_b200.h"
+#include "host_util.h"
+
+namespace glass {
+
+static inline int grid_for(int64_t total, int block) {
+  int64_t g = (total + block - 1) / block;
+  const int64_t cap = (int64_t)num_sms() * 32;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// ------------------------------------------------------------------ NCHW fp32 -> split padded NHWC
+// One thread per (pixel, 8-channel group): reads 8 strided floats (coalesced across the warp along
+// x), writes one 16 B vector per plane.
+__global__ void pack_nchw_kernel(const float* __restrict__ src, int n, int c, int h, int w,
+                                 __nv_bfloat16* __restrict__ dhi, __nv_bfloat16* __restrict__ dlo, int cp,
+                                 int border) {
+  const int groups = (c + 7) / 8;
+  const int64_t total = (int64_t)n * groups * h * w;
+  const int hp = h + 2 * border, wp = w + 2 * border;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % w);
+    int64_t t = i / w;
+    const int y = (int)(t % h);
+    t /= h;
+    const int g = (int)(t % groups);
+    const int img = (int)(t / groups);
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float v0 = 0.f, v1 = 0.f;
+      const int c0 = g * 8 + 2 * j;
+      if (c0 < c) v0 = src[(((int64_t)img * c + c0) * h + y) * w + x];
+      if (c0 + 1 < c) v1 = src[(((int64_t)img * c + c0 + 1) * h + y) * w + x];
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(v0, h0, l0);
+      split_bf16(v1, h1, l1);
+      hw[j] = pack_bf16x2(h0, h1);
+      lw[j] = pack_bf16x2(l0, l1);
+    }
+    const int64_t row = ((int64_t)img * hp + y + border) * wp + x + border;
+    *reinterpret_cast<uint4*>(dhi + row * cp + g * 8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    *reinterpret_cast<uint4*>(dlo + row * cp + g * 8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+  }
+}
+
+__global__ void unpack_nchw_kernel(const __nv_bfloat16* __restrict__ shi, const __nv_bfloat16* __restrict__ slo,
+                                   int n, int c, int h, int w, int cp, int border, float* __restrict__ dst) {
+  const int64_t total = (int64_t)n * c * h * w;
+  const int hp = h + 2 * border, wp = w + 2 * border;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % w);
+    int64_t t = i / w;
+    const int y = (int)(t % h);
+    t /= h;
+    const int ch = (int)(t % c);
+    const int img = (int)(t / c);
+    const int64_t row = ((int64_t)img * hp + y + border) * wp + x + border;
+    dst[i] = __bfloat162float(shi[row * cp + ch]) + __bfloat162float(slo[row * cp + ch]);
+  }
+}
+
+__global__ void nhwc_f32_to_nchw_kernel(const float* __restrict__ src, int n, int c, int h, int w, int ld,
+                                        int border, float* __restrict__ dst) {
+  const int64_t total = (int64_t)n * c * h * w;
+  const int hp = h + 2 * border, wp = w + 2 * border;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % w);
+    int64_t t = i / w;
+    const int y = (int)(t % h);
+    t /= h;
+    const int ch = (int)(t % c);
+    const int img = (int)(t / c);
+    const int64_t row = ((int64_t)img * hp + y + border) * wp + x + border;
+    dst[i] = src[row * ld + ch];
+  }
+}
+
+// ------------------------------------------------------------------ stem im2col (7x7 s2 p3, Cin 3)
+// One thread per (output pixel, 8-wide k group).  k = (r*7+s)*3 + c.
+__global__ void stem_im2col_kernel(const float* __restrict__ img, int n, int h, int w, float m0, float m1, float m2,
+                                   float is0, float is1, float is2, __nv_bfloat16* __restrict__ dhi,
+                                   __nv_bfloat16* __restrict__ dlo, int kp) {
+  const int ho = h / 2, wo = w / 2;
+  const int groups = kp / 8;
+  const int64_t total = (int64_t)n * ho * wo * groups;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    const int64_t pix = i / groups;
+    const int x = (int)(pix % wo);
+    const int y = (int)((pix / wo) % ho);
+    const int b = (int)(pix / ((int64_t)wo * ho));
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = g * 8 + j;
+      float val = 0.f;
+      if (k < 147) {
+        const int tap = k / 3, c = k - tap * 3;
+        const int r = tap / 7, s = tap - r * 7;
+        const int iy = 2 * y - 3 + r, ix = 2 * x - 3 + s;
+        if (iy >= 0 && iy < h && ix >= 0 && ix < w) {
+          const float raw = __ldg(img + (((int64_t)b * 3 + c) * h + iy) * w + ix);
+          const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2);
+          const float is = c == 0 ? is0 : (c == 1 ? is1 : is2);
+          val = (raw - mean) * is;
+        }
+      }
+      v[j] = val;
+    }
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(v[2 * j], h0, l0);
+      split_bf16(v[2 * j + 1], h1, l1);
+      hw[j] = pack_bf16x2(h0, h1);
+      lw[j] = pack_bf16x2(l0, l1);
+    }
+    *reinterpret_cast<uint4*>(dhi + pix * kp + g * 8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    *reinterpret_cast<uint4*>(dlo + pix * kp + g * 8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+  }
+}
+
+// ------------------------------------------------------------------ generic tap gather
+__global__ void gather_taps_kernel(const uint4* __restrict__ shi, const uint4* __restrict__ slo, int n, int h, int w,
+                                   int cv /*cp/8*/, int border, int kh, int kw, int sh, int sw, int ph, int pw,
+                                   int ho, int wo, uint4* __restrict__ dhi, uint4* __restrict__ dlo) {
+  const int taps = kh * kw;
+  const int64_t total = (int64_t)n * ho * wo * taps * cv;
+  const int hp = h + 2 * border, wp = w + 2 * border;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv);
+    int64_t t = i / cv;
+    const int tap = (int)(t % taps);
+    const int64_t pix = t / taps;
+    const int x = (int)(pix % wo);
+    const int y = (int)((pix / wo) % ho);
+    const int b = (int)(pix / ((int64_t)wo * ho));
+    const int r = tap / kw, s = tap - r * kw;
+    const int iy = y * sh - ph + r, ix = x * sw - pw + s;
+    uint4 vh = make_uint4(0, 0, 0, 0), vl = vh;
+    if (iy >= 0 && iy < h && ix >= 0 && ix < w) {
+      const int64_t row = ((int64_t)b * hp + iy + border) * wp + ix + border;
+      vh = __ldg(shi + row * cv + c);
+      vl = __ldg(slo + row * cv + c);
+    }
+    dhi[i] = vh;
+    dlo[i] = vl;
+  }
+}
+
+// ------------------------------------------------------------------ max pool (padding = -inf)
+__global__ void maxpool_kernel(const uint4* __restrict__ shi, const uint4* __restrict__ slo, int n, int h, int w,
+                               int cv, int border, int kh, int kw, int sh, int sw, int ph, int pw, int ho, int wo,
+                               uint4* __restrict__ dhi, uint4* __restrict__ dlo, int dborder) {
+  const int64_t total = (int64_t)n * ho * wo * cv;
+  const int hp = h + 2 * border, wp = w + 2 * border;
+  const int dhp = ho + 2 * dborder, dwp = wo + 2 * dborder;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv);
+    const int64_t pix = i / cv;
+    const int x = (int)(pix % wo);
+    const int y = (int)((pix / wo) % ho);
+    const int b = (int)(pix / ((int64_t)wo * ho));
+    float best[8];
+    uint32_t bh[8], bl[8];  // bf16 bit patterns of the winning (hi, lo)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      best[j] = -INFINITY;
+      bh[j] = 0;
+      bl[j] = 0;
+    }
+    for (int r = 0; r < kh; ++r) {
+      const int iy = y * sh - ph + r;
+      if (iy < 0 || iy >= h) continue;
+      for (int s = 0; s < kw; ++s) {
+        const int ix = x * sw - pw + s;
+        if (ix < 0 || ix >= w) continue;
+        const int64_t row = ((int64_t)b * hp + iy + border) * wp + ix + border;
+        const uint4 a = __ldg(shi + row * cv + c);
+        const uint4 d = __ldg(slo + row * cv + c);
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+        const uint32_t dw[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float v0 = bf16_lo_of(aw[j]) + bf16_lo_of(dw[j]);
+          const float v1 = bf16_hi_of(aw[j]) + bf16_hi_of(dw[j]);
+          if (v0 > best[2 * j]) {
+            best[2 * j] = v0;
+            bh[2 * j] = aw[j] & 0xffffu;
+            bl[2 * j] = dw[j] & 0xffffu;
+          }
+          if (v1 > best[2 * j + 1]) {
+            best[2 * j + 1] = v1;
+            bh[2 * j + 1] = aw[j] >> 16;
+            bl[2 * j + 1] = dw[j] >> 16;
+          }
+        }
+      }
+    }
+    const int64_t orow = ((int64_t)b * dhp + y + dborder) * dwp + x + dborder;
+    dhi[orow * cv + c] = make_uint4(bh[0] | (bh[1] << 16), bh[2] | (bh[3] << 16), bh[4] | (bh[5] << 16),
+                                    bh[6] | (bh[7] << 16));
+    dlo[orow * cv + c] = make_uint4(bl[0] | (bl[1] << 16), bl[2] | (bl[3] << 16), bl[4] | (bl[5] << 16),
+                                    bl[6] | (bl[7] << 16));
+  }
+}
+
+}  // namespace glass
+
+using namespace glass;
+#define STREAM reinterpret_cast<cudaStream_t>(stream)
+
+extern "C" int glass_pack_nchw(const float* src, int n, int c, int h, int w, void* dst_hi, void* dst_lo, int cp,
+                               int border, void* stream) {
+  GLASS_CHECK(src && dst_hi && dst_lo, "null pointer");
+  GLASS_CHECK(n > 0 && c > 0 && h > 0 && w > 0 && cp >= c && cp % 8 == 0 && border >= 0, "bad shape");
+  const int64_t total = (int64_t)n * ((c + 7) / 8) * h * w;
+  pack_nchw_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>(src, n, c, h, w, (__nv_bfloat16*)dst_hi,
+                                                             (__nv_bfloat16*)dst_lo, cp, border);
+  count_launch();
+  GLASS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int glass_unpack_nchw(const void* src_hi, const void* src_lo, int n, int c, int h, int w, int cp,
+                                 int border, float* dst, void* stream) {
+  GLASS_CHECK(src_hi && src_lo && dst, "null pointer");
+  GLASS_CHECK(n > 0 && c > 0 && h > 0 && w > 0 && cp >= c && border >= 0, "bad shape");
+  const int64_t total = (int64_t)n * c * h * w;
+  unpack_nchw_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>((const __nv_bfloat16*)src_hi,
+                                                               (const __nv_bfloat16*)src_lo, n, c, h, w, cp, border,
+                                                               dst);
+  count_launch();
+  GLASS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int glass_nhwc_f32_to_nchw(const float* src, int n, int c, int h, int w, int ld, int border, float* dst,
+                                      void* stream) {
+  GLASS_CHECK(src && dst, "null pointer");
+  GLASS_CHECK(n > 0 && c > 0 && h > 0 && w > 0 && ld >= c && border >= 0, "bad shape");
+  const int64_t total = (int64_t)n * c * h * w;
+  nhwc_f32_to_nchw_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>(src, n, c, h, w, ld, border, dst);
+  count_launch();
+  GLASS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int glass_stem_im2col(const float* img, int n, int h, int w, const float* mean, const float* inv_std,
+                                 void* dst_hi, void* dst_lo, int kp, void* stream) {
+  GLASS_CHECK(img && mean && inv_std && dst_hi && dst_lo, "null pointer (mean / inv_std are HOST float[3])");
+  GLASS_CHECK(n > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0, "h, w must be even");
+  GLASS_CHECK(kp >= 152 && kp % 64 == 0, "kp must be a multiple of 64 >= 192");
+  const int64_t total = (int64_t)n * (h / 2) * (w / 2) * (kp / 8);
+  stem_im2col_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>(img, n, h, w, mean[0], mean[1], mean[2], inv_std[0],
+                                                               inv_std[1], inv_std[2], (__nv_bfloat16*)dst_hi,
+                                                               (__nv_bfloat16*)dst_lo, kp);
+  count_launch();
+  GLASS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int glass_gather_taps(const void* src_hi, const void* src_lo, int n, int h, int w, int cp, int border,
+                                 int kh, int kw, int sh, int sw, int ph, int pw, int ho, int wo, void* dst_hi,
+                                 void* dst_lo, void* stream) {
+  GLASS_CHECK(src_hi && src_lo && dst_hi && dst_lo, "null pointer");
+  GLASS_CHECK(n > 0 && h > 0 && w > 0 && cp % 8 == 0 && kh > 0 && kw > 0 && sh > 0 && sw > 0 && ho > 0 && wo > 0,
+              "bad shape");
+  const int64_t total = (int64_t)n * ho * wo * kh * kw * (cp / 8);
+  gather_taps_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>((const uint4*)src_hi, (const uint4*)src_lo, n, h, w,
+                                                               cp / 8, border, kh, kw, sh, sw, ph, pw, ho, wo,
+                                                               (uint4*)dst_hi, (uint4*)dst_lo);
+  count_launch();
+  GLASS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int glass_maxpool(const void* src_hi, const void* src_lo, int n, int h, int w, int cp, int border, int kh,
+                             int kw, int sh, int sw, int ph, int pw, int ho, int wo, void* dst_hi, void* dst_lo,
+                             int dst_border, void* stream) {
+  GLASS_CHECK(src_hi && src_lo && dst_hi && dst_lo, "null pointer");
+  GLASS_CHECK(n > 0 && h > 0 && w > 0 && cp % 8 == 0 && kh > 0 && kw > 0 && sh > 0 && sw > 0 && ho > 0 && wo > 0,
+              "bad shape");
+  const int64_t total = (int64_t)n * ho * wo * (cp / 8);
+  maxpool_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>((const uint4*)src_hi, (const uint4*)src_lo, n, h, w,
+                                                           cp / 8, border, kh, kw, sh, sw, ph, pw, ho, wo,
+                                                           (uint4*)dst_hi, (uint4*)dst_lo, dst_border);
+  count_launch();
+  GLASS_CUDA(cudaGetLastError());
+  return 0;
+}

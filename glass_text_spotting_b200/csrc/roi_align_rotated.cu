@@ -1,0 +1,288 @@
+// roi_align_rotated.cu -- multi-level rotated RoIAlign for sm_100a (HBM/L2 gather-bound).
+//
+// Algorithm = detectron2 v0.6 ROIAlignRotated (layers/csrc/ROIAlignRotated) + ROIPooler level
+// assignment (modeling/poolers.py), as used by the reference at recognizers_hybrid_head.py:320,
+// :550, :556.  Layout is ours: feature maps are fp32 NHWC so that the four
+// bilinear taps of a sample are four contiguous C-vectors; one warp owns one output bin and its
+// lanes sweep the channel vector with 16-byte loads (C = 256 -> two float4 per lane per tap, a
+// fully coalesced 1 KB request).  The geometry (cos/sin, bin size, sampling grid) is warp-uniform.
+#include "common.cuh"
+#include "glass_b200.h"
+#include "host_util.h"
+
+namespace glass {
+
+struct RoiKernelParams {
+  int num_levels;
+  const float* feat[GLASS_MAX_LEVELS];
+  int feat_h[GLASS_MAX_LEVELS], feat_w[GLASS_MAX_LEVELS];
+  float scale[GLASS_MAX_LEVELS];
+  int border, ld, channels, min_level;
+  const float* rois;
+  const int* n_rois_dev;
+  int n_rois, ph, pw, sampling;
+  float* out_f32;
+  __nv_bfloat16* out_hi;
+  __nv_bfloat16* out_lo;
+  int out_hp, out_wp, out_border, out_coff, ld_out;
+};
+
+__device__ __forceinline__ int assign_level(float w, float h, int min_level, int num_levels) {
+  // d2 assign_boxes_to_levels: floor(4 + log2(sqrt(area)/224 + 1e-8)), clamped to the pooler's levels
+  const float size = sqrtf(w * h);
+  float lvl = floorf(4.f + log2f(size / 224.f + 1e-8f));
+  const float lo = (float)min_level, hi = (float)(min_level + num_levels - 1);
+  lvl = fminf(fmaxf(lvl, lo), hi);
+  return (int)lvl - min_level;
+}
+
+template <int NV>  // float4 vectors per lane: channels <= 128*NV
+__global__ void __launch_bounds__(256) roi_align_rotated_kernel(const RoiKernelParams p) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_rois = p.n_rois_dev ? min(*p.n_rois_dev, p.n_rois) : p.n_rois;
+  const int bins = p.ph * p.pw;
+  const int64_t total = (int64_t)n_rois * bins;
+  const int cvecs = p.channels >> 2;
+  for (int64_t wid = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); wid < total;
+       wid += (int64_t)gridDim.x * warps_per_block) {
+    const int roi_idx = (int)(wid / bins);
+    const int bin = (int)(wid - (int64_t)roi_idx * bins);
+    const int bph = bin / p.pw, bpw = bin - bph * p.pw;
+    const float* roi = p.rois + (int64_t)roi_idx * 6;
+    const int batch = (int)roi[0];
+    const float bx = roi[1], by = roi[2], bw = roi[3], bh = roi[4], ba = roi[5];
+    const int lvl = p.num_levels > 1 ? assign_level(bw, bh, p.min_level, p.num_levels) : 0;
+    const int H = p.feat_h[lvl], W = p.feat_w[lvl];
+    const float s = p.scale[lvl];
+    const int Hp = H + 2 * p.border, Wp = W + 2 * p.border;
+    const float* f = p.feat[lvl] + (int64_t)batch * Hp * Wp * p.ld;
+
+    const float cw = bx * s - 0.5f, chh = by * s - 0.5f;
+    const float rw = bw * s, rh = bh * s;
+    const float theta = (float)((double)ba * 3.14159265358979323846 / 180.0);
+    float sn, cs;
+    sincosf(theta, &sn, &cs);
+    const float bsh = rh / (float)p.ph, bsw = rw / (float)p.pw;
+    const int gh = p.sampling > 0 ? p.sampling : (int)ceilf(rh / (float)p.ph);
+    const int gw = p.sampling > 0 ? p.sampling : (int)ceilf(rw / (float)p.pw);
+    const float count = (float)max(gh * gw, 1);
+    const float sh0 = -rh / 2.0f, sw0 = -rw / 2.0f;
+
+    float4 acc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (int iy = 0; iy < gh; ++iy) {
+      const float yy = sh0 + bph * bsh + ((float)iy + .5f) * bsh / (float)gh;
+      for (int ix = 0; ix < gw; ++ix) {
+        const float xx = sw0 + bpw * bsw + ((float)ix + .5f) * bsw / (float)gw;
+        float y = yy * cs - xx * sn + chh;
+        float x = yy * sn + xx * cs + cw;
+        if (y < -1.0f || y > (float)H || x < -1.0f || x > (float)W) continue;
+        y = fmaxf(y, 0.f);
+        x = fmaxf(x, 0.f);
+        int yl = (int)y, xl = (int)x, yh, xh;
+        if (yl >= H - 1) { yh = yl = H - 1; y = (float)yl; } else { yh = yl + 1; }
+        if (xl >= W - 1) { xh = xl = W - 1; x = (float)xl; } else { xh = xl + 1; }
+        const float ly = y - (float)yl, lx = x - (float)xl;
+        const float hy = 1.f - ly, hx = 1.f - lx;
+        const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+        const float4* r1 = reinterpret_cast<const float4*>(f + ((int64_t)(yl + p.border) * Wp + xl + p.border) * p.ld);
+        const float4* r2 = reinterpret_cast<const float4*>(f + ((int64_t)(yl + p.border) * Wp + xh + p.border) * p.ld);
+        const float4* r3 = reinterpret_cast<const float4*>(f + ((int64_t)(yh + p.border) * Wp + xl + p.border) * p.ld);
+        const float4* r4 = reinterpret_cast<const float4*>(f + ((int64_t)(yh + p.border) * Wp + xh + p.border) * p.ld);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const int ci = lane + 32 * v;
+          if (ci < cvecs) {
+            const float4 a = __ldg(r1 + ci), b = __ldg(r2 + ci), c = __ldg(r3 + ci), d = __ldg(r4 + ci);
+            acc[v].x += w1 * a.x + w2 * b.x + w3 * c.x + w4 * d.x;
+            acc[v].y += w1 * a.y + w2 * b.y + w3 * c.y + w4 * d.y;
+            acc[v].z += w1 * a.z + w2 * b.z + w3 * c.z + w4 * d.z;
+            acc[v].w += w1 * a.w + w2 * b.w + w3 * c.w + w4 * d.w;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int ci = lane + 32 * v;
+      if (ci < cvecs) {
+        const float4 o = make_float4(acc[v].x / count, acc[v].y / count, acc[v].z / count, acc[v].w / count);
+        if (p.out_f32) {
+          reinterpret_cast<float4*>(p.out_f32 + ((int64_t)roi_idx * bins + bin) * p.channels)[ci] = o;
+        }
+        if (p.out_hi) {
+          const int64_t row = ((int64_t)roi_idx * p.out_hp + bph + p.out_border) * p.out_wp + bpw + p.out_border;
+          __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
+          split_bf16(o.x, h0, l0);
+          split_bf16(o.y, h1, l1);
+          split_bf16(o.z, h2, l2);
+          split_bf16(o.w, h3, l3);
+          const int64_t off = row * p.ld_out + p.out_coff + ci * 4;
+          *reinterpret_cast<uint2*>(p.out_hi + off) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+          *reinterpret_cast<uint2*>(p.out_lo + off) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ image pooler (3 channels, NCHW raw image)
+struct ImgRoiKernelParams {
+  const float* img;
+  int n, h, w, h_pad, w_pad;
+  float mean[3], inv_std[3];
+  const float* rois;
+  const int* n_rois_dev;
+  int n_rois, ph, pw, sampling;
+  float* out_f32;
+  __nv_bfloat16* out_hi;
+  __nv_bfloat16* out_lo;
+  int out_border, ld_out;
+};
+
+__global__ void __launch_bounds__(256) image_roi_align_rotated_kernel(const ImgRoiKernelParams p) {
+  const int n_rois = p.n_rois_dev ? min(*p.n_rois_dev, p.n_rois) : p.n_rois;
+  const int bins = p.ph * p.pw;
+  const int64_t total = (int64_t)n_rois * bins;
+  const int H = p.h_pad, W = p.w_pad;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int roi_idx = (int)(i / bins);
+    const int bin = (int)(i - (int64_t)roi_idx * bins);
+    const int bph = bin / p.pw, bpw = bin - bph * p.pw;
+    const float* roi = p.rois + (int64_t)roi_idx * 6;
+    const int batch = (int)roi[0];
+    const float cw = roi[1] - 0.5f, chh = roi[2] - 0.5f;
+    const float rw = roi[3], rh = roi[4];
+    const float theta = (float)((double)roi[5] * 3.14159265358979323846 / 180.0);
+    float sn, cs;
+    sincosf(theta, &sn, &cs);
+    const float bsh = rh / (float)p.ph, bsw = rw / (float)p.pw;
+    const int gh = p.sampling > 0 ? p.sampling : (int)ceilf(rh / (float)p.ph);
+    const int gw = p.sampling > 0 ? p.sampling : (int)ceilf(rw / (float)p.pw);
+    const float count = (float)max(gh * gw, 1);
+    const float sh0 = -rh / 2.0f, sw0 = -rw / 2.0f;
+    const float* f = p.img + (int64_t)batch * 3 * p.h * p.w;
+    const int64_t cstride = (int64_t)p.h * p.w;
+    float acc[3] = {0.f, 0.f, 0.f};
+    for (int iy = 0; iy < gh; ++iy) {
+      const float yy = sh0 + bph * bsh + ((float)iy + .5f) * bsh / (float)gh;
+      for (int ix = 0; ix < gw; ++ix) {
+        const float xx = sw0 + bpw * bsw + ((float)ix + .5f) * bsw / (float)gw;
+        float y = yy * cs - xx * sn + chh;
+        float x = yy * sn + xx * cs + cw;
+        if (y < -1.0f || y > (float)H || x < -1.0f || x > (float)W) continue;
+        y = fmaxf(y, 0.f);
+        x = fmaxf(x, 0.f);
+        int yl = (int)y, xl = (int)x, yh, xh;
+        if (yl >= H - 1) { yh = yl = H - 1; y = (float)yl; } else { yh = yl + 1; }
+        if (xl >= W - 1) { xh = xl = W - 1; x = (float)xl; } else { xh = xl + 1; }
+        const float ly = y - (float)yl, lx = x - (float)xl;
+        const float hy = 1.f - ly, hx = 1.f - lx;
+        const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+        const bool in1 = yl < p.h && xl < p.w, in2 = yl < p.h && xh < p.w;
+        const bool in3 = yh < p.h && xl < p.w, in4 = yh < p.h && xh < p.w;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float* fc = f + c * cstride;
+          const float a = in1 ? (__ldg(fc + (int64_t)yl * p.w + xl) - p.mean[c]) * p.inv_std[c] : 0.f;
+          const float b = in2 ? (__ldg(fc + (int64_t)yl * p.w + xh) - p.mean[c]) * p.inv_std[c] : 0.f;
+          const float cc = in3 ? (__ldg(fc + (int64_t)yh * p.w + xl) - p.mean[c]) * p.inv_std[c] : 0.f;
+          const float d = in4 ? (__ldg(fc + (int64_t)yh * p.w + xh) - p.mean[c]) * p.inv_std[c] : 0.f;
+          acc[c] += w1 * a + w2 * b + w3 * cc + w4 * d;
+        }
+      }
+    }
+    const float o0 = acc[0] / count, o1 = acc[1] / count, o2 = acc[2] / count;
+    if (p.out_f32) {
+      float* o = p.out_f32 + (int64_t)roi_idx * 3 * bins + bin;
+      o[0] = o0;
+      o[bins] = o1;
+      o[2 * bins] = o2;
+    }
+    if (p.out_hi) {
+      const int hp = p.ph + 2 * p.out_border, wp = p.pw + 2 * p.out_border;
+      const int64_t row = ((int64_t)roi_idx * hp + bph + p.out_border) * wp + bpw + p.out_border;
+      __nv_bfloat16 h0, l0, h1, l1, h2, l2;
+      split_bf16(o0, h0, l0);
+      split_bf16(o1, h1, l1);
+      split_bf16(o2, h2, l2);
+      const __nv_bfloat16 z = __float2bfloat16_rn(0.f);
+      *reinterpret_cast<uint4*>(p.out_hi + row * p.ld_out) = make_uint4(pack_bf16x2(h0, h1), pack_bf16x2(h2, z), 0, 0);
+      *reinterpret_cast<uint4*>(p.out_lo + row * p.ld_out) = make_uint4(pack_bf16x2(l0, l1), pack_bf16x2(l2, z), 0, 0);
+    }
+  }
+}
+
+}  // namespace glass
+
+using namespace glass;
+
+extern "C" int glass_roi_align_rotated(const GlassRoiAlignParams* p, void* stream_v) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  GLASS_CHECK(p != nullptr, "null params");
+  GLASS_CHECK(p->num_levels >= 1 && p->num_levels <= GLASS_MAX_LEVELS, "num_levels out of range");
+  GLASS_CHECK(p->channels > 0 && p->channels % 4 == 0 && p->channels <= 256, "channels must be a multiple of 4, <= 256");
+  GLASS_CHECK(p->feat_ld >= p->channels && p->feat_ld % 4 == 0, "feat_ld must be >= channels and a multiple of 4");
+  GLASS_CHECK(p->rois != nullptr && p->n_rois >= 0, "rois missing");
+  GLASS_CHECK(p->pooled_h > 0 && p->pooled_w > 0 && p->sampling_ratio >= 0, "bad pooled size");
+  GLASS_CHECK(p->out_f32 || (p->out_hi && p->out_lo), "no output requested");
+  if (p->out_hi) GLASS_CHECK(p->ld_out % 4 == 0 && p->out_coff % 4 == 0 && p->out_hp > 0 && p->out_wp > 0, "bad split-output geometry");
+  if (p->n_rois == 0) return 0;
+  RoiKernelParams k{};
+  k.num_levels = p->num_levels;
+  for (int l = 0; l < p->num_levels; ++l) {
+    GLASS_CHECK(p->feat[l] != nullptr && p->feat_h[l] > 0 && p->feat_w[l] > 0, "bad feature level");
+    GLASS_CHECK((reinterpret_cast<uintptr_t>(p->feat[l]) & 15) == 0, "feature maps must be 16-byte aligned");
+    k.feat[l] = p->feat[l];
+    k.feat_h[l] = p->feat_h[l];
+    k.feat_w[l] = p->feat_w[l];
+    k.scale[l] = p->spatial_scale[l];
+  }
+  k.border = p->feat_border; k.ld = p->feat_ld; k.channels = p->channels; k.min_level = p->min_level;
+  k.rois = p->rois; k.n_rois_dev = p->n_rois_dev; k.n_rois = p->n_rois;
+  k.ph = p->pooled_h; k.pw = p->pooled_w; k.sampling = p->sampling_ratio;
+  k.out_f32 = p->out_f32; k.out_hi = (__nv_bfloat16*)p->out_hi; k.out_lo = (__nv_bfloat16*)p->out_lo;
+  k.out_hp = p->out_hp; k.out_wp = p->out_wp; k.out_border = p->out_border; k.out_coff = p->out_coff;
+  k.ld_out = p->ld_out;
+  const int64_t warps = (int64_t)p->n_rois * p->pooled_h * p->pooled_w;
+  int64_t blocks = (warps + 7) / 8;
+  const int64_t cap = (int64_t)num_sms() * 8 * 4;  // 8 resident CTAs/SM x 4 waves, grid-stride beyond
+  if (blocks > cap) blocks = cap;
+  if (p->channels <= 128) {
+    roi_align_rotated_kernel<1><<<(int)blocks, 256, 0, stream>>>(k);
+  } else {
+    roi_align_rotated_kernel<2><<<(int)blocks, 256, 0, stream>>>(k);
+  }
+  count_launch();
+  GLASS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int glass_image_roi_align_rotated(const GlassImageRoiAlignParams* p, void* stream_v) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  GLASS_CHECK(p != nullptr, "null params");
+  GLASS_CHECK(p->img && p->rois, "null pointer");
+  GLASS_CHECK(p->n > 0 && p->h > 0 && p->w > 0 && p->h_pad >= p->h && p->w_pad >= p->w, "bad image shape");
+  GLASS_CHECK(p->pooled_h > 0 && p->pooled_w > 0 && p->sampling_ratio >= 0, "bad pooled size");
+  GLASS_CHECK(p->out_f32 || (p->out_hi && p->out_lo), "no output requested");
+  if (p->out_hi) GLASS_CHECK(p->ld_out >= 8 && p->ld_out % 8 == 0, "ld_out must be a multiple of 8");
+  if (p->n_rois == 0) return 0;
+  ImgRoiKernelParams k{};
+  k.img = p->img; k.n = p->n; k.h = p->h; k.w = p->w; k.h_pad = p->h_pad; k.w_pad = p->w_pad;
+  for (int c = 0; c < 3; ++c) { k.mean[c] = p->mean[c]; k.inv_std[c] = p->inv_std[c]; }
+  k.rois = p->rois; k.n_rois_dev = p->n_rois_dev; k.n_rois = p->n_rois;
+  k.ph = p->pooled_h; k.pw = p->pooled_w; k.sampling = p->sampling_ratio;
+  k.out_f32 = p->out_f32; k.out_hi = (__nv_bfloat16*)p->out_hi; k.out_lo = (__nv_bfloat16*)p->out_lo;
+  k.out_border = p->out_border; k.ld_out = p->ld_out;
+  const int64_t total = (int64_t)p->n_rois * p->pooled_h * p->pooled_w;
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = (int64_t)num_sms() * 32;
+  if (blocks > cap) blocks = cap;
+  image_roi_align_rotated_kernel<<<(int)blocks, 256, 0, stream>>>(k);
+  count_launch();
+  GLASS_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,95 @@
+"""ctypes binding of libglass_b200.so (C ABI: include/glass_b200.h)."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_lib", "libglass_b200.so")
+
+MAX_TAPS = 16
+MAX_LEVELS = 5
+
+# every symbol include/glass_b200.h declares (checked by tests/test_abi.py)
+SYMBOLS = [
+    "glass_last_error", "glass_abi_version", "glass_launch_count", "glass_conv_gemm", "glass_pack_nchw",
+    "glass_unpack_nchw", "glass_nhwc_f32_to_nchw", "glass_stem_im2col", "glass_gather_taps", "glass_maxpool",
+    "glass_roi_align_rotated", "glass_image_roi_align_rotated",
+]
+
+
+class ConvGemmParams(C.Structure):
+    _fields_ = [
+        ("a_hi", C.c_void_p), ("a_lo", C.c_void_p), ("rows_a", C.c_int64),
+        ("k_per_tap", C.c_int32), ("ntaps", C.c_int32), ("tap_shift", C.c_int32 * MAX_TAPS),
+        ("b_hi", C.c_void_p), ("b_lo", C.c_void_p), ("n", C.c_int32), ("mode", C.c_int32),
+        ("m_imgs", C.c_int32), ("m_h", C.c_int32), ("m_w", C.c_int32), ("m_border", C.c_int32),
+        ("scale", C.c_void_p), ("bias", C.c_void_p), ("relu_pre", C.c_int32), ("relu_post", C.c_int32),
+        ("res_hi", C.c_void_p), ("res_lo", C.c_void_p),
+        ("res_hp", C.c_int32), ("res_wp", C.c_int32), ("res_border", C.c_int32), ("res_shift", C.c_int32),
+        ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("out_f32", C.c_void_p),
+        ("out_hp", C.c_int32), ("out_wp", C.c_int32), ("out_border", C.c_int32),
+        ("ld_out", C.c_int32), ("ld_f32", C.c_int32), ("n_store", C.c_int32),
+    ]
+
+
+class RoiAlignParams(C.Structure):
+    _fields_ = [
+        ("num_levels", C.c_int32), ("feat", C.c_void_p * MAX_LEVELS),
+        ("feat_h", C.c_int32 * MAX_LEVELS), ("feat_w", C.c_int32 * MAX_LEVELS),
+        ("spatial_scale", C.c_float * MAX_LEVELS),
+        ("feat_border", C.c_int32), ("feat_ld", C.c_int32), ("channels", C.c_int32), ("min_level", C.c_int32),
+        ("rois", C.c_void_p), ("n_rois_dev", C.c_void_p), ("n_rois", C.c_int32),
+        ("pooled_h", C.c_int32), ("pooled_w", C.c_int32), ("sampling_ratio", C.c_int32),
+        ("out_f32", C.c_void_p), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p),
+        ("out_hp", C.c_int32), ("out_wp", C.c_int32), ("out_border", C.c_int32), ("out_coff", C.c_int32),
+        ("ld_out", C.c_int32),
+    ]
+
+
+class ImageRoiAlignParams(C.Structure):
+    _fields_ = [
+        ("img", C.c_void_p), ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+        ("h_pad", C.c_int32), ("w_pad", C.c_int32), ("mean", C.c_float * 3), ("inv_std", C.c_float * 3),
+        ("rois", C.c_void_p), ("n_rois_dev", C.c_void_p), ("n_rois", C.c_int32),
+        ("pooled_h", C.c_int32), ("pooled_w", C.c_int32), ("sampling_ratio", C.c_int32),
+        ("out_f32", C.c_void_p), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p),
+        ("out_border", C.c_int32), ("ld_out", C.c_int32),
+    ]
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the extension; fails loudly when it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m glass_text_spotting_b200.build` "
+            "(or __graft_entry__.build()); there is no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    lib.glass_last_error.restype = C.c_char_p
+    lib.glass_abi_version.restype = C.c_int
+    lib.glass_launch_count.restype = C.c_int64
+    i, p, f = C.c_int, C.c_void_p, C.POINTER(C.c_float)
+    lib.glass_conv_gemm.argtypes = [C.POINTER(ConvGemmParams), p]
+    lib.glass_pack_nchw.argtypes = [p, i, i, i, i, p, p, i, i, p]
+    lib.glass_unpack_nchw.argtypes = [p, p, i, i, i, i, i, i, p, p]
+    lib.glass_nhwc_f32_to_nchw.argtypes = [p, i, i, i, i, i, i, p, p]
+    lib.glass_stem_im2col.argtypes = [p, i, i, i, f, f, p, p, i, p]
+    lib.glass_gather_taps.argtypes = [p, p] + [i] * 13 + [p, p, p]
+    lib.glass_maxpool.argtypes = [p, p] + [i] * 13 + [p, p, i, p]
+    lib.glass_roi_align_rotated.argtypes = [C.POINTER(RoiAlignParams), p]
+    lib.glass_image_roi_align_rotated.argtypes = [C.POINTER(ImageRoiAlignParams), p]
+    for name in SYMBOLS:
+        fn = getattr(lib, name)
+        if name.startswith("glass_") and name not in ("glass_last_error", "glass_abi_version", "glass_launch_count"):
+            fn.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise RuntimeError("libglass_b200: " + load().glass_last_error().decode())

@@ -1,0 +1,266 @@
+"""Tensor-level wrappers over the C ABI (include/glass_b200.h).
+
+PyTorch is used only for device memory and streams: every function here takes/returns CUDA
+tensors, passes raw pointers to ``libglass_b200.so`` and enqueues on the current stream.
+There is no fallback: a missing extension or a non-CUDA tensor raises.
+"""
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import lib as _lib
+
+MODE_BF16X3 = 0   # fp32-grade split precision (parity mode; default)
+MODE_BF16 = 1     # single bf16 pass (fast mode)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("glass_text_spotting_b200 ops need CUDA tensors (no CPU fallback)")
+    return t.data_ptr()
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+class Act:
+    """An fp32 activation [n,c,h,w] stored as split-bf16 padded NHWC (see include/glass_b200.h).
+
+    ``buf`` is one bf16 tensor [2, n, h+2b, w+2b, cp]: plane 0 = hi, plane 1 = lo.  Borders and pad
+    channels are zero and are never written by any kernel.
+    """
+
+    def __init__(self, n: int, c: int, h: int, w: int, border: int = 1, cp: Optional[int] = None,
+                 device="cuda", buf: Optional[torch.Tensor] = None):
+        self.n, self.c, self.h, self.w, self.border = n, c, h, w, border
+        self.cp = cp if cp is not None else round_up(c, 64)
+        self.hp, self.wp = h + 2 * border, w + 2 * border
+        shape = (2, n, self.hp, self.wp, self.cp)
+        if buf is None:
+            buf = torch.zeros(shape, dtype=torch.bfloat16, device=device)
+        else:
+            assert tuple(buf.shape) == shape and buf.dtype == torch.bfloat16 and buf.is_contiguous()
+        self.buf = buf
+
+    @property
+    def hi(self) -> torch.Tensor:
+        return self.buf[0]
+
+    @property
+    def lo(self) -> torch.Tensor:
+        return self.buf[1]
+
+    @property
+    def rows(self) -> int:
+        return self.n * self.hp * self.wp
+
+    @staticmethod
+    def from_nchw(x: torch.Tensor, border: int = 1, cp: Optional[int] = None) -> "Act":
+        n, c, h, w = x.shape
+        a = Act(n, c, h, w, border, cp, x.device)
+        x = x.contiguous().float()
+        _lib.check(_lib.load().glass_pack_nchw(_ptr(x), n, c, h, w, _ptr(a.hi), _ptr(a.lo), a.cp, border, _stream()))
+        return a
+
+    def to_nchw(self) -> torch.Tensor:
+        out = torch.empty((self.n, self.c, self.h, self.w), dtype=torch.float32, device=self.buf.device)
+        _lib.check(_lib.load().glass_unpack_nchw(_ptr(self.hi), _ptr(self.lo), self.n, self.c, self.h, self.w,
+                                                 self.cp, self.border, _ptr(out), _stream()))
+        return out
+
+
+class F32Map:
+    """fp32 padded NHWC feature map [n, h+2b, w+2b, ld] (the conv kernel's fp32 output; RoIAlign input)."""
+
+    def __init__(self, n, c, h, w, border=1, ld=None, device="cuda"):
+        self.n, self.c, self.h, self.w, self.border = n, c, h, w, border
+        self.ld = ld if ld is not None else round_up(c, 64)
+        self.hp, self.wp = h + 2 * border, w + 2 * border
+        self.buf = torch.zeros((n, self.hp, self.wp, self.ld), dtype=torch.float32, device=device)
+
+    def to_nchw(self) -> torch.Tensor:
+        out = torch.empty((self.n, self.c, self.h, self.w), dtype=torch.float32, device=self.buf.device)
+        _lib.check(_lib.load().glass_nhwc_f32_to_nchw(_ptr(self.buf), self.n, self.c, self.h, self.w, self.ld,
+                                                      self.border, _ptr(out), _stream()))
+        return out
+
+
+class PackedWeight:
+    """Weights of one conv / Linear packed K-major [n_p, taps*cin_p] as bf16 hi/lo, plus the folded
+    per-channel epilogue (scale, bias).  Built by ``packing.pack_conv`` / ``pack_linear``."""
+
+    def __init__(self, w: torch.Tensor, scale: torch.Tensor, bias: torch.Tensor, cout: int, cin: int,
+                 kh: int, kw: int, stride: Tuple[int, int], pad: Tuple[int, int], cin_p: int):
+        self.w = w  # bf16 [2, n_p, taps*cin_p]
+        self.scale, self.bias = scale, bias
+        self.cout, self.cin, self.kh, self.kw = cout, cin, kh, kw
+        self.stride, self.pad, self.cin_p = stride, pad, cin_p
+        self.n_p = w.shape[1]
+
+
+def conv_gemm(a_hi: torch.Tensor, a_lo: Optional[torch.Tensor], rows_a: int, k_per_tap: int,
+              tap_shift: Sequence[int], w: PackedWeight, m_geom: Tuple[int, int, int, int],
+              out: Optional[Act] = None, out_f32: Optional[torch.Tensor] = None, ld_f32: int = 0,
+              out_geom: Optional[Tuple[int, int, int]] = None, ld_out: int = 0,
+              out_hi: Optional[torch.Tensor] = None, out_lo: Optional[torch.Tensor] = None,
+              residual: Optional[Act] = None, res_shift: int = 0, relu_pre: bool = False, relu_post: bool = False,
+              use_scale: bool = True, mode: int = MODE_BF16X3, n_store: int = 0) -> None:
+    """Raw launch of glass_conv_gemm.  m_geom = (imgs, h, w, border) of the M space;
+    out_geom = (hp, wp, border) of the output rows (defaults to ``out``'s geometry)."""
+    p = _lib.ConvGemmParams()
+    p.a_hi, p.a_lo, p.rows_a = _ptr(a_hi), _ptr(a_lo), rows_a
+    p.k_per_tap, p.ntaps = k_per_tap, len(tap_shift)
+    for i, s in enumerate(tap_shift):
+        p.tap_shift[i] = s
+    p.b_hi, p.b_lo, p.n, p.mode = _ptr(w.w[0]), _ptr(w.w[1]), w.n_p, mode
+    p.m_imgs, p.m_h, p.m_w, p.m_border = m_geom
+    p.scale = _ptr(w.scale) if use_scale else None
+    p.bias = _ptr(w.bias) if use_scale else None
+    p.relu_pre, p.relu_post = int(relu_pre), int(relu_post)
+    if out is not None:
+        out_hi, out_lo = out.hi, out.lo
+        out_geom = (out.hp, out.wp, out.border)
+        ld_out = out.cp
+    if residual is not None:
+        p.res_hi, p.res_lo = _ptr(residual.hi), _ptr(residual.lo)
+        p.res_hp, p.res_wp, p.res_border, p.res_shift = residual.hp, residual.wp, residual.border, res_shift
+        if ld_out == 0:
+            ld_out = residual.cp
+        assert residual.cp == ld_out, "residual and output must share the channel stride"
+    p.out_hi, p.out_lo, p.out_f32 = _ptr(out_hi), _ptr(out_lo), _ptr(out_f32)
+    p.out_hp, p.out_wp, p.out_border = out_geom
+    p.ld_out, p.ld_f32, p.n_store = ld_out, ld_f32, n_store
+    _lib.check(_lib.load().glass_conv_gemm(C.byref(p), _stream()))
+
+
+def conv2d(x: Act, w: PackedWeight, relu: bool = False, residual: Optional[Act] = None, res_shift: int = 0,
+           relu_pre: bool = False, out: Optional[Act] = None, f32: Optional[F32Map] = None, want_act: bool = True,
+           mode: int = MODE_BF16X3) -> Optional[Act]:
+    """conv (+ folded norm) (+ReLU) (+residual) on a split-bf16 activation.
+
+    stride-1 'same' convs run as shifted-row implicit GEMM straight from ``x``; everything else goes
+    through one tap-gather pass.  ``relu`` = ReLU after the residual add (d2 bottleneck order),
+    ``relu_pre`` = ReLU before it (CNN_V1_1 order)."""
+    assert x.cp == w.cin_p, (x.cp, w.cin_p)
+    sh, sw = w.stride
+    ph, pw = w.pad
+    ho = (x.h + 2 * ph - w.kh) // sh + 1
+    wo = (x.w + 2 * pw - w.kw) // sw + 1
+    if want_act and out is None:
+        out = Act(x.n, w.cout, ho, wo, 1, w.n_p, x.buf.device)
+    if out is not None:
+        assert (out.n, out.h, out.w, out.cp) == (x.n, ho, wo, w.n_p)
+    geom = (out.hp, out.wp, out.border) if out is not None else (f32.hp, f32.wp, f32.border)
+    kwargs = dict(out=out, out_f32=None if f32 is None else f32.buf, ld_f32=0 if f32 is None else f32.ld,
+                  out_geom=geom, residual=residual, res_shift=res_shift, relu_pre=relu_pre, relu_post=relu,
+                  mode=mode)
+    flat = (sh == 1 and sw == 1 and ho == x.h and wo == x.w and w.kh % 2 == 1 and w.kw % 2 == 1
+            and x.border >= ph and x.border >= pw)
+    if flat:
+        shifts = [(r - ph) * x.wp + (s - pw) for r in range(w.kh) for s in range(w.kw)]
+        conv_gemm(x.hi, x.lo, x.rows, x.cp, shifts, w, (x.n, x.hp, x.wp, x.border), **kwargs)
+    else:
+        taps = w.kh * w.kw
+        rows = x.n * ho * wo
+        g = torch.empty((2, rows, taps * x.cp), dtype=torch.bfloat16, device=x.buf.device)
+        _lib.check(_lib.load().glass_gather_taps(_ptr(x.hi), _ptr(x.lo), x.n, x.h, x.w, x.cp, x.border, w.kh, w.kw,
+                                                 sh, sw, ph, pw, ho, wo, _ptr(g[0]), _ptr(g[1]), _stream()))
+        # the gathered matrix is already tap-major: one "tap" of width taps*cp
+        conv_gemm(g[0], g[1], rows, taps * x.cp, [0], w, (x.n, ho, wo, 0), **kwargs)
+    return out
+
+
+def linear(a: torch.Tensor, w: PackedWeight, relu: bool = False, want_split: bool = True, want_f32: bool = False,
+           mode: int = MODE_BF16X3, use_scale: bool = True):
+    """y = a @ W^T (*scale + bias) for a split-bf16 matrix ``a`` [2, rows, k] (k == w.cin_p).
+    Returns (split [2, rows, n_p] or None, fp32 [rows, n_p] or None)."""
+    assert a.dim() == 3 and a.shape[0] == 2 and a.shape[2] == w.cin_p and a.is_contiguous()
+    rows = a.shape[1]
+    o = torch.empty((2, rows, w.n_p), dtype=torch.bfloat16, device=a.device) if want_split else None
+    of = torch.empty((rows, w.n_p), dtype=torch.float32, device=a.device) if want_f32 else None
+    conv_gemm(a[0], a[1], rows, w.cin_p, [0], w, (1, rows, 1, 0),
+              out_hi=None if o is None else o[0], out_lo=None if o is None else o[1], out_f32=of, ld_f32=w.n_p,
+              out_geom=(rows, 1, 0), ld_out=w.n_p, relu_post=relu, mode=mode, use_scale=use_scale)
+    return o, of
+
+
+def maxpool2d(x: Act, k: Tuple[int, int], s: Tuple[int, int], p: Tuple[int, int]) -> Act:
+    ho = (x.h + 2 * p[0] - k[0]) // s[0] + 1
+    wo = (x.w + 2 * p[1] - k[1]) // s[1] + 1
+    out = Act(x.n, x.c, ho, wo, 1, x.cp, x.buf.device)
+    _lib.check(_lib.load().glass_maxpool(_ptr(x.hi), _ptr(x.lo), x.n, x.h, x.w, x.cp, x.border, k[0], k[1], s[0],
+                                         s[1], p[0], p[1], ho, wo, _ptr(out.hi), _ptr(out.lo), out.border,
+                                         _stream()))
+    return out
+
+
+def stem_im2col(img: torch.Tensor, mean: Sequence[float], std: Sequence[float], kp: int = 192) -> torch.Tensor:
+    """raw fp32 NCHW [n,3,h,w] -> split rows [2, n*(h/2)*(w/2), kp] of the 7x7/s2/p3 stem conv."""
+    n, c, h, w = img.shape
+    assert c == 3 and img.dtype == torch.float32 and img.is_contiguous()
+    out = torch.empty((2, n * (h // 2) * (w // 2), kp), dtype=torch.bfloat16, device=img.device)
+    m = (C.c_float * 3)(*[float(v) for v in mean])
+    s = (C.c_float * 3)(*[1.0 / float(v) for v in std])
+    _lib.check(_lib.load().glass_stem_im2col(_ptr(img), n, h, w, m, s, _ptr(out[0]), _ptr(out[1]), kp, _stream()))
+    return out
+
+
+def roi_align_rotated(feats: List[F32Map], rois: torch.Tensor, output_size: Tuple[int, int],
+                      scales: Sequence[float], sampling_ratio: int, min_level: int = 2,
+                      out_f32: bool = True, out_split: Optional[Tuple[torch.Tensor, int, int, int, int, int]] = None,
+                      n_rois_dev: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+    """Multi-level rotated RoIAlign.  rois fp32 [R,6] (batch, cx, cy, w, h, angle).  Returns fp32
+    [R, ph, pw, C] (NHWC order) when out_f32; out_split = (buf[2,...], hp, wp, border, coff, ld)."""
+    assert rois.dtype == torch.float32 and rois.dim() == 2 and rois.shape[1] == 6 and rois.is_contiguous()
+    p = _lib.RoiAlignParams()
+    p.num_levels = len(feats)
+    for i, f in enumerate(feats):
+        p.feat[i], p.feat_h[i], p.feat_w[i], p.spatial_scale[i] = _ptr(f.buf), f.h, f.w, float(scales[i])
+    f0 = feats[0]
+    assert all(f.ld == f0.ld and f.border == f0.border and f.c == f0.c for f in feats)
+    p.feat_border, p.feat_ld, p.channels, p.min_level = f0.border, f0.ld, f0.c, min_level
+    p.rois, p.n_rois = _ptr(rois), rois.shape[0]
+    p.n_rois_dev = _ptr(n_rois_dev)
+    p.pooled_h, p.pooled_w, p.sampling_ratio = output_size[0], output_size[1], sampling_ratio
+    out = None
+    if out_f32:
+        out = torch.zeros((rois.shape[0], output_size[0], output_size[1], f0.c), dtype=torch.float32,
+                          device=rois.device)
+        p.out_f32 = _ptr(out)
+    if out_split is not None:
+        buf, hp, wp, border, coff, ld = out_split
+        p.out_hi, p.out_lo = _ptr(buf[0]), _ptr(buf[1])
+        p.out_hp, p.out_wp, p.out_border, p.out_coff, p.ld_out = hp, wp, border, coff, ld
+    _lib.check(_lib.load().glass_roi_align_rotated(C.byref(p), _stream()))
+    return out
+
+
+def image_roi_align_rotated(img: torch.Tensor, pad_hw: Tuple[int, int], mean, std, rois: torch.Tensor,
+                            output_size: Tuple[int, int], sampling_ratio: int, out_f32: bool = False,
+                            out_act: Optional[Act] = None, n_rois_dev: Optional[torch.Tensor] = None):
+    n, c, h, w = img.shape
+    assert c == 3 and img.dtype == torch.float32 and img.is_contiguous()
+    p = _lib.ImageRoiAlignParams()
+    p.img, p.n, p.h, p.w, p.h_pad, p.w_pad = _ptr(img), n, h, w, pad_hw[0], pad_hw[1]
+    for i in range(3):
+        p.mean[i] = float(mean[i])
+        p.inv_std[i] = 1.0 / float(std[i])
+    p.rois, p.n_rois, p.n_rois_dev = _ptr(rois), rois.shape[0], _ptr(n_rois_dev)
+    p.pooled_h, p.pooled_w, p.sampling_ratio = output_size[0], output_size[1], sampling_ratio
+    out = None
+    if out_f32:
+        out = torch.zeros((rois.shape[0], 3, output_size[0], output_size[1]), dtype=torch.float32, device=img.device)
+        p.out_f32 = _ptr(out)
+    if out_act is not None:
+        assert (out_act.h, out_act.w) == tuple(output_size) and out_act.n >= rois.shape[0]
+        p.out_hi, p.out_lo, p.out_border, p.ld_out = _ptr(out_act.hi), _ptr(out_act.lo), out_act.border, out_act.cp
+    _lib.check(_lib.load().glass_image_roi_align_rotated(C.byref(p), _stream()))
+    return out

@@ -1,0 +1,68 @@
+"""Weight pre-packing: detectron2-style ``state_dict`` tensors -> the K-major split-bf16 layout the
+tcgen05 GEMM consumes (SURVEY.md A.10 lists the key names).  Done once at load time."""
+from typing import Optional, Tuple
+
+import torch
+
+from .ops import PackedWeight, round_up
+
+
+def split_bf16(x: torch.Tensor) -> torch.Tensor:
+    """fp32 tensor -> bf16 [2, ...] (hi, lo) with x ~= hi + lo."""
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    return torch.stack((hi, lo), 0).contiguous()
+
+
+def fold_bn(bn_w, bn_b, bn_mean, bn_var, eps: float = 1e-5, conv_bias: Optional[torch.Tensor] = None):
+    """eval-mode BatchNorm after a conv -> per-channel (scale, bias) applied in the GEMM epilogue."""
+    scale = bn_w.double() / torch.sqrt(bn_var.double() + eps)
+    bias = bn_b.double() - bn_mean.double() * scale
+    if conv_bias is not None:
+        bias = bias + conv_bias.double() * scale
+    return scale.float(), bias.float()
+
+
+def pack_conv(weight: torch.Tensor, scale: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+              stride: Tuple[int, int] = (1, 1), pad: Tuple[int, int] = (0, 0), cin_p: Optional[int] = None,
+              n_align: int = 64, device="cuda") -> PackedWeight:
+    """weight fp32 [cout, cin, kh, kw] -> [2, n_p, kh*kw*cin_p] bf16 (K = tap-major, channel-minor)."""
+    cout, cin, kh, kw = weight.shape
+    cin_p = cin_p if cin_p is not None else round_up(cin, 64)
+    n_p = round_up(cout, n_align)
+    w = torch.zeros((n_p, kh * kw, cin_p), dtype=torch.float32)
+    w[:cout, :, :cin] = weight.detach().float().permute(0, 2, 3, 1).reshape(cout, kh * kw, cin)
+    s = torch.ones(n_p, dtype=torch.float32)
+    b = torch.zeros(n_p, dtype=torch.float32)
+    if scale is not None:
+        s[:cout] = scale.detach().float()
+    if bias is not None:
+        b[:cout] = bias.detach().float()
+    return PackedWeight(split_bf16(w.reshape(n_p, kh * kw * cin_p)).to(device), s.to(device), b.to(device), cout, cin,
+                        kh, kw, tuple(stride), tuple(pad), cin_p)
+
+
+def pack_linear(weight: torch.Tensor, bias: Optional[torch.Tensor] = None, k_p: Optional[int] = None,
+                n_align: int = 64, device="cuda") -> PackedWeight:
+    """nn.Linear weight [out, in] -> packed as a 1x1 'conv' over rows."""
+    out_f, in_f = weight.shape
+    k_p = k_p if k_p is not None else round_up(in_f, 64)
+    w = torch.zeros((round_up(out_f, n_align), k_p), dtype=torch.float32)
+    w[:out_f, :in_f] = weight.detach().float()
+    s = torch.ones(w.shape[0], dtype=torch.float32)
+    b = torch.zeros(w.shape[0], dtype=torch.float32)
+    if bias is not None:
+        b[:out_f] = bias.detach().float()
+    return PackedWeight(split_bf16(w).to(device), s.to(device), b.to(device), out_f, in_f, 1, 1, (1, 1), (0, 0), k_p)
+
+
+def pack_stem(weight: torch.Tensor, scale, bias, kp: int = 192, device="cuda") -> PackedWeight:
+    """BasicStem conv1 [64,3,7,7] -> K = (r*7+s)*3 + c (matches glass_stem_im2col), zero padded to kp."""
+    cout = weight.shape[0]
+    w = torch.zeros((round_up(cout, 64), kp), dtype=torch.float32)
+    w[:cout, :147] = weight.detach().float().permute(0, 2, 3, 1).reshape(cout, 147)
+    s = torch.ones(w.shape[0])
+    b = torch.zeros(w.shape[0])
+    s[:cout] = scale
+    b[:cout] = bias
+    return PackedWeight(split_bf16(w).to(device), s.to(device), b.to(device), cout, 3, 7, 7, (2, 2), (3, 3), kp)

@@ -1,0 +1,167 @@
+/*
+ * glass_b200.h -- C ABI of libglass_b200.so: the B200 (sm_100a) kernels behind GLASS's
+ * per-image dense forward path.
+ *
+ * The reference (amazon-science/glass-text-spotting) contains no native code and no FFI:
+ * every native operator on its hot path lives in detectron2 v0.6's `_C` extension or in
+ * PyTorch/cuDNN/cuBLAS and is reached through Python.  Each entry point below therefore
+ * cites the reference *call site* (file:line under /root/reference) whose arithmetic it
+ * replaces; INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain pointers + sizes only; all pointers are DEVICE pointers unless named host_*.
+ *   - every op enqueues on `stream` (a cudaStream_t passed as void*), never synchronises,
+ *     never allocates device memory; the caller owns every buffer incl. workspaces.
+ *   - return 0 on success, negative on error; glass_last_error() gives the message
+ *     (thread-local).  Shapes/alignments are validated on the host before launch.
+ *
+ * Activation storage ("split-bf16 padded NHWC"): an fp32 tensor [N,C,H,W] is held as two
+ * bf16 planes hi, lo (x ~= hi + lo, 16 mantissa bits) each laid out [N, H+2b, W+2b, Cp]
+ * (b = border of zero pixels, Cp = C rounded up to 64, pad channels zero).  The zero
+ * border is the conv padding; kernels never write it.
+ */
+#ifndef GLASS_B200_H_
+#define GLASS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GLASS_MAX_TAPS 16
+#define GLASS_MAX_LEVELS 5
+
+const char* glass_last_error(void);
+int glass_abi_version(void);
+/* number of kernels launched by this library in this process so far (bench "gpu_launches") */
+int64_t glass_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * glass_conv_gemm -- the tcgen05 implicit-GEMM used by every conv / Linear on the path.
+ *   D[m, n] = sum_t sum_k A[m + tap_shift[t], k] * W[n, t*k_per_tap + k]
+ *   y = D*scale[n] + bias[n];  (relu_pre) y = max(y,0);  y += residual;  (relu_post) y = max(y,0)
+ * replaces: torch.nn.Conv2d / detectron2 Conv2d(+norm+act) / nn.Linear as used by
+ *   d2 ResNet+FPN (configs/glass_pretrain.yaml:41-54), StandardRPNHead (rotated_rpn.py:17),
+ *   FastRCNNConvFCHead (recognizers_hybrid_head.py:321), P2P3Fusion (fusion_modules.py:281-286),
+ *   ResNetFeatureExtractor (local_feature_extraction.py:154-188), MultiAspectGCAttention.out
+ *   (fusion_modules.py:157), CNN_V1_1 (recognizer_backbone.py:77-81), BiLSTM input projections
+ *   (recognizer_encoder.py:141-143), AttentionUnit.xEmbed (prediction_aster.py:250).
+ * A rows are pixels of a padded NHWC tensor flattened over (img, y, x); a conv tap is a constant
+ * row shift.  mode: 0 = bf16x3 split (hi*hi + hi*lo + lo*hi, fp32 accumulate in TMEM; fp32-grade),
+ * 1 = single bf16 pass (fast, lower precision).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  /* A operand */
+  const void* a_hi;  /* bf16 [rows_a, k_per_tap] */
+  const void* a_lo;  /* bf16, same shape (unused when mode == 1) */
+  int64_t rows_a;
+  int32_t k_per_tap; /* multiple of 64 */
+  int32_t ntaps;     /* 1..GLASS_MAX_TAPS */
+  int32_t tap_shift[GLASS_MAX_TAPS];
+  /* B operand: packed weights [n, ntaps*k_per_tap], bf16 hi/lo */
+  const void* b_hi;
+  const void* b_lo;
+  int32_t n;         /* multiple of 16; if > 256 a multiple of 128 */
+  int32_t mode;
+  /* M space: rows m in [0, m_imgs*m_h*m_w) decode to (img, yy, xx); rows whose yy/xx fall in the
+   * m_border ring are computed but not stored */
+  int32_t m_imgs, m_h, m_w, m_border;
+  /* epilogue */
+  const float* scale; /* [n] or NULL (=1) */
+  const float* bias;  /* [n] or NULL (=0) */
+  int32_t relu_pre, relu_post;
+  /* residual (optional): split bf16 planes [m_imgs, res_hp, res_wp, n]; pixel (y>>res_shift, x>>res_shift) */
+  const void* res_hi;
+  const void* res_lo;
+  int32_t res_hp, res_wp, res_border, res_shift;
+  /* outputs (any subset): split bf16 planes and/or fp32, rows laid out [m_imgs, out_hp, out_wp, ld] */
+  void* out_hi;
+  void* out_lo;
+  float* out_f32;
+  int32_t out_hp, out_wp, out_border;
+  int32_t ld_out;     /* channel stride of out_hi/out_lo/res rows (>= n) */
+  int32_t ld_f32;     /* channel stride of out_f32 rows (>= n) */
+  int32_t n_store;    /* columns actually stored (<= n); 0 = n */
+} GlassConvGemmParams;
+int glass_conv_gemm(const GlassConvGemmParams* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Layout / glue kernels
+ * ------------------------------------------------------------------------------------------ */
+/* fp32 NCHW [n,c,h,w] -> split-bf16 padded NHWC [n,h+2b,w+2b,cp] (interior only; border/pad channels must be 0) */
+int glass_pack_nchw(const float* src, int n, int c, int h, int w, void* dst_hi, void* dst_lo, int cp, int border,
+                    void* stream);
+/* split-bf16 padded NHWC -> fp32 NCHW (hi + lo) */
+int glass_unpack_nchw(const void* src_hi, const void* src_lo, int n, int c, int h, int w, int cp, int border,
+                      float* dst, void* stream);
+/* fp32 padded NHWC [n,h+2b,w+2b,ld] -> fp32 NCHW [n,c,h,w] */
+int glass_nhwc_f32_to_nchw(const float* src, int n, int c, int h, int w, int ld, int border, float* dst,
+                           void* stream);
+
+/* Stem im2col with fused (x - mean)/std (d2 GeneralizedRCNN.preprocess_image, called at
+ * glass_rcnn.py:82; BasicStem conv 7x7 s2 p3): raw fp32 NCHW image [n,3,h,w] ->
+ * split-bf16 rows [n*(h/2)*(w/2), kp] with k = (r*7+s)*3 + c, zero for k >= 147. */
+int glass_stem_im2col(const float* img, int n, int h, int w, const float* mean, const float* inv_std,
+                      void* dst_hi, void* dst_lo, int kp, void* stream);
+
+/* Generic tap gather (im2col) for strided / odd-shaped convs:
+ * src split padded NHWC [n,h+2b,w+2b,cp] -> rows [n*ho*wo, kh*kw*cp], tap-major K. */
+int glass_gather_taps(const void* src_hi, const void* src_lo, int n, int h, int w, int cp, int border, int kh,
+                      int kw, int sh, int sw, int ph, int pw, int ho, int wo, void* dst_hi, void* dst_lo,
+                      void* stream);
+
+/* max_pool2d on split-bf16 padded NHWC (F.max_pool2d: BasicStem, local_feature_extraction.py:163-178). */
+int glass_maxpool(const void* src_hi, const void* src_lo, int n, int h, int w, int cp, int border, int kh, int kw,
+                  int sh, int sw, int ph, int pw, int ho, int wo, void* dst_hi, void* dst_lo, int dst_border,
+                  void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * glass_roi_align_rotated -- multi-level rotated RoIAlign (detectron2 ROIPooler + ROIAlignRotated).
+ * replaces: torch.ops.detectron2.roi_align_rotated_forward as called through ROIPooler at
+ *   recognizers_hybrid_head.py:320 (box pooler 7x7, 5 levels, sampling 2), :550 (recognizer pooler
+ *   8x32, 1 level, adaptive sampling) and :556 (image pooler 128x128, scale 1, sampling 2).
+ * Feature maps are fp32 padded NHWC [n, h+2b, w+2b, ld] (the conv kernel's out_f32).
+ * rois: fp32 [n_rois, 6] = (batch_idx, cx, cy, w, h, angle_deg).  With num_levels > 1 the level of
+ * each RoI follows d2's assign_boxes_to_levels (canonical size 224 at level 4).
+ * Outputs (any subset): out_f32 [n_rois, ph, pw, c] (NHWC order) and split bf16 rows written at
+ *   row ((roi*out_hp + y + out_border)*out_wp + x + out_border), channel offset out_coff, stride ld_out.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t num_levels;
+  const float* feat[GLASS_MAX_LEVELS];
+  int32_t feat_h[GLASS_MAX_LEVELS], feat_w[GLASS_MAX_LEVELS];
+  float spatial_scale[GLASS_MAX_LEVELS];
+  int32_t feat_border, feat_ld, channels;
+  int32_t min_level; /* level index of feat[0] (2 for p2) */
+  const float* rois;
+  const int32_t* n_rois_dev; /* optional device count (<= n_rois); NULL = n_rois */
+  int32_t n_rois;
+  int32_t pooled_h, pooled_w, sampling_ratio;
+  float* out_f32;
+  void* out_hi;
+  void* out_lo;
+  int32_t out_hp, out_wp, out_border, out_coff, ld_out;
+} GlassRoiAlignParams;
+int glass_roi_align_rotated(const GlassRoiAlignParams* p, void* stream);
+
+/* Image pooler variant (recognizers_hybrid_head.py:556): raw fp32 NCHW image [n,3,h,w], normalised on
+ * the fly with (x-mean)*inv_std, padded to (hp_img, wp_img) with zeros (ImageList.from_tensors). */
+typedef struct {
+  const float* img;
+  int32_t n, h, w, h_pad, w_pad;
+  float mean[3], inv_std[3];
+  const float* rois;
+  const int32_t* n_rois_dev;
+  int32_t n_rois, pooled_h, pooled_w, sampling_ratio;
+  float* out_f32; /* optional [n_rois, 3, ph, pw] NCHW */
+  void* out_hi;   /* optional split bf16 [n_rois, ph+2b, pw+2b, ld_out], channels 0..2 */
+  void* out_lo;
+  int32_t out_border, ld_out;
+} GlassImageRoiAlignParams;
+int glass_image_roi_align_rotated(const GlassImageRoiAlignParams* p, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLASS_B200_H_ */

@@ -1,0 +1,220 @@
+"""GPU parity tests of the individual kernels, called through the C ABI (ctypes) and compared with
+the CPU oracle (oracle/d2_ops.c for the detectron2 operators; torch fp32 CPU conv/linear -- which is
+what the oracle's nets are made of -- for the tcgen05 GEMM).  Tolerance for floating point is the
+north-star's rtol=1e-3 / atol=1e-4 (relative to the tensor's scale)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-3, 1e-4
+
+
+def _close(got: torch.Tensor, ref: torch.Tensor, name=""):
+    got, ref = got.detach().cpu().float(), ref.detach().cpu().float()
+    assert got.shape == ref.shape, (name, got.shape, ref.shape)
+    scale = max(ref.abs().max().item(), 1e-6)
+    err = (got - ref).abs()
+    tol = ATOL * max(scale, 1.0) + RTOL * ref.abs()
+    bad = (err > tol).sum().item()
+    assert bad == 0, f"{name}: {bad}/{err.numel()} out of tolerance, max err {err.max().item():.3e}, scale {scale:.3e}"
+
+
+@pytest.fixture(scope="module")
+def ops(glass_lib):
+    from glass_text_spotting_b200 import ops
+    return ops
+
+
+def test_pack_unpack_roundtrip(ops):
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 70, 9, 13, generator=g) * 3
+    a = ops.Act.from_nchw(x.cuda())
+    assert a.cp == 128
+    y = a.to_nchw().cpu()
+    assert (y - x).abs().max().item() <= 2 ** -16 * x.abs().max().item()
+    # borders and pad channels stay zero
+    assert a.buf[:, :, 0].abs().max().item() == 0 and a.buf[..., 70:].abs().max().item() == 0
+
+
+def test_maxpool_matches_torch(ops):
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 64, 16, 32, generator=g)
+    a = ops.Act.from_nchw(x.cuda())
+    xs = a.to_nchw().cpu()  # the split representation is the kernel's input
+    for k, s, p in [((3, 3), (2, 2), (1, 1)), ((2, 2), (2, 2), (0, 0)), ((2, 2), (2, 1), (0, 1))]:
+        got = ops.maxpool2d(a, k, s, p).to_nchw().cpu()
+        ref = F.max_pool2d(xs, k, s, p)
+        assert torch.equal(got, ref), (k, s, p)
+
+
+def test_stem_im2col(ops):
+    from glass_text_spotting_b200 import packing
+    g = torch.Generator().manual_seed(2)
+    img = torch.randint(0, 256, (2, 3, 64, 96), generator=g).float()
+    mean, std = (103.53, 116.28, 123.675), (1.0, 1.0, 1.0)
+    w = torch.randn(64, 3, 7, 7, generator=g) * 0.05
+    cols = ops.stem_im2col(img.cuda(), mean, std)
+    pw = packing.pack_stem(w, torch.ones(64), torch.zeros(64))
+    out = ops.Act(2, 64, 32, 48)
+    ops.conv_gemm(cols[0], cols[1], cols.shape[1], 192, [0], pw, (2, 32, 48, 0), out=out)
+    ref = F.conv2d(img - torch.tensor(mean).view(1, 3, 1, 1), w, stride=2, padding=3)
+    _close(out.to_nchw(), ref, "stem")
+
+
+CONV_CASES = [
+    # name, n, cin, cout, h, w, k, stride, pad, relu, residual
+    ("1x1_64_256", 2, 64, 256, 24, 40, 1, 1, 0, False, False),
+    ("3x3_64_64_relu", 2, 64, 64, 24, 40, 3, 1, 1, True, False),
+    ("3x3_128_128_res_relu", 1, 128, 128, 33, 16, 3, 1, 1, True, True),
+    ("1x1_256_512_s2", 2, 256, 512, 32, 32, 1, 2, 0, False, False),
+    ("3x3_256_256_big", 3, 256, 256, 64, 64, 3, 1, 1, True, True),
+    ("1x1_512_2048", 1, 512, 2048, 16, 16, 1, 1, 0, True, False),
+    ("3x3_16_32_padded_channels", 2, 16, 32, 20, 20, 3, 1, 1, True, False),
+    ("2x2_s21_256", 2, 256, 256, 16, 33, 2, (2, 1), 0, True, False),
+    ("2x1_s21_256", 2, 256, 256, 8, 32, (2, 1), (2, 1), 0, True, False),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv_gemm_matches_torch_fp32(ops, case):
+    from glass_text_spotting_b200 import packing
+    name, n, cin, cout, h, w, k, stride, pad, relu, use_res = case
+    k = (k, k) if isinstance(k, int) else k
+    stride = (stride, stride) if isinstance(stride, int) else stride
+    pad = (pad, pad) if isinstance(pad, int) else pad
+    g = torch.Generator().manual_seed(sum(map(ord, name)))
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, *k, generator=g) / math.sqrt(cin * k[0] * k[1])
+    scale = 1.0 + 0.1 * torch.randn(cout, generator=g)
+    bias = 0.1 * torch.randn(cout, generator=g)
+    a = ops.Act.from_nchw(x.cuda())
+    pw = packing.pack_conv(wt, scale, bias, stride, pad)
+    ref = F.conv2d(x, wt, stride=stride, padding=pad) * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)
+    res_act = None
+    if use_res:
+        r = torch.randn(ref.shape, generator=g)
+        res_act = ops.Act.from_nchw(r.cuda())
+        ref = ref + r
+    if relu:
+        ref = F.relu(ref)
+    f32 = ops.F32Map(n, cout, ref.shape[2], ref.shape[3], ld=pw.n_p)
+    out = ops.conv2d(a, pw, relu=relu, residual=res_act, f32=f32)
+    _close(out.to_nchw(), ref, name + "/split")
+    _close(f32.to_nchw(), ref, name + "/f32")
+    # zero border is never written
+    assert out.buf[:, :, 0].abs().max().item() == 0 and out.buf[:, :, :, 0].abs().max().item() == 0
+    assert f32.buf[:, 0].abs().max().item() == 0
+
+
+def test_conv_gemm_fast_mode_is_bf16_grade(ops):
+    from glass_text_spotting_b200 import packing
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(1, 128, 16, 16, generator=g)
+    wt = torch.randn(128, 128, 3, 3, generator=g) / math.sqrt(128 * 9)
+    a = ops.Act.from_nchw(x.cuda())
+    pw = packing.pack_conv(wt, None, None, (1, 1), (1, 1))
+    out = ops.conv2d(a, pw, mode=ops.MODE_BF16).to_nchw().cpu()
+    ref = F.conv2d(x, wt, padding=1)
+    rel = (out - ref).norm() / ref.norm()
+    assert 1e-5 < rel < 2e-2, rel
+
+
+def test_fpn_upsample_residual(ops):
+    """lateral 1x1 conv + nearest-2x upsampled coarser map, fused in the epilogue (d2 FPN top-down)."""
+    from glass_text_spotting_b200 import packing
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(2, 128, 16, 24, generator=g)
+    top = torch.randn(2, 64, 8, 12, generator=g)
+    wt = torch.randn(64, 128, 1, 1, generator=g) / math.sqrt(128)
+    a, t = ops.Act.from_nchw(x.cuda()), ops.Act.from_nchw(top.cuda())
+    pw = packing.pack_conv(wt)
+    out = ops.conv2d(a, pw, residual=t, res_shift=1)
+    ref = F.conv2d(x, wt) + F.interpolate(top, scale_factor=2.0, mode="nearest")
+    _close(out.to_nchw(), ref, "fpn_topdown")
+
+
+def test_linear_gemm(ops):
+    from glass_text_spotting_b200 import packing
+    g = torch.Generator().manual_seed(7)
+    a = torch.randn(100, 12544, generator=g)
+    w = torch.randn(2048, 12544, generator=g) / math.sqrt(12544)
+    b = torch.randn(2048, generator=g) * 0.1
+    pw = packing.pack_linear(w, b)
+    o, of = ops.linear(packing.split_bf16(a).cuda(), pw, relu=True, want_f32=True)
+    ref = F.relu(a @ w.t() + b)
+    _close(of, ref, "fc1/f32")
+    _close(o[0].float() + o[1].float(), ref, "fc1/split")
+
+
+# ------------------------------------------------------------------------------ rotated RoIAlign
+def _random_rois(g, n, img=1024.0, batch=1):
+    cx = torch.rand(n, generator=g) * img
+    cy = torch.rand(n, generator=g) * img
+    w = torch.exp(torch.rand(n, generator=g) * (math.log(512) - math.log(16)) + math.log(16))
+    h = w * (0.1 + 0.9 * torch.rand(n, generator=g))
+    a = torch.rand(n, generator=g) * 360 - 180
+    b = torch.randint(0, batch, (n,), generator=g).float()
+    return torch.stack((b, cx, cy, w, h, a), 1).contiguous()
+
+
+def _f32map_from_nchw(ops, x):
+    n, c, h, w = x.shape
+    f = ops.F32Map(n, c, h, w, border=1, ld=c)
+    f.buf[:, 1:-1, 1:-1, :] = x.permute(0, 2, 3, 1).cuda()
+    return f
+
+
+def test_roi_align_rotated_d2_kat(ops):
+    """detectron2 tests/layers/test_roi_align_rotated.py::test_forward_output_0_90_180_270."""
+    x = torch.arange(25, dtype=torch.float32).reshape(1, 1, 5, 5).repeat(1, 4, 1, 1)
+    f = _f32map_from_nchw(ops, x)
+    base = torch.tensor([[4.5, 5.0, 5.5, 6.0], [7.0, 7.5, 8.0, 8.5], [9.5, 10.0, 10.5, 11.0], [12.0, 12.5, 13.0, 13.5]])
+    for i in range(4):
+        rois = torch.tensor([[0, 2, 2, 2, 2, 90.0 * i]], dtype=torch.float32).cuda()
+        out = ops.roi_align_rotated([f], rois, (4, 4), [1.0], 0).cpu()  # [1,4,4,C]
+        want = torch.rot90(base, -i)
+        for c in range(4):
+            assert torch.allclose(out[0, :, :, c], want, atol=1e-5), (i, c)
+
+
+@pytest.mark.parametrize("cfg", ["box_pooler", "recog_pooler"])
+def test_roi_align_rotated_matches_oracle(ops, cfg):
+    from oracle import d2_ops
+    g = torch.Generator().manual_seed(11)
+    if cfg == "box_pooler":
+        sizes, scales, out_size, sampling, n = [64, 32, 16, 8, 4], [1 / 4, 1 / 8, 1 / 16, 1 / 32, 1 / 64], (7, 7), 2, 96
+        feats = [torch.randn(2, 256, s, s, generator=g) for s in sizes]
+        rois = _random_rois(g, n, img=256.0, batch=2)
+        rois[:, 3:5] *= 0.6
+    else:
+        scales, out_size, sampling, n = [1 / 4], (8, 32), 0, 24
+        feats = [torch.randn(1, 256, 64, 64, generator=g)]
+        rois = _random_rois(g, n, img=256.0, batch=1)
+        rois[:, 3:5] *= 0.5
+    ref = d2_ops.roi_pooler(feats, [rois[rois[:, 0] == b][:, 1:] for b in range(feats[0].shape[0])], out_size,
+                            scales, sampling)
+    order = torch.cat([torch.nonzero(rois[:, 0] == b).squeeze(1) for b in range(feats[0].shape[0])])
+    maps = [_f32map_from_nchw(ops, f) for f in feats]
+    got = ops.roi_align_rotated(maps, rois[order].contiguous().cuda(), out_size, scales, sampling)
+    _close(got.permute(0, 3, 1, 2), ref, cfg)
+
+
+def test_image_roi_align_matches_oracle(ops):
+    from oracle import d2_ops
+    g = torch.Generator().manual_seed(12)
+    img = torch.randint(0, 256, (1, 3, 200, 232), generator=g).float()
+    mean, std = (103.53, 116.28, 123.675), (1.0, 1.0, 1.0)
+    norm = torch.zeros(1, 3, 224, 256)
+    norm[:, :, :200, :232] = img - torch.tensor(mean).view(1, 3, 1, 1)
+    rois = _random_rois(g, 6, img=220.0)
+    rois[:, 3:5] *= 0.3
+    ref = d2_ops.roi_pooler([norm], [rois[:, 1:]], (128, 128), [1.0], 2)
+    act = ops.Act(6, 3, 128, 128)
+    got = ops.image_roi_align_rotated(img.cuda(), (224, 256), mean, std, rois.cuda(), (128, 128), 2, out_f32=True,
+                                      out_act=act)
+    _close(got, ref, "image_pooler/f32")
+    _close(act.to_nchw(), ref, "image_pooler/split")
