@@ -14,7 +14,8 @@ namespace glass {
 
 struct RoiKernelParams {
   int num_levels;
-  const float* feat[GLASS_MAX_LEVELS];
+  const void* feat[GLASS_MAX_LEVELS];
+  const void* feat_lo[GLASS_MAX_LEVELS];
   int feat_h[GLASS_MAX_LEVELS], feat_w[GLASS_MAX_LEVELS];
   float scale[GLASS_MAX_LEVELS];
   int border, ld, channels, min_level;
@@ -36,7 +37,19 @@ __device__ __forceinline__ int assign_level(float w, float h, int min_level, int
   return (int)lvl - min_level;
 }
 
-template <int NV>  // float4 vectors per lane: channels <= 128*NV
+// 4 channels of one pixel: fp32 map -> one 16 B load; split-bf16 map -> two 8 B loads (hi + lo).
+template <bool SPLIT_IN>
+__device__ __forceinline__ float4 load4(const void* base, const void* base_lo, int64_t pix_off, int ci) {
+  if (SPLIT_IN) {
+    const uint2 h = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(base) + pix_off) + ci);
+    const uint2 l = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(base_lo) + pix_off) + ci);
+    return make_float4(bf16_lo_of(h.x) + bf16_lo_of(l.x), bf16_hi_of(h.x) + bf16_hi_of(l.x),
+                       bf16_lo_of(h.y) + bf16_lo_of(l.y), bf16_hi_of(h.y) + bf16_hi_of(l.y));
+  }
+  return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + pix_off) + ci);
+}
+
+template <int NV, bool SPLIT_IN>  // float4 vectors per lane: channels <= 128*NV
 __global__ void __launch_bounds__(256) roi_align_rotated_kernel(const RoiKernelParams p) {
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -56,7 +69,9 @@ __global__ void __launch_bounds__(256) roi_align_rotated_kernel(const RoiKernelP
     const int H = p.feat_h[lvl], W = p.feat_w[lvl];
     const float s = p.scale[lvl];
     const int Hp = H + 2 * p.border, Wp = W + 2 * p.border;
-    const float* f = p.feat[lvl] + (int64_t)batch * Hp * Wp * p.ld;
+    const void* f = p.feat[lvl];
+    const void* flo = p.feat_lo[lvl];
+    const int64_t img_off = (int64_t)batch * Hp * Wp * p.ld;
 
     const float cw = bx * s - 0.5f, chh = by * s - 0.5f;
     const float rw = bw * s, rh = bh * s;
@@ -88,15 +103,16 @@ __global__ void __launch_bounds__(256) roi_align_rotated_kernel(const RoiKernelP
         const float ly = y - (float)yl, lx = x - (float)xl;
         const float hy = 1.f - ly, hx = 1.f - lx;
         const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
-        const float4* r1 = reinterpret_cast<const float4*>(f + ((int64_t)(yl + p.border) * Wp + xl + p.border) * p.ld);
-        const float4* r2 = reinterpret_cast<const float4*>(f + ((int64_t)(yl + p.border) * Wp + xh + p.border) * p.ld);
-        const float4* r3 = reinterpret_cast<const float4*>(f + ((int64_t)(yh + p.border) * Wp + xl + p.border) * p.ld);
-        const float4* r4 = reinterpret_cast<const float4*>(f + ((int64_t)(yh + p.border) * Wp + xh + p.border) * p.ld);
+        const int64_t o1 = img_off + ((int64_t)(yl + p.border) * Wp + xl + p.border) * p.ld;
+        const int64_t o2 = img_off + ((int64_t)(yl + p.border) * Wp + xh + p.border) * p.ld;
+        const int64_t o3 = img_off + ((int64_t)(yh + p.border) * Wp + xl + p.border) * p.ld;
+        const int64_t o4 = img_off + ((int64_t)(yh + p.border) * Wp + xh + p.border) * p.ld;
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
           const int ci = lane + 32 * v;
           if (ci < cvecs) {
-            const float4 a = __ldg(r1 + ci), b = __ldg(r2 + ci), c = __ldg(r3 + ci), d = __ldg(r4 + ci);
+            const float4 a = load4<SPLIT_IN>(f, flo, o1, ci), b = load4<SPLIT_IN>(f, flo, o2, ci);
+            const float4 c = load4<SPLIT_IN>(f, flo, o3, ci), d = load4<SPLIT_IN>(f, flo, o4, ci);
             acc[v].x += w1 * a.x + w2 * b.x + w3 * c.x + w4 * d.x;
             acc[v].y += w1 * a.y + w2 * b.y + w3 * c.y + w4 * d.y;
             acc[v].z += w1 * a.z + w2 * b.z + w3 * c.z + w4 * d.z;
@@ -237,6 +253,8 @@ extern "C" int glass_roi_align_rotated(const GlassRoiAlignParams* p, void* strea
     GLASS_CHECK(p->feat[l] != nullptr && p->feat_h[l] > 0 && p->feat_w[l] > 0, "bad feature level");
     GLASS_CHECK((reinterpret_cast<uintptr_t>(p->feat[l]) & 15) == 0, "feature maps must be 16-byte aligned");
     k.feat[l] = p->feat[l];
+    k.feat_lo[l] = p->feat_lo[l];
+    if (p->feat_is_split) GLASS_CHECK(p->feat_lo[l] != nullptr, "feat_lo missing for split feature map");
     k.feat_h[l] = p->feat_h[l];
     k.feat_w[l] = p->feat_w[l];
     k.scale[l] = p->spatial_scale[l];
@@ -252,9 +270,11 @@ extern "C" int glass_roi_align_rotated(const GlassRoiAlignParams* p, void* strea
   const int64_t cap = (int64_t)num_sms() * 8 * 4;  // 8 resident CTAs/SM x 4 waves, grid-stride beyond
   if (blocks > cap) blocks = cap;
   if (p->channels <= 128) {
-    roi_align_rotated_kernel<1><<<(int)blocks, 256, 0, stream>>>(k);
+    if (p->feat_is_split) roi_align_rotated_kernel<1, true><<<(int)blocks, 256, 0, stream>>>(k);
+    else roi_align_rotated_kernel<1, false><<<(int)blocks, 256, 0, stream>>>(k);
   } else {
-    roi_align_rotated_kernel<2><<<(int)blocks, 256, 0, stream>>>(k);
+    if (p->feat_is_split) roi_align_rotated_kernel<2, true><<<(int)blocks, 256, 0, stream>>>(k);
+    else roi_align_rotated_kernel<2, false><<<(int)blocks, 256, 0, stream>>>(k);
   }
   count_launch();
   GLASS_CUDA(cudaGetLastError());

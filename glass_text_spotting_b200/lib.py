@@ -33,7 +33,8 @@ class ConvGemmParams(C.Structure):
 
 class RoiAlignParams(C.Structure):
     _fields_ = [
-        ("num_levels", C.c_int32), ("feat", C.c_void_p * MAX_LEVELS),
+        ("num_levels", C.c_int32), ("feat", C.c_void_p * MAX_LEVELS), ("feat_lo", C.c_void_p * MAX_LEVELS),
+        ("feat_is_split", C.c_int32),
         ("feat_h", C.c_int32 * MAX_LEVELS), ("feat_w", C.c_int32 * MAX_LEVELS),
         ("spatial_scale", C.c_float * MAX_LEVELS),
         ("feat_border", C.c_int32), ("feat_ld", C.c_int32), ("channels", C.c_int32), ("min_level", C.c_int32),

@@ -1,0 +1,194 @@
+"""ResNet-50 + FPN (+ LastLevelMaxPool) on the tcgen05 conv kernel.
+
+Mirrors detectron2's ``build_resnet_fpn_backbone`` as selected by configs/glass_pretrain.yaml:41-54
+(the reference calls it at glass/modeling/meta_arch/glass_rcnn.py:83): same ``state_dict`` names
+(SURVEY.md A.10), same outputs {"p2".."p6"} with strides 4..64, ``size_divisibility`` 32.
+Activations stay in split-bf16 padded NHWC (ops.Act) between layers; BatchNorm (eval) is folded into
+each GEMM's epilogue scale/bias; ReLU, the bottleneck residual add and the FPN top-down
+nearest-upsample add are fused into the epilogue as well.
+"""
+from typing import Dict, Optional
+
+import torch
+
+from .. import ops, packing
+from ..ops import Act
+
+PIXEL_MEAN = (103.530, 116.280, 123.675)
+PIXEL_STD = (1.0, 1.0, 1.0)
+
+
+def _conv_bn(sd: Dict[str, torch.Tensor], prefix: str, stride=(1, 1), pad=(0, 0), device="cuda"):
+    w = sd[prefix + ".weight"]
+    if prefix + ".norm.weight" in sd:
+        scale, bias = packing.fold_bn(sd[prefix + ".norm.weight"], sd[prefix + ".norm.bias"],
+                                      sd[prefix + ".norm.running_mean"], sd[prefix + ".norm.running_var"],
+                                      conv_bias=sd.get(prefix + ".bias"))
+    else:
+        scale, bias = None, sd.get(prefix + ".bias")
+    return packing.pack_conv(w, scale, bias, stride, pad, device=device)
+
+
+class Workspace:
+    """Named, shape-checked device buffers allocated once (zero-filled) and reused every step, so the
+    steady state performs no allocation and the zero borders of Act buffers are established once."""
+
+    def __init__(self, device="cuda"):
+        self.device = device
+        self._acts: Dict[str, Act] = {}
+        self._raw: Dict[str, torch.Tensor] = {}
+
+    def act(self, name: str, n: int, c: int, h: int, w: int, cp: Optional[int] = None) -> Act:
+        a = self._acts.get(name)
+        cp = cp if cp is not None else ops.round_up(c, 64)
+        if a is None or (a.n, a.c, a.h, a.w, a.cp) != (n, c, h, w, cp):
+            a = Act(n, c, h, w, 1, cp, self.device)
+            self._acts[name] = a
+        return a
+
+    def raw(self, name: str, shape, dtype=torch.bfloat16, zero: bool = False) -> torch.Tensor:
+        t = self._raw.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = (torch.zeros if zero else torch.empty)(tuple(shape), dtype=dtype, device=self.device)
+            self._raw[name] = t
+        return t
+
+    def nbytes(self) -> int:
+        return sum(a.buf.numel() * 2 for a in self._acts.values()) + \
+            sum(t.numel() * t.element_size() for t in self._raw.values())
+
+
+class B200ResNetFPN:
+    """Backbone.forward(Tensor[N,3,H,W]) -> dict of Acts (d2 Backbone contract).
+
+    ``forward`` takes the RAW image batch (fp32 NCHW, BGR, unnormalised, already padded to /32): the
+    (x - pixel_mean)/pixel_std of GeneralizedRCNN.preprocess_image is fused into the stem's im2col."""
+
+    size_divisibility = 32
+    out_features = ("p2", "p3", "p4", "p5", "p6")
+    strides = {"p2": 4, "p3": 8, "p4": 16, "p5": 32, "p6": 64}
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], prefix: str = "backbone.", device="cuda",
+                 mode: int = ops.MODE_BF16X3, pixel_mean=PIXEL_MEAN, pixel_std=PIXEL_STD):
+        sd = {k[len(prefix):]: v for k, v in state_dict.items() if k.startswith(prefix)}
+        self.device, self.mode = device, mode
+        self.pixel_mean, self.pixel_std = pixel_mean, pixel_std
+        s = "bottom_up.stem.conv1"
+        scale, bias = packing.fold_bn(sd[s + ".norm.weight"], sd[s + ".norm.bias"], sd[s + ".norm.running_mean"],
+                                      sd[s + ".norm.running_var"])
+        self.stem = packing.pack_stem(sd[s + ".weight"], scale, bias, device=device)
+        self.blocks = {}
+        for i, (nb, stage) in enumerate(zip([3, 4, 6, 3], ["res2", "res3", "res4", "res5"])):
+            blks = []
+            for b in range(nb):
+                p = f"bottom_up.{stage}.{b}"
+                st = (2, 2) if (b == 0 and i > 0) else (1, 1)
+                blk = {
+                    "stride": st[0],
+                    "conv1": _conv_bn(sd, p + ".conv1", st, (0, 0), device),
+                    "conv2": _conv_bn(sd, p + ".conv2", (1, 1), (1, 1), device),
+                    "conv3": _conv_bn(sd, p + ".conv3", (1, 1), (0, 0), device),
+                    "shortcut": _conv_bn(sd, p + ".shortcut", st, (0, 0), device)
+                    if (p + ".shortcut.weight") in sd else None,
+                }
+                blks.append(blk)
+            self.blocks[stage] = blks
+        self.lateral = {k: _conv_bn(sd, f"fpn_lateral{k}", device=device) for k in [2, 3, 4, 5]}
+        self.output = {k: _conv_bn(sd, f"fpn_output{k}", (1, 1), (1, 1), device) for k in [2, 3, 4, 5]}
+        self.ws = Workspace(device)
+
+    # ------------------------------------------------------------------------------------------
+    def _gemm_rows(self, g: torch.Tensor, w, n, ho, wo, out: Act, relu: bool):
+        ops.conv_gemm(g[0], g[1], g.shape[1], g.shape[2], [0], w, (n, ho, wo, 0), out=out, relu_post=relu,
+                      mode=self.mode)
+
+    def _bottleneck(self, x: Act, blk, name: str) -> Act:
+        ws, n = self.ws, x.n
+        s = blk["stride"]
+        ho, wo = x.h // s, x.w // s
+        c1, c2, c3 = blk["conv1"], blk["conv2"], blk["conv3"]
+        t1 = ws.act(f"{name}.t1", n, c1.cout, ho, wo)
+        t2 = ws.act(f"{name}.t2", n, c2.cout, ho, wo)
+        out = ws.act(f"{name}.out", n, c3.cout, ho, wo)
+        if s == 1:
+            ops.conv2d(x, c1, relu=True, out=t1, mode=self.mode)
+            sc = x
+            if blk["shortcut"] is not None:
+                sc = ws.act(f"{name}.sc", n, c3.cout, ho, wo)
+                ops.conv2d(x, blk["shortcut"], out=sc, mode=self.mode)
+        else:
+            # STRIDE_IN_1X1: conv1 and the shortcut read the same stride-2 subsampled pixels -> gather once
+            g = ws.raw(f"{name}.gather", (2, n * ho * wo, x.cp))
+            ops.gather_taps(x, 1, 1, s, s, 0, 0, ho, wo, g)
+            self._gemm_rows(g, c1, n, ho, wo, t1, True)
+            sc = ws.act(f"{name}.sc", n, c3.cout, ho, wo)
+            self._gemm_rows(g, blk["shortcut"], n, ho, wo, sc, False)
+        ops.conv2d(t1, c2, relu=True, out=t2, mode=self.mode)
+        ops.conv2d(t2, c3, relu=True, residual=sc, out=out, mode=self.mode)
+        return out
+
+    def bottom_up(self, images: torch.Tensor) -> Dict[str, Act]:
+        n, _, h, w = images.shape
+        assert h % 32 == 0 and w % 32 == 0, "pad the batch to size_divisibility first (ImageList.from_tensors)"
+        ws = self.ws
+        cols = ws.raw("stem.cols", (2, n * (h // 2) * (w // 2), 192))
+        ops.stem_im2col(images, self.pixel_mean, self.pixel_std, out=cols)
+        s1 = ws.act("stem.conv", n, 64, h // 2, w // 2)
+        ops.conv_gemm(cols[0], cols[1], cols.shape[1], 192, [0], self.stem, (n, h // 2, w // 2, 0), out=s1,
+                      relu_post=True, mode=self.mode)
+        x = ws.act("stem.pool", n, 64, h // 4, w // 4)
+        ops.maxpool2d(s1, (3, 3), (2, 2), (1, 1), out=x)
+        feats = {}
+        for stage in ["res2", "res3", "res4", "res5"]:
+            for b, blk in enumerate(self.blocks[stage]):
+                x = self._bottleneck(x, blk, f"{stage}.{b}")
+            feats[stage] = x
+        return feats
+
+    def fpn(self, c: Dict[str, Act]) -> Dict[str, Act]:
+        ws = self.ws
+        out: Dict[str, Act] = {}
+        prev = None
+        for k in [5, 4, 3, 2]:
+            x = c[f"res{k}"]
+            lat = ws.act(f"fpn.prev{k}", x.n, 256, x.h, x.w)
+            ops.conv2d(x, self.lateral[k], residual=prev, res_shift=1 if prev is not None else 0, out=lat,
+                       mode=self.mode)
+            pk = ws.act(f"fpn.p{k}", x.n, 256, x.h, x.w)
+            ops.conv2d(lat, self.output[k], out=pk, mode=self.mode)
+            out[f"p{k}"] = pk
+            prev = lat
+        p5 = out["p5"]
+        p6 = ws.act("fpn.p6", p5.n, 256, p5.h // 2, p5.w // 2)
+        ops.maxpool2d(p5, (1, 1), (2, 2), (0, 0), out=p6)  # LastLevelMaxPool: k=1, s=2 subsample
+        out["p6"] = p6
+        return out
+
+    def forward(self, images: torch.Tensor) -> Dict[str, Act]:
+        c = self.bottom_up(images)
+        out = self.fpn(c)
+        out.update(c)
+        return out
+
+    __call__ = forward
+
+    def output_shape(self):
+        return {k: {"channels": 256, "stride": s} for k, s in self.strides.items()}
+
+    @staticmethod
+    def flops_per_image(h: int = 1024, w: int = 1024) -> float:
+        """Algorithmic conv FLOPs (2*MACs) of ResNet-50 + FPN for one h x w image."""
+        f = 2.0 * 147 * 64 * (h // 2) * (w // 2)
+        cin = 64
+        for i, nb in enumerate([3, 4, 6, 3]):
+            bott, cout = 64 * 2 ** i, 256 * 2 ** i
+            hw = (h // (4 * 2 ** i)) * (w // (4 * 2 ** i))
+            for b in range(nb):
+                f += 2.0 * hw * (cin * bott + 9 * bott * bott + bott * cout)
+                if cin != cout:
+                    f += 2.0 * hw * cin * cout
+                cin = cout
+        for k, cin in zip([2, 3, 4, 5], [256, 512, 1024, 2048]):
+            hw = (h // 2 ** k) * (w // 2 ** k)
+            f += 2.0 * hw * (cin * 256 + 9 * 256 * 256)
+        return f

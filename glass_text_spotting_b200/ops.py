@@ -213,20 +213,28 @@ def stem_im2col(img: torch.Tensor, mean: Sequence[float], std: Sequence[float], 
     return out
 
 
-def roi_align_rotated(feats: List[F32Map], rois: torch.Tensor, output_size: Tuple[int, int],
+def roi_align_rotated(feats: List, rois: torch.Tensor, output_size: Tuple[int, int],
                       scales: Sequence[float], sampling_ratio: int, min_level: int = 2,
                       out_f32: bool = True, out_split: Optional[Tuple[torch.Tensor, int, int, int, int, int]] = None,
                       n_rois_dev: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
-    """Multi-level rotated RoIAlign.  rois fp32 [R,6] (batch, cx, cy, w, h, angle).  Returns fp32
+    """Multi-level rotated RoIAlign over fp32 maps (F32Map) or split-bf16 activations (Act).
+    rois fp32 [R,6] (batch, cx, cy, w, h, angle).  Returns fp32
     [R, ph, pw, C] (NHWC order) when out_f32; out_split = (buf[2,...], hp, wp, border, coff, ld)."""
     assert rois.dtype == torch.float32 and rois.dim() == 2 and rois.shape[1] == 6 and rois.is_contiguous()
     p = _lib.RoiAlignParams()
     p.num_levels = len(feats)
-    for i, f in enumerate(feats):
-        p.feat[i], p.feat_h[i], p.feat_w[i], p.spatial_scale[i] = _ptr(f.buf), f.h, f.w, float(scales[i])
     f0 = feats[0]
-    assert all(f.ld == f0.ld and f.border == f0.border and f.c == f0.c for f in feats)
-    p.feat_border, p.feat_ld, p.channels, p.min_level = f0.border, f0.ld, f0.c, min_level
+    split_in = isinstance(f0, Act)
+    p.feat_is_split = int(split_in)
+    for i, f in enumerate(feats):
+        p.feat_h[i], p.feat_w[i], p.spatial_scale[i] = f.h, f.w, float(scales[i])
+        if split_in:
+            p.feat[i], p.feat_lo[i] = _ptr(f.hi), _ptr(f.lo)
+        else:
+            p.feat[i] = _ptr(f.buf)
+    ld0 = f0.cp if split_in else f0.ld
+    assert all((f.cp if split_in else f.ld) == ld0 and f.border == f0.border and f.c == f0.c for f in feats)
+    p.feat_border, p.feat_ld, p.channels, p.min_level = f0.border, ld0, f0.c, min_level
     p.rois, p.n_rois = _ptr(rois), rois.shape[0]
     p.n_rois_dev = _ptr(n_rois_dev)
     p.pooled_h, p.pooled_w, p.sampling_ratio = output_size[0], output_size[1], sampling_ratio

@@ -121,7 +121,8 @@ int glass_maxpool(const void* src_hi, const void* src_lo, int n, int h, int w, i
  * replaces: torch.ops.detectron2.roi_align_rotated_forward as called through ROIPooler at
  *   recognizers_hybrid_head.py:320 (box pooler 7x7, 5 levels, sampling 2), :550 (recognizer pooler
  *   8x32, 1 level, adaptive sampling) and :556 (image pooler 128x128, scale 1, sampling 2).
- * Feature maps are fp32 padded NHWC [n, h+2b, w+2b, ld] (the conv kernel's out_f32).
+ * Feature maps are padded NHWC [n, h+2b, w+2b, ld]: either fp32 (the conv kernel's out_f32) or the
+ * split-bf16 hi/lo planes of an activation (feat_is_split; value = hi + lo, same bytes per element).
  * rois: fp32 [n_rois, 6] = (batch_idx, cx, cy, w, h, angle_deg).  With num_levels > 1 the level of
  * each RoI follows d2's assign_boxes_to_levels (canonical size 224 at level 4).
  * Outputs (any subset): out_f32 [n_rois, ph, pw, c] (NHWC order) and split bf16 rows written at
@@ -129,7 +130,9 @@ int glass_maxpool(const void* src_hi, const void* src_lo, int n, int h, int w, i
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
   int32_t num_levels;
-  const float* feat[GLASS_MAX_LEVELS];
+  const void* feat[GLASS_MAX_LEVELS];    /* fp32 map, or the bf16 hi plane when feat_is_split */
+  const void* feat_lo[GLASS_MAX_LEVELS]; /* bf16 lo plane (feat_is_split only) */
+  int32_t feat_is_split;
   int32_t feat_h[GLASS_MAX_LEVELS], feat_w[GLASS_MAX_LEVELS];
   float spatial_scale[GLASS_MAX_LEVELS];
   int32_t feat_border, feat_ld, channels;
