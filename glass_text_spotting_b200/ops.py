@@ -14,6 +14,9 @@ from . import lib as _lib
 MODE_BF16X3 = 0   # fp32-grade split precision (parity mode; default)
 MODE_BF16 = 1     # single bf16 pass (fast mode)
 
+# bench.py's per-kernel timing: when a list, every conv_gemm launch appends (start, end) CUDA events
+PROFILE = None
+
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
@@ -138,12 +141,19 @@ def conv_gemm(a_hi: torch.Tensor, a_lo: Optional[torch.Tensor], rows_a: int, k_p
     p.out_hi, p.out_lo, p.out_f32 = _ptr(out_hi), _ptr(out_lo), _ptr(out_f32)
     p.out_hp, p.out_wp, p.out_border = out_geom
     p.ld_out, p.ld_f32, p.n_store = ld_out, ld_f32, n_store
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(torch.cuda.current_stream())
+        _lib.check(_lib.load().glass_conv_gemm(C.byref(p), _stream()))
+        e1.record(torch.cuda.current_stream())
+        PROFILE.append((e0, e1))
+        return
     _lib.check(_lib.load().glass_conv_gemm(C.byref(p), _stream()))
 
 
 def conv2d(x: Act, w: PackedWeight, relu: bool = False, residual: Optional[Act] = None, res_shift: int = 0,
            relu_pre: bool = False, out: Optional[Act] = None, f32: Optional[F32Map] = None, want_act: bool = True,
-           mode: int = MODE_BF16X3) -> Optional[Act]:
+           mode: int = MODE_BF16X3, gather_buf: Optional[torch.Tensor] = None) -> Optional[Act]:
     """conv (+ folded norm) (+ReLU) (+residual) on a split-bf16 activation.
 
     stride-1 'same' convs run as shifted-row implicit GEMM straight from ``x``; everything else goes
@@ -170,9 +180,7 @@ def conv2d(x: Act, w: PackedWeight, relu: bool = False, residual: Optional[Act] 
     else:
         taps = w.kh * w.kw
         rows = x.n * ho * wo
-        g = torch.empty((2, rows, taps * x.cp), dtype=torch.bfloat16, device=x.buf.device)
-        _lib.check(_lib.load().glass_gather_taps(_ptr(x.hi), _ptr(x.lo), x.n, x.h, x.w, x.cp, x.border, w.kh, w.kw,
-                                                 sh, sw, ph, pw, ho, wo, _ptr(g[0]), _ptr(g[1]), _stream()))
+        g = gather_taps(x, w.kh, w.kw, sh, sw, ph, pw, ho, wo, out=gather_buf)
         # the gathered matrix is already tap-major: one "tap" of width taps*cp
         conv_gemm(g[0], g[1], rows, taps * x.cp, [0], w, (x.n, ho, wo, 0), **kwargs)
     return out
@@ -192,21 +200,37 @@ def linear(a: torch.Tensor, w: PackedWeight, relu: bool = False, want_split: boo
     return o, of
 
 
-def maxpool2d(x: Act, k: Tuple[int, int], s: Tuple[int, int], p: Tuple[int, int]) -> Act:
+def maxpool2d(x: Act, k: Tuple[int, int], s: Tuple[int, int], p: Tuple[int, int], out: Optional[Act] = None) -> Act:
     ho = (x.h + 2 * p[0] - k[0]) // s[0] + 1
     wo = (x.w + 2 * p[1] - k[1]) // s[1] + 1
-    out = Act(x.n, x.c, ho, wo, 1, x.cp, x.buf.device)
+    if out is None:
+        out = Act(x.n, x.c, ho, wo, 1, x.cp, x.buf.device)
+    assert (out.n, out.h, out.w, out.cp) == (x.n, ho, wo, x.cp)
     _lib.check(_lib.load().glass_maxpool(_ptr(x.hi), _ptr(x.lo), x.n, x.h, x.w, x.cp, x.border, k[0], k[1], s[0],
                                          s[1], p[0], p[1], ho, wo, _ptr(out.hi), _ptr(out.lo), out.border,
                                          _stream()))
     return out
 
 
-def stem_im2col(img: torch.Tensor, mean: Sequence[float], std: Sequence[float], kp: int = 192) -> torch.Tensor:
+def gather_taps(x: Act, kh: int, kw: int, sh: int, sw: int, ph: int, pw: int, ho: int, wo: int,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """im2col of a split activation: rows [2, n*ho*wo, kh*kw*cp] (tap-major K)."""
+    if out is None:
+        out = torch.empty((2, x.n * ho * wo, kh * kw * x.cp), dtype=torch.bfloat16, device=x.buf.device)
+    assert tuple(out.shape) == (2, x.n * ho * wo, kh * kw * x.cp) and out.is_contiguous()
+    _lib.check(_lib.load().glass_gather_taps(_ptr(x.hi), _ptr(x.lo), x.n, x.h, x.w, x.cp, x.border, kh, kw, sh, sw,
+                                             ph, pw, ho, wo, _ptr(out[0]), _ptr(out[1]), _stream()))
+    return out
+
+
+def stem_im2col(img: torch.Tensor, mean: Sequence[float], std: Sequence[float], kp: int = 192,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """raw fp32 NCHW [n,3,h,w] -> split rows [2, n*(h/2)*(w/2), kp] of the 7x7/s2/p3 stem conv."""
     n, c, h, w = img.shape
     assert c == 3 and img.dtype == torch.float32 and img.is_contiguous()
-    out = torch.empty((2, n * (h // 2) * (w // 2), kp), dtype=torch.bfloat16, device=img.device)
+    if out is None:
+        out = torch.empty((2, n * (h // 2) * (w // 2), kp), dtype=torch.bfloat16, device=img.device)
+    assert tuple(out.shape) == (2, n * (h // 2) * (w // 2), kp) and out.is_contiguous()
     m = (C.c_float * 3)(*[float(v) for v in mean])
     s = (C.c_float * 3)(*[1.0 / float(v) for v in std])
     _lib.check(_lib.load().glass_stem_im2col(_ptr(img), n, h, w, m, s, _ptr(out[0]), _ptr(out[1]), kp, _stream()))
