@@ -6,7 +6,7 @@
 // the PTX ISA (cross-checked against cute/arch/mma_sm100_desc.hpp).
 #pragma once
 
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -38,18 +38,29 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
-// Split an fp32 value into (hi, lo) bf16 with x ~= hi + lo (|lo| <= 2^-8 |hi|).
-__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-  hi = __float2bfloat16_rn(x);
-  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+// "split-fp16" storage: an fp32 value x is held as two fp16 planes (hi, lo) with
+//   kActScale * x ~= hi + lo      (22 mantissa bits; |lo| <= 2^-11 |hi|).
+// The power-of-two pre-scale keeps the lo plane out of fp16's subnormal range for |x| >~ 8e-3 and
+// leaves head-room up to |x| = 60000/16; it is undone exactly in the GEMM epilogue / by readers.
+static constexpr float kActScale = 16.0f;
+static constexpr float kActScaleInv = 0.0625f;
+
+__device__ __forceinline__ void split16(float x, __half& hi, __half& lo) {
+  const float xs = fminf(fmaxf(x * kActScale, -60000.f), 60000.f);
+  hi = __float2half_rn(xs);
+  lo = __float2half_rn(xs - __half2float(hi));
 }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
-  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+__device__ __forceinline__ uint32_t pack16x2(__half a, __half b) {
+  return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
 }
 
-__device__ __forceinline__ float bf16_lo_of(uint32_t packed) { return __uint_as_float(packed << 16); }
-__device__ __forceinline__ float bf16_hi_of(uint32_t packed) { return __uint_as_float(packed & 0xffff0000u); }
+// two packed fp16 words (hi plane, lo plane) -> the two represented fp32 values (scale removed)
+__device__ __forceinline__ float2 unpack16x2(uint32_t hi, uint32_t lo) {
+  const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  const float2 l = __half22float2(*reinterpret_cast<const __half2*>(&lo));
+  return make_float2((h.x + l.x) * kActScaleInv, (h.y + l.y) * kActScaleInv);
+}
 
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -143,8 +154,8 @@ __device__ __forceinline__ void tcgen05_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 
-// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32, issued by ONE thread.
-__device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+// D[tmem] (+)= A[smem] * B[smem], fp16 x fp16 -> fp32, issued by ONE thread.
+__device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                              uint32_t accumulate) {
   asm volatile(
       "{\n"
@@ -176,8 +187,8 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
 
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// UMMA shared-memory matrix descriptor: K-major operand, 128-byte swizzle, bf16.
-// A tile is rows x 64 bf16 (128 B per row), 8-row groups 1024 B apart (SBO), as
+// UMMA shared-memory matrix descriptor: K-major operand, 128-byte swizzle, 16-bit elements.
+// A tile is rows x 64 fp16 (128 B per row), 8-row groups 1024 B apart (SBO), as
 // written by a TMA box with CU_TENSOR_MAP_SWIZZLE_128B into 1024 B-aligned smem.
 //   [0,14) start address >> 4   [16,30) LBO >> 4 (ignored for swizzled K-major)
 //   [32,46) SBO >> 4            [46,48) version = 1 (sm_100)   [61,64) layout = 2 (SW128)
@@ -191,11 +202,11 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
-// Instruction descriptor, kind::f16: A = B = bf16 (K-major), D = fp32, dense.
-//   [4,6) c_format = 1 (F32)  [7,10) a_format = 1 (BF16)  [10,13) b_format = 1
+// Instruction descriptor, kind::f16: A = B = fp16 (K-major), D = fp32, dense.
+//   [4,6) c_format = 1 (F32)  [7,10) a_format = 0 (F16)  [10,13) b_format = 0 (F16)
 //   [15] a_major = 0 (K)  [16] b_major = 0 (K)  [17,23) N >> 3  [24,29) M >> 4
-__host__ __device__ inline uint32_t umma_idesc_bf16_f32(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+__host__ __device__ inline uint32_t umma_idesc_f16_f32(int m, int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 #endif  // __CUDACC__
 

@@ -1,7 +1,7 @@
 // conv_gemm.cu -- persistent, warp-specialised tcgen05 implicit-GEMM (sm_100a).
 //
 // One kernel serves every conv / Linear on GLASS's dense path (see include/glass_b200.h).
-//   A: activations, split-bf16 padded NHWC flattened to rows [pixels, C]; a conv tap (r,s) is a
+//   A: activations, split-fp16 padded NHWC flattened to rows [pixels, C]; a conv tap (r,s) is a
 //      constant row shift, so each k-block is ONE 2-D TMA box (64 channels x 128 pixels) at row
 //      m0 + shift -- image borders are real zero pixels in memory, tensor edges are TMA OOB zeros.
 //   B: weights packed [Cout, taps*C] K-major.
@@ -9,8 +9,8 @@
 //      i overlaps the main loop of tile i+1.
 // Roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warp 2 = TMEM
 // allocator, warps 4..7 = epilogue (one TMEM lane quadrant each).
-// Precision modes: bf16x3 split (3 MMAs per k-step into the same accumulator: hi*hi, hi*lo, lo*hi)
-// gives fp32-grade results (rel err ~1e-5); mode 1 issues only hi*hi.
+// Precision modes: fp16x3 split (3 MMAs per k-step into the same accumulator: hi*hi, hi*lo, lo*hi)
+// gives fp32-grade results (22-bit operands, fp32 accumulate); mode 1 issues only hi*hi.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -36,11 +36,11 @@ struct GemmKernelParams {
   const float* scale;
   const float* bias;
   int32_t relu_pre, relu_post;
-  const __nv_bfloat16* res_hi;
-  const __nv_bfloat16* res_lo;
+  const __half* res_hi;
+  const __half* res_lo;
   int32_t res_hp, res_wp, res_border, res_shift;
-  __nv_bfloat16* out_hi;
-  __nv_bfloat16* out_lo;
+  __half* out_hi;
+  __half* out_lo;
   float* out_f32;
   int32_t out_hp, out_wp, out_border;
   int32_t ld_out, ld_f32, n_store;
@@ -130,7 +130,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   } else if (warp == 1) {
     // ===================================================== MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16_f32(BM, p.bn);
+      const uint32_t idesc = umma_idesc_f16_f32(BM, p.bn);
       int stage = 0;
       uint32_t phase = 0;
       int local_tile = 0;
@@ -153,12 +153,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
               const uint64_t da_lo = umma_smem_desc_sw128(s + A_TILE_BYTES);
               const uint64_t db_hi = umma_smem_desc_sw128(s + 2 * A_TILE_BYTES);
               const uint64_t db_lo = umma_smem_desc_sw128(s + 2 * A_TILE_BYTES + p.b_tile_bytes);
-              umma_bf16_ss(d_tmem, da_lo + koff, db_hi + koff, idesc, acc_flag);
-              umma_bf16_ss(d_tmem, da_hi + koff, db_lo + koff, idesc, 1u);
-              umma_bf16_ss(d_tmem, da_hi + koff, db_hi + koff, idesc, 1u);
+              umma_f16_ss(d_tmem, da_lo + koff, db_hi + koff, idesc, acc_flag);
+              umma_f16_ss(d_tmem, da_hi + koff, db_lo + koff, idesc, 1u);
+              umma_f16_ss(d_tmem, da_hi + koff, db_hi + koff, idesc, 1u);
             } else {
               const uint64_t db_hi = umma_smem_desc_sw128(s + A_TILE_BYTES);
-              umma_bf16_ss(d_tmem, da_hi + koff, db_hi + koff, idesc, acc_flag);
+              umma_f16_ss(d_tmem, da_hi + koff, db_hi + koff, idesc, acc_flag);
             }
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
@@ -238,8 +238,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
               const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                v[h * 8 + 2 * j] += bf16_lo_of(aw[j]) + bf16_lo_of(bw[j]);
-                v[h * 8 + 2 * j + 1] += bf16_hi_of(aw[j]) + bf16_hi_of(bw[j]);
+                const float2 rv = unpack16x2(aw[j], bw[j]);
+                v[h * 8 + 2 * j] += rv.x;
+                v[h * 8 + 2 * j + 1] += rv.y;
               }
             }
           }
@@ -256,11 +257,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             uint32_t hw[8], lw[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              __nv_bfloat16 h0, l0, h1, l1;
-              split_bf16(v[2 * j], h0, l0);
-              split_bf16(v[2 * j + 1], h1, l1);
-              hw[j] = pack_bf16x2(h0, h1);
-              lw[j] = pack_bf16x2(l0, l1);
+              __half h0, l0, h1, l1;
+              split16(v[2 * j], h0, l0);
+              split16(v[2 * j + 1], h1, l1);
+              hw[j] = pack16x2(h0, h1);
+              lw[j] = pack16x2(l0, l1);
             }
             uint4* oh = reinterpret_cast<uint4*>(p.out_hi + out_row * p.ld_out + n);
             oh[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
@@ -296,7 +297,7 @@ static int make_map_2d(CUtensorMap* map, const void* base, uint64_t inner, uint6
   cuuint64_t strides[1] = {inner * 2};  // bytes, dim 1
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
@@ -312,8 +313,8 @@ extern "C" int glass_conv_gemm(const GlassConvGemmParams* p, void* stream_v) {
   GLASS_CHECK(p != nullptr, "null params");
   GLASS_CHECK(p->a_hi && p->b_hi, "a_hi / b_hi must be set");
   const bool split = (p->mode == 0);
-  GLASS_CHECK(p->mode == 0 || p->mode == 1, "mode must be 0 (bf16x3) or 1 (bf16)");
-  if (split) GLASS_CHECK(p->a_lo && p->b_lo, "bf16x3 mode needs a_lo / b_lo");
+  GLASS_CHECK(p->mode == 0 || p->mode == 1, "mode must be 0 (fp16x3 split) or 1 (single fp16 pass)");
+  if (split) GLASS_CHECK(p->a_lo && p->b_lo, "split mode needs a_lo / b_lo");
   GLASS_CHECK(p->k_per_tap > 0 && p->k_per_tap % BK == 0, "k_per_tap must be a positive multiple of 64");
   GLASS_CHECK(p->ntaps >= 1 && p->ntaps <= GLASS_MAX_TAPS, "ntaps out of range");
   GLASS_CHECK(p->n >= 16 && p->n % 16 == 0, "n must be a multiple of 16");
@@ -368,9 +369,9 @@ extern "C" int glass_conv_gemm(const GlassConvGemmParams* p, void* stream_v) {
   k.m_h = p->m_h; k.m_w = p->m_w; k.m_border = p->m_border;
   k.scale = p->scale; k.bias = p->bias;
   k.relu_pre = p->relu_pre; k.relu_post = p->relu_post;
-  k.res_hi = (const __nv_bfloat16*)p->res_hi; k.res_lo = (const __nv_bfloat16*)p->res_lo;
+  k.res_hi = (const __half*)p->res_hi; k.res_lo = (const __half*)p->res_lo;
   k.res_hp = p->res_hp; k.res_wp = p->res_wp; k.res_border = p->res_border; k.res_shift = p->res_shift;
-  k.out_hi = (__nv_bfloat16*)p->out_hi; k.out_lo = (__nv_bfloat16*)p->out_lo; k.out_f32 = p->out_f32;
+  k.out_hi = (__half*)p->out_hi; k.out_lo = (__half*)p->out_lo; k.out_f32 = p->out_f32;
   k.out_hp = p->out_hp; k.out_wp = p->out_wp; k.out_border = p->out_border;
   k.ld_out = p->ld_out; k.ld_f32 = p->ld_f32; k.n_store = n_store;
 

@@ -1,5 +1,5 @@
 // layout.cu -- HBM-bound glue kernels around the tcgen05 GEMM: layout conversion between fp32 NCHW
-// (the reference's tensors) and split-bf16 padded NHWC (ours), the stem im2col with fused pixel
+// (the reference's tensors) and split-fp16 padded NHWC (ours), the stem im2col with fused pixel
 // normalisation, the generic tap gather for strided convs, and max-pooling.
 // All are streaming kernels: 16-byte vector accesses along the channel (innermost) dimension.
 #include "common.cuh"
@@ -20,7 +20,7 @@ static inline int grid_for(int64_t total, int block) {
 // One thread per (pixel, 8-channel group): reads 8 strided floats (coalesced across the warp along
 // x), writes one 16 B vector per plane.
 __global__ void pack_nchw_kernel(const float* __restrict__ src, int n, int c, int h, int w,
-                                 __nv_bfloat16* __restrict__ dhi, __nv_bfloat16* __restrict__ dlo, int cp,
+                                 __half* __restrict__ dhi, __half* __restrict__ dlo, int cp,
                                  int border) {
   const int groups = (c + 7) / 8;
   const int64_t total = (int64_t)n * groups * h * w;
@@ -39,11 +39,11 @@ __global__ void pack_nchw_kernel(const float* __restrict__ src, int n, int c, in
       const int c0 = g * 8 + 2 * j;
       if (c0 < c) v0 = src[(((int64_t)img * c + c0) * h + y) * w + x];
       if (c0 + 1 < c) v1 = src[(((int64_t)img * c + c0 + 1) * h + y) * w + x];
-      __nv_bfloat16 h0, l0, h1, l1;
-      split_bf16(v0, h0, l0);
-      split_bf16(v1, h1, l1);
-      hw[j] = pack_bf16x2(h0, h1);
-      lw[j] = pack_bf16x2(l0, l1);
+      __half h0, l0, h1, l1;
+      split16(v0, h0, l0);
+      split16(v1, h1, l1);
+      hw[j] = pack16x2(h0, h1);
+      lw[j] = pack16x2(l0, l1);
     }
     const int64_t row = ((int64_t)img * hp + y + border) * wp + x + border;
     *reinterpret_cast<uint4*>(dhi + row * cp + g * 8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
@@ -51,7 +51,7 @@ __global__ void pack_nchw_kernel(const float* __restrict__ src, int n, int c, in
   }
 }
 
-__global__ void unpack_nchw_kernel(const __nv_bfloat16* __restrict__ shi, const __nv_bfloat16* __restrict__ slo,
+__global__ void unpack_nchw_kernel(const __half* __restrict__ shi, const __half* __restrict__ slo,
                                    int n, int c, int h, int w, int cp, int border, float* __restrict__ dst) {
   const int64_t total = (int64_t)n * c * h * w;
   const int hp = h + 2 * border, wp = w + 2 * border;
@@ -63,7 +63,7 @@ __global__ void unpack_nchw_kernel(const __nv_bfloat16* __restrict__ shi, const 
     const int ch = (int)(t % c);
     const int img = (int)(t / c);
     const int64_t row = ((int64_t)img * hp + y + border) * wp + x + border;
-    dst[i] = __bfloat162float(shi[row * cp + ch]) + __bfloat162float(slo[row * cp + ch]);
+    dst[i] = (__half2float(shi[row * cp + ch]) + __half2float(slo[row * cp + ch])) * kActScaleInv;
   }
 }
 
@@ -86,8 +86,8 @@ __global__ void nhwc_f32_to_nchw_kernel(const float* __restrict__ src, int n, in
 // ------------------------------------------------------------------ stem im2col (7x7 s2 p3, Cin 3)
 // One thread per (output pixel, 8-wide k group).  k = (r*7+s)*3 + c.
 __global__ void stem_im2col_kernel(const float* __restrict__ img, int n, int h, int w, float m0, float m1, float m2,
-                                   float is0, float is1, float is2, __nv_bfloat16* __restrict__ dhi,
-                                   __nv_bfloat16* __restrict__ dlo, int kp) {
+                                   float is0, float is1, float is2, __half* __restrict__ dhi,
+                                   __half* __restrict__ dlo, int kp) {
   const int ho = h / 2, wo = w / 2;
   const int groups = kp / 8;
   const int64_t total = (int64_t)n * ho * wo * groups;
@@ -118,11 +118,11 @@ __global__ void stem_im2col_kernel(const float* __restrict__ img, int n, int h, 
     uint32_t hw[4], lw[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      __nv_bfloat16 h0, l0, h1, l1;
-      split_bf16(v[2 * j], h0, l0);
-      split_bf16(v[2 * j + 1], h1, l1);
-      hw[j] = pack_bf16x2(h0, h1);
-      lw[j] = pack_bf16x2(l0, l1);
+      __half h0, l0, h1, l1;
+      split16(v[2 * j], h0, l0);
+      split16(v[2 * j + 1], h1, l1);
+      hw[j] = pack16x2(h0, h1);
+      lw[j] = pack16x2(l0, l1);
     }
     *reinterpret_cast<uint4*>(dhi + pix * kp + g * 8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
     *reinterpret_cast<uint4*>(dlo + pix * kp + g * 8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
@@ -171,7 +171,7 @@ __global__ void maxpool_kernel(const uint4* __restrict__ shi, const uint4* __res
     const int y = (int)((pix / wo) % ho);
     const int b = (int)(pix / ((int64_t)wo * ho));
     float best[8];
-    uint32_t bh[8], bl[8];  // bf16 bit patterns of the winning (hi, lo)
+    uint32_t bh[8], bl[8];  // fp16 bit patterns of the winning (hi, lo)
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       best[j] = -INFINITY;
@@ -191,8 +191,8 @@ __global__ void maxpool_kernel(const uint4* __restrict__ shi, const uint4* __res
         const uint32_t dw[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float v0 = bf16_lo_of(aw[j]) + bf16_lo_of(dw[j]);
-          const float v1 = bf16_hi_of(aw[j]) + bf16_hi_of(dw[j]);
+          const float2 vv = unpack16x2(aw[j], dw[j]);
+          const float v0 = vv.x, v1 = vv.y;
           if (v0 > best[2 * j]) {
             best[2 * j] = v0;
             bh[2 * j] = aw[j] & 0xffffu;
@@ -224,8 +224,8 @@ extern "C" int glass_pack_nchw(const float* src, int n, int c, int h, int w, voi
   GLASS_CHECK(src && dst_hi && dst_lo, "null pointer");
   GLASS_CHECK(n > 0 && c > 0 && h > 0 && w > 0 && cp >= c && cp % 8 == 0 && border >= 0, "bad shape");
   const int64_t total = (int64_t)n * ((c + 7) / 8) * h * w;
-  pack_nchw_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>(src, n, c, h, w, (__nv_bfloat16*)dst_hi,
-                                                             (__nv_bfloat16*)dst_lo, cp, border);
+  pack_nchw_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>(src, n, c, h, w, (__half*)dst_hi,
+                                                             (__half*)dst_lo, cp, border);
   count_launch();
   GLASS_CUDA(cudaGetLastError());
   return 0;
@@ -236,8 +236,8 @@ extern "C" int glass_unpack_nchw(const void* src_hi, const void* src_lo, int n, 
   GLASS_CHECK(src_hi && src_lo && dst, "null pointer");
   GLASS_CHECK(n > 0 && c > 0 && h > 0 && w > 0 && cp >= c && border >= 0, "bad shape");
   const int64_t total = (int64_t)n * c * h * w;
-  unpack_nchw_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>((const __nv_bfloat16*)src_hi,
-                                                               (const __nv_bfloat16*)src_lo, n, c, h, w, cp, border,
+  unpack_nchw_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>((const __half*)src_hi,
+                                                               (const __half*)src_lo, n, c, h, w, cp, border,
                                                                dst);
   count_launch();
   GLASS_CUDA(cudaGetLastError());
@@ -262,8 +262,8 @@ extern "C" int glass_stem_im2col(const float* img, int n, int h, int w, const fl
   GLASS_CHECK(kp >= 152 && kp % 64 == 0, "kp must be a multiple of 64 >= 192");
   const int64_t total = (int64_t)n * (h / 2) * (w / 2) * (kp / 8);
   stem_im2col_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>(img, n, h, w, mean[0], mean[1], mean[2], inv_std[0],
-                                                               inv_std[1], inv_std[2], (__nv_bfloat16*)dst_hi,
-                                                               (__nv_bfloat16*)dst_lo, kp);
+                                                               inv_std[1], inv_std[2], (__half*)dst_hi,
+                                                               (__half*)dst_lo, kp);
   count_launch();
   GLASS_CUDA(cudaGetLastError());
   return 0;

@@ -23,8 +23,8 @@ struct RoiKernelParams {
   const int* n_rois_dev;
   int n_rois, ph, pw, sampling;
   float* out_f32;
-  __nv_bfloat16* out_hi;
-  __nv_bfloat16* out_lo;
+  __half* out_hi;
+  __half* out_lo;
   int out_hp, out_wp, out_border, out_coff, ld_out;
 };
 
@@ -37,14 +37,14 @@ __device__ __forceinline__ int assign_level(float w, float h, int min_level, int
   return (int)lvl - min_level;
 }
 
-// 4 channels of one pixel: fp32 map -> one 16 B load; split-bf16 map -> two 8 B loads (hi + lo).
+// 4 channels of one pixel: fp32 map -> one 16 B load; split-fp16 map -> two 8 B loads (hi + lo).
 template <bool SPLIT_IN>
 __device__ __forceinline__ float4 load4(const void* base, const void* base_lo, int64_t pix_off, int ci) {
   if (SPLIT_IN) {
-    const uint2 h = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(base) + pix_off) + ci);
-    const uint2 l = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(base_lo) + pix_off) + ci);
-    return make_float4(bf16_lo_of(h.x) + bf16_lo_of(l.x), bf16_hi_of(h.x) + bf16_hi_of(l.x),
-                       bf16_lo_of(h.y) + bf16_lo_of(l.y), bf16_hi_of(h.y) + bf16_hi_of(l.y));
+    const uint2 h = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(base) + pix_off) + ci);
+    const uint2 l = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(base_lo) + pix_off) + ci);
+    const float2 a = unpack16x2(h.x, l.x), b = unpack16x2(h.y, l.y);
+    return make_float4(a.x, a.y, b.x, b.y);
   }
   return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + pix_off) + ci);
 }
@@ -131,14 +131,14 @@ __global__ void __launch_bounds__(256) roi_align_rotated_kernel(const RoiKernelP
         }
         if (p.out_hi) {
           const int64_t row = ((int64_t)roi_idx * p.out_hp + bph + p.out_border) * p.out_wp + bpw + p.out_border;
-          __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
-          split_bf16(o.x, h0, l0);
-          split_bf16(o.y, h1, l1);
-          split_bf16(o.z, h2, l2);
-          split_bf16(o.w, h3, l3);
+          __half h0, l0, h1, l1, h2, l2, h3, l3;
+          split16(o.x, h0, l0);
+          split16(o.y, h1, l1);
+          split16(o.z, h2, l2);
+          split16(o.w, h3, l3);
           const int64_t off = row * p.ld_out + p.out_coff + ci * 4;
-          *reinterpret_cast<uint2*>(p.out_hi + off) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
-          *reinterpret_cast<uint2*>(p.out_lo + off) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+          *reinterpret_cast<uint2*>(p.out_hi + off) = make_uint2(pack16x2(h0, h1), pack16x2(h2, h3));
+          *reinterpret_cast<uint2*>(p.out_lo + off) = make_uint2(pack16x2(l0, l1), pack16x2(l2, l3));
         }
       }
     }
@@ -154,8 +154,8 @@ struct ImgRoiKernelParams {
   const int* n_rois_dev;
   int n_rois, ph, pw, sampling;
   float* out_f32;
-  __nv_bfloat16* out_hi;
-  __nv_bfloat16* out_lo;
+  __half* out_hi;
+  __half* out_lo;
   int out_border, ld_out;
 };
 
@@ -221,13 +221,13 @@ __global__ void __launch_bounds__(256) image_roi_align_rotated_kernel(const ImgR
     if (p.out_hi) {
       const int hp = p.ph + 2 * p.out_border, wp = p.pw + 2 * p.out_border;
       const int64_t row = ((int64_t)roi_idx * hp + bph + p.out_border) * wp + bpw + p.out_border;
-      __nv_bfloat16 h0, l0, h1, l1, h2, l2;
-      split_bf16(o0, h0, l0);
-      split_bf16(o1, h1, l1);
-      split_bf16(o2, h2, l2);
-      const __nv_bfloat16 z = __float2bfloat16_rn(0.f);
-      *reinterpret_cast<uint4*>(p.out_hi + row * p.ld_out) = make_uint4(pack_bf16x2(h0, h1), pack_bf16x2(h2, z), 0, 0);
-      *reinterpret_cast<uint4*>(p.out_lo + row * p.ld_out) = make_uint4(pack_bf16x2(l0, l1), pack_bf16x2(l2, z), 0, 0);
+      __half h0, l0, h1, l1, h2, l2;
+      split16(o0, h0, l0);
+      split16(o1, h1, l1);
+      split16(o2, h2, l2);
+      const __half z = __float2half_rn(0.f);
+      *reinterpret_cast<uint4*>(p.out_hi + row * p.ld_out) = make_uint4(pack16x2(h0, h1), pack16x2(h2, z), 0, 0);
+      *reinterpret_cast<uint4*>(p.out_lo + row * p.ld_out) = make_uint4(pack16x2(l0, l1), pack16x2(l2, z), 0, 0);
     }
   }
 }
@@ -262,7 +262,7 @@ extern "C" int glass_roi_align_rotated(const GlassRoiAlignParams* p, void* strea
   k.border = p->feat_border; k.ld = p->feat_ld; k.channels = p->channels; k.min_level = p->min_level;
   k.rois = p->rois; k.n_rois_dev = p->n_rois_dev; k.n_rois = p->n_rois;
   k.ph = p->pooled_h; k.pw = p->pooled_w; k.sampling = p->sampling_ratio;
-  k.out_f32 = p->out_f32; k.out_hi = (__nv_bfloat16*)p->out_hi; k.out_lo = (__nv_bfloat16*)p->out_lo;
+  k.out_f32 = p->out_f32; k.out_hi = (__half*)p->out_hi; k.out_lo = (__half*)p->out_lo;
   k.out_hp = p->out_hp; k.out_wp = p->out_wp; k.out_border = p->out_border; k.out_coff = p->out_coff;
   k.ld_out = p->ld_out;
   const int64_t warps = (int64_t)p->n_rois * p->pooled_h * p->pooled_w;
@@ -295,7 +295,7 @@ extern "C" int glass_image_roi_align_rotated(const GlassImageRoiAlignParams* p, 
   for (int c = 0; c < 3; ++c) { k.mean[c] = p->mean[c]; k.inv_std[c] = p->inv_std[c]; }
   k.rois = p->rois; k.n_rois_dev = p->n_rois_dev; k.n_rois = p->n_rois;
   k.ph = p->pooled_h; k.pw = p->pooled_w; k.sampling = p->sampling_ratio;
-  k.out_f32 = p->out_f32; k.out_hi = (__nv_bfloat16*)p->out_hi; k.out_lo = (__nv_bfloat16*)p->out_lo;
+  k.out_f32 = p->out_f32; k.out_hi = (__half*)p->out_hi; k.out_lo = (__half*)p->out_lo;
   k.out_border = p->out_border; k.ld_out = p->ld_out;
   const int64_t total = (int64_t)p->n_rois * p->pooled_h * p->pooled_w;
   int64_t blocks = (total + 255) / 256;

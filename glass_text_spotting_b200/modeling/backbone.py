@@ -3,7 +3,7 @@
 Mirrors detectron2's ``build_resnet_fpn_backbone`` as selected by configs/glass_pretrain.yaml:41-54
 (the reference calls it at glass/modeling/meta_arch/glass_rcnn.py:83): same ``state_dict`` names
 (SURVEY.md A.10), same outputs {"p2".."p6"} with strides 4..64, ``size_divisibility`` 32.
-Activations stay in split-bf16 padded NHWC (ops.Act) between layers; BatchNorm (eval) is folded into
+Activations stay in split-fp16 padded NHWC (ops.Act) between layers; BatchNorm (eval) is folded into
 each GEMM's epilogue scale/bias; ReLU, the bottleneck residual add and the FPN top-down
 nearest-upsample add are fused into the epilogue as well.
 """
@@ -46,7 +46,7 @@ class Workspace:
             self._acts[name] = a
         return a
 
-    def raw(self, name: str, shape, dtype=torch.bfloat16, zero: bool = False) -> torch.Tensor:
+    def raw(self, name: str, shape, dtype=torch.float16, zero: bool = False) -> torch.Tensor:
         t = self._raw.get(name)
         if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
             t = (torch.zeros if zero else torch.empty)(tuple(shape), dtype=dtype, device=self.device)
@@ -69,7 +69,7 @@ class B200ResNetFPN:
     strides = {"p2": 4, "p3": 8, "p4": 16, "p5": 32, "p6": 64}
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], prefix: str = "backbone.", device="cuda",
-                 mode: int = ops.MODE_BF16X3, pixel_mean=PIXEL_MEAN, pixel_std=PIXEL_STD):
+                 mode: int = ops.MODE_SPLIT, pixel_mean=PIXEL_MEAN, pixel_std=PIXEL_STD):
         sd = {k[len(prefix):]: v for k, v in state_dict.items() if k.startswith(prefix)}
         self.device, self.mode = device, mode
         self.pixel_mean, self.pixel_std = pixel_mean, pixel_std
@@ -159,7 +159,7 @@ class B200ResNetFPN:
             out[f"p{k}"] = pk
             prev = lat
         p5 = out["p5"]
-        p6 = ws.act("fpn.p6", p5.n, 256, p5.h // 2, p5.w // 2)
+        p6 = ws.act("fpn.p6", p5.n, 256, (p5.h + 1) // 2, (p5.w + 1) // 2)
         ops.maxpool2d(p5, (1, 1), (2, 2), (0, 0), out=p6)  # LastLevelMaxPool: k=1, s=2 subsample
         out["p6"] = p6
         return out

@@ -11,8 +11,9 @@ import torch
 
 from . import lib as _lib
 
-MODE_BF16X3 = 0   # fp32-grade split precision (parity mode; default)
-MODE_BF16 = 1     # single bf16 pass (fast mode)
+MODE_SPLIT = 0    # fp16x3 split: fp32-grade precision (parity mode; default)
+MODE_FAST = 1     # single fp16 pass (fast mode, 11-bit operands)
+ACT_SCALE = 16.0  # == kActScale in csrc/common.cuh: split planes hold ACT_SCALE * x
 
 # bench.py's per-kernel timing: when a list, every conv_gemm launch appends (start, end) CUDA events
 PROFILE = None
@@ -35,9 +36,9 @@ def round_up(x: int, m: int) -> int:
 
 
 class Act:
-    """An fp32 activation [n,c,h,w] stored as split-bf16 padded NHWC (see include/glass_b200.h).
+    """An fp32 activation [n,c,h,w] stored as split-fp16 padded NHWC (see include/glass_b200.h).
 
-    ``buf`` is one bf16 tensor [2, n, h+2b, w+2b, cp]: plane 0 = hi, plane 1 = lo.  Borders and pad
+    ``buf`` is one fp16 tensor [2, n, h+2b, w+2b, cp]: plane 0 = hi, plane 1 = lo.  Borders and pad
     channels are zero and are never written by any kernel.
     """
 
@@ -48,9 +49,9 @@ class Act:
         self.hp, self.wp = h + 2 * border, w + 2 * border
         shape = (2, n, self.hp, self.wp, self.cp)
         if buf is None:
-            buf = torch.zeros(shape, dtype=torch.bfloat16, device=device)
+            buf = torch.zeros(shape, dtype=torch.float16, device=device)
         else:
-            assert tuple(buf.shape) == shape and buf.dtype == torch.bfloat16 and buf.is_contiguous()
+            assert tuple(buf.shape) == shape and buf.dtype == torch.float16 and buf.is_contiguous()
         self.buf = buf
 
     @property
@@ -97,12 +98,12 @@ class F32Map:
 
 
 class PackedWeight:
-    """Weights of one conv / Linear packed K-major [n_p, taps*cin_p] as bf16 hi/lo, plus the folded
+    """Weights of one conv / Linear packed K-major [n_p, taps*cin_p] as fp16 hi/lo, plus the folded
     per-channel epilogue (scale, bias).  Built by ``packing.pack_conv`` / ``pack_linear``."""
 
     def __init__(self, w: torch.Tensor, scale: torch.Tensor, bias: torch.Tensor, cout: int, cin: int,
                  kh: int, kw: int, stride: Tuple[int, int], pad: Tuple[int, int], cin_p: int):
-        self.w = w  # bf16 [2, n_p, taps*cin_p]
+        self.w = w  # fp16 [2, n_p, taps*cin_p]
         self.scale, self.bias = scale, bias
         self.cout, self.cin, self.kh, self.kw = cout, cin, kh, kw
         self.stride, self.pad, self.cin_p = stride, pad, cin_p
@@ -115,7 +116,7 @@ def conv_gemm(a_hi: torch.Tensor, a_lo: Optional[torch.Tensor], rows_a: int, k_p
               out_geom: Optional[Tuple[int, int, int]] = None, ld_out: int = 0,
               out_hi: Optional[torch.Tensor] = None, out_lo: Optional[torch.Tensor] = None,
               residual: Optional[Act] = None, res_shift: int = 0, relu_pre: bool = False, relu_post: bool = False,
-              use_scale: bool = True, mode: int = MODE_BF16X3, n_store: int = 0) -> None:
+              mode: int = MODE_SPLIT, n_store: int = 0) -> None:
     """Raw launch of glass_conv_gemm.  m_geom = (imgs, h, w, border) of the M space;
     out_geom = (hp, wp, border) of the output rows (defaults to ``out``'s geometry)."""
     p = _lib.ConvGemmParams()
@@ -125,8 +126,7 @@ def conv_gemm(a_hi: torch.Tensor, a_lo: Optional[torch.Tensor], rows_a: int, k_p
         p.tap_shift[i] = s
     p.b_hi, p.b_lo, p.n, p.mode = _ptr(w.w[0]), _ptr(w.w[1]), w.n_p, mode
     p.m_imgs, p.m_h, p.m_w, p.m_border = m_geom
-    p.scale = _ptr(w.scale) if use_scale else None
-    p.bias = _ptr(w.bias) if use_scale else None
+    p.scale, p.bias = _ptr(w.scale), _ptr(w.bias)  # scale also undoes the operand pre-scales
     p.relu_pre, p.relu_post = int(relu_pre), int(relu_post)
     if out is not None:
         out_hi, out_lo = out.hi, out.lo
@@ -153,8 +153,8 @@ def conv_gemm(a_hi: torch.Tensor, a_lo: Optional[torch.Tensor], rows_a: int, k_p
 
 def conv2d(x: Act, w: PackedWeight, relu: bool = False, residual: Optional[Act] = None, res_shift: int = 0,
            relu_pre: bool = False, out: Optional[Act] = None, f32: Optional[F32Map] = None, want_act: bool = True,
-           mode: int = MODE_BF16X3, gather_buf: Optional[torch.Tensor] = None) -> Optional[Act]:
-    """conv (+ folded norm) (+ReLU) (+residual) on a split-bf16 activation.
+           mode: int = MODE_SPLIT, gather_buf: Optional[torch.Tensor] = None) -> Optional[Act]:
+    """conv (+ folded norm) (+ReLU) (+residual) on a split-fp16 activation.
 
     stride-1 'same' convs run as shifted-row implicit GEMM straight from ``x``; everything else goes
     through one tap-gather pass.  ``relu`` = ReLU after the residual add (d2 bottleneck order),
@@ -187,16 +187,16 @@ def conv2d(x: Act, w: PackedWeight, relu: bool = False, residual: Optional[Act] 
 
 
 def linear(a: torch.Tensor, w: PackedWeight, relu: bool = False, want_split: bool = True, want_f32: bool = False,
-           mode: int = MODE_BF16X3, use_scale: bool = True):
-    """y = a @ W^T (*scale + bias) for a split-bf16 matrix ``a`` [2, rows, k] (k == w.cin_p).
+           mode: int = MODE_SPLIT):
+    """y = a @ W^T (*scale + bias) for a split-fp16 matrix ``a`` [2, rows, k] (k == w.cin_p).
     Returns (split [2, rows, n_p] or None, fp32 [rows, n_p] or None)."""
     assert a.dim() == 3 and a.shape[0] == 2 and a.shape[2] == w.cin_p and a.is_contiguous()
     rows = a.shape[1]
-    o = torch.empty((2, rows, w.n_p), dtype=torch.bfloat16, device=a.device) if want_split else None
+    o = torch.empty((2, rows, w.n_p), dtype=torch.float16, device=a.device) if want_split else None
     of = torch.empty((rows, w.n_p), dtype=torch.float32, device=a.device) if want_f32 else None
     conv_gemm(a[0], a[1], rows, w.cin_p, [0], w, (1, rows, 1, 0),
               out_hi=None if o is None else o[0], out_lo=None if o is None else o[1], out_f32=of, ld_f32=w.n_p,
-              out_geom=(rows, 1, 0), ld_out=w.n_p, relu_post=relu, mode=mode, use_scale=use_scale)
+              out_geom=(rows, 1, 0), ld_out=w.n_p, relu_post=relu, mode=mode)
     return o, of
 
 
@@ -216,7 +216,7 @@ def gather_taps(x: Act, kh: int, kw: int, sh: int, sw: int, ph: int, pw: int, ho
                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """im2col of a split activation: rows [2, n*ho*wo, kh*kw*cp] (tap-major K)."""
     if out is None:
-        out = torch.empty((2, x.n * ho * wo, kh * kw * x.cp), dtype=torch.bfloat16, device=x.buf.device)
+        out = torch.empty((2, x.n * ho * wo, kh * kw * x.cp), dtype=torch.float16, device=x.buf.device)
     assert tuple(out.shape) == (2, x.n * ho * wo, kh * kw * x.cp) and out.is_contiguous()
     _lib.check(_lib.load().glass_gather_taps(_ptr(x.hi), _ptr(x.lo), x.n, x.h, x.w, x.cp, x.border, kh, kw, sh, sw,
                                              ph, pw, ho, wo, _ptr(out[0]), _ptr(out[1]), _stream()))
@@ -229,7 +229,7 @@ def stem_im2col(img: torch.Tensor, mean: Sequence[float], std: Sequence[float], 
     n, c, h, w = img.shape
     assert c == 3 and img.dtype == torch.float32 and img.is_contiguous()
     if out is None:
-        out = torch.empty((2, n * (h // 2) * (w // 2), kp), dtype=torch.bfloat16, device=img.device)
+        out = torch.empty((2, n * (h // 2) * (w // 2), kp), dtype=torch.float16, device=img.device)
     assert tuple(out.shape) == (2, n * (h // 2) * (w // 2), kp) and out.is_contiguous()
     m = (C.c_float * 3)(*[float(v) for v in mean])
     s = (C.c_float * 3)(*[1.0 / float(v) for v in std])
@@ -241,7 +241,7 @@ def roi_align_rotated(feats: List, rois: torch.Tensor, output_size: Tuple[int, i
                       scales: Sequence[float], sampling_ratio: int, min_level: int = 2,
                       out_f32: bool = True, out_split: Optional[Tuple[torch.Tensor, int, int, int, int, int]] = None,
                       n_rois_dev: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
-    """Multi-level rotated RoIAlign over fp32 maps (F32Map) or split-bf16 activations (Act).
+    """Multi-level rotated RoIAlign over fp32 maps (F32Map) or split-fp16 activations (Act).
     rois fp32 [R,6] (batch, cx, cy, w, h, angle).  Returns fp32
     [R, ph, pw, C] (NHWC order) when out_f32; out_split = (buf[2,...], hp, wp, border, coff, ld)."""
     assert rois.dtype == torch.float32 and rois.dim() == 2 and rois.shape[1] == 6 and rois.is_contiguous()

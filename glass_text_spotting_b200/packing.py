@@ -1,17 +1,32 @@
-"""Weight pre-packing: detectron2-style ``state_dict`` tensors -> the K-major split-bf16 layout the
+"""Weight pre-packing: detectron2-style ``state_dict`` tensors -> the K-major split-fp16 layout the
 tcgen05 GEMM consumes (SURVEY.md A.10 lists the key names).  Done once at load time."""
 from typing import Optional, Tuple
 
 import torch
 
-from .ops import PackedWeight, round_up
+from .ops import ACT_SCALE, PackedWeight, round_up
 
 
-def split_bf16(x: torch.Tensor) -> torch.Tensor:
-    """fp32 tensor -> bf16 [2, ...] (hi, lo) with x ~= hi + lo."""
-    hi = x.to(torch.bfloat16)
-    lo = (x - hi.float()).to(torch.bfloat16)
+def split16(x: torch.Tensor) -> torch.Tensor:
+    """fp32 tensor (already pre-scaled) -> fp16 [2, ...] (hi, lo) with x ~= hi + lo (22 mantissa bits)."""
+    x = x.float().clamp(-60000.0, 60000.0)
+    hi = x.to(torch.float16)
+    lo = (x - hi.float()).to(torch.float16)
     return torch.stack((hi, lo), 0).contiguous()
+
+
+def split_act(x: torch.Tensor) -> torch.Tensor:
+    """An activation matrix in the library's storage convention: planes hold ACT_SCALE * x."""
+    return split16(x.float() * ACT_SCALE)
+
+
+def _pack_rows(w: torch.Tensor, scale: torch.Tensor):
+    """Split a weight matrix [n, k] with a per-row power-of-two pre-scale (rows land in [256, 512) so
+    both planes stay in fp16's normal range) and fold 2^-s / ACT_SCALE into the epilogue scale."""
+    amax = w.abs().amax(dim=1).clamp_min(1e-30)
+    s = torch.floor(torch.log2(512.0 / amax)).clamp(-24, 24)
+    s = torch.where(w.abs().amax(dim=1) > 0, s, torch.zeros_like(s))
+    return split16(w * torch.exp2(s).unsqueeze(1)), scale * torch.exp2(-s) / ACT_SCALE
 
 
 def fold_bn(bn_w, bn_b, bn_mean, bn_var, eps: float = 1e-5, conv_bias: Optional[torch.Tensor] = None):
@@ -26,7 +41,7 @@ def fold_bn(bn_w, bn_b, bn_mean, bn_var, eps: float = 1e-5, conv_bias: Optional[
 def pack_conv(weight: torch.Tensor, scale: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
               stride: Tuple[int, int] = (1, 1), pad: Tuple[int, int] = (0, 0), cin_p: Optional[int] = None,
               n_align: int = 64, device="cuda") -> PackedWeight:
-    """weight fp32 [cout, cin, kh, kw] -> [2, n_p, kh*kw*cin_p] bf16 (K = tap-major, channel-minor)."""
+    """weight fp32 [cout, cin, kh, kw] -> [2, n_p, kh*kw*cin_p] fp16 (K = tap-major, channel-minor)."""
     cout, cin, kh, kw = weight.shape
     cin_p = cin_p if cin_p is not None else round_up(cin, 64)
     n_p = round_up(cout, n_align)
@@ -38,8 +53,8 @@ def pack_conv(weight: torch.Tensor, scale: Optional[torch.Tensor] = None, bias: 
         s[:cout] = scale.detach().float()
     if bias is not None:
         b[:cout] = bias.detach().float()
-    return PackedWeight(split_bf16(w.reshape(n_p, kh * kw * cin_p)).to(device), s.to(device), b.to(device), cout, cin,
-                        kh, kw, tuple(stride), tuple(pad), cin_p)
+    wp, s = _pack_rows(w.reshape(n_p, kh * kw * cin_p), s)
+    return PackedWeight(wp.to(device), s.to(device), b.to(device), cout, cin, kh, kw, tuple(stride), tuple(pad), cin_p)
 
 
 def pack_linear(weight: torch.Tensor, bias: Optional[torch.Tensor] = None, k_p: Optional[int] = None,
@@ -53,7 +68,8 @@ def pack_linear(weight: torch.Tensor, bias: Optional[torch.Tensor] = None, k_p: 
     b = torch.zeros(w.shape[0], dtype=torch.float32)
     if bias is not None:
         b[:out_f] = bias.detach().float()
-    return PackedWeight(split_bf16(w).to(device), s.to(device), b.to(device), out_f, in_f, 1, 1, (1, 1), (0, 0), k_p)
+    wp, s = _pack_rows(w, s)
+    return PackedWeight(wp.to(device), s.to(device), b.to(device), out_f, in_f, 1, 1, (1, 1), (0, 0), k_p)
 
 
 def pack_stem(weight: torch.Tensor, scale, bias, kp: int = 192, device="cuda") -> PackedWeight:
@@ -65,4 +81,5 @@ def pack_stem(weight: torch.Tensor, scale, bias, kp: int = 192, device="cuda") -
     b = torch.zeros(w.shape[0])
     s[:cout] = scale
     b[:cout] = bias
-    return PackedWeight(split_bf16(w).to(device), s.to(device), b.to(device), cout, 3, 7, 7, (2, 2), (3, 3), kp)
+    wp, s = _pack_rows(w, s)
+    return PackedWeight(wp.to(device), s.to(device), b.to(device), cout, 3, 7, 7, (2, 2), (3, 3), kp)

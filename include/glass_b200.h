@@ -15,8 +15,9 @@
  *   - return 0 on success, negative on error; glass_last_error() gives the message
  *     (thread-local).  Shapes/alignments are validated on the host before launch.
  *
- * Activation storage ("split-bf16 padded NHWC"): an fp32 tensor [N,C,H,W] is held as two
- * bf16 planes hi, lo (x ~= hi + lo, 16 mantissa bits) each laid out [N, H+2b, W+2b, Cp]
+ * Activation storage ("split-fp16 padded NHWC"): an fp32 tensor [N,C,H,W] is held as two
+ * fp16 planes hi, lo (16*x ~= hi + lo, 22 mantissa bits; the power-of-two
+ * pre-scale keeps lo out of the fp16 subnormals) each laid out [N, H+2b, W+2b, Cp]
  * (b = border of zero pixels, Cp = C rounded up to 64, pad channels zero).  The zero
  * border is the conv padding; kernels never write it.
  */
@@ -48,18 +49,18 @@ int64_t glass_launch_count(void);
  *   (fusion_modules.py:157), CNN_V1_1 (recognizer_backbone.py:77-81), BiLSTM input projections
  *   (recognizer_encoder.py:141-143), AttentionUnit.xEmbed (prediction_aster.py:250).
  * A rows are pixels of a padded NHWC tensor flattened over (img, y, x); a conv tap is a constant
- * row shift.  mode: 0 = bf16x3 split (hi*hi + hi*lo + lo*hi, fp32 accumulate in TMEM; fp32-grade),
- * 1 = single bf16 pass (fast, lower precision).
+ * row shift.  mode: 0 = fp16x3 split (hi*hi + hi*lo + lo*hi, fp32 accumulate in TMEM; fp32-grade),
+ * 1 = single fp16 pass (fast, 11-bit operands).
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
   /* A operand */
-  const void* a_hi;  /* bf16 [rows_a, k_per_tap] */
-  const void* a_lo;  /* bf16, same shape (unused when mode == 1) */
+  const void* a_hi;  /* fp16 [rows_a, k_per_tap] */
+  const void* a_lo;  /* fp16, same shape (unused when mode == 1) */
   int64_t rows_a;
   int32_t k_per_tap; /* multiple of 64 */
   int32_t ntaps;     /* 1..GLASS_MAX_TAPS */
   int32_t tap_shift[GLASS_MAX_TAPS];
-  /* B operand: packed weights [n, ntaps*k_per_tap], bf16 hi/lo */
+  /* B operand: packed weights [n, ntaps*k_per_tap], fp16 hi/lo */
   const void* b_hi;
   const void* b_lo;
   int32_t n;         /* multiple of 16; if > 256 a multiple of 128 */
@@ -71,11 +72,11 @@ typedef struct {
   const float* scale; /* [n] or NULL (=1) */
   const float* bias;  /* [n] or NULL (=0) */
   int32_t relu_pre, relu_post;
-  /* residual (optional): split bf16 planes [m_imgs, res_hp, res_wp, n]; pixel (y>>res_shift, x>>res_shift) */
+  /* residual (optional): split fp16 planes [m_imgs, res_hp, res_wp, n]; pixel (y>>res_shift, x>>res_shift) */
   const void* res_hi;
   const void* res_lo;
   int32_t res_hp, res_wp, res_border, res_shift;
-  /* outputs (any subset): split bf16 planes and/or fp32, rows laid out [m_imgs, out_hp, out_wp, ld] */
+  /* outputs (any subset): split fp16 planes and/or fp32, rows laid out [m_imgs, out_hp, out_wp, ld] */
   void* out_hi;
   void* out_lo;
   float* out_f32;
@@ -89,10 +90,10 @@ int glass_conv_gemm(const GlassConvGemmParams* p, void* stream);
 /* ------------------------------------------------------------------------------------------
  * Layout / glue kernels
  * ------------------------------------------------------------------------------------------ */
-/* fp32 NCHW [n,c,h,w] -> split-bf16 padded NHWC [n,h+2b,w+2b,cp] (interior only; border/pad channels must be 0) */
+/* fp32 NCHW [n,c,h,w] -> split-fp16 padded NHWC [n,h+2b,w+2b,cp] (interior only; border/pad channels must be 0) */
 int glass_pack_nchw(const float* src, int n, int c, int h, int w, void* dst_hi, void* dst_lo, int cp, int border,
                     void* stream);
-/* split-bf16 padded NHWC -> fp32 NCHW (hi + lo) */
+/* split-fp16 padded NHWC -> fp32 NCHW (hi + lo) */
 int glass_unpack_nchw(const void* src_hi, const void* src_lo, int n, int c, int h, int w, int cp, int border,
                       float* dst, void* stream);
 /* fp32 padded NHWC [n,h+2b,w+2b,ld] -> fp32 NCHW [n,c,h,w] */
@@ -101,7 +102,7 @@ int glass_nhwc_f32_to_nchw(const float* src, int n, int c, int h, int w, int ld,
 
 /* Stem im2col with fused (x - mean)/std (d2 GeneralizedRCNN.preprocess_image, called at
  * glass_rcnn.py:82; BasicStem conv 7x7 s2 p3): raw fp32 NCHW image [n,3,h,w] ->
- * split-bf16 rows [n*(h/2)*(w/2), kp] with k = (r*7+s)*3 + c, zero for k >= 147. */
+ * split-fp16 rows [n*(h/2)*(w/2), kp] with k = (r*7+s)*3 + c, zero for k >= 147. */
 int glass_stem_im2col(const float* img, int n, int h, int w, const float* mean, const float* inv_std,
                       void* dst_hi, void* dst_lo, int kp, void* stream);
 
@@ -111,7 +112,7 @@ int glass_gather_taps(const void* src_hi, const void* src_lo, int n, int h, int 
                       int kw, int sh, int sw, int ph, int pw, int ho, int wo, void* dst_hi, void* dst_lo,
                       void* stream);
 
-/* max_pool2d on split-bf16 padded NHWC (F.max_pool2d: BasicStem, local_feature_extraction.py:163-178). */
+/* max_pool2d on split-fp16 padded NHWC (F.max_pool2d: BasicStem, local_feature_extraction.py:163-178). */
 int glass_maxpool(const void* src_hi, const void* src_lo, int n, int h, int w, int cp, int border, int kh, int kw,
                   int sh, int sw, int ph, int pw, int ho, int wo, void* dst_hi, void* dst_lo, int dst_border,
                   void* stream);
@@ -122,16 +123,16 @@ int glass_maxpool(const void* src_hi, const void* src_lo, int n, int h, int w, i
  *   recognizers_hybrid_head.py:320 (box pooler 7x7, 5 levels, sampling 2), :550 (recognizer pooler
  *   8x32, 1 level, adaptive sampling) and :556 (image pooler 128x128, scale 1, sampling 2).
  * Feature maps are padded NHWC [n, h+2b, w+2b, ld]: either fp32 (the conv kernel's out_f32) or the
- * split-bf16 hi/lo planes of an activation (feat_is_split; value = hi + lo, same bytes per element).
+ * split-fp16 hi/lo planes of an activation (feat_is_split; value = hi + lo, same bytes per element).
  * rois: fp32 [n_rois, 6] = (batch_idx, cx, cy, w, h, angle_deg).  With num_levels > 1 the level of
  * each RoI follows d2's assign_boxes_to_levels (canonical size 224 at level 4).
- * Outputs (any subset): out_f32 [n_rois, ph, pw, c] (NHWC order) and split bf16 rows written at
+ * Outputs (any subset): out_f32 [n_rois, ph, pw, c] (NHWC order) and split fp16 rows written at
  *   row ((roi*out_hp + y + out_border)*out_wp + x + out_border), channel offset out_coff, stride ld_out.
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
   int32_t num_levels;
-  const void* feat[GLASS_MAX_LEVELS];    /* fp32 map, or the bf16 hi plane when feat_is_split */
-  const void* feat_lo[GLASS_MAX_LEVELS]; /* bf16 lo plane (feat_is_split only) */
+  const void* feat[GLASS_MAX_LEVELS];    /* fp32 map, or the fp16 hi plane when feat_is_split */
+  const void* feat_lo[GLASS_MAX_LEVELS]; /* fp16 lo plane (feat_is_split only) */
   int32_t feat_is_split;
   int32_t feat_h[GLASS_MAX_LEVELS], feat_w[GLASS_MAX_LEVELS];
   float spatial_scale[GLASS_MAX_LEVELS];
@@ -158,7 +159,7 @@ typedef struct {
   const int32_t* n_rois_dev;
   int32_t n_rois, pooled_h, pooled_w, sampling_ratio;
   float* out_f32; /* optional [n_rois, 3, ph, pw] NCHW */
-  void* out_hi;   /* optional split bf16 [n_rois, ph+2b, pw+2b, ld_out], channels 0..2 */
+  void* out_hi;   /* optional split fp16 [n_rois, ph+2b, pw+2b, ld_out], channels 0..2 */
   void* out_lo;
   int32_t out_border, ld_out;
 } GlassImageRoiAlignParams;

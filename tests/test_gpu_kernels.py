@@ -35,7 +35,7 @@ def test_pack_unpack_roundtrip(ops):
     a = ops.Act.from_nchw(x.cuda())
     assert a.cp == 128
     y = a.to_nchw().cpu()
-    assert (y - x).abs().max().item() <= 2 ** -16 * x.abs().max().item()
+    assert (y - x).abs().max().item() <= 2 ** -21 * x.abs().max().item()
     # borders and pad channels stay zero
     assert a.buf[:, :, 0].abs().max().item() == 0 and a.buf[..., 70:].abs().max().item() == 0
 
@@ -110,17 +110,17 @@ def test_conv_gemm_matches_torch_fp32(ops, case):
     assert f32.buf[:, 0].abs().max().item() == 0
 
 
-def test_conv_gemm_fast_mode_is_bf16_grade(ops):
+def test_conv_gemm_fast_mode_is_fp16_grade(ops):
     from glass_text_spotting_b200 import packing
     g = torch.Generator().manual_seed(5)
     x = torch.randn(1, 128, 16, 16, generator=g)
     wt = torch.randn(128, 128, 3, 3, generator=g) / math.sqrt(128 * 9)
     a = ops.Act.from_nchw(x.cuda())
     pw = packing.pack_conv(wt, None, None, (1, 1), (1, 1))
-    out = ops.conv2d(a, pw, mode=ops.MODE_BF16).to_nchw().cpu()
+    out = ops.conv2d(a, pw, mode=ops.MODE_FAST).to_nchw().cpu()
     ref = F.conv2d(x, wt, padding=1)
     rel = (out - ref).norm() / ref.norm()
-    assert 1e-5 < rel < 2e-2, rel
+    assert 1e-5 < rel < 3e-3, rel
 
 
 def test_fpn_upsample_residual(ops):
@@ -144,10 +144,10 @@ def test_linear_gemm(ops):
     w = torch.randn(2048, 12544, generator=g) / math.sqrt(12544)
     b = torch.randn(2048, generator=g) * 0.1
     pw = packing.pack_linear(w, b)
-    o, of = ops.linear(packing.split_bf16(a).cuda(), pw, relu=True, want_f32=True)
+    o, of = ops.linear(packing.split_act(a).cuda(), pw, relu=True, want_f32=True)
     ref = F.relu(a @ w.t() + b)
     _close(of, ref, "fc1/f32")
-    _close(o[0].float() + o[1].float(), ref, "fc1/split")
+    _close((o[0].float() + o[1].float()) / ops.ACT_SCALE, ref, "fc1/split")
 
 
 # ------------------------------------------------------------------------------ rotated RoIAlign

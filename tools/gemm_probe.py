@@ -15,11 +15,11 @@ def probe(rows, k, n, mode, taps=1, tag=""):
     w = torch.randint(-4, 5, (n, taps * k), generator=g).float()
     pw = packing.pack_linear(w, None, k_p=taps * k, n_align=16)
     pw.cin_p = k
-    a2 = packing.split_bf16(a).cuda()
+    a2 = packing.split_act(a).cuda()
     out = torch.full((rows, pw.n_p), float("nan"), device="cuda")
     shifts = list(range(taps))
     ops.conv_gemm(a2[0], a2[1], rows, k, shifts, pw, (1, rows, 1, 0), out_f32=out, ld_f32=pw.n_p,
-                  out_geom=(rows, 1, 0), mode=mode, use_scale=False)
+                  out_geom=(rows, 1, 0), mode=mode)
     torch.cuda.synchronize()
     ref = torch.zeros(rows, n)
     for t in range(taps):
