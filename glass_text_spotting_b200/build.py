@@ -17,6 +17,10 @@ NVCC_FLAGS = [
 ]
 
 
+# per-file extra flags: the decision kernels round like the fp32 CPU path (no FMA contraction)
+FILE_FLAGS = {"detect.cu": ["--fmad=false"]}
+
+
 def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
@@ -37,7 +41,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(OUT_DIR, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
         if force or _stale(obj, src, headers):
-            cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            cmd = ["nvcc"] + NVCC_FLAGS + FILE_FLAGS.get(os.path.basename(src), []) + \
+                (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, pr in procs:

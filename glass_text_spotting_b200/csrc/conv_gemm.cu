@@ -7,8 +7,8 @@
 //   B: weights packed [Cout, taps*C] K-major.
 //   D: 128 x BN fp32 accumulator in TMEM, double buffered (2 x 256 columns) so the epilogue of tile
 //      i overlaps the main loop of tile i+1.
-// Roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warp 2 = TMEM
-// allocator, warps 4..7 = epilogue (one TMEM lane quadrant each).
+// Roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warp 2 = TMEM
+// allocator, warps 4..11 = epilogue (TMEM lane quadrant = warp % 4, two warps per quadrant split the columns).
 // Precision modes: fp16x3 split (3 MMAs per k-step into the same accumulator: hi*hi, hi*lo, lo*hi)
 // gives fp32-grade results (22-bit operands, fp32 accumulate); mode 1 issues only hi*hi.
 #include <cuda.h>
@@ -23,7 +23,7 @@ static constexpr int BM = 128;
 static constexpr int BK = 64;
 static constexpr int ACC_COLS = 256;  // TMEM columns per accumulator stage
 static constexpr int A_TILE_BYTES = BM * BK * 2;
-static constexpr int NUM_THREADS = 256;
+static constexpr int NUM_THREADS = 384;  // 4 control warps + 8 epilogue warps
 static constexpr int MAX_STAGES = 8;
 
 struct GemmKernelParams {
@@ -81,7 +81,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty_bar[i], 8);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -171,11 +171,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       }
     }
   } else if (warp >= 4) {
-    // ===================================================== epilogue
-    const int q = warp - 4;  // TMEM lane quadrant == warp % 4
+    // ===================================================== epilogue (8 warps)
+    // warp e = warp-4: TMEM lane quadrant q = e & 3 (== warp % 4, the tcgen05.ld lane rule), column half
+    // e >> 2.  Each thread owns one output row of the tile and walks its half of the 16-column chunks.
+    // The residual does not depend on the MMA, so its loads run two chunks ahead (and, for the first
+    // chunks of a tile, are issued before the accumulator is even ready).
+    const int e = warp - 4;
+    const int q = e & 3;
+    const int half = e >> 2;
     const int row_in_tile = q * 32 + lane;
     const int plane = p.m_h * p.m_w;
-    const int nchunks_full = p.bn / 16;
+    const int nchunks = p.bn / 16;
+    const int c_begin = half ? (nchunks + 1) / 2 : 0;
+    const int c_end = half ? nchunks : (nchunks + 1) / 2;
+    const bool has_res = p.res_hi != nullptr;
     int local_tile = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
       const int tm = tile / p.tiles_n;
@@ -195,14 +204,31 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         res_row = ((int64_t)img * p.res_hp + (y >> p.res_shift) + p.res_border) * p.res_wp + (x >> p.res_shift) +
                   p.res_border;
       }
+      const __half* res_hi_row = p.res_hi + res_row * p.ld_out + n0;
+      const __half* res_lo_row = p.res_lo + res_row * p.ld_out + n0;
+      auto load_res = [&](int c, uint4 (&buf)[4]) {
+        if (has_res && valid && c < c_end && n0 + c * 16 < p.n_store) {
+          const uint4* rh = reinterpret_cast<const uint4*>(res_hi_row + c * 16);
+          const uint4* rl = reinterpret_cast<const uint4*>(res_lo_row + c * 16);
+          buf[0] = __ldg(rh);
+          buf[1] = __ldg(rh + 1);
+          buf[2] = __ldg(rl);
+          buf[3] = __ldg(rl + 1);
+        }
+      };
+      uint4 r_cur[4], r_nxt[4], r_nx2[4];
+      load_res(c_begin, r_cur);
+      load_res(c_begin + 1, r_nxt);
+
       const int acc = local_tile & 1;
       const uint32_t acc_phase = (uint32_t)(local_tile >> 1) & 1;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t)(acc * ACC_COLS) + ((uint32_t)(q * 32) << 16);
-      for (int c = 0; c < nchunks_full; ++c) {
+      for (int c = c_begin; c < c_end; ++c) {
         uint32_t r[16];
         tmem_ld_32x32b_x16(t_row + (uint32_t)(c * 16), r);
+        load_res(c + 2, r_nx2);
         tmem_ld_wait();
         const int n = n0 + c * 16;
         if (valid && n < p.n_store) {
@@ -227,15 +253,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
           }
-          if (p.res_hi != nullptr) {
-            const uint4* rh = reinterpret_cast<const uint4*>(p.res_hi + res_row * p.ld_out + n);
-            const uint4* rl = reinterpret_cast<const uint4*>(p.res_lo + res_row * p.ld_out + n);
+          if (has_res) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              const uint4 a = __ldg(rh + h);
-              const uint4 b = __ldg(rl + h);
-              const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
-              const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+              const uint32_t aw[4] = {r_cur[h].x, r_cur[h].y, r_cur[h].z, r_cur[h].w};
+              const uint32_t bw[4] = {r_cur[2 + h].x, r_cur[2 + h].y, r_cur[2 + h].z, r_cur[2 + h].w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float2 rv = unpack16x2(aw[j], bw[j]);
@@ -272,6 +294,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
               ol[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
             }
           }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          r_cur[j] = r_nxt[j];
+          r_nxt[j] = r_nx2[j];
         }
       }
       tcgen05_fence_before();

@@ -12,7 +12,8 @@ MAX_LEVELS = 5
 SYMBOLS = [
     "glass_last_error", "glass_abi_version", "glass_launch_count", "glass_conv_gemm", "glass_pack_nchw",
     "glass_unpack_nchw", "glass_nhwc_f32_to_nchw", "glass_stem_im2col", "glass_gather_taps", "glass_maxpool",
-    "glass_roi_align_rotated", "glass_image_roi_align_rotated",
+    "glass_roi_align_rotated", "glass_image_roi_align_rotated", "glass_rpn_topk_decode", "glass_nms_workspace_bytes",
+    "glass_nms_rotated", "glass_box_decode",
 ]
 
 
@@ -57,6 +58,26 @@ class ImageRoiAlignParams(C.Structure):
     ]
 
 
+class RpnTopkParams(C.Structure):
+    _fields_ = [
+        ("pred", C.c_void_p), ("n_img", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("ld", C.c_int32),
+        ("num_anchors", C.c_int32), ("stride", C.c_int32),
+        ("anchor_w", C.c_float * 16), ("anchor_h", C.c_float * 16), ("anchor_angle", C.c_float * 16),
+        ("weights", C.c_float * 5), ("topk", C.c_int32), ("level", C.c_int32), ("num_levels", C.c_int32),
+        ("out_boxes", C.c_void_p), ("out_scores", C.c_void_p),
+    ]
+
+
+class NmsParams(C.Structure):
+    _fields_ = [
+        ("boxes", C.c_void_p), ("scores", C.c_void_p), ("group", C.c_void_p), ("group_size", C.c_int32),
+        ("m_dev", C.c_void_p), ("n_img", C.c_int32), ("m", C.c_int32), ("img_hw", C.c_void_p),
+        ("clip", C.c_int32), ("filter_empty", C.c_int32), ("score_thresh", C.c_float), ("iou_thresh", C.c_float),
+        ("max_keep", C.c_int32), ("out_boxes", C.c_void_p), ("out_scores", C.c_void_p), ("out_index", C.c_void_p),
+        ("out_count", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+    ]
+
+
 _lib = None
 
 
@@ -83,9 +104,15 @@ def load() -> C.CDLL:
     lib.glass_maxpool.argtypes = [p, p] + [i] * 13 + [p, p, i, p]
     lib.glass_roi_align_rotated.argtypes = [C.POINTER(RoiAlignParams), p]
     lib.glass_image_roi_align_rotated.argtypes = [C.POINTER(ImageRoiAlignParams), p]
+    lib.glass_rpn_topk_decode.argtypes = [C.POINTER(RpnTopkParams), p]
+    lib.glass_nms_workspace_bytes.argtypes = [i, i]
+    lib.glass_nms_workspace_bytes.restype = C.c_int64
+    lib.glass_nms_rotated.argtypes = [C.POINTER(NmsParams), p]
+    lib.glass_box_decode.argtypes = [p, i, p, p, i, i, f, p, p, p, p]
     for name in SYMBOLS:
         fn = getattr(lib, name)
-        if name.startswith("glass_") and name not in ("glass_last_error", "glass_abi_version", "glass_launch_count"):
+        if name.startswith("glass_") and name not in ("glass_last_error", "glass_abi_version", "glass_launch_count",
+                                                        "glass_nms_workspace_bytes"):
             fn.restype = C.c_int
     _lib = lib
     return lib

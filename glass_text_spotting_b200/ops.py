@@ -296,3 +296,62 @@ def image_roi_align_rotated(img: torch.Tensor, pad_hw: Tuple[int, int], mean, st
         p.out_hi, p.out_lo, p.out_border, p.ld_out = _ptr(out_act.hi), _ptr(out_act.lo), out_act.border, out_act.cp
     _lib.check(_lib.load().glass_image_roi_align_rotated(C.byref(p), _stream()))
     return out
+
+
+# ------------------------------------------------------------------------------------------ detector decisions
+def rpn_topk_decode(pred: torch.Tensor, num_anchors: int, stride: int, cell_anchors, weights: Sequence[float],
+                    topk: int, level: int, num_levels: int, out_boxes: torch.Tensor, out_scores: torch.Tensor) -> None:
+    """pred fp32 [n,h,w,ld] (fused RPN 1x1 output); cell_anchors: list of (w, h, angle) per anchor.
+    Writes slots [level*topk, (level+1)*topk) of out_boxes [n, L*topk, 5] / out_scores [n, L*topk]."""
+    n, h, w, ld = pred.shape
+    assert pred.dtype == torch.float32 and pred.is_contiguous()
+    p = _lib.RpnTopkParams()
+    p.pred, p.n_img, p.h, p.w, p.ld, p.num_anchors, p.stride = _ptr(pred), n, h, w, ld, num_anchors, stride
+    for a, (aw, ah, aa) in enumerate(cell_anchors):
+        p.anchor_w[a], p.anchor_h[a], p.anchor_angle[a] = aw, ah, aa
+    for j in range(5):
+        p.weights[j] = float(weights[j])
+    p.topk, p.level, p.num_levels = topk, level, num_levels
+    p.out_boxes, p.out_scores = _ptr(out_boxes), _ptr(out_scores)
+    _lib.check(_lib.load().glass_rpn_topk_decode(C.byref(p), _stream()))
+
+
+def nms_rotated(boxes: torch.Tensor, scores: torch.Tensor, iou_thresh: float, max_keep: int,
+                group: Optional[torch.Tensor] = None, group_size: int = 0, m_dev: Optional[torch.Tensor] = None,
+                img_hw: Optional[torch.Tensor] = None, clip: bool = False, filter_empty: bool = False,
+                score_thresh: float = float("-inf"), workspace: Optional[torch.Tensor] = None, out=None):
+    """boxes fp32 [n,m,5], scores [n,m] -> (boxes [n,max_keep,5], scores [n,max_keep], index i32, count i32[n])."""
+    n, m, _ = boxes.shape
+    assert boxes.dtype == torch.float32 and boxes.is_contiguous() and scores.is_contiguous()
+    dev = boxes.device
+    L = _lib.load()
+    need = L.glass_nms_workspace_bytes(n, m)
+    if workspace is None:
+        workspace = torch.empty((need,), dtype=torch.uint8, device=dev)
+    if out is None:
+        out = (torch.empty((n, max_keep, 5), dtype=torch.float32, device=dev),
+               torch.empty((n, max_keep), dtype=torch.float32, device=dev),
+               torch.empty((n, max_keep), dtype=torch.int32, device=dev),
+               torch.empty((n,), dtype=torch.int32, device=dev))
+    p = _lib.NmsParams()
+    p.boxes, p.scores, p.group, p.group_size, p.m_dev = _ptr(boxes), _ptr(scores), _ptr(group), group_size, _ptr(m_dev)
+    p.n_img, p.m, p.img_hw, p.clip, p.filter_empty = n, m, _ptr(img_hw), int(clip), int(filter_empty)
+    p.score_thresh, p.iou_thresh, p.max_keep = score_thresh, iou_thresh, max_keep
+    p.out_boxes, p.out_scores, p.out_index, p.out_count = (_ptr(t) for t in out)
+    p.workspace, p.workspace_bytes = _ptr(workspace), workspace.numel()
+    _lib.check(L.glass_nms_rotated(C.byref(p), _stream()))
+    return out
+
+
+def box_decode(pred: torch.Tensor, proposals: torch.Tensor, counts: Optional[torch.Tensor], n_img: int, per_img: int,
+               weights: Sequence[float]):
+    """pred fp32 [n_img*per_img, ld>=11]; proposals fp32 [n_img*per_img, 5] -> (boxes, scores, orientations)."""
+    assert pred.dtype == torch.float32 and pred.is_contiguous() and proposals.is_contiguous()
+    dev = pred.device
+    boxes = torch.empty((n_img, per_img, 5), dtype=torch.float32, device=dev)
+    scores = torch.empty((n_img, per_img), dtype=torch.float32, device=dev)
+    orient = torch.empty((n_img, per_img, 2), dtype=torch.float32, device=dev)
+    w = (C.c_float * 5)(*[float(v) for v in weights])
+    _lib.check(_lib.load().glass_box_decode(_ptr(pred), pred.shape[1], _ptr(proposals), _ptr(counts), n_img, per_img, w,
+                                            _ptr(boxes), _ptr(scores), _ptr(orient), _stream()))
+    return boxes, scores, orient

@@ -165,6 +165,61 @@ typedef struct {
 } GlassImageRoiAlignParams;
 int glass_image_roi_align_rotated(const GlassImageRoiAlignParams* p, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Detector decision kernels (no host round trips).
+ * ------------------------------------------------------------------------------------------ */
+/* glass_rpn_topk_decode -- one FPN level of d2 RRPN inference: exact top-k of the objectness logits per
+ * image (descending, ties by anchor index), RotatedAnchorGenerator anchors for the selected cells and
+ * Box2BoxTransformRotated.apply_deltas.  replaces: RPN.predict_proposals + find_top_rrpn_proposals'
+ * per-level sort/top-k (RotatedRPN inherits them: glass/modeling/proposal_generator/rotated_rpn.py:17;
+ * configs/glass_pretrain.yaml:55-71).  pred = the RPN head's fused 1x1 output, fp32 [n_img,h,w,ld]:
+ * columns [0,A) objectness, [A,6A) deltas ordered (anchor, 5). */
+typedef struct {
+  const float* pred;
+  int32_t n_img, h, w, ld, num_anchors, stride;
+  float anchor_w[16], anchor_h[16], anchor_angle[16];
+  float weights[5];
+  int32_t topk;               /* <= 1024 */
+  int32_t level, num_levels;  /* output slot [level*topk, (level+1)*topk) */
+  float* out_boxes;           /* [n_img, num_levels*topk, 5] */
+  float* out_scores;          /* [n_img, num_levels*topk]; -inf marks an empty slot */
+} GlassRpnTopkParams;
+int glass_rpn_topk_decode(const GlassRpnTopkParams* p, void* stream);
+
+/* glass_nms_rotated -- per image: optional RotatedBoxes.clip + nonempty filter, score threshold,
+ * batched_nms_rotated (group offsets), stable descending sort, greedy rotated NMS, first max_keep kept.
+ * replaces: torch.ops.detectron2.nms_rotated via batched_nms_rotated at rotated_fast_rcnn.py:131 and in
+ * d2 find_top_rrpn_proposals.  Suppression test: iou > iou_thresh. */
+typedef struct {
+  const float* boxes;    /* [n_img, m, 5] */
+  const float* scores;   /* [n_img, m] (non-finite = invalid slot) */
+  const int32_t* group;  /* optional [n_img, m] category ids; NULL: group = index / group_size */
+  int32_t group_size;    /* 0 = one group */
+  const int32_t* m_dev;  /* optional per-image candidate count */
+  int32_t n_img, m;      /* m <= 8192 */
+  const float* img_hw;   /* [n_img, 2] (height, width), needed when clip != 0 */
+  int32_t clip, filter_empty;
+  float score_thresh;    /* keep score > score_thresh; pass -INFINITY to keep all */
+  float iou_thresh;
+  int32_t max_keep;      /* <= 128 */
+  float* out_boxes;      /* [n_img, max_keep, 5] (cleaned boxes, zero padded) */
+  float* out_scores;     /* [n_img, max_keep] */
+  int32_t* out_index;    /* [n_img, max_keep] index of the kept candidate, -1 padded */
+  int32_t* out_count;    /* [n_img] */
+  void* workspace;
+  int64_t workspace_bytes; /* >= glass_nms_workspace_bytes(n_img, m) */
+} GlassNmsParams;
+int64_t glass_nms_workspace_bytes(int n_img, int m);
+int glass_nms_rotated(const GlassNmsParams* p, void* stream);
+
+/* glass_box_decode -- RotatedFastRCNNOutputs.inference up to the score filter (rotated_fast_rcnn.py:
+ * 335-373, 480-491): apply_deltas(host_weights) on the proposals, softmax over (fg, bg), orientation
+ * (argmax, max prob), finite filter.  pred fp32 [n_img*per_img, ld]: cols 0-1 class scores, 2-6 box
+ * deltas, 7-10 orientation logits.  out_scores = P(fg) or -inf for invalid / padded rows. */
+int glass_box_decode(const float* pred, int ld, const float* proposals, const int32_t* counts, int n_img,
+                     int per_img, const float* host_weights, float* out_boxes, float* out_scores,
+                     float* out_orient, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

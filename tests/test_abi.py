@@ -57,7 +57,9 @@ def _struct_fields(name):
 
 @pytest.mark.parametrize("cname,pyname", [("GlassConvGemmParams", "ConvGemmParams"),
                                            ("GlassRoiAlignParams", "RoiAlignParams"),
-                                           ("GlassImageRoiAlignParams", "ImageRoiAlignParams")])
+                                           ("GlassImageRoiAlignParams", "ImageRoiAlignParams"),
+                                           ("GlassRpnTopkParams", "RpnTopkParams"),
+                                           ("GlassNmsParams", "NmsParams")])
 def test_ctypes_structs_match_header(cname, pyname):
     from glass_text_spotting_b200 import lib
     assert [f[0] for f in getattr(lib, pyname)._fields_] == _struct_fields(cname)
