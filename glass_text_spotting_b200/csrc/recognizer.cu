@@ -1,0 +1,568 @@
+// recognizer.cu -- the non-GEMM kernels of GLASS's recognizer head:
+//   glass_gc_attention : MultiAspectGCAttention.spatial_pool + channel_add MLP + broadcast add
+//                        (glass/modeling/fusion/fusion_modules.py:91-157), one CTA per word.
+//   glass_hmean_rows   : BiLSTMBlockV2's mean over H (recognizer_encoder.py:118-120).
+//   glass_lstm_bidir   : nn.LSTM bidirectional recurrence (recognizer_encoder.py:141-142); the input
+//                        projection x W_ih^T + b runs on the tcgen05 GEMM, this kernel owns the T sequential
+//                        steps of h W_hh^T + cell update, persistent over all steps, one CTA per
+//                        (word group, direction); W_hh^T streams from L2.
+//   glass_aster_decode : AttentionRecognitionHead.sample (prediction_aster.py:63-99, 247-302): all 26
+//                        greedy steps (additive attention, GRU cell, classifier, argmax feedback) inside one
+//                        persistent kernel, one CTA per word group -- no per-step launches or host syncs.
+//   glass_aster_finalize : the reference's batch-level early break (rows after the step at which every word
+//                        of the image has emitted class 0 stay zero).
+// Latency-bound fp32 SIMT work: weights are pre-transposed to [k][out] so a warp reads 128 contiguous
+// bytes per k, activations are broadcast from shared memory.
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "glass_b200.h"
+#include "host_util.h"
+
+namespace glass {
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------ GC attention
+// F: split-fp16 padded NHWC [K, H+2, W+2, 512] in CONCAT order (channels 0..255 local, 256..511 global).
+// The reference interleaves the two halves (X[2i] = local i, X[2i+1] = global i) and views X as 8 heads
+// of 64 channels; all weights arrive pre-permuted to concat order, where head(f) = (f % 256) / 32.
+constexpr int GC_C = 512, GC_HEADS = 8, GC_HID = 256;
+
+struct GcParams {
+  const __half* f_hi;
+  const __half* f_lo;
+  __half* y_hi;
+  __half* y_lo;
+  int h, w, border;      // spatial size of one word (8 x 32), border of both tensors
+  const float* w_mask;   // [512] per concat channel
+  float b_mask;
+  const float* w1t;      // [512][256]  (k-major)
+  const float* b1;       // [256]
+  const float* ln_g;     // [256]
+  const float* ln_b;     // [256]
+  const float* w2t;      // [256][512]
+  const float* b2;       // [512]
+};
+
+__global__ void __launch_bounds__(256) gc_attention_kernel(const GcParams p) {
+  extern __shared__ float sm[];
+  const int P = p.h * p.w;              // positions (256)
+  float* logit = sm;                    // [8][P] -> attention weights
+  float* ctx = logit + GC_HEADS * P;    // [512]
+  float* hid = ctx + GC_C;              // [256]
+  float* tvec = hid + GC_HID;           // [512]
+  __shared__ float red[2];
+  const int word = blockIdx.x;
+  const int hp = p.h + 2 * p.border, wp = p.w + 2 * p.border;
+  const int64_t base = (int64_t)word * hp * wp * GC_C;
+  const int tid = threadIdx.x;
+
+  // phase 1: mask logits, one position per thread (loops when P > blockDim)
+  for (int pos = tid; pos < P; pos += blockDim.x) {
+    const int y = pos / p.w, x = pos - y * p.w;
+    const int64_t off = base + ((int64_t)(y + p.border) * wp + x + p.border) * GC_C;
+    float m[GC_HEADS];
+#pragma unroll
+    for (int hh = 0; hh < GC_HEADS; ++hh) m[hh] = 0.f;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+#pragma unroll
+      for (int hh = 0; hh < GC_HEADS; ++hh) {
+        const int f0 = half * 256 + hh * 32;
+        float acc = 0.f;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {  // 8 channels per 16-byte vector
+          const uint4 a = __ldg(reinterpret_cast<const uint4*>(p.f_hi + off + f0) + v);
+          const uint4 b = __ldg(reinterpret_cast<const uint4*>(p.f_lo + off + f0) + v);
+          const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 xv = unpack16x2(aw[j], bw[j]);
+            acc += xv.x * __ldg(p.w_mask + f0 + v * 8 + 2 * j) + xv.y * __ldg(p.w_mask + f0 + v * 8 + 2 * j + 1);
+          }
+        }
+        m[hh] += acc;
+      }
+    }
+#pragma unroll
+    for (int hh = 0; hh < GC_HEADS; ++hh) logit[hh * P + pos] = m[hh] + p.b_mask;
+  }
+  __syncthreads();
+  // phase 2: softmax over positions, one warp per head
+  {
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int hh = warp; hh < GC_HEADS; hh += (blockDim.x >> 5)) {
+      float mx = -CUDART_INF_F;
+      for (int i = lane; i < P; i += 32) mx = fmaxf(mx, logit[hh * P + i]);
+      mx = warp_max(mx);
+      float s = 0.f;
+      for (int i = lane; i < P; i += 32) {
+        const float e = expf(logit[hh * P + i] - mx);
+        logit[hh * P + i] = e;
+        s += e;
+      }
+      s = warp_sum(s);
+      for (int i = lane; i < P; i += 32) logit[hh * P + i] /= s;
+    }
+  }
+  __syncthreads();
+  // phase 3: context per concat channel (2 channels per thread, coalesced across the warp)
+  for (int f = 2 * tid; f < GC_C; f += 2 * blockDim.x) {
+    const int hh = (f & 255) >> 5;
+    float c0 = 0.f, c1 = 0.f;
+    for (int pos = 0; pos < P; ++pos) {
+      const int y = pos / p.w, x = pos - y * p.w;
+      const int64_t off = base + ((int64_t)(y + p.border) * wp + x + p.border) * GC_C + f;
+      const float2 xv = unpack16x2(__ldg(reinterpret_cast<const uint32_t*>(p.f_hi + off)),
+                                   __ldg(reinterpret_cast<const uint32_t*>(p.f_lo + off)));
+      const float a = logit[hh * P + pos];
+      c0 += xv.x * a;
+      c1 += xv.y * a;
+    }
+    ctx[f] = c0;
+    ctx[f + 1] = c1;
+  }
+  __syncthreads();
+  // phase 4: channel_add MLP: 512 -> 256, LayerNorm(256), ReLU, 256 -> 512
+  float hv = 0.f;
+  if (tid < GC_HID) {
+    float acc = __ldg(p.b1 + tid);
+    for (int k = 0; k < GC_C; ++k) acc += __ldg(p.w1t + (int64_t)k * GC_HID + tid) * ctx[k];
+    hv = acc;
+    hid[tid] = acc;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    float s = 0.f;
+    for (int i = tid; i < GC_HID; i += 32) s += hid[i];
+    s = warp_sum(s);
+    const float mean = s / (float)GC_HID;
+    float v = 0.f;
+    for (int i = tid; i < GC_HID; i += 32) {
+      const float d = hid[i] - mean;
+      v += d * d;
+    }
+    v = warp_sum(v);
+    if (tid == 0) {
+      red[0] = mean;
+      red[1] = rsqrtf(v / (float)GC_HID + 1e-5f);
+    }
+  }
+  __syncthreads();
+  if (tid < GC_HID) {
+    const float n = (hv - red[0]) * red[1] * __ldg(p.ln_g + tid) + __ldg(p.ln_b + tid);
+    hid[tid] = fmaxf(n, 0.f);
+  }
+  __syncthreads();
+  for (int f = tid; f < GC_C; f += blockDim.x) {
+    float acc = __ldg(p.b2 + f);
+    for (int k = 0; k < GC_HID; ++k) acc += __ldg(p.w2t + (int64_t)k * GC_C + f) * hid[k];
+    tvec[f] = acc;
+  }
+  __syncthreads();
+  // phase 5: Y = F + t (broadcast over positions)
+  for (int i = tid; i < P * (GC_C / 2); i += blockDim.x) {
+    const int pos = i / (GC_C / 2), f = 2 * (i - pos * (GC_C / 2));
+    const int y = pos / p.w, x = pos - y * p.w;
+    const int64_t off = base + ((int64_t)(y + p.border) * wp + x + p.border) * GC_C + f;
+    const float2 xv = unpack16x2(__ldg(reinterpret_cast<const uint32_t*>(p.f_hi + off)),
+                                 __ldg(reinterpret_cast<const uint32_t*>(p.f_lo + off)));
+    __half h0, l0, h1, l1;
+    split16(xv.x + tvec[f], h0, l0);
+    split16(xv.y + tvec[f + 1], h1, l1);
+    *reinterpret_cast<uint32_t*>(p.y_hi + off) = pack16x2(h0, h1);
+    *reinterpret_cast<uint32_t*>(p.y_lo + off) = pack16x2(l0, l1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ mean over H
+__global__ void hmean_rows_kernel(const __half* __restrict__ shi, const __half* __restrict__ slo, int n, int h, int w,
+                                  int cp, int border, __half* __restrict__ dhi, __half* __restrict__ dlo,
+                                  float* __restrict__ df32) {
+  const int cpairs = cp / 2;
+  const int64_t total = (int64_t)n * w * cpairs;
+  const int hp = h + 2 * border, wp = w + 2 * border;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = 2 * (int)(i % cpairs);
+    const int64_t t = i / cpairs;
+    const int x = (int)(t % w);
+    const int b = (int)(t / w);
+    float s0 = 0.f, s1 = 0.f;
+    for (int y = 0; y < h; ++y) {
+      const int64_t off = (((int64_t)b * hp + y + border) * wp + x + border) * cp + c;
+      const float2 v = unpack16x2(__ldg(reinterpret_cast<const uint32_t*>(shi + off)),
+                                  __ldg(reinterpret_cast<const uint32_t*>(slo + off)));
+      s0 += v.x;
+      s1 += v.y;
+    }
+    s0 /= (float)h;
+    s1 /= (float)h;
+    const int64_t o = ((int64_t)b * w + x) * cp + c;
+    __half h0, l0, h1, l1;
+    split16(s0, h0, l0);
+    split16(s1, h1, l1);
+    *reinterpret_cast<uint32_t*>(dhi + o) = pack16x2(h0, h1);
+    *reinterpret_cast<uint32_t*>(dlo + o) = pack16x2(l0, l1);
+    if (df32) {
+      df32[o] = s0;
+      df32[o + 1] = s1;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ bidirectional LSTM
+// gates_in fp32 [n_seq*T, 2*4H]: x W_ih^T + b_ih + b_hh, forward gates in [0,4H), backward in [4H,8H);
+// PyTorch gate order (i, f, g, o).  whh_t fp32 [2][H][4H] (k-major).  Output split-fp16 rows
+// [n_seq*T, 2H] (forward | backward) + optional fp32 copy.
+constexpr int LSTM_H = 256, LSTM_G = 1024, LSTM_WPC = 4;
+
+__global__ void __launch_bounds__(1024) lstm_bidir_kernel(const float* __restrict__ gates_in,
+                                                          const float* __restrict__ whh_t, int n_seq, int T,
+                                                          __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+                                                          float* __restrict__ out_f32) {
+  __shared__ __align__(16) float h_s[LSTM_H][LSTM_WPC];   // h[k][w]
+  __shared__ float c_s[LSTM_WPC][LSTM_H];
+  __shared__ float g_s[LSTM_WPC][LSTM_G];
+  const int dir = blockIdx.y;
+  const int seq0 = blockIdx.x * LSTM_WPC;
+  const int j = threadIdx.x;  // gate row
+  const float* wt = whh_t + (int64_t)dir * LSTM_H * LSTM_G;
+  for (int i = threadIdx.x; i < LSTM_H * LSTM_WPC; i += blockDim.x) {
+    (&h_s[0][0])[i] = 0.f;
+    (&c_s[0][0])[i] = 0.f;
+  }
+  __syncthreads();
+  for (int step = 0; step < T; ++step) {
+    const int t = dir == 0 ? step : T - 1 - step;
+    float acc[LSTM_WPC];
+#pragma unroll
+    for (int w = 0; w < LSTM_WPC; ++w) {
+      const int s = seq0 + w;
+      acc[w] = s < n_seq ? __ldg(gates_in + ((int64_t)s * T + t) * (2 * LSTM_G) + dir * LSTM_G + j) : 0.f;
+    }
+#pragma unroll 8
+    for (int k = 0; k < LSTM_H; ++k) {
+      const float wv = __ldg(wt + (int64_t)k * LSTM_G + j);
+      const float4 hv = *reinterpret_cast<const float4*>(&h_s[k][0]);
+      acc[0] += wv * hv.x;
+      acc[1] += wv * hv.y;
+      acc[2] += wv * hv.z;
+      acc[3] += wv * hv.w;
+    }
+    const int gate = j >> 8;  // 0:i 1:f 2:g 3:o
+#pragma unroll
+    for (int w = 0; w < LSTM_WPC; ++w) g_s[w][j] = gate == 2 ? tanhf(acc[w]) : sigmoidf_(acc[w]);
+    __syncthreads();
+    {
+      const int w = j >> 8, u = j & 255;  // 4 words x 256 units = 1024 threads
+      const float ig = g_s[w][u], fg = g_s[w][256 + u], gg = g_s[w][512 + u], og = g_s[w][768 + u];
+      const float c = fg * c_s[w][u] + ig * gg;
+      const float hn = og * tanhf(c);
+      c_s[w][u] = c;
+      h_s[u][w] = hn;
+      const int s = seq0 + w;
+      if (s < n_seq) {
+        const int64_t o = ((int64_t)s * T + t) * (2 * LSTM_H) + dir * LSTM_H + u;
+        __half hh, hl;
+        split16(hn, hh, hl);
+        out_hi[o] = hh;
+        out_lo[o] = hl;
+        if (out_f32) out_f32[o] = hn;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------ ASTER decoder
+constexpr int DEC_D = 256, DEC_T_MAX = 32, DEC_WPC = 4, DEC_MAX_CLASSES = 128;
+
+struct AsterParams {
+  const float* x;      // [n_words, T, 256] encoder output
+  const float* xproj;  // [n_words, T, 256] xEmbed(x) (+ bias)
+  int n_words, T, steps, num_classes;
+  const float* ws_t;   // [256][256] sEmbed^T
+  const float* bs;     // [256]
+  const float* we;     // [256] wEmbed weight
+  float be;            // wEmbed bias
+  const float* emb;    // [num_classes][256]
+  const float* wih_t;  // [512][768] GRU W_ih^T (input = [emb ; context]), gate order (r, z, n)
+  const float* whh_t;  // [256][768]
+  const float* bih;    // [768]
+  const float* bhh;    // [768]
+  const float* wo_t;   // [256][num_classes] fc^T
+  const float* bo;     // [num_classes]
+  float temperature;
+  float* probs;        // [n_words, steps, num_classes]
+  float* logits;       // optional [n_words, steps, num_classes]
+  float* alphas;       // optional [n_words, steps, T]
+  int* first_eos;      // [n_words] first step whose argmax is class 0 (steps if never)
+};
+
+__global__ void __launch_bounds__(1024) aster_decode_kernel(const AsterParams p) {
+  __shared__ __align__(16) float h_s[DEC_D][DEC_WPC];        // h[k][w]
+  __shared__ __align__(16) float u_s[2 * DEC_D][DEC_WPC];    // [emb ; context][w]
+  __shared__ float sp_s[DEC_WPC][DEC_D];
+  __shared__ float al_s[DEC_WPC][DEC_T_MAX];
+  __shared__ float gi_s[DEC_WPC][3 * DEC_D];
+  __shared__ float gh_s[DEC_WPC][3 * DEC_D];
+  __shared__ float o_s[DEC_WPC][DEC_MAX_CLASSES];
+  __shared__ int y_s[DEC_WPC], eos_s[DEC_WPC];
+  const int w0 = blockIdx.x * DEC_WPC;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int T = p.T, NC = p.num_classes;
+  for (int i = tid; i < DEC_D * DEC_WPC; i += blockDim.x) (&h_s[0][0])[i] = 0.f;
+  if (tid < DEC_WPC) {
+    y_s[tid] = 0;
+    eos_s[tid] = p.steps;
+  }
+  __syncthreads();
+
+  for (int step = 0; step < p.steps; ++step) {
+    // (1) sProj = sEmbed(h)
+    if (tid < DEC_D) {
+      float acc[DEC_WPC];
+      const float b = __ldg(p.bs + tid);
+#pragma unroll
+      for (int w = 0; w < DEC_WPC; ++w) acc[w] = b;
+#pragma unroll 8
+      for (int k = 0; k < DEC_D; ++k) {
+        const float wv = __ldg(p.ws_t + k * DEC_D + tid);
+        const float4 hv = *reinterpret_cast<const float4*>(&h_s[k][0]);
+        acc[0] += wv * hv.x; acc[1] += wv * hv.y; acc[2] += wv * hv.z; acc[3] += wv * hv.w;
+      }
+#pragma unroll
+      for (int w = 0; w < DEC_WPC; ++w) sp_s[w][tid] = acc[w];
+    }
+    __syncthreads();
+    // (2) e[w][t] = we . tanh(sProj + xProj[t]) + be, one warp per (w, t)
+    for (int pair = warp; pair < DEC_WPC * T; pair += (blockDim.x >> 5)) {
+      const int w = pair / T, t = pair - w * T;
+      const int word = w0 + w;
+      float acc = 0.f;
+      if (word < p.n_words) {
+        const float* xp = p.xproj + ((int64_t)word * T + t) * DEC_D;
+        for (int a = lane; a < DEC_D; a += 32) acc += __ldg(p.we + a) * tanhf(sp_s[w][a] + __ldg(xp + a));
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) al_s[w][t] = acc + p.be;
+    }
+    __syncthreads();
+    // (3) alpha = softmax_t(e), one warp per word
+    if (warp < DEC_WPC) {
+      const float v = lane < T ? al_s[warp][lane] : -CUDART_INF_F;
+      const float mx = warp_max(v);
+      const float e = lane < T ? expf(v - mx) : 0.f;
+      const float s = warp_sum(e);
+      if (lane < T) {
+        const float a = e / s;
+        al_s[warp][lane] = a;
+        const int word = w0 + warp;
+        if (p.alphas && word < p.n_words) p.alphas[((int64_t)word * p.steps + step) * T + lane] = a;
+      }
+    }
+    __syncthreads();
+    // (4) u = [Emb[y] ; sum_t alpha_t x_t]
+    {
+      const int w = tid >> 8, k = tid & 255;  // 4 words x 256
+      const int word = w0 + w;
+      float c = 0.f;
+      if (word < p.n_words) {
+        const float* xw = p.x + (int64_t)word * T * DEC_D + k;
+        for (int t = 0; t < T; ++t) c += al_s[w][t] * __ldg(xw + (int64_t)t * DEC_D);
+      }
+      u_s[DEC_D + k][w] = c;
+      u_s[k][w] = __ldg(p.emb + (int64_t)y_s[w] * DEC_D + k);
+    }
+    __syncthreads();
+    // (5) GRU pre-activations: gi = W_ih u + b_ih (768 x 512), gh = W_hh h + b_hh (768 x 256)
+    if (tid < 3 * DEC_D) {
+      float a[DEC_WPC], b[DEC_WPC];
+      const float bi = __ldg(p.bih + tid), bh = __ldg(p.bhh + tid);
+#pragma unroll
+      for (int w = 0; w < DEC_WPC; ++w) { a[w] = bi; b[w] = bh; }
+#pragma unroll 8
+      for (int k = 0; k < 2 * DEC_D; ++k) {
+        const float wv = __ldg(p.wih_t + (int64_t)k * (3 * DEC_D) + tid);
+        const float4 uv = *reinterpret_cast<const float4*>(&u_s[k][0]);
+        a[0] += wv * uv.x; a[1] += wv * uv.y; a[2] += wv * uv.z; a[3] += wv * uv.w;
+      }
+#pragma unroll 8
+      for (int k = 0; k < DEC_D; ++k) {
+        const float wv = __ldg(p.whh_t + (int64_t)k * (3 * DEC_D) + tid);
+        const float4 hv = *reinterpret_cast<const float4*>(&h_s[k][0]);
+        b[0] += wv * hv.x; b[1] += wv * hv.y; b[2] += wv * hv.z; b[3] += wv * hv.w;
+      }
+#pragma unroll
+      for (int w = 0; w < DEC_WPC; ++w) { gi_s[w][tid] = a[w]; gh_s[w][tid] = b[w]; }
+    }
+    __syncthreads();
+    // (6) GRU cell
+    {
+      const int w = tid >> 8, k = tid & 255;
+      const float r = sigmoidf_(gi_s[w][k] + gh_s[w][k]);
+      const float z = sigmoidf_(gi_s[w][DEC_D + k] + gh_s[w][DEC_D + k]);
+      const float n = tanhf(gi_s[w][2 * DEC_D + k] + r * gh_s[w][2 * DEC_D + k]);
+      h_s[k][w] = (1.0f - z) * n + z * h_s[k][w];
+    }
+    __syncthreads();
+    // (7) classifier
+    if (tid < NC) {
+      float acc[DEC_WPC];
+      const float b = __ldg(p.bo + tid);
+#pragma unroll
+      for (int w = 0; w < DEC_WPC; ++w) acc[w] = b;
+#pragma unroll 8
+      for (int k = 0; k < DEC_D; ++k) {
+        const float wv = __ldg(p.wo_t + (int64_t)k * NC + tid);
+        const float4 hv = *reinterpret_cast<const float4*>(&h_s[k][0]);
+        acc[0] += wv * hv.x; acc[1] += wv * hv.y; acc[2] += wv * hv.z; acc[3] += wv * hv.w;
+      }
+#pragma unroll
+      for (int w = 0; w < DEC_WPC; ++w) o_s[w][tid] = acc[w] * p.temperature;
+    }
+    __syncthreads();
+    // (8) softmax + argmax (first maximal index), one warp per word
+    if (warp < DEC_WPC) {
+      const int word = w0 + warp;
+      float mx = -CUDART_INF_F;
+      int arg = 0x7fffffff;
+      for (int v = lane; v < NC; v += 32) {
+        const float o = o_s[warp][v];
+        if (o > mx) { mx = o; arg = v; }
+      }
+      for (int off = 16; off > 0; off >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, mx, off);
+        const int oa = __shfl_xor_sync(0xffffffffu, arg, off);
+        if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
+      }
+      float s = 0.f;
+      for (int v = lane; v < NC; v += 32) s += expf(o_s[warp][v] - mx);
+      s = warp_sum(s);
+      if (word < p.n_words) {
+        for (int v = lane; v < NC; v += 32) {
+          const int64_t o = ((int64_t)word * p.steps + step) * NC + v;
+          p.probs[o] = expf(o_s[warp][v] - mx) / s;
+          if (p.logits) p.logits[o] = o_s[warp][v];
+        }
+      }
+      if (lane == 0) {
+        y_s[warp] = arg;
+        if (arg == 0 && eos_s[warp] == p.steps) eos_s[warp] = step;
+      }
+    }
+    __syncthreads();
+  }
+  if (tid < DEC_WPC && w0 + tid < p.n_words) p.first_eos[w0 + tid] = eos_s[tid];
+}
+
+// rows after the image's break step are zero: break step = max over the image's words of first_eos
+__global__ void aster_finalize_kernel(float* __restrict__ probs, const int* __restrict__ first_eos,
+                                      const int* __restrict__ word_start, int n_img, int steps, int nc) {
+  const int img = blockIdx.x;
+  const int a = word_start[img], b = word_start[img + 1];
+  __shared__ int s_break;
+  if (threadIdx.x == 0) s_break = 0;
+  __syncthreads();
+  int m = 0;
+  for (int w = a + threadIdx.x; w < b; w += blockDim.x) m = max(m, first_eos[w]);
+  atomicMax(&s_break, m);
+  __syncthreads();
+  const int brk = s_break;  // == steps when some word never emitted class 0 -> nothing is cleared
+  if (brk >= steps - 1) return;
+  const int64_t per_word = (int64_t)steps * nc;
+  const int64_t tail0 = (int64_t)(brk + 1) * nc;
+  for (int w = a; w < b; ++w)
+    for (int64_t i = tail0 + threadIdx.x; i < per_word; i += blockDim.x) probs[(int64_t)w * per_word + i] = 0.f;
+}
+
+}  // namespace glass
+
+using namespace glass;
+#define STREAM reinterpret_cast<cudaStream_t>(stream)
+
+extern "C" int glass_gc_attention(const GlassGcAttentionParams* p, void* stream) {
+  GLASS_CHECK(p != nullptr && p->f_hi && p->f_lo && p->y_hi && p->y_lo, "null pointer");
+  GLASS_CHECK(p->w_mask && p->w1t && p->b1 && p->ln_g && p->ln_b && p->w2t && p->b2, "null weight pointer");
+  GLASS_CHECK(p->channels == GC_C, "channels must be 512");
+  GLASS_CHECK(p->h > 0 && p->w > 0 && p->h * p->w <= 1024, "at most 1024 positions per word");
+  if (p->n_words == 0) return 0;
+  GcParams k{};
+  k.f_hi = (const __half*)p->f_hi; k.f_lo = (const __half*)p->f_lo; k.y_hi = (__half*)p->y_hi; k.y_lo = (__half*)p->y_lo;
+  k.h = p->h; k.w = p->w; k.border = p->border;
+  k.w_mask = p->w_mask; k.b_mask = p->b_mask; k.w1t = p->w1t; k.b1 = p->b1; k.ln_g = p->ln_g; k.ln_b = p->ln_b;
+  k.w2t = p->w2t; k.b2 = p->b2;
+  const int smem = (GC_HEADS * p->h * p->w + GC_C + GC_HID + GC_C) * (int)sizeof(float);
+  gc_attention_kernel<<<p->n_words, 256, smem, STREAM>>>(k);
+  count_launch();
+  GLASS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int glass_hmean_rows(const void* src_hi, const void* src_lo, int n, int h, int w, int cp, int border,
+                                void* dst_hi, void* dst_lo, float* dst_f32, void* stream) {
+  GLASS_CHECK(src_hi && src_lo && dst_hi && dst_lo, "null pointer");
+  GLASS_CHECK(n >= 0 && h > 0 && w > 0 && cp % 2 == 0, "bad shape");
+  if (n == 0) return 0;
+  const int64_t total = (int64_t)n * w * (cp / 2);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > (int64_t)num_sms() * 16) blocks = (int64_t)num_sms() * 16;
+  hmean_rows_kernel<<<(int)blocks, 256, 0, STREAM>>>((const __half*)src_hi, (const __half*)src_lo, n, h, w, cp, border,
+                                                     (__half*)dst_hi, (__half*)dst_lo, dst_f32);
+  count_launch();
+  GLASS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int glass_lstm_bidir(const float* gates_in, const float* whh_t, int n_seq, int T, int hidden, void* out_hi,
+                                void* out_lo, float* out_f32, void* stream) {
+  GLASS_CHECK(gates_in && whh_t && out_hi && out_lo, "null pointer");
+  GLASS_CHECK(hidden == LSTM_H, "hidden size must be 256");
+  GLASS_CHECK(n_seq >= 0 && T > 0, "bad shape");
+  if (n_seq == 0) return 0;
+  dim3 grid((n_seq + LSTM_WPC - 1) / LSTM_WPC, 2);
+  lstm_bidir_kernel<<<grid, 1024, 0, STREAM>>>(gates_in, whh_t, n_seq, T, (__half*)out_hi, (__half*)out_lo, out_f32);
+  count_launch();
+  GLASS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int glass_aster_decode(const GlassAsterParams* p, void* stream) {
+  GLASS_CHECK(p != nullptr && p->x && p->xproj && p->probs && p->first_eos, "null pointer");
+  GLASS_CHECK(p->ws_t && p->bs && p->we && p->emb && p->wih_t && p->whh_t && p->bih && p->bhh && p->wo_t && p->bo,
+              "null weight pointer");
+  GLASS_CHECK(p->dim == DEC_D, "dim must be 256");
+  GLASS_CHECK(p->T >= 1 && p->T <= DEC_T_MAX, "T must be in [1,32]");
+  GLASS_CHECK(p->num_classes >= 2 && p->num_classes <= DEC_MAX_CLASSES, "num_classes must be in [2,128]");
+  GLASS_CHECK(p->steps >= 1, "steps must be positive");
+  if (p->n_words == 0) return 0;
+  AsterParams k{};
+  k.x = p->x; k.xproj = p->xproj; k.n_words = p->n_words; k.T = p->T; k.steps = p->steps; k.num_classes = p->num_classes;
+  k.ws_t = p->ws_t; k.bs = p->bs; k.we = p->we; k.be = p->be; k.emb = p->emb; k.wih_t = p->wih_t; k.whh_t = p->whh_t;
+  k.bih = p->bih; k.bhh = p->bhh; k.wo_t = p->wo_t; k.bo = p->bo; k.temperature = p->temperature;
+  k.probs = p->probs; k.logits = p->logits; k.alphas = p->alphas; k.first_eos = p->first_eos;
+  aster_decode_kernel<<<(p->n_words + DEC_WPC - 1) / DEC_WPC, 1024, 0, STREAM>>>(k);
+  count_launch();
+  GLASS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int glass_aster_finalize(float* probs, const int32_t* first_eos, const int32_t* word_start, int n_img,
+                                    int steps, int num_classes, void* stream) {
+  GLASS_CHECK(probs && first_eos && word_start, "null pointer");
+  GLASS_CHECK(n_img > 0 && steps > 0 && num_classes > 0, "bad shape");
+  aster_finalize_kernel<<<n_img, 256, 0, STREAM>>>(probs, first_eos, word_start, n_img, steps, num_classes);
+  count_launch();
+  GLASS_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -13,7 +13,8 @@ SYMBOLS = [
     "glass_last_error", "glass_abi_version", "glass_launch_count", "glass_conv_gemm", "glass_pack_nchw",
     "glass_unpack_nchw", "glass_nhwc_f32_to_nchw", "glass_stem_im2col", "glass_gather_taps", "glass_maxpool",
     "glass_roi_align_rotated", "glass_image_roi_align_rotated", "glass_rpn_topk_decode", "glass_nms_workspace_bytes",
-    "glass_nms_rotated", "glass_box_decode",
+    "glass_nms_rotated", "glass_box_decode", "glass_gc_attention", "glass_hmean_rows", "glass_lstm_bidir",
+    "glass_aster_decode", "glass_aster_finalize",
 ]
 
 
@@ -78,6 +79,25 @@ class NmsParams(C.Structure):
     ]
 
 
+class GcAttentionParams(C.Structure):
+    _fields_ = [
+        ("f_hi", C.c_void_p), ("f_lo", C.c_void_p), ("y_hi", C.c_void_p), ("y_lo", C.c_void_p),
+        ("n_words", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("border", C.c_int32), ("channels", C.c_int32),
+        ("w_mask", C.c_void_p), ("b_mask", C.c_float), ("w1t", C.c_void_p), ("b1", C.c_void_p), ("ln_g", C.c_void_p),
+        ("ln_b", C.c_void_p), ("w2t", C.c_void_p), ("b2", C.c_void_p),
+    ]
+
+
+class AsterParams(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("xproj", C.c_void_p), ("n_words", C.c_int32), ("T", C.c_int32), ("steps", C.c_int32),
+        ("num_classes", C.c_int32), ("dim", C.c_int32), ("ws_t", C.c_void_p), ("bs", C.c_void_p), ("we", C.c_void_p),
+        ("be", C.c_float), ("emb", C.c_void_p), ("wih_t", C.c_void_p), ("whh_t", C.c_void_p), ("bih", C.c_void_p),
+        ("bhh", C.c_void_p), ("wo_t", C.c_void_p), ("bo", C.c_void_p), ("temperature", C.c_float),
+        ("probs", C.c_void_p), ("logits", C.c_void_p), ("alphas", C.c_void_p), ("first_eos", C.c_void_p),
+    ]
+
+
 _lib = None
 
 
@@ -109,6 +129,11 @@ def load() -> C.CDLL:
     lib.glass_nms_workspace_bytes.restype = C.c_int64
     lib.glass_nms_rotated.argtypes = [C.POINTER(NmsParams), p]
     lib.glass_box_decode.argtypes = [p, i, p, p, i, i, f, p, p, p, p]
+    lib.glass_gc_attention.argtypes = [C.POINTER(GcAttentionParams), p]
+    lib.glass_hmean_rows.argtypes = [p, p, i, i, i, i, i, p, p, p, p]
+    lib.glass_lstm_bidir.argtypes = [p, p, i, i, i, p, p, p, p]
+    lib.glass_aster_decode.argtypes = [C.POINTER(AsterParams), p]
+    lib.glass_aster_finalize.argtypes = [p, p, p, i, i, i, p]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if name.startswith("glass_") and name not in ("glass_last_error", "glass_abi_version", "glass_launch_count",

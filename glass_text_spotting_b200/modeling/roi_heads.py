@@ -1,0 +1,263 @@
+"""MaskRotatedRecognizerHybridHead inference on B200 kernels.
+
+Mirrors glass/modeling/fusion/recognizers_hybrid_head.py (the reference's ROI head): ``forward`` eval
+branch :176-181 = ``_forward_box`` :291-339 followed by ``forward_with_given_boxes`` :571-609 ->
+``_forward_recognizer`` :513-569.  The mask branch is built but skipped at inference
+(MASK_INFERENCE False, glass/config.py:170) and is out of scope.
+State-dict names follow SURVEY.md A.10 so reference checkpoints load unchanged.
+"""
+from typing import Dict, List, Optional
+
+import torch
+
+from .. import ops, packing
+from ..ops import Act
+from .backbone import Workspace, _conv_bn
+
+
+def _bn_fold(sd, prefix):
+    return packing.fold_bn(sd[prefix + ".weight"], sd[prefix + ".bias"], sd[prefix + ".running_mean"],
+                           sd[prefix + ".running_var"])
+
+
+class B200GlassROIHeads:
+    def __init__(self, state_dict: Dict[str, torch.Tensor], prefix: str = "roi_heads.", device="cuda",
+                 mode: int = ops.MODE_SPLIT, strides=(4, 8, 16, 32, 64), box_pooler_resolution: int = 7,
+                 box_pooler_sampling_ratio: int = 2, box_reg_weights=(10.0, 10.0, 5.0, 5.0, 10.0),
+                 score_thresh: float = 0.05, nms_thresh: float = 0.35, detections_per_image: int = 100,
+                 recog_pool=(8, 32), recog_sampling_ratio: int = 0, num_text_classes: int = 97, max_word_len: int = 26,
+                 pixel_mean=(103.530, 116.280, 123.675), pixel_std=(1.0, 1.0, 1.0)):
+        sd = {k[len(prefix):]: v.detach().float().cpu() for k, v in state_dict.items() if k.startswith(prefix)}
+        self.device, self.mode = device, mode
+        self.strides, self.res, self.sampling = tuple(strides), box_pooler_resolution, box_pooler_sampling_ratio
+        self.box_reg_weights, self.score_thresh, self.nms_thresh = tuple(box_reg_weights), score_thresh, nms_thresh
+        self.max_det = detections_per_image
+        self.pool_h, self.pool_w, self.recog_sampling = recog_pool[0], recog_pool[1], recog_sampling_ratio
+        self.num_classes, self.steps = num_text_classes, max_word_len
+        self.pixel_mean, self.pixel_std = pixel_mean, pixel_std
+        self.ws = Workspace(device)
+        dev = device
+
+        # ---- box head (FastRCNNConvFCHead 2 x FC 2048; d2 flattens NCHW -> (c, ph, pw); ours is (ph, pw, c))
+        r = self.res
+        w1 = sd["box_head.fc1.weight"]
+        c = w1.shape[1] // (r * r)
+        w1 = w1.view(-1, c, r, r).permute(0, 2, 3, 1).reshape(w1.shape[0], -1)
+        self.fc1 = packing.pack_linear(w1, sd["box_head.fc1.bias"], device=dev)
+        self.fc2 = packing.pack_linear(sd["box_head.fc2.weight"], sd["box_head.fc2.bias"], device=dev)
+        wp = torch.cat((sd["box_predictor.cls_score.weight"], sd["box_predictor.bbox_pred.weight"],
+                        sd["box_predictor.orientation_pred.weight"]), 0)
+        bp = torch.cat((sd["box_predictor.cls_score.bias"], sd["box_predictor.bbox_pred.bias"],
+                        sd["box_predictor.orientation_pred.bias"]), 0)
+        assert wp.shape[0] == 11, "one foreground class (configs/glass_pretrain.yaml:79)"
+        self.predictor = packing.pack_linear(wp, bp, n_align=16, device=dev)
+
+        # ---- P2P3Fusion (fusion_modules.py:250-286): conv1(p2) + up2(conv2(p3)), no bias / norm
+        self.p2p3_conv1 = packing.pack_conv(sd["recognizer_feature_fusion.conv1.weight"], device=dev)
+        self.p2p3_conv2 = packing.pack_conv(sd["recognizer_feature_fusion.conv2.weight"], device=dev)
+
+        # ---- hybrid_net = ResNetFeatureExtractor (local_feature_extraction.py:95-188), layers [1,2,5,3]
+        hp = "hybrid_net.ConvNet."
+
+        def cb(conv, bn, stride=(1, 1), pad=(1, 1)):
+            s, b = _bn_fold(sd, hp + bn)
+            return packing.pack_conv(sd[hp + conv + ".weight"], s, b, stride, pad, device=dev)
+
+        self.h_conv0_1, self.h_conv0_2 = cb("conv0_1", "bn0_1"), cb("conv0_2", "bn0_2")
+        self.h_layers = []
+        for li, nblk in zip([1, 2, 3, 4], [1, 2, 5, 3]):
+            blocks = []
+            for b in range(nblk):
+                q = f"layer{li}.{b}."
+                blk = {"conv1": cb(q + "conv1", q + "bn1"), "conv2": cb(q + "conv2", q + "bn2"), "down": None}
+                if hp + q + "downsample.0.weight" in sd:
+                    blk["down"] = cb(q + "downsample.0", q + "downsample.1", pad=(0, 0))
+                blocks.append(blk)
+            self.h_layers.append(blocks)
+        self.h_conv1, self.h_conv2, self.h_conv3 = cb("conv1", "bn1"), cb("conv2", "bn2"), cb("conv3", "bn3")
+        self.h_conv4_1 = cb("conv4_1", "bn4_1", stride=(2, 1), pad=(0, 0))
+
+        # ---- fusion_net = MultiAspectGCAttention; channel interleave folded into the weights (concat order)
+        fp = "fusion_net."
+        xc = torch.cat((2 * torch.arange(256), 2 * torch.arange(256) + 1))   # interleaved index of concat channel f
+        wm = sd[fp + "conv_mask.weight"].view(-1)                           # [64], shared by the 8 heads
+        w1 = sd[fp + "channel_add_conv.0.weight"].view(256, 512)
+        w2 = sd[fp + "channel_add_conv.3.weight"].view(512, 256)
+        self.gc = {
+            "w_mask": wm[xc % 64].contiguous().to(dev), "b_mask": float(sd[fp + "conv_mask.bias"].item()),
+            "w1t": w1[:, xc].t().contiguous().to(dev), "b1": sd[fp + "channel_add_conv.0.bias"].to(dev),
+            "ln_g": sd[fp + "channel_add_conv.1.weight"].view(-1).contiguous().to(dev),
+            "ln_b": sd[fp + "channel_add_conv.1.bias"].view(-1).contiguous().to(dev),
+            "w2t": w2[xc, :].t().contiguous().to(dev), "b2": sd[fp + "channel_add_conv.3.bias"][xc].contiguous().to(dev),
+        }
+        self.fusion_out = packing.pack_conv(sd[fp + "out.weight"][:, xc], None, sd[fp + "out.bias"], (1, 1), (1, 1),
+                                            device=dev)
+
+        # ---- recognizer head: CNN_V1_1 -> BiLSTMBlockV2 -> ASTER_V2
+        rp = "recognizer_head."
+        sdr = {k[len(rp):]: v for k, v in sd.items() if k.startswith(rp)}
+        self.r_conv1 = _conv_bn(sdr, "backbone.conv1", (2, 1), (0, 0), dev)
+        self.r_conv2 = _conv_bn(sdr, "backbone.conv2", (1, 1), (1, 1), dev)
+        self.lstm = []
+        for l in range(2):
+            q = f"encoder.bilsm_stack.{l}."
+            wih = torch.cat((sdr[q + "rnn.weight_ih_l0"], sdr[q + "rnn.weight_ih_l0_reverse"]), 0)       # [2048, 256]
+            bias = torch.cat((sdr[q + "rnn.bias_ih_l0"] + sdr[q + "rnn.bias_hh_l0"],
+                              sdr[q + "rnn.bias_ih_l0_reverse"] + sdr[q + "rnn.bias_hh_l0_reverse"]), 0)
+            whh_t = torch.stack((sdr[q + "rnn.weight_hh_l0"].t(), sdr[q + "rnn.weight_hh_l0_reverse"].t()), 0)
+            self.lstm.append({"wih": packing.pack_linear(wih, bias, device=dev), "whh_t": whh_t.contiguous().to(dev),
+                              "linear": packing.pack_linear(sdr[q + "linear.weight"], sdr[q + "linear.bias"], device=dev)})
+        dp = "decoder.recognizer.decoder."
+        self.x_embed = packing.pack_linear(sdr[dp + "attention_unit.xEmbed.weight"], sdr[dp + "attention_unit.xEmbed.bias"],
+                                           device=dev)
+        self.dec = {
+            "ws_t": sdr[dp + "attention_unit.sEmbed.weight"].t().contiguous().to(dev),
+            "bs": sdr[dp + "attention_unit.sEmbed.bias"].to(dev),
+            "we": sdr[dp + "attention_unit.wEmbed.weight"].view(-1).contiguous().to(dev),
+            "be": float(sdr[dp + "attention_unit.wEmbed.bias"].item()),
+            "emb": sdr[dp + "tgt_embedding.weight"].contiguous().to(dev),
+            "wih_t": sdr[dp + "gru.weight_ih_l0"].t().contiguous().to(dev),
+            "whh_t": sdr[dp + "gru.weight_hh_l0"].t().contiguous().to(dev),
+            "bih": sdr[dp + "gru.bias_ih_l0"].to(dev), "bhh": sdr[dp + "gru.bias_hh_l0"].to(dev),
+            "wo_t": sdr[dp + "fc.weight"].t().contiguous().to(dev), "bo": sdr[dp + "fc.bias"].to(dev),
+            "temperature": float(sdr[dp + "temperature"].item()) if (dp + "temperature") in sdr else 1.0,
+        }
+
+    # ============================================================================================ box branch
+    def box_features(self, features: Dict[str, Act], rois: torch.Tensor) -> torch.Tensor:
+        """ROIPooler (7x7, 5 levels, sampling 2) -> split rows [2, R, 49*256] in (ph, pw, c) order (tap T6)."""
+        R = rois.shape[0]
+        r = self.res
+        pooled = self.ws.raw("box.pooled", (2, R, r * r * 256))
+        feats = [features[k] for k in ("p2", "p3", "p4", "p5", "p6")]
+        ops.roi_align_rotated(feats, rois, (r, r), [1.0 / s for s in self.strides], self.sampling, min_level=2,
+                              out_f32=False, out_split=(pooled, r, r, 0, 0, 256))
+        return pooled
+
+    def box_head(self, pooled: torch.Tensor):
+        """fc1 -> ReLU -> fc2 -> ReLU -> fused predictor.  Returns (x split [2,R,2048], pred fp32 [R,16])."""
+        x, _ = ops.linear(pooled, self.fc1, relu=True, mode=self.mode)
+        x, _ = ops.linear(x, self.fc2, relu=True, mode=self.mode)
+        _, pred = ops.linear(x, self.predictor, want_split=False, want_f32=True, mode=self.mode)
+        return x, pred
+
+    def box_inference(self, pred: torch.Tensor, proposals: torch.Tensor, counts: Optional[torch.Tensor],
+                      img_hw: torch.Tensor):
+        """RotatedFastRCNNOutputs.inference: decode, softmax, clip, score > thr, rotated NMS, top-k."""
+        n, per = proposals.shape[0], proposals.shape[1]
+        cand_b, cand_s, cand_o = ops.box_decode(pred, proposals.view(-1, 5), counts, n, per, self.box_reg_weights)
+        boxes, scores, index, count = ops.nms_rotated(cand_b, cand_s, self.nms_thresh, self.max_det, img_hw=img_hw,
+                                                      clip=True, filter_empty=False, score_thresh=self.score_thresh)
+        orient = torch.gather(cand_o, 1, index.clamp_min(0).long().unsqueeze(-1).expand(-1, -1, 2))
+        return {"pred_boxes": boxes, "scores": scores, "orientations": orient, "index": index, "count": count}
+
+    def forward_box(self, features: Dict[str, Act], proposals: torch.Tensor, counts: Optional[torch.Tensor],
+                    img_hw: torch.Tensor, taps: Optional[dict] = None):
+        n, per = proposals.shape[0], proposals.shape[1]
+        bidx = torch.arange(n, device=proposals.device, dtype=torch.float32).view(n, 1, 1).expand(n, per, 1)
+        rois = torch.cat((bidx, proposals), 2).view(-1, 6).contiguous()
+        pooled = self.box_features(features, rois)
+        x, pred = self.box_head(pooled)
+        det = self.box_inference(pred, proposals, counts, img_hw)
+        if taps is not None:
+            taps.update(box_pooled=pooled, box_head_out=x, box_pred=pred)
+        return det
+
+    # ============================================================================================ recognizer
+    def p2p3(self, features: Dict[str, Act]) -> Act:
+        p2, p3 = features["p2"], features["p3"]
+        t = self.ws.act("rec.p3conv", p3.n, 256, p3.h, p3.w)
+        ops.conv2d(p3, self.p2p3_conv2, out=t, mode=self.mode)
+        g = self.ws.act("rec.g", p2.n, 256, p2.h, p2.w)
+        ops.conv2d(p2, self.p2p3_conv1, residual=t, res_shift=1, out=g, mode=self.mode)
+        return g
+
+    def _basic_block(self, x: Act, blk, name: str) -> Act:
+        ws = self.ws
+        t = ws.act(name + ".t", x.n, blk["conv1"].cout, x.h, x.w)
+        ops.conv2d(x, blk["conv1"], relu=True, out=t, mode=self.mode)
+        res = x
+        if blk["down"] is not None:
+            res = ws.act(name + ".ds", x.n, blk["down"].cout, x.h, x.w)
+            ops.conv2d(x, blk["down"], out=res, mode=self.mode)
+        out = ws.act(name + ".out", x.n, blk["conv2"].cout, x.h, x.w)
+        ops.conv2d(t, blk["conv2"], relu=True, residual=res, out=out, mode=self.mode)
+        return out
+
+    def hybrid_net(self, crops: Act, f_out: Act, taps: Optional[dict] = None) -> None:
+        """ResNetFeatureExtractor on [K,3,128,128] crops; the [K,256,8,32] result lands in channels 0..255
+        of the fused buffer ``f_out`` (cp 512)."""
+        ws, m, k = self.ws, self.mode, crops.n
+        x = ops.conv2d(crops, self.h_conv0_1, relu=True, out=ws.act("hyb.c01", k, 16, crops.h, crops.w), mode=m)
+        x = ops.conv2d(x, self.h_conv0_2, relu=True, out=ws.act("hyb.c02", k, 32, x.h, x.w), mode=m)
+        x = ops.maxpool2d(x, (2, 2), (2, 2), (0, 0), out=ws.act("hyb.pool1", k, 32, x.h // 2, x.w // 2))
+        for b, blk in enumerate(self.h_layers[0]):
+            x = self._basic_block(x, blk, f"hyb.l1.{b}")
+        x = ops.conv2d(x, self.h_conv1, relu=True, out=ws.act("hyb.c1", k, x.c, x.h, x.w), mode=m)
+        x = ops.maxpool2d(x, (2, 2), (2, 2), (0, 0), out=ws.act("hyb.pool2", k, x.c, x.h // 2, x.w // 2))
+        for b, blk in enumerate(self.h_layers[1]):
+            x = self._basic_block(x, blk, f"hyb.l2.{b}")
+        x = ops.conv2d(x, self.h_conv2, relu=True, out=ws.act("hyb.c2", k, x.c, x.h, x.w), mode=m)
+        x = ops.maxpool2d(x, (2, 2), (2, 1), (0, 1), out=ws.act("hyb.pool3", k, x.c, x.h // 2, x.w + 1))
+        for b, blk in enumerate(self.h_layers[2]):
+            x = self._basic_block(x, blk, f"hyb.l3.{b}")
+        x = ops.conv2d(x, self.h_conv3, relu=True, out=ws.act("hyb.c3", k, x.c, x.h, x.w), mode=m)
+        for b, blk in enumerate(self.h_layers[3]):
+            x = self._basic_block(x, blk, f"hyb.l4.{b}")
+        # conv4_1: k2 s(2,1) p0 + BN + ReLU -> [K,256,8,32], written into the fused buffer's local half
+        ho, wo = (x.h - 2) // 2 + 1, x.w - 1
+        assert (ho, wo) == (f_out.h, f_out.w)
+        g = ws.raw("hyb.c41.gather", (2, k * ho * wo, 4 * x.cp))
+        ops.gather_taps(x, 2, 2, 2, 1, 0, 0, ho, wo, out=g)
+        ops.conv_gemm(g[0], g[1], g.shape[1], g.shape[2], [0], self.h_conv4_1, (k, ho, wo, 0), out_hi=f_out.hi,
+                      out_lo=f_out.lo, out_geom=(f_out.hp, f_out.wp, f_out.border), ld_out=f_out.cp, relu_post=True,
+                      mode=m)
+
+    def forward_recognizer(self, images: torch.Tensor, pad_hw, features: Dict[str, Act], rois: torch.Tensor,
+                           word_start: torch.Tensor, n_img: int, taps: Optional[dict] = None) -> torch.Tensor:
+        """rois fp32 [K,6] (batch, cx, cy, w, h, angle) of the detections of all images, grouped by image;
+        word_start int32 [n_img+1].  Returns pred_text_prob [K, 26, 97]."""
+        K = rois.shape[0]
+        ws, m = self.ws, self.mode
+        probs = torch.zeros((K, self.steps, self.num_classes), dtype=torch.float32, device=rois.device)
+        if K == 0:
+            return probs
+        ph, pw = self.pool_h, self.pool_w
+        g = self.p2p3(features)
+        fused = ws.act("rec.fused", K, 512, ph, pw)
+        ops.roi_align_rotated([g], rois, (ph, pw), [1.0 / self.strides[0]], self.recog_sampling, out_f32=False,
+                              out_split=(fused.buf, fused.hp, fused.wp, fused.border, 256, fused.cp))
+        crops = ws.act("rec.crops", K, 3, ph * 16, pw * 4)
+        ops.image_roi_align_rotated(images, pad_hw, self.pixel_mean, self.pixel_std, rois, (ph * 16, pw * 4),
+                                    self.sampling, out_act=crops)
+        self.hybrid_net(crops, fused, taps)
+        fused2 = ws.act("rec.fused2", K, 512, ph, pw)
+        ops.gc_attention(fused, fused2, K, self.gc)
+        y = ops.conv2d(fused2, self.fusion_out, out=ws.act("rec.fusion_out", K, 256, ph, pw), mode=m)
+        # CNN_V1_1
+        x1 = ops.conv2d(y, self.r_conv1, relu=True, out=ws.act("rec.cnn1", K, 256, ph // 2, pw), mode=m,
+                        gather_buf=ws.raw("rec.cnn1.gather", (2, K * (ph // 2) * pw, 2 * 256)))
+        x2 = ops.conv2d(x1, self.r_conv2, relu_pre=True, residual=x1, out=ws.act("rec.cnn2", K, 256, ph // 2, pw), mode=m)
+        # BiLSTMBlockV2
+        T = pw
+        seq = ws.raw("rec.seq0", (2, K * T, 256))
+        ops.hmean_rows(x2, K, seq)
+        enc_f32 = None
+        for l, lw in enumerate(self.lstm):
+            _, gates = ops.linear(seq, lw["wih"], want_split=False, want_f32=True, mode=m)
+            hcat = ws.raw(f"rec.lstm{l}.h", (2, K * T, 512))
+            ops.lstm_bidir(gates, lw["whh_t"], K, T, hcat)
+            seq, enc_f32 = ops.linear(hcat, lw["linear"], want_f32=(l == len(self.lstm) - 1), mode=m)
+        # ASTER decoder
+        _, xproj = ops.linear(seq, self.x_embed, want_split=False, want_f32=True, mode=m)
+        first_eos = ws.raw("rec.first_eos", (K,), torch.int32)
+        logits = alphas = None
+        if taps is not None:
+            logits = torch.zeros_like(probs)
+            alphas = torch.zeros((K, self.steps, T), dtype=torch.float32, device=rois.device)
+        ops.aster_decode(enc_f32, xproj, K, T, self.steps, self.num_classes, self.dec, probs, first_eos, logits, alphas)
+        ops.aster_finalize(probs, first_eos, word_start, n_img, self.steps, self.num_classes)
+        if taps is not None:
+            taps.update(p2p3=g, fused=fused, crops=crops, fused2=fused2, fusion_out=y, recog_cnn=x2, encoder_out=enc_f32,
+                        decoder_logits=logits, decoder_alpha=alphas, first_eos=first_eos)
+        return probs

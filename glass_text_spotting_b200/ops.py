@@ -355,3 +355,51 @@ def box_decode(pred: torch.Tensor, proposals: torch.Tensor, counts: Optional[tor
     _lib.check(_lib.load().glass_box_decode(_ptr(pred), pred.shape[1], _ptr(proposals), _ptr(counts), n_img, per_img, w,
                                             _ptr(boxes), _ptr(scores), _ptr(orient), _stream()))
     return boxes, scores, orient
+
+
+# ------------------------------------------------------------------------------------------ recognizer head
+def gc_attention(f: Act, y: Act, n_words: int, w) -> None:
+    """MultiAspectGCAttention pooling + channel_add MLP + broadcast add (concat channel order); w: dict of
+    fp32 device tensors w_mask[512], b_mask(float), w1t[512,256], b1, ln_g, ln_b, w2t[256,512], b2."""
+    assert f.cp == 512 and y.cp == 512 and (f.h, f.w, f.border) == (y.h, y.w, y.border)
+    p = _lib.GcAttentionParams()
+    p.f_hi, p.f_lo, p.y_hi, p.y_lo = _ptr(f.hi), _ptr(f.lo), _ptr(y.hi), _ptr(y.lo)
+    p.n_words, p.h, p.w, p.border, p.channels = n_words, f.h, f.w, f.border, 512
+    p.w_mask, p.b_mask = _ptr(w["w_mask"]), float(w["b_mask"])
+    p.w1t, p.b1, p.ln_g, p.ln_b, p.w2t, p.b2 = (_ptr(w[k]) for k in ("w1t", "b1", "ln_g", "ln_b", "w2t", "b2"))
+    _lib.check(_lib.load().glass_gc_attention(C.byref(p), _stream()))
+
+
+def hmean_rows(x: Act, n: int, out: torch.Tensor, out_f32: Optional[torch.Tensor] = None) -> None:
+    """mean over H: x [n,c,h,w] -> rows out [2, n*w, cp]."""
+    assert tuple(out.shape) == (2, n * x.w, x.cp)
+    _lib.check(_lib.load().glass_hmean_rows(_ptr(x.hi), _ptr(x.lo), n, x.h, x.w, x.cp, x.border, _ptr(out[0]),
+                                            _ptr(out[1]), _ptr(out_f32), _stream()))
+
+
+def lstm_bidir(gates_in: torch.Tensor, whh_t: torch.Tensor, n_seq: int, T: int, out: torch.Tensor,
+               out_f32: Optional[torch.Tensor] = None) -> None:
+    assert gates_in.dtype == torch.float32 and tuple(gates_in.shape) == (n_seq * T, 2048) and gates_in.is_contiguous()
+    assert tuple(whh_t.shape) == (2, 256, 1024) and whh_t.is_contiguous() and tuple(out.shape) == (2, n_seq * T, 512)
+    _lib.check(_lib.load().glass_lstm_bidir(_ptr(gates_in), _ptr(whh_t), n_seq, T, 256, _ptr(out[0]), _ptr(out[1]),
+                                            _ptr(out_f32), _stream()))
+
+
+def aster_decode(x: torch.Tensor, xproj: torch.Tensor, n_words: int, T: int, steps: int, num_classes: int, w,
+                 probs: torch.Tensor, first_eos: torch.Tensor, logits: Optional[torch.Tensor] = None,
+                 alphas: Optional[torch.Tensor] = None) -> None:
+    assert x.dtype == torch.float32 and x.is_contiguous() and xproj.is_contiguous()
+    p = _lib.AsterParams()
+    p.x, p.xproj, p.n_words, p.T, p.steps, p.num_classes, p.dim = _ptr(x), _ptr(xproj), n_words, T, steps, num_classes, 256
+    p.ws_t, p.bs, p.we, p.be, p.emb = _ptr(w["ws_t"]), _ptr(w["bs"]), _ptr(w["we"]), float(w["be"]), _ptr(w["emb"])
+    p.wih_t, p.whh_t, p.bih, p.bhh = _ptr(w["wih_t"]), _ptr(w["whh_t"]), _ptr(w["bih"]), _ptr(w["bhh"])
+    p.wo_t, p.bo, p.temperature = _ptr(w["wo_t"]), _ptr(w["bo"]), float(w["temperature"])
+    p.probs, p.logits, p.alphas, p.first_eos = _ptr(probs), _ptr(logits), _ptr(alphas), _ptr(first_eos)
+    _lib.check(_lib.load().glass_aster_decode(C.byref(p), _stream()))
+
+
+def aster_finalize(probs: torch.Tensor, first_eos: torch.Tensor, word_start: torch.Tensor, n_img: int, steps: int,
+                   num_classes: int) -> None:
+    assert word_start.dtype == torch.int32 and word_start.numel() == n_img + 1
+    _lib.check(_lib.load().glass_aster_finalize(_ptr(probs), _ptr(first_eos), _ptr(word_start), n_img, steps,
+                                                num_classes, _stream()))

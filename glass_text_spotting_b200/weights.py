@@ -54,3 +54,109 @@ def random_backbone_state_dict(seed: int = 0, prefix: str = "backbone.") -> Dict
         sd[f"{prefix}fpn_output{k}.weight"] = _xavier(g, 256, 256, 3, 3)
         _bn(sd, f"{prefix}fpn_output{k}.norm", 256, g)
     return sd
+
+
+def _kaiming_u(g, *shape):
+    fan_in = 1
+    for s in shape[1:]:
+        fan_in *= s
+    b = 1.0 / math.sqrt(fan_in)
+    return (torch.rand(*shape, generator=g) * 2 - 1) * b
+
+
+def _linear(sd, prefix, g, out_f, in_f, std=None, bias=True):
+    sd[prefix + ".weight"] = (torch.randn(out_f, in_f, generator=g) * std) if std else _kaiming_u(g, out_f, in_f)
+    if bias:
+        sd[prefix + ".bias"] = torch.zeros(out_f) if std else _kaiming_u(g, out_f, in_f)[:, 0].clone()
+
+
+def random_state_dict(seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Full GLASS (glass_pretrain.yaml) state_dict with random weights; every BatchNorm keeps activations O(1)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = random_backbone_state_dict(seed)
+    # RPN head (normal 0.01; a larger std on the predictors gives a non-degenerate ranking)
+    p = "proposal_generator.rpn_head."
+    sd[p + "conv.weight"] = torch.randn(256, 256, 3, 3, generator=g) * 0.02
+    sd[p + "conv.bias"] = torch.zeros(256)
+    sd[p + "objectness_logits.weight"] = torch.randn(12, 256, 1, 1, generator=g) * 0.05
+    sd[p + "objectness_logits.bias"] = torch.zeros(12)
+    sd[p + "anchor_deltas.weight"] = torch.randn(60, 256, 1, 1, generator=g) * 0.02
+    sd[p + "anchor_deltas.bias"] = torch.zeros(60)
+    r = "roi_heads."
+    sd[r + "box_head.fc1.weight"] = _xavier(g, 2048, 12544, 1, 1).view(2048, 12544)
+    sd[r + "box_head.fc1.bias"] = torch.zeros(2048)
+    sd[r + "box_head.fc2.weight"] = _xavier(g, 2048, 2048, 1, 1).view(2048, 2048)
+    sd[r + "box_head.fc2.bias"] = torch.zeros(2048)
+    # foreground-biased classifier so that a realistic number of words survives the 0.05 threshold
+    sd[r + "box_predictor.cls_score.weight"] = torch.randn(2, 2048, generator=g) * 0.01
+    sd[r + "box_predictor.cls_score.bias"] = torch.tensor([0.5, -0.5])
+    sd[r + "box_predictor.bbox_pred.weight"] = torch.randn(5, 2048, generator=g) * 0.001
+    sd[r + "box_predictor.bbox_pred.bias"] = torch.zeros(5)
+    sd[r + "box_predictor.orientation_pred.weight"] = torch.randn(4, 2048, generator=g) * 0.01
+    sd[r + "box_predictor.orientation_pred.bias"] = torch.zeros(4)
+    sd[r + "recognizer_feature_fusion.conv1.weight"] = _msra(g, 256, 256, 1, 1)
+    sd[r + "recognizer_feature_fusion.conv2.weight"] = _msra(g, 256, 256, 1, 1)
+    # hybrid_net (ResNetFeatureExtractor, layers [1,2,5,3], 3 -> 256)
+    h = r + "hybrid_net.ConvNet."
+
+    def conv_bn(cname, bname, cout, cin, k, gain=1.0):
+        sd[h + cname + ".weight"] = _msra(g, cout, cin, *k)
+        _bn(sd, h + bname, cout, g, gain)
+
+    conv_bn("conv0_1", "bn0_1", 16, 3, (3, 3))
+    sd[h + "conv0_1.weight"] /= 50.0  # raw pixel scale
+    conv_bn("conv0_2", "bn0_2", 32, 16, (3, 3))
+    inpl = 32
+    for li, (planes, nblk) in enumerate(zip([64, 128, 256, 256], [1, 2, 5, 3]), start=1):
+        for b in range(nblk):
+            q = f"layer{li}.{b}."
+            conv_bn(q + "conv1", q + "bn1", planes, inpl, (3, 3))
+            conv_bn(q + "conv2", q + "bn2", planes, planes, (3, 3), 0.5)
+            if inpl != planes:
+                conv_bn(q + "downsample.0", q + "downsample.1", planes, inpl, (1, 1), 0.7)
+            inpl = planes
+        if li <= 3:
+            conv_bn(f"conv{li}", f"bn{li}", planes, planes, (3, 3))
+    conv_bn("conv4_1", "bn4_1", 256, 256, (2, 2))
+    # fusion_net (MultiAspectGCAttention)
+    f = r + "fusion_net."
+    sd[f + "conv_mask.weight"] = _kaiming_u(g, 1, 64, 1, 1)
+    sd[f + "conv_mask.bias"] = torch.zeros(1)
+    sd[f + "channel_add_conv.0.weight"] = _kaiming_u(g, 256, 512, 1, 1)
+    sd[f + "channel_add_conv.0.bias"] = torch.zeros(256)
+    sd[f + "channel_add_conv.1.weight"] = torch.ones(256, 1, 1)
+    sd[f + "channel_add_conv.1.bias"] = torch.zeros(256, 1, 1)
+    sd[f + "channel_add_conv.3.weight"] = _kaiming_u(g, 512, 256, 1, 1)
+    sd[f + "channel_add_conv.3.bias"] = torch.zeros(512)
+    sd[f + "out.weight"] = _kaiming_u(g, 256, 512, 3, 3)
+    sd[f + "out.bias"] = torch.zeros(256)
+    # recognizer head
+    q = r + "recognizer_head."
+    sd[q + "backbone.conv1.weight"] = _msra(g, 256, 256, 2, 1)
+    _bn(sd, q + "backbone.conv1.norm", 256, g)
+    sd[q + "backbone.conv2.weight"] = _msra(g, 256, 256, 3, 3)
+    _bn(sd, q + "backbone.conv2.norm", 256, g)
+    for l in range(2):
+        e = q + f"encoder.bilsm_stack.{l}."
+        for suf in ("", "_reverse"):
+            sd[e + "rnn.weight_ih_l0" + suf] = _kaiming_u(g, 1024, 256)
+            sd[e + "rnn.weight_hh_l0" + suf] = _kaiming_u(g, 1024, 256)
+            sd[e + "rnn.bias_ih_l0" + suf] = torch.zeros(1024)
+            sd[e + "rnn.bias_hh_l0" + suf] = torch.zeros(1024)
+        sd[e + "linear.weight"] = _kaiming_u(g, 256, 512)
+        sd[e + "linear.bias"] = torch.zeros(256)
+    d = q + "decoder.recognizer.decoder."
+    for nm in ("sEmbed", "xEmbed"):
+        sd[d + f"attention_unit.{nm}.weight"] = _kaiming_u(g, 256, 256)
+        sd[d + f"attention_unit.{nm}.bias"] = torch.zeros(256)
+    sd[d + "attention_unit.wEmbed.weight"] = _kaiming_u(g, 1, 256)
+    sd[d + "attention_unit.wEmbed.bias"] = torch.zeros(1)
+    sd[d + "tgt_embedding.weight"] = torch.randn(97, 256, generator=g)
+    sd[d + "gru.weight_ih_l0"] = _kaiming_u(g, 768, 512)
+    sd[d + "gru.weight_hh_l0"] = _kaiming_u(g, 768, 256)
+    sd[d + "gru.bias_ih_l0"] = torch.zeros(768)
+    sd[d + "gru.bias_hh_l0"] = torch.zeros(768)
+    sd[d + "fc.weight"] = _kaiming_u(g, 97, 256)
+    sd[d + "fc.bias"] = torch.zeros(97)
+    sd[d + "temperature"] = torch.ones(1)
+    return sd

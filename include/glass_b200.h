@@ -220,6 +220,74 @@ int glass_box_decode(const float* pred, int ld, const float* proposals, const in
                      int per_img, const float* host_weights, float* out_boxes, float* out_scores,
                      float* out_orient, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Recognizer-head kernels.
+ * ------------------------------------------------------------------------------------------ */
+/* glass_gc_attention -- MultiAspectGCAttention up to (not including) its 3x3 output conv
+ * (glass/modeling/fusion/fusion_modules.py:91-127 spatial_pool, :129-156 channel_add): per word, 8-head
+ * softmax-pooled global context over the h*w positions, 512->256->LayerNorm->ReLU->512 MLP, broadcast add.
+ * f / y: split-fp16 padded NHWC [n_words, h+2b, w+2b, 512] in CONCAT channel order (0..255 local,
+ * 256..511 global); the reference's channel interleave (`order`, :50-53) is folded into the weights:
+ * w_mask[f], w1t[k=f][256], w2t[k][f], b2[f] are given in concat order. */
+typedef struct {
+  const void* f_hi;
+  const void* f_lo;
+  void* y_hi;
+  void* y_lo;
+  int32_t n_words, h, w, border, channels;
+  const float* w_mask; /* [512] */
+  float b_mask;
+  const float* w1t;    /* [512][256] */
+  const float* b1;     /* [256] */
+  const float* ln_g;   /* [256] */
+  const float* ln_b;   /* [256] */
+  const float* w2t;    /* [256][512] */
+  const float* b2;     /* [512] */
+} GlassGcAttentionParams;
+int glass_gc_attention(const GlassGcAttentionParams* p, void* stream);
+
+/* mean over H of a split activation [n,h+2b,w+2b,cp] -> rows [n*w, cp] (split fp16 + optional fp32):
+ * BiLSTMBlockV2.forward's feats.mean(dim=2) (recognizer_encoder.py:118-120). */
+int glass_hmean_rows(const void* src_hi, const void* src_lo, int n, int h, int w, int cp, int border, void* dst_hi,
+                     void* dst_lo, float* dst_f32, void* stream);
+
+/* nn.LSTM(bidirectional) recurrence (recognizer_encoder.py:141-142).  gates_in fp32 [n_seq*T, 8*hidden] =
+ * x W_ih^T + b_ih + b_hh (forward gates | backward gates, order i,f,g,o); whh_t fp32 [2][hidden][4*hidden].
+ * Output rows [n_seq*T, 2*hidden] (forward | backward) as split fp16 (+ optional fp32). hidden must be 256. */
+int glass_lstm_bidir(const float* gates_in, const float* whh_t, int n_seq, int T, int hidden, void* out_hi,
+                     void* out_lo, float* out_f32, void* stream);
+
+/* glass_aster_decode -- AttentionRecognitionHead.sample (prediction_aster.py:63-99; DecoderUnit :291-302,
+ * AttentionUnit :247-266): greedy additive-attention GRU decoding, all steps in one persistent kernel.
+ * Weights are transposed to [in][out].  probs = softmax outputs (pred_text_prob); logits = pre-softmax tap.
+ * first_eos[w] = first step whose argmax is class 0, or `steps`. */
+typedef struct {
+  const float* x;      /* [n_words, T, dim] encoder output */
+  const float* xproj;  /* [n_words, T, dim] xEmbed(x) */
+  int32_t n_words, T, steps, num_classes, dim;
+  const float* ws_t;   /* [dim][dim] */
+  const float* bs;
+  const float* we;     /* [dim] */
+  float be;
+  const float* emb;    /* [num_classes][dim] */
+  const float* wih_t;  /* [2*dim][3*dim], GRU input = [embedding ; context], gates (r,z,n) */
+  const float* whh_t;  /* [dim][3*dim] */
+  const float* bih;
+  const float* bhh;
+  const float* wo_t;   /* [dim][num_classes] */
+  const float* bo;
+  float temperature;
+  float* probs;        /* [n_words, steps, num_classes] */
+  float* logits;       /* optional */
+  float* alphas;       /* optional [n_words, steps, T] */
+  int32_t* first_eos;  /* [n_words] */
+} GlassAsterParams;
+int glass_aster_decode(const GlassAsterParams* p, void* stream);
+/* The reference's batch-level early break (prediction_aster.py:91-93): zero the rows after the step at which
+ * every word of an image has emitted class 0.  word_start: int32 [n_img+1] prefix offsets of each image's words. */
+int glass_aster_finalize(float* probs, const int32_t* first_eos, const int32_t* word_start, int n_img, int steps,
+                         int num_classes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -59,7 +59,9 @@ def _struct_fields(name):
                                            ("GlassRoiAlignParams", "RoiAlignParams"),
                                            ("GlassImageRoiAlignParams", "ImageRoiAlignParams"),
                                            ("GlassRpnTopkParams", "RpnTopkParams"),
-                                           ("GlassNmsParams", "NmsParams")])
+                                           ("GlassNmsParams", "NmsParams"),
+                                           ("GlassGcAttentionParams", "GcAttentionParams"),
+                                           ("GlassAsterParams", "AsterParams")])
 def test_ctypes_structs_match_header(cname, pyname):
     from glass_text_spotting_b200 import lib
     assert [f[0] for f in getattr(lib, pyname)._fields_] == _struct_fields(cname)
