@@ -20,10 +20,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
+    # BASELINE.json configs[3]: the configuration the images/sec metric is quoted on
+    "full_bs4": dict(batch=4, h=1024, w=1024, full=True,
+                     desc="full GLASS inference (backbone+RPN+rotated RoI+global-local recognizer), bs=4/GPU, "
+                          "1024x1024 synthetic (BASELINE.json configs[3])"),
     # BASELINE.json configs[1]
-    "backbone_bs8": dict(batch=8, h=1024, w=1024,
+    "backbone_bs8": dict(batch=8, h=1024, w=1024, full=False,
                          desc="ResNet-50+FPN backbone only, bs=8/GPU, 1024x1024 synthetic (BASELINE.json configs[1])"),
 }
+CPU_WORD_CAP = 16  # the CPU arm decodes at most this many words per image (bounded sample)
 
 
 def _peaks():
@@ -83,53 +88,68 @@ class ClockSampler:
 
 
 # ============================================================================================ CPU (reference) arm
-def cpu_backbone_sample(wl, repeats: int):
-    """The oracle's ResNet-50+FPN (CPU restatement of the detectron2 path) on ONE 1024x1024 image per
-    repeat -- a bounded sample of the bs=8 workload.  Returns (images/s, cores, sample description)."""
+def _cpu_runner(wl):
+    """Returns (callable running ONE image through the reference's CPU path, sample description)."""
     import torch
-    from oracle import nets  # test infrastructure; allowed here only as the timed CPU baseline
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     g = torch.Generator().manual_seed(0)
-    net = nets.ResNetFPN().eval()
-    x = torch.randint(0, 256, (1, 3, wl["h"], wl["w"]), generator=g).float() - 110.0
-    with torch.no_grad():
-        net(x)  # warm-up
-        t0 = time.perf_counter()
-        for _ in range(repeats):
-            net(x)
-        dt = time.perf_counter() - t0
-    return repeats / dt, torch.get_num_threads(), f"{repeats} x 1 image 1024x1024 through oracle.nets.ResNetFPN (fp32, torch CPU)"
+    if not wl["full"]:
+        from oracle import nets  # test infrastructure; allowed here only as the timed CPU baseline
+        net = nets.ResNetFPN().eval()
+        x = torch.randint(0, 256, (1, 3, wl["h"], wl["w"]), generator=g).float() - 110.0
+
+        def run():
+            with torch.no_grad():
+                net(x)
+        return run, "1 image 1024x1024 through the oracle's ResNet-50+FPN (fp32, torch CPU)"
+    from glass_text_spotting_b200 import weights
+    from oracle import model as om
+    o = om.GlassOracle(om.HotPathConfig(max_detections_override=CPU_WORD_CAP))
+    o.load_state_dict(weights.random_state_dict(0), strict=False)
+    img = torch.randint(0, 256, (3, wl["h"], wl["w"]), generator=g).float()
+    last = {}
+
+    def run():
+        with torch.no_grad():
+            r = o.inference([{"image": img}])
+        last["k"] = int(r[0]["instances"]["pred_boxes"].shape[0])
+    return run, (f"1 image 1024x1024 through the oracle's full GLASS inference (CPU restatement of the detectron2 "
+                 f"path, fp32 torch CPU), recognizer capped at {CPU_WORD_CAP} words/image (the GPU arm decodes all)")
+
+
+def cpu_sample(wl, repeats: int):
+    import torch
+    run, desc = _cpu_runner(wl)
+    run()  # warm-up
+    t0 = time.perf_counter()
+    for _ in range(repeats):
+        run()
+    dt = time.perf_counter() - t0
+    return repeats / dt, torch.get_num_threads(), f"{repeats} x {desc}"
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    wl = WORKLOADS[args.workload]
     import torch
-    from oracle import nets
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    g = torch.Generator().manual_seed(0)
-    net = nets.ResNetFPN().eval()
-    x = torch.randint(0, 256, (1, 3, wl["h"], wl["w"]), generator=g).float() - 110.0
-    with torch.no_grad():
-        for _ in range(max(1, min(args.warmup, 2))):
-            net(x)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            net(x)
-        dt = time.perf_counter() - t0
+    wl = WORKLOADS[args.workload]
+    run, desc = _cpu_runner(wl)
+    for _ in range(max(1, min(args.warmup, 1))):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run()
+    dt = time.perf_counter() - t0
     ips = args.steps / dt
-    sample = "each step = 1 image 1024x1024 (bounded sample of the bs=8 batch) through the oracle's ResNet-50+FPN"
     print(json.dumps({
         "impl": "reference", "metric": "images/sec @1024x1024", "value": ips, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["desc"]},
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": sample},
+                         "sample": "each step = " + desc},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -140,6 +160,7 @@ def run_b200(args):
     import torch.distributed as dist
     from glass_text_spotting_b200 import lib, ops, weights
     from glass_text_spotting_b200.modeling.backbone import B200ResNetFPN
+    from glass_text_spotting_b200.modeling.glass_rcnn import B200GlassRCNN
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -149,75 +170,100 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     wl = WORKLOADS[args.workload]
     B, H, W = wl["batch"], wl["h"], wl["w"]
+    full = wl["full"]
     L = lib.load()
     mode = ops.MODE_FAST if args.fast else ops.MODE_SPLIT
+    stream = torch.cuda.current_stream()
 
-    model = B200ResNetFPN(weights.random_backbone_state_dict(0), mode=mode)
     g = torch.Generator().manual_seed(1000 + rank)
     host = [torch.randint(0, 256, (B, 3, H, W), generator=g).float().pin_memory() for _ in range(2)]
     dev = [h.cuda() for h in host]
-    stream = torch.cuda.current_stream()
+    dbuf = [torch.empty_like(d) for d in dev]
+    img_hw = torch.tensor([[H, W]] * B, dtype=torch.float32, device="cuda")
+    words = []
+
+    if full:
+        model = B200GlassRCNN(weights.random_state_dict(0), mode=mode)
+        gathered = None
+
+        def step(images):
+            """One pass of the hot path over one batch, ending in the packed per-image detection records and
+            (N > 1) the single all-gather of those records."""
+            nonlocal gathered
+            det, probs, counts, starts = model.forward_device(images, img_hw)
+            rec = model.pack_detections(det, probs, counts, starts)
+            words.append(sum(counts))
+            if world > 1:
+                if gathered is None:
+                    gathered = torch.empty((world,) + tuple(rec.shape), dtype=rec.dtype, device=rec.device)
+                dist.all_gather_into_tensor(gathered, rec)
+                return gathered
+            return rec
+        conv_flops = None
+    else:
+        model = B200ResNetFPN(weights.random_backbone_state_dict(0), mode=mode)
+
+        def step(images):
+            out = model(images)
+            return torch.cat([out[k].hi.float().abs().mean().view(1) for k in ["p2", "p3", "p4", "p5", "p6"]] +
+                             [out["p6"].buf.float().view(-1)])
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def checksum(out):
-        return torch.stack([out[k].hi.float().abs().mean() for k in ["p2", "p3", "p4", "p5", "p6"]])
-
-    # ---- warm-up (also allocates the workspace once)
+    # ---- warm-up (also allocates every workspace buffer once)
     for i in range(max(args.warmup, 3)):
-        model(dev[i % 2])
+        step(dev[i % 2])
     barrier()
 
     # ---- timed: inputs resident in HBM
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    words.clear()
     launches0 = L.glass_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
     for i in range(args.steps):
-        model(dev[i % 2])
+        step(dev[i % 2])
     e1.record(stream)
     barrier()
     t_dev = e0.elapsed_time(e1) / 1e3
     launches = L.glass_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
+    words_per_step = sum(words) / max(len(words), 1)
 
-    # ---- e2e: host buffers, H2D inside the timed region, D2H of the step's result
-    dbuf = [torch.empty_like(d) for d in dev]
-    res_host = torch.empty((5,), dtype=torch.float32).pin_memory()
-    p6_host = None
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # ---- e2e: host buffers; H2D of the batch and D2H of the step's result inside the timed region
+    res_host = None
     for i in range(2):
         dbuf[i % 2].copy_(host[i % 2], non_blocking=True)
-        model(dbuf[i % 2])
+        step(dbuf[i % 2])
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     f0.record(stream)
-    d2h_bytes = 0
     for i in range(args.steps):
         dbuf[i % 2].copy_(host[i % 2], non_blocking=True)
-        out = model(dbuf[i % 2])
-        res_host.copy_(checksum(out), non_blocking=True)
-        p6 = out["p6"].buf
-        if p6_host is None:
-            p6_host = torch.empty(p6.shape, dtype=p6.dtype).pin_memory()
-        p6_host.copy_(p6, non_blocking=True)
-        d2h_bytes = res_host.numel() * 4 + p6_host.numel() * 2
+        res = step(dbuf[i % 2])
+        if res_host is None:
+            res_host = torch.empty(res.shape, dtype=res.dtype).pin_memory()
+        res_host.copy_(res, non_blocking=True)
     f1.record(stream)
     barrier()
     t_e2e = f0.elapsed_time(f1) / 1e3
+    d2h_bytes = res_host.numel() * res_host.element_size()
 
     # ---- per-kernel profile pass: CUDA events around every launch of the dominant kernel (conv GEMM)
     ops.PROFILE = []
-    for i in range(2):
-        model(dev[i % 2])
+    nprof = 2
+    for i in range(nprof):
+        step(dev[i % 2])
     torch.cuda.synchronize()
-    gemm_ms = sum(a.elapsed_time(b) for a, b in ops.PROFILE) / 2
-    n_gemm = len(ops.PROFILE) // 2
+    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in ops.PROFILE) / nprof
+    gemm_flops = sum(f for _, _, f in ops.PROFILE) / nprof
+    n_gemm = len(ops.PROFILE) // nprof
     ops.PROFILE = None
 
     times = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device="cuda")
@@ -227,35 +273,40 @@ def run_b200(args):
 
     if rank == 0:
         peaks, peak_src = _peaks()
-        flops_img = B200ResNetFPN.flops_per_image(H, W)
-        flops_step = flops_img * B
         peak = peaks["bf16_tflops_sustained"]
-        achieved = flops_step / (gemm_ms / 1e3) / 1e12
+        achieved = gemm_flops / (gemm_ms / 1e3) / 1e12
+        cfg = {"workload": wl["desc"], "global_batch": world * B, "parallelism": f"image-sharded x{world}",
+               "l2": "inputs rotated between 2 batches; per-step working set (GBs of activations) >> 126 MB L2",
+               "weights": "random init (seeded), BatchNorm folded",
+               "kb_per_chunk": ops.KB_PER_CHUNK or 1}
+        if full:
+            cfg["words_per_step"] = words_per_step
+            cfg["collective"] = "one NCCL all-gather of packed detection records per step" if world > 1 else "none (N=1)"
         out = {
             "metric": "images/sec @1024x1024", "value": world * B * args.steps / t_dev, "unit": "images/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "fp16 (single pass)" if args.fast else "fp16x3 split (22-bit operands, fp32 accumulate; 3 tcgen05 MMAs per product)",
-            "data": "synthetic",
-            "config": {"workload": wl["desc"], "global_batch": world * B, "parallelism": f"image-sharded x{world}",
-                       "l2": "inputs rotated between 2 batches; per-step working set (~10 GB of activations) >> 126 MB L2",
-                       "weights": "random init (seeded), BatchNorm folded"},
+            "vs_baseline": None,
+            "dtype": "fp16 (single tcgen05 pass)" if args.fast else
+                     "fp16x3 split (22-bit operands, 3 tcgen05 MMAs per product, chunked fp32 RN accumulation)",
+            "data": "synthetic", "config": cfg,
             "e2e": {"value": world * B * args.steps / t_e2e, "unit": "images/s",
                     "h2d_bytes_per_step": B * 3 * H * W * 4, "d2h_bytes_per_step": d2h_bytes,
-                    "note": "pinned host batch -> H2D -> B200ResNetFPN.forward -> D2H of p6 + per-level checksums"},
+                    "note": "pinned host batch -> H2D -> hot path -> D2H of the step's result "
+                            + ("(packed detection records)" if full else "(p6 + per-level checksums)")},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": None,
-                         "kernel": "conv_gemm_kernel<SPLIT> (tcgen05 implicit GEMM)",
+                         "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM), all launches of one step",
                          "launches_per_step": n_gemm, "kernel_ms_per_step": gemm_ms,
                          "kernel_share_of_step": gemm_ms / (1e3 * t_dev / args.steps),
-                         "algorithmic_flops_per_step": flops_step,
-                         "issued_mma_flops_per_step": flops_step * (1 if args.fast else 3),
+                         "algorithmic_flops_per_step": gemm_flops,
+                         "issued_mma_flops_per_step": gemm_flops * (1 if args.fast else 3),
                          "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src})"},
         }
         if world == 1 and not args.no_cpu:
-            v, cores, sample = cpu_backbone_sample(wl, repeats=3)
+            v, cores, sample = cpu_sample(wl, repeats=1 if full else 3)
             out["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}
         print(json.dumps(out))
     if world > 1:
@@ -268,8 +319,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="backbone_bs8", choices=sorted(WORKLOADS))
-    ap.add_argument("--fast", action="store_true", help="single-pass bf16 (NOT the parity precision)")
+    ap.add_argument("--workload", default="full_bs4", choices=sorted(WORKLOADS))
+    ap.add_argument("--fast", action="store_true", help="single-pass fp16 (NOT the parity precision)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

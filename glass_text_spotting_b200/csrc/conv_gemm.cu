@@ -5,8 +5,11 @@
 //      constant row shift, so each k-block is ONE 2-D TMA box (64 channels x 128 pixels) at row
 //      m0 + shift -- image borders are real zero pixels in memory, tensor edges are TMA OOB zeros.
 //   B: weights packed [Cout, taps*C] K-major.
-//   D: 128 x BN fp32 accumulator in TMEM, double buffered (2 x 256 columns) so the epilogue of tile
-//      i overlaps the main loop of tile i+1.
+//   D: 128 x BN fp32 partial sums in TMEM, double buffered (2 x 256 columns).  The tensor core's
+//      accumulator TRUNCATES (round-toward-zero, measured: error grows linearly with the chain length,
+//      tools/accuracy_probe.py), so a chain is cut every kb_per_chunk k-blocks: the MMA warp switches
+//      to the other TMEM buffer and the epilogue warps drain the finished chunk into fp32 registers
+//      with round-to-nearest adds (Ootomo & Yokota's "accumulate outside the tensor core").
 // Roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warp 2 = TMEM
 // allocator, warps 4..11 = epilogue (TMEM lane quadrant = warp % 4, two warps per quadrant split the columns).
 // Precision modes: fp16x3 split (3 MMAs per k-step into the same accumulator: hi*hi, hi*lo, lo*hi)
@@ -25,6 +28,7 @@ static constexpr int ACC_COLS = 256;  // TMEM columns per accumulator stage
 static constexpr int A_TILE_BYTES = BM * BK * 2;
 static constexpr int NUM_THREADS = 384;  // 4 control warps + 8 epilogue warps
 static constexpr int MAX_STAGES = 8;
+static constexpr int MAX_CHUNKS_PER_WARP = 8;  // 256 columns / 16 per chunk / 2 column halves
 
 struct GemmKernelParams {
   int64_t rows_m;
@@ -32,6 +36,7 @@ struct GemmKernelParams {
   int32_t kblocks_per_tap, ntaps;
   int32_t tap_shift[GLASS_MAX_TAPS];
   int32_t num_stages, stage_bytes, b_tile_bytes;
+  int32_t kb_per_chunk;  // k-blocks accumulated inside the tensor core before a drain to registers
   int32_t m_h, m_w, m_border;
   const float* scale;
   const float* bias;
@@ -93,6 +98,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
+  // Register re-balancing between the warpgroups (the launch gives every thread 168): the control
+  // warpgroup needs few registers, the two epilogue warpgroups hold the whole 128 x BN fp32 tile.
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  }
+
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0) {
@@ -133,14 +144,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       const uint32_t idesc = umma_idesc_f16_f32(BM, p.bn);
       int stage = 0;
       uint32_t phase = 0;
-      int local_tile = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
-        const int acc = local_tile & 1;
-        const uint32_t acc_phase = (uint32_t)(local_tile >> 1) & 1;
-        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
-        tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
+      uint32_t chunk = 0;  // running chunk counter of this CTA: TMEM buffer = chunk & 1
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        uint32_t d_tmem = 0;
         for (int kb = 0; kb < kblocks; ++kb) {
+          const int kin = kb % p.kb_per_chunk;  // position inside the accumulation chunk
+          if (kin == 0) {
+            // a new chunk starts from zero in the other TMEM buffer once the epilogue has drained it
+            const uint32_t buf = chunk & 1u;
+            mbar_wait(&tmem_empty_bar[buf], ((chunk >> 1) & 1u) ^ 1u);
+            tcgen05_fence_after();
+            d_tmem = tmem_base + buf * (uint32_t)ACC_COLS;
+          }
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
           const uint32_t s = smem_u32(smem + (size_t)stage * p.stage_bytes);
@@ -148,7 +163,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t koff = (uint64_t)(k * 2);  // 32 bytes >> 4
-            const uint32_t acc_flag = (kb > 0 || k > 0) ? 1u : 0u;
+            const uint32_t acc_flag = (kin > 0 || k > 0) ? 1u : 0u;
             if (SPLIT) {
               const uint64_t da_lo = umma_smem_desc_sw128(s + A_TILE_BYTES);
               const uint64_t db_hi = umma_smem_desc_sw128(s + 2 * A_TILE_BYTES);
@@ -162,7 +177,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             }
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-          if (kb == kblocks - 1) umma_commit(&tmem_full_bar[acc]);
+          if (kin == p.kb_per_chunk - 1 || kb == kblocks - 1) {
+            umma_commit(&tmem_full_bar[chunk & 1u]);  // chunk complete -> epilogue drains it
+            ++chunk;
+          }
           if (++stage == p.num_stages) {
             stage = 0;
             phase ^= 1;
@@ -171,6 +189,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       }
     }
   } else if (warp >= 4) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     // ===================================================== epilogue (8 warps)
     // warp e = warp-4: TMEM lane quadrant q = e & 3 (== warp % 4, the tcgen05.ld lane rule), column half
     // e >> 2.  Each thread owns one output row of the tile and walks its half of the 16-column chunks.
@@ -185,8 +204,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     const int c_begin = half ? (nchunks + 1) / 2 : 0;
     const int c_end = half ? nchunks : (nchunks + 1) / 2;
     const bool has_res = p.res_hi != nullptr;
-    int local_tile = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
+    const int chunks_per_tile = (kblocks + p.kb_per_chunk - 1) / p.kb_per_chunk;
+    uint32_t chunk = 0;  // mirrors the MMA warp's running chunk counter
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int tm = tile / p.tiles_n;
       const int tn = tile - tm * p.tiles_n;
       const int n0 = tn * p.bn;
@@ -216,94 +236,113 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           buf[3] = __ldg(rl + 1);
         }
       };
-      uint4 r_cur[4], r_nxt[4], r_nx2[4];
-      load_res(c_begin, r_cur);
-      load_res(c_begin + 1, r_nxt);
+      uint4 r_cur[4], r_nxt[4];
+      load_res(c_begin, r_cur);  // issued before the accumulator is ready
 
-      const int acc = local_tile & 1;
-      const uint32_t acc_phase = (uint32_t)(local_tile >> 1) & 1;
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
-      tcgen05_fence_after();
-      const uint32_t t_row = tmem_base + (uint32_t)(acc * ACC_COLS) + ((uint32_t)(q * 32) << 16);
-      for (int c = c_begin; c < c_end; ++c) {
-        uint32_t r[16];
-        tmem_ld_32x32b_x16(t_row + (uint32_t)(c * 16), r);
-        load_res(c + 2, r_nx2);
-        tmem_ld_wait();
-        const int n = n0 + c * 16;
-        if (valid && n < p.n_store) {
-          float v[16];
+      // ---- drain every accumulation chunk of this tile from TMEM into fp32 registers (round-to-nearest
+      // adds): the tensor core's own accumulator truncates, so chains are kept to kb_per_chunk k-blocks.
+      float accv[MAX_CHUNKS_PER_WARP][16];
+      const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+      for (int g = 0; g < chunks_per_tile; ++g, ++chunk) {
+        const uint32_t buf = chunk & 1u;
+        mbar_wait(&tmem_full_bar[buf], (chunk >> 1) & 1u);
+        tcgen05_fence_after();
+        const uint32_t t_row = tmem_base + buf * (uint32_t)ACC_COLS + lane_sel;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-          if (p.scale != nullptr) {
+        for (int ci = 0; ci < MAX_CHUNKS_PER_WARP; ++ci) {
+          if (c_begin + ci < c_end) {
+            uint32_t r[16];
+            tmem_ld_32x32b_x16(t_row + (uint32_t)((c_begin + ci) * 16), r);
+            tmem_ld_wait();
+            if (g == 0) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + n + j));
-              v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
+              for (int j = 0; j < 16; ++j) accv[ci][j] = __uint_as_float(r[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) accv[ci][j] += __uint_as_float(r[j]);
             }
           }
-          if (p.bias != nullptr) {
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+      }
+
+      // ---- final math + stores from registers
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
-              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+      for (int ci = 0; ci < MAX_CHUNKS_PER_WARP; ++ci) {
+        const int c = c_begin + ci;
+        if (c < c_end) {
+          load_res(c + 1, r_nxt);
+          const int n = n0 + c * 16;
+          if (valid && n < p.n_store) {
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = accv[ci][j];
+            if (p.scale != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + n + j));
+                v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
+              }
             }
-          }
-          if (p.relu_pre) {
+            if (p.bias != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-          }
-          if (has_res) {
+              for (int j = 0; j < 16; j += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+              }
+            }
+            if (p.relu_pre) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const uint32_t aw[4] = {r_cur[h].x, r_cur[h].y, r_cur[h].z, r_cur[h].w};
-              const uint32_t bw[4] = {r_cur[2 + h].x, r_cur[2 + h].y, r_cur[2 + h].z, r_cur[2 + h].w};
+              for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (has_res) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 rv = unpack16x2(aw[j], bw[j]);
-                v[h * 8 + 2 * j] += rv.x;
-                v[h * 8 + 2 * j + 1] += rv.y;
+              for (int h = 0; h < 2; ++h) {
+                const uint32_t aw[4] = {r_cur[h].x, r_cur[h].y, r_cur[h].z, r_cur[h].w};
+                const uint32_t bw[4] = {r_cur[2 + h].x, r_cur[2 + h].y, r_cur[2 + h].z, r_cur[2 + h].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 rv = unpack16x2(aw[j], bw[j]);
+                  v[h * 8 + 2 * j] += rv.x;
+                  v[h * 8 + 2 * j + 1] += rv.y;
+                }
+              }
+            }
+            if (p.relu_post) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (p.out_f32 != nullptr) {
+              float4* o = reinterpret_cast<float4*>(p.out_f32 + out_row * p.ld_f32 + n);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            if (p.out_hi != nullptr) {
+              uint32_t hw[8], lw[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                __half h0, l0, h1, l1;
+                split16(v[2 * j], h0, l0);
+                split16(v[2 * j + 1], h1, l1);
+                hw[j] = pack16x2(h0, h1);
+                lw[j] = pack16x2(l0, l1);
+              }
+              uint4* oh = reinterpret_cast<uint4*>(p.out_hi + out_row * p.ld_out + n);
+              oh[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+              oh[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+              if (p.out_lo != nullptr) {
+                uint4* ol = reinterpret_cast<uint4*>(p.out_lo + out_row * p.ld_out + n);
+                ol[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                ol[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
               }
             }
           }
-          if (p.relu_post) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-          }
-          if (p.out_f32 != nullptr) {
-            float4* o = reinterpret_cast<float4*>(p.out_f32 + out_row * p.ld_f32 + n);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          }
-          if (p.out_hi != nullptr) {
-            uint32_t hw[8], lw[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              __half h0, l0, h1, l1;
-              split16(v[2 * j], h0, l0);
-              split16(v[2 * j + 1], h1, l1);
-              hw[j] = pack16x2(h0, h1);
-              lw[j] = pack16x2(l0, l1);
-            }
-            uint4* oh = reinterpret_cast<uint4*>(p.out_hi + out_row * p.ld_out + n);
-            oh[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-            oh[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
-            if (p.out_lo != nullptr) {
-              uint4* ol = reinterpret_cast<uint4*>(p.out_lo + out_row * p.ld_out + n);
-              ol[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-              ol[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
-            }
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          r_cur[j] = r_nxt[j];
-          r_nxt[j] = r_nx2[j];
+          for (int j = 0; j < 4; ++j) r_cur[j] = r_nxt[j];
         }
       }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
     }
   }
 
@@ -393,6 +432,7 @@ extern "C" int glass_conv_gemm(const GlassConvGemmParams* p, void* stream_v) {
   k.num_stages = smem_budget / k.stage_bytes;
   if (k.num_stages > MAX_STAGES) k.num_stages = MAX_STAGES;
   GLASS_CHECK(k.num_stages >= 2, "stage too large");
+  k.kb_per_chunk = p->kb_per_chunk > 0 ? p->kb_per_chunk : 1;
   k.m_h = p->m_h; k.m_w = p->m_w; k.m_border = p->m_border;
   k.scale = p->scale; k.bias = p->bias;
   k.relu_pre = p->relu_pre; k.relu_post = p->relu_post;

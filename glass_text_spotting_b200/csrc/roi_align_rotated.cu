@@ -75,9 +75,10 @@ __global__ void __launch_bounds__(256) roi_align_rotated_kernel(const RoiKernelP
 
     const float cw = bx * s - 0.5f, chh = by * s - 0.5f;
     const float rw = bw * s, rh = bh * s;
+    // the sampling coordinates must round like the fp32 CPU path (a 1-ulp difference in cos/sin moves a
+    // sample by ~1e-5 px, visible on high-frequency inputs): correctly rounded sin/cos via double
     const float theta = (float)((double)ba * 3.14159265358979323846 / 180.0);
-    float sn, cs;
-    sincosf(theta, &sn, &cs);
+    const float sn = (float)sin((double)theta), cs = (float)cos((double)theta);
     const float bsh = rh / (float)p.ph, bsw = rw / (float)p.pw;
     const int gh = p.sampling > 0 ? p.sampling : (int)ceilf(rh / (float)p.ph);
     const int gw = p.sampling > 0 ? p.sampling : (int)ceilf(rw / (float)p.pw);
@@ -173,8 +174,7 @@ __global__ void __launch_bounds__(256) image_roi_align_rotated_kernel(const ImgR
     const float cw = roi[1] - 0.5f, chh = roi[2] - 0.5f;
     const float rw = roi[3], rh = roi[4];
     const float theta = (float)((double)roi[5] * 3.14159265358979323846 / 180.0);
-    float sn, cs;
-    sincosf(theta, &sn, &cs);
+    const float sn = (float)sin((double)theta), cs = (float)cos((double)theta);
     const float bsh = rh / (float)p.ph, bsw = rw / (float)p.pw;
     const int gh = p.sampling > 0 ? p.sampling : (int)ceilf(rh / (float)p.ph);
     const int gw = p.sampling > 0 ? p.sampling : (int)ceilf(rw / (float)p.pw);

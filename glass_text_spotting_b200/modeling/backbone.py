@@ -127,6 +127,12 @@ class B200ResNetFPN:
         ops.conv2d(t2, c3, relu=True, residual=sc, out=out, mode=self.mode)
         return out
 
+    def run_stage(self, stage: str, x: Act) -> Act:
+        """One residual stage ("res2".."res5") from a given input activation (stage-wise parity tests)."""
+        for b, blk in enumerate(self.blocks[stage]):
+            x = self._bottleneck(x, blk, f"{stage}.{b}")
+        return x
+
     def bottom_up(self, images: torch.Tensor) -> Dict[str, Act]:
         n, _, h, w = images.shape
         assert h % 32 == 0 and w % 32 == 0, "pad the batch to size_divisibility first (ImageList.from_tensors)"

@@ -61,14 +61,37 @@ class B200GlassRCNN:
         return self.roi_heads.forward_recognizer(images, tuple(images.shape[-2:]), feats, rois_t, word_start, n, taps), starts
 
     @torch.no_grad()
+    def forward_device(self, images: torch.Tensor, img_hw: torch.Tensor, taps: Optional[dict] = None):
+        """Whole hot path on device tensors (images: RAW fp32 [n,3,H,W] padded to /32 with the pixel mean).
+        One host sync (the detection counts size the recognizer's batch)."""
+        feats, det = self.detect(images, img_hw, taps)
+        counts_host = det["count"].cpu().tolist()
+        probs, starts = self.recognize(images, feats, det, counts_host, taps)
+        return det, probs, counts_host, starts
+
+    def pack_detections(self, det, probs: torch.Tensor, counts_host: List[int], starts: List[int]) -> torch.Tensor:
+        """Fixed-size record per image for the end-of-loop all-gather:
+        [n, max_det, 1 + 5 + 1 + 1 + 2 + steps*classes] = (valid, box, score, class, orientation, text probs)."""
+        n, m = det["pred_boxes"].shape[0], det["pred_boxes"].shape[1]
+        tp = self.roi_heads.steps * self.roi_heads.num_classes
+        rec = torch.zeros((n, m, 10 + tp), dtype=torch.float32, device=probs.device)
+        for i, c in enumerate(counts_host):
+            if c == 0:
+                continue
+            rec[i, :c, 0] = 1.0
+            rec[i, :c, 1:6] = det["pred_boxes"][i, :c]
+            rec[i, :c, 6] = det["scores"][i, :c]
+            rec[i, :c, 8:10] = det["orientations"][i, :c]
+            rec[i, :c, 10:] = probs[starts[i]: starts[i + 1]].reshape(c, tp)
+        return rec
+
+    @torch.no_grad()
     def inference(self, batched_inputs: List[dict], detected_instances=None, do_postprocess: bool = True,
                   taps: Optional[dict] = None):
         assert detected_instances is None, "given-box inference is not on the benchmarked path"
         il = self.preprocess_image(batched_inputs)
         img_hw = torch.tensor(il.image_sizes, dtype=torch.float32, device=self.device)
-        feats, det = self.detect(il.tensor, img_hw, taps)
-        counts_host = det["count"].cpu().tolist()  # the one host sync of the forward: K sizes the recognizer
-        probs, starts = self.recognize(il.tensor, feats, det, counts_host, taps)
+        det, probs, counts_host, starts = self.forward_device(il.tensor, img_hw, taps)
         results = []
         for i, c in enumerate(counts_host):
             inst = Instances(il.image_sizes[i],

@@ -15,7 +15,10 @@ MODE_SPLIT = 0    # fp16x3 split: fp32-grade precision (parity mode; default)
 MODE_FAST = 1     # single fp16 pass (fast mode, 11-bit operands)
 ACT_SCALE = 16.0  # == kActScale in csrc/common.cuh: split planes hold ACT_SCALE * x
 
-# bench.py's per-kernel timing: when a list, every conv_gemm launch appends (start, end) CUDA events
+# k-blocks (64 wide) accumulated inside the tensor core between drains to fp32 registers (0 = library default)
+KB_PER_CHUNK = int(__import__("os").environ.get("GLASS_KB_PER_CHUNK", "0"))
+
+# bench.py's per-kernel timing: when a list, every conv_gemm launch appends (start event, end event, algorithmic FLOPs)
 PROFILE = None
 
 
@@ -141,12 +144,14 @@ def conv_gemm(a_hi: torch.Tensor, a_lo: Optional[torch.Tensor], rows_a: int, k_p
     p.out_hi, p.out_lo, p.out_f32 = _ptr(out_hi), _ptr(out_lo), _ptr(out_f32)
     p.out_hp, p.out_wp, p.out_border = out_geom
     p.ld_out, p.ld_f32, p.n_store = ld_out, ld_f32, n_store
+    p.kb_per_chunk = KB_PER_CHUNK
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(torch.cuda.current_stream())
         _lib.check(_lib.load().glass_conv_gemm(C.byref(p), _stream()))
         e1.record(torch.cuda.current_stream())
-        PROFILE.append((e0, e1))
+        m_valid = p.m_imgs * (p.m_h - 2 * p.m_border) * (p.m_w - 2 * p.m_border)
+        PROFILE.append((e0, e1, 2.0 * m_valid * w.cout * w.cin * w.kh * w.kw))  # algorithmic FLOPs of this launch
         return
     _lib.check(_lib.load().glass_conv_gemm(C.byref(p), _stream()))
 

@@ -84,6 +84,8 @@ typedef struct {
   int32_t ld_out;     /* channel stride of out_hi/out_lo/res rows (>= n) */
   int32_t ld_f32;     /* channel stride of out_f32 rows (>= n) */
   int32_t n_store;    /* columns actually stored (<= n); 0 = n */
+  int32_t kb_per_chunk; /* 64-wide k-blocks summed inside the tensor core between drains; 0 = default (1:
+                           every k-block, fp32-SGEMM-grade; larger = faster, error grows with the chain) */
 } GlassConvGemmParams;
 int glass_conv_gemm(const GlassConvGemmParams* p, void* stream);
 

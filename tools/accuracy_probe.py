@@ -34,6 +34,9 @@ def run(rows, k, n, positive):
 
 
 if __name__ == "__main__":
-    for positive in (False, True):
-        for k in (64, 576, 2304, 12544):
-            run(256, k, 256, positive)
+    for kbc in (1000, 4, 2, 1):
+        ops.KB_PER_CHUNK = kbc
+        print(f"---- kb_per_chunk = {kbc}")
+        for positive in (False, True):
+            for k in (576, 2304, 12544):
+                run(256, k, 256, positive)

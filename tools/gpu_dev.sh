@@ -1,3 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_roi_heads.py -q -m gpu 2>&1 | tail -60 | tee gpurun_out/test_heads.log
+timeout 1200 python -m pytest tests -q -m gpu 2>&1 | grep -E "^E   |passed|failed|^FAILED" | cut -c1-300 | tee gpurun_out/test_gpu.log
+timeout 300 python __graft_entry__.py smoke 2>&1 | tail -3 | tee gpurun_out/smoke.log
+timeout 900 python bench.py --steps 5 --warmup 3 2>&1 | tail -3 | tee gpurun_out/bench.log
