@@ -195,7 +195,8 @@ def run_b200(args):
             words.append(sum(counts))
             if world > 1:
                 if gathered is None:
-                    gathered = torch.empty((world,) + tuple(rec.shape), dtype=rec.dtype, device=rec.device)
+                    gathered = torch.empty((world * rec.shape[0],) + tuple(rec.shape[1:]), dtype=rec.dtype,
+                                           device=rec.device)
                 dist.all_gather_into_tensor(gathered, rec)
                 return gathered
             return rec
@@ -220,7 +221,7 @@ def run_b200(args):
 
     # ---- timed: inputs resident in HBM
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not args.no_clocks:
         sampler.start()
     words.clear()
     launches0 = L.glass_launch_count()
@@ -322,6 +323,7 @@ def main():
     ap.add_argument("--workload", default="full_bs4", choices=sorted(WORKLOADS))
     ap.add_argument("--fast", action="store_true", help="single-pass fp16 (NOT the parity precision)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-clocks", action="store_true", help="do not spawn the nvidia-smi clock sampler (ncu runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1,5 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -q -m gpu 2>&1 | grep -E "^E   |passed|failed|^FAILED" | cut -c1-300 | tee gpurun_out/test_gpu.log
-timeout 300 python __graft_entry__.py smoke 2>&1 | tail -3 | tee gpurun_out/smoke.log
-timeout 900 python bench.py --steps 5 --warmup 3 2>&1 | tail -3 | tee gpurun_out/bench.log
+rm -f gpurun_out/launches_full*.csv
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 500 -c 700 --csv --log-file gpurun_out/launches_full.csv python bench.py --steps 1 --warmup 1 --no-cpu --no-clocks > gpurun_out/ncu_bench_full.log 2>&1
+tail -1 gpurun_out/ncu_bench_full.log | cut -c1-200
+wc -l gpurun_out/launches_full*.csv
