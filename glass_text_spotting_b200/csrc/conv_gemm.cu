@@ -28,6 +28,7 @@ static constexpr int ACC_COLS = 256;  // TMEM columns per accumulator stage
 static constexpr int A_TILE_BYTES = BM * BK * 2;
 static constexpr int NUM_THREADS = 384;  // 4 control warps + 8 epilogue warps
 static constexpr int MAX_STAGES = 8;
+static constexpr int EPI_STAGE_BYTES = 8 * 4096;  // per epilogue warp: 32 rows x 32 fp32 columns
 static constexpr int MAX_CHUNKS_PER_WARP = 8;  // 256 columns / 16 per chunk / 2 column halves
 
 struct GemmKernelParams {
@@ -59,7 +60,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages x (A_hi, A_lo?, B_hi, B_lo?)] then barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.num_stages * p.stage_bytes);
+  float* stage_base = reinterpret_cast<float*>(smem + (size_t)p.num_stages * p.stage_bytes);  // 8 warps x 4 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.num_stages * p.stage_bytes + EPI_STAGE_BYTES);
   uint64_t* full_bar = bars;                      // [MAX_STAGES]
   uint64_t* empty_bar = bars + MAX_STAGES;        // [MAX_STAGES]
   uint64_t* tmem_full_bar = bars + 2 * MAX_STAGES;   // [2]
@@ -204,6 +206,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     const int c_begin = half ? (nchunks + 1) / 2 : 0;
     const int c_end = half ? nchunks : (nchunks + 1) / 2;
     const bool has_res = p.res_hi != nullptr;
+    float* stage = stage_base + e * 1024;
     const int chunks_per_tile = (kblocks + p.kb_per_chunk - 1) / p.kb_per_chunk;
     uint32_t chunk = 0;  // mirrors the MMA warp's running chunk counter
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -224,21 +227,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         res_row = ((int64_t)img * p.res_hp + (y >> p.res_shift) + p.res_border) * p.res_wp + (x >> p.res_shift) +
                   p.res_border;
       }
-      const __half* res_hi_row = p.res_hi + res_row * p.ld_out + n0;
-      const __half* res_lo_row = p.res_lo + res_row * p.ld_out + n0;
-      auto load_res = [&](int c, uint4 (&buf)[4]) {
-        if (has_res && valid && c < c_end && n0 + c * 16 < p.n_store) {
-          const uint4* rh = reinterpret_cast<const uint4*>(res_hi_row + c * 16);
-          const uint4* rl = reinterpret_cast<const uint4*>(res_lo_row + c * 16);
-          buf[0] = __ldg(rh);
-          buf[1] = __ldg(rh + 1);
-          buf[2] = __ldg(rl);
-          buf[3] = __ldg(rl + 1);
-        }
-      };
-      uint4 r_cur[4], r_nxt[4];
-      load_res(c_begin, r_cur);  // issued before the accumulator is ready
-
       // ---- drain every accumulation chunk of this tile from TMEM into fp32 registers (round-to-nearest
       // adds): the tensor core's own accumulator truncates, so chains are kept to kb_per_chunk k-blocks.
       float accv[MAX_CHUNKS_PER_WARP][16];
@@ -268,79 +256,101 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
       }
 
-      // ---- final math + stores from registers
+      // ---- final math + stores.  Each lane owns one output ROW in registers, but a warp store that
+      // writes 32 different rows touches 32 cache lines (LSU-bound, measured 31 sectors/request), so
+      // the tile goes through a per-warp XOR-swizzled shared-memory stage, 32 columns at a time, and is
+      // written back in the transposed mapping: 4 lanes x 16 B = 64 contiguous bytes of one row per
+      // plane, 8 rows per instruction.  The residual is read in that same coalesced mapping.
 #pragma unroll
-      for (int ci = 0; ci < MAX_CHUNKS_PER_WARP; ++ci) {
-        const int c = c_begin + ci;
-        if (c < c_end) {
-          load_res(c + 1, r_nxt);
-          const int n = n0 + c * 16;
-          if (valid && n < p.n_store) {
-            float v[16];
+      for (int gi = 0; gi < MAX_CHUNKS_PER_WARP / 2; ++gi) {
+        const int cb = c_begin + 2 * gi;  // first 16-column chunk of this 32-column group
+        if (cb < c_end) {                 // warp-uniform
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = accv[ci][j];
-            if (p.scale != nullptr) {
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const int ci = 2 * gi + h2;
+            const int c = c_begin + ci;
+            if (c < c_end) {
+              const int n = n0 + c * 16;
+              float v[16];
 #pragma unroll
-              for (int j = 0; j < 16; j += 4) {
-                const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + n + j));
-                v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
-              }
-            }
-            if (p.bias != nullptr) {
+              for (int j = 0; j < 16; ++j) v[j] = accv[ci][j];
+              if (p.scale != nullptr) {
 #pragma unroll
-              for (int j = 0; j < 16; j += 4) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
-                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-              }
-            }
-            if (p.relu_pre) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-            }
-            if (has_res) {
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const uint32_t aw[4] = {r_cur[h].x, r_cur[h].y, r_cur[h].z, r_cur[h].w};
-                const uint32_t bw[4] = {r_cur[2 + h].x, r_cur[2 + h].y, r_cur[2 + h].z, r_cur[2 + h].w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float2 rv = unpack16x2(aw[j], bw[j]);
-                  v[h * 8 + 2 * j] += rv.x;
-                  v[h * 8 + 2 * j + 1] += rv.y;
+                for (int j = 0; j < 16; j += 4) {
+                  const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + n + j));
+                  v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
                 }
               }
-            }
-            if (p.relu_post) {
+              if (p.bias != nullptr) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-            }
-            if (p.out_f32 != nullptr) {
-              float4* o = reinterpret_cast<float4*>(p.out_f32 + out_row * p.ld_f32 + n);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            }
-            if (p.out_hi != nullptr) {
-              uint32_t hw[8], lw[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                __half h0, l0, h1, l1;
-                split16(v[2 * j], h0, l0);
-                split16(v[2 * j + 1], h1, l1);
-                hw[j] = pack16x2(h0, h1);
-                lw[j] = pack16x2(l0, l1);
+                for (int j = 0; j < 16; j += 4) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+                  v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                }
               }
-              uint4* oh = reinterpret_cast<uint4*>(p.out_hi + out_row * p.ld_out + n);
-              oh[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-              oh[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
-              if (p.out_lo != nullptr) {
-                uint4* ol = reinterpret_cast<uint4*>(p.out_lo + out_row * p.ld_out + n);
-                ol[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-                ol[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+              if (p.relu_pre) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+              }
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const int phys = (h2 * 4 + jj) ^ (lane & 7);
+                *reinterpret_cast<float4*>(stage + lane * 32 + phys * 4) =
+                    make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
               }
             }
           }
+          __syncwarp();
+          const int ncols = min(32, (c_end - cb) * 16);
+          const int cg = lane & 3;  // 8-column group inside the 32-column stage
+          const int n = n0 + cb * 16 + cg * 8;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) r_cur[j] = r_nxt[j];
+          for (int ps = 0; ps < 4; ++ps) {
+            const int R = ps * 8 + (lane >> 2);
+            const int valid_r = __shfl_sync(0xffffffffu, (int)valid, R);
+            const long long out_row_r = __shfl_sync(0xffffffffu, (long long)out_row, R);
+            const long long res_row_r = __shfl_sync(0xffffffffu, (long long)res_row, R);
+            if (valid_r && cg * 8 < ncols && n < p.n_store) {
+              const float4 a = *reinterpret_cast<const float4*>(stage + R * 32 + (((2 * cg) ^ (R & 7)) * 4));
+              const float4 b = *reinterpret_cast<const float4*>(stage + R * 32 + (((2 * cg + 1) ^ (R & 7)) * 4));
+              float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+              if (has_res) {
+                const uint4 rh = __ldg(reinterpret_cast<const uint4*>(p.res_hi + res_row_r * p.ld_out + n));
+                const uint4 rl = __ldg(reinterpret_cast<const uint4*>(p.res_lo + res_row_r * p.ld_out + n));
+                const uint32_t aw[4] = {rh.x, rh.y, rh.z, rh.w}, bw[4] = {rl.x, rl.y, rl.z, rl.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 rv = unpack16x2(aw[j], bw[j]);
+                  v[2 * j] += rv.x;
+                  v[2 * j + 1] += rv.y;
+                }
+              }
+              if (p.relu_post) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+              }
+              if (p.out_f32 != nullptr) {
+                float4* o = reinterpret_cast<float4*>(p.out_f32 + out_row_r * p.ld_f32 + n);
+                o[0] = make_float4(v[0], v[1], v[2], v[3]);
+                o[1] = make_float4(v[4], v[5], v[6], v[7]);
+              }
+              if (p.out_hi != nullptr) {
+                uint32_t hw[4], lw[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  __half h0, l0, h1, l1;
+                  split16(v[2 * j], h0, l0);
+                  split16(v[2 * j + 1], h1, l1);
+                  hw[j] = pack16x2(h0, h1);
+                  lw[j] = pack16x2(l0, l1);
+                }
+                *reinterpret_cast<uint4*>(p.out_hi + out_row_r * p.ld_out + n) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                if (p.out_lo != nullptr)
+                  *reinterpret_cast<uint4*>(p.out_lo + out_row_r * p.ld_out + n) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+              }
+            }
+          }
+          __syncwarp();
         }
       }
     }
@@ -428,7 +438,7 @@ extern "C" int glass_conv_gemm(const GlassConvGemmParams* p, void* stream_v) {
   for (int i = 0; i < GLASS_MAX_TAPS; ++i) k.tap_shift[i] = p->tap_shift[i];
   k.b_tile_bytes = bn * BK * 2;
   k.stage_bytes = (A_TILE_BYTES + k.b_tile_bytes) * (split ? 2 : 1);
-  const int smem_budget = 200 * 1024;
+  const int smem_budget = 227 * 1024 - EPI_STAGE_BYTES - 1024 /*align slack*/ - 256 /*barriers*/;
   k.num_stages = smem_budget / k.stage_bytes;
   if (k.num_stages > MAX_STAGES) k.num_stages = MAX_STAGES;
   GLASS_CHECK(k.num_stages >= 2, "stage too large");
@@ -443,7 +453,7 @@ extern "C" int glass_conv_gemm(const GlassConvGemmParams* p, void* stream_v) {
   k.ld_out = p->ld_out; k.ld_f32 = p->ld_f32; k.n_store = n_store;
 
   // always ask for > half of the SM's shared memory: exactly one CTA per SM owns all 512 TMEM columns
-  const int smem_bytes = k.num_stages * k.stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  const int smem_bytes = k.num_stages * k.stage_bytes + EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   const int smem_req = smem_bytes < 120 * 1024 ? 120 * 1024 : smem_bytes;
   const int sms = num_sms();
   GLASS_CHECK(sms > 0, "no CUDA device");

@@ -38,13 +38,15 @@ class Workspace:
         self._acts: Dict[str, Act] = {}
         self._raw: Dict[str, torch.Tensor] = {}
 
-    def act(self, name: str, n: int, c: int, h: int, w: int, cp: Optional[int] = None) -> Act:
+    def act(self, name: str, n: int, c: int, h: int, w: int, cp: Optional[int] = None, cap: int = 0) -> Act:
+        """Activation buffer ``name`` for n images; allocated (zeroed) once with capacity max(n, cap) images and
+        handed out as a view of the first n, so a varying n (detected words) never re-allocates or re-zeroes."""
         a = self._acts.get(name)
         cp = cp if cp is not None else ops.round_up(c, 64)
-        if a is None or (a.n, a.c, a.h, a.w, a.cp) != (n, c, h, w, cp):
-            a = Act(n, c, h, w, 1, cp, self.device)
+        if a is None or (a.c, a.h, a.w, a.cp) != (c, h, w, cp) or a.buf.shape[1] < n:
+            a = Act(max(n, cap), c, h, w, 1, cp, self.device)
             self._acts[name] = a
-        return a
+        return a if a.n == n else Act(n, c, h, w, 1, cp, self.device, buf=a.buf)
 
     def raw(self, name: str, shape, dtype=torch.float16, zero: bool = False) -> torch.Tensor:
         t = self._raw.get(name)
@@ -52,6 +54,16 @@ class Workspace:
             t = (torch.zeros if zero else torch.empty)(tuple(shape), dtype=dtype, device=self.device)
             self._raw[name] = t
         return t
+
+    def rows(self, name: str, rows: int, width: int, cap_rows: int = 0, planes: int = 2,
+             dtype=torch.float16) -> torch.Tensor:
+        """Row-matrix buffer [planes, rows, width] as a view of a buffer with capacity max(rows, cap_rows) rows
+        (each plane's prefix is contiguous)."""
+        t = self._raw.get(name)
+        if t is None or t.shape[0] != planes or t.shape[2] != width or t.dtype != dtype or t.shape[1] < rows:
+            t = torch.empty((planes, max(rows, cap_rows), width), dtype=dtype, device=self.device)
+            self._raw[name] = t
+        return t[:, :rows]
 
     def nbytes(self) -> int:
         return sum(a.buf.numel() * 2 for a in self._acts.values()) + \

@@ -172,8 +172,12 @@ class B200GlassROIHeads:
         ops.conv2d(p2, self.p2p3_conv1, residual=t, res_shift=1, out=g, mode=self.mode)
         return g
 
+    def act(self, name: str, n: int, c: int, h: int, w: int) -> Act:
+        """Recognizer-side activation: capacity = every detection slot of the batch, view of the n live words."""
+        return self.ws.act(name, n, c, h, w, cap=self._word_cap)
+
     def _basic_block(self, x: Act, blk, name: str) -> Act:
-        ws = self.ws
+        ws = self
         t = ws.act(name + ".t", x.n, blk["conv1"].cout, x.h, x.w)
         ops.conv2d(x, blk["conv1"], relu=True, out=t, mode=self.mode)
         res = x
@@ -187,7 +191,7 @@ class B200GlassROIHeads:
     def hybrid_net(self, crops: Act, f_out: Act, taps: Optional[dict] = None) -> None:
         """ResNetFeatureExtractor on [K,3,128,128] crops; the [K,256,8,32] result lands in channels 0..255
         of the fused buffer ``f_out`` (cp 512)."""
-        ws, m, k = self.ws, self.mode, crops.n
+        ws, m, k = self, self.mode, crops.n
         x = ops.conv2d(crops, self.h_conv0_1, relu=True, out=ws.act("hyb.c01", k, 16, crops.h, crops.w), mode=m)
         x = ops.conv2d(x, self.h_conv0_2, relu=True, out=ws.act("hyb.c02", k, 32, x.h, x.w), mode=m)
         x = ops.maxpool2d(x, (2, 2), (2, 2), (0, 0), out=ws.act("hyb.pool1", k, 32, x.h // 2, x.w // 2))
@@ -207,7 +211,7 @@ class B200GlassROIHeads:
         # conv4_1: k2 s(2,1) p0 + BN + ReLU -> [K,256,8,32], written into the fused buffer's local half
         ho, wo = (x.h - 2) // 2 + 1, x.w - 1
         assert (ho, wo) == (f_out.h, f_out.w)
-        g = ws.raw("hyb.c41.gather", (2, k * ho * wo, 4 * x.cp))
+        g = self.ws.rows("hyb.c41.gather", k * ho * wo, 4 * x.cp, self._word_cap * ho * wo)
         ops.gather_taps(x, 2, 2, 2, 1, 0, 0, ho, wo, out=g)
         ops.conv_gemm(g[0], g[1], g.shape[1], g.shape[2], [0], self.h_conv4_1, (k, ho, wo, 0), out_hi=f_out.hi,
                       out_lo=f_out.lo, out_geom=(f_out.hp, f_out.wp, f_out.border), ld_out=f_out.cp, relu_post=True,
@@ -218,7 +222,8 @@ class B200GlassROIHeads:
         """rois fp32 [K,6] (batch, cx, cy, w, h, angle) of the detections of all images, grouped by image;
         word_start int32 [n_img+1].  Returns pred_text_prob [K, 26, 97]."""
         K = rois.shape[0]
-        ws, m = self.ws, self.mode
+        self._word_cap = max(n_img * self.max_det, K)
+        ws, m, cap = self, self.mode, self._word_cap
         probs = torch.zeros((K, self.steps, self.num_classes), dtype=torch.float32, device=rois.device)
         if K == 0:
             return probs
@@ -236,21 +241,21 @@ class B200GlassROIHeads:
         y = ops.conv2d(fused2, self.fusion_out, out=ws.act("rec.fusion_out", K, 256, ph, pw), mode=m)
         # CNN_V1_1
         x1 = ops.conv2d(y, self.r_conv1, relu=True, out=ws.act("rec.cnn1", K, 256, ph // 2, pw), mode=m,
-                        gather_buf=ws.raw("rec.cnn1.gather", (2, K * (ph // 2) * pw, 2 * 256)))
+                        gather_buf=self.ws.rows("rec.cnn1.gather", K * (ph // 2) * pw, 2 * 256, cap * (ph // 2) * pw))
         x2 = ops.conv2d(x1, self.r_conv2, relu_pre=True, residual=x1, out=ws.act("rec.cnn2", K, 256, ph // 2, pw), mode=m)
         # BiLSTMBlockV2
         T = pw
-        seq = ws.raw("rec.seq0", (2, K * T, 256))
+        seq = self.ws.rows("rec.seq0", K * T, 256, cap * T)
         ops.hmean_rows(x2, K, seq)
         enc_f32 = None
         for l, lw in enumerate(self.lstm):
             _, gates = ops.linear(seq, lw["wih"], want_split=False, want_f32=True, mode=m)
-            hcat = ws.raw(f"rec.lstm{l}.h", (2, K * T, 512))
+            hcat = self.ws.rows(f"rec.lstm{l}.h", K * T, 512, cap * T)
             ops.lstm_bidir(gates, lw["whh_t"], K, T, hcat)
             seq, enc_f32 = ops.linear(hcat, lw["linear"], want_f32=(l == len(self.lstm) - 1), mode=m)
         # ASTER decoder
         _, xproj = ops.linear(seq, self.x_embed, want_split=False, want_f32=True, mode=m)
-        first_eos = ws.raw("rec.first_eos", (K,), torch.int32)
+        first_eos = self.ws.raw("rec.first_eos", (cap,), torch.int32)
         logits = alphas = None
         if taps is not None:
             logits = torch.zeros_like(probs)

@@ -54,16 +54,18 @@ class Act:
         if buf is None:
             buf = torch.zeros(shape, dtype=torch.float16, device=device)
         else:
-            assert tuple(buf.shape) == shape and buf.dtype == torch.float16 and buf.is_contiguous()
+            # ``buf`` may have spare capacity along n (Workspace): this Act is then a view of its first n images
+            assert buf.dtype == torch.float16 and buf.is_contiguous() and buf.shape[0] == 2 and buf.shape[1] >= n \
+                and tuple(buf.shape[2:]) == shape[2:]
         self.buf = buf
 
     @property
     def hi(self) -> torch.Tensor:
-        return self.buf[0]
+        return self.buf[0, : self.n]
 
     @property
     def lo(self) -> torch.Tensor:
-        return self.buf[1]
+        return self.buf[1, : self.n]
 
     @property
     def rows(self) -> int:
@@ -195,7 +197,7 @@ def linear(a: torch.Tensor, w: PackedWeight, relu: bool = False, want_split: boo
            mode: int = MODE_SPLIT):
     """y = a @ W^T (*scale + bias) for a split-fp16 matrix ``a`` [2, rows, k] (k == w.cin_p).
     Returns (split [2, rows, n_p] or None, fp32 [rows, n_p] or None)."""
-    assert a.dim() == 3 and a.shape[0] == 2 and a.shape[2] == w.cin_p and a.is_contiguous()
+    assert a.dim() == 3 and a.shape[0] == 2 and a.shape[2] == w.cin_p and a[0].is_contiguous()
     rows = a.shape[1]
     o = torch.empty((2, rows, w.n_p), dtype=torch.float16, device=a.device) if want_split else None
     of = torch.empty((rows, w.n_p), dtype=torch.float32, device=a.device) if want_f32 else None
@@ -222,7 +224,7 @@ def gather_taps(x: Act, kh: int, kw: int, sh: int, sw: int, ph: int, pw: int, ho
     """im2col of a split activation: rows [2, n*ho*wo, kh*kw*cp] (tap-major K)."""
     if out is None:
         out = torch.empty((2, x.n * ho * wo, kh * kw * x.cp), dtype=torch.float16, device=x.buf.device)
-    assert tuple(out.shape) == (2, x.n * ho * wo, kh * kw * x.cp) and out.is_contiguous()
+    assert tuple(out.shape) == (2, x.n * ho * wo, kh * kw * x.cp) and out[0].is_contiguous()
     _lib.check(_lib.load().glass_gather_taps(_ptr(x.hi), _ptr(x.lo), x.n, x.h, x.w, x.cp, x.border, kh, kw, sh, sw,
                                              ph, pw, ho, wo, _ptr(out[0]), _ptr(out[1]), _stream()))
     return out
@@ -235,7 +237,7 @@ def stem_im2col(img: torch.Tensor, mean: Sequence[float], std: Sequence[float], 
     assert c == 3 and img.dtype == torch.float32 and img.is_contiguous()
     if out is None:
         out = torch.empty((2, n * (h // 2) * (w // 2), kp), dtype=torch.float16, device=img.device)
-    assert tuple(out.shape) == (2, n * (h // 2) * (w // 2), kp) and out.is_contiguous()
+    assert tuple(out.shape) == (2, n * (h // 2) * (w // 2), kp) and out[0].is_contiguous()
     m = (C.c_float * 3)(*[float(v) for v in mean])
     s = (C.c_float * 3)(*[1.0 / float(v) for v in std])
     _lib.check(_lib.load().glass_stem_im2col(_ptr(img), n, h, w, m, s, _ptr(out[0]), _ptr(out[1]), kp, _stream()))
