@@ -366,11 +366,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
 
 // ------------------------------------------------------------------------------------------ host
 static int make_map_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint32_t box_inner,
-                       uint32_t box_outer) {
+                       uint32_t box_outer, uint64_t row_stride_elems = 0) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (enc == nullptr) return fail("cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {inner * 2};  // bytes, dim 1
+  cuuint64_t strides[1] = {(row_stride_elems ? row_stride_elems : inner) * 2};  // bytes, dim 1 (may overlap)
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
@@ -418,10 +418,19 @@ extern "C" int glass_conv_gemm(const GlassConvGemmParams* p, void* stream_v) {
 
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   const uint64_t ktot = (uint64_t)p->k_per_tap * p->ntaps;
-  if (make_map_2d(&ma_hi, p->a_hi, p->k_per_tap, p->rows_a, BK, BM)) return -1;
+  // compact-channel mode: rows overlap (stride a_ld < 64 elements); the last 64/a_ld - 1 rows would read past
+  // the tensor, so they are left to the TMA's out-of-bounds zero fill (they start inside the zero border)
+  const int a_ld = p->a_ld > 0 ? p->a_ld : p->k_per_tap;
+  uint64_t a_rows = (uint64_t)p->rows_a;
+  if (a_ld != p->k_per_tap) {
+    GLASS_CHECK(p->k_per_tap == BK && (a_ld == 8 || a_ld == 16 || a_ld == 32), "compact mode needs k_per_tap 64, a_ld 8/16/32");
+    GLASS_CHECK(p->rows_a > BK / a_ld, "too few rows for compact mode");
+    a_rows = (uint64_t)p->rows_a - (uint64_t)(BK / a_ld) + 1;
+  }
+  if (make_map_2d(&ma_hi, p->a_hi, p->k_per_tap, a_rows, BK, BM, a_ld)) return -1;
   if (make_map_2d(&mb_hi, p->b_hi, ktot, p->n, BK, bn)) return -1;
   if (split) {
-    if (make_map_2d(&ma_lo, p->a_lo, p->k_per_tap, p->rows_a, BK, BM)) return -1;
+    if (make_map_2d(&ma_lo, p->a_lo, p->k_per_tap, a_rows, BK, BM, a_ld)) return -1;
     if (make_map_2d(&mb_lo, p->b_lo, ktot, p->n, BK, bn)) return -1;
   } else {
     ma_lo = ma_hi;

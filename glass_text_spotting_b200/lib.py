@@ -20,7 +20,7 @@ SYMBOLS = [
 
 class ConvGemmParams(C.Structure):
     _fields_ = [
-        ("a_hi", C.c_void_p), ("a_lo", C.c_void_p), ("rows_a", C.c_int64),
+        ("a_hi", C.c_void_p), ("a_lo", C.c_void_p), ("rows_a", C.c_int64), ("a_ld", C.c_int32),
         ("k_per_tap", C.c_int32), ("ntaps", C.c_int32), ("tap_shift", C.c_int32 * MAX_TAPS),
         ("b_hi", C.c_void_p), ("b_lo", C.c_void_p), ("n", C.c_int32), ("mode", C.c_int32),
         ("m_imgs", C.c_int32), ("m_h", C.c_int32), ("m_w", C.c_int32), ("m_border", C.c_int32),

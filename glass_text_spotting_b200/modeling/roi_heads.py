@@ -59,19 +59,24 @@ class B200GlassROIHeads:
         # ---- hybrid_net = ResNetFeatureExtractor (local_feature_extraction.py:95-188), layers [1,2,5,3]
         hp = "hybrid_net.ConvNet."
 
-        def cb(conv, bn, stride=(1, 1), pad=(1, 1)):
+        def cb(conv, bn, stride=(1, 1), pad=(1, 1), compact_cp=0):
             s, b = _bn_fold(sd, hp + bn)
+            if compact_cp:  # narrow input activation (3/16/32 channels): compact-channel implicit GEMM
+                return packing.pack_conv_compact(sd[hp + conv + ".weight"], compact_cp, s, b, device=dev)
             return packing.pack_conv(sd[hp + conv + ".weight"], s, b, stride, pad, device=dev)
 
-        self.h_conv0_1, self.h_conv0_2 = cb("conv0_1", "bn0_1"), cb("conv0_2", "bn0_2")
+        # the first layers keep their real channel counts (crops 3->8, 16, 32) instead of padding to 64
+        self.h_conv0_1, self.h_conv0_2 = cb("conv0_1", "bn0_1", compact_cp=8), cb("conv0_2", "bn0_2", compact_cp=16)
         self.h_layers = []
         for li, nblk in zip([1, 2, 3, 4], [1, 2, 5, 3]):
             blocks = []
             for b in range(nblk):
                 q = f"layer{li}.{b}."
-                blk = {"conv1": cb(q + "conv1", q + "bn1"), "conv2": cb(q + "conv2", q + "bn2"), "down": None}
+                narrow = 32 if (li == 1 and b == 0) else 0  # layer1.0 reads the 32-channel activation
+                blk = {"conv1": cb(q + "conv1", q + "bn1", compact_cp=narrow), "conv2": cb(q + "conv2", q + "bn2"),
+                       "down": None}
                 if hp + q + "downsample.0.weight" in sd:
-                    blk["down"] = cb(q + "downsample.0", q + "downsample.1", pad=(0, 0))
+                    blk["down"] = cb(q + "downsample.0", q + "downsample.1", pad=(0, 0), compact_cp=narrow)
                 blocks.append(blk)
             self.h_layers.append(blocks)
         self.h_conv1, self.h_conv2, self.h_conv3 = cb("conv1", "bn1"), cb("conv2", "bn2"), cb("conv3", "bn3")
@@ -172,9 +177,9 @@ class B200GlassROIHeads:
         ops.conv2d(p2, self.p2p3_conv1, residual=t, res_shift=1, out=g, mode=self.mode)
         return g
 
-    def act(self, name: str, n: int, c: int, h: int, w: int) -> Act:
+    def act(self, name: str, n: int, c: int, h: int, w: int, cp: Optional[int] = None) -> Act:
         """Recognizer-side activation: capacity = every detection slot of the batch, view of the n live words."""
-        return self.ws.act(name, n, c, h, w, cap=self._word_cap)
+        return self.ws.act(name, n, c, h, w, cp=cp, cap=self._word_cap)
 
     def _basic_block(self, x: Act, blk, name: str) -> Act:
         ws = self
@@ -192,9 +197,9 @@ class B200GlassROIHeads:
         """ResNetFeatureExtractor on [K,3,128,128] crops; the [K,256,8,32] result lands in channels 0..255
         of the fused buffer ``f_out`` (cp 512)."""
         ws, m, k = self, self.mode, crops.n
-        x = ops.conv2d(crops, self.h_conv0_1, relu=True, out=ws.act("hyb.c01", k, 16, crops.h, crops.w), mode=m)
-        x = ops.conv2d(x, self.h_conv0_2, relu=True, out=ws.act("hyb.c02", k, 32, x.h, x.w), mode=m)
-        x = ops.maxpool2d(x, (2, 2), (2, 2), (0, 0), out=ws.act("hyb.pool1", k, 32, x.h // 2, x.w // 2))
+        x = ops.conv2d(crops, self.h_conv0_1, relu=True, out=ws.act("hyb.c01", k, 16, crops.h, crops.w, cp=16), mode=m)
+        x = ops.conv2d(x, self.h_conv0_2, relu=True, out=ws.act("hyb.c02", k, 32, x.h, x.w, cp=32), mode=m)
+        x = ops.maxpool2d(x, (2, 2), (2, 2), (0, 0), out=ws.act("hyb.pool1", k, 32, x.h // 2, x.w // 2, cp=32))
         for b, blk in enumerate(self.h_layers[0]):
             x = self._basic_block(x, blk, f"hyb.l1.{b}")
         x = ops.conv2d(x, self.h_conv1, relu=True, out=ws.act("hyb.c1", k, x.c, x.h, x.w), mode=m)
@@ -232,7 +237,7 @@ class B200GlassROIHeads:
         fused = ws.act("rec.fused", K, 512, ph, pw)
         ops.roi_align_rotated([g], rois, (ph, pw), [1.0 / self.strides[0]], self.recog_sampling, out_f32=False,
                               out_split=(fused.buf, fused.hp, fused.wp, fused.border, 256, fused.cp))
-        crops = ws.act("rec.crops", K, 3, ph * 16, pw * 4)
+        crops = ws.act("rec.crops", K, 3, ph * 16, pw * 4, cp=8)
         ops.image_roi_align_rotated(images, pad_hw, self.pixel_mean, self.pixel_std, rois, (ph * 16, pw * 4),
                                     self.sampling, out_act=crops)
         self.hybrid_net(crops, fused, taps)

@@ -49,6 +49,7 @@ class Act:
                  device="cuda", buf: Optional[torch.Tensor] = None):
         self.n, self.c, self.h, self.w, self.border = n, c, h, w, border
         self.cp = cp if cp is not None else round_up(c, 64)
+        assert self.cp % 8 == 0 and self.cp >= c
         self.hp, self.wp = h + 2 * border, w + 2 * border
         shape = (2, n, self.hp, self.wp, self.cp)
         if buf is None:
@@ -121,11 +122,11 @@ def conv_gemm(a_hi: torch.Tensor, a_lo: Optional[torch.Tensor], rows_a: int, k_p
               out_geom: Optional[Tuple[int, int, int]] = None, ld_out: int = 0,
               out_hi: Optional[torch.Tensor] = None, out_lo: Optional[torch.Tensor] = None,
               residual: Optional[Act] = None, res_shift: int = 0, relu_pre: bool = False, relu_post: bool = False,
-              mode: int = MODE_SPLIT, n_store: int = 0) -> None:
+              mode: int = MODE_SPLIT, n_store: int = 0, a_ld: int = 0) -> None:
     """Raw launch of glass_conv_gemm.  m_geom = (imgs, h, w, border) of the M space;
     out_geom = (hp, wp, border) of the output rows (defaults to ``out``'s geometry)."""
     p = _lib.ConvGemmParams()
-    p.a_hi, p.a_lo, p.rows_a = _ptr(a_hi), _ptr(a_lo), rows_a
+    p.a_hi, p.a_lo, p.rows_a, p.a_ld = _ptr(a_hi), _ptr(a_lo), rows_a, a_ld
     p.k_per_tap, p.ntaps = k_per_tap, len(tap_shift)
     for i, s in enumerate(tap_shift):
         p.tap_shift[i] = s
@@ -166,6 +167,8 @@ def conv2d(x: Act, w: PackedWeight, relu: bool = False, residual: Optional[Act] 
     stride-1 'same' convs run as shifted-row implicit GEMM straight from ``x``; everything else goes
     through one tap-gather pass.  ``relu`` = ReLU after the residual add (d2 bottleneck order),
     ``relu_pre`` = ReLU before it (CNN_V1_1 order)."""
+    if getattr(w, "compact_cp", 0):
+        return _conv2d_compact(x, w, relu, residual, res_shift, relu_pre, out, mode)
     assert x.cp == w.cin_p, (x.cp, w.cin_p)
     sh, sw = w.stride
     ph, pw = w.pad
@@ -190,6 +193,22 @@ def conv2d(x: Act, w: PackedWeight, relu: bool = False, residual: Optional[Act] 
         g = gather_taps(x, w.kh, w.kw, sh, sw, ph, pw, ho, wo, out=gather_buf)
         # the gathered matrix is already tap-major: one "tap" of width taps*cp
         conv_gemm(g[0], g[1], rows, taps * x.cp, [0], w, (x.n, ho, wo, 0), **kwargs)
+    return out
+
+
+def _conv2d_compact(x: Act, w: PackedWeight, relu, residual, res_shift, relu_pre, out, mode) -> Act:
+    """stride-1 'same' 1x1 / 3x3 conv on a narrow activation (cp = 8/16/32): a 64-wide k-block spans 64/cp
+    consecutive pixels, so the three s-taps of a row are read by one (cp <= 16) or two (cp = 32) TMA boxes."""
+    cp = w.compact_cp
+    assert x.cp == cp and w.stride == (1, 1) and x.border >= w.pad[0] and (w.kh, w.kw) in ((1, 1), (3, 3))
+    ppk = 64 // cp
+    nj = (w.kw + ppk - 1) // ppk
+    shifts = [(r - w.pad[0]) * x.wp - w.pad[1] + j * ppk for r in range(w.kh) for j in range(nj)]
+    if out is None:
+        out = Act(x.n, w.cout, x.h, x.w, 1, w.n_p, x.buf.device)
+    assert (out.n, out.h, out.w, out.cp) == (x.n, x.h, x.w, w.n_p)
+    conv_gemm(x.hi, x.lo, x.rows, 64, shifts, w, (x.n, x.hp, x.wp, x.border), out=out, residual=residual,
+              res_shift=res_shift, relu_pre=relu_pre, relu_post=relu, mode=mode, a_ld=cp)
     return out
 
 

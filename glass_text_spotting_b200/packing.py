@@ -57,6 +57,31 @@ def pack_conv(weight: torch.Tensor, scale: Optional[torch.Tensor] = None, bias: 
     return PackedWeight(wp.to(device), s.to(device), b.to(device), cout, cin, kh, kw, tuple(stride), tuple(pad), cin_p)
 
 
+def pack_conv_compact(weight: torch.Tensor, cp_in: int, scale: Optional[torch.Tensor] = None,
+                      bias: Optional[torch.Tensor] = None, n_align: int = 16, device="cuda") -> PackedWeight:
+    """stride-1 'same' conv (1x1 or 3x3) whose INPUT activation is narrow (cp_in = 8/16/32 channels per pixel).
+    K layout per tap-row r: nj k-blocks of 64 = (64/cp_in pixels) x cp_in channels starting at pixel x - pad;
+    entries beyond the kw taps / cin channels are zero (see ops._conv2d_compact)."""
+    cout, cin, kh, kw = weight.shape
+    assert cp_in in (8, 16, 32) and cin <= cp_in and (kh, kw) in ((1, 1), (3, 3))
+    ppk = 64 // cp_in
+    nj = (kw + ppk - 1) // ppk
+    n_p = round_up(cout, n_align)
+    w = torch.zeros((n_p, kh, nj * ppk, cp_in), dtype=torch.float32)
+    w[:cout, :, :kw, :cin] = weight.detach().float().permute(0, 2, 3, 1)
+    s = torch.ones(n_p, dtype=torch.float32)
+    b = torch.zeros(n_p, dtype=torch.float32)
+    if scale is not None:
+        s[:cout] = scale.detach().float()
+    if bias is not None:
+        b[:cout] = bias.detach().float()
+    wp, s = _pack_rows(w.reshape(n_p, kh * nj * 64), s)
+    pw = PackedWeight(wp.to(device), s.to(device), b.to(device), cout, cin, kh, kw, (1, 1), ((kh - 1) // 2, (kw - 1) // 2),
+                      64)
+    pw.compact_cp = cp_in
+    return pw
+
+
 def pack_linear(weight: torch.Tensor, bias: Optional[torch.Tensor] = None, k_p: Optional[int] = None,
                 n_align: int = 64, device="cuda") -> PackedWeight:
     """nn.Linear weight [out, in] -> packed as a 1x1 'conv' over rows."""

@@ -57,6 +57,9 @@ typedef struct {
   const void* a_hi;  /* fp16 [rows_a, k_per_tap] */
   const void* a_lo;  /* fp16, same shape (unused when mode == 1) */
   int64_t rows_a;
+  int32_t a_ld;      /* element stride between consecutive A rows; 0 = k_per_tap.  a_ld < k_per_tap (8, 16 or 32
+                        with k_per_tap = 64) is the compact-channel mode: one 64-wide k-block then spans 64/a_ld
+                        consecutive pixels of a narrow NHWC tensor (the s-taps of a 3x3 conv are contiguous) */
   int32_t k_per_tap; /* multiple of 64 */
   int32_t ntaps;     /* 1..GLASS_MAX_TAPS */
   int32_t tap_shift[GLASS_MAX_TAPS];

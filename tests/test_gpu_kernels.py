@@ -110,6 +110,32 @@ def test_conv_gemm_matches_torch_fp32(ops, case):
     assert f32.buf[:, 0].abs().max().item() == 0
 
 
+COMPACT_CASES = [
+    # name, cin, cp_in, cout, k
+    ("c3_cp8_3x3", 3, 8, 16, 3), ("c16_cp16_3x3", 16, 16, 32, 3), ("c32_cp32_3x3", 32, 32, 64, 3),
+    ("c32_cp32_1x1", 32, 32, 64, 1), ("c5_cp8_1x1", 5, 8, 48, 1),
+]
+
+
+@pytest.mark.parametrize("case", COMPACT_CASES, ids=[c[0] for c in COMPACT_CASES])
+def test_conv_gemm_compact_channels(ops, case):
+    """Narrow activations (8/16/32 channels per pixel): overlapping-row TMA, 64/cp pixels per k-block."""
+    from glass_text_spotting_b200 import packing
+    name, cin, cp_in, cout, k = case
+    g = torch.Generator().manual_seed(sum(map(ord, name)))
+    x = torch.randn(3, cin, 21, 37, generator=g)
+    wt = torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)
+    scale = 1.0 + 0.1 * torch.randn(cout, generator=g)
+    bias = 0.1 * torch.randn(cout, generator=g)
+    a = ops.Act.from_nchw(x.cuda(), cp=cp_in)
+    pw = packing.pack_conv_compact(wt, cp_in, scale, bias)
+    out = ops.conv2d(a, pw, relu=True)
+    ref = F.relu(F.conv2d(x, wt, padding=k // 2) * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1))
+    assert out.cp == pw.n_p and out.cp % 16 == 0
+    _close(out.to_nchw(), ref, name)
+    assert out.buf[:, :, 0].abs().max().item() == 0 and out.buf[:, :, :, -1].abs().max().item() == 0
+
+
 def test_conv_gemm_fast_mode_is_fp16_grade(ops):
     from glass_text_spotting_b200 import packing
     g = torch.Generator().manual_seed(5)

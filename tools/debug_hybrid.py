@@ -48,7 +48,8 @@ with torch.no_grad():
     x = F.relu(net.bn4_1(net.conv4_1(x))); ref["final"] = x
 
 heads = B200GlassROIHeads(o.state_dict())
-crops_act = ops.Act.from_nchw(crops.cuda())
+crops_act = ops.Act.from_nchw(crops.cuda(), cp=8)
+heads._word_cap = crops.shape[0]
 fused = ops.Act(crops.shape[0], 512, 8, 32)
 heads.hybrid_net(crops_act, fused)
 torch.cuda.synchronize()
