@@ -28,6 +28,9 @@ WORKLOADS = {
     "backbone_bs8": dict(batch=8, h=1024, w=1024, full=False,
                          desc="ResNet-50+FPN backbone only, bs=8/GPU, 1024x1024 synthetic (BASELINE.json configs[1])"),
 }
+WORKLOADS["roialign_512"] = dict(batch=1, h=1024, w=1024, full=False, roialign=True,
+                                 desc="RotatedROIAlign microbench: 512 rotated RoIs over 5 FPN levels, 7x7, sampling 2 "
+                                      "(BASELINE.json configs[2])")
 CPU_WORD_CAP = 16  # the CPU arm decodes at most this many words per image (bounded sample)
 
 
@@ -154,6 +157,94 @@ def run_reference(args):
     }))
 
 
+# ============================================================================================ RoIAlign microbench
+def _roialign_inputs(seed=0):
+    """SURVEY.md 8d cfg 3: p2..p6 [1,256,{256..16}^2] N(0,1); 512 RoIs, centres U(0,1024)^2, w log-uniform
+    [16,512], h = w*U(0.1,1), angle U(-180,180)."""
+    import math
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    feats = [torch.randn(1, 256, s, s, generator=g) for s in (256, 128, 64, 32, 16)]
+    n = 512
+    cx, cy = torch.rand(n, generator=g) * 1024, torch.rand(n, generator=g) * 1024
+    w = torch.exp(torch.rand(n, generator=g) * (math.log(512) - math.log(16)) + math.log(16))
+    h = w * (0.1 + 0.9 * torch.rand(n, generator=g))
+    a = torch.rand(n, generator=g) * 360 - 180
+    return feats, torch.stack((torch.zeros(n), cx, cy, w, h, a), 1).contiguous()
+
+
+def _roialign_algorithmic_bytes(rois, sizes=(256, 128, 64, 32, 16), strides=(4, 8, 16, 32, 64), res=7, sr=2, c=256):
+    """Sum over RoIs of (distinct feature cells touched by the 4 taps of the res*sr x res*sr samples) * C * 4 B
+    + output + rois (SURVEY.md 8d cfg 3)."""
+    import math
+    import torch
+    total = 0
+    for r in rois.tolist():
+        _, cx, cy, w, h, ang = r
+        lvl = int(min(max(math.floor(4 + math.log2(math.sqrt(w * h) / 224 + 1e-8)), 2), 6)) - 2
+        s, H = 1.0 / strides[lvl], sizes[lvl]
+        th = ang * math.pi / 180
+        cs, sn = math.cos(th), math.sin(th)
+        g = res * sr
+        ii = (torch.arange(g, dtype=torch.float64) + 0.5) / g
+        yy = (-h * s / 2 + ii * h * s).view(-1, 1).expand(g, g)
+        xx = (-w * s / 2 + ii * w * s).view(1, -1).expand(g, g)
+        y = yy * cs - xx * sn + cy * s - 0.5
+        x = yy * sn + xx * cs + cx * s - 0.5
+        ok = (y >= -1) & (y <= H) & (x >= -1) & (x <= H)
+        y0 = y.clamp(min=0).floor().clamp(max=H - 1).long()
+        x0 = x.clamp(min=0).floor().clamp(max=H - 1).long()
+        y1, x1 = (y0 + 1).clamp(max=H - 1), (x0 + 1).clamp(max=H - 1)
+        cells = set()
+        for yy_, xx_ in ((y0, x0), (y0, x1), (y1, x0), (y1, x1)):
+            cells.update((yy_[ok] * H + xx_[ok]).tolist())
+        total += len(cells) * c * 4
+    return total + rois.shape[0] * c * res * res * 4 + rois.numel() * 4
+
+
+def run_roialign(args):
+    import torch
+    from glass_text_spotting_b200 import lib, ops
+    from glass_text_spotting_b200.ops import Act
+    wl = WORKLOADS["roialign_512"]
+    feats, rois = _roialign_inputs()
+    acts = [Act.from_nchw(f.cuda()) for f in feats]
+    rois_d = rois.cuda()
+    out = torch.empty((2, 512, 49 * 256), dtype=torch.float16, device="cuda")
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    scales = [1 / 4, 1 / 8, 1 / 16, 1 / 32, 1 / 64]
+
+    def step():
+        ops.roi_align_rotated(acts, rois_d, (7, 7), scales, 2, out_f32=False, out_split=(out, 7, 7, 0, 0, 256))
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(args.steps):
+        flush.zero_()  # evict the 126 MB L2 between timed launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = sum(ts) / len(ts)
+    nbytes = _roialign_algorithmic_bytes(rois)
+    peaks, src = _peaks()
+    gbs = nbytes / (ms / 1e3) / 1e9
+    print(json.dumps({
+        "metric": "RotatedROIAlign GB/s (algorithmic bytes)", "value": gbs, "unit": "GB/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (split-fp16 storage)", "data": "synthetic",
+        "config": {"workload": wl["desc"], "l2": "256 MB buffer written between timed launches (L2 flushed)",
+                   "rois_per_s": 512 / (ms / 1e3)},
+        "gpu_launches": args.steps,
+        "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                     "traffic": None, "kernel": "roi_align_rotated_kernel<2, split>", "algorithmic_bytes": nbytes,
+                     "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({src})"}}))
+
+
 # ============================================================================================ B200 arm
 def run_b200(args):
     import torch
@@ -176,9 +267,10 @@ def run_b200(args):
     stream = torch.cuda.current_stream()
 
     g = torch.Generator().manual_seed(1000 + rank)
-    host = [torch.randint(0, 256, (B, 3, H, W), generator=g).float().pin_memory() for _ in range(2)]
-    dev = [h.cuda() for h in host]
-    dbuf = [torch.empty_like(d) for d in dev]
+    # host images are uint8 like the reference's dataset mapper output; they become fp32 on the device
+    host = [torch.randint(0, 256, (B, 3, H, W), generator=g, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    dev = [h.cuda().float() for h in host]
+    dbuf = [torch.empty((B, 3, H, W), dtype=torch.uint8, device="cuda") for _ in range(2)]
     img_hw = torch.tensor([[H, W]] * B, dtype=torch.float32, device="cuda")
     words = []
 
@@ -241,13 +333,13 @@ def run_b200(args):
     res_host = None
     for i in range(2):
         dbuf[i % 2].copy_(host[i % 2], non_blocking=True)
-        step(dbuf[i % 2])
+        step(dbuf[i % 2].float())
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     f0.record(stream)
     for i in range(args.steps):
         dbuf[i % 2].copy_(host[i % 2], non_blocking=True)
-        res = step(dbuf[i % 2])
+        res = step(dbuf[i % 2].float())
         if res_host is None:
             res_host = torch.empty(res.shape, dtype=res.dtype).pin_memory()
         res_host.copy_(res, non_blocking=True)
@@ -292,8 +384,8 @@ def run_b200(args):
                      "fp16x3 split (22-bit operands, 3 tcgen05 MMAs per product, chunked fp32 RN accumulation)",
             "data": "synthetic", "config": cfg,
             "e2e": {"value": world * B * args.steps / t_e2e, "unit": "images/s",
-                    "h2d_bytes_per_step": B * 3 * H * W * 4, "d2h_bytes_per_step": d2h_bytes,
-                    "note": "pinned host batch -> H2D -> hot path -> D2H of the step's result "
+                    "h2d_bytes_per_step": B * 3 * H * W, "d2h_bytes_per_step": d2h_bytes,
+                    "note": "pinned host uint8 batch -> H2D -> hot path -> D2H of the step's result "
                             + ("(packed detection records)" if full else "(p6 + per-level checksums)")},
             "gpu_launches": launches,
             "clocks": clocks,
@@ -327,6 +419,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif WORKLOADS[args.workload].get("roialign"):
+        run_roialign(args)
     else:
         run_b200(args)
 

@@ -75,8 +75,32 @@ struct RpnTopkKernelParams {
   int topk, level, num_levels;
   float* out_boxes;
   float* out_scores;
+  unsigned int* keys;  // [n_img, h*w*A] dense sortable keys
+  unsigned int* hist;  // [n_img, 256] histogram of the top 8 key bits
 };
 
+// Pass 0, many CTAs per image: gather the strided logits into a dense key array and histogram the top byte.
+__global__ void __launch_bounds__(256) rpn_keys_kernel(const RpnTopkKernelParams p) {
+  __shared__ unsigned int hist[256];
+  const int img = blockIdx.y;
+  const int npix = p.h * p.w;
+  hist[threadIdx.x] = 0;
+  __syncthreads();
+  const float* base = p.pred + (int64_t)img * npix * p.ld;
+  unsigned int* keys = p.keys + (int64_t)img * npix * p.A;
+  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += gridDim.x * blockDim.x) {
+    const float* row = base + (int64_t)pix * p.ld;
+    for (int a = 0; a < p.A; ++a) {
+      const unsigned key = float_to_sortable(__ldg(row + a));
+      keys[(int64_t)pix * p.A + a] = key;
+      atomicAdd(&hist[key >> 24], 1u);
+    }
+  }
+  __syncthreads();
+  if (hist[threadIdx.x]) atomicAdd(&p.hist[img * 256 + threadIdx.x], hist[threadIdx.x]);
+}
+
+// Passes 1..3 + compaction + sort + decode, one CTA per image, over the dense keys (coalesced).
 __global__ void __launch_bounds__(1024) rpn_topk_decode_kernel(const RpnTopkKernelParams p) {
   __shared__ unsigned int hist[256];
   __shared__ unsigned int s_prefix, s_mask, s_remaining, s_cnt_gt, s_cnt_eq;
@@ -86,6 +110,7 @@ __global__ void __launch_bounds__(1024) rpn_topk_decode_kernel(const RpnTopkKern
   const int n = npix * p.A;
   const int want = min(p.topk, n);
   const float* base = p.pred + (int64_t)img * npix * p.ld;
+  const unsigned int* keys = p.keys + (int64_t)img * n;
 
   if (threadIdx.x == 0) {
     s_prefix = 0;
@@ -97,16 +122,17 @@ __global__ void __launch_bounds__(1024) rpn_topk_decode_kernel(const RpnTopkKern
   for (int i = threadIdx.x; i < 1024; i += blockDim.x) sel[i] = ~0ull;
   __syncthreads();
 
-  // radix select (MSB first) of the want-th largest key
+  // radix select (MSB first) of the want-th largest key; the top byte's histogram comes from pass 0
   for (int pass = 0; pass < 4; ++pass) {
     const int shift = 24 - 8 * pass;
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
-    __syncthreads();
     const unsigned prefix = s_prefix, mask = s_mask;
-    for (int pix = threadIdx.x; pix < npix; pix += blockDim.x) {
-      const float* row = base + (int64_t)pix * p.ld;
-      for (int a = 0; a < p.A; ++a) {
-        const unsigned key = float_to_sortable(row[a]);
+    if (pass == 0) {
+      for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = p.hist[img * 256 + i];
+    } else {
+      for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+      __syncthreads();
+      for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        const unsigned key = keys[e];
         if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
       }
     }
@@ -130,18 +156,14 @@ __global__ void __launch_bounds__(1024) rpn_topk_decode_kernel(const RpnTopkKern
   const unsigned n_gt = (unsigned)want - need_eq;
 
   // compaction: everything above the threshold, then `need_eq` elements equal to it
-  for (int pix = threadIdx.x; pix < npix; pix += blockDim.x) {
-    const float* row = base + (int64_t)pix * p.ld;
-    for (int a = 0; a < p.A; ++a) {
-      const unsigned key = float_to_sortable(row[a]);
-      const unsigned e = (unsigned)(pix * p.A + a);
-      if (key > thr) {
-        const unsigned slot = atomicAdd(&s_cnt_gt, 1u);
-        sel[slot] = ((unsigned long long)(~key) << 32) | e;
-      } else if (key == thr) {
-        const unsigned slot = atomicAdd(&s_cnt_eq, 1u);
-        if (slot < need_eq) sel[n_gt + slot] = ((unsigned long long)(~key) << 32) | e;
-      }
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    const unsigned key = keys[e];
+    if (key > thr) {
+      const unsigned slot = atomicAdd(&s_cnt_gt, 1u);
+      sel[slot] = ((unsigned long long)(~key) << 32) | (unsigned)e;
+    } else if (key == thr) {
+      const unsigned slot = atomicAdd(&s_cnt_eq, 1u);
+      if (slot < need_eq) sel[n_gt + slot] = ((unsigned long long)(~key) << 32) | (unsigned)e;
     }
   }
   __syncthreads();
@@ -414,6 +436,10 @@ __global__ void box_decode_kernel(const float* __restrict__ pred, int ld, const 
 
 using namespace glass;
 
+extern "C" int64_t glass_rpn_topk_workspace_bytes(int n_img, int h, int w, int num_anchors) {
+  return (int64_t)n_img * (256 + (int64_t)h * w * num_anchors) * (int64_t)sizeof(unsigned int);
+}
+
 extern "C" int glass_rpn_topk_decode(const GlassRpnTopkParams* p, void* stream_v) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
   GLASS_CHECK(p != nullptr && p->pred && p->out_boxes && p->out_scores, "null pointer");
@@ -431,8 +457,17 @@ extern "C" int glass_rpn_topk_decode(const GlassRpnTopkParams* p, void* stream_v
   for (int j = 0; j < 5; ++j) k.wts[j] = p->weights[j];
   k.topk = p->topk; k.level = p->level; k.num_levels = p->num_levels;
   k.out_boxes = p->out_boxes; k.out_scores = p->out_scores;
+  GLASS_CHECK(p->workspace && p->workspace_bytes >= glass_rpn_topk_workspace_bytes(p->n_img, p->h, p->w, p->num_anchors),
+              "workspace too small");
+  k.hist = reinterpret_cast<unsigned int*>(p->workspace);
+  k.keys = k.hist + (size_t)p->n_img * 256;
+  GLASS_CUDA(cudaMemsetAsync(k.hist, 0, (size_t)p->n_img * 256 * sizeof(unsigned int), stream));
+  const int npix = p->h * p->w;
+  int chunks = (npix + 256 * 8 - 1) / (256 * 8);  // ~8 pixels per thread
+  if (chunks > 64) chunks = 64;
+  rpn_keys_kernel<<<dim3(chunks, p->n_img), 256, 0, stream>>>(k);
   rpn_topk_decode_kernel<<<p->n_img, 1024, 0, stream>>>(k);
-  count_launch();
+  count_launch(2);
   GLASS_CUDA(cudaGetLastError());
   return 0;
 }

@@ -12,7 +12,8 @@ MAX_LEVELS = 5
 SYMBOLS = [
     "glass_last_error", "glass_abi_version", "glass_launch_count", "glass_conv_gemm", "glass_pack_nchw",
     "glass_unpack_nchw", "glass_nhwc_f32_to_nchw", "glass_stem_im2col", "glass_gather_taps", "glass_maxpool",
-    "glass_roi_align_rotated", "glass_image_roi_align_rotated", "glass_rpn_topk_decode", "glass_nms_workspace_bytes",
+    "glass_roi_align_rotated", "glass_image_roi_align_rotated", "glass_rpn_topk_decode", "glass_rpn_topk_workspace_bytes",
+    "glass_nms_workspace_bytes",
     "glass_nms_rotated", "glass_box_decode", "glass_gc_attention", "glass_hmean_rows", "glass_lstm_bidir",
     "glass_aster_decode", "glass_aster_finalize",
 ]
@@ -65,7 +66,7 @@ class RpnTopkParams(C.Structure):
         ("num_anchors", C.c_int32), ("stride", C.c_int32),
         ("anchor_w", C.c_float * 16), ("anchor_h", C.c_float * 16), ("anchor_angle", C.c_float * 16),
         ("weights", C.c_float * 5), ("topk", C.c_int32), ("level", C.c_int32), ("num_levels", C.c_int32),
-        ("out_boxes", C.c_void_p), ("out_scores", C.c_void_p),
+        ("out_boxes", C.c_void_p), ("out_scores", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
     ]
 
 
@@ -125,6 +126,8 @@ def load() -> C.CDLL:
     lib.glass_roi_align_rotated.argtypes = [C.POINTER(RoiAlignParams), p]
     lib.glass_image_roi_align_rotated.argtypes = [C.POINTER(ImageRoiAlignParams), p]
     lib.glass_rpn_topk_decode.argtypes = [C.POINTER(RpnTopkParams), p]
+    lib.glass_rpn_topk_workspace_bytes.argtypes = [i, i, i, i]
+    lib.glass_rpn_topk_workspace_bytes.restype = C.c_int64
     lib.glass_nms_workspace_bytes.argtypes = [i, i]
     lib.glass_nms_workspace_bytes.restype = C.c_int64
     lib.glass_nms_rotated.argtypes = [C.POINTER(NmsParams), p]
@@ -137,7 +140,7 @@ def load() -> C.CDLL:
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if name.startswith("glass_") and name not in ("glass_last_error", "glass_abi_version", "glass_launch_count",
-                                                        "glass_nms_workspace_bytes"):
+                                                        "glass_nms_workspace_bytes", "glass_rpn_topk_workspace_bytes"):
             fn.restype = C.c_int
     _lib = lib
     return lib

@@ -68,8 +68,10 @@ class B200RotatedRPN:
         boxes = self.ws.raw("rpn.topk_boxes", (n, L * K, 5), torch.float32)
         scores = self.ws.raw("rpn.topk_scores", (n, L * K), torch.float32)
         for lvl, pred in enumerate(preds):
+            need = ops._lib.load().glass_rpn_topk_workspace_bytes(n, pred.shape[1], pred.shape[2], self.A)
+            wsb = self.ws.raw(f"rpn.topk_ws{lvl}", (need,), torch.uint8)
             ops.rpn_topk_decode(pred, self.A, self.strides[lvl], self.cell_anchors[lvl], self.weights, K, lvl, L,
-                                boxes, scores)
+                                boxes, scores, workspace=wsb)
         return boxes, scores
 
     def select(self, boxes: torch.Tensor, scores: torch.Tensor, img_hw: torch.Tensor):

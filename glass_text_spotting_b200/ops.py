@@ -326,7 +326,8 @@ def image_roi_align_rotated(img: torch.Tensor, pad_hw: Tuple[int, int], mean, st
 
 # ------------------------------------------------------------------------------------------ detector decisions
 def rpn_topk_decode(pred: torch.Tensor, num_anchors: int, stride: int, cell_anchors, weights: Sequence[float],
-                    topk: int, level: int, num_levels: int, out_boxes: torch.Tensor, out_scores: torch.Tensor) -> None:
+                    topk: int, level: int, num_levels: int, out_boxes: torch.Tensor, out_scores: torch.Tensor,
+                    workspace: Optional[torch.Tensor] = None) -> None:
     """pred fp32 [n,h,w,ld] (fused RPN 1x1 output); cell_anchors: list of (w, h, angle) per anchor.
     Writes slots [level*topk, (level+1)*topk) of out_boxes [n, L*topk, 5] / out_scores [n, L*topk]."""
     n, h, w, ld = pred.shape
@@ -339,6 +340,10 @@ def rpn_topk_decode(pred: torch.Tensor, num_anchors: int, stride: int, cell_anch
         p.weights[j] = float(weights[j])
     p.topk, p.level, p.num_levels = topk, level, num_levels
     p.out_boxes, p.out_scores = _ptr(out_boxes), _ptr(out_scores)
+    need = _lib.load().glass_rpn_topk_workspace_bytes(n, h, w, num_anchors)
+    if workspace is None:
+        workspace = torch.empty((need,), dtype=torch.uint8, device=pred.device)
+    p.workspace, p.workspace_bytes = _ptr(workspace), workspace.numel()
     _lib.check(_lib.load().glass_rpn_topk_decode(C.byref(p), _stream()))
 
 

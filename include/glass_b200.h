@@ -188,7 +188,10 @@ typedef struct {
   int32_t level, num_levels;  /* output slot [level*topk, (level+1)*topk) */
   float* out_boxes;           /* [n_img, num_levels*topk, 5] */
   float* out_scores;          /* [n_img, num_levels*topk]; -inf marks an empty slot */
+  void* workspace;            /* dense sortable keys + top-byte histogram */
+  int64_t workspace_bytes;    /* >= glass_rpn_topk_workspace_bytes(n_img, h, w, num_anchors) */
 } GlassRpnTopkParams;
+int64_t glass_rpn_topk_workspace_bytes(int n_img, int h, int w, int num_anchors);
 int glass_rpn_topk_decode(const GlassRpnTopkParams* p, void* stream);
 
 /* glass_nms_rotated -- per image: optional RotatedBoxes.clip + nonempty filter, score threshold,

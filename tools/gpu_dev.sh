@@ -1,9 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -q -m gpu 2>&1 | grep -E "^E   |passed|failed|^FAILED" | cut -c1-300 | tee gpurun_out/test_gpu.log
-GLASS_KB_PER_CHUNK=2 timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu 2>&1 | tail -1 | python -c "
-import json,sys
-d=json.loads(sys.stdin.readline()); print('kb2 full: img/s', round(d['value'],1), 'e2e', round(d['e2e']['value'],1), 'ms', round(d['ms_per_step'],2), 'gemm_ms', round(d['roofline']['kernel_ms_per_step'],2), 'TF', round(d['roofline']['achieved'],1), 'words', d['config']['words_per_step'])"
-timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu 2>&1 | tail -1 | tee gpurun_out/bench.log | python -c "
-import json,sys
-d=json.loads(sys.stdin.readline()); print('kb1 full: img/s', round(d['value'],1), 'e2e', round(d['e2e']['value'],1), 'ms', round(d['ms_per_step'],2), 'gemm_ms', round(d['roofline']['kernel_ms_per_step'],2), 'TF', round(d['roofline']['achieved'],1), 'words', d['config']['words_per_step'])"
+nproc; grep -m1 "model name" /proc/cpuinfo
+( time timeout 1200 python bench.py --steps 5 --warmup 3 ) 2>&1 | tail -5 | tee gpurun_out/bench_default.log | cut -c1-2500
+( time timeout 900 python bench.py --impl reference --steps 2 --warmup 1 ) 2>&1 | tail -5 | tee gpurun_out/bench_reference.log | cut -c1-1200
