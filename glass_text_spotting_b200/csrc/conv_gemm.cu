@@ -52,7 +52,11 @@ struct GemmKernelParams {
   int32_t ld_out, ld_f32, n_store;
 };
 
-template <bool SPLIT>
+// PAIR = true: two CTAs of a cluster (one TPC) cooperate through tcgen05 cta_group::2 -- an M = 256 tile pair
+// shares ONE weight tile, each CTA staging only half of it (N/2 rows), which halves the dominant L2->SMEM
+// traffic of the wide layers.  The leader (even) CTA issues the MMAs for both; each CTA keeps its own 128 rows
+// of the accumulator in its own TMEM and runs its own epilogue.
+template <bool SPLIT, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -70,8 +74,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.tiles_m * p.tiles_n;
   const int kblocks = p.kblocks_per_tap * p.ntaps;
+  // work decomposition: a "unit" is one (M tile, N tile) for a single CTA, or one (M tile PAIR, N tile) for a
+  // CTA pair; units are strided over the CTAs (pairs) of the persistent grid
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int num_workers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int units_m = PAIR ? (p.tiles_m + 1) / 2 : p.tiles_m;
+  const int num_units = units_m * p.tiles_n;
+  const int b_rows = PAIR ? p.bn / 2 : p.bn;  // weight-tile rows staged by this CTA
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a_hi);
@@ -88,15 +100,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], 8);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty_bar[i], PAIR ? 16 : 8);  // one arrive per epilogue warp (of both CTAs)
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_holder, 2 * ACC_COLS);
+    if (PAIR) tmem_alloc_pair(tmem_holder, 2 * ACC_COLS);
+    else tmem_alloc(tmem_holder, 2 * ACC_COLS);
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer's barriers must be initialised before any remote arrive / TMA signal
+  else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
@@ -111,26 +125,31 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int tm = tile / p.tiles_n;
-        const int tn = tile - tm * p.tiles_n;
-        const int m0 = tm * BM;
-        const int n0 = tn * p.bn;
+      for (int unit = worker; unit < num_units; unit += num_workers) {
+        const int um = unit / p.tiles_n;
+        const int tn = unit - um * p.tiles_n;
+        const int m0 = (PAIR ? um * 2 + (int)rank : um) * BM;
+        const int n0 = tn * p.bn + (int)rank * b_rows;  // this CTA's half of the weight tile
         for (int t = 0; t < p.ntaps; ++t) {
           const int arow = m0 + p.tap_shift[t];
           for (int kb = 0; kb < p.kblocks_per_tap; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* s = smem + (size_t)stage * p.stage_bytes;
-            mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)p.stage_bytes);
+            // the leader's barrier collects the bytes of BOTH CTAs' loads
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)p.stage_bytes * (PAIR ? 2u : 1u));
             const int ka = kb * BK;
             const int kw = (t * p.kblocks_per_tap + kb) * BK;
-            tma_load_2d(s, &map_a_hi, &full_bar[stage], ka, arow);
+            auto load = [&](void* dst, const CUtensorMap* map, int c0, int c1) {
+              if (PAIR) tma_load_2d_pair(dst, map, &full_bar[stage], c0, c1);
+              else tma_load_2d(dst, map, &full_bar[stage], c0, c1);
+            };
+            load(s, &map_a_hi, ka, arow);
             if (SPLIT) {
-              tma_load_2d(s + A_TILE_BYTES, &map_a_lo, &full_bar[stage], ka, arow);
-              tma_load_2d(s + 2 * A_TILE_BYTES, &map_b_hi, &full_bar[stage], kw, n0);
-              tma_load_2d(s + 2 * A_TILE_BYTES + p.b_tile_bytes, &map_b_lo, &full_bar[stage], kw, n0);
+              load(s + A_TILE_BYTES, &map_a_lo, ka, arow);
+              load(s + 2 * A_TILE_BYTES, &map_b_hi, kw, n0);
+              load(s + 2 * A_TILE_BYTES + p.b_tile_bytes, &map_b_lo, kw, n0);
             } else {
-              tma_load_2d(s + A_TILE_BYTES, &map_b_hi, &full_bar[stage], kw, n0);
+              load(s + A_TILE_BYTES, &map_b_hi, kw, n0);
             }
             if (++stage == p.num_stages) {
               stage = 0;
@@ -142,12 +161,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_f16_f32(BM, p.bn);
+    if (lane == 0 && leader) {
+      const uint32_t idesc = umma_idesc_f16_f32(PAIR ? 2 * BM : BM, p.bn);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t chunk = 0;  // running chunk counter of this CTA: TMEM buffer = chunk & 1
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t acc) {
+        if (PAIR) umma_f16_ss_pair(d, da, db, idesc, acc);
+        else umma_f16_ss(d, da, db, idesc, acc);
+      };
+      auto commit = [&](uint64_t* bar) {
+        if (PAIR) umma_commit_pair(bar);
+        else umma_commit(bar);
+      };
+      for (int unit = worker; unit < num_units; unit += num_workers) {
         uint32_t d_tmem = 0;
         for (int kb = 0; kb < kblocks; ++kb) {
           const int kin = kb % p.kb_per_chunk;  // position inside the accumulation chunk
@@ -170,17 +197,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
               const uint64_t da_lo = umma_smem_desc_sw128(s + A_TILE_BYTES);
               const uint64_t db_hi = umma_smem_desc_sw128(s + 2 * A_TILE_BYTES);
               const uint64_t db_lo = umma_smem_desc_sw128(s + 2 * A_TILE_BYTES + p.b_tile_bytes);
-              umma_f16_ss(d_tmem, da_lo + koff, db_hi + koff, idesc, acc_flag);
-              umma_f16_ss(d_tmem, da_hi + koff, db_lo + koff, idesc, 1u);
-              umma_f16_ss(d_tmem, da_hi + koff, db_hi + koff, idesc, 1u);
+              mma(d_tmem, da_lo + koff, db_hi + koff, acc_flag);
+              mma(d_tmem, da_hi + koff, db_lo + koff, 1u);
+              mma(d_tmem, da_hi + koff, db_hi + koff, 1u);
             } else {
               const uint64_t db_hi = umma_smem_desc_sw128(s + A_TILE_BYTES);
-              umma_f16_ss(d_tmem, da_hi + koff, db_hi + koff, idesc, acc_flag);
+              mma(d_tmem, da_hi + koff, db_hi + koff, acc_flag);
             }
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          commit(&empty_bar[stage]);  // frees the smem slot (in both CTAs) when these MMAs retire
           if (kin == p.kb_per_chunk - 1 || kb == kblocks - 1) {
-            umma_commit(&tmem_full_bar[chunk & 1u]);  // chunk complete -> epilogue drains it
+            commit(&tmem_full_bar[chunk & 1u]);  // chunk complete -> the epilogue(s) drain it
             ++chunk;
           }
           if (++stage == p.num_stages) {
@@ -209,9 +236,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     float* stage = stage_base + e * 1024;
     const int chunks_per_tile = (kblocks + p.kb_per_chunk - 1) / p.kb_per_chunk;
     uint32_t chunk = 0;  // mirrors the MMA warp's running chunk counter
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int tm = tile / p.tiles_n;
-      const int tn = tile - tm * p.tiles_n;
+    for (int unit = worker; unit < num_units; unit += num_workers) {
+      const int um = unit / p.tiles_n;
+      const int tn = unit - um * p.tiles_n;
+      const int tm = PAIR ? um * 2 + (int)rank : um;
       const int n0 = tn * p.bn;
       const int64_t m = (int64_t)tm * BM + row_in_tile;
       bool valid = m < p.rows_m;
@@ -253,7 +281,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         }
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_remote(&tmem_empty_bar[buf], 0u);  // the leader's MMA thread owns the wait
+          else mbar_arrive(&tmem_empty_bar[buf]);
+        }
       }
 
       // ---- final math + stores.  Each lane owns one output ROW in registers, but a warp store that
@@ -357,10 +388,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();
+  else __syncthreads();
   if (warp == 2) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, 2 * ACC_COLS);
+    if (PAIR) tmem_dealloc_pair(tmem_base, 2 * ACC_COLS);
+    else tmem_dealloc(tmem_base, 2 * ACC_COLS);
   }
 }
 
@@ -416,6 +449,18 @@ extern "C" int glass_conv_gemm(const GlassConvGemmParams* p, void* stream_v) {
                   al16(p->bias),
               "all pointers must be 16-byte aligned");
 
+  // CTA-pair (cta_group::2) mode: worth it when the weight tile is wide and there is enough work to pair up
+  const int sms = num_sms();
+  GLASS_CHECK(sms > 0, "no CUDA device");
+  const int tiles_m_all = (int)((rows_m + BM - 1) / BM);
+  bool pair = (bn % 32 == 0) && bn >= 128 && (int64_t)tiles_m_all * (p->n / bn) >= sms;
+  if (p->pair_mode == 1) pair = false;
+  if (p->pair_mode == 2) {
+    GLASS_CHECK(bn % 32 == 0, "pair mode needs a tile width that is a multiple of 32");
+    pair = true;
+  }
+  const int b_rows = pair ? bn / 2 : bn;
+
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   const uint64_t ktot = (uint64_t)p->k_per_tap * p->ntaps;
   // compact-channel mode: rows overlap (stride a_ld < 64 elements); the last 64/a_ld - 1 rows would read past
@@ -428,10 +473,10 @@ extern "C" int glass_conv_gemm(const GlassConvGemmParams* p, void* stream_v) {
     a_rows = (uint64_t)p->rows_a - (uint64_t)(BK / a_ld) + 1;
   }
   if (make_map_2d(&ma_hi, p->a_hi, p->k_per_tap, a_rows, BK, BM, a_ld)) return -1;
-  if (make_map_2d(&mb_hi, p->b_hi, ktot, p->n, BK, bn)) return -1;
+  if (make_map_2d(&mb_hi, p->b_hi, ktot, p->n, BK, b_rows)) return -1;
   if (split) {
     if (make_map_2d(&ma_lo, p->a_lo, p->k_per_tap, a_rows, BK, BM, a_ld)) return -1;
-    if (make_map_2d(&mb_lo, p->b_lo, ktot, p->n, BK, bn)) return -1;
+    if (make_map_2d(&mb_lo, p->b_lo, ktot, p->n, BK, b_rows)) return -1;
   } else {
     ma_lo = ma_hi;
     mb_lo = mb_hi;
@@ -445,7 +490,7 @@ extern "C" int glass_conv_gemm(const GlassConvGemmParams* p, void* stream_v) {
   k.kblocks_per_tap = p->k_per_tap / BK;
   k.ntaps = p->ntaps;
   for (int i = 0; i < GLASS_MAX_TAPS; ++i) k.tap_shift[i] = p->tap_shift[i];
-  k.b_tile_bytes = bn * BK * 2;
+  k.b_tile_bytes = b_rows * BK * 2;
   k.stage_bytes = (A_TILE_BYTES + k.b_tile_bytes) * (split ? 2 : 1);
   const int smem_budget = 227 * 1024 - EPI_STAGE_BYTES - 1024 /*align slack*/ - 256 /*barriers*/;
   k.num_stages = smem_budget / k.stage_bytes;
@@ -464,16 +509,38 @@ extern "C" int glass_conv_gemm(const GlassConvGemmParams* p, void* stream_v) {
   // always ask for > half of the SM's shared memory: exactly one CTA per SM owns all 512 TMEM columns
   const int smem_bytes = k.num_stages * k.stage_bytes + EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   const int smem_req = smem_bytes < 120 * 1024 ? 120 * 1024 : smem_bytes;
-  const int sms = num_sms();
-  GLASS_CHECK(sms > 0, "no CUDA device");
-  const int total_tiles = k.tiles_m * k.tiles_n;
-  const int grid = total_tiles < sms ? total_tiles : sms;
-  if (split) {
-    GLASS_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_req));
-    conv_gemm_kernel<true><<<grid, NUM_THREADS, smem_req, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, k);
+  if (!pair) {
+    const int total_tiles = k.tiles_m * k.tiles_n;
+    const int grid = total_tiles < sms ? total_tiles : sms;
+    if (split) {
+      GLASS_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_req));
+      conv_gemm_kernel<true, false><<<grid, NUM_THREADS, smem_req, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, k);
+    } else {
+      GLASS_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_req));
+      conv_gemm_kernel<false, false><<<grid, NUM_THREADS, smem_req, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, k);
+    }
   } else {
-    GLASS_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_req));
-    conv_gemm_kernel<false><<<grid, NUM_THREADS, smem_req, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, k);
+    const int units = ((k.tiles_m + 1) / 2) * k.tiles_n;
+    const int pairs = units < sms / 2 ? units : sms / 2;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = smem_req;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (split) {
+      GLASS_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_req));
+      GLASS_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true, true>, ma_hi, ma_lo, mb_hi, mb_lo, k));
+    } else {
+      GLASS_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_req));
+      GLASS_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<false, true>, ma_hi, ma_lo, mb_hi, mb_lo, k));
+    }
   }
   count_launch();
   GLASS_CUDA(cudaGetLastError());

@@ -89,6 +89,7 @@ typedef struct {
   int32_t n_store;    /* columns actually stored (<= n); 0 = n */
   int32_t kb_per_chunk; /* 64-wide k-blocks summed inside the tensor core between drains; 0 = default (1:
                            every k-block, fp32-SGEMM-grade; larger = faster, error grows with the chain) */
+  int32_t pair_mode;    /* 0 = auto, 1 = one CTA per tile, 2 = CTA pairs (tcgen05 cta_group::2, shared weight tile) */
 } GlassConvGemmParams;
 int glass_conv_gemm(const GlassConvGemmParams* p, void* stream);
 
