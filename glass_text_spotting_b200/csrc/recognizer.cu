@@ -224,7 +224,7 @@ __global__ void hmean_rows_kernel(const __half* __restrict__ shi, const __half* 
 // gates_in fp32 [n_seq*T, 2*4H]: x W_ih^T + b_ih + b_hh, forward gates in [0,4H), backward in [4H,8H);
 // PyTorch gate order (i, f, g, o).  whh_t fp32 [2][H][4H] (k-major).  Output split-fp16 rows
 // [n_seq*T, 2H] (forward | backward) + optional fp32 copy.
-constexpr int LSTM_H = 256, LSTM_G = 1024, LSTM_WPC = 4;
+constexpr int LSTM_H = 256, LSTM_G = 1024, LSTM_WPC = 8;  // 8 words per CTA: W_hh^T streams once per 8 words
 
 __global__ void __launch_bounds__(1024) lstm_bidir_kernel(const float* __restrict__ gates_in,
                                                           const float* __restrict__ whh_t, int n_seq, int T,
@@ -253,18 +253,17 @@ __global__ void __launch_bounds__(1024) lstm_bidir_kernel(const float* __restric
 #pragma unroll 8
     for (int k = 0; k < LSTM_H; ++k) {
       const float wv = __ldg(wt + (int64_t)k * LSTM_G + j);
-      const float4 hv = *reinterpret_cast<const float4*>(&h_s[k][0]);
-      acc[0] += wv * hv.x;
-      acc[1] += wv * hv.y;
-      acc[2] += wv * hv.z;
-      acc[3] += wv * hv.w;
+      const float4 h0 = *reinterpret_cast<const float4*>(&h_s[k][0]);
+      const float4 h1 = *reinterpret_cast<const float4*>(&h_s[k][4]);
+      acc[0] += wv * h0.x; acc[1] += wv * h0.y; acc[2] += wv * h0.z; acc[3] += wv * h0.w;
+      acc[4] += wv * h1.x; acc[5] += wv * h1.y; acc[6] += wv * h1.z; acc[7] += wv * h1.w;
     }
     const int gate = j >> 8;  // 0:i 1:f 2:g 3:o
 #pragma unroll
     for (int w = 0; w < LSTM_WPC; ++w) g_s[w][j] = gate == 2 ? tanhf(acc[w]) : sigmoidf_(acc[w]);
     __syncthreads();
-    {
-      const int w = j >> 8, u = j & 255;  // 4 words x 256 units = 1024 threads
+    for (int wu = j; wu < LSTM_WPC * LSTM_H; wu += blockDim.x) {
+      const int w = wu >> 8, u = wu & 255;  // (word, hidden unit)
       const float ig = g_s[w][u], fg = g_s[w][256 + u], gg = g_s[w][512 + u], og = g_s[w][768 + u];
       const float c = fg * c_s[w][u] + ig * gg;
       const float hn = og * tanhf(c);
