@@ -10,8 +10,8 @@
 //      tools/accuracy_probe.py), so a chain is cut every kb_per_chunk k-blocks: the MMA warp switches
 //      to the other TMEM buffer and the epilogue warps drain the finished chunk into fp32 registers
 //      with round-to-nearest adds (Ootomo & Yokota's "accumulate outside the tensor core").
-// Roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warp 2 = TMEM
-// allocator, warps 4..11 = epilogue (TMEM lane quadrant = warp % 4, two warps per quadrant split the columns).
+// Roles (640 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warp 2 = TMEM
+// allocator, warps 4..19 = epilogue (TMEM lane quadrant = warp % 4, four warps per quadrant split the columns).
 // Precision modes: fp16x3 split (3 MMAs per k-step into the same accumulator: hi*hi, hi*lo, lo*hi)
 // gives fp32-grade results (22-bit operands, fp32 accumulate); mode 1 issues only hi*hi.
 #include <cuda.h>
@@ -26,10 +26,11 @@ static constexpr int BM = 128;
 static constexpr int BK = 64;
 static constexpr int ACC_COLS = 256;  // TMEM columns per accumulator stage
 static constexpr int A_TILE_BYTES = BM * BK * 2;
-static constexpr int NUM_THREADS = 384;  // 4 control warps + 8 epilogue warps
+static constexpr int EPI_WARPS = 16;
+static constexpr int NUM_THREADS = 128 + 32 * EPI_WARPS;  // 4 control warps + 16 epilogue warps
 static constexpr int MAX_STAGES = 8;
-static constexpr int EPI_STAGE_BYTES = 8 * 4096;  // per epilogue warp: 32 rows x 32 fp32 columns
-static constexpr int MAX_CHUNKS_PER_WARP = 8;  // 256 columns / 16 per chunk / 2 column halves
+static constexpr int EPI_STAGE_BYTES = EPI_WARPS * 2048;  // per epilogue warp: 32 rows x 16 fp32 columns
+static constexpr int MAX_CHUNKS_PER_WARP = 4;  // 256 columns / 16 per chunk / 4 column parts
 
 struct GemmKernelParams {
   int64_t rows_m;
@@ -100,7 +101,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], PAIR ? 16 : 8);  // one arrive per epilogue warp (of both CTAs)
+      mbar_init(&tmem_empty_bar[i], PAIR ? 2 * EPI_WARPS : EPI_WARPS);  // one arrive per epilogue warp (of both CTAs)
     }
     fence_barrier_init();
   }
@@ -117,7 +118,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   // Register re-balancing between the warpgroups (the launch gives every thread 168): the control
   // warpgroup needs few registers, the two epilogue warpgroups hold the whole 128 x BN fp32 tile.
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
   }
 
   if (warp == 0) {
@@ -218,7 +219,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       }
     }
   } else if (warp >= 4) {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     // ===================================================== epilogue (8 warps)
     // warp e = warp-4: TMEM lane quadrant q = e & 3 (== warp % 4, the tcgen05.ld lane rule), column half
     // e >> 2.  Each thread owns one output row of the tile and walks its half of the 16-column chunks.
@@ -226,14 +227,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     // chunks of a tile, are issued before the accumulator is even ready).
     const int e = warp - 4;
     const int q = e & 3;
-    const int half = e >> 2;
+    const int part = e >> 2;  // which quarter of the tile's columns
     const int row_in_tile = q * 32 + lane;
     const int plane = p.m_h * p.m_w;
     const int nchunks = p.bn / 16;
-    const int c_begin = half ? (nchunks + 1) / 2 : 0;
-    const int c_end = half ? nchunks : (nchunks + 1) / 2;
+    const int cbase = nchunks >> 2, crem = nchunks & 3;
+    const int c_begin = part * cbase + min(part, crem);
+    const int c_end = c_begin + cbase + (part < crem ? 1 : 0);
     const bool has_res = p.res_hi != nullptr;
-    float* stage = stage_base + e * 1024;
+    float* stage = stage_base + e * 512;
     const int chunks_per_tile = (kblocks + p.kb_per_chunk - 1) / p.kb_per_chunk;
     uint32_t chunk = 0;  // mirrors the MMA warp's running chunk counter
     for (int unit = worker; unit < num_units; unit += num_workers) {
@@ -293,57 +295,52 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       // written back in the transposed mapping: 4 lanes x 16 B = 64 contiguous bytes of one row per
       // plane, 8 rows per instruction.  The residual is read in that same coalesced mapping.
 #pragma unroll
-      for (int gi = 0; gi < MAX_CHUNKS_PER_WARP / 2; ++gi) {
-        const int cb = c_begin + 2 * gi;  // first 16-column chunk of this 32-column group
-        if (cb < c_end) {                 // warp-uniform
+      for (int ci = 0; ci < MAX_CHUNKS_PER_WARP; ++ci) {
+        const int c = c_begin + ci;  // 16-column chunk (warp-uniform)
+        if (c < c_end) {
+          {
+            const int n = n0 + c * 16;
+            float v[16];
 #pragma unroll
-          for (int h2 = 0; h2 < 2; ++h2) {
-            const int ci = 2 * gi + h2;
-            const int c = c_begin + ci;
-            if (c < c_end) {
-              const int n = n0 + c * 16;
-              float v[16];
+            for (int j = 0; j < 16; ++j) v[j] = accv[ci][j];
+            if (p.scale != nullptr) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = accv[ci][j];
-              if (p.scale != nullptr) {
-#pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                  const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + n + j));
-                  v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
-                }
+              for (int j = 0; j < 16; j += 4) {
+                const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + n + j));
+                v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
               }
-              if (p.bias != nullptr) {
+            }
+            if (p.bias != nullptr) {
 #pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
-                  v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-                }
+              for (int j = 0; j < 16; j += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
               }
-              if (p.relu_pre) {
+            }
+            if (p.relu_pre) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-              }
+              for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
 #pragma unroll
-              for (int jj = 0; jj < 4; ++jj) {
-                const int phys = (h2 * 4 + jj) ^ (lane & 7);
-                *reinterpret_cast<float4*>(stage + lane * 32 + phys * 4) =
-                    make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
-              }
+            for (int jj = 0; jj < 4; ++jj) {
+              const int phys = jj ^ ((lane >> 1) & 3);
+              *reinterpret_cast<float4*>(stage + lane * 16 + phys * 4) =
+                  make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
             }
           }
           __syncwarp();
-          const int ncols = min(32, (c_end - cb) * 16);
-          const int cg = lane & 3;  // 8-column group inside the 32-column stage
-          const int n = n0 + cb * 16 + cg * 8;
+          const int cg = lane & 1;  // 8-column half of the 16-column stage
+          const int n = n0 + c * 16 + cg * 8;
 #pragma unroll
-          for (int ps = 0; ps < 4; ++ps) {
-            const int R = ps * 8 + (lane >> 2);
+          for (int ps = 0; ps < 2; ++ps) {
+            const int R = ps * 16 + (lane >> 1);
             const int valid_r = __shfl_sync(0xffffffffu, (int)valid, R);
             const long long out_row_r = __shfl_sync(0xffffffffu, (long long)out_row, R);
             const long long res_row_r = __shfl_sync(0xffffffffu, (long long)res_row, R);
-            if (valid_r && cg * 8 < ncols && n < p.n_store) {
-              const float4 a = *reinterpret_cast<const float4*>(stage + R * 32 + (((2 * cg) ^ (R & 7)) * 4));
-              const float4 b = *reinterpret_cast<const float4*>(stage + R * 32 + (((2 * cg + 1) ^ (R & 7)) * 4));
+            if (valid_r && n < p.n_store) {
+              const int sw = (R >> 1) & 3;
+              const float4 a = *reinterpret_cast<const float4*>(stage + R * 16 + (((2 * cg) ^ sw) * 4));
+              const float4 b = *reinterpret_cast<const float4*>(stage + R * 16 + (((2 * cg + 1) ^ sw) * 4));
               float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
               if (has_res) {
                 const uint4 rh = __ldg(reinterpret_cast<const uint4*>(p.res_hi + res_row_r * p.ld_out + n));
@@ -496,7 +493,9 @@ extern "C" int glass_conv_gemm(const GlassConvGemmParams* p, void* stream_v) {
   k.num_stages = smem_budget / k.stage_bytes;
   if (k.num_stages > MAX_STAGES) k.num_stages = MAX_STAGES;
   GLASS_CHECK(k.num_stages >= 2, "stage too large");
-  k.kb_per_chunk = p->kb_per_chunk > 0 ? p->kb_per_chunk : 1;
+  // default: drain every 2 k-blocks (split) / 4 (single pass): a drain reads the whole 128 x BN fp32 tile from TMEM
+  // (64 B/clk/SM), which hides behind two k-blocks of MMA work but not behind one
+  k.kb_per_chunk = p->kb_per_chunk > 0 ? p->kb_per_chunk : (split ? 2 : 4);
   k.m_h = p->m_h; k.m_w = p->m_w; k.m_border = p->m_border;
   k.scale = p->scale; k.bias = p->bias;
   k.relu_pre = p->relu_pre; k.relu_post = p->relu_post;
