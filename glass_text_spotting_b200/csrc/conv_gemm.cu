@@ -450,7 +450,7 @@ extern "C" int glass_conv_gemm(const GlassConvGemmParams* p, void* stream_v) {
   const int sms = num_sms();
   GLASS_CHECK(sms > 0, "no CUDA device");
   const int tiles_m_all = (int)((rows_m + BM - 1) / BM);
-  bool pair = (bn % 32 == 0) && bn >= 128 && (int64_t)tiles_m_all * (p->n / bn) >= sms;
+  bool pair = (bn % 32 == 0) && bn >= 64 && (int64_t)tiles_m_all * (p->n / bn) >= sms;
   if (p->pair_mode == 1) pair = false;
   if (p->pair_mode == 2) {
     GLASS_CHECK(bn % 32 == 0, "pair mode needs a tile width that is a multiple of 32");

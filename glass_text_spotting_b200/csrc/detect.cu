@@ -76,15 +76,17 @@ struct RpnTopkKernelParams {
   float* out_boxes;
   float* out_scores;
   unsigned int* keys;  // [n_img, h*w*A] dense sortable keys
-  unsigned int* hist;  // [n_img, 256] histogram of the top 8 key bits
+  unsigned int* hist;  // [n_img, 4096] histogram of the top 12 key bits
 };
+constexpr int RPN_HIST0_BITS = 12, RPN_HIST0_BINS = 1 << RPN_HIST0_BITS;
 
-// Pass 0, many CTAs per image: gather the strided logits into a dense key array and histogram the top byte.
+// Pass 0, many CTAs per image: gather the strided logits into a dense key array and histogram the top 12 bits
+// (sign, exponent, 3 mantissa bits: fine enough that the later passes only touch a few thousand candidates).
 __global__ void __launch_bounds__(256) rpn_keys_kernel(const RpnTopkKernelParams p) {
-  __shared__ unsigned int hist[256];
+  __shared__ unsigned int hist[RPN_HIST0_BINS];
   const int img = blockIdx.y;
   const int npix = p.h * p.w;
-  hist[threadIdx.x] = 0;
+  for (int i = threadIdx.x; i < RPN_HIST0_BINS; i += blockDim.x) hist[i] = 0;
   __syncthreads();
   const float* base = p.pred + (int64_t)img * npix * p.ld;
   unsigned int* keys = p.keys + (int64_t)img * npix * p.A;
@@ -93,16 +95,18 @@ __global__ void __launch_bounds__(256) rpn_keys_kernel(const RpnTopkKernelParams
     for (int a = 0; a < p.A; ++a) {
       const unsigned key = float_to_sortable(__ldg(row + a));
       keys[(int64_t)pix * p.A + a] = key;
-      atomicAdd(&hist[key >> 24], 1u);
+      atomicAdd(&hist[key >> (32 - RPN_HIST0_BITS)], 1u);
     }
   }
   __syncthreads();
-  if (hist[threadIdx.x]) atomicAdd(&p.hist[img * 256 + threadIdx.x], hist[threadIdx.x]);
+  for (int i = threadIdx.x; i < RPN_HIST0_BINS; i += blockDim.x)
+    if (hist[i]) atomicAdd(&p.hist[img * RPN_HIST0_BINS + i], hist[i]);
 }
 
 // Passes 1..3 + compaction + sort + decode, one CTA per image, over the dense keys (coalesced).
 __global__ void __launch_bounds__(1024) rpn_topk_decode_kernel(const RpnTopkKernelParams p) {
-  __shared__ unsigned int hist[256];
+  __shared__ unsigned int hist[RPN_HIST0_BINS];
+  __shared__ unsigned int coarse[32];
   __shared__ unsigned int s_prefix, s_mask, s_remaining, s_cnt_gt, s_cnt_eq;
   __shared__ unsigned long long sel[1024];
   const int img = blockIdx.x;
@@ -122,32 +126,50 @@ __global__ void __launch_bounds__(1024) rpn_topk_decode_kernel(const RpnTopkKern
   for (int i = threadIdx.x; i < 1024; i += blockDim.x) sel[i] = ~0ull;
   __syncthreads();
 
-  // radix select (MSB first) of the want-th largest key; the top byte's histogram comes from pass 0
-  for (int pass = 0; pass < 4; ++pass) {
-    const int shift = 24 - 8 * pass;
+  // radix select (MSB first) of the want-th largest key in digits of 12 + 10 + 10 bits; the 12-bit
+  // histogram comes from pass 0, the two remaining passes only count keys inside the threshold bin
+  for (int pass = 0; pass < 3; ++pass) {
+    const int bits = pass == 0 ? RPN_HIST0_BITS : 10;
+    const int shift = pass == 0 ? 20 : (pass == 1 ? 10 : 0);
+    const int bins = 1 << bits;
     const unsigned prefix = s_prefix, mask = s_mask;
     if (pass == 0) {
-      for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = p.hist[img * 256 + i];
+      for (int i = threadIdx.x; i < bins; i += blockDim.x) hist[i] = p.hist[img * RPN_HIST0_BINS + i];
     } else {
-      for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+      for (int i = threadIdx.x; i < bins; i += blockDim.x) hist[i] = 0;
       __syncthreads();
       for (int e = threadIdx.x; e < n; e += blockDim.x) {
         const unsigned key = keys[e];
-        if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & (unsigned)(bins - 1)], 1u);
       }
     }
     __syncthreads();
+    {  // two-level scan from the top bin down: 32 warp sums, then one thread walks <= 32 + bins/32 entries
+      const int per_warp = bins >> 5;
+      const int wid = threadIdx.x >> 5, ln = threadIdx.x & 31;
+      unsigned part = 0;
+      for (int i = ln; i < per_warp; i += 32) part += hist[wid * per_warp + i];
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      if (ln == 0) coarse[wid] = part;
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
+      const int per_warp = bins >> 5;
       unsigned remaining = s_remaining;
-      int d = 255;
-      for (; d > 0; --d) {
+      int wsel = 31;
+      for (; wsel > 0; --wsel) {
+        if (coarse[wsel] >= remaining) break;
+        remaining -= coarse[wsel];
+      }
+      int d = (wsel + 1) * per_warp - 1;
+      for (; d > wsel * per_warp; --d) {
         const unsigned c = hist[d];
         if (c >= remaining) break;
         remaining -= c;
       }
       s_remaining = remaining;
       s_prefix = prefix | ((unsigned)d << shift);
-      s_mask = mask | (255u << shift);
+      s_mask = mask | ((unsigned)(bins - 1) << shift);
     }
     __syncthreads();
   }
@@ -437,7 +459,7 @@ __global__ void box_decode_kernel(const float* __restrict__ pred, int ld, const 
 using namespace glass;
 
 extern "C" int64_t glass_rpn_topk_workspace_bytes(int n_img, int h, int w, int num_anchors) {
-  return (int64_t)n_img * (256 + (int64_t)h * w * num_anchors) * (int64_t)sizeof(unsigned int);
+  return (int64_t)n_img * (RPN_HIST0_BINS + (int64_t)h * w * num_anchors) * (int64_t)sizeof(unsigned int);
 }
 
 extern "C" int glass_rpn_topk_decode(const GlassRpnTopkParams* p, void* stream_v) {
@@ -460,8 +482,8 @@ extern "C" int glass_rpn_topk_decode(const GlassRpnTopkParams* p, void* stream_v
   GLASS_CHECK(p->workspace && p->workspace_bytes >= glass_rpn_topk_workspace_bytes(p->n_img, p->h, p->w, p->num_anchors),
               "workspace too small");
   k.hist = reinterpret_cast<unsigned int*>(p->workspace);
-  k.keys = k.hist + (size_t)p->n_img * 256;
-  GLASS_CUDA(cudaMemsetAsync(k.hist, 0, (size_t)p->n_img * 256 * sizeof(unsigned int), stream));
+  k.keys = k.hist + (size_t)p->n_img * RPN_HIST0_BINS;
+  GLASS_CUDA(cudaMemsetAsync(k.hist, 0, (size_t)p->n_img * RPN_HIST0_BINS * sizeof(unsigned int), stream));
   const int npix = p->h * p->w;
   int chunks = (npix + 256 * 8 - 1) / (256 * 8);  // ~8 pixels per thread
   if (chunks > 64) chunks = 64;
