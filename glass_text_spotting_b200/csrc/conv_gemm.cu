@@ -257,6 +257,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         res_row = ((int64_t)img * p.res_hp + (y >> p.res_shift) + p.res_border) * p.res_wp + (x >> p.res_shift) +
                   p.res_border;
       }
+      // the residual does not depend on the MMA: pull this lane's row segment into L2 now, so the coalesced
+      // loads of the final phase find it there instead of waiting on HBM
+      if (has_res && valid && c_begin < c_end && n0 + c_begin * 16 < p.n_store) {
+        const __half* rp_hi = p.res_hi + res_row * p.ld_out + n0 + c_begin * 16;
+        const __half* rp_lo = p.res_lo + res_row * p.ld_out + n0 + c_begin * 16;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(rp_hi));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(rp_lo));
+      }
+
       // ---- drain every accumulation chunk of this tile from TMEM into fp32 registers (round-to-nearest
       // adds): the tensor core's own accumulator truncates, so chains are kept to kb_per_chunk k-blocks.
       float accv[MAX_CHUNKS_PER_WARP][16];
