@@ -15,6 +15,7 @@
 // Precision modes: fp16x3 split (3 MMAs per k-step into the same accumulator: hi*hi, hi*lo, lo*hi)
 // gives fp32-grade results (22-bit operands, fp32 accumulate); mode 1 issues only hi*hi.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "glass_b200.h"
@@ -24,7 +25,8 @@ namespace glass {
 
 static constexpr int BM = 128;
 static constexpr int BK = 64;
-static constexpr int ACC_COLS = 256;  // TMEM columns per accumulator stage
+static constexpr int TMEM_COLS = 512;     // all of the SM's tensor memory
+static constexpr int MAX_ACC_BUFS = 8;    // accumulator ring: 512 / max(64, tile width rounded to a power of two)
 static constexpr int A_TILE_BYTES = BM * BK * 2;
 static constexpr int EPI_WARPS = 16;
 static constexpr int NUM_THREADS = 128 + 32 * EPI_WARPS;  // 4 control warps + 16 epilogue warps
@@ -39,6 +41,7 @@ struct GemmKernelParams {
   int32_t tap_shift[GLASS_MAX_TAPS];
   int32_t num_stages, stage_bytes, b_tile_bytes;
   int32_t kb_per_chunk;  // k-blocks accumulated inside the tensor core before a drain to registers
+  int32_t acc_cols, acc_bufs;  // TMEM accumulator ring: acc_bufs buffers of acc_cols columns (acc_cols * acc_bufs = 512)
   int32_t m_h, m_w, m_border;
   const float* scale;
   const float* bias;
@@ -69,9 +72,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.num_stages * p.stage_bytes + EPI_STAGE_BYTES);
   uint64_t* full_bar = bars;                      // [MAX_STAGES]
   uint64_t* empty_bar = bars + MAX_STAGES;        // [MAX_STAGES]
-  uint64_t* tmem_full_bar = bars + 2 * MAX_STAGES;   // [2]
-  uint64_t* tmem_empty_bar = bars + 2 * MAX_STAGES + 2;  // [2]
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
+  uint64_t* tmem_full_bar = bars + 2 * MAX_STAGES;   // [MAX_ACC_BUFS]
+  uint64_t* tmem_empty_bar = bars + 2 * MAX_STAGES + MAX_ACC_BUFS;  // [MAX_ACC_BUFS]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 2 * MAX_ACC_BUFS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -99,15 +102,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < MAX_ACC_BUFS; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
       mbar_init(&tmem_empty_bar[i], PAIR ? 2 * EPI_WARPS : EPI_WARPS);  // one arrive per epilogue warp (of both CTAs)
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    if (PAIR) tmem_alloc_pair(tmem_holder, 2 * ACC_COLS);
-    else tmem_alloc(tmem_holder, 2 * ACC_COLS);
+    if (PAIR) tmem_alloc_pair(tmem_holder, TMEM_COLS);
+    else tmem_alloc(tmem_holder, TMEM_COLS);
   }
   tcgen05_fence_before();
   if (PAIR) cluster_sync_all();  // the peer's barriers must be initialised before any remote arrive / TMA signal
@@ -181,10 +184,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           const int kin = kb % p.kb_per_chunk;  // position inside the accumulation chunk
           if (kin == 0) {
             // a new chunk starts from zero in the other TMEM buffer once the epilogue has drained it
-            const uint32_t buf = chunk & 1u;
-            mbar_wait(&tmem_empty_bar[buf], ((chunk >> 1) & 1u) ^ 1u);
+            const uint32_t buf = chunk % (uint32_t)p.acc_bufs;
+            mbar_wait(&tmem_empty_bar[buf], ((chunk / (uint32_t)p.acc_bufs) & 1u) ^ 1u);
             tcgen05_fence_after();
-            d_tmem = tmem_base + buf * (uint32_t)ACC_COLS;
+            d_tmem = tmem_base + buf * (uint32_t)p.acc_cols;
           }
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
@@ -208,7 +211,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           }
           commit(&empty_bar[stage]);  // frees the smem slot (in both CTAs) when these MMAs retire
           if (kin == p.kb_per_chunk - 1 || kb == kblocks - 1) {
-            commit(&tmem_full_bar[chunk & 1u]);  // chunk complete -> the epilogue(s) drain it
+            commit(&tmem_full_bar[chunk % (uint32_t)p.acc_bufs]);  // chunk complete -> the epilogue(s) drain it
             ++chunk;
           }
           if (++stage == p.num_stages) {
@@ -271,10 +274,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       float accv[MAX_CHUNKS_PER_WARP][16];
       const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
       for (int g = 0; g < chunks_per_tile; ++g, ++chunk) {
-        const uint32_t buf = chunk & 1u;
-        mbar_wait(&tmem_full_bar[buf], (chunk >> 1) & 1u);
+        const uint32_t buf = chunk % (uint32_t)p.acc_bufs;
+        mbar_wait(&tmem_full_bar[buf], (chunk / (uint32_t)p.acc_bufs) & 1u);
         tcgen05_fence_after();
-        const uint32_t t_row = tmem_base + buf * (uint32_t)ACC_COLS + lane_sel;
+        const uint32_t t_row = tmem_base + buf * (uint32_t)p.acc_cols + lane_sel;
 #pragma unroll
         for (int ci = 0; ci < MAX_CHUNKS_PER_WARP; ++ci) {
           if (c_begin + ci < c_end) {
@@ -398,8 +401,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   else __syncthreads();
   if (warp == 2) {
     tcgen05_fence_after();
-    if (PAIR) tmem_dealloc_pair(tmem_base, 2 * ACC_COLS);
-    else tmem_dealloc(tmem_base, 2 * ACC_COLS);
+    if (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -498,13 +501,19 @@ extern "C" int glass_conv_gemm(const GlassConvGemmParams* p, void* stream_v) {
   for (int i = 0; i < GLASS_MAX_TAPS; ++i) k.tap_shift[i] = p->tap_shift[i];
   k.b_tile_bytes = b_rows * BK * 2;
   k.stage_bytes = (A_TILE_BYTES + k.b_tile_bytes) * (split ? 2 : 1);
-  const int smem_budget = 227 * 1024 - EPI_STAGE_BYTES - 1024 /*align slack*/ - 256 /*barriers*/;
+  const int smem_budget = 227 * 1024 - EPI_STAGE_BYTES - 1024 /*align slack*/ - 512 /*barriers*/;
   k.num_stages = smem_budget / k.stage_bytes;
   if (k.num_stages > MAX_STAGES) k.num_stages = MAX_STAGES;
   GLASS_CHECK(k.num_stages >= 2, "stage too large");
   // default: drain every 2 k-blocks (split) / 4 (single pass): a drain reads the whole 128 x BN fp32 tile from TMEM
   // (64 B/clk/SM), which hides behind two k-blocks of MMA work but not behind one
   k.kb_per_chunk = p->kb_per_chunk > 0 ? p->kb_per_chunk : (split ? 2 : 4);
+  k.acc_cols = bn <= 64 ? 64 : (bn <= 128 ? 128 : 256);
+  k.acc_bufs = TMEM_COLS / k.acc_cols;  // narrow tiles get a deeper ring: the chunk hand-shake latency hides behind it
+  if (const char* e = getenv("GLASS_ACC_BUFS")) {  // tuning / A-B knob
+    const int v = atoi(e);
+    if (v >= 2 && v <= k.acc_bufs) k.acc_bufs = v;
+  }
   k.m_h = p->m_h; k.m_w = p->m_w; k.m_border = p->m_border;
   k.scale = p->scale; k.bias = p->bias;
   k.relu_pre = p->relu_pre; k.relu_post = p->relu_post;
@@ -515,7 +524,7 @@ extern "C" int glass_conv_gemm(const GlassConvGemmParams* p, void* stream_v) {
   k.ld_out = p->ld_out; k.ld_f32 = p->ld_f32; k.n_store = n_store;
 
   // always ask for > half of the SM's shared memory: exactly one CTA per SM owns all 512 TMEM columns
-  const int smem_bytes = k.num_stages * k.stage_bytes + EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  const int smem_bytes = k.num_stages * k.stage_bytes + EPI_STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
   const int smem_req = smem_bytes < 120 * 1024 ? 120 * 1024 : smem_bytes;
   if (!pair) {
     const int total_tiles = k.tiles_m * k.tiles_n;
