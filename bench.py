@@ -306,15 +306,16 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up (also allocates every workspace buffer once)
+    # ---- warm-up (also allocates every workspace buffer once); the clock sampler runs from here to the end of the
+    # timed region so that it collects enough 100 ms samples under load
+    sampler = ClockSampler(local_rank)
+    if rank == 0 and not args.no_clocks:
+        sampler.start()
     for i in range(max(args.warmup, 3)):
         step(dev[i % 2])
     barrier()
 
     # ---- timed: inputs resident in HBM
-    sampler = ClockSampler(local_rank)
-    if rank == 0 and not args.no_clocks:
-        sampler.start()
     words.clear()
     launches0 = L.glass_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

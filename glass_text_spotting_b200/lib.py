@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "_lib", "libglass_b200.so")
+LIB_PATH = os.environ.get("GLASS_B200_LIB", os.path.join(HERE, "_lib", "libglass_b200.so"))  # env: A/B builds
 
 MAX_TAPS = 16
 MAX_LEVELS = 5
