@@ -146,6 +146,112 @@ __global__ void __launch_bounds__(256) roi_align_rotated_kernel(const RoiKernelP
   }
 }
 
+// Split-fp16 input, 8 channels per lane: a tap is one 16-byte load per plane per lane (C = 256 -> the whole
+// channel vector in one pass, 512 B per plane per warp request), 8 accumulators, 16-byte stores.
+__device__ __forceinline__ void load8(const __half* hi, const __half* lo, int64_t off, float (&v)[8]) {
+  const uint4 h = __ldg(reinterpret_cast<const uint4*>(hi + off));
+  const uint4 l = __ldg(reinterpret_cast<const uint4*>(lo + off));
+  const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = unpack16x2(hw[j], lw[j]);
+    v[2 * j] = f.x;
+    v[2 * j + 1] = f.y;
+  }
+}
+
+__global__ void __launch_bounds__(256, 3) roi_align_rotated_split8_kernel(const RoiKernelParams p) {
+  // one warp per output bin (one warp per row of bins was measured slower: too few warps in flight)
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_rois = p.n_rois_dev ? min(*p.n_rois_dev, p.n_rois) : p.n_rois;
+  const int bins = p.ph * p.pw;
+  const int64_t total = (int64_t)n_rois * bins;
+  const bool active = lane * 8 < p.channels;
+  for (int64_t wid = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); wid < total;
+       wid += (int64_t)gridDim.x * warps_per_block) {
+    const int roi_idx = (int)(wid / bins);
+    const int bin = (int)(wid - (int64_t)roi_idx * bins);
+    const int bph = bin / p.pw, bpw = bin - bph * p.pw;
+    const float* roi = p.rois + (int64_t)roi_idx * 6;
+    const int batch = (int)roi[0];
+    const float bx = roi[1], by = roi[2], bw = roi[3], bh = roi[4], ba = roi[5];
+    const int lvl = p.num_levels > 1 ? assign_level(bw, bh, p.min_level, p.num_levels) : 0;
+    const int H = p.feat_h[lvl], W = p.feat_w[lvl];
+    const float s = p.scale[lvl];
+    const int Hp = H + 2 * p.border, Wp = W + 2 * p.border;
+    const __half* fhi = reinterpret_cast<const __half*>(p.feat[lvl]);
+    const __half* flo = reinterpret_cast<const __half*>(p.feat_lo[lvl]);
+    const int64_t img_off = (int64_t)batch * Hp * Wp * p.ld + lane * 8;
+
+    const float cw = bx * s - 0.5f, chh = by * s - 0.5f;
+    const float rw = bw * s, rh = bh * s;
+    const float theta = (float)((double)ba * 3.14159265358979323846 / 180.0);
+    const float sn = (float)sin((double)theta), cs = (float)cos((double)theta);
+    const float bsh = rh / (float)p.ph, bsw = rw / (float)p.pw;
+    const int gh = p.sampling > 0 ? p.sampling : (int)ceilf(rh / (float)p.ph);
+    const int gw = p.sampling > 0 ? p.sampling : (int)ceilf(rw / (float)p.pw);
+    const float count = (float)max(gh * gw, 1);
+    const float sh0 = -rh / 2.0f, sw0 = -rw / 2.0f;
+
+    {
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      for (int iy = 0; iy < gh; ++iy) {
+        const float yy = sh0 + bph * bsh + ((float)iy + .5f) * bsh / (float)gh;
+        for (int ix = 0; ix < gw; ++ix) {
+          const float xx = sw0 + bpw * bsw + ((float)ix + .5f) * bsw / (float)gw;
+          float y = yy * cs - xx * sn + chh;
+          float x = yy * sn + xx * cs + cw;
+          if (y < -1.0f || y > (float)H || x < -1.0f || x > (float)W) continue;
+          y = fmaxf(y, 0.f);
+          x = fmaxf(x, 0.f);
+          int yl = (int)y, xl = (int)x, yh, xh;
+          if (yl >= H - 1) { yh = yl = H - 1; y = (float)yl; } else { yh = yl + 1; }
+          if (xl >= W - 1) { xh = xl = W - 1; x = (float)xl; } else { xh = xl + 1; }
+          const float ly = y - (float)yl, lx = x - (float)xl;
+          const float hy = 1.f - ly, hx = 1.f - lx;
+          const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+          if (active) {
+            float a[8], b[8], c[8], d[8];
+            load8(fhi, flo, img_off + ((int64_t)(yl + p.border) * Wp + xl + p.border) * p.ld, a);
+            load8(fhi, flo, img_off + ((int64_t)(yl + p.border) * Wp + xh + p.border) * p.ld, b);
+            load8(fhi, flo, img_off + ((int64_t)(yh + p.border) * Wp + xl + p.border) * p.ld, c);
+            load8(fhi, flo, img_off + ((int64_t)(yh + p.border) * Wp + xh + p.border) * p.ld, d);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += w1 * a[j] + w2 * b[j] + w3 * c[j] + w4 * d[j];
+          }
+        }
+      }
+      if (active) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = acc[j] / count;
+        if (p.out_f32) {
+          float4* o = reinterpret_cast<float4*>(p.out_f32 + ((int64_t)roi_idx * bins + bin) * p.channels + lane * 8);
+          o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+          o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        }
+        if (p.out_hi) {
+          const int64_t row = ((int64_t)roi_idx * p.out_hp + bph + p.out_border) * p.out_wp + bpw + p.out_border;
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            __half h0, l0, h1, l1;
+            split16(acc[2 * j], h0, l0);
+            split16(acc[2 * j + 1], h1, l1);
+            hw[j] = pack16x2(h0, h1);
+            lw[j] = pack16x2(l0, l1);
+          }
+          const int64_t off = row * p.ld_out + p.out_coff + lane * 8;
+          *reinterpret_cast<uint4*>(p.out_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          *reinterpret_cast<uint4*>(p.out_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ image pooler (3 channels, NCHW raw image)
 struct ImgRoiKernelParams {
   const float* img;
@@ -267,9 +373,13 @@ extern "C" int glass_roi_align_rotated(const GlassRoiAlignParams* p, void* strea
   k.ld_out = p->ld_out;
   const int64_t warps = (int64_t)p->n_rois * p->pooled_h * p->pooled_w;
   int64_t blocks = (warps + 7) / 8;
-  const int64_t cap = (int64_t)num_sms() * 8 * 4;  // 8 resident CTAs/SM x 4 waves, grid-stride beyond
+  const int64_t cap = (int64_t)num_sms() * 8 * 8;  // grid-stride beyond ~8 waves of resident CTAs
   if (blocks > cap) blocks = cap;
-  if (p->channels <= 128) {
+  const bool split8 = p->feat_is_split && p->channels % 8 == 0 && p->feat_ld % 8 == 0 &&
+                      (!p->out_hi || (p->ld_out % 8 == 0 && p->out_coff % 8 == 0));
+  if (split8) {
+    roi_align_rotated_split8_kernel<<<(int)blocks, 256, 0, stream>>>(k);
+  } else if (p->channels <= 128) {
     if (p->feat_is_split) roi_align_rotated_kernel<1, true><<<(int)blocks, 256, 0, stream>>>(k);
     else roi_align_rotated_kernel<1, false><<<(int)blocks, 256, 0, stream>>>(k);
   } else {
