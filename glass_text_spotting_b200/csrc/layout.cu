@@ -214,10 +214,47 @@ __global__ void maxpool_kernel(const uint4* __restrict__ shi, const uint4* __res
   }
 }
 
+// ------------------------------------------------------------------ bilinear resize, uint8 HWC -> fp32 CHW
+// torch.nn.functional.interpolate(mode="bilinear", align_corners=False, size=(ho, wo)) semantics:
+// src = scale * (dst + 0.5) - 0.5 clamped at 0, scale = in / out, neighbours clamped at the last pixel.
+__global__ void resize_bilinear_u8_kernel(const uint8_t* __restrict__ src, int h, int w, int flip,
+                                          float* __restrict__ dst, int ho, int wo) {
+  const float sy = (float)h / (float)ho, sx = (float)w / (float)wo;
+  const int64_t total = (int64_t)ho * wo;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % wo), y = (int)(i / wo);
+    const float fy = fmaxf(sy * ((float)y + 0.5f) - 0.5f, 0.f), fx = fmaxf(sx * ((float)x + 0.5f) - 0.5f, 0.f);
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+    const float ly = fy - (float)y0, lx = fx - (float)x0;
+    const float hy = 1.f - ly, hx = 1.f - lx;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int cs = flip ? 2 - c : c;
+      const float p00 = (float)__ldg(src + ((int64_t)y0 * w + x0) * 3 + cs);
+      const float p01 = (float)__ldg(src + ((int64_t)y0 * w + x1) * 3 + cs);
+      const float p10 = (float)__ldg(src + ((int64_t)y1 * w + x0) * 3 + cs);
+      const float p11 = (float)__ldg(src + ((int64_t)y1 * w + x1) * 3 + cs);
+      dst[(int64_t)c * total + i] = hy * (hx * p00 + lx * p01) + ly * (hx * p10 + lx * p11);
+    }
+  }
+}
+
 }  // namespace glass
 
 using namespace glass;
 #define STREAM reinterpret_cast<cudaStream_t>(stream)
+
+extern "C" int glass_resize_bilinear_u8(const uint8_t* src_hwc, int h, int w, int flip_channels, float* dst_chw, int ho,
+                                        int wo, void* stream) {
+  GLASS_CHECK(src_hwc && dst_chw, "null pointer");
+  GLASS_CHECK(h > 0 && w > 0 && ho > 0 && wo > 0, "bad shape");
+  resize_bilinear_u8_kernel<<<grid_for((int64_t)ho * wo, 256), 256, 0, STREAM>>>(src_hwc, h, w, flip_channels, dst_chw,
+                                                                                  ho, wo);
+  count_launch();
+  GLASS_CUDA(cudaGetLastError());
+  return 0;
+}
 
 extern "C" int glass_pack_nchw(const float* src, int n, int c, int h, int w, void* dst_hi, void* dst_lo, int cp,
                                int border, void* stream) {

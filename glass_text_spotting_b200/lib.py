@@ -15,7 +15,7 @@ SYMBOLS = [
     "glass_roi_align_rotated", "glass_image_roi_align_rotated", "glass_rpn_topk_decode", "glass_rpn_topk_workspace_bytes",
     "glass_nms_workspace_bytes",
     "glass_nms_rotated", "glass_box_decode", "glass_gc_attention", "glass_hmean_rows", "glass_lstm_bidir",
-    "glass_aster_decode", "glass_aster_finalize",
+    "glass_aster_decode", "glass_aster_finalize", "glass_resize_bilinear_u8",
 ]
 
 
@@ -137,6 +137,7 @@ def load() -> C.CDLL:
     lib.glass_lstm_bidir.argtypes = [p, p, i, i, i, p, p, p, p]
     lib.glass_aster_decode.argtypes = [C.POINTER(AsterParams), p]
     lib.glass_aster_finalize.argtypes = [p, p, p, i, i, i, p]
+    lib.glass_resize_bilinear_u8.argtypes = [p, i, i, i, p, i, i, p]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if name.startswith("glass_") and name not in ("glass_last_error", "glass_abi_version", "glass_launch_count",

@@ -437,3 +437,14 @@ def aster_finalize(probs: torch.Tensor, first_eos: torch.Tensor, word_start: tor
     assert word_start.dtype == torch.int32 and word_start.numel() == n_img + 1
     _lib.check(_lib.load().glass_aster_finalize(_ptr(probs), _ptr(first_eos), _ptr(word_start), n_img, steps,
                                                 num_classes, _stream()))
+
+
+def resize_bilinear_u8(img_hwc: torch.Tensor, out_hw: Tuple[int, int], flip_channels: bool = False) -> torch.Tensor:
+    """uint8 HWC CUDA image -> fp32 CHW, bilinear (align_corners=False) resize to out_hw
+    (GlassRunner._image_to_tensor, glass/inference/glass_runner.py:123-148)."""
+    assert img_hwc.dtype == torch.uint8 and img_hwc.dim() == 3 and img_hwc.shape[2] == 3 and img_hwc.is_contiguous()
+    h, w, _ = img_hwc.shape
+    out = torch.empty((3, out_hw[0], out_hw[1]), dtype=torch.float32, device=img_hwc.device)
+    _lib.check(_lib.load().glass_resize_bilinear_u8(_ptr(img_hwc), h, w, int(flip_channels), _ptr(out), out_hw[0],
+                                                    out_hw[1], _stream()))
+    return out

@@ -124,6 +124,12 @@ int glass_maxpool(const void* src_hi, const void* src_lo, int n, int h, int w, i
                   int sh, int sw, int ph, int pw, int ho, int wo, void* dst_hi, void* dst_lo, int dst_border,
                   void* stream);
 
+/* Pre-processing of GlassRunner._image_to_tensor (glass/inference/glass_runner.py:123-148): uint8 HWC image ->
+ * fp32 CHW tensor, bilinear resize with align_corners=False semantics of torch.nn.functional.interpolate(size=...),
+ * optional channel reversal (RGB input_format, glass_runner.py:83-85).  ho == h && wo == w is a plain convert. */
+int glass_resize_bilinear_u8(const uint8_t* src_hwc, int h, int w, int flip_channels, float* dst_chw, int ho, int wo,
+                             void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * glass_roi_align_rotated -- multi-level rotated RoIAlign (detectron2 ROIPooler + ROIAlignRotated).
  * replaces: torch.ops.detectron2.roi_align_rotated_forward as called through ROIPooler at
