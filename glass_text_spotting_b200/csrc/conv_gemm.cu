@@ -76,6 +76,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   uint64_t* tmem_empty_bar = bars + 2 * MAX_STAGES + MAX_ACC_BUFS;  // [MAX_ACC_BUFS]
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 2 * MAX_ACC_BUFS);
 
+  // Programmatic dependent launch: let the next kernel of the stream start its prologue as soon as SMs free up
+  // (it blocks at its own griddepcontrol.wait until this grid has completed and flushed).
+  asm volatile("griddepcontrol.launch_dependents;");
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int kblocks = p.kblocks_per_tap * p.ntaps;
@@ -117,6 +120,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail;
+  // global memory written by it may only be touched from here on
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   // Register re-balancing between the warpgroups (the launch gives every thread 168): the control
   // warpgroup needs few registers, the two epilogue warpgroups hold the whole 128 x BN fp32 tile.
@@ -526,39 +532,39 @@ extern "C" int glass_conv_gemm(const GlassConvGemmParams* p, void* stream_v) {
   // always ask for > half of the SM's shared memory: exactly one CTA per SM owns all 512 TMEM columns
   const int smem_bytes = k.num_stages * k.stage_bytes + EPI_STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
   const int smem_req = smem_bytes < 120 * 1024 ? 120 * 1024 : smem_bytes;
-  if (!pair) {
-    const int total_tiles = k.tiles_m * k.tiles_n;
-    const int grid = total_tiles < sms ? total_tiles : sms;
-    if (split) {
-      GLASS_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_req));
-      conv_gemm_kernel<true, false><<<grid, NUM_THREADS, smem_req, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, k);
-    } else {
-      GLASS_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_req));
-      conv_gemm_kernel<false, false><<<grid, NUM_THREADS, smem_req, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, k);
-    }
-  } else {
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[2];
+  int nattr = 0;
+  attr[nattr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[nattr].val.programmaticStreamSerializationAllowed = 1;
+  ++nattr;
+  if (pair) {
+    attr[nattr].id = cudaLaunchAttributeClusterDimension;
+    attr[nattr].val.clusterDim.x = 2;
+    attr[nattr].val.clusterDim.y = 1;
+    attr[nattr].val.clusterDim.z = 1;
+    ++nattr;
     const int units = ((k.tiles_m + 1) / 2) * k.tiles_n;
     const int pairs = units < sms / 2 ? units : sms / 2;
-    cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * pairs);
-    cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = smem_req;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    if (split) {
-      GLASS_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_req));
-      GLASS_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true, true>, ma_hi, ma_lo, mb_hi, mb_lo, k));
-    } else {
-      GLASS_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_req));
-      GLASS_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<false, true>, ma_hi, ma_lo, mb_hi, mb_lo, k));
-    }
+  } else {
+    const int total_tiles = k.tiles_m * k.tiles_n;
+    cfg.gridDim = dim3(total_tiles < sms ? total_tiles : sms);
   }
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem_req;
+  cfg.stream = stream;
+  cfg.attrs = attr;
+  cfg.numAttrs = nattr;
+  auto launch = [&](auto kern) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_req);
+    if (e != cudaSuccess) return e;
+    return cudaLaunchKernelEx(&cfg, kern, ma_hi, ma_lo, mb_hi, mb_lo, k);
+  };
+  if (split && pair) GLASS_CUDA(launch(conv_gemm_kernel<true, true>));
+  else if (split) GLASS_CUDA(launch(conv_gemm_kernel<true, false>));
+  else if (pair) GLASS_CUDA(launch(conv_gemm_kernel<false, true>));
+  else GLASS_CUDA(launch(conv_gemm_kernel<false, false>));
   count_launch();
   GLASS_CUDA(cudaGetLastError());
   return 0;
