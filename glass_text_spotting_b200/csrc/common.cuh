@@ -62,6 +62,19 @@ __device__ __forceinline__ float2 unpack16x2(uint32_t hi, uint32_t lo) {
   return make_float2((h.x + l.x) * kActScaleInv, (h.y + l.y) * kActScaleInv);
 }
 
+// one lane of a converged warp (the compiler keeps warp-uniform operands in uniform registers around it)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -28,6 +28,9 @@ static constexpr int BK = 64;
 static constexpr int TMEM_COLS = 512;     // all of the SM's tensor memory
 static constexpr int MAX_ACC_BUFS = 8;    // accumulator ring: 512 / max(64, tile width rounded to a power of two)
 static constexpr int A_TILE_BYTES = BM * BK * 2;
+static constexpr int A_BLOCK_ROWS = BM + 8;                 // tap-row mode: one block serves the 3 s-taps (row offsets 0,1,2)
+static constexpr int A_BLOCK_BYTES = A_BLOCK_ROWS * BK * 2;  // 17408 = 17 x 1024
+static constexpr int MAX_A_STAGES = 4;
 static constexpr int EPI_WARPS = 16;
 static constexpr int NUM_THREADS = 128 + 32 * EPI_WARPS;  // 4 control warps + 16 epilogue warps
 static constexpr int MAX_STAGES = 8;
@@ -40,6 +43,10 @@ struct GemmKernelParams {
   int32_t kblocks_per_tap, ntaps;
   int32_t tap_shift[GLASS_MAX_TAPS];
   int32_t num_stages, stage_bytes, b_tile_bytes;
+  // tap-row mode (3x3 convs): per (tap row r, channel block) ONE activation block of 136 rows is staged and its three
+  // s-taps are addressed by advancing the UMMA descriptor start by s rows (the 128B swizzle is a function of the
+  // absolute shared-memory address, verified by tools/probes/umma_rowoffset_probe.cu); weights stream per tap.
+  int32_t group3, a_stages, a_stage_bytes, b_stages, b_stage_bytes, ring_bytes;
   int32_t kb_per_chunk;  // k-blocks accumulated inside the tensor core before a drain to registers
   int32_t acc_cols, acc_bufs;  // TMEM accumulator ring: acc_bufs buffers of acc_cols columns (acc_cols * acc_bufs = 512)
   int32_t m_h, m_w, m_border;
@@ -68,13 +75,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages x (A_hi, A_lo?, B_hi, B_lo?)] then barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* stage_base = reinterpret_cast<float*>(smem + (size_t)p.num_stages * p.stage_bytes);  // 8 warps x 4 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.num_stages * p.stage_bytes + EPI_STAGE_BYTES);
+  float* stage_base = reinterpret_cast<float*>(smem + (size_t)p.ring_bytes);  // epilogue staging, 2 KB per warp
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.ring_bytes + EPI_STAGE_BYTES);
   uint64_t* full_bar = bars;                      // [MAX_STAGES]
   uint64_t* empty_bar = bars + MAX_STAGES;        // [MAX_STAGES]
   uint64_t* tmem_full_bar = bars + 2 * MAX_STAGES;   // [MAX_ACC_BUFS]
   uint64_t* tmem_empty_bar = bars + 2 * MAX_STAGES + MAX_ACC_BUFS;  // [MAX_ACC_BUFS]
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 2 * MAX_ACC_BUFS);
+  uint64_t* a_full_bar = bars + 2 * MAX_STAGES + 2 * MAX_ACC_BUFS;                  // [MAX_A_STAGES]
+  uint64_t* a_empty_bar = bars + 2 * MAX_STAGES + 2 * MAX_ACC_BUFS + MAX_A_STAGES;  // [MAX_A_STAGES]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 2 * MAX_ACC_BUFS + 2 * MAX_A_STAGES);
 
   // Programmatic dependent launch: let the next kernel of the stream start its prologue as soon as SMs free up
   // (it blocks at its own griddepcontrol.wait until this grid has completed and flushed).
@@ -101,9 +110,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     }
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < p.num_stages; ++i) {
+    for (int i = 0; i < MAX_STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < MAX_A_STAGES; ++i) {
+      mbar_init(&a_full_bar[i], 1);
+      mbar_init(&a_empty_bar[i], 1);
     }
     for (int i = 0; i < MAX_ACC_BUFS; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
@@ -132,7 +145,53 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
 
   if (warp == 0) {
     // ===================================================== TMA producer
-    if (lane == 0) {
+    if (lane == 0 && p.group3) {
+      int as = 0, bs = 0;
+      uint32_t aphase = 0, bphase = 0;
+      uint8_t* b_ring = smem + (size_t)p.a_stages * p.a_stage_bytes;
+      for (int unit = worker; unit < num_units; unit += num_workers) {
+        const int um = unit / p.tiles_n;
+        const int tn = unit - um * p.tiles_n;
+        const int m0 = (PAIR ? um * 2 + (int)rank : um) * BM;
+        const int n0 = tn * p.bn + (int)rank * b_rows;
+        for (int r = 0; r < 3; ++r) {
+          const int arow = m0 + p.tap_shift[3 * r];  // first row of the block = rows of tap (r, s = 0)
+          for (int kb = 0; kb < p.kblocks_per_tap; ++kb) {
+            mbar_wait(&a_empty_bar[as], aphase ^ 1);
+            uint8_t* sa = smem + (size_t)as * p.a_stage_bytes;
+            if (leader) mbar_arrive_expect_tx(&a_full_bar[as], (uint32_t)p.a_stage_bytes * (PAIR ? 2u : 1u));
+            if (PAIR) {
+              tma_load_2d_pair(sa, &map_a_hi, &a_full_bar[as], kb * BK, arow);
+              if (SPLIT) tma_load_2d_pair(sa + A_BLOCK_BYTES, &map_a_lo, &a_full_bar[as], kb * BK, arow);
+            } else {
+              tma_load_2d(sa, &map_a_hi, &a_full_bar[as], kb * BK, arow);
+              if (SPLIT) tma_load_2d(sa + A_BLOCK_BYTES, &map_a_lo, &a_full_bar[as], kb * BK, arow);
+            }
+            if (++as == p.a_stages) {
+              as = 0;
+              aphase ^= 1;
+            }
+            for (int sx = 0; sx < 3; ++sx) {
+              mbar_wait(&empty_bar[bs], bphase ^ 1);
+              uint8_t* sb = b_ring + (size_t)bs * p.b_stage_bytes;
+              if (leader) mbar_arrive_expect_tx(&full_bar[bs], (uint32_t)p.b_stage_bytes * (PAIR ? 2u : 1u));
+              const int kw = ((3 * r + sx) * p.kblocks_per_tap + kb) * BK;
+              if (PAIR) {
+                tma_load_2d_pair(sb, &map_b_hi, &full_bar[bs], kw, n0);
+                if (SPLIT) tma_load_2d_pair(sb + p.b_tile_bytes, &map_b_lo, &full_bar[bs], kw, n0);
+              } else {
+                tma_load_2d(sb, &map_b_hi, &full_bar[bs], kw, n0);
+                if (SPLIT) tma_load_2d(sb + p.b_tile_bytes, &map_b_lo, &full_bar[bs], kw, n0);
+              }
+              if (++bs == p.b_stages) {
+                bs = 0;
+                bphase ^= 1;
+              }
+            }
+          }
+        }
+      }
+    } else if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int unit = worker; unit < num_units; unit += num_workers) {
@@ -171,7 +230,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
-    if (lane == 0 && leader) {
+    // The whole warp walks the (warp-uniform) loop so that descriptors and addresses stay in uniform registers;
+    // only the elected lane issues tcgen05.mma / tcgen05.commit.  With one lane doing everything the issue path
+    // costs ~80 clk per MMA (R2UR traffic), which starves tiles narrower than 256 columns (32-64 clk per MMA).
+    if (leader) {
       const uint32_t idesc = umma_idesc_f16_f32(PAIR ? 2 * BM : BM, p.bn);
       int stage = 0;
       uint32_t phase = 0;
@@ -184,43 +246,72 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         if (PAIR) umma_commit_pair(bar);
         else umma_commit(bar);
       };
+      int as = 0;
+      uint32_t aphase = 0;
+      const uint32_t b_ring = smem_u32(smem) + (uint32_t)(p.group3 ? p.a_stages * p.a_stage_bytes : 0);
       for (int unit = worker; unit < num_units; unit += num_workers) {
         uint32_t d_tmem = 0;
+        uint32_t a_block = 0;  // tap-row mode: shared-memory address of the current activation block
         for (int kb = 0; kb < kblocks; ++kb) {
           const int kin = kb % p.kb_per_chunk;  // position inside the accumulation chunk
           if (kin == 0) {
-            // a new chunk starts from zero in the other TMEM buffer once the epilogue has drained it
+            // a new chunk starts from zero in the next TMEM buffer once the epilogue has drained it
             const uint32_t buf = chunk % (uint32_t)p.acc_bufs;
             mbar_wait(&tmem_empty_bar[buf], ((chunk / (uint32_t)p.acc_bufs) & 1u) ^ 1u);
             tcgen05_fence_after();
             d_tmem = tmem_base + buf * (uint32_t)p.acc_cols;
           }
-          mbar_wait(&full_bar[stage], phase);
-          tcgen05_fence_after();
-          const uint32_t s = smem_u32(smem + (size_t)stage * p.stage_bytes);
-          const uint64_t da_hi = umma_smem_desc_sw128(s);
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t koff = (uint64_t)(k * 2);  // 32 bytes >> 4
-            const uint32_t acc_flag = (kin > 0 || k > 0) ? 1u : 0u;
-            if (SPLIT) {
-              const uint64_t da_lo = umma_smem_desc_sw128(s + A_TILE_BYTES);
-              const uint64_t db_hi = umma_smem_desc_sw128(s + 2 * A_TILE_BYTES);
-              const uint64_t db_lo = umma_smem_desc_sw128(s + 2 * A_TILE_BYTES + p.b_tile_bytes);
-              mma(d_tmem, da_lo + koff, db_hi + koff, acc_flag);
-              mma(d_tmem, da_hi + koff, db_lo + koff, 1u);
-              mma(d_tmem, da_hi + koff, db_hi + koff, 1u);
-            } else {
-              const uint64_t db_hi = umma_smem_desc_sw128(s + A_TILE_BYTES);
-              mma(d_tmem, da_hi + koff, db_hi + koff, acc_flag);
+          // operand addresses of this k-block
+          uint32_t sa_hi, sa_lo, sb_hi, sb_lo;
+          int sx = 0;
+          if (p.group3) {
+            sx = kb % 3;  // k-block order: (tap row r, channel block) outer, s-tap inner
+            if (sx == 0) {
+              mbar_wait(&a_full_bar[as], aphase);
+              a_block = smem_u32(smem) + (uint32_t)(as * p.a_stage_bytes);
             }
+            mbar_wait(&full_bar[stage], phase);
+            sa_hi = a_block + (uint32_t)(sx * BK * 2);  // descriptor start advanced by sx rows of 128 bytes
+            sa_lo = sa_hi + A_BLOCK_BYTES;
+            sb_hi = b_ring + (uint32_t)(stage * p.b_stage_bytes);
+            sb_lo = sb_hi + (uint32_t)p.b_tile_bytes;
+          } else {
+            mbar_wait(&full_bar[stage], phase);
+            const uint32_t s0 = smem_u32(smem + (size_t)stage * p.stage_bytes);
+            sa_hi = s0;
+            sa_lo = s0 + A_TILE_BYTES;
+            sb_hi = s0 + (SPLIT ? 2 : 1) * A_TILE_BYTES;
+            sb_lo = sb_hi + (uint32_t)p.b_tile_bytes;
           }
-          commit(&empty_bar[stage]);  // frees the smem slot (in both CTAs) when these MMAs retire
-          if (kin == p.kb_per_chunk - 1 || kb == kblocks - 1) {
-            commit(&tmem_full_bar[chunk % (uint32_t)p.acc_bufs]);  // chunk complete -> the epilogue(s) drain it
-            ++chunk;
+          tcgen05_fence_after();
+          const uint64_t da_hi = umma_smem_desc_sw128(sa_hi), da_lo = umma_smem_desc_sw128(sa_lo);
+          const uint64_t db_hi = umma_smem_desc_sw128(sb_hi), db_lo = umma_smem_desc_sw128(sb_lo);
+          const bool a_done = p.group3 && sx == 2;
+          const bool chunk_done = kin == p.kb_per_chunk - 1 || kb == kblocks - 1;
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t koff = (uint64_t)(k * 2);  // 32 bytes >> 4
+              const uint32_t acc_flag = (kin > 0 || k > 0) ? 1u : 0u;
+              if (SPLIT) {
+                mma(d_tmem, da_lo + koff, db_hi + koff, acc_flag);
+                mma(d_tmem, da_hi + koff, db_lo + koff, 1u);
+                mma(d_tmem, da_hi + koff, db_hi + koff, 1u);
+              } else {
+                mma(d_tmem, da_hi + koff, db_hi + koff, acc_flag);
+              }
+            }
+            commit(&empty_bar[stage]);  // frees the (weight) slot in both CTAs when these MMAs retire
+            if (a_done) commit(&a_empty_bar[as]);  // all three s-taps have consumed the activation block
+            if (chunk_done) commit(&tmem_full_bar[chunk % (uint32_t)p.acc_bufs]);  // -> the epilogue(s) drain it
           }
-          if (++stage == p.num_stages) {
+          __syncwarp();
+          if (a_done && ++as == p.a_stages) {
+            as = 0;
+            aphase ^= 1;
+          }
+          if (chunk_done) ++chunk;
+          if (++stage == (p.group3 ? p.b_stages : p.num_stages)) {
             stage = 0;
             phase ^= 1;
           }
@@ -487,10 +578,28 @@ extern "C" int glass_conv_gemm(const GlassConvGemmParams* p, void* stream_v) {
     GLASS_CHECK(p->rows_a > BK / a_ld, "too few rows for compact mode");
     a_rows = (uint64_t)p->rows_a - (uint64_t)(BK / a_ld) + 1;
   }
-  if (make_map_2d(&ma_hi, p->a_hi, p->k_per_tap, a_rows, BK, BM, a_ld)) return -1;
+  // tap-row mode for 3x3 'same' convs (taps ordered (r, s), s-taps = consecutive rows): one 136-row block per tap row
+  const int split_mul = split ? 2 : 1;
+  const int smem_budget = 227 * 1024 - EPI_STAGE_BYTES - 1024 /*align slack*/ - 512 /*barriers*/;
+  const int b_stage_bytes = b_rows * BK * 2 * split_mul;
+  bool group3 = p->ntaps == 9 && a_ld == p->k_per_tap && p->tap_mode != 1;
+  for (int r = 0; r < 3 && group3; ++r)
+    group3 = p->tap_shift[3 * r + 1] == p->tap_shift[3 * r] + 1 && p->tap_shift[3 * r + 2] == p->tap_shift[3 * r] + 2;
+  int a_stages = 2, b_stages = 0;
+  if (group3) {
+    b_stages = (smem_budget - a_stages * A_BLOCK_BYTES * split_mul) / b_stage_bytes;
+    if (b_stages > MAX_STAGES) {
+      b_stages = MAX_STAGES;
+      a_stages = (smem_budget - b_stages * b_stage_bytes) / (A_BLOCK_BYTES * split_mul);
+      if (a_stages > MAX_A_STAGES) a_stages = MAX_A_STAGES;
+    }
+    if (b_stages < 3) group3 = false;  // not enough room to keep the weight stream pipelined
+  }
+  const int a_box_rows = group3 ? A_BLOCK_ROWS : BM;
+  if (make_map_2d(&ma_hi, p->a_hi, p->k_per_tap, a_rows, BK, a_box_rows, a_ld)) return -1;
   if (make_map_2d(&mb_hi, p->b_hi, ktot, p->n, BK, b_rows)) return -1;
   if (split) {
-    if (make_map_2d(&ma_lo, p->a_lo, p->k_per_tap, a_rows, BK, BM, a_ld)) return -1;
+    if (make_map_2d(&ma_lo, p->a_lo, p->k_per_tap, a_rows, BK, a_box_rows, a_ld)) return -1;
     if (make_map_2d(&mb_lo, p->b_lo, ktot, p->n, BK, b_rows)) return -1;
   } else {
     ma_lo = ma_hi;
@@ -506,11 +615,16 @@ extern "C" int glass_conv_gemm(const GlassConvGemmParams* p, void* stream_v) {
   k.ntaps = p->ntaps;
   for (int i = 0; i < GLASS_MAX_TAPS; ++i) k.tap_shift[i] = p->tap_shift[i];
   k.b_tile_bytes = b_rows * BK * 2;
-  k.stage_bytes = (A_TILE_BYTES + k.b_tile_bytes) * (split ? 2 : 1);
-  const int smem_budget = 227 * 1024 - EPI_STAGE_BYTES - 1024 /*align slack*/ - 512 /*barriers*/;
+  k.stage_bytes = (A_TILE_BYTES + k.b_tile_bytes) * split_mul;
   k.num_stages = smem_budget / k.stage_bytes;
   if (k.num_stages > MAX_STAGES) k.num_stages = MAX_STAGES;
   GLASS_CHECK(k.num_stages >= 2, "stage too large");
+  k.group3 = group3 ? 1 : 0;
+  k.a_stages = a_stages;
+  k.a_stage_bytes = A_BLOCK_BYTES * split_mul;
+  k.b_stages = b_stages;
+  k.b_stage_bytes = b_stage_bytes;
+  k.ring_bytes = group3 ? a_stages * k.a_stage_bytes + b_stages * b_stage_bytes : k.num_stages * k.stage_bytes;
   // default: drain every 2 k-blocks (split) / 4 (single pass): a drain reads the whole 128 x BN fp32 tile from TMEM
   // (64 B/clk/SM), which hides behind two k-blocks of MMA work but not behind one
   k.kb_per_chunk = p->kb_per_chunk > 0 ? p->kb_per_chunk : (split ? 2 : 4);
@@ -530,7 +644,7 @@ extern "C" int glass_conv_gemm(const GlassConvGemmParams* p, void* stream_v) {
   k.ld_out = p->ld_out; k.ld_f32 = p->ld_f32; k.n_store = n_store;
 
   // always ask for > half of the SM's shared memory: exactly one CTA per SM owns all 512 TMEM columns
-  const int smem_bytes = k.num_stages * k.stage_bytes + EPI_STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
+  const int smem_bytes = k.ring_bytes + EPI_STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
   const int smem_req = smem_bytes < 120 * 1024 ? 120 * 1024 : smem_bytes;
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[2];

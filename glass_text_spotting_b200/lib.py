@@ -30,7 +30,7 @@ class ConvGemmParams(C.Structure):
         ("res_hp", C.c_int32), ("res_wp", C.c_int32), ("res_border", C.c_int32), ("res_shift", C.c_int32),
         ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("out_f32", C.c_void_p),
         ("out_hp", C.c_int32), ("out_wp", C.c_int32), ("out_border", C.c_int32),
-        ("ld_out", C.c_int32), ("ld_f32", C.c_int32), ("n_store", C.c_int32), ("kb_per_chunk", C.c_int32), ("pair_mode", C.c_int32),
+        ("ld_out", C.c_int32), ("ld_f32", C.c_int32), ("n_store", C.c_int32), ("kb_per_chunk", C.c_int32), ("pair_mode", C.c_int32), ("tap_mode", C.c_int32),
     ]
 
 

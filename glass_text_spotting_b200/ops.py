@@ -19,6 +19,8 @@ ACT_SCALE = 16.0  # == kActScale in csrc/common.cuh: split planes hold ACT_SCALE
 KB_PER_CHUNK = int(__import__("os").environ.get("GLASS_KB_PER_CHUNK", "0"))
 # 0 = auto, 1 = never pair CTAs, 2 = always use tcgen05 cta_group::2 CTA pairs (when the tile width allows)
 PAIR_MODE = int(__import__("os").environ.get("GLASS_PAIR_MODE", "0"))
+# 0 = auto (3x3 convs stage one activation block per tap row), 1 = every tap loads its own tile
+TAP_MODE = int(__import__("os").environ.get("GLASS_TAP_MODE", "0"))
 
 # bench.py's per-kernel timing: when a list, every conv_gemm launch appends (start event, end event, algorithmic FLOPs)
 PROFILE = None
@@ -151,6 +153,7 @@ def conv_gemm(a_hi: torch.Tensor, a_lo: Optional[torch.Tensor], rows_a: int, k_p
     p.ld_out, p.ld_f32, p.n_store = ld_out, ld_f32, n_store
     p.kb_per_chunk = KB_PER_CHUNK
     p.pair_mode = PAIR_MODE if (PAIR_MODE != 2 or w.n_p % 32 == 0) else 0
+    p.tap_mode = TAP_MODE
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(torch.cuda.current_stream())

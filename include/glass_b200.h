@@ -91,6 +91,8 @@ typedef struct {
                            mode: relL2 4.6e-7 vs fp64, 1.5x an fp32 CPU GEMM; 1 = 2.6e-7; larger = faster, error grows
                            with the chain) */
   int32_t pair_mode;    /* 0 = auto, 1 = one CTA per tile, 2 = CTA pairs (tcgen05 cta_group::2, shared weight tile) */
+  int32_t tap_mode;     /* 0 = auto (3x3 taps ordered (r,s) with consecutive s-rows share one staged activation block),
+                           1 = every tap loads its own 128-row tile */
 } GlassConvGemmParams;
 int glass_conv_gemm(const GlassConvGemmParams* p, void* stream);
 
