@@ -62,6 +62,37 @@ __device__ __forceinline__ float2 unpack16x2(uint32_t hi, uint32_t lo) {
   return make_float2((h.x + l.x) * kActScaleInv, (h.y + l.y) * kActScaleInv);
 }
 
+// hi + lo of two packed fp16 words as fp32 (storage scale NOT removed): HADD2.F32 + FHADD per element
+// (add.rn.f32.f16 is sm_100's mixed-precision add: fp16 operand + fp32 operand -> fp32)
+__device__ __forceinline__ float2 unpack16x2_sum(uint32_t hi, uint32_t lo) {
+  float2 r;
+  asm("{\n"
+      ".reg .b16 h0, h1, l0, l1;\n"
+      ".reg .f32 f0, f1;\n"
+      "mov.b32 {h0, h1}, %2;\n"
+      "mov.b32 {l0, l1}, %3;\n"
+      "cvt.f32.f16 f0, h0;\n"
+      "cvt.f32.f16 f1, h1;\n"
+      "add.rn.f32.f16 %0, l0, f0;\n"
+      "add.rn.f32.f16 %1, l1, f1;\n"
+      "}"
+      : "=f"(r.x), "=f"(r.y)
+      : "r"(hi), "r"(lo));
+  return r;
+}
+
+// two fp32 values -> packed (hi, hi) and (lo, lo) words: same values as split16 on each, with the two
+// roundings to fp16 done by one packed conversion each
+__device__ __forceinline__ void split16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const float a = fminf(fmaxf(x0 * kActScale, -60000.f), 60000.f);
+  const float b = fminf(fmaxf(x1 * kActScale, -60000.f), 60000.f);
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 // one lane of a converged warp (the compiler keeps warp-uniform operands in uniform registers around it)
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;

@@ -6,6 +6,8 @@
 // bilinear taps of a sample are four contiguous C-vectors; one warp owns one output bin and its
 // lanes sweep the channel vector with 16-byte loads (C = 256 -> two float4 per lane per tap, a
 // fully coalesced 1 KB request).  The geometry (cos/sin, bin size, sampling grid) is warp-uniform.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "glass_b200.h"
 #include "host_util.h"
@@ -26,6 +28,7 @@ struct RoiKernelParams {
   __half* out_hi;
   __half* out_lo;
   int out_hp, out_wp, out_border, out_coff, ld_out;
+  int bins_per_warp;
 };
 
 __device__ __forceinline__ int assign_level(float w, float h, int min_level, int num_levels) {
@@ -148,105 +151,186 @@ __global__ void __launch_bounds__(256) roi_align_rotated_kernel(const RoiKernelP
 
 // Split-fp16 input, 8 channels per lane: a tap is one 16-byte load per plane per lane (C = 256 -> the whole
 // channel vector in one pass, 512 B per plane per warp request), 8 accumulators, 16-byte stores.
-__device__ __forceinline__ void load8(const __half* hi, const __half* lo, int64_t off, float (&v)[8]) {
-  const uint4 h = __ldg(reinterpret_cast<const uint4*>(hi + off));
-  const uint4 l = __ldg(reinterpret_cast<const uint4*>(lo + off));
+//
+// The first version of this kernel was ISSUE-bound, not memory-bound (ncu: 73 % issue slots busy, 13 % DRAM;
+// ~500 warp instructions per sample because the file is built with --fmad=false for the coordinate math).
+// Per element and tap it now costs 3 instructions: HADD2.F32 (hi -> fp32), FHADD (mixed-precision add of the lo
+// half, PTX add.rn.f32.f16) and one explicit FFMA with the 1/16 storage scale folded into the bilinear weight
+// (a power of two: exact).  The sampling coordinates keep the unfused fp32 arithmetic of the CPU path.
+struct TapSet {
+  int o1, o2, o3, o4;   // element offsets of the four taps inside the image plane (32-bit)
+  float w1, w2, w3, w4;  // bilinear weights * kActScaleInv; all zero for a sample outside the map
+};
+
+__device__ __forceinline__ TapSet make_taps(float y, float x, int H, int W, int Wp, int border, int ld) {
+  TapSet t;
+  const bool inside = !(y < -1.0f || y > (float)H || x < -1.0f || x > (float)W);
+  y = fmaxf(y, 0.f);
+  x = fmaxf(x, 0.f);
+  int yl = (int)y, xl = (int)x, yh, xh;
+  if (yl >= H - 1) { yh = yl = H - 1; y = (float)yl; } else { yh = yl + 1; }
+  if (xl >= W - 1) { xh = xl = W - 1; x = (float)xl; } else { xh = xl + 1; }
+  if (!inside) { yl = yh = xl = xh = 0; }  // keep the (unused) addresses in range
+  const float ly = y - (float)yl, lx = x - (float)xl;
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  const float sc = inside ? kActScaleInv : 0.f;
+  t.w1 = hy * hx * sc; t.w2 = hy * lx * sc; t.w3 = ly * hx * sc; t.w4 = ly * lx * sc;
+  const int r0 = (yl + border) * Wp + border, r1 = (yh + border) * Wp + border;
+  t.o1 = (r0 + xl) * ld; t.o2 = (r0 + xh) * ld; t.o3 = (r1 + xl) * ld; t.o4 = (r1 + xh) * ld;
+  return t;
+}
+
+// acc += w * (hi + lo) for 8 packed channels, 2.5 instructions per element:
+//   hi plane: HADD2.F32 (fp16 -> fp32) and one packed FFMA2 (fma.rn.f32x2) per channel pair;
+//   lo plane: one FHFMA (fma.rn.f32.f16: fp16 x fp16 + fp32, the product is exact) with the weight rounded to
+//   fp16 -- |lo| <= 2^-11 |hi|, so the weight's 2^-12 rounding error enters at 2^-23 relative, below fp32's own.
+__device__ __forceinline__ void fma8(const uint4& h, const uint4& l, float w, float (&acc)[8]) {
   const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+  const unsigned short wh = __half_as_ushort(__float2half_rn(w));
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const float2 f = unpack16x2(hw[j], lw[j]);
-    v[2 * j] = f.x;
-    v[2 * j + 1] = f.y;
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hw[j]));
+    asm("{\n"
+        ".reg .b64 ra, rb, rc;\n"
+        ".reg .b16 l0, l1;\n"
+        ".reg .f32 t0, t1;\n"
+        "mov.b64 ra, {%2, %2};\n"
+        "mov.b64 rb, {%3, %4};\n"
+        "mov.b64 rc, {%0, %1};\n"
+        "fma.rn.f32x2 rc, ra, rb, rc;\n"
+        "mov.b64 {t0, t1}, rc;\n"
+        "mov.b32 {l0, l1}, %5;\n"
+        "fma.rn.f32.f16 %0, l0, %6, t0;\n"
+        "fma.rn.f32.f16 %1, l1, %6, t1;\n"
+        "}"
+        : "+f"(acc[2 * j]), "+f"(acc[2 * j + 1])
+        : "f"(w), "f"(f.x), "f"(f.y), "r"(lw[j]), "h"(wh));
   }
 }
 
-__global__ void __launch_bounds__(256, 3) roi_align_rotated_split8_kernel(const RoiKernelParams p) {
-  // one warp per output bin (one warp per row of bins was measured slower: too few warps in flight)
-  const int warps_per_block = blockDim.x >> 5;
+#define GLASS_LD16(ptr) __ldg(reinterpret_cast<const uint4*>(ptr))
+
+static constexpr int kBinsPerWarp = 4;  // default consecutive bins per warp task: the per-RoI set-up is amortised over them
+
+template <int S, int OCC>  // S = 2: the sampling grid is 2 x 2 (both samples of a row are in flight together); 0: generic
+__global__ void __launch_bounds__(256, OCC) roi_align_rotated_split8_kernel(const RoiKernelParams p) {
+  // One warp per task of kBinsPerWarp consecutive output bins (a warp per whole row of bins was measured slower:
+  // too few warps in flight); the grid is NOT persistent so that the block scheduler balances the tail.
   const int lane = threadIdx.x & 31;
   const int n_rois = p.n_rois_dev ? min(*p.n_rois_dev, p.n_rois) : p.n_rois;
   const int bins = p.ph * p.pw;
   const int64_t total = (int64_t)n_rois * bins;
   const bool active = lane * 8 < p.channels;
-  for (int64_t wid = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); wid < total;
-       wid += (int64_t)gridDim.x * warps_per_block) {
+  const int lane_off = active ? lane * 8 : 0;
+  const int64_t task = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t w_begin = task * p.bins_per_warp;
+  const int64_t w_end = min(total, w_begin + p.bins_per_warp);
+
+  // per-RoI state (warp-uniform), recomputed only when the task crosses into another RoI
+  int cur_roi = -1;
+  int H = 0, W = 0, Wp = 0, gh = 1, gw = 1;
+  const __half* fhi = nullptr;
+  const __half* flo = nullptr;
+  float cw = 0.f, chh = 0.f, sn = 0.f, cs = 1.f, bsh = 0.f, bsw = 0.f, sh0 = 0.f, sw0 = 0.f, count = 1.f, inv_count = 0.f;
+
+  for (int64_t wid = w_begin; wid < w_end; ++wid) {
     const int roi_idx = (int)(wid / bins);
     const int bin = (int)(wid - (int64_t)roi_idx * bins);
     const int bph = bin / p.pw, bpw = bin - bph * p.pw;
-    const float* roi = p.rois + (int64_t)roi_idx * 6;
-    const int batch = (int)roi[0];
-    const float bx = roi[1], by = roi[2], bw = roi[3], bh = roi[4], ba = roi[5];
-    const int lvl = p.num_levels > 1 ? assign_level(bw, bh, p.min_level, p.num_levels) : 0;
-    const int H = p.feat_h[lvl], W = p.feat_w[lvl];
-    const float s = p.scale[lvl];
-    const int Hp = H + 2 * p.border, Wp = W + 2 * p.border;
-    const __half* fhi = reinterpret_cast<const __half*>(p.feat[lvl]);
-    const __half* flo = reinterpret_cast<const __half*>(p.feat_lo[lvl]);
-    const int64_t img_off = (int64_t)batch * Hp * Wp * p.ld + lane * 8;
+    if (roi_idx != cur_roi) {
+      cur_roi = roi_idx;
+      const float* roi = p.rois + (int64_t)roi_idx * 6;
+      const int batch = (int)roi[0];
+      const float bx = roi[1], by = roi[2], bw = roi[3], bh = roi[4], ba = roi[5];
+      const int lvl = p.num_levels > 1 ? assign_level(bw, bh, p.min_level, p.num_levels) : 0;
+      H = p.feat_h[lvl];
+      W = p.feat_w[lvl];
+      const float s = p.scale[lvl];
+      const int Hp = H + 2 * p.border;
+      Wp = W + 2 * p.border;
+      const int64_t img_off = (int64_t)batch * Hp * Wp * p.ld + lane_off;
+      fhi = reinterpret_cast<const __half*>(p.feat[lvl]) + img_off;
+      flo = reinterpret_cast<const __half*>(p.feat_lo[lvl]) + img_off;
+      cw = bx * s - 0.5f;
+      chh = by * s - 0.5f;
+      const float rw = bw * s, rh = bh * s;
+      // correctly rounded sin/cos (via double) so that the samples land exactly where the fp32 CPU path puts them
+      const float theta = (float)((double)ba * 3.14159265358979323846 / 180.0);
+      sn = (float)sin((double)theta);
+      cs = (float)cos((double)theta);
+      bsh = rh / (float)p.ph;
+      bsw = rw / (float)p.pw;
+      gh = S > 0 ? S : (p.sampling > 0 ? p.sampling : (int)ceilf(rh / (float)p.ph));
+      gw = S > 0 ? S : (p.sampling > 0 ? p.sampling : (int)ceilf(rw / (float)p.pw));
+      const int cnt = max(gh * gw, 1);
+      count = (float)cnt;
+      // x / 2^k == x * 2^-k exactly: skip the division sequence for power-of-two sample counts
+      inv_count = (cnt & (cnt - 1)) == 0 ? 1.0f / count : 0.f;
+      sh0 = -rh / 2.0f;
+      sw0 = -rw / 2.0f;
+    }
 
-    const float cw = bx * s - 0.5f, chh = by * s - 0.5f;
-    const float rw = bw * s, rh = bh * s;
-    const float theta = (float)((double)ba * 3.14159265358979323846 / 180.0);
-    const float sn = (float)sin((double)theta), cs = (float)cos((double)theta);
-    const float bsh = rh / (float)p.ph, bsw = rw / (float)p.pw;
-    const int gh = p.sampling > 0 ? p.sampling : (int)ceilf(rh / (float)p.ph);
-    const int gw = p.sampling > 0 ? p.sampling : (int)ceilf(rw / (float)p.pw);
-    const float count = (float)max(gh * gw, 1);
-    const float sh0 = -rh / 2.0f, sw0 = -rw / 2.0f;
-
-    {
-      float acc[8];
+    float acc[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (S == 2) {
+      // same expressions as the generic path with gh = gw = 2 (x / 2.0f == x * 0.5f exactly)
+      const float xx0 = sw0 + bpw * bsw + (0.f + .5f) * bsw * 0.5f;
+      const float xx1 = sw0 + bpw * bsw + (1.f + .5f) * bsw * 0.5f;
+      const float xs0 = xx0 * sn, xc0 = xx0 * cs, xs1 = xx1 * sn, xc1 = xx1 * cs;
+#pragma unroll(OCC == 2 ? 2 : 1)
+      for (int iy = 0; iy < 2; ++iy) {
+        const float yy = sh0 + bph * bsh + ((float)iy + .5f) * bsh * 0.5f;
+        const float yc = yy * cs, ys = yy * sn;
+        const TapSet t0 = make_taps(yc - xs0 + chh, ys + xc0 + cw, H, W, Wp, p.border, p.ld);
+        const TapSet t1 = make_taps(yc - xs1 + chh, ys + xc1 + cw, H, W, Wp, p.border, p.ld);
+        // 16 independent 16-byte loads in flight per lane before the first use
+        const uint4 a0h = GLASS_LD16(fhi + t0.o1), a0l = GLASS_LD16(flo + t0.o1);
+        const uint4 b0h = GLASS_LD16(fhi + t0.o2), b0l = GLASS_LD16(flo + t0.o2);
+        const uint4 c0h = GLASS_LD16(fhi + t0.o3), c0l = GLASS_LD16(flo + t0.o3);
+        const uint4 d0h = GLASS_LD16(fhi + t0.o4), d0l = GLASS_LD16(flo + t0.o4);
+        const uint4 a1h = GLASS_LD16(fhi + t1.o1), a1l = GLASS_LD16(flo + t1.o1);
+        const uint4 b1h = GLASS_LD16(fhi + t1.o2), b1l = GLASS_LD16(flo + t1.o2);
+        const uint4 c1h = GLASS_LD16(fhi + t1.o3), c1l = GLASS_LD16(flo + t1.o3);
+        const uint4 d1h = GLASS_LD16(fhi + t1.o4), d1l = GLASS_LD16(flo + t1.o4);
+        fma8(a0h, a0l, t0.w1, acc); fma8(b0h, b0l, t0.w2, acc); fma8(c0h, c0l, t0.w3, acc); fma8(d0h, d0l, t0.w4, acc);
+        fma8(a1h, a1l, t1.w1, acc); fma8(b1h, b1l, t1.w2, acc); fma8(c1h, c1l, t1.w3, acc); fma8(d1h, d1l, t1.w4, acc);
+      }
+    } else {
       for (int iy = 0; iy < gh; ++iy) {
         const float yy = sh0 + bph * bsh + ((float)iy + .5f) * bsh / (float)gh;
         for (int ix = 0; ix < gw; ++ix) {
           const float xx = sw0 + bpw * bsw + ((float)ix + .5f) * bsw / (float)gw;
-          float y = yy * cs - xx * sn + chh;
-          float x = yy * sn + xx * cs + cw;
-          if (y < -1.0f || y > (float)H || x < -1.0f || x > (float)W) continue;
-          y = fmaxf(y, 0.f);
-          x = fmaxf(x, 0.f);
-          int yl = (int)y, xl = (int)x, yh, xh;
-          if (yl >= H - 1) { yh = yl = H - 1; y = (float)yl; } else { yh = yl + 1; }
-          if (xl >= W - 1) { xh = xl = W - 1; x = (float)xl; } else { xh = xl + 1; }
-          const float ly = y - (float)yl, lx = x - (float)xl;
-          const float hy = 1.f - ly, hx = 1.f - lx;
-          const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
-          if (active) {
-            float a[8], b[8], c[8], d[8];
-            load8(fhi, flo, img_off + ((int64_t)(yl + p.border) * Wp + xl + p.border) * p.ld, a);
-            load8(fhi, flo, img_off + ((int64_t)(yl + p.border) * Wp + xh + p.border) * p.ld, b);
-            load8(fhi, flo, img_off + ((int64_t)(yh + p.border) * Wp + xl + p.border) * p.ld, c);
-            load8(fhi, flo, img_off + ((int64_t)(yh + p.border) * Wp + xh + p.border) * p.ld, d);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] += w1 * a[j] + w2 * b[j] + w3 * c[j] + w4 * d[j];
-          }
+          const TapSet t = make_taps(yy * cs - xx * sn + chh, yy * sn + xx * cs + cw, H, W, Wp, p.border, p.ld);
+          const uint4 ah = GLASS_LD16(fhi + t.o1), al = GLASS_LD16(flo + t.o1);
+          const uint4 bh2 = GLASS_LD16(fhi + t.o2), bl = GLASS_LD16(flo + t.o2);
+          const uint4 ch = GLASS_LD16(fhi + t.o3), cl = GLASS_LD16(flo + t.o3);
+          const uint4 dh = GLASS_LD16(fhi + t.o4), dl = GLASS_LD16(flo + t.o4);
+          fma8(ah, al, t.w1, acc); fma8(bh2, bl, t.w2, acc); fma8(ch, cl, t.w3, acc); fma8(dh, dl, t.w4, acc);
         }
       }
-      if (active) {
+    }
+    if (active) {
+      if (inv_count != 0.f) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = acc[j] * inv_count;
+      } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = acc[j] / count;
-        if (p.out_f32) {
-          float4* o = reinterpret_cast<float4*>(p.out_f32 + ((int64_t)roi_idx * bins + bin) * p.channels + lane * 8);
-          o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-          o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-        }
-        if (p.out_hi) {
-          const int64_t row = ((int64_t)roi_idx * p.out_hp + bph + p.out_border) * p.out_wp + bpw + p.out_border;
-          uint32_t hw[4], lw[4];
+      }
+      if (p.out_f32) {
+        float4* o = reinterpret_cast<float4*>(p.out_f32 + ((int64_t)roi_idx * bins + bin) * p.channels + lane * 8);
+        o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      }
+      if (p.out_hi) {
+        const int64_t row = ((int64_t)roi_idx * p.out_hp + bph + p.out_border) * p.out_wp + bpw + p.out_border;
+        uint32_t hw[4], lw[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            __half h0, l0, h1, l1;
-            split16(acc[2 * j], h0, l0);
-            split16(acc[2 * j + 1], h1, l1);
-            hw[j] = pack16x2(h0, h1);
-            lw[j] = pack16x2(l0, l1);
-          }
-          const int64_t off = row * p.ld_out + p.out_coff + lane * 8;
-          *reinterpret_cast<uint4*>(p.out_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-          *reinterpret_cast<uint4*>(p.out_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-        }
+        for (int j = 0; j < 4; ++j) split16x2(acc[2 * j], acc[2 * j + 1], hw[j], lw[j]);
+        const int64_t off = row * p.ld_out + p.out_coff + lane * 8;
+        *reinterpret_cast<uint4*>(p.out_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        *reinterpret_cast<uint4*>(p.out_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
       }
     }
   }
@@ -378,7 +462,17 @@ extern "C" int glass_roi_align_rotated(const GlassRoiAlignParams* p, void* strea
   const bool split8 = p->feat_is_split && p->channels % 8 == 0 && p->feat_ld % 8 == 0 &&
                       (!p->out_hi || (p->ld_out % 8 == 0 && p->out_coff % 8 == 0));
   if (split8) {
-    roi_align_rotated_split8_kernel<<<(int)blocks, 256, 0, stream>>>(k);
+    GLASS_CHECK((int64_t)(p->feat_h[0] + 2 * p->feat_border) * (p->feat_w[0] + 2 * p->feat_border) * p->feat_ld < ((int64_t)1 << 31),
+                "feature plane too large for 32-bit tap offsets");
+    static const int bpw_env = getenv("GLASS_ROI_BPW") ? atoi(getenv("GLASS_ROI_BPW")) : 0;  // A/B knob
+    k.bins_per_warp = bpw_env > 0 ? bpw_env : kBinsPerWarp;
+    const int64_t tasks = (warps + k.bins_per_warp - 1) / k.bins_per_warp;
+    const int64_t sblocks = (tasks + 7) / 8;
+    GLASS_CHECK(sblocks < ((int64_t)1 << 31), "too many bins");
+    static const int variant = getenv("GLASS_ROI_VARIANT") ? atoi(getenv("GLASS_ROI_VARIANT")) : 0;  // A/B knob
+    if (p->sampling_ratio == 2 && variant == 1) roi_align_rotated_split8_kernel<2, 3><<<(int)sblocks, 256, 0, stream>>>(k);
+    else if (p->sampling_ratio == 2) roi_align_rotated_split8_kernel<2, 2><<<(int)sblocks, 256, 0, stream>>>(k);
+    else roi_align_rotated_split8_kernel<0, 2><<<(int)sblocks, 256, 0, stream>>>(k);
   } else if (p->channels <= 128) {
     if (p->feat_is_split) roi_align_rotated_kernel<1, true><<<(int)blocks, 256, 0, stream>>>(k);
     else roi_align_rotated_kernel<1, false><<<(int)blocks, 256, 0, stream>>>(k);

@@ -160,7 +160,10 @@ def conv_gemm(a_hi: torch.Tensor, a_lo: Optional[torch.Tensor], rows_a: int, k_p
         _lib.check(_lib.load().glass_conv_gemm(C.byref(p), _stream()))
         e1.record(torch.cuda.current_stream())
         m_valid = p.m_imgs * (p.m_h - 2 * p.m_border) * (p.m_w - 2 * p.m_border)
-        PROFILE.append((e0, e1, 2.0 * m_valid * w.cout * w.cin * w.kh * w.kw))  # algorithmic FLOPs of this launch
+        # algorithmic FLOPs of this launch + the GEMM's shape (tools/layer_profile.py)
+        PROFILE.append((e0, e1, 2.0 * m_valid * w.cout * w.cin * w.kh * w.kw,
+                        dict(m=p.m_imgs * p.m_h * p.m_w, n=w.n_p, k=k_per_tap * len(tap_shift), taps=len(tap_shift),
+                             a_ld=a_ld, res=residual is not None, f32=out_f32 is not None)))
         return
     _lib.check(_lib.load().glass_conv_gemm(C.byref(p), _stream()))
 

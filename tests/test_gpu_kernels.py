@@ -229,6 +229,36 @@ def test_roi_align_rotated_matches_oracle(ops, cfg):
     _close(got.permute(0, 3, 1, 2), ref, cfg)
 
 
+@pytest.mark.parametrize("cfg", ["box_pooler", "recog_pooler", "narrow"])
+def test_roi_align_rotated_split_input_matches_oracle(ops, cfg):
+    """The production path: split-fp16 feature maps in (8 channels per lane), fp32 and split rows out.  The oracle
+    pools the values the split planes represent (Act.to_nchw), so the only differences are summation order."""
+    from oracle import d2_ops
+    g = torch.Generator().manual_seed(21)
+    if cfg == "box_pooler":
+        sizes, scales, out_size, sampling, n, c = [64, 32, 16, 8, 4], [1 / 4, 1 / 8, 1 / 16, 1 / 32, 1 / 64], (7, 7), 2, 96, 256
+        batch = 2
+    elif cfg == "recog_pooler":
+        sizes, scales, out_size, sampling, n, c, batch = [64], [1 / 4], (8, 32), 0, 24, 256, 1
+    else:  # fewer channels than lanes * 8: the upper lanes are idle
+        sizes, scales, out_size, sampling, n, c, batch = [32, 16], [1 / 4, 1 / 8], (5, 3), 2, 17, 72, 1
+    acts = [ops.Act.from_nchw((torch.randn(batch, c, s, s, generator=g) * 2).cuda()) for s in sizes]
+    feats = [a.to_nchw().cpu() for a in acts]
+    rois = _random_rois(g, n, img=256.0, batch=batch)
+    rois[:, 3:5] *= 0.55
+    # a few RoIs hanging over the border / fully outside exercise the "sample outside the map" path
+    rois[0, 1:3] = torch.tensor([-3.0, 10.0])
+    rois[1, 1:3] = torch.tensor([400.0, 400.0])
+    ref = d2_ops.roi_pooler(feats, [rois[rois[:, 0] == b][:, 1:] for b in range(batch)], out_size, scales, sampling)
+    order = torch.cat([torch.nonzero(rois[:, 0] == b).squeeze(1) for b in range(batch)])
+    out_act = ops.Act(n, c, out_size[0], out_size[1], border=1)
+    got = ops.roi_align_rotated(acts, rois[order].contiguous().cuda(), out_size, scales, sampling,
+                                out_split=(out_act.buf, out_act.hp, out_act.wp, out_act.border, 0, out_act.cp))
+    _close(got.permute(0, 3, 1, 2), ref, cfg + "/f32")
+    _close(out_act.to_nchw(), ref, cfg + "/split")
+    assert out_act.buf[:, :, 0].abs().max().item() == 0  # the zero border is never written
+
+
 def test_image_roi_align_matches_oracle(ops):
     from oracle import d2_ops
     g = torch.Generator().manual_seed(12)
