@@ -15,7 +15,7 @@ SYMBOLS = [
     "glass_roi_align_rotated", "glass_image_roi_align_rotated", "glass_rpn_topk_decode", "glass_rpn_topk_workspace_bytes",
     "glass_nms_workspace_bytes",
     "glass_nms_rotated", "glass_box_decode", "glass_gc_attention", "glass_hmean_rows", "glass_lstm_bidir",
-    "glass_aster_decode", "glass_aster_finalize", "glass_resize_bilinear_u8",
+    "glass_aster_decode", "glass_aster_finalize", "glass_resize_bilinear_u8", "glass_postprocess_merge", "glass_text_scores",
 ]
 
 
@@ -99,6 +99,19 @@ class AsterParams(C.Structure):
     ]
 
 
+class PostprocessParams(C.Structure):
+    _fields_ = [
+        ("boxes", C.c_void_p), ("scores", C.c_void_p), ("text_scores", C.c_void_p), ("counts", C.c_void_p),
+        ("n_img", C.c_int32), ("m", C.c_int32),
+        ("min_box_dim", C.c_float), ("valid_score", C.c_float), ("detect_threshold", C.c_float),
+        ("text_threshold", C.c_float), ("merge_ioa_thresh", C.c_float), ("pairs_height_ratio_thresh", C.c_float),
+        ("max_angle_diff", C.c_float), ("minimal_ioa_thresh", C.c_float), ("nms_iou", C.c_float),
+        ("max_iters", C.c_int32),
+        ("out_boxes", C.c_void_p), ("out_scores", C.c_void_p), ("out_polygons", C.c_void_p),
+        ("out_index", C.c_void_p), ("out_count", C.c_void_p), ("out_iters", C.c_void_p),
+    ]
+
+
 _lib = None
 
 
@@ -138,6 +151,8 @@ def load() -> C.CDLL:
     lib.glass_aster_decode.argtypes = [C.POINTER(AsterParams), p]
     lib.glass_aster_finalize.argtypes = [p, p, p, i, i, i, p]
     lib.glass_resize_bilinear_u8.argtypes = [p, i, i, i, p, i, i, p]
+    lib.glass_postprocess_merge.argtypes = [C.POINTER(PostprocessParams), p]
+    lib.glass_text_scores.argtypes = [p, i, i, i, i, p, p, p, p]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if name.startswith("glass_") and name not in ("glass_last_error", "glass_abi_version", "glass_launch_count",

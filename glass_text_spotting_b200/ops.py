@@ -454,3 +454,52 @@ def resize_bilinear_u8(img_hwc: torch.Tensor, out_hw: Tuple[int, int], flip_chan
     _lib.check(_lib.load().glass_resize_bilinear_u8(_ptr(img_hwc), h, w, int(flip_channels), _ptr(out), out_hw[0],
                                                     out_hw[1], _stream()))
     return out
+
+
+# ---------------------------------------------------------------------------------------------- post-processing
+def text_scores(probs: torch.Tensor, stop_index: int = 1, want_steps: bool = False):
+    """pred_text_prob fp32 [n, steps, classes] -> word score [n] (+ per-step argmax int32 and max prob [n, steps])."""
+    assert probs.dim() == 3 and probs.dtype == torch.float32 and probs.is_contiguous()
+    n, steps, classes = probs.shape
+    score = torch.empty((n,), dtype=torch.float32, device=probs.device)
+    idx = torch.empty((n, steps), dtype=torch.int32, device=probs.device) if want_steps else None
+    maxp = torch.empty((n, steps), dtype=torch.float32, device=probs.device) if want_steps else None
+    if n:
+        _lib.check(_lib.load().glass_text_scores(_ptr(probs), n, steps, classes, stop_index, _ptr(score), _ptr(idx),
+                                                 _ptr(maxp), _stream()))
+    return (score, idx, maxp) if want_steps else score
+
+
+def postprocess_merge(boxes: torch.Tensor, scores: torch.Tensor, counts: Optional[torch.Tensor] = None,
+                      text_scores_: Optional[torch.Tensor] = None, min_box_dim: float = 2.0, valid_score: float = 0.15,
+                      detect_threshold: float = 0.25, text_threshold: float = 0.25, merge_ioa_thresh: float = 0.3,
+                      pairs_height_ratio_thresh: float = 0.35, max_angle_diff: float = 15.0,
+                      minimal_ioa_thresh: float = 0.01, nms_iou: float = 0.99, max_iters: int = 1000,
+                      want_polygons: bool = True):
+    """Device-side PostProcessorRotatedBoxes / PostProcessorAcademic (see include/glass_b200.h).
+    boxes fp32 [n_img, m, 5], scores [n_img, m], counts int32 [n_img] -> dict of padded outputs."""
+    assert boxes.dim() == 3 and boxes.shape[2] == 5 and boxes.dtype == torch.float32 and boxes.is_contiguous()
+    n_img, m = boxes.shape[0], boxes.shape[1]
+    assert scores.shape == (n_img, m) and scores.dtype == torch.float32 and scores.is_contiguous()
+    dev = boxes.device
+    out = {"boxes": torch.empty((n_img, m, 5), dtype=torch.float32, device=dev),
+           "scores": torch.empty((n_img, m), dtype=torch.float32, device=dev),
+           "polygons": torch.empty((n_img, m, 4, 2), dtype=torch.float32, device=dev) if want_polygons else None,
+           "index": torch.empty((n_img, m), dtype=torch.int32, device=dev),
+           "count": torch.empty((n_img,), dtype=torch.int32, device=dev),
+           "iters": torch.empty((n_img,), dtype=torch.int32, device=dev)}
+    p = _lib.PostprocessParams()
+    p.boxes, p.scores, p.text_scores, p.counts = _ptr(boxes), _ptr(scores), _ptr(text_scores_), _ptr(counts)
+    if counts is not None:
+        assert counts.dtype == torch.int32 and counts.numel() == n_img
+    if text_scores_ is not None:
+        assert text_scores_.shape == (n_img, m) and text_scores_.dtype == torch.float32 and text_scores_.is_contiguous()
+    p.n_img, p.m = n_img, m
+    p.min_box_dim, p.valid_score, p.detect_threshold, p.text_threshold = min_box_dim, valid_score, detect_threshold, text_threshold
+    p.merge_ioa_thresh, p.pairs_height_ratio_thresh, p.max_angle_diff = merge_ioa_thresh, pairs_height_ratio_thresh, max_angle_diff
+    p.minimal_ioa_thresh, p.nms_iou, p.max_iters = minimal_ioa_thresh, nms_iou, max_iters
+    p.out_boxes, p.out_scores, p.out_polygons = _ptr(out["boxes"]), _ptr(out["scores"]), _ptr(out["polygons"])
+    p.out_index, p.out_count, p.out_iters = _ptr(out["index"]), _ptr(out["count"]), _ptr(out["iters"])
+    if n_img:
+        _lib.check(_lib.load().glass_postprocess_merge(C.byref(p), _stream()))
+    return out

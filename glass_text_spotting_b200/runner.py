@@ -1,7 +1,7 @@
 """B200GlassRunner: the single-image Python API of the reference (glass/inference/glass_runner.py:72-109) on
 the B200 hot path: numpy HWC image -> device resize (bilinear, align_corners=False) -> model -> boxes rescaled
-to the original image.  The reference then applies its host-side PostProcessorAcademic merge loop
-(glass_runner.py:106), which is outside this project's scope and is left to the caller."""
+to the original image -> the post-processor (glass_runner.py:106; here the device-side merge loop of
+``postprocess.B200PostProcessor``)."""
 from typing import Dict
 
 import numpy as np
@@ -9,18 +9,22 @@ import torch
 
 from . import ops
 from .modeling.glass_rcnn import B200GlassRCNN
+from .postprocess import B200PostProcessor
 from .structures import Instances
 from .text import TextDecoder
 
 
 class B200GlassRunner:
     def __init__(self, state_dict: Dict[str, torch.Tensor], min_target_size: int = 1200, max_target_size: int = 1600,
-                 max_upscale_ratio: float = 2.0, input_format: str = "BGR", device="cuda", **model_kwargs):
+                 max_upscale_ratio: float = 2.0, input_format: str = "BGR", device="cuda", post_processor="default",
+                 **model_kwargs):
         # defaults: configs/glass_finetune_totaltext.yaml:22-25 (INFERENCE_TH_TEST block)
         self.min_target_size, self.max_target_size = min_target_size, max_target_size
         self.max_upscale_ratio, self.input_format, self.device = max_upscale_ratio, input_format, device
         self.model = B200GlassRCNN(state_dict, device=device, **model_kwargs)
         self.text_decoder = TextDecoder()
+        # build_post_processor(cfg) (glass_runner.py:70); pass None to get the raw detections
+        self.post_processor = B200PostProcessor() if post_processor == "default" else post_processor
 
     def get_inference_scale_ratio(self, image_shape) -> float:
         """glass_runner.py:111-121."""
@@ -47,6 +51,8 @@ class B200GlassRunner:
         if scale != 1:
             preds.pred_boxes.scale(1 / scale, 1 / scale)
         preds._image_size = (h, w)
+        if self.post_processor is not None:
+            preds = self.post_processor(preds)
         return preds
 
     def read_text(self, preds: Instances):

@@ -306,6 +306,44 @@ int glass_aster_decode(const GlassAsterParams* p, void* stream);
 int glass_aster_finalize(float* probs, const int32_t* first_eos, const int32_t* word_start, int n_img, int steps,
                          int num_classes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Post-processing: the step that follows the hot path in every caller.
+ * ------------------------------------------------------------------------------------------ */
+/* glass_postprocess_merge -- PostProcessorRotatedBoxes.__call__ (glass/postprocess/post_processor_rotated_boxes.py:
+ * 66-184) + the text-score filter of PostProcessorAcademic.__call__ (post_processor_academic.py:26-34), one CTA per
+ * image, no host round trips: min(w,h) >= min_box_dim and score >= valid_score filters; then until no pair merges:
+ * rotated intersection-over-min-area of every pair (glass/structures/boxes.py:24-49), pair masks (IoA, angle,
+ * height ratio), min-area-rectangle merge of each valid pair (replaces cv2.minAreaRect on the host, :251-286),
+ * reference write-back order, nms_rotated(nms_iou); finally score >= detect_threshold, text score >= text_threshold
+ * (when text_scores is given) and boxes_to_polygons (:221-249).  Survivors are written in the reference's order
+ * (descending score once a merge round has run), zero / -1 padded to m. */
+typedef struct {
+  const float* boxes;       /* [n_img, m, 5] (cx, cy, w, h, angle_deg) */
+  const float* scores;      /* [n_img, m] */
+  const float* text_scores; /* optional [n_img, m] word scores (glass_text_scores) */
+  const int32_t* counts;    /* optional [n_img] detections per image (default m) */
+  int32_t n_img, m;         /* m <= 128 */
+  float min_box_dim, valid_score, detect_threshold, text_threshold;           /* cfg.POST_PROCESSING.* */
+  float merge_ioa_thresh, pairs_height_ratio_thresh, max_angle_diff;
+  float minimal_ioa_thresh; /* 0.01, post_processor_rotated_boxes.py:40 */
+  float nms_iou;            /* 0.99, :181 */
+  int32_t max_iters;        /* safety bound on merge rounds (the reference loops until nothing merges) */
+  float* out_boxes;         /* [n_img, m, 5] */
+  float* out_scores;        /* [n_img, m] */
+  float* out_polygons;      /* optional [n_img, m, 4, 2] */
+  int32_t* out_index;       /* [n_img, m] index of the surviving detection in the input, -1 padded */
+  int32_t* out_count;       /* [n_img] */
+  int32_t* out_iters;       /* optional [n_img] merge rounds run */
+} GlassPostprocessParams;
+int glass_postprocess_merge(const GlassPostprocessParams* p, void* stream);
+
+/* glass_text_scores -- numeric part of get_instances_text (glass/evaluation/text_evaluator.py:323-331) +
+ * TextEncoder.decode_attention's word score (glass/modeling/recognition/text_encoder.py:80-151): per decoding
+ * step max / argmax over the classes; score = product of the max probabilities up to and including the first
+ * stop symbol.  probs fp32 [n_words, steps, classes]; out_idx / out_maxp optional [n_words, steps]. */
+int glass_text_scores(const float* probs, int n_words, int steps, int classes, int stop_index, float* score,
+                      int32_t* out_idx, float* out_maxp, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
