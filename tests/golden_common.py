@@ -97,3 +97,17 @@ def make_postprocess_case(seed: int, n_lines: int, n_iso: int, img: float = 1024
     perm = torch.randperm(len(t), generator=g)
     t = t[perm]
     return t[:, :5].contiguous(), t[:, 5].contiguous()
+
+
+def make_eval_inputs(seed, n):
+    g = torch.Generator().manual_seed(seed)
+    boxes = torch.stack([torch.rand(n, generator=g) * 900 + 50, torch.rand(n, generator=g) * 900 + 50,
+                         torch.rand(n, generator=g) * 200 + 10, torch.rand(n, generator=g) * 60 + 8,
+                         torch.rand(n, generator=g) * 360 - 180], 1)
+    scores = torch.rand(n, generator=g)
+    probs = torch.softmax(torch.randn(n, 26, 97, generator=g) * 9.0, dim=2)
+    for i in range(n):
+        stop = int(torch.randint(0, 9, (1,), generator=g))   # stop == 0: empty word (record dropped)
+        probs[i, stop] = 0.001
+        probs[i, stop, 1] = 0.904
+    return boxes, scores, probs
