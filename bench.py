@@ -31,6 +31,9 @@ WORKLOADS = {
 WORKLOADS["roialign_512"] = dict(batch=1, h=1024, w=1024, full=False, roialign=True,
                                  desc="RotatedROIAlign microbench: 512 rotated RoIs over 5 FPN levels, 7x7, sampling 2 "
                                       "(BASELINE.json configs[2])")
+WORKLOADS["postprocess_bs4"] = dict(batch=4, h=1024, w=1024, full=False, postprocess=True,
+                                   desc="word post-processor (merge loop + text-score filter, SURVEY.md 8f #1) on the "
+                                        "detections of 4 images x 100 words (synthetic broken text lines)")
 CPU_WORD_CAP = 16  # the CPU arm decodes at most this many words per image (bounded sample)
 
 
@@ -97,6 +100,18 @@ def _cpu_runner(wl):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     g = torch.Generator().manual_seed(0)
+    if wl.get("postprocess"):
+        from oracle import postprocess as opp  # test infrastructure; allowed here only as the timed CPU baseline
+        from glass_text_spotting_b200.text import TextDecoder
+        boxes, scores, probs = _postprocess_inputs(wl["batch"])
+        dec = TextDecoder()
+
+        def run():
+            for i in range(1):  # ONE image per call, like every other CPU leg
+                ts = torch.tensor([w["score"] for w in dec.decode_probs(probs[i])], dtype=torch.float32)
+                opp.post_process(boxes[i], scores[i], ts)
+        return run, ("1 image x 100 detections through the oracle's post-processor (reference algorithm: torch fp32 + "
+                     "cv2.minAreaRect + C rotated IoU/NMS)")
     if not wl["full"]:
         from oracle import nets  # test infrastructure; allowed here only as the timed CPU baseline
         net = nets.ResNetFPN().eval()
@@ -200,6 +215,105 @@ def _roialign_algorithmic_bytes(rois, sizes=(256, 128, 64, 32, 16), strides=(4, 
             cells.update((yy_[ok] * H + xx_[ok]).tolist())
         total += len(cells) * c * 4
     return total + rois.shape[0] * c * res * res * 4 + rois.numel() * 4
+
+
+def _postprocess_inputs(batch, m=100):
+    import torch
+    from glass_text_spotting_b200.synthetic import make_postprocess_case
+    boxes, scores, probs = [], [], []
+    for i in range(batch):
+        b, s = make_postprocess_case(100 + i, 24, 40)
+        assert len(b) >= m
+        boxes.append(b[:m]); scores.append(s[:m])
+        g = torch.Generator().manual_seed(200 + i)
+        pr = torch.softmax(torch.randn(m, 26, 97, generator=g) * 12.0, dim=2)
+        stops = torch.randint(1, 12, (m,), generator=g)
+        for k in range(m):
+            pr[k, stops[k]] = 0.002
+            pr[k, stops[k], 1] = 0.808
+        probs.append(pr)
+    return torch.stack(boxes), torch.stack(scores), torch.stack(probs)
+
+
+def run_postprocess(args):
+    """SURVEY.md 8f #1 measured like the hot path: device-resident inputs for `value`; `e2e` = detections and text
+    probabilities from pinned host memory, survivors back to the host."""
+    import torch
+    from glass_text_spotting_b200 import lib, ops
+    wl = WORKLOADS["postprocess_bs4"]
+    B, m = wl["batch"], 100
+    boxes, scores, probs = _postprocess_inputs(B, m)
+    host = [t.contiguous().pin_memory() for t in (boxes, scores, probs)]
+    dev = [t.cuda() for t in host]
+    L = lib.load()
+
+    def step(b, s, p):
+        ts = ops.text_scores(p.view(B * m, 26, 97), 1).view(B, m)
+        return ops.postprocess_merge(b, s, None, ts)
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        r = step(*dev)
+    torch.cuda.synchronize()
+    kept = r["count"].cpu().tolist()
+    iters = r["iters"].cpu().tolist()
+    sampler = ClockSampler(0)
+    if not args.no_clocks:
+        sampler.start()
+    launches0 = L.glass_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(*dev)
+    e1.record()
+    torch.cuda.synchronize()
+    t_dev = e0.elapsed_time(e1) / 1e3
+    launches = L.glass_launch_count() - launches0
+    clocks = sampler.stop() if not args.no_clocks else None
+    dbuf = [torch.empty_like(t) for t in dev]
+    out_host = None
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        for d, h in zip(dbuf, host):
+            d.copy_(h, non_blocking=True)
+        r = step(*dbuf)
+        packed = torch.cat((r["boxes"].view(B, -1), r["index"].float(), r["count"].float().view(B, 1)), 1)
+        if out_host is None:
+            out_host = torch.empty(packed.shape, dtype=packed.dtype).pin_memory()
+        out_host.copy_(packed, non_blocking=True)
+    f1.record()
+    torch.cuda.synchronize()
+    t_e2e = f0.elapsed_time(f1) / 1e3
+    # the merge kernel alone
+    ts = ops.text_scores(dev[2].view(B * m, 26, 97), 1).view(B, m)
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(args.steps):
+        ops.postprocess_merge(dev[0], dev[1], None, ts)
+    k1.record()
+    torch.cuda.synchronize()
+    merge_ms = k0.elapsed_time(k1) / args.steps
+    out = {
+        "metric": "images/sec post-processed (100 detections each)", "value": B * args.steps / t_dev, "unit": "images/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": warm, "ms_per_step": 1e3 * t_dev / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "survivors_per_image": kept, "merge_rounds_per_image": iters,
+                   "l2": "working set is 4 MB of text probabilities + 10 KB of boxes per step: L2-resident by nature "
+                         "(latency-bound, one CTA per image)"},
+        "e2e": {"value": B * args.steps / t_e2e, "unit": "images/s",
+                "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in host),
+                "d2h_bytes_per_step": out_host.numel() * out_host.element_size(),
+                "note": "pinned host detections + text probabilities -> H2D -> text scores + merge loop -> D2H of survivors"},
+        "gpu_launches": launches, "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": None, "peak": None, "unit": "GB/s", "frac": None, "traffic": None,
+                     "kernel": "postprocess_merge_kernel (one CTA per image; latency-bound: sequential merge rounds x "
+                               "greedy NMS, no roofline applies)", "kernel_ms_per_launch": merge_ms},
+    }
+    if not args.no_cpu:
+        v, cores, sample = cpu_sample(wl, repeats=5)
+        out["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}
+    print(json.dumps(out))
 
 
 def run_roialign(args):
@@ -464,6 +578,8 @@ def main():
         run_reference(args)
     elif WORKLOADS[args.workload].get("roialign"):
         run_roialign(args)
+    elif WORKLOADS[args.workload].get("postprocess"):
+        run_postprocess(args)
     else:
         run_b200(args)
 

@@ -41,6 +41,7 @@ struct GemmKernelParams {
   int64_t rows_m;
   int32_t tiles_m, tiles_n, bn;
   int32_t kblocks_per_tap, ntaps;
+  int32_t a_col0;  // pixel-grouped mode: first column of the k-block boxes inside the (overlapping) tensor row
   int32_t tap_shift[GLASS_MAX_TAPS];
   int32_t num_stages, stage_bytes, b_tile_bytes;
   // tap-row mode (3x3 convs): per (tap row r, channel block) ONE activation block of 136 rows is staged and its three
@@ -206,7 +207,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             uint8_t* s = smem + (size_t)stage * p.stage_bytes;
             // the leader's barrier collects the bytes of BOTH CTAs' loads
             if (leader) mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)p.stage_bytes * (PAIR ? 2u : 1u));
-            const int ka = kb * BK;
+            const int ka = p.a_col0 + kb * BK;
             const int kw = (t * p.kblocks_per_tap + kb) * BK;
             auto load = [&](void* dst, const CUtensorMap* map, int c0, int c1) {
               if (PAIR) tma_load_2d_pair(dst, map, &full_bar[stage], c0, c1);
@@ -573,7 +574,17 @@ extern "C" int glass_conv_gemm(const GlassConvGemmParams* p, void* stream_v) {
   // the tensor, so they are left to the TMA's out-of-bounds zero fill (they start inside the zero border)
   const int a_ld = p->a_ld > 0 ? p->a_ld : p->k_per_tap;
   uint64_t a_rows = (uint64_t)p->rows_a;
-  if (a_ld != p->k_per_tap) {
+  const bool grouped = p->a_inner > 0;
+  int a_inner = p->k_per_tap;
+  if (grouped) {
+    // pixel-grouped mode: rows_a counts GROUP rows of a_ld elements; the tensor row is a window of a_inner elements
+    GLASS_CHECK(p->a_ld > 0 && a_ld % 8 == 0 && p->a_col0 >= 0 && p->a_col0 % 8 == 0, "grouped mode: a_ld / a_col0 must be multiples of 8");
+    GLASS_CHECK(p->a_inner >= p->a_col0 + p->k_per_tap && p->a_inner % 8 == 0, "grouped mode: a_inner too small");
+    a_inner = p->a_inner;
+    const int64_t total = p->rows_a * (int64_t)a_ld;
+    GLASS_CHECK(total > a_inner, "too few rows for grouped mode");
+    a_rows = (uint64_t)((total - a_inner) / a_ld + 1);  // later rows would read past the tensor: TMA zero fill
+  } else if (a_ld != p->k_per_tap) {
     GLASS_CHECK(p->k_per_tap == BK && (a_ld == 8 || a_ld == 16 || a_ld == 32), "compact mode needs k_per_tap 64, a_ld 8/16/32");
     GLASS_CHECK(p->rows_a > BK / a_ld, "too few rows for compact mode");
     a_rows = (uint64_t)p->rows_a - (uint64_t)(BK / a_ld) + 1;
@@ -582,7 +593,7 @@ extern "C" int glass_conv_gemm(const GlassConvGemmParams* p, void* stream_v) {
   const int split_mul = split ? 2 : 1;
   const int smem_budget = 227 * 1024 - EPI_STAGE_BYTES - 1024 /*align slack*/ - 512 /*barriers*/;
   const int b_stage_bytes = b_rows * BK * 2 * split_mul;
-  bool group3 = p->ntaps == 9 && a_ld == p->k_per_tap && p->tap_mode != 1;
+  bool group3 = p->ntaps == 9 && a_ld == p->k_per_tap && p->tap_mode != 1 && !grouped;
   for (int r = 0; r < 3 && group3; ++r)
     group3 = p->tap_shift[3 * r + 1] == p->tap_shift[3 * r] + 1 && p->tap_shift[3 * r + 2] == p->tap_shift[3 * r] + 2;
   int a_stages = 2, b_stages = 0;
@@ -596,10 +607,10 @@ extern "C" int glass_conv_gemm(const GlassConvGemmParams* p, void* stream_v) {
     if (b_stages < 3) group3 = false;  // not enough room to keep the weight stream pipelined
   }
   const int a_box_rows = group3 ? A_BLOCK_ROWS : BM;
-  if (make_map_2d(&ma_hi, p->a_hi, p->k_per_tap, a_rows, BK, a_box_rows, a_ld)) return -1;
+  if (make_map_2d(&ma_hi, p->a_hi, a_inner, a_rows, BK, a_box_rows, a_ld)) return -1;
   if (make_map_2d(&mb_hi, p->b_hi, ktot, p->n, BK, b_rows)) return -1;
   if (split) {
-    if (make_map_2d(&ma_lo, p->a_lo, p->k_per_tap, a_rows, BK, a_box_rows, a_ld)) return -1;
+    if (make_map_2d(&ma_lo, p->a_lo, a_inner, a_rows, BK, a_box_rows, a_ld)) return -1;
     if (make_map_2d(&mb_lo, p->b_lo, ktot, p->n, BK, b_rows)) return -1;
   } else {
     ma_lo = ma_hi;
@@ -613,6 +624,7 @@ extern "C" int glass_conv_gemm(const GlassConvGemmParams* p, void* stream_v) {
   k.bn = bn;
   k.kblocks_per_tap = p->k_per_tap / BK;
   k.ntaps = p->ntaps;
+  k.a_col0 = grouped ? p->a_col0 : 0;
   for (int i = 0; i < GLASS_MAX_TAPS; ++i) k.tap_shift[i] = p->tap_shift[i];
   k.b_tile_bytes = b_rows * BK * 2;
   k.stage_bytes = (A_TILE_BYTES + k.b_tile_bytes) * split_mul;

@@ -157,6 +157,25 @@ __global__ void gather_taps_kernel(const uint4* __restrict__ shi, const uint4* _
   }
 }
 
+// ------------------------------------------------------------------ border re-zero (border = 1)
+__global__ void zero_border_kernel(uint4* __restrict__ hi, uint4* __restrict__ lo, int n, int hp, int wp, int cv) {
+  const int per_img = 2 * wp + 2 * (hp - 2);
+  const int64_t total = (int64_t)n * per_img * cv;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i % cv);
+    const int64_t t = i / cv;
+    const int b = (int)(t % per_img);
+    const int img = (int)(t / per_img);
+    int y, x;
+    if (b < wp) { y = 0; x = b; }
+    else if (b < 2 * wp) { y = hp - 1; x = b - wp; }
+    else { const int r = b - 2 * wp; y = 1 + (r >> 1); x = (r & 1) ? wp - 1 : 0; }
+    const int64_t off = (((int64_t)img * hp + y) * wp + x) * cv + v;
+    hi[off] = make_uint4(0, 0, 0, 0);
+    lo[off] = make_uint4(0, 0, 0, 0);
+  }
+}
+
 // ------------------------------------------------------------------ max pool (padding = -inf)
 __global__ void maxpool_kernel(const uint4* __restrict__ shi, const uint4* __restrict__ slo, int n, int h, int w,
                                int cv, int border, int kh, int kw, int sh, int sw, int ph, int pw, int ho, int wo,
@@ -316,6 +335,17 @@ extern "C" int glass_gather_taps(const void* src_hi, const void* src_lo, int n, 
   gather_taps_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>((const uint4*)src_hi, (const uint4*)src_lo, n, h, w,
                                                                cp / 8, border, kh, kw, sh, sw, ph, pw, ho, wo,
                                                                (uint4*)dst_hi, (uint4*)dst_lo);
+  count_launch();
+  GLASS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int glass_zero_border(void* hi, void* lo, int n, int h, int w, int cp, void* stream) {
+  GLASS_CHECK(hi && lo, "null pointer");
+  GLASS_CHECK(n > 0 && h > 0 && w > 0 && cp > 0 && cp % 8 == 0, "bad shape");
+  const int hp = h + 2, wp = w + 2;
+  const int64_t total = (int64_t)n * (2 * wp + 2 * (hp - 2)) * (cp / 8);
+  zero_border_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>((uint4*)hi, (uint4*)lo, n, hp, wp, cp / 8);
   count_launch();
   GLASS_CUDA(cudaGetLastError());
   return 0;

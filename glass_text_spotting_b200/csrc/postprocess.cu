@@ -29,6 +29,7 @@ namespace glass {
 
 constexpr int PP_MAX = 128;  // detections per image (DETECTIONS_PER_IMAGE = 100)
 constexpr int PP_WORDS = PP_MAX / 32;
+constexpr int PP_THREADS = 512;  // the pair loops (IoA matrix, NMS relation) are spread over 4x more threads than boxes
 
 struct PostprocessKernelParams {
   const float* boxes;
@@ -135,7 +136,7 @@ __device__ inline void merge_pair(const float* b1, const float* b2, float s1, fl
   out[0] = (float)cxr; out[1] = (float)cyr; out[2] = (float)wd; out[3] = (float)ht; out[4] = (float)ang;
 }
 
-__global__ void __launch_bounds__(PP_MAX) postprocess_merge_kernel(const PostprocessKernelParams p) {
+__global__ void __launch_bounds__(PP_THREADS) postprocess_merge_kernel(const PostprocessKernelParams p) {
   __shared__ float bx[PP_MAX][5];
   __shared__ float nb[PP_MAX][5];
   __shared__ float sc[PP_MAX];
@@ -242,24 +243,36 @@ __global__ void __launch_bounds__(PP_MAX) postprocess_merge_kernel(const Postpro
     }
     __syncthreads();
 
-    // ---- nms_rotated(boxes, scores, 0.99) (:181): greedy over the sorted list, suppression in parallel
-    for (int a = 0; a < n; ++a) {
-      const int ia = order[a];
-      if (!supp[ia]) {  // block-uniform: supp[ia] was last written before the previous barrier
-        if (t > a && t < n) {
-          const int jb = order[t];
-          if (!supp[jb]) {
-            const float dx = bx[ia][0] - bx[jb][0], dy = bx[ia][1] - bx[jb][1];
-            const float ra = 0.5f * sqrtf(bx[ia][2] * bx[ia][2] + bx[ia][3] * bx[ia][3]);
-            const float rj = 0.5f * sqrtf(bx[jb][2] * bx[jb][2] + bx[jb][3] * bx[jb][3]);
-            if (!(dx * dx + dy * dy > (ra + rj + 1.f) * (ra + rj + 1.f))) {
-              if (rotated_iou(rb[ia], rb[jb]) > p.nms_iou) supp[jb] = 1;
-            }
-          }
-        }
-      }
-      __syncthreads();
+    // ---- nms_rotated(boxes, scores, 0.99) (:181).  The suppression relation (IoU > thr between sorted positions
+    // a < b) is evaluated for all pairs in parallel into bit rows; one thread then replays the greedy scan on the bits.
+    // IoU <= min(area) / max(area), so pairs whose areas differ by more than the threshold allows are skipped unseen.
+    for (int k = t; k < PP_MAX * PP_WORDS; k += blockDim.x) (&vmask[0][0])[k] = 0u;
+    __syncthreads();
+    for (int idx = t; idx < n * n; idx += blockDim.x) {
+      const int a = idx / n, b = idx - a * n;
+      if (a >= b) continue;
+      const int ia = order[a], jb = order[b];
+      const float aa = bx[ia][2] * bx[ia][3], ab = bx[jb][2] * bx[jb][3];
+      if (fminf(aa, ab) < (p.nms_iou - 0.01f) * fmaxf(aa, ab)) continue;
+      const float dx = bx[ia][0] - bx[jb][0], dy = bx[ia][1] - bx[jb][1];
+      const float ra = 0.5f * sqrtf(bx[ia][2] * bx[ia][2] + bx[ia][3] * bx[ia][3]);
+      const float rj = 0.5f * sqrtf(bx[jb][2] * bx[jb][2] + bx[jb][3] * bx[jb][3]);
+      if (dx * dx + dy * dy > (ra + rj + 1.f) * (ra + rj + 1.f)) continue;
+      if (rotated_iou(rb[ia], rb[jb]) > p.nms_iou) atomicOr(&vmask[a][b >> 5], 1u << (b & 31));
     }
+    __syncthreads();
+    if (t == 0) {
+      unsigned int dead[PP_WORDS];
+#pragma unroll
+      for (int w = 0; w < PP_WORDS; ++w) dead[w] = 0u;
+      for (int a = 0; a < n; ++a) {
+        if (dead[a >> 5] & (1u << (a & 31))) continue;
+#pragma unroll
+        for (int w = 0; w < PP_WORDS; ++w) dead[w] |= vmask[a][w];
+      }
+      for (int a = 0; a < n; ++a) supp[order[a]] = (dead[a >> 5] >> (a & 31)) & 1u;
+    }
+    __syncthreads();
     // survivors, in descending-score order, become the next round's list
     if (t == 0) {
       int k = 0;
@@ -419,7 +432,7 @@ extern "C" int glass_postprocess_merge(const GlassPostprocessParams* p, void* st
   k.max_iters = p->max_iters;
   k.out_boxes = p->out_boxes; k.out_scores = p->out_scores; k.out_polygons = p->out_polygons;
   k.out_index = p->out_index; k.out_count = p->out_count; k.out_iters = p->out_iters;
-  postprocess_merge_kernel<<<p->n_img, PP_MAX, 0, stream>>>(k);
+  postprocess_merge_kernel<<<p->n_img, PP_THREADS, 0, stream>>>(k);
   count_launch();
   GLASS_CUDA(cudaGetLastError());
   return 0;

@@ -15,7 +15,7 @@ SYMBOLS = [
     "glass_roi_align_rotated", "glass_image_roi_align_rotated", "glass_rpn_topk_decode", "glass_rpn_topk_workspace_bytes",
     "glass_nms_workspace_bytes",
     "glass_nms_rotated", "glass_box_decode", "glass_gc_attention", "glass_hmean_rows", "glass_lstm_bidir",
-    "glass_aster_decode", "glass_aster_finalize", "glass_resize_bilinear_u8", "glass_postprocess_merge", "glass_text_scores",
+    "glass_aster_decode", "glass_aster_finalize", "glass_resize_bilinear_u8", "glass_postprocess_merge", "glass_text_scores", "glass_zero_border",
 ]
 
 
@@ -31,6 +31,7 @@ class ConvGemmParams(C.Structure):
         ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("out_f32", C.c_void_p),
         ("out_hp", C.c_int32), ("out_wp", C.c_int32), ("out_border", C.c_int32),
         ("ld_out", C.c_int32), ("ld_f32", C.c_int32), ("n_store", C.c_int32), ("kb_per_chunk", C.c_int32), ("pair_mode", C.c_int32), ("tap_mode", C.c_int32),
+        ("a_col0", C.c_int32), ("a_inner", C.c_int32),
     ]
 
 
@@ -153,6 +154,7 @@ def load() -> C.CDLL:
     lib.glass_resize_bilinear_u8.argtypes = [p, i, i, i, p, i, i, p]
     lib.glass_postprocess_merge.argtypes = [C.POINTER(PostprocessParams), p]
     lib.glass_text_scores.argtypes = [p, i, i, i, i, p, p, p, p]
+    lib.glass_zero_border.argtypes = [p, p, i, i, i, i, p]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if name.startswith("glass_") and name not in ("glass_last_error", "glass_abi_version", "glass_launch_count",

@@ -6,6 +6,7 @@ branch :176-181 = ``_forward_box`` :291-339 followed by ``forward_with_given_box
 (MASK_INFERENCE False, glass/config.py:170) and is out of scope.
 State-dict names follow SURVEY.md A.10 so reference checkpoints load unchanged.
 """
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -59,8 +60,19 @@ class B200GlassROIHeads:
         # ---- hybrid_net = ResNetFeatureExtractor (local_feature_extraction.py:95-188), layers [1,2,5,3]
         hp = "hybrid_net.ConvNet."
 
+        # pixels per GEMM row for the narrow layers (ops._conv2d_grouped); the padded crop width must divide:
+        # conv0_1 / conv0_2 see 130-wide planes (P = 5 / 2), layer1.0 66-wide ones (P = 2).  GLASS_GROUPED=0: compact mode
+        grouped = os.environ.get("GLASS_GROUPED", "1") != "0"
+        group_of = {8: 5, 16: 2, 32: 2}
+
         def cb(conv, bn, stride=(1, 1), pad=(1, 1), compact_cp=0):
             s, b = _bn_fold(sd, hp + bn)
+            if compact_cp and grouped:
+                pw = packing.pack_conv_grouped(sd[hp + conv + ".weight"], compact_cp, group_of[compact_cp], s, b,
+                                               device=dev)
+                # crop sizes whose padded width is not a multiple of the group fall back to the compact mode
+                pw.fallback = packing.pack_conv_compact(sd[hp + conv + ".weight"], compact_cp, s, b, device=dev)
+                return pw
             if compact_cp:  # narrow input activation (3/16/32 channels): compact-channel implicit GEMM
                 return packing.pack_conv_compact(sd[hp + conv + ".weight"], compact_cp, s, b, device=dev)
             return packing.pack_conv(sd[hp + conv + ".weight"], s, b, stride, pad, device=dev)

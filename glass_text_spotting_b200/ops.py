@@ -126,7 +126,7 @@ def conv_gemm(a_hi: torch.Tensor, a_lo: Optional[torch.Tensor], rows_a: int, k_p
               out_geom: Optional[Tuple[int, int, int]] = None, ld_out: int = 0,
               out_hi: Optional[torch.Tensor] = None, out_lo: Optional[torch.Tensor] = None,
               residual: Optional[Act] = None, res_shift: int = 0, relu_pre: bool = False, relu_post: bool = False,
-              mode: int = MODE_SPLIT, n_store: int = 0, a_ld: int = 0) -> None:
+              mode: int = MODE_SPLIT, n_store: int = 0, a_ld: int = 0, a_col0: int = 0, a_inner: int = 0) -> None:
     """Raw launch of glass_conv_gemm.  m_geom = (imgs, h, w, border) of the M space;
     out_geom = (hp, wp, border) of the output rows (defaults to ``out``'s geometry)."""
     p = _lib.ConvGemmParams()
@@ -154,6 +154,7 @@ def conv_gemm(a_hi: torch.Tensor, a_lo: Optional[torch.Tensor], rows_a: int, k_p
     p.kb_per_chunk = KB_PER_CHUNK
     p.pair_mode = PAIR_MODE if (PAIR_MODE != 2 or w.n_p % 32 == 0) else 0
     p.tap_mode = TAP_MODE
+    p.a_col0, p.a_inner = a_col0, a_inner
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(torch.cuda.current_stream())
@@ -161,7 +162,7 @@ def conv_gemm(a_hi: torch.Tensor, a_lo: Optional[torch.Tensor], rows_a: int, k_p
         e1.record(torch.cuda.current_stream())
         m_valid = p.m_imgs * (p.m_h - 2 * p.m_border) * (p.m_w - 2 * p.m_border)
         # algorithmic FLOPs of this launch + the GEMM's shape (tools/layer_profile.py)
-        PROFILE.append((e0, e1, 2.0 * m_valid * w.cout * w.cin * w.kh * w.kw,
+        PROFILE.append((e0, e1, 2.0 * m_valid * getattr(w, "grouped_p", 1) * w.cout * w.cin * w.kh * w.kw,
                         dict(m=p.m_imgs * p.m_h * p.m_w, n=w.n_p, k=k_per_tap * len(tap_shift), taps=len(tap_shift),
                              a_ld=a_ld, res=residual is not None, f32=out_f32 is not None)))
         return
@@ -176,6 +177,10 @@ def conv2d(x: Act, w: PackedWeight, relu: bool = False, residual: Optional[Act] 
     stride-1 'same' convs run as shifted-row implicit GEMM straight from ``x``; everything else goes
     through one tap-gather pass.  ``relu`` = ReLU after the residual add (d2 bottleneck order),
     ``relu_pre`` = ReLU before it (CNN_V1_1 order)."""
+    if getattr(w, "grouped_p", 0):
+        if x.wp % w.grouped_p == 0 and residual is None:
+            return _conv2d_grouped(x, w, relu, residual, relu_pre, out, mode)
+        w = w.fallback
     if getattr(w, "compact_cp", 0):
         return _conv2d_compact(x, w, relu, residual, res_shift, relu_pre, out, mode)
     assert x.cp == w.cin_p, (x.cp, w.cin_p)
@@ -218,6 +223,29 @@ def _conv2d_compact(x: Act, w: PackedWeight, relu, residual, res_shift, relu_pre
     assert (out.n, out.h, out.w, out.cp) == (x.n, x.h, x.w, w.n_p)
     conv_gemm(x.hi, x.lo, x.rows, 64, shifts, w, (x.n, x.hp, x.wp, x.border), out=out, residual=residual,
               res_shift=res_shift, relu_pre=relu_pre, relu_post=relu, mode=mode, a_ld=cp)
+    return out
+
+
+def _conv2d_grouped(x: Act, w: PackedWeight, relu, residual, relu_pre, out, mode) -> Act:
+    """Pixel-grouped implicit GEMM (include/glass_b200.h, a_inner > 0; packing.pack_conv_grouped): P pixels per GEMM
+    row, then the border of the output (which the all-valid M space overwrites) is re-zeroed."""
+    P, cp = w.grouped_p, w.grouped_cp
+    assert residual is None, "grouped convs have no residual input"
+    assert x.cp == cp and x.border == 1 and x.wp % P == 0 and x.rows % P == 0, (x.cp, cp, x.wp, P)
+    if out is None:
+        out = Act(x.n, w.cout, x.h, x.w, 1, w.grouped_cout_p, x.buf.device)
+    assert (out.n, out.h, out.w, out.cp, out.border) == (x.n, x.h, x.w, w.grouped_cout_p, 1)
+    rows = x.rows // P
+    kwin = w.cin_p  # K per tap row (window, padded to 64)
+    left = 1 if w.kw == 3 else 0
+    # window of group g, tap row r starts at pixel P*g - left + (r - pad)*wp = row (g - left + (r - pad)*wp/P), column
+    # left * (P - 1) * cp of the overlapping-row tensor
+    shifts = [(r - w.pad[0]) * (x.wp // P) - left for r in range(w.kh)]
+    col0 = left * (P - 1) * cp
+    conv_gemm(x.hi, x.lo, rows, kwin, shifts, w, (1, rows, 1, 0), out_hi=out.hi, out_lo=out.lo, out_geom=(rows, 1, 0),
+              ld_out=P * out.cp, relu_pre=relu_pre, relu_post=relu, mode=mode, a_ld=P * cp, a_col0=col0,
+              a_inner=col0 + kwin)
+    _lib.check(_lib.load().glass_zero_border(_ptr(out.hi), _ptr(out.lo), out.n, out.h, out.w, out.cp, _stream()))
     return out
 
 

@@ -82,6 +82,38 @@ def pack_conv_compact(weight: torch.Tensor, cp_in: int, scale: Optional[torch.Te
     return pw
 
 
+def pack_conv_grouped(weight: torch.Tensor, cp_in: int, group: int, scale: Optional[torch.Tensor] = None,
+                      bias: Optional[torch.Tensor] = None, device="cuda") -> PackedWeight:
+    """Pixel-grouped packing of a stride-1 'same' conv (1x1 or 3x3) on a narrow activation (cp_in channels per pixel):
+    one GEMM row = ``group`` consecutive pixels, K per tap row = the window of group + kw - 1 pixels (zero padded to a
+    multiple of 64), weights = the block-Toeplitz matrix [group * cout_p, kh * Kwin] whose row (p, co) holds
+    weight[co, :, r, s] at window pixel p + s.  Output row = group * cout_p contiguous elements = the NHWC rows of the
+    group's pixels, so cout_p (cout rounded up to 16) must be the output activation's channel stride."""
+    cout, cin, kh, kw = weight.shape
+    assert cin <= cp_in and cp_in % 8 == 0 and (kh, kw) in ((1, 1), (3, 3)) and group >= 1
+    cout_p = round_up(cout, 16)
+    win = group + kw - 1
+    kwin = round_up(win * cp_in, 64)
+    assert kwin % cp_in == 0
+    w = torch.zeros((group, cout_p, kh, kwin // cp_in, cp_in), dtype=torch.float32)
+    wt = weight.detach().float().permute(0, 2, 3, 1)  # [cout, kh, kw, cin]
+    for p in range(group):
+        for s_ in range(kw):
+            w[p, :cout, :, p + s_, :cin] = wt[:, :, s_, :]
+    n_p = group * cout_p
+    s = torch.ones(cout_p, dtype=torch.float32)
+    b = torch.zeros(cout_p, dtype=torch.float32)
+    if scale is not None:
+        s[:cout] = scale.detach().float()
+    if bias is not None:
+        b[:cout] = bias.detach().float()
+    wp, s_all = _pack_rows(w.reshape(n_p, kh * kwin), s.repeat(group))
+    pw = PackedWeight(wp.to(device), s_all.to(device), b.repeat(group).to(device), cout, cin, kh, kw, (1, 1),
+                      ((kh - 1) // 2, (kw - 1) // 2), kwin)
+    pw.grouped_p, pw.grouped_cp, pw.grouped_cout_p = group, cp_in, cout_p
+    return pw
+
+
 def pack_linear(weight: torch.Tensor, bias: Optional[torch.Tensor] = None, k_p: Optional[int] = None,
                 n_align: int = 64, device="cuda") -> PackedWeight:
     """nn.Linear weight [out, in] -> packed as a 1x1 'conv' over rows."""

@@ -93,6 +93,14 @@ typedef struct {
   int32_t pair_mode;    /* 0 = auto, 1 = one CTA per tile, 2 = CTA pairs (tcgen05 cta_group::2, shared weight tile) */
   int32_t tap_mode;     /* 0 = auto (3x3 taps ordered (r,s) with consecutive s-rows share one staged activation block),
                            1 = every tap loads its own 128-row tile */
+  /* Pixel-grouped mode (a_inner > 0) for narrow activations: ONE GEMM row = P consecutive pixels (row stride
+   * a_ld = P * channels), its K window = the (P + kw - 1) pixels the group's outputs read (a_inner >= a_col0 +
+   * k_per_tap elements of the overlapping-row tensor), the weights are the block-Toeplitz matrix [P * Cout,
+   * taps * k_per_tap], and the output row is P * Cout contiguous elements = the NHWC rows of the P pixels.
+   * P-fold fewer (128-byte) TMA rows per pixel than the compact mode.  The caller passes an all-valid M space
+   * (m_border 0) and re-zeroes the activation border afterwards (glass_zero_border). */
+  int32_t a_col0;       /* first column of every k-block box inside the tensor row (multiple of 8) */
+  int32_t a_inner;      /* inner extent of the tensor map in elements; 0 = k_per_tap (not grouped) */
 } GlassConvGemmParams;
 int glass_conv_gemm(const GlassConvGemmParams* p, void* stream);
 
@@ -125,6 +133,10 @@ int glass_gather_taps(const void* src_hi, const void* src_lo, int n, int h, int 
 int glass_maxpool(const void* src_hi, const void* src_lo, int n, int h, int w, int cp, int border, int kh, int kw,
                   int sh, int sw, int ph, int pw, int ho, int wo, void* dst_hi, void* dst_lo, int dst_border,
                   void* stream);
+
+/* Re-zero the 1-pixel border of a split-fp16 padded NHWC activation [n, h+2, w+2, cp] (after a pixel-grouped
+ * glass_conv_gemm, which writes every pixel of the padded plane). */
+int glass_zero_border(void* hi, void* lo, int n, int h, int w, int cp, void* stream);
 
 /* Pre-processing of GlassRunner._image_to_tensor (glass/inference/glass_runner.py:123-148): uint8 HWC image ->
  * fp32 CHW tensor, bilinear resize with align_corners=False semantics of torch.nn.functional.interpolate(size=...),

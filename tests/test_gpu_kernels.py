@@ -136,6 +136,31 @@ def test_conv_gemm_compact_channels(ops, case):
     assert out.buf[:, :, 0].abs().max().item() == 0 and out.buf[:, :, :, -1].abs().max().item() == 0
 
 
+@pytest.mark.parametrize("case", [("g3x3_c3_P5", 3, 8, 16, 3, 5, (18, 33)), ("g3x3_c16_P2", 16, 16, 32, 3, 2, (20, 38)),
+                                  ("g3x3_c32_P2", 32, 32, 64, 3, 2, (14, 22)), ("g1x1_c32_P2", 32, 32, 64, 1, 2, (14, 22)),
+                                  ("g3x3_c3_P1", 3, 8, 16, 3, 1, (9, 11))], ids=lambda c: c[0])
+def test_conv_gemm_pixel_grouped(ops, case):
+    """Pixel-grouped mode: P pixels per GEMM row, block-Toeplitz weights, border re-zeroed afterwards.  Widths are
+    chosen so that the padded width w + 2 is a multiple of P."""
+    from glass_text_spotting_b200 import packing
+    name, cin, cp_in, cout, k, P, (h, w_) = case
+    assert (w_ + 2) % P == 0
+    g = torch.Generator().manual_seed(sum(map(ord, name)))
+    x = torch.randn(3, cin, h, w_, generator=g)
+    wt = torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)
+    scale = 1.0 + 0.1 * torch.randn(cout, generator=g)
+    bias = 0.1 * torch.randn(cout, generator=g)
+    a = ops.Act.from_nchw(x.cuda(), cp=cp_in)
+    pw = packing.pack_conv_grouped(wt, cp_in, P, scale, bias)
+    out = ops.conv2d(a, pw, relu=True)
+    ref = F.relu(F.conv2d(x, wt, padding=k // 2) * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1))
+    assert out.cp == pw.grouped_cout_p
+    _close(out.to_nchw(), ref, name)
+    b = out.buf
+    assert b[:, :, 0].abs().max().item() == 0 and b[:, :, -1].abs().max().item() == 0
+    assert b[:, :, :, 0].abs().max().item() == 0 and b[:, :, :, -1].abs().max().item() == 0
+
+
 def test_conv_gemm_fast_mode_is_fp16_grade(ops):
     from glass_text_spotting_b200 import packing
     g = torch.Generator().manual_seed(5)
