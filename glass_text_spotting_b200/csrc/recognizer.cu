@@ -15,6 +15,8 @@
 // bytes per k, activations are broadcast from shared memory.
 #include <math_constants.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "glass_b200.h"
 #include "host_util.h"
@@ -224,45 +226,89 @@ __global__ void hmean_rows_kernel(const __half* __restrict__ shi, const __half* 
 // gates_in fp32 [n_seq*T, 2*4H]: x W_ih^T + b_ih + b_hh, forward gates in [0,4H), backward in [4H,8H);
 // PyTorch gate order (i, f, g, o).  whh_t fp32 [2][H][4H] (k-major).  Output split-fp16 rows
 // [n_seq*T, 2H] (forward | backward) + optional fp32 copy.
-constexpr int LSTM_H = 256, LSTM_G = 1024, LSTM_WPC = 8;  // 8 words per CTA: W_hh^T streams once per 8 words
+constexpr int LSTM_H = 256, LSTM_G = 1024;
+constexpr int LSTM_THREADS = LSTM_G / 2;                  // every thread owns two adjacent gate rows
 
-__global__ void __launch_bounds__(1024) lstm_bidir_kernel(const float* __restrict__ gates_in,
-                                                          const float* __restrict__ whh_t, int n_seq, int T,
-                                                          __half* __restrict__ out_hi, __half* __restrict__ out_lo,
-                                                          float* __restrict__ out_f32) {
-  __shared__ __align__(16) float h_s[LSTM_H][LSTM_WPC];   // h[k][w]
-  __shared__ float c_s[LSTM_WPC][LSTM_H];
-  __shared__ float g_s[LSTM_WPC][LSTM_G];
+// d = a * (b.x, b.y) + c on a register pair: Blackwell's packed FFMA2 with a scalar-broadcast first operand --
+// the same fused multiply-add per lane as FFMA, at half the issue slots
+__device__ __forceinline__ float2 ffma2_bcast(float a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n"
+      ".reg .b64 ra, rb, rc, rd;\n"
+      "mov.b64 ra, {%2, %2};\n"
+      "mov.b64 rb, {%3, %4};\n"
+      "mov.b64 rc, {%5, %6};\n"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n"
+      "mov.b64 {%0, %1}, rd;\n"
+      "}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+
+// The recurrent product is issue-bound on the FMA stream (ncu: one LDG + two broadcast LDS.128 + 8 FFMA per k and
+// gate row): two gate rows per thread share the h loads, and word pairs go through FFMA2, i.e. 11 instructions per
+// 16 multiply-adds instead of 22.  Each accumulator still sums its 256 products in k order with fused multiply-adds.
+template <int WPC>  // words per CTA: W_hh^T (1 MB) streams from L2 once per WPC words and step
+__global__ void __launch_bounds__(LSTM_THREADS) lstm_bidir_kernel(const float* __restrict__ gates_in,
+                                                                 const float* __restrict__ whh_t, int n_seq, int T,
+                                                                 __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+                                                                 float* __restrict__ out_f32) {
+  extern __shared__ __align__(16) float lstm_smem[];
+  float (*h_s)[WPC] = reinterpret_cast<float (*)[WPC]>(lstm_smem);                               // h[k][w]
+  float (*c_s)[LSTM_H] = reinterpret_cast<float (*)[LSTM_H]>(lstm_smem + LSTM_H * WPC);           // c[w][u]
+  float (*g_s)[LSTM_G] = reinterpret_cast<float (*)[LSTM_G]>(lstm_smem + 2 * LSTM_H * WPC);       // gates[w][row]
   const int dir = blockIdx.y;
-  const int seq0 = blockIdx.x * LSTM_WPC;
-  const int j = threadIdx.x;  // gate row
+  const int seq0 = blockIdx.x * WPC;
+  const int j = 2 * threadIdx.x;  // first of this thread's two gate rows
   const float* wt = whh_t + (int64_t)dir * LSTM_H * LSTM_G;
-  for (int i = threadIdx.x; i < LSTM_H * LSTM_WPC; i += blockDim.x) {
+  for (int i = threadIdx.x; i < LSTM_H * WPC; i += blockDim.x) {
     (&h_s[0][0])[i] = 0.f;
     (&c_s[0][0])[i] = 0.f;
   }
   __syncthreads();
   for (int step = 0; step < T; ++step) {
     const int t = dir == 0 ? step : T - 1 - step;
-    float acc[LSTM_WPC];
+    float2 acc0[WPC / 2], acc1[WPC / 2];  // rows j / j + 1, word pairs (2q, 2q + 1)
 #pragma unroll
-    for (int w = 0; w < LSTM_WPC; ++w) {
-      const int s = seq0 + w;
-      acc[w] = s < n_seq ? __ldg(gates_in + ((int64_t)s * T + t) * (2 * LSTM_G) + dir * LSTM_G + j) : 0.f;
+    for (int q = 0; q < WPC / 2; ++q) {
+      float2 g[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int s = seq0 + 2 * q + e;
+        g[e] = s < n_seq ? __ldg(reinterpret_cast<const float2*>(gates_in + ((int64_t)s * T + t) * (2 * LSTM_G) +
+                                                                 dir * LSTM_G + j))
+                         : make_float2(0.f, 0.f);
+      }
+      acc0[q] = make_float2(g[0].x, g[1].x);
+      acc1[q] = make_float2(g[0].y, g[1].y);
     }
+    // (an explicit load-16/32-rows-then-compute structure was measured 10-25 % slower than letting the compiler
+    // software-pipeline this loop)
 #pragma unroll 8
     for (int k = 0; k < LSTM_H; ++k) {
-      const float wv = __ldg(wt + (int64_t)k * LSTM_G + j);
-      const float4 h0 = *reinterpret_cast<const float4*>(&h_s[k][0]);
-      const float4 h1 = *reinterpret_cast<const float4*>(&h_s[k][4]);
-      acc[0] += wv * h0.x; acc[1] += wv * h0.y; acc[2] += wv * h0.z; acc[3] += wv * h0.w;
-      acc[4] += wv * h1.x; acc[5] += wv * h1.y; acc[6] += wv * h1.z; acc[7] += wv * h1.w;
-    }
-    const int gate = j >> 8;  // 0:i 1:f 2:g 3:o
+      const float2 wv = __ldg(reinterpret_cast<const float2*>(wt + (int64_t)k * LSTM_G + j));
 #pragma unroll
-    for (int w = 0; w < LSTM_WPC; ++w) g_s[w][j] = gate == 2 ? tanhf(acc[w]) : sigmoidf_(acc[w]);
+      for (int v = 0; v < WPC / 4; ++v) {
+        const float4 h = *reinterpret_cast<const float4*>(&h_s[k][4 * v]);
+        acc0[2 * v] = ffma2_bcast(wv.x, make_float2(h.x, h.y), acc0[2 * v]);
+        acc0[2 * v + 1] = ffma2_bcast(wv.x, make_float2(h.z, h.w), acc0[2 * v + 1]);
+        acc1[2 * v] = ffma2_bcast(wv.y, make_float2(h.x, h.y), acc1[2 * v]);
+        acc1[2 * v + 1] = ffma2_bcast(wv.y, make_float2(h.z, h.w), acc1[2 * v + 1]);
+      }
+    }
+    const int gate = j >> 8;  // 0:i 1:f 2:g 3:o (rows j and j + 1 belong to the same gate)
+#pragma unroll
+    for (int q = 0; q < WPC / 2; ++q) {
+      const float a[2][2] = {{acc0[q].x, acc1[q].x}, {acc0[q].y, acc1[q].y}};  // [word parity][row]
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        g_s[2 * q + e][j] = gate == 2 ? tanhf(a[e][0]) : sigmoidf_(a[e][0]);
+        g_s[2 * q + e][j + 1] = gate == 2 ? tanhf(a[e][1]) : sigmoidf_(a[e][1]);
+      }
+    }
     __syncthreads();
-    for (int wu = j; wu < LSTM_WPC * LSTM_H; wu += blockDim.x) {
+    for (int wu = threadIdx.x; wu < WPC * LSTM_H; wu += blockDim.x) {
       const int w = wu >> 8, u = wu & 255;  // (word, hidden unit)
       const float ig = g_s[w][u], fg = g_s[w][256 + u], gg = g_s[w][512 + u], og = g_s[w][768 + u];
       const float c = fg * c_s[w][u] + ig * gg;
@@ -529,8 +575,19 @@ extern "C" int glass_lstm_bidir(const float* gates_in, const float* whh_t, int n
   GLASS_CHECK(hidden == LSTM_H, "hidden size must be 256");
   GLASS_CHECK(n_seq >= 0 && T > 0, "bad shape");
   if (n_seq == 0) return 0;
-  dim3 grid((n_seq + LSTM_WPC - 1) / LSTM_WPC, 2);
-  lstm_bidir_kernel<<<grid, 1024, 0, STREAM>>>(gates_in, whh_t, n_seq, T, (__half*)out_hi, (__half*)out_lo, out_f32);
+  // 16 words per CTA once that still fills >= 40 SMs (the L2 stream of W_hh^T is the bound), else 8
+  static const int wpc_env = getenv("GLASS_LSTM_WPC") ? atoi(getenv("GLASS_LSTM_WPC")) : 0;  // A/B knob
+  const int wpc = wpc_env ? wpc_env : 8;  // 16 was measured 2x slower: the CTA is latency-bound, not L2-bound
+  auto launch = [&](auto kern, int w) -> cudaError_t {
+    const int smem = (2 * LSTM_H * w + w * LSTM_G) * (int)sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid((n_seq + w - 1) / w, 2);
+    kern<<<grid, LSTM_THREADS, smem, STREAM>>>(gates_in, whh_t, n_seq, T, (__half*)out_hi, (__half*)out_lo, out_f32);
+    return cudaSuccess;
+  };
+  if (wpc == 16) GLASS_CUDA(launch(lstm_bidir_kernel<16>, 16));
+  else GLASS_CUDA(launch(lstm_bidir_kernel<8>, 8));
   count_launch();
   GLASS_CUDA(cudaGetLastError());
   return 0;

@@ -47,6 +47,7 @@ class B200RotatedRPN:
         b = torch.cat((sd["objectness_logits.bias"], sd["anchor_deltas.bias"]), 0)
         self.pred = packing.pack_conv(w, None, b, (1, 1), (0, 0), n_align=16, device=device)
         self.ws = Workspace(device)
+        self._streams = None
 
     def head(self, features: Dict[str, Act]) -> List[torch.Tensor]:
         """-> per level fp32 [n, h, w, ld] with columns [0,A) objectness, [A,6A) deltas (tap T3)."""
@@ -67,11 +68,26 @@ class B200RotatedRPN:
         L, K = len(preds), self.pre_nms_topk
         boxes = self.ws.raw("rpn.topk_boxes", (n, L * K, 5), torch.float32)
         scores = self.ws.raw("rpn.topk_scores", (n, L * K), torch.float32)
+        # The select kernel runs ONE CTA per image, so a level occupies n of the 148 SMs: the five levels are
+        # independent (disjoint output slices, own workspaces) and are forked onto side streams so they run side by
+        # side, joined before the NMS.  All buffers are persistent workspace, so no allocator/stream hazards arise.
+        cur = torch.cuda.current_stream()
+        if self._streams is None:
+            self._streams = [torch.cuda.Stream() for _ in range(L - 1)]
         for lvl, pred in enumerate(preds):
             need = ops._lib.load().glass_rpn_topk_workspace_bytes(n, pred.shape[1], pred.shape[2], self.A)
             wsb = self.ws.raw(f"rpn.topk_ws{lvl}", (need,), torch.uint8)
-            ops.rpn_topk_decode(pred, self.A, self.strides[lvl], self.cell_anchors[lvl], self.weights, K, lvl, L,
-                                boxes, scores, workspace=wsb)
+            if lvl == 0:
+                ops.rpn_topk_decode(pred, self.A, self.strides[lvl], self.cell_anchors[lvl], self.weights, K, lvl, L,
+                                    boxes, scores, workspace=wsb)
+            else:
+                side = self._streams[lvl - 1]
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    ops.rpn_topk_decode(pred, self.A, self.strides[lvl], self.cell_anchors[lvl], self.weights, K, lvl, L,
+                                        boxes, scores, workspace=wsb)
+        for side in self._streams[: L - 1]:
+            cur.wait_stream(side)
         return boxes, scores
 
     def select(self, boxes: torch.Tensor, scores: torch.Tensor, img_hw: torch.Tensor):
