@@ -34,6 +34,11 @@ WORKLOADS["roialign_512"] = dict(batch=1, h=1024, w=1024, full=False, roialign=T
 WORKLOADS["postprocess_bs4"] = dict(batch=4, h=1024, w=1024, full=False, postprocess=True,
                                    desc="word post-processor (merge loop + text-score filter, SURVEY.md 8f #1) on the "
                                         "detections of 4 images x 100 words (synthetic broken text lines)")
+WORKLOADS["totaltext_loop"] = dict(batch=4, h=1024, w=1024, full=True, totaltext=True,
+                                   desc="TotalText-shape eval loop (BASELINE.json configs[4]): uint8 1024x1024 images -> "
+                                        "device resize to 1200x1200 (glass_finetune_totaltext.yaml MIN_SIZE_TEST) -> pad "
+                                        "1216 -> full GLASS inference -> word post-processor -> 24 KB/image records -> "
+                                        "one NCCL all-gather, bs=4/GPU")
 CPU_WORD_CAP = 16  # the CPU arm decodes at most this many words per image (bounded sample)
 
 
@@ -316,6 +321,151 @@ def run_postprocess(args):
     print(json.dumps(out))
 
 
+def run_totaltext(args):
+    """BASELINE.json configs[4]: the evaluation loop of tools/eval_glass.py / GlassRunner on synthetic images, image-sharded
+    over the ranks, ending in ONE all-gather of fixed-size per-image records.  Reports end-to-end
+    images/s and the all-gather time separately (CUDA events around it)."""
+    import torch
+    import torch.distributed as dist
+    from glass_text_spotting_b200 import lib, ops, weights
+    from glass_text_spotting_b200.modeling.backbone import PIXEL_MEAN
+    from glass_text_spotting_b200.modeling.glass_rcnn import B200GlassRCNN
+    from glass_text_spotting_b200.postprocess import B200PostProcessor
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    wl = WORKLOADS["totaltext_loop"]
+    B, H, W = wl["batch"], wl["h"], wl["w"]
+    scale = min(2.0, 1200 / max(H, W))                      # GlassRunner.get_inference_scale_ratio
+    nh, nw = int(round(scale * H)), int(round(scale * W))   # 1200 x 1200
+    ph, pw = (nh + 31) // 32 * 32, (nw + 31) // 32 * 32     # 1216 x 1216 (size_divisibility 32)
+    L = lib.load()
+    stream = torch.cuda.current_stream()
+    model = B200GlassRCNN(weights.random_state_dict(0))
+    post = B200PostProcessor()
+    m = model.roi_heads.max_det
+    g = torch.Generator().manual_seed(2000 + rank)
+    host = [torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    dev = [h.cuda() for h in host]
+    dbuf = [torch.empty_like(d) for d in dev]
+    padded = torch.empty((B, 3, ph, pw), dtype=torch.float32, device="cuda")
+    padded[:] = torch.tensor(PIXEL_MEAN, device="cuda").view(1, 3, 1, 1)   # mean padding normalises to exactly 0
+    img_hw = torch.tensor([[nh, nw]] * B, dtype=torch.float32, device="cuda")
+    ts_pad = torch.zeros((B, m), dtype=torch.float32, device="cuda")
+    steps_t = model.roi_heads.steps
+    rec = torch.zeros((B, m, 8 + 2 * steps_t), dtype=torch.float32, device="cuda")
+    gathered = torch.empty((world * B,) + tuple(rec.shape[1:]), dtype=rec.dtype, device="cuda") if world > 1 else None
+    ag_events, survivors, words = [], [], []
+
+    def step(images_u8):
+        for i in range(B):
+            padded[i, :, :nh, :nw] = ops.resize_bilinear_u8(images_u8[i], (nh, nw), flip_channels=False)
+        det, probs, counts, starts = model.forward_device(padded, img_hw)
+        ts, tidx, tmax = ops.text_scores(probs, 1, want_steps=True)
+        ts_pad.zero_()
+        for i, c in enumerate(counts):
+            ts_pad[i, :c] = ts[starts[i]: starts[i + 1]]
+        boxes = det["pred_boxes"].clone()
+        boxes[:, :, :4] *= 1.0 / scale                       # back to the original image (glass_runner.py:100-101)
+        r = post.batch(boxes.contiguous(), det["scores"].contiguous(), det["count"], ts_pad)
+        # per-image record: (box 5, score, original index, valid) + per-step argmax and its probability
+        rec.zero_()
+        rec[:, :, 0:5], rec[:, :, 5], rec[:, :, 6] = r["boxes"], r["scores"], r["index"].float()
+        rec[:, :, 7] = (r["index"] >= 0).float()
+        for i, c in enumerate(counts):
+            if c:
+                sel = r["index"][i].clamp(min=0).long() + starts[i]
+                rec[i, :, 8:8 + steps_t] = tidx[sel].float()
+                rec[i, :, 8 + steps_t:] = tmax[sel]
+        survivors.append(r["count"])
+        words.append(sum(counts))
+        if world > 1:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            dist.all_gather_into_tensor(gathered, rec)
+            e1.record(stream)
+            ag_events.append((e0, e1))
+            return gathered
+        return rec
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0 and not args.no_clocks:
+        sampler.start()
+    warm = max(args.warmup, 3)
+    for i in range(warm):
+        step(dev[i % 2])
+    barrier()
+    ag_events.clear(); survivors.clear(); words.clear()
+    launches0 = L.glass_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for i in range(args.steps):
+        step(dev[i % 2])
+    e1.record(stream)
+    barrier()
+    t_dev = e0.elapsed_time(e1) / 1e3
+    launches = L.glass_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ag_ms = sum(a.elapsed_time(b) for a, b in ag_events) / max(len(ag_events), 1) if ag_events else 0.0
+    kept = torch.stack(survivors).float().mean().item() if survivors else 0.0
+    words_per_step = sum(words) / max(len(words), 1)
+    # e2e: pinned host uint8 batch -> H2D -> loop body -> D2H of the (gathered) records
+    res_host = None
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    f0.record(stream)
+    for i in range(args.steps):
+        dbuf[i % 2].copy_(host[i % 2], non_blocking=True)
+        res = step(dbuf[i % 2])
+        if res_host is None:
+            res_host = torch.empty(res.shape, dtype=res.dtype).pin_memory()
+        res_host.copy_(res, non_blocking=True)
+    f1.record(stream)
+    barrier()
+    t_e2e = f0.elapsed_time(f1) / 1e3
+    times = torch.tensor([t_dev, t_e2e, ag_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    t_dev, t_e2e, ag_ms = times.tolist()
+    if rank == 0:
+        print(json.dumps({
+            "metric": "images/sec @1024x1024 (TotalText-shape eval loop)", "value": world * B * args.steps / t_dev,
+            "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp16x3 split (22-bit operands, 3 tcgen05 MMAs per product, chunked fp32 RN accumulation)",
+            "data": "synthetic",
+            "config": {"workload": wl["desc"], "global_batch": world * B, "parallelism": f"image-sharded x{world}",
+                       "model_input": [ph, pw], "scale_ratio": scale,
+                       "l2": "inputs rotated between 2 batches; per-step working set >> 126 MB L2",
+                       "weights": "random init (seeded), BatchNorm folded",
+                       "words_recognized_per_step": words_per_step,
+                       "words_after_postprocess_per_image": kept,
+                       "note": "random weights give word scores far below TEXT_THRESHOLD 0.25, so the (faithful) "
+                               "post-processor drops nearly everything; its merge loop is exercised by the "
+                               "postprocess_bs4 workload",
+                       "allgather_ms_per_step": ag_ms, "allgather_bytes_per_rank": rec.numel() * 4,
+                       "collective": "one NCCL all-gather of 24 KB/image records per step" if world > 1 else "none (N=1)"},
+            "e2e": {"value": world * B * args.steps / t_e2e, "unit": "images/s", "h2d_bytes_per_step": B * H * W * 3,
+                    "d2h_bytes_per_step": res_host.numel() * 4,
+                    "note": "pinned host uint8 HWC batch -> H2D -> resize/pad -> hot path -> post-processor -> "
+                            "(all-gather) -> D2H of the records"},
+            "gpu_launches": launches, "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": None, "peak": None, "unit": "TFLOP/s", "frac": None,
+                         "traffic": None, "kernel": "conv_gemm_kernel (see the full_bs4 workload for its roofline line)"}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_roialign(args):
     """BASELINE.json configs[2].  Timed region = K back-to-back launches (CUDA events on the launching stream), each
     on the NEXT of 4 copies of the feature pyramid (4 x 91 MB of split-fp16 maps + 4 x 26 MB of outputs >> 126 MB L2), so
@@ -580,6 +730,8 @@ def main():
         run_roialign(args)
     elif WORKLOADS[args.workload].get("postprocess"):
         run_postprocess(args)
+    elif WORKLOADS[args.workload].get("totaltext"):
+        run_totaltext(args)
     else:
         run_b200(args)
 
