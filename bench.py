@@ -49,6 +49,15 @@ def _peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def _traffic(workload):
+    """DRAM bytes of the dominant kernel from the committed ncu capture (profiles/r01_traffic.json), or None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(workload)
+        return t and (t.get("dram_bytes_per_step") or t.get("dram_bytes_per_launch"))
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
 
@@ -547,7 +556,8 @@ def run_roialign(args):
                    "single_launch_l2_flushed_gbs": nbytes / (ms_flushed / 1e3) / 1e9},
         "gpu_launches": launches, "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-                     "traffic": None, "kernel": "roi_align_rotated_split8_kernel<2>", "algorithmic_bytes": nbytes,
+                     "traffic": _traffic("roialign_512"), "kernel": "roi_align_rotated_split8_kernel<2>",
+                     "algorithmic_bytes": nbytes,
                      "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({src})"}}))
 
 
@@ -697,7 +707,9 @@ def run_b200(args):
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak, "traffic": _traffic(args.workload),
+                         "traffic_note": "dram__bytes_read+write summed over the step's conv_gemm launches (ncu, "
+                                         "profiles/r01_traffic.json); null when no capture exists for this workload",
                          "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM), all launches of one step",
                          "launches_per_step": n_gemm, "kernel_ms_per_step": gemm_ms,
                          "kernel_share_of_step": gemm_ms / (1e3 * t_dev / args.steps),
