@@ -157,6 +157,49 @@ __global__ void gather_taps_kernel(const uint4* __restrict__ shi, const uint4* _
   }
 }
 
+// ------------------------------------------------------------------ stem: normalise + space-to-depth
+// raw fp32 NCHW [n,3,h,w] -> split-fp16 NHWC [n, h/2+4, w/2+4, 16] with a 2-pixel zero border: pixel (Y, X) holds
+// channel (dy*2+dx)*3 + c = (img[c, 2Y+dy, 2X+dx] - mean[c]) * inv_std[c]; channels 12..15 are zero.  The 7x7/s2/p3
+// stem conv then is a 4x4 stride-1 conv over this map (taps Y-2..Y+1, X-2..X+1), i.e. 4 k-blocks of 4 pixels x 16
+// channels in the GEMM's compact-channel mode -- no 192-wide im2col matrix is materialised (805 MB at bs = 4).
+__global__ void stem_s2d_kernel(const float* __restrict__ img, int n, int h, int w, float m0, float m1, float m2,
+                                float is0, float is1, float is2, uint4* __restrict__ dhi, uint4* __restrict__ dlo) {
+  const int ho = h / 2, wo = w / 2, hp = ho + 4, wp = wo + 4;
+  const int64_t total = (int64_t)n * ho * wo;
+  const float mean[3] = {m0, m1, m2}, istd[3] = {is0, is1, is2};
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % wo);
+    const int y = (int)((i / wo) % ho);
+    const int b = (int)(i / ((int64_t)wo * ho));
+    float v[16];
+#pragma unroll
+    for (int j = 12; j < 16; ++j) v[j] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy) {
+        const float2 r = __ldg(reinterpret_cast<const float2*>(img + (((int64_t)b * 3 + c) * h + 2 * y + dy) * w + 2 * x));
+        v[(dy * 2 + 0) * 3 + c] = (r.x - mean[c]) * istd[c];
+        v[(dy * 2 + 1) * 3 + c] = (r.y - mean[c]) * istd[c];
+      }
+    }
+    uint32_t hw[8], lw[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      __half h0, l0, h1, l1;
+      split16(v[2 * j], h0, l0);
+      split16(v[2 * j + 1], h1, l1);
+      hw[j] = pack16x2(h0, h1);
+      lw[j] = pack16x2(l0, l1);
+    }
+    const int64_t o = ((((int64_t)b * hp + y + 2) * wp) + x + 2) * 2;  // 2 x uint4 per 16-channel pixel
+    dhi[o] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    dhi[o + 1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+    dlo[o] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    dlo[o + 1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+  }
+}
+
 // ------------------------------------------------------------------ border re-zero (border = 1)
 __global__ void zero_border_kernel(uint4* __restrict__ hi, uint4* __restrict__ lo, int n, int hp, int wp, int cv) {
   const int per_img = 2 * wp + 2 * (hp - 2);
@@ -320,6 +363,19 @@ extern "C" int glass_stem_im2col(const float* img, int n, int h, int w, const fl
   stem_im2col_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>(img, n, h, w, mean[0], mean[1], mean[2], inv_std[0],
                                                                inv_std[1], inv_std[2], (__half*)dst_hi,
                                                                (__half*)dst_lo, kp);
+  count_launch();
+  GLASS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int glass_stem_s2d(const float* img, int n, int h, int w, const float* mean, const float* inv_std,
+                              void* dst_hi, void* dst_lo, void* stream) {
+  GLASS_CHECK(img && mean && inv_std && dst_hi && dst_lo, "null pointer");
+  GLASS_CHECK(n > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0, "image size must be even");
+  GLASS_CHECK((reinterpret_cast<uintptr_t>(img) & 7) == 0, "image must be 8-byte aligned");
+  const int64_t total = (int64_t)n * (h / 2) * (w / 2);
+  stem_s2d_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>(img, n, h, w, mean[0], mean[1], mean[2], inv_std[0],
+                                                            inv_std[1], inv_std[2], (uint4*)dst_hi, (uint4*)dst_lo);
   count_launch();
   GLASS_CUDA(cudaGetLastError());
   return 0;

@@ -300,6 +300,18 @@ def stem_im2col(img: torch.Tensor, mean: Sequence[float], std: Sequence[float], 
     return out
 
 
+def stem_s2d(img: torch.Tensor, mean: Sequence[float], std: Sequence[float], out: torch.Tensor) -> torch.Tensor:
+    """raw fp32 NCHW [n,3,h,w] -> normalised space-to-depth map, split planes [2, n, h/2+4, w/2+4, 16] (2-pixel zero
+    border, which must already be zero in ``out``)."""
+    n, c, h, w = img.shape
+    assert c == 3 and img.dtype == torch.float32 and img.is_contiguous()
+    assert tuple(out.shape) == (2, n, h // 2 + 4, w // 2 + 4, 16) and out.dtype == torch.float16 and out.is_contiguous()
+    m = (C.c_float * 3)(*[float(v) for v in mean])
+    s = (C.c_float * 3)(*[1.0 / float(v) for v in std])
+    _lib.check(_lib.load().glass_stem_s2d(_ptr(img), n, h, w, m, s, _ptr(out[0]), _ptr(out[1]), _stream()))
+    return out
+
+
 def roi_align_rotated(feats: List, rois: torch.Tensor, output_size: Tuple[int, int],
                       scales: Sequence[float], sampling_ratio: int, min_level: int = 2,
                       out_f32: bool = True, out_split: Optional[Tuple[torch.Tensor, int, int, int, int, int]] = None,

@@ -129,6 +129,32 @@ def pack_linear(weight: torch.Tensor, bias: Optional[torch.Tensor] = None, k_p: 
     return PackedWeight(wp.to(device), s.to(device), b.to(device), out_f, in_f, 1, 1, (1, 1), (0, 0), k_p)
 
 
+def pack_stem_s2d(weight: torch.Tensor, scale, bias, device="cuda") -> PackedWeight:
+    """BasicStem conv1 [64,3,7,7] (stride 2, pad 3) as a 4x4 stride-1 conv over the space-to-depth map of
+    ops.stem_s2d: K = (i*4 + q)*16 + (dy*2+dx)*3 + c with w[co, c, 2i+dy-1, 2q+dx-1] (zero outside the 7x7 support);
+    i, q index the s2d rows / columns Y-2..Y+1, X-2..X+1."""
+    cout = weight.shape[0]
+    wt = weight.detach().float()
+    w = torch.zeros((round_up(cout, 64), 4, 4, 16), dtype=torch.float32)
+    for i in range(4):
+        for dy in range(2):
+            r = 2 * i + dy - 1
+            if not 0 <= r < 7:
+                continue
+            for q in range(4):
+                for dx in range(2):
+                    s_ = 2 * q + dx - 1
+                    if 0 <= s_ < 7:
+                        base = (dy * 2 + dx) * 3
+                        w[:cout, i, q, base:base + 3] = wt[:, :, r, s_]
+    s = torch.ones(w.shape[0])
+    b = torch.zeros(w.shape[0])
+    s[:cout] = scale.detach().float()
+    b[:cout] = bias.detach().float()
+    wp, s = _pack_rows(w.reshape(w.shape[0], 256), s)
+    return PackedWeight(wp.to(device), s.to(device), b.to(device), cout, 3, 7, 7, (2, 2), (3, 3), 64)
+
+
 def pack_stem(weight: torch.Tensor, scale, bias, kp: int = 192, device="cuda") -> PackedWeight:
     """BasicStem conv1 [64,3,7,7] -> K = (r*7+s)*3 + c (matches glass_stem_im2col), zero padded to kp."""
     cout = weight.shape[0]

@@ -123,6 +123,14 @@ int glass_nhwc_f32_to_nchw(const float* src, int n, int c, int h, int w, int ld,
 int glass_stem_im2col(const float* img, int n, int h, int w, const float* mean, const float* inv_std,
                       void* dst_hi, void* dst_lo, int kp, void* stream);
 
+/* Stem pre-pass without an im2col matrix: raw fp32 NCHW [n,3,h,w] -> normalised space-to-depth map, split-fp16 NHWC
+ * [n, h/2+4, w/2+4, 16] with a 2-pixel zero border (pixel (Y,X), channel (dy*2+dx)*3+c = (img[c,2Y+dy,2X+dx]-mean)*inv_std;
+ * channels 12..15 zero).  BasicStem's 7x7/s2/p3 conv (d2 resnet.py via configs/glass_pretrain.yaml:41-50) then runs as a
+ * 4x4 stride-1 conv in glass_conv_gemm's compact-channel mode (a_ld = 16, 4 taps of one 64-wide k-block,
+ * packing.pack_stem_s2d).  The destination's border must be zero (allocate it zeroed once; only the interior is written). */
+int glass_stem_s2d(const float* img, int n, int h, int w, const float* mean, const float* inv_std, void* dst_hi,
+                   void* dst_lo, void* stream);
+
 /* Generic tap gather (im2col) for strided / odd-shaped convs:
  * src split padded NHWC [n,h+2b,w+2b,cp] -> rows [n*ho*wo, kh*kw*cp], tap-major K. */
 int glass_gather_taps(const void* src_hi, const void* src_lo, int n, int h, int w, int cp, int border, int kh,

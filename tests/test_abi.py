@@ -61,7 +61,8 @@ def _struct_fields(name):
                                            ("GlassRpnTopkParams", "RpnTopkParams"),
                                            ("GlassNmsParams", "NmsParams"),
                                            ("GlassGcAttentionParams", "GcAttentionParams"),
-                                           ("GlassAsterParams", "AsterParams")])
+                                           ("GlassAsterParams", "AsterParams"),
+                                           ("GlassPostprocessParams", "PostprocessParams")])
 def test_ctypes_structs_match_header(cname, pyname):
     from glass_text_spotting_b200 import lib
     assert [f[0] for f in getattr(lib, pyname)._fields_] == _struct_fields(cname)

@@ -65,6 +65,33 @@ def test_stem_im2col(ops):
     _close(out.to_nchw(), ref, "stem")
 
 
+@pytest.mark.parametrize("shape", [(2, 64, 96), (1, 32, 160), (3, 96, 64)])
+def test_stem_space_to_depth(ops, shape):
+    """The 7x7/s2/p3 stem as a 4x4/s1 conv over the normalised space-to-depth map (no im2col matrix), with a
+    non-trivial std and folded scale / bias; borders of the map (2 pixels) stay zero."""
+    from glass_text_spotting_b200 import packing
+    n, h, w_ = shape
+    g = torch.Generator().manual_seed(n * 1000 + h)
+    img = torch.randint(0, 256, (n, 3, h, w_), generator=g).float()
+    mean, std = (103.53, 116.28, 123.675), (57.375, 57.12, 58.395)
+    wt = torch.randn(64, 3, 7, 7, generator=g) * 0.05
+    scale = 1.0 + 0.1 * torch.randn(64, generator=g)
+    bias = 0.1 * torch.randn(64, generator=g)
+    hp2, wp2 = h // 2 + 4, w_ // 2 + 4
+    s2d = torch.zeros((2, n, hp2, wp2, 16), dtype=torch.float16, device="cuda")
+    ops.stem_s2d(img.cuda(), mean, std, out=s2d)
+    assert s2d[:, :, :2].abs().max().item() == 0 and s2d[:, :, :, -2:].abs().max().item() == 0
+    assert s2d[..., 12:].abs().max().item() == 0
+    pw = packing.pack_stem_s2d(wt, scale, bias)
+    out = ops.Act(n, 64, h // 2, w_ // 2)
+    ops.conv_gemm(s2d[0], s2d[1], n * hp2 * wp2, 64, [(i - 2) * wp2 - 2 for i in range(4)], pw, (n, hp2, wp2, 2),
+                  out=out, relu_post=True, a_ld=16)
+    x = (img - torch.tensor(mean).view(1, 3, 1, 1)) / torch.tensor(std).view(1, 3, 1, 1)
+    ref = F.relu(F.conv2d(x, wt, stride=2, padding=3) * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1))
+    _close(out.to_nchw(), ref, "stem_s2d")
+    assert out.buf[:, :, 0].abs().max().item() == 0 and out.buf[:, :, :, -1].abs().max().item() == 0
+
+
 CONV_CASES = [
     # name, n, cin, cout, h, w, k, stride, pad, relu, residual
     ("1x1_64_256", 2, 64, 256, 24, 40, 1, 1, 0, False, False),
