@@ -228,6 +228,30 @@ def test_linear_gemm(ops):
     _close((o[0].float() + o[1].float()) / ops.ACT_SCALE, ref, "fc1/split")
 
 
+@pytest.mark.parametrize("n_seq", [100, 37, 21, 1])
+def test_lstm_bidir_matches_torch(ops, n_seq):
+    """The persistent recurrent kernel against torch.nn.LSTM(bidirectional) given the same input projections;
+    T = 32, H = 256 as in BiLSTMBlockV2 (recognizer_encoder.py:136-144)."""
+    mode = "stream"
+    T, H = 32, 256
+    g = torch.Generator().manual_seed(n_seq)
+    lstm = torch.nn.LSTM(H, H, bidirectional=True, batch_first=True)
+    with torch.no_grad():
+        for p_ in lstm.parameters():
+            p_.copy_(torch.randn(p_.shape, generator=g) * 0.06)
+    x = torch.randn(n_seq, T, H, generator=g)
+    with torch.no_grad():
+        ref, _ = lstm(x)
+        gates = torch.cat([x @ lstm.weight_ih_l0.t() + lstm.bias_ih_l0 + lstm.bias_hh_l0,
+                           x @ lstm.weight_ih_l0_reverse.t() + lstm.bias_ih_l0_reverse + lstm.bias_hh_l0_reverse], 2)
+        whh_t = torch.stack((lstm.weight_hh_l0.t().contiguous(), lstm.weight_hh_l0_reverse.t().contiguous()), 0)
+    out = torch.zeros((2, n_seq * T, 2 * H), dtype=torch.float16, device="cuda")
+    f32 = torch.zeros((n_seq * T, 2 * H), dtype=torch.float32, device="cuda")
+    ops.lstm_bidir(gates.reshape(n_seq * T, 8 * H).contiguous().cuda(), whh_t.contiguous().cuda(), n_seq, T, out, f32)
+    _close(f32.view(n_seq, T, 2 * H), ref, f"lstm/{mode}/f32")
+    _close(((out[0].float() + out[1].float()) / ops.ACT_SCALE).view(n_seq, T, 2 * H), ref, f"lstm/{mode}/split")
+
+
 # ------------------------------------------------------------------------------ rotated RoIAlign
 def _random_rois(g, n, img=1024.0, batch=1):
     cx = torch.rand(n, generator=g) * img
