@@ -150,6 +150,43 @@ def _cpu_runner(wl):
                  f"path, fp32 torch CPU), recognizer capped at {CPU_WORD_CAP} words/image (the GPU arm decodes all)")
 
 
+def _torch_backbone_on_gpu(B, H, W):
+    """BASELINE.json configs[1] says "tcgen05 conv kernels vs torch.conv2d": the same ResNet-50+FPN in plain PyTorch
+    (cuDNN) on this GPU, INFORMATIONAL only -- library kernels at their own precisions (strict fp32, TF32, bf16), none of
+    which is the fp32-grade split arithmetic of the product path."""
+    import torch
+    from oracle import nets  # test infrastructure; a comparison leg like cpu_baseline, never the measured product
+    res = {}
+    try:
+        net = nets.ResNetFPN().eval().cuda()
+        x = torch.randn(B, 3, H, W, device="cuda")
+        for name, tf32, dtype in (("fp32_strict", False, torch.float32), ("tf32", True, torch.float32),
+                                  ("bf16_channels_last", True, torch.bfloat16)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            m = net.to(dtype)
+            xi = x.to(dtype)
+            if dtype == torch.bfloat16:
+                m, xi = m.to(memory_format=torch.channels_last), xi.contiguous(memory_format=torch.channels_last)
+            with torch.no_grad():
+                for _ in range(2):
+                    m(xi)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(5):
+                    m(xi)
+                e1.record()
+                torch.cuda.synchronize()
+            res[name + "_images_per_s"] = B * 5 / (e0.elapsed_time(e1) / 1e3)
+            net = net.float()
+    except Exception as e:  # informational: never fail the bench line over it
+        res["error"] = repr(e)[:200]
+    finally:
+        torch.backends.cudnn.allow_tf32 = True
+    return res
+
+
 def cpu_sample(wl, repeats: int):
     import torch
     run, desc = _cpu_runner(wl)
@@ -544,6 +581,20 @@ def run_roialign(args):
     nbytes = _roialign_algorithmic_bytes(rois)
     peaks, src = _peaks()
     gbs = nbytes / (ms / 1e3) / 1e9
+    # comparison arm: detectron2's GPU formulation restated (fp32 NCHW, thread per output, one launch per level incl.
+    # the ROIPooler's index glue), same RoIs, rotating copies of the NCHW pyramid
+    feats_nchw = [[f.cuda().contiguous() for f in feats] for _ in range(ncopy)]
+    for i in range(3):
+        ops.baseline_roi_pooler_d2(feats_nchw[i % ncopy], rois_d, (7, 7), scales, 2)
+    torch.cuda.synchronize()
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nb = 20
+    b0.record()
+    for i in range(nb):
+        ops.baseline_roi_pooler_d2(feats_nchw[i % ncopy], rois_d, (7, 7), scales, 2)
+    b1.record()
+    torch.cuda.synchronize()
+    d2_ms = b0.elapsed_time(b1) / nb
     print(json.dumps({
         "metric": "RotatedROIAlign GB/s (algorithmic bytes)", "value": gbs, "unit": "GB/s", "n_gpus": 1, "steps": args.steps,
         "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -553,7 +604,12 @@ def run_roialign(args):
                          f"({ncopy} x 117 MB > 126 MB L2)",
                    "rois_per_s": 512 / (ms / 1e3),
                    "single_launch_l2_flushed_ms": ms_flushed,
-                   "single_launch_l2_flushed_gbs": nbytes / (ms_flushed / 1e3) / 1e9},
+                   "single_launch_l2_flushed_gbs": nbytes / (ms_flushed / 1e3) / 1e9,
+                   "d2_style_baseline_ms": d2_ms, "d2_style_baseline_gbs": nbytes / (d2_ms / 1e3) / 1e9,
+                   "speedup_vs_d2_style": d2_ms / ms,
+                   "d2_style_baseline": "detectron2 v0.6 ROIPooler + ROIAlignRotated CUDA formulation restated "
+                                        "(csrc/baseline_d2.cu: fp32 NCHW, one thread per output element, one launch per "
+                                        "level); detectron2 itself cannot be built offline"},
         "gpu_launches": launches, "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
                      "traffic": _traffic("roialign_512"), "kernel": "roi_align_rotated_split8_kernel<2>",
@@ -720,6 +776,8 @@ def run_b200(args):
         if world == 1 and not args.no_cpu:
             v, cores, sample = cpu_sample(wl, repeats=1 if full else 3)
             out["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}
+            if not full:
+                out["config"]["torch_cudnn_informational"] = _torch_backbone_on_gpu(B, H, W)
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -543,3 +543,27 @@ def postprocess_merge(boxes: torch.Tensor, scores: torch.Tensor, counts: Optiona
     if n_img:
         _lib.check(_lib.load().glass_postprocess_merge(C.byref(p), _stream()))
     return out
+
+
+# ---------------------------------------------------------------------------------------------- benchmark baseline
+def baseline_roi_pooler_d2(feats_nchw: Sequence[torch.Tensor], rois: torch.Tensor, output_size: Tuple[int, int],
+                           scales: Sequence[float], sampling_ratio: int, min_level: int = 2) -> torch.Tensor:
+    """detectron2's ROIPooler with its ROIAlignRotated CUDA formulation restated (csrc/baseline_d2.cu): level assignment
+    with torch ops, then ONE kernel call per FPN level on that level's RoIs, results scattered back -- the comparison
+    arm of bench.py's RoIAlign microbench, never used by the model.  fp32 NCHW in, fp32 [R, C, ph, pw] out."""
+    lvl = torch.floor(4 + torch.log2(torch.sqrt(rois[:, 3] * rois[:, 4]) / 224 + 1e-8))
+    lvl = torch.clamp(lvl, min=min_level, max=min_level + len(feats_nchw) - 1).to(torch.int64) - min_level
+    c = feats_nchw[0].shape[1]
+    out = torch.zeros((rois.shape[0], c, output_size[0], output_size[1]), dtype=torch.float32, device=rois.device)
+    for l, f in enumerate(feats_nchw):
+        inds = torch.nonzero(lvl == l).squeeze(1)
+        if inds.numel() == 0:
+            continue
+        r = rois[inds].contiguous()
+        o = torch.empty((r.shape[0], c, output_size[0], output_size[1]), dtype=torch.float32, device=rois.device)
+        n, _, h, w = f.shape
+        _lib.check(_lib.load().glass_baseline_roi_align_rotated_d2(_ptr(f), n, c, h, w, _ptr(r), r.shape[0], float(scales[l]),
+                                                                   output_size[0], output_size[1], sampling_ratio, _ptr(o),
+                                                                   _stream()))
+        out[inds] = o
+    return out

@@ -364,6 +364,15 @@ int glass_postprocess_merge(const GlassPostprocessParams* p, void* stream);
 int glass_text_scores(const float* probs, int n_words, int steps, int classes, int stop_index, float* score,
                       int32_t* out_idx, float* out_maxp, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Benchmark baseline (NOT on the product path): detectron2 v0.6's GPU formulation of rotated RoIAlign restated --
+ * fp32 NCHW, one thread per output element, one call per FPN level (ROIPooler).  Timed by bench.py --workload
+ * roialign_512 next to glass_roi_align_rotated (BASELINE.json configs[2]: "HBM GB/s vs detectron2 CUDA op").
+ * ------------------------------------------------------------------------------------------ */
+int glass_baseline_roi_align_rotated_d2(const float* input_nchw, int n, int channels, int height, int width,
+                                        const float* rois, int n_rois, float spatial_scale, int pooled_h, int pooled_w,
+                                        int sampling_ratio, float* out_nchw, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

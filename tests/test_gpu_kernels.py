@@ -335,6 +335,20 @@ def test_roi_align_rotated_split_input_matches_oracle(ops, cfg):
     assert out_act.buf[:, :, 0].abs().max().item() == 0  # the zero border is never written
 
 
+def test_d2_style_baseline_matches_oracle(ops):
+    """The benchmark's comparison arm (detectron2's thread-per-output NCHW formulation, csrc/baseline_d2.cu) computes the
+    same thing as the oracle -- otherwise the speed-up quoted against it would be meaningless."""
+    from oracle import d2_ops
+    g = torch.Generator().manual_seed(31)
+    sizes, scales = [64, 32, 16, 8, 4], [1 / 4, 1 / 8, 1 / 16, 1 / 32, 1 / 64]
+    feats = [torch.randn(1, 64, s, s, generator=g) for s in sizes]
+    rois = _random_rois(g, 64, img=256.0, batch=1)
+    rois[:, 3:5] *= 0.6
+    ref = d2_ops.roi_pooler(feats, [rois[:, 1:]], (7, 7), scales, 2)
+    got = ops.baseline_roi_pooler_d2([f.cuda() for f in feats], rois.cuda(), (7, 7), scales, 2)
+    _close(got, ref, "d2-style baseline")
+
+
 def test_image_roi_align_matches_oracle(ops):
     from oracle import d2_ops
     g = torch.Generator().manual_seed(12)
