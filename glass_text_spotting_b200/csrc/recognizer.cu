@@ -118,21 +118,44 @@ __global__ void __launch_bounds__(256) gc_attention_kernel(const GcParams p) {
     }
   }
   __syncthreads();
-  // phase 3: context per concat channel (2 channels per thread, coalesced across the warp)
-  for (int f = 2 * tid; f < GC_C; f += 2 * blockDim.x) {
+  // phase 3: context per concat channel.  64 channel groups of 8 (one 16-byte vector per plane) x 4 position
+  // quarters over the 256 threads, partial sums combined in a fixed order (the scalar 2-channels-per-thread walk over
+  // all positions was latency-bound: 256 dependent-address 4-byte loads per thread)
+  {
+    const int cgp = tid & 63, quarter = tid >> 6;  // channels 8*cgp .. 8*cgp+7
+    const int f = 8 * cgp;
     const int hh = (f & 255) >> 5;
-    float c0 = 0.f, c1 = 0.f;
-    for (int pos = 0; pos < P; ++pos) {
+    float c[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) c[j] = 0.f;
+    const int per = (P + 3) >> 2;
+    const int pos_end = min(P, (quarter + 1) * per);
+#pragma unroll 4
+    for (int pos = quarter * per; pos < pos_end; ++pos) {
       const int y = pos / p.w, x = pos - y * p.w;
       const int64_t off = base + ((int64_t)(y + p.border) * wp + x + p.border) * GC_C + f;
-      const float2 xv = unpack16x2(__ldg(reinterpret_cast<const uint32_t*>(p.f_hi + off)),
-                                   __ldg(reinterpret_cast<const uint32_t*>(p.f_lo + off)));
-      const float a = logit[hh * P + pos];
-      c0 += xv.x * a;
-      c1 += xv.y * a;
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(p.f_hi + off));
+      const uint4 b = __ldg(reinterpret_cast<const uint4*>(p.f_lo + off));
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+      const float wgt = logit[hh * P + pos];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 xv = unpack16x2(aw[j], bw[j]);
+        c[2 * j] += xv.x * wgt;
+        c[2 * j + 1] += xv.y * wgt;
+      }
     }
-    ctx[f] = c0;
-    ctx[f + 1] = c1;
+    if (quarter == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ctx[f + j] = c[j];
+    }
+    for (int q = 1; q < 4; ++q) {
+      __syncthreads();
+      if (quarter == q) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ctx[f + j] += c[j];
+      }
+    }
   }
   __syncthreads();
   // phase 4: channel_add MLP: 512 -> 256, LayerNorm(256), ReLU, 256 -> 512
@@ -172,18 +195,26 @@ __global__ void __launch_bounds__(256) gc_attention_kernel(const GcParams p) {
     tvec[f] = acc;
   }
   __syncthreads();
-  // phase 5: Y = F + t (broadcast over positions)
-  for (int i = tid; i < P * (GC_C / 2); i += blockDim.x) {
-    const int pos = i / (GC_C / 2), f = 2 * (i - pos * (GC_C / 2));
+  // phase 5: Y = F + t (broadcast over positions), 8 channels per thread and iteration (16-byte vectors)
+  for (int i = tid; i < P * (GC_C / 8); i += blockDim.x) {
+    const int pos = i / (GC_C / 8), f = 8 * (i - pos * (GC_C / 8));
     const int y = pos / p.w, x = pos - y * p.w;
     const int64_t off = base + ((int64_t)(y + p.border) * wp + x + p.border) * GC_C + f;
-    const float2 xv = unpack16x2(__ldg(reinterpret_cast<const uint32_t*>(p.f_hi + off)),
-                                 __ldg(reinterpret_cast<const uint32_t*>(p.f_lo + off)));
-    __half h0, l0, h1, l1;
-    split16(xv.x + tvec[f], h0, l0);
-    split16(xv.y + tvec[f + 1], h1, l1);
-    *reinterpret_cast<uint32_t*>(p.y_hi + off) = pack16x2(h0, h1);
-    *reinterpret_cast<uint32_t*>(p.y_lo + off) = pack16x2(l0, l1);
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(p.f_hi + off));
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(p.f_lo + off));
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 xv = unpack16x2(aw[j], bw[j]);
+      __half h0, l0, h1, l1;
+      split16(xv.x + tvec[f + 2 * j], h0, l0);
+      split16(xv.y + tvec[f + 2 * j + 1], h1, l1);
+      hw[j] = pack16x2(h0, h1);
+      lw[j] = pack16x2(l0, l1);
+    }
+    *reinterpret_cast<uint4*>(p.y_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    *reinterpret_cast<uint4*>(p.y_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
   }
 }
 
