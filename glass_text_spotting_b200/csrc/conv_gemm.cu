@@ -540,6 +540,14 @@ extern "C" int glass_conv_gemm(const GlassConvGemmParams* p, void* stream_v) {
     bn = (p->n % 256 == 0) ? 256 : 128;
   }
   const int64_t rows_m = (int64_t)p->m_imgs * p->m_h * p->m_w;
+  // Small-M GEMMs (the box head's FCs: 400 rows x 2048 columns x K = 12544; the RPN head on p5 / p6) would occupy a
+  // fraction of the 148 SMs with 256-wide tiles, and each of those CTAs is bound by its own TMA feed: narrower tiles
+  // put more SMs to work and shrink the weight stream per CTA (per-output arithmetic does not depend on the tile width).
+  {
+    const int sms_now = num_sms();
+    const int64_t tm = (rows_m + BM - 1) / BM;
+    while (bn > 64 && bn % 2 == 0 && (bn / 2) % 16 == 0 && p->n % (bn / 2) == 0 && tm * (p->n / bn) * 2 <= sms_now) bn /= 2;
+  }
   GLASS_CHECK(rows_m > 0 && rows_m < (int64_t)1 << 31, "bad M space");
   GLASS_CHECK(p->rows_a > 0 && p->rows_a < (int64_t)1 << 31, "bad rows_a");
   GLASS_CHECK(p->m_border >= 0 && 2 * p->m_border < p->m_h && 2 * p->m_border < p->m_w, "bad m_border");
