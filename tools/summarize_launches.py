@@ -6,7 +6,7 @@ import sys
 from collections import OrderedDict
 
 path = sys.argv[1]
-marker = sys.argv[2] if len(sys.argv) > 2 else "stem_im2col"
+marker = sys.argv[2] if len(sys.argv) > 2 else "stem_s2d"
 rows = []
 with open(path, newline="") as f:
     lines = [ln for ln in f if ln.startswith('"')]
