@@ -39,6 +39,9 @@ WORKLOADS["totaltext_loop"] = dict(batch=4, h=1024, w=1024, full=True, totaltext
                                         "device resize to 1200x1200 (glass_finetune_totaltext.yaml MIN_SIZE_TEST) -> pad "
                                         "1216 -> full GLASS inference -> word post-processor -> 24 KB/image records -> "
                                         "one NCCL all-gather, bs=4/GPU")
+WORKLOADS["mask_bs4"] = dict(batch=4, h=1024, w=1024, full=False, mask=True,
+                             desc="mask branch (SURVEY.md 8f #3: 14x14 rotated mask pooler over 5 FPN levels -> 4 conv3x3 + "
+                                  "deconv + predictor -> sigmoid -> rotated paste at 1024x1024) for 4 images x 89 detections")
 CPU_WORD_CAP = 16  # the CPU arm decodes at most this many words per image (bounded sample)
 
 
@@ -114,6 +117,17 @@ def _cpu_runner(wl):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     g = torch.Generator().manual_seed(0)
+    if wl.get("mask"):
+        from oracle import d2_ops, mask as omask  # test infrastructure; allowed here only as the timed CPU baseline
+        feats, rois = _mask_inputs(1, CPU_WORD_CAP)
+        head = omask.seeded_mask_head(0)
+
+        def run():
+            with torch.no_grad():
+                pooled = d2_ops.roi_pooler(feats, [rois[:, 1:]], (14, 14), [1 / 4, 1 / 8, 1 / 16, 1 / 32, 1 / 64], 0)
+                omask.paste_masks_in_image(head(pooled)[:, 0], rois[:, 1:].contiguous(), (wl["h"], wl["w"]), 0.5)
+        return run, (f"1 image, {CPU_WORD_CAP} detections through the oracle's mask branch (torch fp32 CPU: rotated pooler, "
+                     f"mask head, reference paste at 1024x1024); the GPU arm does 89 per image")
     if wl.get("postprocess"):
         from oracle import postprocess as opp  # test infrastructure; allowed here only as the timed CPU baseline
         from glass_text_spotting_b200.text import TextDecoder
@@ -284,6 +298,77 @@ def _postprocess_inputs(batch, m=100):
             pr[k, stops[k], 1] = 0.808
         probs.append(pr)
     return torch.stack(boxes), torch.stack(scores), torch.stack(probs)
+
+
+def _mask_inputs(n_img, per_img, seed=0):
+    import math
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    feats = [torch.randn(n_img, 256, s, s, generator=g) for s in (256, 128, 64, 32, 16)]
+    n = n_img * per_img
+    cx, cy = torch.rand(n, generator=g) * 1024, torch.rand(n, generator=g) * 1024
+    w = torch.exp(torch.rand(n, generator=g) * (math.log(400) - math.log(24)) + math.log(24))
+    h = w * (0.15 + 0.6 * torch.rand(n, generator=g))
+    a = torch.rand(n, generator=g) * 360 - 180
+    b = torch.arange(n_img).repeat_interleave(per_img).float()
+    return feats, torch.stack((b, cx, cy, w, h, a), 1).contiguous()
+
+
+def run_mask(args):
+    """SURVEY.md 8f #3 measured like the hot path (device-resident pyramid; e2e adds the D2H of the pasted masks)."""
+    import torch
+    from glass_text_spotting_b200 import lib, ops, weights
+    from glass_text_spotting_b200.modeling.mask_head import B200MaskHead
+    wl = WORKLOADS["mask_bs4"]
+    B, per = wl["batch"], 89
+    feats, rois = _mask_inputs(B, per)
+    acts = {f"p{i + 2}": ops.Act.from_nchw(f.cuda()) for i, f in enumerate(feats)}
+    rois_d = rois.cuda()
+    head = B200MaskHead(weights.random_mask_head_state_dict(0))
+    L = lib.load()
+
+    def step():
+        m = head(acts, rois_d, cap=B * 100)
+        return B200MaskHead.paste(m, rois_d[:, 1:].contiguous(), (wl["h"], wl["w"]), 0.5)
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        out = step()
+    torch.cuda.synchronize()
+    launches0 = L.glass_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    torch.cuda.synchronize()
+    t_dev = e0.elapsed_time(e1) / 1e3
+    launches = L.glass_launch_count() - launches0
+    host = torch.empty(out.shape, dtype=torch.bool).pin_memory()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        host.copy_(step(), non_blocking=True)
+    f1.record()
+    torch.cuda.synchronize()
+    t_e2e = f0.elapsed_time(f1) / 1e3
+    res = {
+        "metric": "images/sec through the mask branch (89 detections each, masks pasted at 1024x1024)",
+        "value": B * args.steps / t_dev, "unit": "images/s", "n_gpus": 1, "steps": args.steps, "warmup": warm,
+        "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp16x3 split GEMMs, fp32 paste", "data": "synthetic",
+        "config": {"workload": wl["desc"], "pixels_set_fraction": float(out.float().mean()),
+                   "l2": "every step writes 373 MB of pasted masks (> 126 MB L2)"},
+        "e2e": {"value": B * args.steps / t_e2e, "unit": "images/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": host.numel(), "note": "device-resident pyramid and boxes -> D2H of the bool masks"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "achieved": None, "peak": None, "unit": "GB/s", "frac": None, "traffic": None,
+                     "kernel": "paste_masks_rotated_kernel + conv_gemm_kernel (not profiled separately this round)"},
+    }
+    if not args.no_cpu:
+        v, cores, sample = cpu_sample(wl, repeats=2)
+        res["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}
+    print(json.dumps(res))
 
 
 def run_postprocess(args):
@@ -802,6 +887,8 @@ def main():
         run_postprocess(args)
     elif WORKLOADS[args.workload].get("totaltext"):
         run_totaltext(args)
+    elif WORKLOADS[args.workload].get("mask"):
+        run_mask(args)
     else:
         run_b200(args)
 

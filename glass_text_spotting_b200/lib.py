@@ -15,7 +15,7 @@ SYMBOLS = [
     "glass_roi_align_rotated", "glass_image_roi_align_rotated", "glass_rpn_topk_decode", "glass_rpn_topk_workspace_bytes",
     "glass_nms_workspace_bytes",
     "glass_nms_rotated", "glass_box_decode", "glass_gc_attention", "glass_hmean_rows", "glass_lstm_bidir",
-    "glass_aster_decode", "glass_aster_finalize", "glass_resize_bilinear_u8", "glass_postprocess_merge", "glass_text_scores", "glass_zero_border", "glass_stem_s2d", "glass_baseline_roi_align_rotated_d2",
+    "glass_aster_decode", "glass_aster_finalize", "glass_resize_bilinear_u8", "glass_postprocess_merge", "glass_text_scores", "glass_zero_border", "glass_stem_s2d", "glass_baseline_roi_align_rotated_d2", "glass_mask_finalize", "glass_paste_masks_rotated",
 ]
 
 
@@ -156,6 +156,8 @@ def load() -> C.CDLL:
     lib.glass_text_scores.argtypes = [p, i, i, i, i, p, p, p, p]
     lib.glass_zero_border.argtypes = [p, p, i, i, i, i, p]
     lib.glass_stem_s2d.argtypes = [p, i, i, i, f, f, p, p, p]
+    lib.glass_mask_finalize.argtypes = [p, i, i, i, i, p, p]
+    lib.glass_paste_masks_rotated.argtypes = [p, p, i, i, i, i, C.c_float, p, p, p]
     lib.glass_baseline_roi_align_rotated_d2.argtypes = [p, i, i, i, i, p, i, C.c_float, i, i, i, p, p]
     for name in SYMBOLS:
         fn = getattr(lib, name)

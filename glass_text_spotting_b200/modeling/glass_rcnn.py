@@ -16,19 +16,22 @@ import torch
 from .. import ops
 from ..structures import ImageList, Instances, RotatedBoxes
 from .backbone import B200ResNetFPN, PIXEL_MEAN, PIXEL_STD
+from .mask_head import B200MaskHead
 from .roi_heads import B200GlassROIHeads
 from .rpn import B200RotatedRPN
 
 
 class B200GlassRCNN:
     def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda", mode: int = ops.MODE_SPLIT,
-                 pixel_mean=PIXEL_MEAN, pixel_std=PIXEL_STD, **head_kwargs):
+                 pixel_mean=PIXEL_MEAN, pixel_std=PIXEL_STD, mask_inference: bool = False, **head_kwargs):
         self.device = device
         self.pixel_mean, self.pixel_std = tuple(pixel_mean), tuple(pixel_std)
         self.backbone = B200ResNetFPN(state_dict, device=device, mode=mode, pixel_mean=pixel_mean, pixel_std=pixel_std)
         self.proposal_generator = B200RotatedRPN(state_dict, device=device, mode=mode)
         self.roi_heads = B200GlassROIHeads(state_dict, device=device, mode=mode, pixel_mean=pixel_mean,
                                            pixel_std=pixel_std, **head_kwargs)
+        # MODEL.ROI_MASK_HEAD.MASK_INFERENCE (recognizers_hybrid_head.py:595-601): off in every shipped config
+        self.mask_head = B200MaskHead(state_dict, device=device, mode=mode) if mask_inference else None
 
     # ------------------------------------------------------------------ a1
     def preprocess_image(self, batched_inputs: List[dict]) -> ImageList:
@@ -91,13 +94,22 @@ class B200GlassRCNN:
         assert detected_instances is None, "given-box inference is not on the benchmarked path"
         il = self.preprocess_image(batched_inputs)
         img_hw = torch.tensor(il.image_sizes, dtype=torch.float32, device=self.device)
-        det, probs, counts_host, starts = self.forward_device(il.tensor, img_hw, taps)
+        keep = {} if self.mask_head is not None and taps is None else taps
+        det, probs, counts_host, starts = self.forward_device(il.tensor, img_hw, keep)
+        masks = None
+        if self.mask_head is not None:   # _forward_mask on the detected boxes (recognizers_hybrid_head.py:598-601)
+            rois = [torch.cat((torch.full((c, 1), float(i), device=self.device), det["pred_boxes"][i, :c]), 1)
+                    for i, c in enumerate(counts_host) if c > 0]
+            rois_t = torch.cat(rois).contiguous() if rois else torch.zeros((0, 6), device=self.device)
+            masks = self.mask_head(keep["features"], rois_t, cap=len(counts_host) * self.roi_heads.max_det)
         results = []
         for i, c in enumerate(counts_host):
             inst = Instances(il.image_sizes[i],
                              pred_boxes=RotatedBoxes(det["pred_boxes"][i, :c].clone()),
                              scores=det["scores"][i, :c], pred_classes=torch.zeros(c, dtype=torch.int64, device=self.device),
                              orientations=det["orientations"][i, :c], pred_text_prob=probs[starts[i]: starts[i + 1]])
+            if masks is not None:
+                inst.pred_masks = masks[starts[i]: starts[i + 1]]
             if do_postprocess:
                 inp = batched_inputs[i]
                 inst = detector_postprocess(inst, inp.get("height", il.image_sizes[i][0]), inp.get("width", il.image_sizes[i][1]))
@@ -120,4 +132,7 @@ def detector_postprocess(results: Instances, output_height: int, output_width: i
     boxes.scale(sx, sy)
     boxes.clip((output_height, output_width))
     out._fields["pred_boxes"] = boxes
-    return out[boxes.nonempty()]
+    out = out[boxes.nonempty()]
+    if out.has("pred_masks"):   # paste_masks_in_image on the rescaled boxes (post_processor_academic.py:163-169)
+        out._fields["pred_masks"] = B200MaskHead.paste(out.pred_masks, out.pred_boxes.tensor, (output_height, output_width), 0.5)
+    return out

@@ -545,6 +545,30 @@ def postprocess_merge(boxes: torch.Tensor, scores: torch.Tensor, counts: Optiona
     return out
 
 
+# ---------------------------------------------------------------------------------------------- mask branch
+def mask_finalize(logits: torch.Tensor, k_words: int, h: int, w: int, out: torch.Tensor) -> torch.Tensor:
+    """logits fp32 [>= k*(h+2)*(w+2), ld] (columns dy*2+dx) -> out fp32 [k, 1, 2h, 2w] = sigmoid, sub-pixels scattered."""
+    assert logits.dtype == torch.float32 and logits.is_contiguous() and logits.shape[0] >= k_words * (h + 2) * (w + 2)
+    assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() == k_words * 4 * h * w
+    _lib.check(_lib.load().glass_mask_finalize(_ptr(logits), logits.shape[1], k_words, h, w, _ptr(out), _stream()))
+    return out
+
+
+def paste_masks_rotated(masks: torch.Tensor, boxes: torch.Tensor, image_shape: Tuple[int, int], threshold: float = 0.5,
+                        want_soft: bool = False):
+    """masks fp32 [k, m, m], boxes fp32 [k, 5] -> bool [k, H, W] (+ fp32 sampled values when want_soft)."""
+    assert masks.dim() == 3 and masks.shape[1] == masks.shape[2] and masks.dtype == torch.float32 and masks.is_contiguous()
+    assert boxes.shape == (masks.shape[0], 5) and boxes.dtype == torch.float32 and boxes.is_contiguous()
+    k, m = masks.shape[0], masks.shape[1]
+    h, w = int(image_shape[0]), int(image_shape[1])
+    out = torch.empty((k, h, w), dtype=torch.uint8, device=masks.device)
+    soft = torch.empty((k, h, w), dtype=torch.float32, device=masks.device) if want_soft else None
+    if k:
+        _lib.check(_lib.load().glass_paste_masks_rotated(_ptr(masks), _ptr(boxes), k, m, h, w, float(threshold), _ptr(out),
+                                                         _ptr(soft), _stream()))
+    return (out.bool(), soft) if want_soft else out.bool()
+
+
 # ---------------------------------------------------------------------------------------------- benchmark baseline
 def baseline_roi_pooler_d2(feats_nchw: Sequence[torch.Tensor], rois: torch.Tensor, output_size: Tuple[int, int],
                            scales: Sequence[float], sampling_ratio: int, min_level: int = 2) -> torch.Tensor:

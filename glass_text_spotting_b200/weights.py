@@ -160,3 +160,18 @@ def random_state_dict(seed: int = 0) -> Dict[str, torch.Tensor]:
     sd[d + "fc.bias"] = torch.zeros(97)
     sd[d + "temperature"] = torch.ones(1)
     return sd
+
+
+def random_mask_head_state_dict(seed: int = 0, prefix: str = "roi_heads.mask_head.") -> Dict[str, torch.Tensor]:
+    """detectron2 MaskRCNNConvUpsampleHead keys (ROI_MASK_HEAD: NUM_CONV 4, CONV_DIM 256, one class): mask_fcn1..4,
+    deconv, predictor.  Own generator, so adding it never changes the weights random_state_dict() draws."""
+    g = torch.Generator().manual_seed(seed + 7777)
+    sd = {}
+    for k in range(1, 5):
+        sd[f"{prefix}mask_fcn{k}.weight"] = _msra(g, 256, 256, 3, 3)
+        sd[f"{prefix}mask_fcn{k}.bias"] = torch.randn(256, generator=g) * 0.05
+    sd[prefix + "deconv.weight"] = torch.randn(256, 256, 2, 2, generator=g) * (2.0 / 1024) ** 0.5
+    sd[prefix + "deconv.bias"] = torch.randn(256, generator=g) * 0.05
+    sd[prefix + "predictor.weight"] = torch.randn(1, 256, 1, 1, generator=g) * 0.5
+    sd[prefix + "predictor.bias"] = torch.zeros(1)
+    return sd

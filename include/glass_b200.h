@@ -365,6 +365,19 @@ int glass_text_scores(const float* probs, int n_words, int steps, int classes, i
                       int32_t* out_idx, float* out_maxp, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Mask branch (MODEL.ROI_MASK_HEAD.MASK_INFERENCE): the head's convolutions run on glass_conv_gemm
+ * (the 2x2/s2 deconv as a GEMM with one 256-column block per output sub-pixel, the predictor block-diagonal over them).
+ * ------------------------------------------------------------------------------------------ */
+/* mask_rcnn_inference (detectron2) + sub-pixel scatter: logits fp32 [K*(h+2)*(w+2), ld] over the padded pooled plane,
+ * columns dy*2+dx -> masks fp32 [K, 2h, 2w] = sigmoid(logit). */
+int glass_mask_finalize(const float* logits, int ld, int k_words, int h, int w, float* masks, void* stream);
+/* paste_masks_in_image / _do_paste_mask for rotated boxes (glass/postprocess/post_processor_academic.py:187-335):
+ * masks fp32 [k, m, m] probabilities, boxes [k, 5] in image coordinates -> out uint8 [k, img_h, img_w] = (sampled mask
+ * >= threshold); out_soft optional fp32 [k, img_h, img_w] (the sampled values, for tests). */
+int glass_paste_masks_rotated(const float* masks, const float* boxes, int k, int m, int img_h, int img_w, float threshold,
+                              uint8_t* out, float* out_soft, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Benchmark baseline (NOT on the product path): detectron2 v0.6's GPU formulation of rotated RoIAlign restated --
  * fp32 NCHW, one thread per output element, one call per FPN level (ROIPooler).  Timed by bench.py --workload
  * roialign_512 next to glass_roi_align_rotated (BASELINE.json configs[2]: "HBM GB/s vs detectron2 CUDA op").

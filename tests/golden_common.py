@@ -78,3 +78,21 @@ def make_eval_inputs(seed, n):
         probs[i, stop] = 0.001
         probs[i, stop, 1] = 0.904
     return boxes, scores, probs
+
+
+def make_paste_inputs(seed: int, n: int, h: int, w: int, side: int = 28):
+    """Seeded soft masks [n, side, side] in (0, 1) (a blurred blob per mask) and rotated boxes [n, 5] partly hanging
+    over the image border, for the rotated mask paste (tools/make_golden_paste.py and the tests)."""
+    g = torch.Generator().manual_seed(4000 + seed)
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, side), torch.linspace(-1, 1, side), indexing="ij")
+    masks = []
+    for _ in range(n):
+        a, b = 0.5 + 0.6 * torch.rand(1, generator=g).item(), 0.4 + 0.6 * torch.rand(1, generator=g).item()
+        r = (xx / a) ** 2 + (yy / b) ** 2
+        m = torch.sigmoid(6.0 * (1.0 - r)) * (0.75 + 0.25 * torch.rand(side, side, generator=g))
+        masks.append(m)
+    masks = torch.stack(masks) if n else torch.zeros(0, side, side)
+    boxes = torch.stack([torch.rand(n, generator=g) * (w + 20) - 10, torch.rand(n, generator=g) * (h + 20) - 10,
+                         torch.rand(n, generator=g) * (w / 2) + 6, torch.rand(n, generator=g) * (h / 3) + 4,
+                         torch.rand(n, generator=g) * 360 - 180], 1) if n else torch.zeros(0, 5)
+    return masks.float().contiguous(), boxes.float().contiguous()
