@@ -10,7 +10,7 @@ packed detection records gathered at the end of the loop can feed the reference'
 * ``instances_from_packed``     the inverse of B200GlassRCNN.pack_detections (the all-gathered record)
 Host-side formatting only (numpy / python); masks (``pred_masks`` -> rasterio polygons) are out of scope with the
 mask branch."""
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List, Tuple
 
 import numpy as np
 import torch

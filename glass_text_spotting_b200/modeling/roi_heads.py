@@ -7,7 +7,7 @@ branch :176-181 = ``_forward_box`` :291-339 followed by ``forward_with_given_box
 State-dict names follow SURVEY.md A.10 so reference checkpoints load unchanged.
 """
 import os
-from typing import Dict, List, Optional
+from typing import Dict, Optional
 
 import torch
 
