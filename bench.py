@@ -879,6 +879,9 @@ def run_b200(args):
                          "kernel_share_of_step": gemm_ms / (1e3 * t_dev / args.steps),
                          "algorithmic_flops_per_step": gemm_flops,
                          "issued_mma_flops_per_step": gemm_flops * (1 if args.fast else 3),
+                         # SURVEY.md 8d cfg 4: the WHOLE step against t_min = algorithmic FLOPs / tensor peak (the gather
+                         # term bytes / HBM peak is < 0.1 ms and is left out)
+                         "whole_step_frac_of_tensor_roofline": (gemm_flops / (peak * 1e12)) / (t_dev / args.steps),
                          "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src})"},
         }
         if world == 1 and not args.no_cpu:
