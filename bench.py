@@ -820,6 +820,10 @@ def run_b200(args):
         stream.wait_event(ready[b])
         res = step(dbuf[b].float())
         consumed[b].record(stream)
+        if full and world > 1 and rank != 0:
+            # the gathered records are read back where they are consumed -- on rank 0, like the reference's
+            # comm.gather(dst=0) (text_evaluator.py:246-249); the other ranks read back their own share
+            res = res[rank * B:(rank + 1) * B]
         if res_host is None:
             res_host = torch.empty(res.shape, dtype=res.dtype).pin_memory()
         res_host.copy_(res, non_blocking=True)
