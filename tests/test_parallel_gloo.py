@@ -64,6 +64,16 @@ def test_two_rank_gather_equals_single_process():
     dets = parallel.unpack_detections(got, STEPS, NC)
     assert [len(d["scores"]) for d in dets] == [i % (MAXDET + 1) for i in range(n_images)]
     assert dets[3]["pred_text_prob"].shape == (3, STEPS, NC)
+    # rank 0's consumer: the gathered tensor -> Instances -> the evaluator's records
+    from glass_text_spotting_b200 import evaluation
+    from glass_text_spotting_b200.text import TextDecoder
+    insts = evaluation.instances_from_packed(got.reshape(n_images, MAXDET, -1), [(64, 64)] * n_images, STEPS, NC)
+    assert [len(i) for i in insts] == [len(d["scores"]) for d in dets]
+    assert all(torch.equal(i.pred_boxes.tensor, d["pred_boxes"]) for i, d in zip(insts, dets))
+    dec = TextDecoder("abcde")   # 2 + 5 = 7 classes
+    recs = [evaluation.instances_to_coco_json(inst, img_id, dec) for img_id, inst in enumerate(insts)]
+    assert all(r["image_id"] == i for i, rr in enumerate(recs) for r in rr)
+    assert sum(len(r) for r in recs) <= sum(len(i) for i in insts)
 
 
 def test_single_process_gather_is_identity():
