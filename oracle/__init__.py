@@ -13,7 +13,8 @@ not installable offline.  The oracle is therefore pinned by
     (tests/test_oracle_d2_ops.py), torchvision angle-0 equivalences, and
   * golden vectors generated in the authoring container by importing the reference's
     own pure-torch modules from /root/reference (tools/make_golden.py ->
-    tests/golden/*.pt; checked by tests/test_oracle_golden.py).
+    tests/golden/*.pt; checked by tests/test_oracle_golden.py), including the box branch's inference
+    (tools/make_golden_box_inference.py), the word post-processor, the evaluator formats and the mask paste.
 The detectron2-recalled parts (backbone wiring, RPN, poolers) have no reference-run
 pin: for them parity is "unpinned beyond the upstream KATs" (see DESIGN.md).
 """

@@ -96,3 +96,25 @@ def make_paste_inputs(seed: int, n: int, h: int, w: int, side: int = 28):
                          torch.rand(n, generator=g) * (w / 2) + 6, torch.rand(n, generator=g) * (h / 3) + 4,
                          torch.rand(n, generator=g) * 360 - 180], 1) if n else torch.zeros(0, 5)
     return masks.float().contiguous(), boxes.float().contiguous()
+
+
+def make_box_inference_inputs(seed: int, r: int, hw):
+    """Seeded box-head outputs for R proposals of one image: class logits [R,2] (fg, bg), deltas [R,5], orientation
+    logits [R,4], proposals [R,5]; a few rows are made non-finite and many proposals overlap so that the finite filter,
+    the score threshold, the rotated NMS and the top-k all act."""
+    g = torch.Generator().manual_seed(5000 + seed)
+    h, w = hw
+    n_c = max(r // 4, 1)
+    centers = torch.stack((torch.rand(n_c, generator=g) * w, torch.rand(n_c, generator=g) * h), 1)
+    idx = torch.randint(0, n_c, (r,), generator=g)
+    bw = torch.rand(r, generator=g) * (w / 4) + 8
+    proposals = torch.stack((centers[idx, 0] + torch.randn(r, generator=g) * 4, centers[idx, 1] + torch.randn(r, generator=g) * 3,
+                             bw, bw * (0.15 + 0.5 * torch.rand(r, generator=g)),
+                             torch.rand(r, generator=g) * 360 - 180), 1)
+    logits = torch.stack((torch.randn(r, generator=g) * 2.0, torch.randn(r, generator=g) * 2.0), 1)
+    deltas = torch.randn(r, 5, generator=g) * torch.tensor([1.0, 1.0, 0.5, 0.5, 2.0])
+    orient = torch.randn(r, 4, generator=g) * 2.0
+    if r >= 20:
+        deltas[3, 2] = float("inf")
+        logits[7, 0] = float("nan")
+    return logits.float(), deltas.float(), orient.float(), proposals.float().contiguous()

@@ -127,3 +127,39 @@ def test_recognizer_branch_matches_oracle(glass_lib):
         close(taps["decoder_alpha"][sl, :steps], ot["decoder_alpha"][:, :steps], f"img{i} decoder_alpha", atol=1e-5)
         close(probs[sl], want, f"img{i} pred_text_prob", atol=1e-5)
         off += k
+
+
+@pytest.mark.parametrize("i", range(4))
+def test_box_inference_matches_reference_golden(glass_lib, i):
+    """glass_box_decode + glass_nms_rotated (B200GlassROIHeads.box_inference) against golden vectors from the
+    reference's OWN RotatedFastRCNNOutputs.inference (tests/golden/box_inference.pt): kept proposals and their order
+    exactly, boxes / scores / orientations to fp32 rounding."""
+    import os
+    from golden_common import make_box_inference_inputs
+    from glass_text_spotting_b200 import ops
+    c = torch.load(os.path.join(os.path.dirname(__file__), "golden", "box_inference.pt"), weights_only=False)["cases"][i]
+    logits, deltas, orient, proposals = make_box_inference_inputs(c["seed"], c["r"], c["hw"])
+    r = c["r"]
+    pred = torch.zeros(r, 16)
+    pred[:, 0:2], pred[:, 2:7], pred[:, 7:11] = logits, deltas, orient
+    hw = torch.tensor([list(c["hw"])], dtype=torch.float32).cuda()
+    cand_b, cand_s, cand_o = ops.box_decode(pred.cuda().contiguous(), proposals.cuda().contiguous(), None, 1, r,
+                                            (10.0, 10.0, 5.0, 5.0, 10.0))
+    boxes, scores, index, count = ops.nms_rotated(cand_b, cand_s, 0.35, 100, img_hw=hw, clip=True, filter_empty=False,
+                                                  score_thresh=0.05)
+    k = int(count[0])
+    assert k == len(c["kept"])
+    # the reference drops non-finite rows first, so its kept indices count only the valid rows before them; the device
+    # keeps every proposal in its slot (invalid ones get score -inf) and reports original indices
+    from oracle import d2_ops
+    valid = torch.isfinite(d2_ops.apply_deltas_rotated(deltas, proposals, (10.0, 10.0, 5.0, 5.0, 10.0))).all(1) & \
+        torch.isfinite(torch.softmax(logits, -1)).all(1)
+    compact = torch.cumsum(valid.long(), 0) - 1
+    got_idx = index[0, :k].cpu().long()
+    assert valid[got_idx].all()
+    assert torch.equal(compact[got_idx], c["kept"])
+    assert torch.allclose(boxes[0, :k].cpu(), c["pred_boxes"], rtol=1e-5, atol=1e-4)
+    assert torch.allclose(scores[0, :k].cpu(), c["scores"], rtol=1e-5, atol=1e-6)
+    got_o = cand_o[0][index[0, :k].long()].cpu()
+    assert torch.equal(got_o[:, 0], c["orientations"][:, 0])
+    assert torch.allclose(got_o[:, 1], c["orientations"][:, 1], rtol=1e-5, atol=1e-6)
