@@ -66,3 +66,14 @@ def test_decoder_golden(case):
     assert probs[:, g["num_steps"]:].abs().sum().item() == 0.0
     if case == "decoder_break":
         assert 1 < g["num_steps"] < 26
+
+
+@torch.no_grad()
+def test_cnn_v1_1_golden():
+    """a14: the recognizer's CNN_V1_1 against the reference's own class (tools/make_golden_cnn_v1_1.py)."""
+    m = nets.CNN_V1_1(256).eval()
+    g = torch.load(os.path.join(GOLD, "cnn_v1_1.pt"))
+    assert sorted(m.state_dict().keys()) == g["keys"]   # same parameter names as the reference module
+    gc.seeded_fill(m, 17)
+    x = torch.randn(3, 256, 8, 32, generator=torch.Generator().manual_seed(1017))
+    _check(m(x), "cnn_v1_1")
