@@ -22,9 +22,23 @@ from .rpn import B200RotatedRPN
 
 
 class B200GlassRCNN:
+    """``filter_small_boxes`` / ``inflate_ratio`` are GlassRCNN's ``_postprocess`` options
+    (glass_rcnn.py:43-50: cfg.POST_PROCESSING.MIN_BOX_DIMENSION / INFLATE_RATIO; the three fine-tune configs set
+    MIN_BOX_DIMENSION 2, none sets INFLATE_RATIO).  With both None the model is d2's plain GeneralizedRCNN, which is
+    what configs/glass_pretrain.yaml:40 selects.  ``drop_overlapping_boxes`` (cfg.POST_PROCESSING.DROP_OVERLAPPING,
+    in no shipped config) cannot run in the reference either: post_processor_academic.py:73 hands RotatedBoxes
+    OBJECTS to pairwise_ioa_rotated, whose first statement reads ``.shape`` (glass/structures/boxes.py:31) and
+    raises AttributeError -- requesting it here raises at construction instead of at the first image."""
+
     def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda", mode: int = ops.MODE_SPLIT,
-                 pixel_mean=PIXEL_MEAN, pixel_std=PIXEL_STD, mask_inference: bool = False, **head_kwargs):
+                 pixel_mean=PIXEL_MEAN, pixel_std=PIXEL_STD, mask_inference: bool = False,
+                 filter_small_boxes: Optional[float] = None, inflate_ratio: Optional[float] = None,
+                 drop_overlapping_boxes=None, **head_kwargs):
+        if drop_overlapping_boxes:
+            raise NotImplementedError("POST_PROCESSING.DROP_OVERLAPPING raises AttributeError in the reference "
+                                      "(post_processor_academic.py:73 -> glass/structures/boxes.py:31); not provided")
         self.device = device
+        self.filter_small_boxes, self.inflate_ratio = filter_small_boxes, inflate_ratio
         self.pixel_mean, self.pixel_std = tuple(pixel_mean), tuple(pixel_std)
         self.backbone = B200ResNetFPN(state_dict, device=device, mode=mode, pixel_mean=pixel_mean, pixel_std=pixel_std)
         self.proposal_generator = B200RotatedRPN(state_dict, device=device, mode=mode)
@@ -32,6 +46,7 @@ class B200GlassRCNN:
                                            pixel_std=pixel_std, **head_kwargs)
         # MODEL.ROI_MASK_HEAD.MASK_INFERENCE (recognizers_hybrid_head.py:595-601): off in every shipped config
         self.mask_head = B200MaskHead(state_dict, device=device, mode=mode) if mask_inference else None
+        self.roi_heads.mask_head = self.mask_head      # forward_with_given_boxes runs it (:595-601)
 
     # ------------------------------------------------------------------ a1
     def preprocess_image(self, batched_inputs: List[dict]) -> ImageList:
@@ -43,7 +58,7 @@ class B200GlassRCNN:
     # ------------------------------------------------------------------ dense + decision stages on device
     def detect(self, images: torch.Tensor, img_hw: torch.Tensor, taps: Optional[dict] = None):
         feats = self.backbone(images)
-        pb, ps, pi, pc = self.proposal_generator(feats, img_hw)
+        pb, ps, pi, pc = self.proposal_generator.forward_device(feats, img_hw)
         det = self.roi_heads.forward_box(feats, pb, pc, img_hw, taps)
         if taps is not None:
             taps.update(features=feats, proposal_boxes=pb, objectness_logits=ps, proposal_count=pc)
@@ -89,10 +104,16 @@ class B200GlassRCNN:
         return rec
 
     @torch.no_grad()
-    def inference(self, batched_inputs: List[dict], detected_instances=None, do_postprocess: bool = True,
-                  taps: Optional[dict] = None):
-        assert detected_instances is None, "given-box inference is not on the benchmarked path"
+    def inference(self, batched_inputs: List[dict], detected_instances: Optional[List[Instances]] = None,
+                  do_postprocess: bool = True, taps: Optional[dict] = None):
+        """glass_rcnn.py:57-101.  ``detected_instances`` (one Instances per image with ``pred_boxes`` and
+        ``pred_classes``) skips detection and only predicts the other per-RoI outputs (text, masks).
+        Returns ``list[{"instances": Instances}]``, or the raw ``list[Instances]`` when ``do_postprocess`` is False."""
         il = self.preprocess_image(batched_inputs)
+        if detected_instances is not None:
+            feats = self.backbone(il.tensor)
+            results = self.roi_heads.forward_with_given_boxes(il, feats, [x.to(self.device) for x in detected_instances])
+            return self._postprocess(results, batched_inputs, il.image_sizes) if do_postprocess else results
         img_hw = torch.tensor(il.image_sizes, dtype=torch.float32, device=self.device)
         keep = {} if self.mask_head is not None and taps is None else taps
         det, probs, counts_host, starts = self.forward_device(il.tensor, img_hw, keep)
@@ -110,11 +131,21 @@ class B200GlassRCNN:
                              orientations=det["orientations"][i, :c], pred_text_prob=probs[starts[i]: starts[i + 1]])
             if masks is not None:
                 inst.pred_masks = masks[starts[i]: starts[i + 1]]
-            if do_postprocess:
-                inp = batched_inputs[i]
-                inst = detector_postprocess(inst, inp.get("height", il.image_sizes[i][0]), inp.get("width", il.image_sizes[i][1]))
-            results.append({"instances": inst})
-        return results
+            results.append(inst)
+        return self._postprocess(results, batched_inputs, il.image_sizes) if do_postprocess else results
+
+    def _postprocess(self, instances: List[Instances], batched_inputs: List[dict], image_sizes):
+        """GlassRCNN._postprocess (glass_rcnn.py:103-128): optional small-box filter and inflation, then
+        detector_postprocess to the requested output size.  Index glue on <= 100 boxes per image."""
+        out = []
+        for inst, inp, size in zip(instances, batched_inputs, image_sizes):
+            height, width = inp.get("height", size[0]), inp.get("width", size[1])
+            if self.filter_small_boxes:
+                inst = filter_small_boxes(inst, self.filter_small_boxes)
+            if self.inflate_ratio:
+                inst = resize_boxes(inst, self.inflate_ratio)
+            out.append({"instances": detector_postprocess(inst, height, width)})
+        return out
 
     def forward(self, batched_inputs: List[dict]):
         return self.inference(batched_inputs)
@@ -122,17 +153,53 @@ class B200GlassRCNN:
     __call__ = forward
 
 
+def filter_small_boxes(preds: Instances, min_box_dim: float) -> Instances:
+    """PostProcessorRotatedBoxes.filter_small_boxes (post_processor_rotated_boxes.py:89-94): keep min(w, h) >= dim."""
+    if len(preds) == 0:
+        return preds
+    boxes = preds.pred_boxes.tensor
+    return preds[torch.min(boxes[:, 2], boxes[:, 3]) >= min_box_dim]
+
+
+def resize_boxes(preds: Instances, ratio: float, axis: str = "both") -> Instances:
+    """PostProcessorAcademic.resize_boxes (post_processor_academic.py:36-63): widen / heighten every box by
+    ``ratio`` of its own width / height IN PLACE (like the reference), then clip to the image."""
+    if len(preds) == 0:
+        return preds
+    if axis not in ("both", "vertical", "horizontal"):
+        raise Exception('Please provide an axis value of either "both"/"horizontal"/"vertical')
+    boxes = preds.pred_boxes.tensor
+    delta_x = ratio * boxes[:, 2] if axis != "vertical" else 0
+    delta_y = ratio * boxes[:, 3] if axis != "horizontal" else 0
+    boxes[:, 2] += delta_x
+    boxes[:, 3] += delta_y
+    preds.pred_boxes.clip(preds.image_size)
+    return preds
+
+
 def detector_postprocess(results: Instances, output_height: int, output_width: int) -> Instances:
-    """d2 detector_postprocess (boxes only; glass/postprocess/post_processor_academic.py:118-178 without masks):
-    rescale to the requested output size, clip, drop empty boxes."""
+    """glass/postprocess/post_processor_academic.py:118-178: rescale ``pred_boxes`` (or ``proposal_boxes``) to the
+    requested output size, clip, drop empty boxes, paste masks, rescale ``pred_rboxes``.  Unlike the reference the
+    caller's box tensor is not modified in place (the result holds a scaled copy).  When ``pred_rboxes`` IS the
+    ``pred_boxes`` object (forward_with_given_boxes under MASK_INFERENCE, recognizers_hybrid_head.py:596-597) the
+    reference's in-place scale/clip of :158-159 has already moved it before :173-175 scale and clip it again; the
+    result is reproduced (tests/golden/meta_postprocess.pt "alias")."""
     sx = output_width / results.image_size[1]
     sy = output_height / results.image_size[0]
     out = Instances((output_height, output_width), **results.get_fields())
-    boxes = RotatedBoxes(out.pred_boxes.tensor.clone())
+    name = "pred_boxes" if out.has("pred_boxes") else "proposal_boxes"
+    src = out.get(name)
+    boxes = RotatedBoxes(src.tensor.clone())
     boxes.scale(sx, sy)
     boxes.clip((output_height, output_width))
-    out._fields["pred_boxes"] = boxes
+    out._fields[name] = boxes
+    if out.has("pred_rboxes"):
+        rb = out.pred_rboxes
+        out._fields["pred_rboxes"] = RotatedBoxes((boxes if rb is src else rb).tensor.clone())
     out = out[boxes.nonempty()]
+    if out.has("pred_rboxes"):   # :173-175
+        out.pred_rboxes.scale(sx, sy)
+        out.pred_rboxes.clip((output_height, output_width))
     if out.has("pred_masks"):   # paste_masks_in_image on the rescaled boxes (post_processor_academic.py:163-169)
         out._fields["pred_masks"] = B200MaskHead.paste(out.pred_masks, out.pred_boxes.tensor, (output_height, output_width), 0.5)
     return out

@@ -7,12 +7,13 @@ branch :176-181 = ``_forward_box`` :291-339 followed by ``forward_with_given_box
 State-dict names follow SURVEY.md A.10 so reference checkpoints load unchanged.
 """
 import os
-from typing import Dict, Optional
+from typing import Dict, List, Optional
 
 import torch
 
 from .. import ops, packing
 from ..ops import Act
+from ..structures import ImageList, Instances, RotatedBoxes
 from .backbone import Workspace, _conv_bn
 
 
@@ -36,6 +37,7 @@ class B200GlassROIHeads:
         self.pool_h, self.pool_w, self.recog_sampling = recog_pool[0], recog_pool[1], recog_sampling_ratio
         self.num_classes, self.steps = num_text_classes, max_word_len
         self.pixel_mean, self.pixel_std = pixel_mean, pixel_std
+        self.mask_head = None      # B200MaskHead when MODEL.ROI_MASK_HEAD.MASK_INFERENCE (set by B200GlassRCNN)
         self.ws = Workspace(device)
         dev = device
 
@@ -179,6 +181,58 @@ class B200GlassROIHeads:
         if taps is not None:
             taps.update(box_pooled=pooled, box_head_out=x, box_pred=pred)
         return det
+
+    # ============================================================================================ d2 ROIHeads surface
+    @torch.no_grad()
+    def forward(self, images: ImageList, features: Dict[str, Act], proposals: List[Instances], targets=None):
+        """ROIHeads.forward, eval branch (recognizers_hybrid_head.py:136-142, 176-181; called at glass_rcnn.py:93 as
+        ``results, _ = self.roi_heads(images, features, proposals, None)``): box branch on the proposals, then the
+        recognizer (and the mask head under MASK_INFERENCE) on the detected boxes -> (list[Instances], {}).
+        ``images.tensor`` holds RAW pixels padded with the pixel mean (B200GlassRCNN.preprocess_image): the image
+        pooler normalises on the fly."""
+        assert targets is None, "inference only: label_and_sample_proposals / losses are out of scope"
+        n, per = len(proposals), max([len(p) for p in proposals] + [1])
+        pb = torch.zeros((n, per, 5), dtype=torch.float32, device=self.device)
+        for i, p in enumerate(proposals):
+            pb[i, : len(p)] = p.proposal_boxes.tensor
+        counts = torch.tensor([len(p) for p in proposals], dtype=torch.int32, device=self.device)
+        img_hw = torch.tensor(images.image_sizes, dtype=torch.float32, device=self.device)
+        det = self.forward_box(features, pb, counts, img_hw)
+        instances = []
+        for i, c in enumerate(det["count"].cpu().tolist()):
+            instances.append(Instances(images.image_sizes[i], pred_boxes=RotatedBoxes(det["pred_boxes"][i, :c].clone()),
+                                       scores=det["scores"][i, :c].clone(),
+                                       pred_classes=torch.zeros(c, dtype=torch.int64, device=self.device),
+                                       orientations=det["orientations"][i, :c].clone()))
+        return self.forward_with_given_boxes(images, features, instances), {}
+
+    __call__ = forward
+
+    @torch.no_grad()
+    def forward_with_given_boxes(self, images: ImageList, features: Dict[str, Act], instances: List[Instances]):
+        """recognizers_hybrid_head.py:571-609 (note the extra ``images`` argument vs stock d2): the same Instances with
+        ``pred_text_prob`` added by the recognizer; under MASK_INFERENCE also ``pred_masks`` and ``pred_rboxes``
+        (= the pred_boxes OBJECT, :596-597)."""
+        assert instances[0].has("pred_boxes") and instances[0].has("pred_classes")
+        counts = [len(x) for x in instances]
+        rois = [torch.cat((torch.full((c, 1), float(i), device=self.device),
+                           instances[i].pred_boxes.tensor.to(self.device)), 1) for i, c in enumerate(counts) if c > 0]
+        rois_t = torch.cat(rois).contiguous() if rois else torch.zeros((0, 6), device=self.device)
+        starts = [0]
+        for c in counts:
+            starts.append(starts[-1] + c)
+        word_start = torch.tensor(starts, dtype=torch.int32, device=self.device)
+        probs = self.forward_recognizer(images.tensor, tuple(images.tensor.shape[-2:]), features, rois_t, word_start,
+                                        len(instances))
+        masks = None
+        if self.mask_head is not None:
+            masks = self.mask_head(features, rois_t, cap=max(len(instances) * self.max_det, rois_t.shape[0]))
+        for i, inst in enumerate(instances):
+            inst.pred_text_prob = probs[starts[i]: starts[i + 1]]
+            if masks is not None:
+                inst.pred_masks = masks[starts[i]: starts[i + 1]]
+                inst.pred_rboxes = inst.pred_boxes
+        return instances
 
     # ============================================================================================ recognizer
     def p2p3(self, features: Dict[str, Act]) -> Act:

@@ -13,6 +13,7 @@ import torch
 
 from .. import ops, packing
 from ..ops import Act
+from ..structures import ImageList, Instances, RotatedBoxes
 from .backbone import Workspace
 
 
@@ -102,11 +103,25 @@ class B200RotatedRPN:
         return ops.nms_rotated(boxes, scores, self.nms_thresh, self.post_nms_topk, group_size=self.pre_nms_topk,
                                img_hw=img_hw, clip=True, filter_empty=True, workspace=wsb, out=out)
 
-    def forward(self, features: Dict[str, Act], img_hw: torch.Tensor):
+    def forward_device(self, features: Dict[str, Act], img_hw: torch.Tensor):
         """img_hw: fp32 [n,2] device tensor of the (unpadded) image sizes.
         Returns (proposal_boxes [n,100,5], objectness_logits [n,100], index, count [n])."""
         preds = self.head(features)
         boxes, scores = self.topk_decode(preds)
         return self.select(boxes, scores, img_hw)
+
+    @torch.no_grad()
+    def forward(self, images: ImageList, features: Dict[str, Act], gt_instances=None):
+        """The detectron2 ProposalGenerator surface RotatedRPN inherits (rotated_rpn.py:17; called at
+        glass_rcnn.py:88 as ``proposals, _ = self.proposal_generator(images, features, None)``):
+        -> (list[Instances{proposal_boxes: RotatedBoxes, objectness_logits}] sorted by score, {} losses)."""
+        assert gt_instances is None, "inference only: the training losses are out of scope (DESIGN.md section 7)"
+        img_hw = torch.tensor(images.image_sizes, dtype=torch.float32, device=self.device)
+        boxes, scores, _, count = self.forward_device(features, img_hw)
+        out = []
+        for i, c in enumerate(count.cpu().tolist()):
+            out.append(Instances(images.image_sizes[i], proposal_boxes=RotatedBoxes(boxes[i, :c].clone()),
+                                 objectness_logits=scores[i, :c].clone()))
+        return out, {}
 
     __call__ = forward

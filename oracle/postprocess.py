@@ -152,3 +152,57 @@ def post_process(boxes: torch.Tensor, scores: torch.Tensor, text_scores: Optiona
         k = text_scores.float()[idx] >= cfg.text_threshold
         boxes, scores, idx = boxes[k], scores[k], idx[k]
     return boxes, idx, boxes_to_polygons(boxes), iters
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# a17: GlassRCNN._postprocess (glass/modeling/meta_arch/glass_rcnn.py:103-128) and the detector_postprocess it ends in
+# (glass/postprocess/post_processor_academic.py:118-178).  Pinned by tests/golden/meta_postprocess.pt, written by the
+# reference's OWN functions (tools/make_golden_meta_postprocess.py) -- tests/test_oracle_meta_postprocess.py.
+# ----------------------------------------------------------------------------------------------------------------
+def filter_small_boxes_keep(boxes: torch.Tensor, min_box_dim: float) -> torch.Tensor:
+    """post_processor_rotated_boxes.py:89-94 -> boolean keep mask."""
+    return torch.min(boxes[:, 2], boxes[:, 3]) >= min_box_dim
+
+
+def resize_boxes_(boxes: torch.Tensor, ratio: float, image_size, axis: str = "both") -> torch.Tensor:
+    """post_processor_academic.py:36-63, in place: w += ratio*w, h += ratio*h, then RotatedBoxes.clip."""
+    if len(boxes) == 0:
+        return boxes
+    dx = ratio * boxes[:, 2] if axis in ("both", "horizontal") else 0
+    dy = ratio * boxes[:, 3] if axis in ("both", "vertical") else 0
+    boxes[:, 2] += dx
+    boxes[:, 3] += dy
+    d2_ops.clip_rotated_(boxes, image_size)
+    return boxes
+
+
+def detector_postprocess(boxes: torch.Tensor, image_size, out_h: int, out_w: int, rboxes_alias: bool = False):
+    """post_processor_academic.py:118-178 on a box tensor: scale, clip, nonempty.  Returns (boxes, keep[, rboxes]).
+    ``rboxes_alias``: ``pred_rboxes`` is the SAME object as ``pred_boxes`` (recognizers_hybrid_head.py:596-597), so the
+    in-place scale/clip of :158-159 already moved it and :173-175 scale and clip it a second time."""
+    sx, sy = out_w / image_size[1], out_h / image_size[0]
+    b = boxes.clone()
+    d2_ops.scale_rotated_(b, sx, sy)
+    d2_ops.clip_rotated_(b, (out_h, out_w))
+    keep = d2_ops.nonempty_rotated(b)
+    out = b[keep]
+    if not rboxes_alias:
+        return out, keep
+    rb = out.clone()
+    d2_ops.scale_rotated_(rb, sx, sy)
+    d2_ops.clip_rotated_(rb, (out_h, out_w))
+    return out, keep, rb
+
+
+def glass_rcnn_postprocess(boxes: torch.Tensor, image_size, out_h: int, out_w: int,
+                           min_box_dim: Optional[float] = None, inflate_ratio: Optional[float] = None):
+    """glass_rcnn.py:103-128 for one image -> (boxes, original indices of the survivors)."""
+    idx = torch.arange(len(boxes))
+    b = boxes.clone()
+    if min_box_dim and len(b):
+        k = filter_small_boxes_keep(b, min_box_dim)
+        b, idx = b[k], idx[k]
+    if inflate_ratio:
+        resize_boxes_(b, inflate_ratio, image_size)
+    out, keep = detector_postprocess(b, image_size, out_h, out_w)
+    return out, idx[keep]

@@ -118,3 +118,33 @@ def make_box_inference_inputs(seed: int, r: int, hw):
         deltas[3, 2] = float("inf")
         logits[7, 0] = float("nan")
     return logits.float(), deltas.float(), orient.float(), proposals.float().contiguous()
+
+
+def make_meta_postprocess_inputs(seed: int, n: int, hw):
+    """Seeded raw detections for GlassRCNN._postprocess (glass_rcnn.py:103-128): a mix of ordinary words, boxes
+    thinner than MIN_BOX_DIMENSION, near-axis-aligned boxes hanging over the border (the only ones
+    RotatedBoxes.clip touches) and boxes wholly outside the image (empty after the clip)."""
+    g = torch.Generator().manual_seed(7000 + seed)
+    h, w = hw
+    cx = torch.rand(n, generator=g) * w
+    cy = torch.rand(n, generator=g) * h
+    bw = torch.exp(torch.rand(n, generator=g) * math.log(40.0)) * 6.0
+    bh = bw * (0.15 + 0.6 * torch.rand(n, generator=g))
+    ang = (torch.rand(n, generator=g) - 0.5) * 120.0
+    for i in range(n):
+        r = i % 8
+        if r == 1:      # too thin (min side < 2)
+            bh[i] = 0.5 + 1.4 * float(torch.rand(1, generator=g))
+        elif r == 2:    # near-axis-aligned, over the right / bottom border
+            ang[i] = (float(torch.rand(1, generator=g)) - 0.5) * 1.8
+            cx[i], cy[i] = w - 3.0, h - 2.0
+        elif r == 3:    # axis-aligned and completely outside
+            ang[i] = 0.0
+            cx[i] = w + 50.0 + bw[i]
+        elif r == 4:    # exactly on the small-box limit
+            bh[i] = 2.0
+        elif r == 5:    # angle outside [-180, 180): normalised by the clip
+            ang[i] = 200.0 + 100.0 * float(torch.rand(1, generator=g))
+    boxes = torch.stack((cx, cy, bw, bh, ang), 1).float()
+    scores = torch.rand(n, generator=g)
+    return boxes, scores

@@ -47,7 +47,7 @@ def test_ragged_batch_matches_oracle_on_the_same_canvas(model_and_oracle):
             feats = o.backbone(canvas[i:i + 1])
             pboxes, _ = o.rpn(feats, sizes[i])
             want = o.box_branch(feats, pboxes, sizes[i])
-            got = both[i]["instances"]
+            got = both[i]   # do_postprocess=False -> raw list[Instances] (glass_rcnn.py:100-101)
             assert got.image_size == sizes[i] and len(got) == len(want["pred_boxes"])
             close(got.pred_boxes.tensor, want["pred_boxes"], f"ragged boxes img{i}", rtol=5e-3, atol=5e-3)
             close(got.scores, want["scores"], f"ragged scores img{i}", rtol=5e-3, atol=1e-4)

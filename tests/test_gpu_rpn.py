@@ -115,7 +115,7 @@ def test_rpn_end_to_end_from_features(glass_lib):
     taps = _oracle_rpn_per_image(o, feats, size)
     rpn = B200RotatedRPN(o.state_dict())
     hw = torch.tensor([size, size], dtype=torch.float32).cuda()
-    ob, os_, oi, oc = rpn({k: ops.Act.from_nchw(v.cuda()) for k, v in feats.items()}, hw)
+    ob, os_, oi, oc = rpn.forward_device({k: ops.Act.from_nchw(v.cuda()) for k, v in feats.items()}, hw)
     for i in range(2):
         want_b = taps[i]["proposal_boxes"]
         k = int(oc[i].item())
