@@ -18,7 +18,8 @@ NVCC_FLAGS = [
 
 
 # per-file extra flags: the decision kernels round like the fp32 CPU path (no FMA contraction)
-FILE_FLAGS = {"detect.cu": ["--fmad=false"], "roi_align_rotated.cu": ["--fmad=false"], "postprocess.cu": ["--fmad=false"]}
+FILE_FLAGS = {"detect.cu": ["--fmad=false"], "roi_align_rotated.cu": ["--fmad=false"], "postprocess.cu": ["--fmad=false"],
+              "d2_ops.cu": ["--fmad=false"]}
 
 
 def sources():

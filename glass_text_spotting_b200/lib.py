@@ -16,6 +16,7 @@ SYMBOLS = [
     "glass_nms_workspace_bytes",
     "glass_nms_rotated", "glass_box_decode", "glass_gc_attention", "glass_hmean_rows", "glass_lstm_bidir",
     "glass_aster_decode", "glass_aster_finalize", "glass_resize_bilinear_u8", "glass_postprocess_merge", "glass_text_scores", "glass_zero_border", "glass_stem_s2d", "glass_baseline_roi_align_rotated_d2", "glass_mask_finalize", "glass_paste_masks_rotated",
+    "glass_box_iou_rotated", "glass_nms_rotated_all", "glass_nms_rotated_all_workspace_bytes",
 ]
 
 
@@ -158,11 +159,16 @@ def load() -> C.CDLL:
     lib.glass_stem_s2d.argtypes = [p, i, i, i, f, f, p, p, p]
     lib.glass_mask_finalize.argtypes = [p, i, i, i, i, p, p]
     lib.glass_paste_masks_rotated.argtypes = [p, p, i, i, i, i, C.c_float, p, p, p]
+    lib.glass_box_iou_rotated.argtypes = [p, i, p, i, i, p, p]
+    lib.glass_nms_rotated_all_workspace_bytes.argtypes = [i]
+    lib.glass_nms_rotated_all_workspace_bytes.restype = C.c_int64
+    lib.glass_nms_rotated_all.argtypes = [p, p, i, C.c_float, p, p, p, C.c_int64, p]
     lib.glass_baseline_roi_align_rotated_d2.argtypes = [p, i, i, i, i, p, i, C.c_float, i, i, i, p, p]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if name.startswith("glass_") and name not in ("glass_last_error", "glass_abi_version", "glass_launch_count",
-                                                        "glass_nms_workspace_bytes", "glass_rpn_topk_workspace_bytes"):
+                                                        "glass_nms_workspace_bytes", "glass_rpn_topk_workspace_bytes",
+                                                        "glass_nms_rotated_all_workspace_bytes"):
             fn.restype = C.c_int
     _lib = lib
     return lib

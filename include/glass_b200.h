@@ -378,6 +378,26 @@ int glass_paste_masks_rotated(const float* masks, const float* boxes, int k, int
                               uint8_t* out, float* out_soft, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * detectron2 operator surface outside the fused path: what the reference's own Python reaches through
+ * torch.ops.detectron2.* when it is NOT inside the hot path's fused kernels (post-processor, evaluation, user code).
+ * ------------------------------------------------------------------------------------------ */
+/* glass_box_iou_rotated -- pairwise IoU of rotated boxes (cx, cy, w, h, angle_deg): boxes1 fp32 [n1,5], boxes2 [n2,5]
+ * -> out fp32 [n1, n2].  mode 0 replaces torch.ops.detectron2.box_iou_rotated (pairwise_iou_rotated, called at
+ * glass/structures/boxes.py:34); mode 1 = glass.structures.boxes.pairwise_ioa_rotated (:24-49: intersection over the
+ * smaller area, recovered from the IoU in the reference's operation order; call site
+ * glass/postprocess/post_processor_rotated_boxes.py:128). */
+int glass_box_iou_rotated(const float* boxes1, int n1, const float* boxes2, int n2, int mode, float* out, void* stream);
+/* glass_nms_rotated_all -- torch.ops.detectron2.nms_rotated(boxes, scores, iou_threshold) with EVERY survivor returned
+ * (call sites: glass/postprocess/post_processor_rotated_boxes.py:181; batched through coordinate offsets at
+ * glass/modeling/roi_heads/rotated_fast_rcnn.py:131).  boxes fp32 [n,5]; order int64 [n] = indices by descending score
+ * (the caller's sort; detectron2 sorts the same way before its mask kernel); a box is suppressed when its IoU with an
+ * earlier kept box is > iou_thresh.  keep int64 [n]: kept indices in score order, -1 padded; keep_count int32 [1].
+ * No host round trip (detectron2 scans its bitmask on the host). */
+int64_t glass_nms_rotated_all_workspace_bytes(int n);
+int glass_nms_rotated_all(const float* boxes, const int64_t* order, int n, float iou_thresh, int64_t* keep,
+                          int32_t* keep_count, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Benchmark baseline (NOT on the product path): detectron2 v0.6's GPU formulation of rotated RoIAlign restated --
  * fp32 NCHW, one thread per output element, one call per FPN level (ROIPooler).  Timed by bench.py --workload
  * roialign_512 next to glass_roi_align_rotated (BASELINE.json configs[2]: "HBM GB/s vs detectron2 CUDA op").
