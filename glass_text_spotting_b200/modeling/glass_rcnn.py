@@ -33,7 +33,7 @@ class B200GlassRCNN:
     def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda", mode: int = ops.MODE_SPLIT,
                  pixel_mean=PIXEL_MEAN, pixel_std=PIXEL_STD, mask_inference: bool = False,
                  filter_small_boxes: Optional[float] = None, inflate_ratio: Optional[float] = None,
-                 drop_overlapping_boxes=None, **head_kwargs):
+                 drop_overlapping_boxes=None, rpn_kwargs: Optional[dict] = None, **head_kwargs):
         if drop_overlapping_boxes:
             raise NotImplementedError("POST_PROCESSING.DROP_OVERLAPPING raises AttributeError in the reference "
                                       "(post_processor_academic.py:73 -> glass/structures/boxes.py:31); not provided")
@@ -41,7 +41,7 @@ class B200GlassRCNN:
         self.filter_small_boxes, self.inflate_ratio = filter_small_boxes, inflate_ratio
         self.pixel_mean, self.pixel_std = tuple(pixel_mean), tuple(pixel_std)
         self.backbone = B200ResNetFPN(state_dict, device=device, mode=mode, pixel_mean=pixel_mean, pixel_std=pixel_std)
-        self.proposal_generator = B200RotatedRPN(state_dict, device=device, mode=mode)
+        self.proposal_generator = B200RotatedRPN(state_dict, device=device, mode=mode, **(rpn_kwargs or {}))
         self.roi_heads = B200GlassROIHeads(state_dict, device=device, mode=mode, pixel_mean=pixel_mean,
                                            pixel_std=pixel_std, **head_kwargs)
         # MODEL.ROI_MASK_HEAD.MASK_INFERENCE (recognizers_hybrid_head.py:595-601): off in every shipped config
@@ -127,8 +127,10 @@ class B200GlassRCNN:
         for i, c in enumerate(counts_host):
             inst = Instances(il.image_sizes[i],
                              pred_boxes=RotatedBoxes(det["pred_boxes"][i, :c].clone()),
-                             scores=det["scores"][i, :c], pred_classes=torch.zeros(c, dtype=torch.int64, device=self.device),
-                             orientations=det["orientations"][i, :c], pred_text_prob=probs[starts[i]: starts[i + 1]])
+                             scores=det["scores"][i, :c], pred_classes=torch.zeros(c, dtype=torch.int64, device=self.device))
+            if self.roi_heads.orientation_on:    # MODEL.ORIENTATION_ON (rotated_fast_rcnn.py:141-142)
+                inst.orientations = det["orientations"][i, :c]
+            inst.pred_text_prob = probs[starts[i]: starts[i + 1]]
             if masks is not None:
                 inst.pred_masks = masks[starts[i]: starts[i + 1]]
             results.append(inst)

@@ -48,10 +48,16 @@ class B200GlassROIHeads:
         w1 = w1.view(-1, c, r, r).permute(0, 2, 3, 1).reshape(w1.shape[0], -1)
         self.fc1 = packing.pack_linear(w1, sd["box_head.fc1.bias"], device=dev)
         self.fc2 = packing.pack_linear(sd["box_head.fc2.weight"], sd["box_head.fc2.bias"], device=dev)
-        wp = torch.cat((sd["box_predictor.cls_score.weight"], sd["box_predictor.bbox_pred.weight"],
-                        sd["box_predictor.orientation_pred.weight"]), 0)
-        bp = torch.cat((sd["box_predictor.cls_score.bias"], sd["box_predictor.bbox_pred.bias"],
-                        sd["box_predictor.orientation_pred.bias"]), 0)
+        # MODEL.ORIENTATION_ON False (configs/glass_finetune_textocr.yaml:106): RotatedFastRCNNOutputLayers has no
+        # orientation_pred (rotated_fast_rcnn.py:547-549) and the results carry no ``orientations`` field (:141-142);
+        # the fused predictor keeps its 11 columns with zero orientation weights so the kernels see one layout.
+        self.orientation_on = "box_predictor.orientation_pred.weight" in sd
+        if self.orientation_on:
+            wo, bo = sd["box_predictor.orientation_pred.weight"], sd["box_predictor.orientation_pred.bias"]
+        else:
+            wo, bo = torch.zeros((4, sd["box_predictor.cls_score.weight"].shape[1])), torch.zeros((4,))
+        wp = torch.cat((sd["box_predictor.cls_score.weight"], sd["box_predictor.bbox_pred.weight"], wo), 0)
+        bp = torch.cat((sd["box_predictor.cls_score.bias"], sd["box_predictor.bbox_pred.bias"], bo), 0)
         assert wp.shape[0] == 11, "one foreground class (configs/glass_pretrain.yaml:79)"
         self.predictor = packing.pack_linear(wp, bp, n_align=16, device=dev)
 
@@ -200,10 +206,12 @@ class B200GlassROIHeads:
         det = self.forward_box(features, pb, counts, img_hw)
         instances = []
         for i, c in enumerate(det["count"].cpu().tolist()):
-            instances.append(Instances(images.image_sizes[i], pred_boxes=RotatedBoxes(det["pred_boxes"][i, :c].clone()),
-                                       scores=det["scores"][i, :c].clone(),
-                                       pred_classes=torch.zeros(c, dtype=torch.int64, device=self.device),
-                                       orientations=det["orientations"][i, :c].clone()))
+            inst = Instances(images.image_sizes[i], pred_boxes=RotatedBoxes(det["pred_boxes"][i, :c].clone()),
+                             scores=det["scores"][i, :c].clone(),
+                             pred_classes=torch.zeros(c, dtype=torch.int64, device=self.device))
+            if self.orientation_on:
+                inst.orientations = det["orientations"][i, :c].clone()
+            instances.append(inst)
         return self.forward_with_given_boxes(images, features, instances), {}
 
     __call__ = forward

@@ -76,3 +76,22 @@ def test_postprocess_options_apply_after_the_device_path(model_and_inputs):
         assert g.image_size == w.image_size and torch.equal(g.pred_boxes.tensor, w.pred_boxes.tensor)
         assert torch.equal(g.pred_text_prob, w.pred_text_prob)
         assert bool((torch.min(g.pred_boxes.tensor[:, 2], g.pred_boxes.tensor[:, 3]) > 0).all())
+
+
+def test_checkpoint_without_orientation_head(model_and_inputs):
+    """MODEL.ORIENTATION_ON False (configs/glass_finetune_textocr.yaml:106): no box_predictor.orientation_pred in the
+    checkpoint, no ``orientations`` in the results (rotated_fast_rcnn.py:141-142, 547-549); everything else unchanged."""
+    from glass_text_spotting_b200.modeling.glass_rcnn import B200GlassRCNN
+    from oracle import model as om
+    model, inputs = model_and_inputs
+    want = _snapshot(model.inference(inputs, do_postprocess=False))
+    o = om.build_oracle(seed=5, calib_images=[inputs[0]["image"]], cfg=om.HotPathConfig(max_detections_override=6))
+    sd = {k: v for k, v in o.state_dict().items() if "orientation_pred" not in k}
+    assert len(sd) == len(o.state_dict()) - 2
+    plain = B200GlassRCNN(sd, detections_per_image=6)
+    assert plain.roi_heads.orientation_on is False and model.roi_heads.orientation_on is True
+    got = plain.inference(inputs, do_postprocess=False)
+    for g, w in zip(got, want):
+        assert not g.has("orientations") and "orientations" in w
+        assert torch.equal(g.pred_boxes.tensor, w["pred_boxes"]) and torch.equal(g.scores, w["scores"])
+        assert torch.equal(g.pred_text_prob, w["pred_text_prob"])
