@@ -148,3 +148,19 @@ def make_meta_postprocess_inputs(seed: int, n: int, hw):
     boxes = torch.stack((cx, cy, bw, bh, ang), 1).float()
     scores = torch.rand(n, generator=g)
     return boxes, scores
+
+
+def make_recognizer_branch_inputs(seed: int, k: int, hw=(96, 160)):
+    """Seeded inputs of MaskRotatedRecognizerHybridHead._forward_recognizer (recognizers_hybrid_head.py:513-569):
+    the normalised image [3,H,W], p2 [1,256,H/4,W/4], p3 [1,256,H/8,W/8] and k detected boxes inside the image."""
+    g = torch.Generator().manual_seed(8000 + seed)
+    h, w = hw
+    image = torch.randn(3, h, w, generator=g) * 5.0   # keeps every activation of the seeded branch below ~1e3
+    p2 = torch.randn(1, 256, h // 4, w // 4, generator=g)
+    p3 = torch.randn(1, 256, h // 8, w // 8, generator=g)
+    cx = 20 + torch.rand(k, generator=g) * (w - 40)
+    cy = 15 + torch.rand(k, generator=g) * (h - 30)
+    bw = 24 + torch.rand(k, generator=g) * 70
+    bh = 8 + torch.rand(k, generator=g) * 20
+    ang = (torch.rand(k, generator=g) - 0.5) * 90
+    return image, p2, p3, torch.stack((cx, cy, bw, bh, ang), 1).float()

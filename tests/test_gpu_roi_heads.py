@@ -163,3 +163,37 @@ def test_box_inference_matches_reference_golden(glass_lib, i):
     got_o = cand_o[0][index[0, :k].long()].cpu()
     assert torch.equal(got_o[:, 0], c["orientations"][:, 0])
     assert torch.allclose(got_o[:, 1], c["orientations"][:, 1], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("i", [0, 1, 3])
+def test_recognizer_branch_matches_reference_golden(glass_lib, i):
+    """B200GlassROIHeads.forward_recognizer against golden vectors written by the reference's OWN
+    ``MaskRotatedRecognizerHybridHead._forward_recognizer`` + ``RecognizerRCNNHeadV3`` (tests/golden/recognizer_branch.pt,
+    tools/make_golden_recognizer_branch.py): the wiring of rows a9-a16 on the device, incl. the early break (case 3)."""
+    import os
+    from golden_common import force_eos_bias, make_recognizer_branch_inputs, seeded_fill
+    from glass_text_spotting_b200 import ops
+    from glass_text_spotting_b200.modeling.roi_heads import B200GlassROIHeads
+    from oracle import model as om
+    c = torch.load(os.path.join(os.path.dirname(__file__), "golden", "recognizer_branch.pt"), weights_only=False)["cases"][i]
+    o = om.GlassOracle()     # only a container of correctly named parameters here; the golden is the checker
+    for j, name in enumerate(("recognizer_feature_fusion", "hybrid_net", "fusion_net", "recognizer_head")):
+        seeded_fill(getattr(o.roi_heads, name), 500 + 10 * c["seed"] + j)
+    if c["eos"]:
+        with torch.no_grad():
+            force_eos_bias(o.roi_heads.recognizer_head.decoder.recognizer)
+            o.roi_heads.recognizer_head.decoder.recognizer.decoder.fc.bias[0] += 2.2
+    image, p2, p3, boxes = make_recognizer_branch_inputs(c["seed"], c["k"])
+    # the golden image is already normalised: mean 0 / std 1 make the fused normalisation the identity
+    heads = B200GlassROIHeads(o.state_dict(), pixel_mean=(0.0, 0.0, 0.0), pixel_std=(1.0, 1.0, 1.0))
+    k = c["k"]
+    rois = torch.cat((torch.zeros(k, 1), boxes), 1).contiguous().cuda()
+    word_start = torch.tensor([0, k], dtype=torch.int32).cuda()
+    feats = {"p2": ops.Act.from_nchw(p2.cuda()), "p3": ops.Act.from_nchw(p3.cuda())}
+    probs = heads.forward_recognizer(image[None].contiguous().cuda(), tuple(image.shape[-2:]), feats, rois, word_start, 1)
+    torch.cuda.synchronize()
+    want = c["pred_text_prob"]
+    assert tuple(probs.shape) == tuple(want.shape)
+    assert torch.equal((probs.cpu().sum(2) > 0).sum(1), (want.sum(2) > 0).sum(1)), "early break at a different step"
+    assert torch.equal(probs.cpu().argmax(2), want.argmax(2))
+    close(probs, want, f"case {i} pred_text_prob vs the reference", atol=1e-5)
