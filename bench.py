@@ -597,6 +597,52 @@ def run_totaltext(args):
         dist.destroy_process_group()
 
 
+def _roialign_glass_shapes(rois_d, flush, reps: int = 10):
+    """SURVEY.md 8d cfg 3, second half: the two GLASS-specific poolers on the first 100 RoIs of the cfg-3 set --
+    the recognizer pooler ([100,256,8,32], ADAPTIVE grid ceil(roi/bins), on the 256^2 P2P3 map; a10) and the image pooler
+    ([100,3,128,128], sampling 2, normalisation fused, on the 1024^2 image; a11).  Single launches after an L2 flush.
+    Bytes = output written (in the kernel's own storage format) + the RoIs' footprint on the input, clipped to it."""
+    import torch
+    from glass_text_spotting_b200 import ops
+    from glass_text_spotting_b200.ops import Act
+    k = rois_d.shape[0]
+    g = torch.Generator().manual_seed(1)
+    gmap = Act.from_nchw(torch.randn(1, 256, 256, 256, generator=g).cuda())
+    image = torch.randint(0, 256, (1, 3, 1024, 1024), generator=g).float().cuda()
+    fused = Act(k, 512, 8, 32)          # [local | global]: the pooler writes channels 256..511 (roi_heads.forward_recognizer)
+    crops = Act(k, 3, 128, 128, 1, 8)
+
+    def recog():
+        ops.roi_align_rotated([gmap], rois_d, (8, 32), [0.25], 0, out_f32=False,
+                              out_split=(fused.buf, fused.hp, fused.wp, fused.border, 256, fused.cp))
+
+    def img():
+        ops.image_roi_align_rotated(image, (1024, 1024), (103.530, 116.280, 123.675), (1.0, 1.0, 1.0), rois_d, (128, 128), 2,
+                                    out_act=crops)
+
+    r = rois_d.cpu()
+    area = (r[:, 3].clamp(max=1024) * r[:, 4].clamp(max=1024)).sum().item()      # px^2 on the image
+    out = {}
+    for name, fn, nbytes in (
+            ("recognizer_pooler_100x256x8x32_adaptive", recog, k * 256 * 8 * 32 * 4 + area / 16 * 256 * 4),
+            ("image_pooler_100x3x128x128", img, k * 128 * 128 * 8 * 4 + area * 3 * 4)):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = sorted(ts)[len(ts) // 2]
+        out[name] = {"ms": ms, "bytes": int(nbytes), "gbs": nbytes / (ms / 1e3) / 1e9}
+    return out
+
+
 def run_roialign(args):
     """BASELINE.json configs[2].  Timed region = K back-to-back launches (CUDA events on the launching stream), each
     on the NEXT of 4 copies of the feature pyramid (4 x 91 MB of split-fp16 maps + 4 x 26 MB of outputs >> 126 MB L2), so
@@ -680,6 +726,7 @@ def run_roialign(args):
     b1.record()
     torch.cuda.synchronize()
     d2_ms = b0.elapsed_time(b1) / nb
+    glass_shapes = _roialign_glass_shapes(rois_d[:100].contiguous(), flush)
     print(json.dumps({
         "metric": "RotatedROIAlign GB/s (algorithmic bytes)", "value": gbs, "unit": "GB/s", "n_gpus": 1, "steps": args.steps,
         "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -692,6 +739,7 @@ def run_roialign(args):
                    "single_launch_l2_flushed_gbs": nbytes / (ms_flushed / 1e3) / 1e9,
                    "d2_style_baseline_ms": d2_ms, "d2_style_baseline_gbs": nbytes / (d2_ms / 1e3) / 1e9,
                    "speedup_vs_d2_style": d2_ms / ms,
+                   "glass_shapes": glass_shapes,
                    "d2_style_baseline": "detectron2 v0.6 ROIPooler + ROIAlignRotated CUDA formulation restated "
                                         "(csrc/baseline_d2.cu: fp32 NCHW, one thread per output element, one launch per "
                                         "level); detectron2 itself cannot be built offline"},
