@@ -15,9 +15,8 @@ and keeps every decision on the device.  These wrappers are the drop-in for code
 (the reference's post-processor, evaluation and user scripts): NCHW fp32 in, NCHW fp32 out, device tensors only.
 There is no CPU path: a CPU tensor raises.
 """
-import ctypes as C
 import math
-from typing import List, Sequence, Tuple, Union
+from typing import List, Sequence, Union
 
 import torch
 
@@ -197,4 +196,4 @@ class ROIPooler:
 
 __all__ = ["box_iou_rotated", "pairwise_iou_rotated", "pairwise_ioa_rotated", "nms_rotated", "batched_nms_rotated",
            "roi_align_rotated_forward", "ROIAlignRotated", "ROIPooler", "convert_boxes_to_pooler_format"]
-_ = (C, Tuple)
+

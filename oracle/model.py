@@ -5,7 +5,7 @@ End-to-end CPU restatement of GLASS inference for ``configs/glass_pretrain.yaml`
 recorded, plus the seeded weight factory (d2-style ``state_dict`` names, A.10) with
 BatchNorm calibration.
 """
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch

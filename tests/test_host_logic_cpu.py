@@ -1,6 +1,5 @@
 """CPU tests of the host-side logic (no GPU): weight packing layouts, structures, post-processing --
 each checked against the oracle / plain torch on the same inputs."""
-import math
 
 import pytest
 import torch

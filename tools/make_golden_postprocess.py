@@ -10,12 +10,10 @@ the thresholds -- is the reference's code, unmodified.
     python tools/make_golden_postprocess.py
 """
 import importlib.util
-import math
 import os
 import sys
 import types
 
-import numpy as np
 import torch
 import yaml
 
