@@ -903,7 +903,7 @@ def run_b200(args):
         cfg = {"workload": wl["desc"], "global_batch": world * B, "parallelism": f"image-sharded x{world}",
                "l2": "inputs rotated between 2 batches; per-step working set (GBs of activations) >> 126 MB L2",
                "weights": "random init (seeded), BatchNorm folded",
-               "kb_per_chunk": ops.KB_PER_CHUNK or 2}
+               "kb_per_chunk": ops.KB_PER_CHUNK or "2 (backbone, RPN, box head), 4 (per-word recognizer convs)"}
         if full:
             cfg["words_per_step"] = words_per_step
             cfg["collective"] = "one NCCL all-gather of packed detection records per step" if world > 1 else "none (N=1)"

@@ -151,7 +151,7 @@ def conv_gemm(a_hi: torch.Tensor, a_lo: Optional[torch.Tensor], rows_a: int, k_p
     p.out_hi, p.out_lo, p.out_f32 = _ptr(out_hi), _ptr(out_lo), _ptr(out_f32)
     p.out_hp, p.out_wp, p.out_border = out_geom
     p.ld_out, p.ld_f32, p.n_store = ld_out, ld_f32, n_store
-    p.kb_per_chunk = KB_PER_CHUNK
+    p.kb_per_chunk = KB_PER_CHUNK or getattr(w, "kb_per_chunk", 0)   # env override > per-weight choice > library default
     p.pair_mode = PAIR_MODE if (PAIR_MODE != 2 or w.n_p % 32 == 0) else 0
     p.tap_mode = TAP_MODE
     p.a_col0, p.a_inner = a_col0, a_inner
