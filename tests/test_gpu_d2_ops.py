@@ -165,3 +165,27 @@ def test_cpu_tensors_are_refused(d2):
         d2.nms_rotated(b, torch.ones(1), 0.5)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         d2.roi_align_rotated_forward(torch.zeros(1, 4, 8, 8), torch.zeros(1, 6), 1.0, 2, 2, 2)
+
+
+@pytest.mark.parametrize("rot", [0, 90, 180])
+def test_nms_rotated_d2_kat_rotations(d2, rot):
+    """detectron2 tests/layers/test_nms_rotated.py: all boxes rotated by 90 degrees (w/h swapped) or 180 keep the same
+    indices as torchvision.ops.nms / batched_nms on the axis-aligned boxes (same fixture as tests/test_oracle_d2_ops.py)."""
+    import torchvision
+    g = torch.Generator().manual_seed(3)
+    n = 200
+    x0, y0 = torch.rand(n, generator=g) * 100, torch.rand(n, generator=g) * 100
+    w, h = torch.rand(n, generator=g) * 40 + 1, torch.rand(n, generator=g) * 40 + 1
+    boxes = torch.stack([x0, y0, x0 + w, y0 + h], 1)
+    scores = torch.rand(n, generator=g)
+    r = torch.zeros(n, 5)
+    r[:, 0], r[:, 1] = (boxes[:, 0] + boxes[:, 2]) / 2, (boxes[:, 1] + boxes[:, 3]) / 2
+    r[:, 2], r[:, 3] = boxes[:, 2] - boxes[:, 0], boxes[:, 3] - boxes[:, 1]
+    if rot == 90:
+        r[:, 2], r[:, 3] = r[:, 3].clone(), r[:, 2].clone()
+    r[:, 4] = rot
+    for thr in [0.2, 0.5, 0.8]:
+        assert torch.equal(d2.nms_rotated(r.cuda(), scores.cuda(), thr).cpu(), torchvision.ops.nms(boxes, scores, thr)), (rot, thr)
+    idxs = torch.randint(0, 4, (n,), generator=g)
+    assert torch.equal(d2.batched_nms_rotated(r.cuda(), scores.cuda(), idxs.cuda(), 0.5).cpu(),
+                       torchvision.ops.batched_nms(boxes, scores, idxs, 0.5))

@@ -143,3 +143,48 @@ def test_rotated_cell_anchors_match_oracle():
 def test_backbone_flop_count_matches_survey():
     from glass_text_spotting_b200.modeling.backbone import B200ResNetFPN
     assert abs(B200ResNetFPN.flops_per_image(1024, 1024) / 1e9 - 279.94) < 0.1   # 161.16 + 118.78
+
+
+def test_d2_ops_surface_validates_on_the_host():
+    """glass_text_spotting_b200.d2_ops keeps detectron2's names and argument checks; CPU tensors are refused before any
+    library call (no fallback path)."""
+    import pytest
+    from glass_text_spotting_b200 import d2_ops
+    from glass_text_spotting_b200.structures import RotatedBoxes
+    for name in ("ROIPooler", "ROIAlignRotated", "roi_align_rotated_forward", "nms_rotated", "batched_nms_rotated",
+                 "box_iou_rotated", "pairwise_iou_rotated", "pairwise_ioa_rotated"):
+        assert hasattr(d2_ops, name)
+    p = d2_ops.ROIPooler(output_size=7, scales=[1 / 4, 1 / 8, 1 / 16, 1 / 32, 1 / 64], sampling_ratio=2,
+                         pooler_type="ROIAlignRotated")
+    assert (p.min_level, p.max_level, p.output_size) == (2, 6, (7, 7))
+    assert d2_ops.ROIPooler([8, 32], (1 / 4,), 0, "ROIAlignRotated").output_size == (8, 32)      # recognizers_hybrid_head.py:464
+    with pytest.raises(ValueError, match="Unknown pooler type"):
+        d2_ops.ROIPooler(7, [0.25], 2, pooler_type="ROIAlignV2")
+    with pytest.raises(AssertionError, match="power of 2"):
+        d2_ops.ROIPooler(7, [0.3], 2)
+    with pytest.raises(AssertionError, match="pyramid"):
+        d2_ops.ROIPooler(7, [1 / 4, 1 / 16], 2)
+    b = torch.tensor([[5.0, 5.0, 4.0, 2.0, 0.0]])
+    with pytest.raises(AssertionError, match="lists"):
+        p(torch.zeros(1, 4, 8, 8), [RotatedBoxes(b)])
+    for call in (lambda: d2_ops.box_iou_rotated(b, b), lambda: d2_ops.nms_rotated(b, torch.ones(1), 0.5),
+                 lambda: d2_ops.pairwise_ioa_rotated(b, b),
+                 lambda: d2_ops.roi_align_rotated_forward(torch.zeros(1, 4, 8, 8), torch.zeros(1, 6), 1.0, 2, 2, 2),
+                 lambda: p([torch.zeros(1, 4, s, s) for s in (64, 32, 16, 8, 4)], [RotatedBoxes(b)])):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            call()
+    fmt = d2_ops.convert_boxes_to_pooler_format([RotatedBoxes(b), RotatedBoxes(torch.cat((b, b + 1)))])
+    assert fmt.shape == (3, 6) and fmt[:, 0].tolist() == [0.0, 1.0, 1.0]
+
+
+def test_glass_rcnn_module_signatures_match_the_reference_call_sites():
+    """glass_rcnn.py:88, :93, :96 call the sub-modules positionally; the B200 modules must accept exactly that."""
+    import inspect
+    from glass_text_spotting_b200.modeling.glass_rcnn import B200GlassRCNN
+    from glass_text_spotting_b200.modeling.roi_heads import B200GlassROIHeads
+    from glass_text_spotting_b200.modeling.rpn import B200RotatedRPN
+    assert list(inspect.signature(B200RotatedRPN.forward).parameters) == ["self", "images", "features", "gt_instances"]
+    assert list(inspect.signature(B200GlassROIHeads.forward).parameters) == ["self", "images", "features", "proposals", "targets"]
+    assert list(inspect.signature(B200GlassROIHeads.forward_with_given_boxes).parameters) == ["self", "images", "features", "instances"]
+    assert list(inspect.signature(B200GlassRCNN.inference).parameters)[:4] == ["self", "batched_inputs", "detected_instances", "do_postprocess"]
+    assert B200GlassRCNN.__call__ is B200GlassRCNN.forward and B200GlassROIHeads.__call__ is B200GlassROIHeads.forward
