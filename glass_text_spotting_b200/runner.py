@@ -21,6 +21,7 @@ class B200GlassRunner:
         # defaults: configs/glass_finetune_totaltext.yaml:22-25 (INFERENCE_TH_TEST block)
         self.min_target_size, self.max_target_size = min_target_size, max_target_size
         self.max_upscale_ratio, self.input_format, self.device = max_upscale_ratio, input_format, device
+        assert self.input_format in ["RGB", "BGR", "GREY"], self.input_format      # glass_runner.py:66
         self.model = B200GlassRCNN(state_dict, device=device, **model_kwargs)
         self.text_decoder = TextDecoder()
         # build_post_processor(cfg) (glass_runner.py:70); pass None to get the raw detections
@@ -36,7 +37,13 @@ class B200GlassRunner:
         return 1
 
     def image_to_tensor(self, original_image: np.ndarray):
-        """glass_runner.py:123-148, on the device (uint8 H2D, then one resize/convert kernel)."""
+        """glass_runner.py:83-87 (channel order / greyscale) + :123-148 (resize), on the device: uint8 H2D, then one
+        resize/convert kernel (the RGB flip is fused into it; the greyscale conversion is the reference's uint8 numpy
+        expression, glass/utils/common_utils.py:38-41, applied before the upload)."""
+        if self.input_format == "GREY":
+            grey = np.uint8(0.2125 * original_image[:, :, 0] + 0.7154 * original_image[:, :, 1]
+                            + 0.0721 * original_image[:, :, 2])
+            original_image = np.repeat(grey[:, :, None], 3, axis=2)
         h, w = original_image.shape[:2]
         scale = self.get_inference_scale_ratio(original_image.shape)
         nh, nw = (int(np.round(scale * h)), int(np.round(scale * w))) if scale != 1 else (h, w)

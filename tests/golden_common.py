@@ -164,3 +164,17 @@ def make_recognizer_branch_inputs(seed: int, k: int, hw=(96, 160)):
     bh = 8 + torch.rand(k, generator=g) * 20
     ang = (torch.rand(k, generator=g) - 0.5) * 90
     return image, p2, p3, torch.stack((cx, cy, bw, bh, ang), 1).float()
+
+
+def make_runner_case(seed: int, hw):
+    """A uint8 HWC image and model-space detections for the GlassRunner flow (glass/inference/glass_runner.py:72-109)."""
+    import numpy as np
+    rng = np.random.RandomState(9000 + seed)
+    image = rng.randint(0, 256, size=tuple(hw) + (3,), dtype=np.uint8)
+    g = torch.Generator().manual_seed(9000 + seed)
+    n = 7
+    boxes = torch.stack((torch.rand(n, generator=g) * hw[1], torch.rand(n, generator=g) * hw[0],
+                         4 + torch.rand(n, generator=g) * 30, 3 + torch.rand(n, generator=g) * 10,
+                         (torch.rand(n, generator=g) - 0.5) * 60), 1).float()
+    scores = torch.rand(n, generator=g)
+    return image, boxes, scores
