@@ -14,7 +14,10 @@ not installable offline.  The oracle is therefore pinned by
   * golden vectors generated in the authoring container by importing the reference's
     own pure-torch modules from /root/reference (tools/make_golden.py ->
     tests/golden/*.pt; checked by tests/test_oracle_golden.py), including the box branch's inference
-    (tools/make_golden_box_inference.py), the word post-processor, the evaluator formats and the mask paste.
+    (tools/make_golden_box_inference.py), the recognizer branch end to end through the reference's own
+    ``_forward_recognizer`` + ``RecognizerRCNNHeadV3`` (tools/make_golden_recognizer_branch.py), GlassRCNN's
+    ``_postprocess`` / ``detector_postprocess`` (tools/make_golden_meta_postprocess.py), the word post-processor,
+    the evaluator formats, the GlassRunner flow and the mask paste.
 The detectron2-recalled parts (backbone wiring, RPN, poolers) have no reference-run
 pin: for them parity is "unpinned beyond the upstream KATs" (see DESIGN.md).
 """
