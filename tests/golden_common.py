@@ -178,3 +178,20 @@ def make_runner_case(seed: int, hw):
                          (torch.rand(n, generator=g) - 0.5) * 60), 1).float()
     scores = torch.rand(n, generator=g)
     return image, boxes, scores
+
+
+def make_box_branch_inputs(seed: int, r: int, hw=(128, 160)):
+    """Seeded FPN maps p2..p6 of one image and r proposals for the box branch (recognizers_hybrid_head.py:291-339)."""
+    g = torch.Generator().manual_seed(9500 + seed)
+    h, w = hw
+    feats = {f"p{k}": torch.randn(1, 256, math.ceil(h / 2 ** k), math.ceil(w / 2 ** k), generator=g) for k in range(2, 7)}
+    cx = torch.rand(r, generator=g) * w
+    cy = torch.rand(r, generator=g) * h
+    bw = torch.exp(torch.rand(r, generator=g) * math.log(10.0)) * 12.0
+    bh = bw * (0.15 + 0.6 * torch.rand(r, generator=g))
+    ang = (torch.rand(r, generator=g) - 0.5) * 180.0
+    props = torch.stack((cx, cy, bw, bh, ang), 1).float()
+    k = r // 3                       # near-duplicates so that the rotated NMS has something to suppress
+    props[k:2 * k] = props[:k] + torch.randn(k, 5, generator=g) * torch.tensor([1.0, 1.0, 0.8, 0.5, 2.0])
+    props[:, 2:4] = props[:, 2:4].clamp_min(2.0)
+    return feats, props, hw

@@ -197,3 +197,34 @@ def test_recognizer_branch_matches_reference_golden(glass_lib, i):
     assert torch.equal((probs.cpu().sum(2) > 0).sum(1), (want.sum(2) > 0).sum(1)), "early break at a different step"
     assert torch.equal(probs.cpu().argmax(2), want.argmax(2))
     close(probs, want, f"case {i} pred_text_prob vs the reference", atol=1e-5)
+
+
+@pytest.mark.parametrize("i", [0, 2])
+def test_box_branch_matches_reference_golden(glass_lib, i):
+    """B200GlassROIHeads.forward_box against golden vectors written by the reference's OWN ``_forward_box`` +
+    ``RotatedFastRCNNOutputLayers`` + ``RotatedFastRCNNOutputs.inference`` (tests/golden/box_branch.pt,
+    tools/make_golden_box_branch.py): rows a5-a8 wired together on the device, free-running from its own logits."""
+    import os
+    from golden_common import make_box_branch_inputs, seeded_fill
+    from glass_text_spotting_b200 import ops
+    from glass_text_spotting_b200.modeling.roi_heads import B200GlassROIHeads
+    from oracle import model as om
+    c = torch.load(os.path.join(os.path.dirname(__file__), "golden", "box_branch.pt"), weights_only=False)["cases"][i]
+    o = om.GlassOracle()     # a container of correctly named parameters; the golden is the checker
+    seeded_fill(o.roi_heads.box_head, 700 + c["seed"])
+    seeded_fill(o.roi_heads.box_predictor, 710 + c["seed"])
+    with torch.no_grad():
+        o.roi_heads.box_predictor.cls_score.weight.mul_(4.0)
+        o.roi_heads.box_predictor.bbox_pred.weight.mul_(0.3)
+    feats, proposals, hw = make_box_branch_inputs(c["seed"], c["r"])
+    heads = B200GlassROIHeads(o.state_dict(), detections_per_image=c["detections"])
+    det = heads.forward_box({k: ops.Act.from_nchw(v.cuda()) for k, v in feats.items()}, proposals[None].contiguous().cuda(),
+                            torch.tensor([c["r"]], dtype=torch.int32).cuda(),
+                            torch.tensor([list(hw)], dtype=torch.float32).cuda())
+    torch.cuda.synchronize()
+    k = int(det["count"][0])
+    assert k == len(c["scores"])
+    close(det["pred_boxes"][0, :k], c["pred_boxes"], f"case {i} boxes vs the reference")
+    close(det["scores"][0, :k], c["scores"], f"case {i} scores vs the reference", atol=1e-5)
+    assert torch.equal(det["orientations"][0, :k, 0].cpu(), c["orientations"][:, 0])
+    close(det["orientations"][0, :k, 1], c["orientations"][:, 1], f"case {i} orientation prob", atol=1e-5)
