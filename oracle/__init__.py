@@ -18,6 +18,9 @@ not installable offline.  The oracle is therefore pinned by
     ``_forward_recognizer`` + ``RecognizerRCNNHeadV3`` (tools/make_golden_recognizer_branch.py), GlassRCNN's
     ``_postprocess`` / ``detector_postprocess`` (tools/make_golden_meta_postprocess.py), the word post-processor,
     the evaluator formats, the GlassRunner flow and the mask paste.
+    The box branch end to end likewise (tools/make_golden_box_branch.py).
 The detectron2-recalled parts (backbone wiring, RPN, poolers) have no reference-run
-pin: for them parity is "unpinned beyond the upstream KATs" (see DESIGN.md).
+pin: for them parity is "unpinned beyond the upstream KATs"  -- plus, for
+the ResNet-50 / FPN wiring, a cross-check against torchvision's independent
+implementations of the same architectures (tests/test_oracle_backbone_torchvision.py).
 """
