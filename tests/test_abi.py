@@ -90,3 +90,14 @@ def test_ops_reject_cpu_tensors(built_lib):
     from glass_text_spotting_b200 import ops
     with pytest.raises(RuntimeError, match="CUDA"):
         ops.Act.from_nchw(torch.zeros(1, 3, 4, 4))
+
+
+def test_integration_doc_stub_matches_the_binding():
+    """INTEGRATION.md shows the ctypes stub a reference maintainer would add; its struct must be the header's."""
+    from glass_text_spotting_b200 import lib
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blk = doc[doc.index("class _RoiAlignParams"):doc.index("def roi_align_rotated_forward")]
+    assert re.findall(r'\("(\w+)"', blk) == [f[0] for f in lib.RoiAlignParams._fields_]
+    assert re.findall(r'\("(\w+)"', blk) == _struct_fields("GlassRoiAlignParams")
+    for sym in ("glass_roi_align_rotated", "glass_nms_rotated_all", "glass_box_iou_rotated", "glass_postprocess_merge"):
+        assert sym in doc and sym in _declared_symbols()
