@@ -226,10 +226,18 @@ def model_kwargs(cfg: CfgNode) -> Dict[str, Any]:
     return kw
 
 
+def _state_dict(cfg: CfgNode, state_dict_or_path):
+    if isinstance(state_dict_or_path, (str, os.PathLike)):
+        from .weights import load_checkpoint
+        return load_checkpoint(str(state_dict_or_path), mask=bool(cfg.MODEL.ROI_MASK_HEAD.MASK_INFERENCE))
+    return state_dict_or_path
+
+
 def build_model(cfg: CfgNode, state_dict, device="cuda"):
-    """detectron2 ``build_model(cfg)`` + checkpoint load, in one step (weights are packed at construction)."""
+    """detectron2 ``build_model(cfg)`` + ``DetectionCheckpointer.load``, in one step (weights are packed at
+    construction).  ``state_dict`` is a d2-style state_dict or the path of a ``.pth`` checkpoint."""
     from .modeling.glass_rcnn import B200GlassRCNN
-    return B200GlassRCNN(state_dict, device=device, **model_kwargs(cfg))
+    return B200GlassRCNN(_state_dict(cfg, state_dict), device=device, **model_kwargs(cfg))
 
 
 def post_processing_config(cfg: CfgNode):
@@ -257,7 +265,7 @@ def build_runner(cfg: CfgNode, state_dict, device="cuda", post_process: bool = T
     """GlassRunner(model_path, config_path, post_process) (glass/inference/glass_runner.py:24-70)."""
     from .runner import B200GlassRunner
     from .text import TextDecoder
-    runner = B200GlassRunner(state_dict, min_target_size=int(cfg.INPUT.MIN_SIZE_TEST),
+    runner = B200GlassRunner(_state_dict(cfg, state_dict), min_target_size=int(cfg.INPUT.MIN_SIZE_TEST),
                              max_target_size=int(cfg.INPUT.MAX_SIZE_TEST),
                              max_upscale_ratio=float(cfg.INPUT.MAX_UPSCALE_RATIO), input_format=cfg.INPUT.FORMAT,
                              device=device, post_processor=build_post_processor(cfg) if post_process else None,

@@ -175,3 +175,48 @@ def random_mask_head_state_dict(seed: int = 0, prefix: str = "roi_heads.mask_hea
     sd[prefix + "predictor.weight"] = torch.randn(1, 256, 1, 1, generator=g) * 0.5
     sd[prefix + "predictor.bias"] = torch.zeros(1)
     return sd
+
+
+# ------------------------------------------------------------------------------------------ released checkpoints
+_BASE_KEYS = None
+
+
+def required_keys(orientation: bool = True, mask: bool = False):
+    """Parameter names the inference path reads (the detectron2 / GLASS names of SURVEY.md A.10)."""
+    global _BASE_KEYS
+    if _BASE_KEYS is None:
+        _BASE_KEYS = frozenset(random_state_dict(0).keys())
+    keys = set(_BASE_KEYS)
+    if not orientation:
+        keys = {k for k in keys if "orientation_pred" not in k}
+    if mask:
+        keys |= set(random_mask_head_state_dict(0).keys())
+    return keys
+
+
+def load_checkpoint(path: str, mask: bool = False) -> Dict[str, torch.Tensor]:
+    """What ``DetectionCheckpointer(model).load(path)`` does for a ``.pth`` file (glass/inference/glass_runner.py:58-60):
+    read the ``"model"`` entry (or a bare state_dict), drop a DataParallel ``module.`` prefix, turn numpy arrays into
+    tensors, and check that every parameter the inference path reads is there -- naming the missing ones instead of
+    failing somewhere inside weight packing.  Keys the inference path does not read (training-only heads, mask head when
+    ``mask`` is False, ``num_batches_tracked``) are dropped.  A checkpoint without ``box_predictor.orientation_pred``
+    (MODEL.ORIENTATION_ON false) is accepted."""
+    if not str(path).endswith((".pth", ".pt")):
+        raise ValueError(f"{path}: only torch checkpoints (.pth) are supported; convert Caffe2 .pkl weights with detectron2")
+    ckpt = torch.load(path, map_location="cpu", weights_only=False)
+    sd = ckpt["model"] if isinstance(ckpt, dict) and "model" in ckpt and isinstance(ckpt["model"], dict) else ckpt
+    if not isinstance(sd, dict):
+        raise ValueError(f"{path}: no state_dict found (expected a dict or a dict under 'model')")
+    out = {}
+    for k, v in sd.items():
+        if k.startswith("module."):
+            k = k[len("module."):]
+        if k.endswith("num_batches_tracked"):
+            continue
+        out[k] = v if isinstance(v, torch.Tensor) else torch.as_tensor(v)
+    orientation = "roi_heads.box_predictor.orientation_pred.weight" in out
+    need = required_keys(orientation=orientation, mask=mask)
+    missing = sorted(need - set(out))
+    if missing:
+        raise KeyError(f"{path}: {len(missing)} parameters of the GLASS inference path are missing, e.g. {missing[:5]}")
+    return {k: out[k].detach().float() for k in need}

@@ -24,3 +24,32 @@ def test_oracle_loads_product_weights():
     o = om.GlassOracle()
     missing, unexpected = o.load_state_dict(weights.random_state_dict(1), strict=False)
     assert not unexpected and all(k.endswith("num_batches_tracked") for k in missing)
+
+
+def test_load_checkpoint_d2_format(tmp_path):
+    """A DetectionCheckpointer-style .pth ({"model": state_dict, ...}) loads by name; problems are named."""
+    import numpy as np
+    import pytest
+    from glass_text_spotting_b200 import weights
+    sd = weights.random_state_dict(2)
+    ck = {"model": {("module." + k): (v.numpy() if i % 2 else v) for i, (k, v) in enumerate(sd.items())},
+          "iteration": 599999, "optimizer": {}}
+    ck["model"]["module.backbone.bottom_up.stem.conv1.norm.num_batches_tracked"] = torch.tensor(7)
+    ck["model"]["module.roi_heads.mask_head.deconv.weight"] = np.zeros((2, 2), dtype=np.float32)     # not read without masks
+    p = tmp_path / "model_0599999.pth"
+    torch.save(ck, p)
+    got = weights.load_checkpoint(str(p))
+    assert set(got) == set(sd) and all(torch.equal(got[k], sd[k]) for k in sd)
+    # a bare state_dict without the orientation head (MODEL.ORIENTATION_ON false) is accepted
+    bare = {k: v for k, v in sd.items() if "orientation_pred" not in k}
+    torch.save(bare, tmp_path / "bare.pth")
+    assert set(weights.load_checkpoint(str(tmp_path / "bare.pth"))) == set(bare)
+    # missing parameters are reported by name
+    del bare["roi_heads.hybrid_net.ConvNet.conv0_1.weight"]
+    torch.save(bare, tmp_path / "broken.pth")
+    with pytest.raises(KeyError, match="conv0_1.weight"):
+        weights.load_checkpoint(str(tmp_path / "broken.pth"))
+    with pytest.raises(KeyError, match="mask_head"):
+        weights.load_checkpoint(str(p), mask=True)
+    with pytest.raises(ValueError, match="pkl"):
+        weights.load_checkpoint("R-50.pkl")
