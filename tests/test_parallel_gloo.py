@@ -80,3 +80,41 @@ def test_single_process_gather_is_identity():
     from glass_text_spotting_b200 import parallel
     rec = torch.stack([_fake_record(i) for i in range(3)])
     assert torch.equal(parallel.all_gather_records(rec)[0], rec)
+
+
+def _ragged_worker(rank, world, port, n_images, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from glass_text_spotting_b200 import parallel
+    b, e = parallel.shard_range(n_images, rank, world)
+    rec = torch.stack([_fake_record(i) for i in range(b, e)]) if e > b else torch.zeros(0, MAXDET, 10 + STEPS * NC)
+    out = parallel.gather_sharded(rec, n_images)
+    q.put((rank, out.clone()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_uneven_shards_gather_in_dataset_order():
+    """7 images on 3 ranks (3 + 2 + 2) and 2 images on 3 ranks (1 + 1 + 0): one all-gather of padded records, every rank
+    ends with the whole dataset in order (the reference: comm.gather of pickled lists, text_evaluator.py:246-252)."""
+    from glass_text_spotting_b200 import parallel
+    for n_images in (7, 2):
+        world = 3
+        with socket.socket() as s:
+            s.bind(("127.0.0.1", 0))
+            port = s.getsockname()[1]
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        procs = [ctx.Process(target=_ragged_worker, args=(r, world, port, n_images, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        got = dict(q.get(timeout=120) for _ in range(world))
+        for p in procs:
+            p.join(timeout=120)
+            assert p.exitcode == 0
+        want = torch.stack([_fake_record(i) for i in range(n_images)])
+        for r in range(world):
+            assert torch.equal(got[r], want), (n_images, r)
+    # single process: identity
+    rec = torch.stack([_fake_record(i) for i in range(4)])
+    assert torch.equal(parallel.gather_sharded(rec, 4), rec)
