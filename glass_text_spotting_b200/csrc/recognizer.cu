@@ -13,6 +13,7 @@
 //                        of the image has emitted class 0 stay zero).
 // Latency-bound fp32 SIMT work: weights are pre-transposed to [k][out] so a warp reads 128 contiguous
 // bytes per k, activations are broadcast from shared memory.
+#include <cooperative_groups.h>
 #include <math_constants.h>
 
 #include <stdlib.h>
@@ -360,6 +361,187 @@ __global__ void __launch_bounds__(LSTM_THREADS) lstm_bidir_kernel(const float* _
   }
 }
 
+// ------------------------------------------------------------------------------------------ cluster-resident LSTM
+// OPT-IN (GLASS_LSTM_CLUSTER=1), written at the end of round 1 WITHOUT GPU time left to run it: it compiles for sm_100a
+// and its arithmetic is the one tools/lstm_split_probe.py emulates (5e-7 from fp64 after 32 steps), but it has not executed
+// on hardware yet -- tests/test_gpu_kernels.py's LSTM-vs-torch.nn.LSTM test is the gate when it is switched on.
+//
+// Why: lstm_bidir_kernel re-streams W_hh^T (1 MB) from L2 on every step into every CTA and does the product on the fp32
+// pipe.  Here a cluster of 8 CTAs owns 64 words of one direction for all T steps; CTA r keeps the split-fp16 W_hh rows of
+// ITS 32 hidden units x 4 gates (128 rows x 256 k, hi + lo = 132 KB) in shared memory for the whole kernel, and every
+// CTA holds the full h [64 words x 256] (hi + lo, 66 KB).  Per step a CTA computes gates[64 x 128] = h . W_r^T with
+// tensor-core mma.sync m16n8k16 (three products hi.hi + hi.lo + lo.hi, fp32 accumulate), updates c / h for its 32 units
+// in registers, and scatters the new h slice into all 8 CTAs' shared memory through DSMEM; two cluster barriers per step
+// (readers done -> writers; writers done -> next step).  Gate rows are ordered inside the CTA so that one thread ends up
+// with all four gates (i, f, g, o) of one hidden unit for its 8 words: no shared-memory round trip for the cell update.
+namespace cg = cooperative_groups;
+constexpr int LC_R = 8;                  // CTAs per cluster
+constexpr int LC_U = LSTM_H / LC_R;      // hidden units per CTA (32)
+constexpr int LC_N = 4 * LC_U;           // gate rows per CTA (128)
+constexpr int LC_W = 64;                 // words per cluster
+constexpr int LC_LD = LSTM_H + 8;        // shared-memory row stride in halfs: 528 B, conflict-free for ldmatrix
+constexpr int LC_THREADS = 256;          // 8 warps: warp w owns gate columns [16w, 16w + 16) = 4 hidden units
+constexpr float LC_SW = 64.f;            // power-of-two pre-scales of the fp16 split (weights, h)
+constexpr float LC_SH = 1024.f;
+constexpr int LC_SMEM = (2 * LC_N + 2 * LC_W) * LC_LD * (int)sizeof(__half);   // 202,752 B
+
+__device__ __forceinline__ void lc_ldsm_x4(uint32_t (&r)[4], const __half* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void lc_mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void lc_split(float x, float scale, __half& hi, __half& lo) {
+  const float v = x * scale;
+  hi = __float2half_rn(v);
+  lo = __float2half_rn(v - __half2float(hi));
+}
+
+__global__ void __cluster_dims__(LC_R, 1, 1) __launch_bounds__(LC_THREADS, 1)
+    lstm_cluster_mma_kernel(const float* __restrict__ gates_in, const float* __restrict__ whh_t, int n_seq, int T,
+                            __half* __restrict__ out_hi, __half* __restrict__ out_lo, float* __restrict__ out_f32) {
+  extern __shared__ __align__(16) unsigned char lc_smem[];
+  __half* w_hi = reinterpret_cast<__half*>(lc_smem);   // [LC_N][LC_LD], row n = this CTA's gate column n (order below)
+  __half* w_lo = w_hi + LC_N * LC_LD;
+  __half* h_hi = w_lo + LC_N * LC_LD;                  // [LC_W][LC_LD], h[word][k] * LC_SH
+  __half* h_lo = h_hi + LC_W * LC_LD;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int dir = blockIdx.y;
+  const int seq0 = (blockIdx.x / LC_R) * LC_W;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+  const float* wt = whh_t + (int64_t)dir * LSTM_H * LSTM_G;   // [k][gate row]
+
+  // column n of this CTA: warp n/16, 8-wide tile (n%16)/8, column c = n%8 inside it -> gate = 2*tile + (c&1),
+  // hidden unit = 4*(n/16) + c/2: the accumulator fragments of thread (g, q) of warp w then hold gates (i, f) in tile 0
+  // and (g, o) in tile 1 of unit 4w + q
+  for (int idx = tid; idx < LC_N * LSTM_H; idx += LC_THREADS) {
+    const int n = idx % LC_N, k = idx / LC_N;
+    const int tile = (n & 15) >> 3, c = n & 7;
+    const int row = (2 * tile + (c & 1)) * LSTM_H + rank * LC_U + 4 * (n >> 4) + (c >> 1);
+    __half hi, lo;
+    lc_split(__ldg(wt + (int64_t)k * LSTM_G + row), LC_SW, hi, lo);
+    w_hi[n * LC_LD + k] = hi;
+    w_lo[n * LC_LD + k] = lo;
+  }
+  for (int idx = tid; idx < 2 * LC_W * LC_LD; idx += LC_THREADS) h_hi[idx] = __float2half_rn(0.f);  // h_hi and h_lo
+  __syncthreads();
+  cluster.sync();   // every CTA's h buffer is zeroed before any peer writes into it
+
+  const int unit = rank * LC_U + 4 * warp + q;                 // the hidden unit this thread updates
+  const float kScale = LC_SW * LC_SH, kInv = 1.0f / (LC_SW * LC_SH);
+  float cst[4][2];                                             // cell state of (word = 16i + g + 8e, unit)
+  float gnext[4][2][4];                                        // next step's input-projection gates (i, f, g, o)
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) cst[i][e] = 0.f;
+
+  auto load_gates = [&](int step) {
+    const int t = dir == 0 ? step : T - 1 - step;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int word = seq0 + 16 * i + g + 8 * e;
+        const float* base = gates_in + ((int64_t)word * T + t) * (2 * LSTM_G) + dir * LSTM_G + unit;
+#pragma unroll
+        for (int gt = 0; gt < 4; ++gt) gnext[i][e][gt] = word < n_seq ? __ldg(base + gt * LSTM_H) : 0.f;
+      }
+  };
+  load_gates(0);
+
+  for (int step = 0; step < T; ++step) {
+    const int t = dir == 0 ? step : T - 1 - step;
+    float acc[4][2][4];   // [m-tile i][n-tile][d0..d3]: d0/d1 = word 16i+g, columns 2q / 2q+1; d2/d3 = word 16i+g+8
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        acc[i][0][2 * e + 0] = gnext[i][e][0] * kScale;   // i
+        acc[i][0][2 * e + 1] = gnext[i][e][1] * kScale;   // f
+        acc[i][1][2 * e + 0] = gnext[i][e][2] * kScale;   // g
+        acc[i][1][2 * e + 1] = gnext[i][e][3] * kScale;   // o
+      }
+    const int brow = 16 * warp + (lane & 7) + ((lane >> 4) << 3);
+#pragma unroll 4
+    for (int ks = 0; ks < LSTM_H / 16; ++ks) {
+      const int k0 = 16 * ks;
+      uint32_t bh[4], bl[4];   // [0],[1] = (b0, b1) of n-tile 0; [2],[3] = n-tile 1
+      const int bcol = k0 + ((lane >> 3) & 1) * 8;
+      lc_ldsm_x4(bh, w_hi + brow * LC_LD + bcol);
+      lc_ldsm_x4(bl, w_lo + brow * LC_LD + bcol);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint32_t ah[4], al[4];
+        const int aoff = (16 * i + (lane & 15)) * LC_LD + k0 + (lane >> 4) * 8;
+        lc_ldsm_x4(ah, h_hi + aoff);
+        lc_ldsm_x4(al, h_lo + aoff);
+        lc_mma(acc[i][0], ah, bh[0], bh[1]);
+        lc_mma(acc[i][0], ah, bl[0], bl[1]);
+        lc_mma(acc[i][0], al, bh[0], bh[1]);
+        lc_mma(acc[i][1], ah, bh[2], bh[3]);
+        lc_mma(acc[i][1], ah, bl[2], bl[3]);
+        lc_mma(acc[i][1], al, bh[2], bh[3]);
+      }
+    }
+    cluster.barrier_arrive();   // this CTA has finished reading h_{t-1}
+
+    float hn[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float ig = sigmoidf_(acc[i][0][2 * e + 0] * kInv), fg = sigmoidf_(acc[i][0][2 * e + 1] * kInv);
+        const float gg = tanhf(acc[i][1][2 * e + 0] * kInv), og = sigmoidf_(acc[i][1][2 * e + 1] * kInv);
+        const float c = fg * cst[i][e] + ig * gg;
+        cst[i][e] = c;
+        hn[i][e] = og * tanhf(c);
+      }
+    if (step + 1 < T) load_gates(step + 1);   // in flight across the barriers
+
+    cluster.barrier_wait();     // every CTA of the cluster has finished reading h_{t-1}: it may be overwritten
+    const int kcol = rank * LC_U + 4 * warp;   // the quad (q = 0..3) holds units kcol .. kcol + 3 of the same 8 words
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = __shfl_sync(0xffffffffu, hn[i][e], (lane & ~3) + j);
+        __half hh[4], hl[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) lc_split(v[j], LC_SH, hh[j], hl[j]);
+        const uint2 ph = make_uint2(pack16x2(hh[0], hh[1]), pack16x2(hh[2], hh[3]));
+        const uint2 pl = make_uint2(pack16x2(hl[0], hl[1]), pack16x2(hl[2], hl[3]));
+        const int off = (16 * i + g + 8 * e) * LC_LD + kcol;
+#pragma unroll
+        for (int pr = 0; pr < 2; ++pr) {       // lane q of the quad serves peers 2q and 2q + 1
+          const unsigned peer = 2 * q + pr;
+          *reinterpret_cast<uint2*>(cluster.map_shared_rank(h_hi, peer) + off) = ph;
+          *reinterpret_cast<uint2*>(cluster.map_shared_rank(h_lo, peer) + off) = pl;
+        }
+        if (i == q) {                            // and stores m-tile q's two words to global memory
+          const int word = seq0 + 16 * i + g + 8 * e;
+          if (word < n_seq) {
+            const int64_t o = ((int64_t)word * T + t) * (2 * LSTM_H) + dir * LSTM_H + kcol;
+            __half oh[4], ol[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) split16(v[j], oh[j], ol[j]);
+            *reinterpret_cast<uint2*>(out_hi + o) = make_uint2(pack16x2(oh[0], oh[1]), pack16x2(oh[2], oh[3]));
+            *reinterpret_cast<uint2*>(out_lo + o) = make_uint2(pack16x2(ol[0], ol[1]), pack16x2(ol[2], ol[3]));
+            if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = make_float4(v[0], v[1], v[2], v[3]);
+          }
+        }
+      }
+    cluster.sync();             // all slices of h_t have landed in every CTA (also keeps peers alive until the last write)
+  }
+}
+
 // ------------------------------------------------------------------------------------------ ASTER decoder
 constexpr int DEC_D = 256, DEC_T_MAX = 32, DEC_WPC = 4, DEC_MAX_CLASSES = 128;
 
@@ -607,6 +789,16 @@ extern "C" int glass_lstm_bidir(const float* gates_in, const float* whh_t, int n
   GLASS_CHECK(n_seq >= 0 && T > 0, "bad shape");
   if (n_seq == 0) return 0;
   // 16 words per CTA once that still fills >= 40 SMs (the L2 stream of W_hh^T is the bound), else 8
+  static const int cluster_env = getenv("GLASS_LSTM_CLUSTER") ? atoi(getenv("GLASS_LSTM_CLUSTER")) : 0;
+  if (cluster_env) {   // opt-in, not yet run on hardware (see lstm_cluster_mma_kernel)
+    GLASS_CUDA(cudaFuncSetAttribute(lstm_cluster_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LC_SMEM));
+    dim3 grid(((n_seq + LC_W - 1) / LC_W) * LC_R, 2);
+    lstm_cluster_mma_kernel<<<grid, LC_THREADS, LC_SMEM, STREAM>>>(gates_in, whh_t, n_seq, T, (__half*)out_hi,
+                                                                    (__half*)out_lo, out_f32);
+    count_launch();
+    GLASS_CUDA(cudaGetLastError());
+    return 0;
+  }
   static const int wpc_env = getenv("GLASS_LSTM_WPC") ? atoi(getenv("GLASS_LSTM_WPC")) : 0;  // A/B knob
   const int wpc = wpc_env ? wpc_env : 8;  // 16 was measured 2x slower: the CTA is latency-bound, not L2-bound
   auto launch = [&](auto kern, int w) -> cudaError_t {
