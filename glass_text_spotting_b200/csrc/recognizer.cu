@@ -566,7 +566,6 @@ struct AsterParams {
   float* logits;       // optional [n_words, steps, num_classes]
   float* alphas;       // optional [n_words, steps, T]
   int* first_eos;      // [n_words] first step whose argmax is class 0 (steps if never)
-  const float* emb_gi; // optional [num_classes][768]: W_ih[:, :256] . Emb[y] + b_ih (lookup instead of 256 k-iterations)
 };
 
 __global__ void __launch_bounds__(1024) aster_decode_kernel(const AsterParams p) {
@@ -651,22 +650,11 @@ __global__ void __launch_bounds__(1024) aster_decode_kernel(const AsterParams p)
       const float bi = __ldg(p.bih + tid), bh = __ldg(p.bhh + tid);
 #pragma unroll
       for (int w = 0; w < DEC_WPC; ++w) { a[w] = bi; b[w] = bh; }
-      if (p.emb_gi) {   // opt-in: the embedding half of W_ih u (+ b_ih) comes from the per-class table
-#pragma unroll
-        for (int w = 0; w < DEC_WPC; ++w) a[w] = __ldg(p.emb_gi + (int64_t)y_s[w] * (3 * DEC_D) + tid);
 #pragma unroll 8
-        for (int k = DEC_D; k < 2 * DEC_D; ++k) {
-          const float wv = __ldg(p.wih_t + (int64_t)k * (3 * DEC_D) + tid);
-          const float4 uv = *reinterpret_cast<const float4*>(&u_s[k][0]);
-          a[0] += wv * uv.x; a[1] += wv * uv.y; a[2] += wv * uv.z; a[3] += wv * uv.w;
-        }
-      } else {
-#pragma unroll 8
-        for (int k = 0; k < 2 * DEC_D; ++k) {
-          const float wv = __ldg(p.wih_t + (int64_t)k * (3 * DEC_D) + tid);
-          const float4 uv = *reinterpret_cast<const float4*>(&u_s[k][0]);
-          a[0] += wv * uv.x; a[1] += wv * uv.y; a[2] += wv * uv.z; a[3] += wv * uv.w;
-        }
+      for (int k = 0; k < 2 * DEC_D; ++k) {
+        const float wv = __ldg(p.wih_t + (int64_t)k * (3 * DEC_D) + tid);
+        const float4 uv = *reinterpret_cast<const float4*>(&u_s[k][0]);
+        a[0] += wv * uv.x; a[1] += wv * uv.y; a[2] += wv * uv.z; a[3] += wv * uv.w;
       }
 #pragma unroll 8
       for (int k = 0; k < DEC_D; ++k) {
@@ -843,7 +831,6 @@ extern "C" int glass_aster_decode(const GlassAsterParams* p, void* stream) {
   k.ws_t = p->ws_t; k.bs = p->bs; k.we = p->we; k.be = p->be; k.emb = p->emb; k.wih_t = p->wih_t; k.whh_t = p->whh_t;
   k.bih = p->bih; k.bhh = p->bhh; k.wo_t = p->wo_t; k.bo = p->bo; k.temperature = p->temperature;
   k.probs = p->probs; k.logits = p->logits; k.alphas = p->alphas; k.first_eos = p->first_eos;
-  k.emb_gi = p->emb_gi;
   aster_decode_kernel<<<(p->n_words + DEC_WPC - 1) / DEC_WPC, 1024, 0, STREAM>>>(k);
   count_launch();
   GLASS_CUDA(cudaGetLastError());

@@ -98,7 +98,6 @@ class AsterParams(C.Structure):
         ("be", C.c_float), ("emb", C.c_void_p), ("wih_t", C.c_void_p), ("whh_t", C.c_void_p), ("bih", C.c_void_p),
         ("bhh", C.c_void_p), ("wo_t", C.c_void_p), ("bo", C.c_void_p), ("temperature", C.c_float),
         ("probs", C.c_void_p), ("logits", C.c_void_p), ("alphas", C.c_void_p), ("first_eos", C.c_void_p),
-        ("emb_gi", C.c_void_p),
     ]
 
 

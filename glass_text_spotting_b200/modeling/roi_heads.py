@@ -162,13 +162,6 @@ class B200GlassROIHeads:
             "wo_t": sdr[dp + "fc.weight"].t().contiguous().to(dev), "bo": sdr[dp + "fc.bias"].to(dev),
             "temperature": float(sdr[dp + "temperature"].item()) if (dp + "temperature") in sdr else 1.0,
         }
-        if os.environ.get("GLASS_DEC_TABLE", "0") == "1":
-            # OPT-IN, not yet run on hardware: the GRU input is [Emb[y_prev] ; context], so the embedding half of W_ih u
-            # (+ b_ih) only takes num_classes distinct values -- a [97, 768] table replaces 256 of the 768 k-iterations
-            # (0.79 of the 2.6 MB of weights each CTA streams per step).  Summed in fp64 and rounded once, i.e. within an
-            # ulp of the in-kernel fp32 sum it replaces.
-            wih, emb = sdr[dp + "gru.weight_ih_l0"].double(), sdr[dp + "tgt_embedding.weight"].double()
-            self.dec["emb_gi"] = (emb @ wih[:, :256].t() + sdr[dp + "gru.bias_ih_l0"].double()).float().contiguous().to(dev)
 
     # ============================================================================================ box branch
     def box_features(self, features: Dict[str, Act], rois: torch.Tensor) -> torch.Tensor:

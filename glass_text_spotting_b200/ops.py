@@ -475,7 +475,6 @@ def aster_decode(x: torch.Tensor, xproj: torch.Tensor, n_words: int, T: int, ste
     p.wih_t, p.whh_t, p.bih, p.bhh = _ptr(w["wih_t"]), _ptr(w["whh_t"]), _ptr(w["bih"]), _ptr(w["bhh"])
     p.wo_t, p.bo, p.temperature = _ptr(w["wo_t"]), _ptr(w["bo"]), float(w["temperature"])
     p.probs, p.logits, p.alphas, p.first_eos = _ptr(probs), _ptr(logits), _ptr(alphas), _ptr(first_eos)
-    p.emb_gi = _ptr(w.get("emb_gi"))
     _lib.check(_lib.load().glass_aster_decode(C.byref(p), _stream()))
 
 

@@ -319,8 +319,6 @@ typedef struct {
   float* logits;       /* optional */
   float* alphas;       /* optional [n_words, steps, T] */
   int32_t* first_eos;  /* [n_words] */
-  const float* emb_gi; /* optional [num_classes][3*dim] = W_ih[:, :dim] . Emb[y] + b_ih: the embedding half of the GRU
-                          input product as a lookup (a third of the per-step weight stream); NULL = compute it */
 } GlassAsterParams;
 int glass_aster_decode(const GlassAsterParams* p, void* stream);
 /* The reference's batch-level early break (prediction_aster.py:91-93): zero the rows after the step at which
