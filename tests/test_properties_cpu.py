@@ -1,0 +1,74 @@
+"""Size-independent properties of the host-side glue (hypothesis): the rotated-box structure against the oracle's
+restatement of detectron2's RotatedBoxes, the GlassRCNN post-processing chain, and the image sharding."""
+import math
+
+import torch
+from hypothesis import given, settings, strategies as st
+
+boxes_st = st.lists(
+    st.tuples(st.floats(-50, 700), st.floats(-50, 500), st.floats(0, 300), st.floats(0, 200), st.floats(-400, 400)),
+    min_size=0, max_size=12)
+
+
+def _t(rows):
+    return torch.tensor(rows, dtype=torch.float32).reshape(-1, 5)
+
+
+@settings(max_examples=60, deadline=None)
+@given(boxes_st, st.integers(16, 640), st.integers(16, 480))
+def test_clip_matches_oracle_and_is_idempotent(rows, w, h):
+    from glass_text_spotting_b200.structures import RotatedBoxes
+    from oracle import d2_ops
+    b = RotatedBoxes(_t(rows).clone())
+    b.clip((h, w))
+    want = d2_ops.clip_rotated_(_t(rows).clone(), (h, w))
+    assert torch.equal(b.tensor, want)
+    again = RotatedBoxes(b.tensor.clone())
+    again.clip((h, w))
+    assert torch.allclose(again.tensor, b.tensor, atol=1e-4)
+    assert bool(((b.tensor[:, 4] >= -180) & (b.tensor[:, 4] < 180)).all())
+
+
+@settings(max_examples=60, deadline=None)
+@given(boxes_st, st.floats(0.25, 4.0), st.floats(0.25, 4.0))
+def test_scale_matches_oracle_and_preserves_area_ratio(rows, sx, sy):
+    from glass_text_spotting_b200.structures import RotatedBoxes
+    from oracle import d2_ops
+    b = RotatedBoxes(_t(rows).clone())
+    b.scale(sx, sy)
+    want = d2_ops.scale_rotated_(_t(rows).clone(), sx, sy)
+    assert torch.allclose(b.tensor, want, rtol=1e-6, atol=1e-5)
+    if sx == sy:      # isotropic scaling keeps the angle and multiplies both sides by the factor
+        src = _t(rows)
+        assert torch.allclose(b.tensor[:, 2:4], src[:, 2:4] * sx, rtol=1e-5, atol=1e-4)
+
+
+@settings(max_examples=40, deadline=None)
+@given(boxes_st, st.sampled_from([None, 1.0, 2.0, 5.0]), st.sampled_from([None, 0.05, 0.2]),
+       st.tuples(st.integers(32, 400), st.integers(32, 400)))
+def test_postprocess_chain_matches_oracle(rows, min_dim, inflate, out_hw):
+    """B200GlassRCNN._postprocess (host glue) == the oracle's restatement of glass_rcnn.py:103-128 for any input."""
+    from glass_text_spotting_b200.modeling.glass_rcnn import B200GlassRCNN
+    from glass_text_spotting_b200.structures import Instances, RotatedBoxes
+    from oracle import postprocess as pp
+    src = _t(rows)
+    hw = (300, 400)
+    model = B200GlassRCNN.__new__(B200GlassRCNN)
+    model.filter_small_boxes, model.inflate_ratio = min_dim, inflate
+    inst = Instances(hw, pred_boxes=RotatedBoxes(src.clone()), idx=torch.arange(len(src)))
+    out = model._postprocess([inst], [{"height": out_hw[0], "width": out_hw[1]}], [hw])[0]["instances"]
+    want_b, want_i = pp.glass_rcnn_postprocess(src, hw, out_hw[0], out_hw[1], min_dim, inflate)
+    assert torch.equal(out.idx, want_i)
+    assert torch.allclose(out.pred_boxes.tensor, want_b, rtol=1e-6, atol=1e-5)
+    assert bool((out.pred_boxes.tensor[:, 2:4] > 0).all())
+
+
+@settings(max_examples=100, deadline=None)
+@given(st.integers(0, 500), st.integers(1, 16))
+def test_shards_partition_the_dataset(n, world):
+    from glass_text_spotting_b200 import parallel
+    r = [parallel.shard_range(n, k, world) for k in range(world)]
+    assert r[0][0] == 0 and r[-1][1] == n and all(r[i][1] == r[i + 1][0] for i in range(world - 1))
+    sizes = [e - b for b, e in r]
+    assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+    assert max(sizes) == math.ceil(n / world)
