@@ -72,3 +72,36 @@ def test_shards_partition_the_dataset(n, world):
     sizes = [e - b for b, e in r]
     assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
     assert max(sizes) == math.ceil(n / world)
+
+
+@settings(max_examples=30, deadline=None)
+@given(st.lists(st.integers(0, 5), min_size=1, max_size=4), st.integers(0, 2 ** 31 - 1))
+def test_pack_detections_roundtrip(counts, seed):
+    """pack_detections (the fixed-size all-gather record) -> parallel.unpack_detections /
+    evaluation.instances_from_packed gives back exactly the detections, for any per-image counts incl. zero."""
+    import types
+    from glass_text_spotting_b200 import evaluation, parallel
+    from glass_text_spotting_b200.modeling.glass_rcnn import B200GlassRCNN
+    steps, nc, max_det = 4, 7, 5
+    g = torch.Generator().manual_seed(seed)
+    n = len(counts)
+    det = {"pred_boxes": torch.rand(n, max_det, 5, generator=g) * 100, "scores": torch.rand(n, max_det, generator=g),
+           "orientations": torch.rand(n, max_det, 2, generator=g)}
+    starts = [0]
+    for c in counts:
+        starts.append(starts[-1] + c)
+    probs = torch.rand(starts[-1], steps, nc, generator=g)
+    model = B200GlassRCNN.__new__(B200GlassRCNN)
+    model.roi_heads = types.SimpleNamespace(steps=steps, num_classes=nc)
+    rec = model.pack_detections(det, probs, counts, starts)
+    assert tuple(rec.shape) == (n, max_det, 10 + steps * nc)
+    dets = parallel.unpack_detections(rec, steps, nc)
+    insts = evaluation.instances_from_packed(rec, [(64, 80)] * n, steps, nc)
+    for i, c in enumerate(counts):
+        assert len(dets[i]["scores"]) == c == len(insts[i])
+        assert torch.equal(dets[i]["pred_boxes"], det["pred_boxes"][i, :c])
+        assert torch.equal(insts[i].pred_boxes.tensor, det["pred_boxes"][i, :c])
+        assert torch.equal(insts[i].scores, det["scores"][i, :c])
+        assert torch.equal(insts[i].orientations, det["orientations"][i, :c])
+        assert torch.equal(insts[i].pred_text_prob, probs[starts[i]: starts[i + 1]])
+        assert bool((rec[i, c:] == 0).all())
