@@ -22,5 +22,7 @@ not installable offline.  The oracle is therefore pinned by
 The detectron2-recalled parts (backbone wiring, RPN, poolers) have no reference-run
 pin: for them parity is "unpinned beyond the upstream KATs"  -- plus, for
 the ResNet-50 / FPN wiring, a cross-check against torchvision's independent
-implementations of the same architectures (tests/test_oracle_backbone_torchvision.py).
+implementations of the same architectures (tests/test_oracle_backbone_torchvision.py), and for the
+proposal selection / box decode a cross-check against torchvision's RPN ``filter_proposals`` and ``BoxCoder``
+at angle 0 (tests/test_oracle_rpn_torchvision.py).
 """
