@@ -59,3 +59,24 @@ def test_rotated_box_decode_at_angle0_matches_torchvision_boxcoder():
                             got[:, 1] + got[:, 3] / 2), 1)
         assert torch.allclose(mine, want, rtol=1e-5, atol=1e-2), float((mine - want).abs().max())
         assert torch.equal(got[:, 4], torch.zeros(n))
+
+
+def test_rotated_anchor_grid_at_angle0_matches_torchvision_anchor_generator():
+    """RotatedAnchorGenerator (w = sqrt(s^2 / r), h = r w; order y, x, then ratio) with the single angle 0
+    == torchvision's AnchorGenerator for sizes / ratios whose anchors are integral (torchvision rounds its base anchors)."""
+    from torchvision.models.detection.anchor_utils import AnchorGenerator
+    from torchvision.models.detection.image_list import ImageList
+    from oracle import d2_ops
+    grids, strides = [(6, 8), (3, 4)], [8, 16]           # a 48 x 64 image: torchvision infers the strides as size // grid
+    got = d2_ops.rotated_grid_anchors(grids, strides, [[32.0], [64.0]], [[0.25, 1.0, 4.0]], [[0.0]])
+    ag = AnchorGenerator(sizes=((32,), (64,)), aspect_ratios=((0.25, 1.0, 4.0),) * 2)
+    tv = ag(ImageList(torch.zeros(1, 3, 48, 64), [(48, 64)]), [torch.zeros(1, 1, gh, gw) for gh, gw in grids])[0]
+    off = 0
+    for lvl, a in enumerate(got):
+        n = a.shape[0]
+        assert n == grids[lvl][0] * grids[lvl][1] * 3
+        mine = torch.stack((a[:, 0] - a[:, 2] / 2, a[:, 1] - a[:, 3] / 2, a[:, 0] + a[:, 2] / 2, a[:, 1] + a[:, 3] / 2), 1)
+        assert torch.equal(a[:, 4], torch.zeros(n))
+        assert torch.allclose(mine, tv[off: off + n], atol=1e-4), (lvl, float((mine - tv[off: off + n]).abs().max()))
+        off += n
+    assert off == tv.shape[0]
