@@ -105,3 +105,25 @@ def test_pack_detections_roundtrip(counts, seed):
         assert torch.equal(insts[i].orientations, det["orientations"][i, :c])
         assert torch.equal(insts[i].pred_text_prob, probs[starts[i]: starts[i + 1]])
         assert bool((rec[i, c:] == 0).all())
+
+
+@settings(max_examples=80, deadline=None)
+@given(st.floats(-170, 170), st.floats(2, 300), st.floats(2, 200), st.floats(0.3, 3.0), st.floats(0.3, 3.0))
+def test_scale_is_the_image_of_the_box_edges(angle, w, h, sx, sy):
+    """RotatedBoxes.scale from first principles (no second implementation exists to compare with): under the map
+    (x, y) -> (sx x, sy y) the new width / height are the lengths of the images of the box's width / height edge and the
+    new angle is the direction of the image of the height edge (detectron2's definition)."""
+    from oracle import d2_ops
+    th = math.radians(angle)
+    c, s = math.cos(th), math.sin(th)
+    # image coordinates (y down), angle counter-clockwise: width edge along (c, -s), height edge along (s, c)
+    we = (sx * c * w, -sy * s * w)
+    he = (sx * s * h, sy * c * h)
+    b = torch.tensor([[10.0, 20.0, w, h, angle]])
+    d2_ops.scale_rotated_(b, sx, sy)
+    assert abs(b[0, 0].item() - 10.0 * sx) < 1e-4 and abs(b[0, 1].item() - 20.0 * sy) < 1e-4
+    assert abs(b[0, 2].item() - math.hypot(*we)) < 1e-3 * max(1.0, math.hypot(*we))
+    assert abs(b[0, 3].item() - math.hypot(*he)) < 1e-3 * max(1.0, math.hypot(*he))
+    want = math.degrees(math.atan2(he[0], he[1]))
+    diff = (b[0, 4].item() - want + 180.0) % 360.0 - 180.0
+    assert abs(diff) < 1e-3
