@@ -24,5 +24,6 @@ pin: for them parity is "unpinned beyond the upstream KATs"  -- p
 the ResNet-50 / FPN wiring, a cross-check against torchvision's independent
 implementations of the same architectures (tests/test_oracle_backbone_torchvision.py), and for the
 proposal selection / box decode a cross-check against torchvision's RPN ``filter_proposals`` and ``BoxCoder``
-at angle 0 (tests/test_oracle_rpn_torchvision.py).
+at angle 0 (tests/test_oracle_rpn_torchvision.py), for the rotated IoU OpenCV's rotated-rectangle
+intersection and for RoIAlignRotated a torch grid_sample formulation (tests/test_oracle_rotated_independent.py).
 """
