@@ -75,3 +75,39 @@ def test_roi_align_rotated_matches_grid_sample_formulation():
         assert got.shape == want.shape
         assert torch.allclose(got, want, rtol=1e-4, atol=2e-5), (out_hw, float((got - want).abs().max()))
     assert np.isfinite(got.numpy()).all()
+
+
+def test_rotated_nms_matches_greedy_nms_on_opencv_ious():
+    """Greedy NMS written from its definition on top of the OpenCV IoUs (neither the IoU nor the loop shared with the
+    oracle) keeps the same boxes in the same order, for arbitrary angles; pairs whose IoU is within 5e-3 of the threshold
+    are excluded from the fixture (the two IoU implementations agree to ~2e-3)."""
+    import cv2
+    from oracle import d2_ops
+    g = torch.Generator().manual_seed(14)
+    n, thr = 160, 0.4
+    base = torch.stack((torch.rand(n, generator=g) * 120, torch.rand(n, generator=g) * 120, 8 + torch.rand(n, generator=g) * 50,
+                        6 + torch.rand(n, generator=g) * 25, torch.rand(n, generator=g) * 360 - 180), 1)
+    base[n // 2:] = base[: n - n // 2] + torch.randn(n - n // 2, 5, generator=g) * torch.tensor([3.0, 3.0, 3.0, 2.0, 10.0])
+    base[:, 2:4] = base[:, 2:4].clamp_min(3.0)
+    scores = torch.rand(n, generator=g)
+
+    def iou(r1, r2):
+        kind, pts = cv2.rotatedRectangleIntersection(((r1[0], r1[1]), (r1[2], r1[3]), -r1[4]), ((r2[0], r2[1]), (r2[2], r2[3]), -r2[4]))
+        inter = cv2.contourArea(cv2.convexHull(pts, returnPoints=True)) if kind != cv2.INTERSECT_NONE and pts is not None and len(pts) >= 3 else 0.0
+        return inter / (r1[2] * r1[3] + r2[2] * r2[3] - inter)
+    rows = base.tolist()
+    m = np.array([[iou(rows[i], rows[j]) if i != j else 1.0 for j in range(n)] for i in range(n)])
+    ambiguous = set(np.argwhere(np.abs(m - thr) < 5e-3).reshape(-1).tolist())
+    keep_idx = [i for i in range(n) if i not in ambiguous]
+    assert len(keep_idx) > 100
+    b, s = base[keep_idx], scores[keep_idx]
+    mm = m[np.ix_(keep_idx, keep_idx)]
+    order = torch.sort(s, descending=True, stable=True).indices.tolist()
+    kept, dead = [], set()
+    for i in order:
+        if i in dead:
+            continue
+        kept.append(i)
+        dead.update(j for j in order if mm[i, j] > thr and j != i)
+    got = d2_ops.nms_rotated(b, s, thr).tolist()
+    assert got == kept and 10 < len(kept) < len(keep_idx)
