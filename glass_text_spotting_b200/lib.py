@@ -16,7 +16,7 @@ SYMBOLS = [
     "glass_nms_workspace_bytes",
     "glass_nms_rotated", "glass_box_decode", "glass_gc_attention", "glass_hmean_rows", "glass_lstm_bidir",
     "glass_aster_decode", "glass_aster_finalize", "glass_resize_bilinear_u8", "glass_postprocess_merge", "glass_text_scores", "glass_zero_border", "glass_stem_s2d", "glass_baseline_roi_align_rotated_d2", "glass_mask_finalize", "glass_paste_masks_rotated",
-    "glass_box_iou_rotated", "glass_nms_rotated_all", "glass_nms_rotated_all_workspace_bytes",
+    "glass_box_iou_rotated", "glass_nms_rotated_all", "glass_nms_rotated_all_workspace_bytes", "glass_aster_decode_pre",
 ]
 
 
@@ -151,6 +151,7 @@ def load() -> C.CDLL:
     lib.glass_hmean_rows.argtypes = [p, p, i, i, i, i, i, p, p, p, p]
     lib.glass_lstm_bidir.argtypes = [p, p, i, i, i, p, p, p, p]
     lib.glass_aster_decode.argtypes = [C.POINTER(AsterParams), p]
+    lib.glass_aster_decode_pre.argtypes = [C.POINTER(AsterParams), p, p, i, p]
     lib.glass_aster_finalize.argtypes = [p, p, p, i, i, i, p]
     lib.glass_resize_bilinear_u8.argtypes = [p, i, i, i, p, i, i, p]
     lib.glass_postprocess_merge.argtypes = [C.POINTER(PostprocessParams), p]

@@ -162,6 +162,14 @@ class B200GlassROIHeads:
             "wo_t": sdr[dp + "fc.weight"].t().contiguous().to(dev), "bo": sdr[dp + "fc.bias"].to(dev),
             "temperature": float(sdr[dp + "temperature"].item()) if (dp + "temperature") in sdr else 1.0,
         }
+        # OPT-IN (GLASS_DEC_PRE=1; compiles, not yet run on hardware): the decoder GRU's input product from two precomputed
+        # tensors instead of the 1.5 MB W_ih stream per step and CTA -- see aster_decode_pre_kernel (csrc/recognizer.cu)
+        self.dec_pre = None
+        if os.environ.get("GLASS_DEC_PRE", "0") == "1":
+            wih = sdr[dp + "gru.weight_ih_l0"]                                   # [768, 512], input = [embedding ; context]
+            table = sdr[dp + "tgt_embedding.weight"].double() @ wih[:, :256].double().t() + sdr[dp + "gru.bias_ih_l0"].double()
+            self.dec_pre = {"emb_gi": table.float().contiguous().to(dev),
+                            "w_ctx": packing.pack_linear(wih[:, 256:], None, device=dev)}
 
     # ============================================================================================ box branch
     def box_features(self, features: Dict[str, Act], rois: torch.Tensor) -> torch.Tensor:
@@ -354,7 +362,12 @@ class B200GlassROIHeads:
         if taps is not None:
             logits = torch.zeros_like(probs)
             alphas = torch.zeros((K, self.steps, T), dtype=torch.float32, device=rois.device)
-        ops.aster_decode(enc_f32, xproj, K, T, self.steps, self.num_classes, self.dec, probs, first_eos, logits, alphas)
+        emb_gi = pctx = None
+        if self.dec_pre is not None:
+            emb_gi = self.dec_pre["emb_gi"]
+            _, pctx = ops.linear(seq, self.dec_pre["w_ctx"], want_split=False, want_f32=True, mode=m)
+        ops.aster_decode(enc_f32, xproj, K, T, self.steps, self.num_classes, self.dec, probs, first_eos, logits, alphas,
+                         emb_gi=emb_gi, pctx=pctx)
         ops.aster_finalize(probs, first_eos, word_start, n_img, self.steps, self.num_classes)
         if taps is not None:
             taps.update(p2p3=g, fused=fused, crops=crops, fused2=fused2, fusion_out=y, recog_cnn=x2, encoder_out=enc_f32,

@@ -467,7 +467,10 @@ def lstm_bidir(gates_in: torch.Tensor, whh_t: torch.Tensor, n_seq: int, T: int, 
 
 def aster_decode(x: torch.Tensor, xproj: torch.Tensor, n_words: int, T: int, steps: int, num_classes: int, w,
                  probs: torch.Tensor, first_eos: torch.Tensor, logits: Optional[torch.Tensor] = None,
-                 alphas: Optional[torch.Tensor] = None) -> None:
+                 alphas: Optional[torch.Tensor] = None, emb_gi: Optional[torch.Tensor] = None,
+                 pctx: Optional[torch.Tensor] = None) -> None:
+    """``emb_gi`` [num_classes, 768] + ``pctx`` [n_words*T, 768] select the opt-in kernel with the precomputed GRU input
+    (glass_aster_decode_pre); without them the default kernel streams W_ih on every step."""
     assert x.dtype == torch.float32 and x.is_contiguous() and xproj.is_contiguous()
     p = _lib.AsterParams()
     p.x, p.xproj, p.n_words, p.T, p.steps, p.num_classes, p.dim = _ptr(x), _ptr(xproj), n_words, T, steps, num_classes, 256
@@ -475,6 +478,11 @@ def aster_decode(x: torch.Tensor, xproj: torch.Tensor, n_words: int, T: int, ste
     p.wih_t, p.whh_t, p.bih, p.bhh = _ptr(w["wih_t"]), _ptr(w["whh_t"]), _ptr(w["bih"]), _ptr(w["bhh"])
     p.wo_t, p.bo, p.temperature = _ptr(w["wo_t"]), _ptr(w["bo"]), float(w["temperature"])
     p.probs, p.logits, p.alphas, p.first_eos = _ptr(probs), _ptr(logits), _ptr(alphas), _ptr(first_eos)
+    if emb_gi is not None and pctx is not None:
+        assert emb_gi.dtype == torch.float32 and tuple(emb_gi.shape) == (num_classes, 768) and emb_gi.is_contiguous()
+        assert pctx.dtype == torch.float32 and tuple(pctx.shape) == (n_words * T, 768) and pctx.is_contiguous()
+        _lib.check(_lib.load().glass_aster_decode_pre(C.byref(p), _ptr(emb_gi), _ptr(pctx), 768, _stream()))
+        return
     _lib.check(_lib.load().glass_aster_decode(C.byref(p), _stream()))
 
 

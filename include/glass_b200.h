@@ -321,6 +321,11 @@ typedef struct {
   int32_t* first_eos;  /* [n_words] */
 } GlassAsterParams;
 int glass_aster_decode(const GlassAsterParams* p, void* stream);
+/* Opt-in variant of glass_aster_decode (compiles; not yet run on hardware): the GRU's input product is taken from two
+ * precomputed tensors instead of streaming W_ih on every step -- emb_gi fp32 [num_classes][3*dim] = W_ih[:, :dim] . Emb[y]
+ * + b_ih, and pctx fp32 [n_words, T, 3*dim] = x . W_ih[:, dim:]^T (one GEMM per launch); ld_pctx must be 3*dim.  Same
+ * outputs as glass_aster_decode up to the re-association sum_t alpha_t (W x_t) = W (sum_t alpha_t x_t). */
+int glass_aster_decode_pre(const GlassAsterParams* p, const float* emb_gi, const float* pctx, int ld_pctx, void* stream);
 /* The reference's batch-level early break (prediction_aster.py:91-93): zero the rows after the step at which
  * every word of an image has emitted class 0.  word_start: int32 [n_img+1] prefix offsets of each image's words. */
 int glass_aster_finalize(float* probs, const int32_t* first_eos, const int32_t* word_start, int n_img, int steps,
