@@ -42,7 +42,22 @@ WORKLOADS["totaltext_loop"] = dict(batch=4, h=1024, w=1024, full=True, totaltext
 WORKLOADS["mask_bs4"] = dict(batch=4, h=1024, w=1024, full=False, mask=True,
                              desc="mask branch (SURVEY.md 8f #3: 14x14 rotated mask pooler over 5 FPN levels -> 4 conv3x3 + "
                                   "deconv + predictor -> sigmoid -> rotated paste at 1024x1024) for 4 images x 89 detections")
-CPU_WORD_CAP = 16  # the CPU arm decodes at most this many words per image (bounded sample)
+MASK_CPU_DETECTIONS = 16  # mask_bs4's CPU leg pastes this many detections per image (bounded sample; stated in its line)
+
+
+def _config(name, n_gpus):
+    """The `config` object of the JSON line -- built by ONE function for both arms (`--impl b200` and `--impl reference`)
+    so that the two lines describe the same workload key for key; run-dependent facts (words found, chunk policy,
+    clocks) live outside it."""
+    wl = WORKLOADS[name]
+    return {"workload": wl["desc"], "name": name, "images_per_step_per_gpu": wl["batch"],
+            "global_batch": n_gpus * wl["batch"], "image_hw": [wl["h"], wl["w"]],
+            "parallelism": f"image-sharded x{n_gpus}",
+            "model": "configs/glass_pretrain.yaml geometry: R=100 proposals, <=100 detections/image, every detection "
+                     "recognised (26 steps x 97 classes)" if wl["full"] else "ResNet-50 + FPN (p2..p6)",
+            "weights": "random init (glass_text_spotting_b200.weights.random_state_dict(0)), BatchNorm folded",
+            "images": "uint8 synthetic, torch.Generator seed 1000 + rank",
+            "l2": "inputs rotated between 2 batches; per-step working set (GBs of activations) >> 126 MB L2"}
 
 
 def _peaks():
@@ -50,15 +65,6 @@ def _peaks():
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
     except Exception:
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
-
-
-def _traffic(workload):
-    """DRAM bytes of the dominant kernel from the committed ncu capture (profiles/r01_traffic.json), or None."""
-    try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(workload)
-        return t and (t.get("dram_bytes_per_step") or t.get("dram_bytes_per_launch"))
-    except Exception:
-        return None
 
 
 class ClockSampler:
@@ -119,14 +125,14 @@ def _cpu_runner(wl):
     g = torch.Generator().manual_seed(0)
     if wl.get("mask"):
         from oracle import d2_ops, mask as omask  # test infrastructure; allowed here only as the timed CPU baseline
-        feats, rois = _mask_inputs(1, CPU_WORD_CAP)
+        feats, rois = _mask_inputs(1, MASK_CPU_DETECTIONS)
         head = omask.seeded_mask_head(0)
 
         def run():
             with torch.no_grad():
                 pooled = d2_ops.roi_pooler(feats, [rois[:, 1:]], (14, 14), [1 / 4, 1 / 8, 1 / 16, 1 / 32, 1 / 64], 0)
                 omask.paste_masks_in_image(head(pooled)[:, 0], rois[:, 1:].contiguous(), (wl["h"], wl["w"]), 0.5)
-        return run, (f"1 image, {CPU_WORD_CAP} detections through the oracle's mask branch (torch fp32 CPU: rotated pooler, "
+        return run, (f"1 image, {MASK_CPU_DETECTIONS} detections through the oracle's mask branch (torch fp32 CPU: rotated pooler, "
                      f"mask head, reference paste at 1024x1024); the GPU arm does 89 per image")
     if wl.get("postprocess"):
         from oracle import postprocess as opp  # test infrastructure; allowed here only as the timed CPU baseline
@@ -151,17 +157,22 @@ def _cpu_runner(wl):
         return run, "1 image 1024x1024 through the oracle's ResNet-50+FPN (fp32, torch CPU)"
     from glass_text_spotting_b200 import weights
     from oracle import model as om
-    o = om.GlassOracle(om.HotPathConfig(max_detections_override=CPU_WORD_CAP))
+    o = om.GlassOracle(om.HotPathConfig())   # same geometry as the GPU arm: every detection (<= 100) is recognised
     o.load_state_dict(weights.random_state_dict(0), strict=False)
-    img = torch.randint(0, 256, (3, wl["h"], wl["w"]), generator=g).float()
-    last = {}
+    # the GPU arm's rank-0 batch (seed 1000): this leg runs its images one per forward, like the reference does
+    g = torch.Generator().manual_seed(1000)
+    batch = torch.randint(0, 256, (wl["batch"], 3, wl["h"], wl["w"]), generator=g, dtype=torch.uint8)
+    last = {"i": 0, "words": []}
 
     def run():
+        img = batch[last["i"] % wl["batch"]].float()
+        last["i"] += 1
         with torch.no_grad():
             r = o.inference([{"image": img}])
-        last["k"] = int(r[0]["instances"]["pred_boxes"].shape[0])
-    return run, (f"1 image 1024x1024 through the oracle's full GLASS inference (CPU restatement of the detectron2 "
-                 f"path, fp32 torch CPU), recognizer capped at {CPU_WORD_CAP} words/image (the GPU arm decodes all)")
+        last["words"].append(int(r[0]["instances"]["pred_boxes"].shape[0]))
+    run.state = last
+    return run, ("1 image 1024x1024 (of the GPU arm's rank-0 batch, same weights) through the oracle's full GLASS inference "
+                 "(CPU restatement of the detectron2 path, fp32 torch CPU), every detection recognised like the GPU arm")
 
 
 def _torch_backbone_on_gpu(B, H, W):
@@ -226,11 +237,15 @@ def run_reference(args):
         run()
     dt = time.perf_counter() - t0
     ips = args.steps / dt
+    words = getattr(run, "state", {}).get("words")
     print(json.dumps({
         "impl": "reference", "metric": "images/sec @1024x1024", "value": ips, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["desc"]},
+        "config": _config(args.workload, args.gpus),
+        "run": {"words_per_image": (sum(words) / len(words)) if words else None,
+                "note": "each timed step = ONE image of the configured batch (bounded sample; the reference runs one image "
+                        "per forward anyway, SURVEY.md section 0 fact 4); value = images/s"},
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": "each step = " + desc},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -643,14 +658,23 @@ def _roialign_glass_shapes(rois_d, flush, reps: int = 10):
     return out
 
 
-def run_roialign(args):
-    """BASELINE.json configs[2].  Timed region = K back-to-back launches (CUDA events on the launching stream), each
+def _ncu(name):
+    """Numbers that only a profiler can give (DRAM bytes, tensor-pipe activity) come from the committed ncu passes:
+    profiles/ncu_metrics.json (written by tools/gpu/ncu_metrics.sh + tools/ncu_to_json.py; says which round)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_metrics.json"))).get(name) or {}
+    except Exception:
+        return {}
+
+
+def measure_roialign(steps, no_clocks, min_seconds=1.2, extras=True):
+    """BASELINE.json configs[2].  Timed region = back-to-back launches (CUDA events on the launching stream), each
     on the NEXT of 4 copies of the feature pyramid (4 x 91 MB of split-fp16 maps + 4 x 26 MB of outputs >> 126 MB L2), so
-    every launch finds its inputs in HBM, not in L2.  The single-launch, L2-flushed time is reported beside it."""
+    every launch finds its inputs in HBM, not in L2; the replay loop lasts >= ``min_seconds`` so that the 100 ms clock
+    sampler sees >= 5 samples under load.  The single-launch, L2-flushed time is reported beside it."""
     import torch
-    from glass_text_spotting_b200 import lib, ops
+    from glass_text_spotting_b200 import ops
     from glass_text_spotting_b200.ops import Act
-    wl = WORKLOADS["roialign_512"]
     feats, rois = _roialign_inputs()
     ncopy = 4
     acts = [[Act.from_nchw(f.cuda()) for f in feats] for _ in range(ncopy)]
@@ -658,19 +682,17 @@ def run_roialign(args):
     outs = [torch.empty((2, 512, 49 * 256), dtype=torch.float16, device="cuda") for _ in range(ncopy)]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
     scales = [1 / 4, 1 / 8, 1 / 16, 1 / 32, 1 / 64]
-    L = lib.load()
 
     def step(i):
         ops.roi_align_rotated(acts[i % ncopy], rois_d, (7, 7), scales, 2, out_f32=False,
                               out_split=(outs[i % ncopy], 7, 7, 0, 0, 256))
 
-    warm = max(args.warmup, 3)
-    for i in range(warm):
+    for i in range(4):
         step(i)
     torch.cuda.synchronize()
     # (1) single launch, L2 flushed by a 256 MB write before it
     ts = []
-    for i in range(min(args.steps, 20)):
+    for i in range(10):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -679,7 +701,7 @@ def run_roialign(args):
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     ms_flushed = sum(ts) / len(ts)
-    # (2) K back-to-back launches over rotating inputs, replayed from a CUDA graph of 2 rounds over the copies (the
+    # (2) back-to-back launches over rotating inputs, replayed from a CUDA graph of 2 rounds over the copies (the
     # Python/ctypes call costs as much host time as the kernel runs, so eager launches would time the host)
     per_graph = 2 * ncopy
     side = torch.cuda.Stream()
@@ -690,15 +712,21 @@ def run_roialign(args):
             for i in range(per_graph):
                 step(i)
     torch.cuda.current_stream().wait_stream(side)
-    replays = max(1, (args.steps + per_graph - 1) // per_graph)
-    args.steps = replays * per_graph
     graph.replay()
     torch.cuda.synchronize()
-    sampler = ClockSampler(0)
-    if not args.no_clocks:
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(20):
+        graph.replay()
+    c1.record()
+    torch.cuda.synchronize()
+    est = c0.elapsed_time(c1) / 20 / 1e3                      # seconds per replay
+    replays = max((steps + per_graph - 1) // per_graph, int(min_seconds / max(est, 1e-6)) + 1)
+    sampler = ClockSampler(torch.cuda.current_device())
+    if not no_clocks:
         sampler.start()
+        time.sleep(0.15)
     flush.zero_()
-    launches0 = L.glass_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
@@ -706,48 +734,99 @@ def run_roialign(args):
         graph.replay()
     e1.record()
     torch.cuda.synchronize()
-    launches = args.steps  # replayed graph nodes (glass_launch_count only sees the capture)
-    ms = e0.elapsed_time(e1) / args.steps
-    clocks = sampler.stop() if not args.no_clocks else None
+    launches = replays * per_graph
+    ms = e0.elapsed_time(e1) / launches
+    clocks = sampler.stop() if not no_clocks else None
     nbytes = _roialign_algorithmic_bytes(rois)
     peaks, src = _peaks()
     gbs = nbytes / (ms / 1e3) / 1e9
-    # comparison arm: detectron2's GPU formulation restated (fp32 NCHW, thread per output, one launch per level incl.
-    # the ROIPooler's index glue), same RoIs, rotating copies of the NCHW pyramid
-    feats_nchw = [[f.cuda().contiguous() for f in feats] for _ in range(ncopy)]
-    for i in range(3):
-        ops.baseline_roi_pooler_d2(feats_nchw[i % ncopy], rois_d, (7, 7), scales, 2)
-    torch.cuda.synchronize()
-    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    nb = 20
-    b0.record()
-    for i in range(nb):
-        ops.baseline_roi_pooler_d2(feats_nchw[i % ncopy], rois_d, (7, 7), scales, 2)
-    b1.record()
-    torch.cuda.synchronize()
-    d2_ms = b0.elapsed_time(b1) / nb
-    glass_shapes = _roialign_glass_shapes(rois_d[:100].contiguous(), flush)
+    dram = _ncu("roialign_512").get("dram_bytes_per_launch")
+    res = {"ms_per_launch": ms, "launches": launches, "timed_s": ms * launches / 1e3, "algorithmic_bytes": nbytes,
+           "gbs_algorithmic": gbs, "frac_algorithmic": gbs / peaks["hbm_gbs"],
+           "dram_bytes_per_launch_ncu": dram,
+           "gbs_dram": (dram / (ms / 1e3) / 1e9) if dram else None,
+           "frac_dram": (dram / (ms / 1e3) / 1e9 / peaks["hbm_gbs"]) if dram else None,
+           "peak_gbs": peaks["hbm_gbs"], "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({src})",
+           "single_launch_l2_flushed_ms": ms_flushed, "single_launch_l2_flushed_gbs": nbytes / (ms_flushed / 1e3) / 1e9,
+           "rois_per_s": 512 / (ms / 1e3), "clocks": clocks,
+           "kernel": "roi_align_rotated_split8_kernel<2>",
+           "l2": f"inputs larger than L2: launches rotate over {ncopy} copies of the pyramid and output "
+                 f"({ncopy} x 117 MB > 126 MB L2)"}
+    if extras:
+        res["glass_shapes"] = _roialign_glass_shapes(rois_d[:100].contiguous(), flush)
+    return res
+
+
+def run_roialign(args):
+    wl = WORKLOADS["roialign_512"]
+    r = measure_roialign(args.steps, args.no_clocks)
+    cfg = {"workload": wl["desc"], "name": "roialign_512", "l2": r["l2"], "rois_per_s": r["rois_per_s"],
+           "single_launch_l2_flushed_ms": r["single_launch_l2_flushed_ms"],
+           "single_launch_l2_flushed_gbs": r["single_launch_l2_flushed_gbs"], "glass_shapes": r.get("glass_shapes"),
+           "timed_s": r["timed_s"]}
     print(json.dumps({
-        "metric": "RotatedROIAlign GB/s (algorithmic bytes)", "value": gbs, "unit": "GB/s", "n_gpus": 1, "steps": args.steps,
-        "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32 (split-fp16 storage)", "data": "synthetic",
-        "config": {"workload": wl["desc"],
-                   "l2": f"inputs larger than L2: launches rotate over {ncopy} copies of the pyramid and output "
-                         f"({ncopy} x 117 MB > 126 MB L2)",
-                   "rois_per_s": 512 / (ms / 1e3),
-                   "single_launch_l2_flushed_ms": ms_flushed,
-                   "single_launch_l2_flushed_gbs": nbytes / (ms_flushed / 1e3) / 1e9,
-                   "d2_style_baseline_ms": d2_ms, "d2_style_baseline_gbs": nbytes / (d2_ms / 1e3) / 1e9,
-                   "speedup_vs_d2_style": d2_ms / ms,
-                   "glass_shapes": glass_shapes,
-                   "d2_style_baseline": "detectron2 v0.6 ROIPooler + ROIAlignRotated CUDA formulation restated "
-                                        "(csrc/baseline_d2.cu: fp32 NCHW, one thread per output element, one launch per "
-                                        "level); detectron2 itself cannot be built offline"},
-        "gpu_launches": launches, "clocks": clocks,
-        "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-                     "traffic": _traffic("roialign_512"), "kernel": "roi_align_rotated_split8_kernel<2>",
-                     "algorithmic_bytes": nbytes,
-                     "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({src})"}}))
+        "metric": "RotatedROIAlign GB/s (algorithmic bytes)", "value": r["gbs_algorithmic"], "unit": "GB/s", "n_gpus": 1,
+        "steps": r["launches"], "warmup": 4, "ms_per_step": r["ms_per_launch"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 (split-fp16 storage)", "data": "synthetic", "config": cfg,
+        "gpu_launches": r["launches"], "clocks": r["clocks"],
+        "roofline": {"bound": "hbm", "achieved": r["gbs_algorithmic"], "peak": r["peak_gbs"], "unit": "GB/s",
+                     "frac": r["frac_algorithmic"], "traffic": r["dram_bytes_per_launch_ncu"],
+                     "achieved_dram_gbs": r["gbs_dram"], "frac_dram": r["frac_dram"], "kernel": r["kernel"],
+                     "algorithmic_bytes": r["algorithmic_bytes"], "peak_source": r["peak_source"]}}))
+
+
+def measure_backbone(min_seconds=1.2, no_clocks=False, mode=0):
+    """BASELINE.json configs[1]: ResNet-50 + FPN, bs = 8, 1024x1024, inputs resident in HBM, rotating between 2 batches;
+    the timed loop lasts >= ``min_seconds`` with the clock sampler running."""
+    import torch
+    from glass_text_spotting_b200 import ops, weights
+    from glass_text_spotting_b200.modeling.backbone import B200ResNetFPN
+    B, H, W = 8, 1024, 1024
+    g = torch.Generator().manual_seed(1000)
+    dev = [torch.randint(0, 256, (B, 3, H, W), generator=g, dtype=torch.uint8).cuda().float() for _ in range(2)]
+    model = B200ResNetFPN(weights.random_backbone_state_dict(0), mode=mode)
+    for i in range(3):
+        model(dev[i % 2])
+    torch.cuda.synchronize()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for i in range(4):
+        model(dev[i % 2])
+    c1.record()
+    torch.cuda.synchronize()
+    steps = int(min_seconds / (c0.elapsed_time(c1) / 4 / 1e3)) + 1
+    sampler = ClockSampler(torch.cuda.current_device())
+    if not no_clocks:
+        sampler.start()
+        time.sleep(0.15)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        model(dev[i % 2])
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) / 1e3
+    clocks = sampler.stop() if not no_clocks else None
+    ops.PROFILE = []
+    for i in range(2):
+        model(dev[i % 2])
+    torch.cuda.synchronize()
+    gemm_ms = sum(r[0].elapsed_time(r[1]) for r in ops.PROFILE) / 2
+    gemm_flops = sum(r[2] for r in ops.PROFILE) / 2
+    ops.PROFILE = None
+    peaks, src = _peaks()
+    peak = peaks["bf16_tflops_sustained"]
+    ach = gemm_flops / (gemm_ms / 1e3) / 1e12
+    mul = 1 if mode else 3
+    nc = _ncu("backbone_bs8")
+    del model
+    return {"images_s": B * steps / t, "ms_per_step": 1e3 * t / steps, "steps": steps, "timed_s": t,
+            "conv_gemm_ms_per_step": gemm_ms, "algorithmic_tflops": ach, "algorithmic_frac": ach / peak,
+            "issued_tflops": ach * mul, "issued_frac": ach * mul / peak,
+            "tensor_pipe_active_pct": nc.get("time_weighted_tensor_pipe_active_pct"),
+            "tensor_pipe_active_pct_mma_bound_layers": nc.get("tensor_pipe_active_pct_mma_bound_layers"),
+            "tensor_pipe_source": nc.get("source"), "peak_tflops": peak,
+            "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({src})", "clocks": clocks}
 
 
 # ============================================================================================ B200 arm
@@ -900,13 +979,12 @@ def run_b200(args):
         peaks, peak_src = _peaks()
         peak = peaks["bf16_tflops_sustained"]
         achieved = gemm_flops / (gemm_ms / 1e3) / 1e12
-        cfg = {"workload": wl["desc"], "global_batch": world * B, "parallelism": f"image-sharded x{world}",
-               "l2": "inputs rotated between 2 batches; per-step working set (GBs of activations) >> 126 MB L2",
-               "weights": "random init (seeded), BatchNorm folded",
-               "kb_per_chunk": ops.KB_PER_CHUNK or "2 (backbone, RPN, box head), 4 (per-word recognizer convs)"}
+        cfg = _config(args.workload, world)
+        run = {"kb_per_chunk": ops.KB_PER_CHUNK or "2 (backbone, RPN, box head), 4 (per-word recognizer convs)"}
         if full:
-            cfg["words_per_step"] = words_per_step
-            cfg["collective"] = "one NCCL all-gather of packed detection records per step" if world > 1 else "none (N=1)"
+            run["words_per_step"] = words_per_step
+            run["collective"] = "one NCCL all-gather of packed detection records per step" if world > 1 else "none (N=1)"
+        nc = _ncu(args.workload)
         out = {
             "metric": "images/sec @1024x1024", "value": world * B * args.steps / t_dev, "unit": "images/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -914,7 +992,7 @@ def run_b200(args):
             "vs_baseline": None,
             "dtype": "fp16 (single tcgen05 pass)" if args.fast else
                      "fp16x3 split (22-bit operands, 3 tcgen05 MMAs per product, chunked fp32 RN accumulation)",
-            "data": "synthetic", "config": cfg,
+            "data": "synthetic", "config": cfg, "run": run,
             "e2e": {"value": world * B * args.steps / t_e2e, "unit": "images/s",
                     "h2d_bytes_per_step": B * 3 * H * W, "d2h_bytes_per_step": d2h_bytes,
                     "note": "pinned host uint8 batch -> H2D (copy stream, overlapped with the previous step) -> hot path -> "
@@ -923,21 +1001,33 @@ def run_b200(args):
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": _traffic(args.workload),
+                         "frac": achieved / peak, "traffic": nc.get("dram_bytes_per_step"),
                          "traffic_note": "dram__bytes_read+write summed over the step's conv_gemm launches (ncu, "
-                                         "profiles/r01_traffic.json); null when no capture exists for this workload",
+                                         "profiles/ncu_metrics.json); null when no capture exists for this workload",
                          "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM), all launches of one step",
                          "launches_per_step": n_gemm, "kernel_ms_per_step": gemm_ms,
                          "kernel_share_of_step": gemm_ms / (1e3 * t_dev / args.steps),
                          "algorithmic_flops_per_step": gemm_flops,
                          "issued_mma_flops_per_step": gemm_flops * (1 if args.fast else 3),
+                         "issued_frac": achieved * (1 if args.fast else 3) / peak,
+                         "tensor_pipe_active_pct_ncu": nc.get("time_weighted_tensor_pipe_active_pct"),
                          # SURVEY.md 8d cfg 4: the WHOLE step against t_min = algorithmic FLOPs / tensor peak (the gather
                          # term bytes / HBM peak is < 0.1 ms and is left out)
                          "whole_step_frac_of_tensor_roofline": (gemm_flops / (peak * 1e12)) / (t_dev / args.steps),
                          "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src})"},
         }
+        if world == 1 and full and not args.no_submetrics:
+            # BASELINE.json's metric names three quantities; the other two are measured here, in the same process on the
+            # same GPU right after the timed region, each in a >= 1.2 s loop with its own clock record
+            del model
+            torch.cuda.empty_cache()
+            out["submetrics"] = {
+                "backbone": dict(measure_backbone(no_clocks=args.no_clocks, mode=mode),
+                                 workload=WORKLOADS["backbone_bs8"]["desc"]),
+                "roialign": dict(measure_roialign(64, args.no_clocks, extras=False),
+                                 workload=WORKLOADS["roialign_512"]["desc"])}
         if world == 1 and not args.no_cpu:
-            v, cores, sample = cpu_sample(wl, repeats=1 if full else 3)
+            v, cores, sample = cpu_sample(wl, repeats=2 if full else 3)
             out["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}
             if not full:
                 out["config"]["torch_cudnn_informational"] = _torch_backbone_on_gpu(B, H, W)
@@ -955,6 +1045,7 @@ def main():
     ap.add_argument("--workload", default="full_bs4", choices=sorted(WORKLOADS))
     ap.add_argument("--fast", action="store_true", help="single-pass fp16 (NOT the parity precision)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-submetrics", action="store_true", help="skip the backbone / RoIAlign sub-benches of full_bs4")
     ap.add_argument("--no-clocks", action="store_true", help="do not spawn the nvidia-smi clock sampler (ncu runs)")
     args = ap.parse_args()
     if args.impl == "reference":

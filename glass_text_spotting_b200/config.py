@@ -185,6 +185,28 @@ def check_supported(cfg: CfgNode) -> None:
         _require(cfg, m + "ROI_MASK_HEAD.POOLER_RESOLUTION", 14)
         _require(cfg, m + "ROI_MASK_HEAD.POOLER_TYPE", "ROIAlignRotated")
         _require(cfg, m + "ROI_MASK_HEAD.NORM", "")
+    # hard numeric limits of the kernels (a YAML that omits these keys inherits detectron2's defaults, e.g. RPN top-k
+    # 6000 / 1000, which the device path cannot hold): refuse here, by key, not at the first image
+    M = cfg.MODEL
+    rec = M.ROI_RECOGNIZER_HEAD
+    n_anchor_levels = len(M.ANCHOR_GENERATOR.SIZES)
+    for dotted, value, limit, why in (
+            ("MODEL.RPN.PRE_NMS_TOPK_TEST", int(M.RPN.PRE_NMS_TOPK_TEST), 1024, "per-level top-k is sorted in one CTA (csrc/detect.cu)"),
+            ("MODEL.RPN.PRE_NMS_TOPK_TEST x levels", n_anchor_levels * int(M.RPN.PRE_NMS_TOPK_TEST), 8192,
+             "the proposal NMS holds at most 8192 candidates per image"),
+            ("MODEL.RPN.POST_NMS_TOPK_TEST", int(M.RPN.POST_NMS_TOPK_TEST), 128, "NMS max_keep <= 128"),
+            ("TEST.DETECTIONS_PER_IMAGE", int(cfg.TEST.DETECTIONS_PER_IMAGE), 128,
+             "NMS max_keep and the device post-processor hold <= 128 detections per image"),
+            ("MODEL.ROI_RECOGNIZER_HEAD.POOLER_RESOLUTION_WIDTH", int(rec.POOLER_RESOLUTION_WIDTH), 32,
+             "the decoder attends over T <= 32 positions"),
+            ("len(MODEL.ROI_RECOGNIZER_HEAD.CHARACTER_SET) + 2", len(rec.CHARACTER_SET) + 2, 128, "decoder classes <= 128"),
+            ("MODEL.ROI_RECOGNIZER_HEAD.MAX_WORD_LENGTH + 1", int(rec.MAX_WORD_LENGTH) + 1, 64, "decoding steps <= 64")):
+        if value > limit or value < 1:
+            raise UnsupportedConfig(f"{dotted} = {value}: outside the device path's range [1, {limit}] ({why})")
+    if int(rec.POOLER_RESOLUTION_HEIGHT) != 8 or int(rec.POOLER_RESOLUTION_WIDTH) != 32:
+        raise UnsupportedConfig("MODEL.ROI_RECOGNIZER_HEAD.POOLER_RESOLUTION_HEIGHT/WIDTH = "
+                                f"{rec.POOLER_RESOLUTION_HEIGHT}/{rec.POOLER_RESOLUTION_WIDTH}: the recognizer is built for the "
+                                "8 x 32 pooler of the shipped configs (local crops 128 x 128, T = 32)")
     if len(cfg.MODEL.ANCHOR_GENERATOR.ASPECT_RATIOS) != 1 or len(cfg.MODEL.ANCHOR_GENERATOR.ANGLES) != 1:
         raise UnsupportedConfig("MODEL.ANCHOR_GENERATOR.ASPECT_RATIOS / ANGLES: one list shared by all levels expected")
     if len(cfg.MODEL.ANCHOR_GENERATOR.SIZES) != 5 or any(len(s) != 1 for s in cfg.MODEL.ANCHOR_GENERATOR.SIZES):

@@ -62,6 +62,9 @@ struct GemmKernelParams {
   float* out_f32;
   int32_t out_hp, out_wp, out_border;
   int32_t ld_out, ld_f32, n_store;
+  // live M extent on the device: rows_m = min(rows_m, *m_count_dev * m_rows_per_count) (detections of this step)
+  const int32_t* m_count_dev;
+  int32_t m_rows_per_count;
 };
 
 // PAIR = true: two CTAs of a cluster (one TPC) cooperate through tcgen05 cta_group::2 -- an M = 256 tile pair
@@ -98,8 +101,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   const bool leader = rank == 0;
   const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int num_workers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int units_m = PAIR ? (p.tiles_m + 1) / 2 : p.tiles_m;
-  const int num_units = units_m * p.tiles_n;
   const int b_rows = PAIR ? p.bn / 2 : p.bn;  // weight-tile rows staged by this CTA
 
   if (warp == 0 && lane == 0) {
@@ -137,6 +138,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail;
   // global memory written by it may only be touched from here on
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  // M extent: the host's worst case, or the live count a previous kernel of the stream left on the device (the number
+  // of detected words) -- the persistent grid simply walks fewer tiles, nothing is re-planned on the host
+  int64_t rows_m = p.rows_m;
+  int tiles_m = p.tiles_m;
+  if (p.m_count_dev != nullptr) {
+    const int64_t live = (int64_t)max(*reinterpret_cast<const volatile int32_t*>(p.m_count_dev), 0) * p.m_rows_per_count;
+    if (live < rows_m) {
+      rows_m = live;
+      tiles_m = (int)((rows_m + BM - 1) / BM);
+    }
+  }
+  const int units_m = PAIR ? (tiles_m + 1) / 2 : tiles_m;
+  const int num_units = units_m * p.tiles_n;
 
   // Register re-balancing between the warpgroups (the launch gives every thread 168): the control
   // warpgroup needs few registers, the two epilogue warpgroups hold the whole 128 x BN fp32 tile.
@@ -345,7 +359,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       const int tm = PAIR ? um * 2 + (int)rank : um;
       const int n0 = tn * p.bn;
       const int64_t m = (int64_t)tm * BM + row_in_tile;
-      bool valid = m < p.rows_m;
+      bool valid = m < rows_m;
       int64_t out_row = 0, res_row = 0;
       if (valid) {
         const int img = (int)(m / plane);
@@ -662,6 +676,9 @@ extern "C" int glass_conv_gemm(const GlassConvGemmParams* p, void* stream_v) {
   k.out_hi = (__half*)p->out_hi; k.out_lo = (__half*)p->out_lo; k.out_f32 = p->out_f32;
   k.out_hp = p->out_hp; k.out_wp = p->out_wp; k.out_border = p->out_border;
   k.ld_out = p->ld_out; k.ld_f32 = p->ld_f32; k.n_store = n_store;
+  k.m_count_dev = p->m_count_dev;
+  k.m_rows_per_count = p->m_rows_per_count;
+  if (p->m_count_dev) GLASS_CHECK(p->m_rows_per_count > 0, "m_count_dev needs m_rows_per_count > 0");
 
   // always ask for > half of the SM's shared memory: exactly one CTA per SM owns all 512 TMEM columns
   const int smem_bytes = k.ring_bytes + EPI_STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;

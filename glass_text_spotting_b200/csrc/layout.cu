@@ -83,56 +83,12 @@ __global__ void nhwc_f32_to_nchw_kernel(const float* __restrict__ src, int n, in
   }
 }
 
-// ------------------------------------------------------------------ stem im2col (7x7 s2 p3, Cin 3)
-// One thread per (output pixel, 8-wide k group).  k = (r*7+s)*3 + c.
-__global__ void stem_im2col_kernel(const float* __restrict__ img, int n, int h, int w, float m0, float m1, float m2,
-                                   float is0, float is1, float is2, __half* __restrict__ dhi,
-                                   __half* __restrict__ dlo, int kp) {
-  const int ho = h / 2, wo = w / 2;
-  const int groups = kp / 8;
-  const int64_t total = (int64_t)n * ho * wo * groups;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int g = (int)(i % groups);
-    const int64_t pix = i / groups;
-    const int x = (int)(pix % wo);
-    const int y = (int)((pix / wo) % ho);
-    const int b = (int)(pix / ((int64_t)wo * ho));
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = g * 8 + j;
-      float val = 0.f;
-      if (k < 147) {
-        const int tap = k / 3, c = k - tap * 3;
-        const int r = tap / 7, s = tap - r * 7;
-        const int iy = 2 * y - 3 + r, ix = 2 * x - 3 + s;
-        if (iy >= 0 && iy < h && ix >= 0 && ix < w) {
-          const float raw = __ldg(img + (((int64_t)b * 3 + c) * h + iy) * w + ix);
-          const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2);
-          const float is = c == 0 ? is0 : (c == 1 ? is1 : is2);
-          val = (raw - mean) * is;
-        }
-      }
-      v[j] = val;
-    }
-    uint32_t hw[4], lw[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      __half h0, l0, h1, l1;
-      split16(v[2 * j], h0, l0);
-      split16(v[2 * j + 1], h1, l1);
-      hw[j] = pack16x2(h0, h1);
-      lw[j] = pack16x2(l0, l1);
-    }
-    *reinterpret_cast<uint4*>(dhi + pix * kp + g * 8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-    *reinterpret_cast<uint4*>(dlo + pix * kp + g * 8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-  }
-}
-
 // ------------------------------------------------------------------ generic tap gather
 __global__ void gather_taps_kernel(const uint4* __restrict__ shi, const uint4* __restrict__ slo, int n, int h, int w,
                                    int cv /*cp/8*/, int border, int kh, int kw, int sh, int sw, int ph, int pw,
-                                   int ho, int wo, uint4* __restrict__ dhi, uint4* __restrict__ dlo) {
+                                   int ho, int wo, uint4* __restrict__ dhi, uint4* __restrict__ dlo,
+                                   const int32_t* __restrict__ n_dev) {
+  if (n_dev) n = min(n, max(*n_dev, 0));  // live image / word count left on the device by an earlier kernel
   const int taps = kh * kw;
   const int64_t total = (int64_t)n * ho * wo * taps * cv;
   const int hp = h + 2 * border, wp = w + 2 * border;
@@ -201,7 +157,9 @@ __global__ void stem_s2d_kernel(const float* __restrict__ img, int n, int h, int
 }
 
 // ------------------------------------------------------------------ border re-zero (border = 1)
-__global__ void zero_border_kernel(uint4* __restrict__ hi, uint4* __restrict__ lo, int n, int hp, int wp, int cv) {
+__global__ void zero_border_kernel(uint4* __restrict__ hi, uint4* __restrict__ lo, int n, int hp, int wp, int cv,
+                                   const int32_t* __restrict__ n_dev) {
+  if (n_dev) n = min(n, max(*n_dev, 0));
   const int per_img = 2 * wp + 2 * (hp - 2);
   const int64_t total = (int64_t)n * per_img * cv;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -222,7 +180,9 @@ __global__ void zero_border_kernel(uint4* __restrict__ hi, uint4* __restrict__ l
 // ------------------------------------------------------------------ max pool (padding = -inf)
 __global__ void maxpool_kernel(const uint4* __restrict__ shi, const uint4* __restrict__ slo, int n, int h, int w,
                                int cv, int border, int kh, int kw, int sh, int sw, int ph, int pw, int ho, int wo,
-                               uint4* __restrict__ dhi, uint4* __restrict__ dlo, int dborder) {
+                               uint4* __restrict__ dhi, uint4* __restrict__ dlo, int dborder,
+                               const int32_t* __restrict__ n_dev) {
+  if (n_dev) n = min(n, max(*n_dev, 0));
   const int64_t total = (int64_t)n * ho * wo * cv;
   const int hp = h + 2 * border, wp = w + 2 * border;
   const int dhp = ho + 2 * dborder, dwp = wo + 2 * dborder;
@@ -354,20 +314,6 @@ extern "C" int glass_nhwc_f32_to_nchw(const float* src, int n, int c, int h, int
   return 0;
 }
 
-extern "C" int glass_stem_im2col(const float* img, int n, int h, int w, const float* mean, const float* inv_std,
-                                 void* dst_hi, void* dst_lo, int kp, void* stream) {
-  GLASS_CHECK(img && mean && inv_std && dst_hi && dst_lo, "null pointer (mean / inv_std are HOST float[3])");
-  GLASS_CHECK(n > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0, "h, w must be even");
-  GLASS_CHECK(kp >= 152 && kp % 64 == 0, "kp must be a multiple of 64 >= 192");
-  const int64_t total = (int64_t)n * (h / 2) * (w / 2) * (kp / 8);
-  stem_im2col_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>(img, n, h, w, mean[0], mean[1], mean[2], inv_std[0],
-                                                               inv_std[1], inv_std[2], (__half*)dst_hi,
-                                                               (__half*)dst_lo, kp);
-  count_launch();
-  GLASS_CUDA(cudaGetLastError());
-  return 0;
-}
-
 extern "C" int glass_stem_s2d(const float* img, int n, int h, int w, const float* mean, const float* inv_std,
                               void* dst_hi, void* dst_lo, void* stream) {
   GLASS_CHECK(img && mean && inv_std && dst_hi && dst_lo, "null pointer");
@@ -383,25 +329,25 @@ extern "C" int glass_stem_s2d(const float* img, int n, int h, int w, const float
 
 extern "C" int glass_gather_taps(const void* src_hi, const void* src_lo, int n, int h, int w, int cp, int border,
                                  int kh, int kw, int sh, int sw, int ph, int pw, int ho, int wo, void* dst_hi,
-                                 void* dst_lo, void* stream) {
+                                 void* dst_lo, const int32_t* n_dev, void* stream) {
   GLASS_CHECK(src_hi && src_lo && dst_hi && dst_lo, "null pointer");
   GLASS_CHECK(n > 0 && h > 0 && w > 0 && cp % 8 == 0 && kh > 0 && kw > 0 && sh > 0 && sw > 0 && ho > 0 && wo > 0,
               "bad shape");
   const int64_t total = (int64_t)n * ho * wo * kh * kw * (cp / 8);
   gather_taps_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>((const uint4*)src_hi, (const uint4*)src_lo, n, h, w,
                                                                cp / 8, border, kh, kw, sh, sw, ph, pw, ho, wo,
-                                                               (uint4*)dst_hi, (uint4*)dst_lo);
+                                                               (uint4*)dst_hi, (uint4*)dst_lo, n_dev);
   count_launch();
   GLASS_CUDA(cudaGetLastError());
   return 0;
 }
 
-extern "C" int glass_zero_border(void* hi, void* lo, int n, int h, int w, int cp, void* stream) {
+extern "C" int glass_zero_border(void* hi, void* lo, int n, int h, int w, int cp, const int32_t* n_dev, void* stream) {
   GLASS_CHECK(hi && lo, "null pointer");
   GLASS_CHECK(n > 0 && h > 0 && w > 0 && cp > 0 && cp % 8 == 0, "bad shape");
   const int hp = h + 2, wp = w + 2;
   const int64_t total = (int64_t)n * (2 * wp + 2 * (hp - 2)) * (cp / 8);
-  zero_border_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>((uint4*)hi, (uint4*)lo, n, hp, wp, cp / 8);
+  zero_border_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>((uint4*)hi, (uint4*)lo, n, hp, wp, cp / 8, n_dev);
   count_launch();
   GLASS_CUDA(cudaGetLastError());
   return 0;
@@ -409,14 +355,14 @@ extern "C" int glass_zero_border(void* hi, void* lo, int n, int h, int w, int cp
 
 extern "C" int glass_maxpool(const void* src_hi, const void* src_lo, int n, int h, int w, int cp, int border, int kh,
                              int kw, int sh, int sw, int ph, int pw, int ho, int wo, void* dst_hi, void* dst_lo,
-                             int dst_border, void* stream) {
+                             int dst_border, const int32_t* n_dev, void* stream) {
   GLASS_CHECK(src_hi && src_lo && dst_hi && dst_lo, "null pointer");
   GLASS_CHECK(n > 0 && h > 0 && w > 0 && cp % 8 == 0 && kh > 0 && kw > 0 && sh > 0 && sw > 0 && ho > 0 && wo > 0,
               "bad shape");
   const int64_t total = (int64_t)n * ho * wo * (cp / 8);
   maxpool_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>((const uint4*)src_hi, (const uint4*)src_lo, n, h, w,
                                                            cp / 8, border, kh, kw, sh, sw, ph, pw, ho, wo,
-                                                           (uint4*)dst_hi, (uint4*)dst_lo, dst_border);
+                                                           (uint4*)dst_hi, (uint4*)dst_lo, dst_border, n_dev);
   count_launch();
   GLASS_CUDA(cudaGetLastError());
   return 0;

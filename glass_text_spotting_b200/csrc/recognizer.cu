@@ -55,9 +55,11 @@ struct GcParams {
   const float* ln_b;     // [256]
   const float* w2t;      // [256][512]
   const float* b2;       // [512]
+  const int32_t* n_words_dev;  // optional live word count (the grid covers the capacity)
 };
 
 __global__ void __launch_bounds__(256) gc_attention_kernel(const GcParams p) {
+  if (p.n_words_dev && (int)blockIdx.x >= *p.n_words_dev) return;
   extern __shared__ float sm[];
   const int P = p.h * p.w;              // positions (256)
   float* logit = sm;                    // [8][P] -> attention weights
@@ -222,7 +224,8 @@ __global__ void __launch_bounds__(256) gc_attention_kernel(const GcParams p) {
 // ------------------------------------------------------------------------------------------ mean over H
 __global__ void hmean_rows_kernel(const __half* __restrict__ shi, const __half* __restrict__ slo, int n, int h, int w,
                                   int cp, int border, __half* __restrict__ dhi, __half* __restrict__ dlo,
-                                  float* __restrict__ df32) {
+                                  float* __restrict__ df32, const int32_t* __restrict__ n_dev) {
+  if (n_dev) n = min(n, max(*n_dev, 0));
   const int cpairs = cp / 2;
   const int64_t total = (int64_t)n * w * cpairs;
   const int hp = h + 2 * border, wp = w + 2 * border;
@@ -920,6 +923,7 @@ extern "C" int glass_gc_attention(const GlassGcAttentionParams* p, void* stream)
   k.h = p->h; k.w = p->w; k.border = p->border;
   k.w_mask = p->w_mask; k.b_mask = p->b_mask; k.w1t = p->w1t; k.b1 = p->b1; k.ln_g = p->ln_g; k.ln_b = p->ln_b;
   k.w2t = p->w2t; k.b2 = p->b2;
+  k.n_words_dev = p->n_words_dev;
   const int smem = (GC_HEADS * p->h * p->w + GC_C + GC_HID + GC_C) * (int)sizeof(float);
   gc_attention_kernel<<<p->n_words, 256, smem, STREAM>>>(k);
   count_launch();
@@ -928,7 +932,7 @@ extern "C" int glass_gc_attention(const GlassGcAttentionParams* p, void* stream)
 }
 
 extern "C" int glass_hmean_rows(const void* src_hi, const void* src_lo, int n, int h, int w, int cp, int border,
-                                void* dst_hi, void* dst_lo, float* dst_f32, void* stream) {
+                                void* dst_hi, void* dst_lo, float* dst_f32, const int32_t* n_dev, void* stream) {
   GLASS_CHECK(src_hi && src_lo && dst_hi && dst_lo, "null pointer");
   GLASS_CHECK(n >= 0 && h > 0 && w > 0 && cp % 2 == 0, "bad shape");
   if (n == 0) return 0;
@@ -936,7 +940,7 @@ extern "C" int glass_hmean_rows(const void* src_hi, const void* src_lo, int n, i
   int64_t blocks = (total + 255) / 256;
   if (blocks > (int64_t)num_sms() * 16) blocks = (int64_t)num_sms() * 16;
   hmean_rows_kernel<<<(int)blocks, 256, 0, STREAM>>>((const __half*)src_hi, (const __half*)src_lo, n, h, w, cp, border,
-                                                     (__half*)dst_hi, (__half*)dst_lo, dst_f32);
+                                                     (__half*)dst_hi, (__half*)dst_lo, dst_f32, n_dev);
   count_launch();
   GLASS_CUDA(cudaGetLastError());
   return 0;
@@ -949,7 +953,7 @@ extern "C" int glass_lstm_bidir(const float* gates_in, const float* whh_t, int n
   GLASS_CHECK(n_seq >= 0 && T > 0, "bad shape");
   if (n_seq == 0) return 0;
   // 16 words per CTA once that still fills >= 40 SMs (the L2 stream of W_hh^T is the bound), else 8
-  static const int cluster_env = getenv("GLASS_LSTM_CLUSTER") ? atoi(getenv("GLASS_LSTM_CLUSTER")) : 0;
+  static const int cluster_env = getenv("GLASS_LSTM_CLUSTER") ? atoi(getenv("GLASS_LSTM_CLUSTER")) : 1;
   if (cluster_env) {   // opt-in: parity-tested on B200, not yet timed (see lstm_cluster_mma_kernel)
     GLASS_CUDA(cudaFuncSetAttribute(lstm_cluster_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LC_SMEM));
     dim3 grid(((n_seq + LC_W - 1) / LC_W) * LC_R, 2);

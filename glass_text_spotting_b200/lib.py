@@ -11,11 +11,11 @@ MAX_LEVELS = 5
 # every symbol include/glass_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "glass_last_error", "glass_abi_version", "glass_launch_count", "glass_conv_gemm", "glass_pack_nchw",
-    "glass_unpack_nchw", "glass_nhwc_f32_to_nchw", "glass_stem_im2col", "glass_gather_taps", "glass_maxpool",
+    "glass_unpack_nchw", "glass_nhwc_f32_to_nchw", "glass_gather_taps", "glass_maxpool",
     "glass_roi_align_rotated", "glass_image_roi_align_rotated", "glass_rpn_topk_decode", "glass_rpn_topk_workspace_bytes",
     "glass_nms_workspace_bytes",
     "glass_nms_rotated", "glass_box_decode", "glass_gc_attention", "glass_hmean_rows", "glass_lstm_bidir",
-    "glass_aster_decode", "glass_aster_finalize", "glass_resize_bilinear_u8", "glass_postprocess_merge", "glass_text_scores", "glass_zero_border", "glass_stem_s2d", "glass_baseline_roi_align_rotated_d2", "glass_mask_finalize", "glass_paste_masks_rotated",
+    "glass_aster_decode", "glass_aster_finalize", "glass_resize_bilinear_u8", "glass_postprocess_merge", "glass_text_scores", "glass_zero_border", "glass_stem_s2d", "glass_mask_finalize", "glass_paste_masks_rotated",
     "glass_box_iou_rotated", "glass_nms_rotated_all", "glass_nms_rotated_all_workspace_bytes", "glass_aster_decode_pre",
 ]
 
@@ -32,7 +32,7 @@ class ConvGemmParams(C.Structure):
         ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("out_f32", C.c_void_p),
         ("out_hp", C.c_int32), ("out_wp", C.c_int32), ("out_border", C.c_int32),
         ("ld_out", C.c_int32), ("ld_f32", C.c_int32), ("n_store", C.c_int32), ("kb_per_chunk", C.c_int32), ("pair_mode", C.c_int32), ("tap_mode", C.c_int32),
-        ("a_col0", C.c_int32), ("a_inner", C.c_int32),
+        ("a_col0", C.c_int32), ("a_inner", C.c_int32), ("m_count_dev", C.c_void_p), ("m_rows_per_count", C.c_int32),
     ]
 
 
@@ -135,7 +135,6 @@ def load() -> C.CDLL:
     lib.glass_pack_nchw.argtypes = [p, i, i, i, i, p, p, i, i, p]
     lib.glass_unpack_nchw.argtypes = [p, p, i, i, i, i, i, i, p, p]
     lib.glass_nhwc_f32_to_nchw.argtypes = [p, i, i, i, i, i, i, p, p]
-    lib.glass_stem_im2col.argtypes = [p, i, i, i, f, f, p, p, i, p]
     lib.glass_gather_taps.argtypes = [p, p] + [i] * 13 + [p, p, p]
     lib.glass_maxpool.argtypes = [p, p] + [i] * 13 + [p, p, i, p]
     lib.glass_roi_align_rotated.argtypes = [C.POINTER(RoiAlignParams), p]
@@ -164,7 +163,6 @@ def load() -> C.CDLL:
     lib.glass_nms_rotated_all_workspace_bytes.argtypes = [i]
     lib.glass_nms_rotated_all_workspace_bytes.restype = C.c_int64
     lib.glass_nms_rotated_all.argtypes = [p, p, i, C.c_float, p, p, p, C.c_int64, p]
-    lib.glass_baseline_roi_align_rotated_d2.argtypes = [p, i, i, i, i, p, i, C.c_float, i, i, i, p, p]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if name.startswith("glass_") and name not in ("glass_last_error", "glass_abi_version", "glass_launch_count",

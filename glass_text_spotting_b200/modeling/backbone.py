@@ -75,7 +75,7 @@ class B200ResNetFPN:
     """Backbone.forward(Tensor[N,3,H,W]) -> dict of Acts (d2 Backbone contract).
 
     ``forward`` takes the RAW image batch (fp32 NCHW, BGR, unnormalised, already padded to /32): the
-    (x - pixel_mean)/pixel_std of GeneralizedRCNN.preprocess_image is fused into the stem's im2col."""
+    (x - pixel_mean)/pixel_std of GeneralizedRCNN.preprocess_image is fused into the stem's space-to-depth pre-pass."""
 
     size_divisibility = 32
     out_features = ("p2", "p3", "p4", "p5", "p6")
@@ -89,10 +89,7 @@ class B200ResNetFPN:
         s = "bottom_up.stem.conv1"
         scale, bias = packing.fold_bn(sd[s + ".norm.weight"], sd[s + ".norm.bias"], sd[s + ".norm.running_mean"],
                                       sd[s + ".norm.running_var"])
-        self.stem = packing.pack_stem(sd[s + ".weight"], scale, bias, device=device)
         self.stem_s2d = packing.pack_stem_s2d(sd[s + ".weight"], scale, bias, device=device)
-        # GLASS_STEM=im2col: the materialised-im2col stem (kept for A/B and as the reference of the s2d form)
-        self.use_s2d = os.environ.get("GLASS_STEM", "s2d") != "im2col"
         self.blocks = {}
         for i, (nb, stage) in enumerate(zip([3, 4, 6, 3], ["res2", "res3", "res4", "res5"])):
             blks = []
@@ -154,20 +151,14 @@ class B200ResNetFPN:
         assert h % 32 == 0 and w % 32 == 0, "pad the batch to size_divisibility first (ImageList.from_tensors)"
         ws = self.ws
         s1 = ws.act("stem.conv", n, 64, h // 2, w // 2)
-        if self.use_s2d:
-            # normalise + space-to-depth, then the 7x7/s2 conv as a 4x4/s1 conv: 4 compact-channel k-blocks (one per
-            # s2d row Y-2..Y+1, each spanning the 4 pixels X-2..X+1 of 16 channels) straight from the 17 MB/image map
-            hp2, wp2 = h // 2 + 4, w // 2 + 4
-            s2d = ws.raw("stem.s2d", (2, n, hp2, wp2, 16), zero=True)
-            ops.stem_s2d(images, self.pixel_mean, self.pixel_std, out=s2d)
-            shifts = [(i - 2) * wp2 - 2 for i in range(4)]
-            ops.conv_gemm(s2d[0], s2d[1], n * hp2 * wp2, 64, shifts, self.stem_s2d, (n, hp2, wp2, 2), out=s1,
-                          relu_post=True, mode=self.mode, a_ld=16)
-        else:
-            cols = ws.raw("stem.cols", (2, n * (h // 2) * (w // 2), 192))
-            ops.stem_im2col(images, self.pixel_mean, self.pixel_std, out=cols)
-            ops.conv_gemm(cols[0], cols[1], cols.shape[1], 192, [0], self.stem, (n, h // 2, w // 2, 0), out=s1,
-                          relu_post=True, mode=self.mode)
+        # normalise + space-to-depth, then the 7x7/s2 conv as a 4x4/s1 conv: 4 compact-channel k-blocks (one per
+        # s2d row Y-2..Y+1, each spanning the 4 pixels X-2..X+1 of 16 channels) straight from the 17 MB/image map
+        hp2, wp2 = h // 2 + 4, w // 2 + 4
+        s2d = ws.raw("stem.s2d", (2, n, hp2, wp2, 16), zero=True)
+        ops.stem_s2d(images, self.pixel_mean, self.pixel_std, out=s2d)
+        shifts = [(i - 2) * wp2 - 2 for i in range(4)]
+        ops.conv_gemm(s2d[0], s2d[1], n * hp2 * wp2, 64, shifts, self.stem_s2d, (n, hp2, wp2, 2), out=s1,
+                      relu_post=True, mode=self.mode, a_ld=16)
         x = ws.act("stem.pool", n, 64, h // 4, w // 4)
         ops.maxpool2d(s1, (3, 3), (2, 2), (1, 1), out=x)
         feats = {}

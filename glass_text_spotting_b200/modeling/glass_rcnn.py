@@ -131,8 +131,9 @@ class B200GlassRCNN:
             if self.roi_heads.orientation_on:    # MODEL.ORIENTATION_ON (rotated_fast_rcnn.py:141-142)
                 inst.orientations = det["orientations"][i, :c]
             inst.pred_text_prob = probs[starts[i]: starts[i + 1]]
-            if masks is not None:
+            if masks is not None:   # forward_with_given_boxes under MASK_INFERENCE (recognizers_hybrid_head.py:595-601)
                 inst.pred_masks = masks[starts[i]: starts[i + 1]]
+                inst.pred_rboxes = inst.pred_boxes      # :596-597 -- the SAME object (detector_postprocess relies on it)
             results.append(inst)
         return self._postprocess(results, batched_inputs, il.image_sizes) if do_postprocess else results
 

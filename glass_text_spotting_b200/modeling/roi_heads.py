@@ -165,7 +165,7 @@ class B200GlassROIHeads:
         # OPT-IN (GLASS_DEC_PRE=1; compiles, not yet run on hardware): the decoder GRU's input product from two precomputed
         # tensors instead of the 1.5 MB W_ih stream per step and CTA -- see aster_decode_pre_kernel (csrc/recognizer.cu)
         self.dec_pre = None
-        if os.environ.get("GLASS_DEC_PRE", "0") == "1":
+        if os.environ.get("GLASS_DEC_PRE", "1") == "1":
             wih = sdr[dp + "gru.weight_ih_l0"]                                   # [768, 512], input = [embedding ; context]
             table = sdr[dp + "tgt_embedding.weight"].double() @ wih[:, :256].double().t() + sdr[dp + "gru.bias_ih_l0"].double()
             self.dec_pre = {"emb_gi": table.float().contiguous().to(dev),
@@ -220,6 +220,7 @@ class B200GlassROIHeads:
         ``images.tensor`` holds RAW pixels padded with the pixel mean (B200GlassRCNN.preprocess_image): the image
         pooler normalises on the fly."""
         assert targets is None, "inference only: label_and_sample_proposals / losses are out of scope"
+        self._check_image_convention(images)
         n, per = len(proposals), max([len(p) for p in proposals] + [1])
         pb = torch.zeros((n, per, 5), dtype=torch.float32, device=self.device)
         for i, p in enumerate(proposals):
@@ -239,12 +240,21 @@ class B200GlassROIHeads:
 
     __call__ = forward
 
+    def _check_image_convention(self, images) -> None:
+        """The image pooler normalises on the fly with this head's (mean, std): an ImageList that says it is ALREADY
+        normalised (detectron2's preprocess_image convention) would be normalised twice -- silently wrong crops.  Build
+        the head with pixel_mean 0 / pixel_std 1 for such callers (d2_adapter.MaskRotatedRecognizerHybridHead does)."""
+        if getattr(images, "normalized", False) and (any(m != 0 for m in self.pixel_mean) or any(s != 1 for s in self.pixel_std)):
+            raise ValueError("images are already normalised but this head was built for RAW pixels "
+                             f"(pixel_mean {tuple(self.pixel_mean)}): construct it with pixel_mean=(0,0,0), pixel_std=(1,1,1)")
+
     @torch.no_grad()
     def forward_with_given_boxes(self, images: ImageList, features: Dict[str, Act], instances: List[Instances]):
         """recognizers_hybrid_head.py:571-609 (note the extra ``images`` argument vs stock d2): the same Instances with
         ``pred_text_prob`` added by the recognizer; under MASK_INFERENCE also ``pred_masks`` and ``pred_rboxes``
         (= the pred_boxes OBJECT, :596-597)."""
         assert instances[0].has("pred_boxes") and instances[0].has("pred_classes")
+        self._check_image_convention(images)
         counts = [len(x) for x in instances]
         rois = [torch.cat((torch.full((c, 1), float(i), device=self.device),
                            instances[i].pred_boxes.tensor.to(self.device)), 1) for i, c in enumerate(counts) if c > 0]

@@ -286,20 +286,6 @@ def gather_taps(x: Act, kh: int, kw: int, sh: int, sw: int, ph: int, pw: int, ho
     return out
 
 
-def stem_im2col(img: torch.Tensor, mean: Sequence[float], std: Sequence[float], kp: int = 192,
-                out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """raw fp32 NCHW [n,3,h,w] -> split rows [2, n*(h/2)*(w/2), kp] of the 7x7/s2/p3 stem conv."""
-    n, c, h, w = img.shape
-    assert c == 3 and img.dtype == torch.float32 and img.is_contiguous()
-    if out is None:
-        out = torch.empty((2, n * (h // 2) * (w // 2), kp), dtype=torch.float16, device=img.device)
-    assert tuple(out.shape) == (2, n * (h // 2) * (w // 2), kp) and out[0].is_contiguous()
-    m = (C.c_float * 3)(*[float(v) for v in mean])
-    s = (C.c_float * 3)(*[1.0 / float(v) for v in std])
-    _lib.check(_lib.load().glass_stem_im2col(_ptr(img), n, h, w, m, s, _ptr(out[0]), _ptr(out[1]), kp, _stream()))
-    return out
-
-
 def stem_s2d(img: torch.Tensor, mean: Sequence[float], std: Sequence[float], out: torch.Tensor) -> torch.Tensor:
     """raw fp32 NCHW [n,3,h,w] -> normalised space-to-depth map, split planes [2, n, h/2+4, w/2+4, 16] (2-pixel zero
     border, which must already be zero in ``out``)."""
@@ -575,27 +561,3 @@ def paste_masks_rotated(masks: torch.Tensor, boxes: torch.Tensor, image_shape: T
         _lib.check(_lib.load().glass_paste_masks_rotated(_ptr(masks), _ptr(boxes), k, m, h, w, float(threshold), _ptr(out),
                                                          _ptr(soft), _stream()))
     return (out.bool(), soft) if want_soft else out.bool()
-
-
-# ---------------------------------------------------------------------------------------------- benchmark baseline
-def baseline_roi_pooler_d2(feats_nchw: Sequence[torch.Tensor], rois: torch.Tensor, output_size: Tuple[int, int],
-                           scales: Sequence[float], sampling_ratio: int, min_level: int = 2) -> torch.Tensor:
-    """detectron2's ROIPooler with its ROIAlignRotated CUDA formulation restated (csrc/baseline_d2.cu): level assignment
-    with torch ops, then ONE kernel call per FPN level on that level's RoIs, results scattered back -- the comparison
-    arm of bench.py's RoIAlign microbench, never used by the model.  fp32 NCHW in, fp32 [R, C, ph, pw] out."""
-    lvl = torch.floor(4 + torch.log2(torch.sqrt(rois[:, 3] * rois[:, 4]) / 224 + 1e-8))
-    lvl = torch.clamp(lvl, min=min_level, max=min_level + len(feats_nchw) - 1).to(torch.int64) - min_level
-    c = feats_nchw[0].shape[1]
-    out = torch.zeros((rois.shape[0], c, output_size[0], output_size[1]), dtype=torch.float32, device=rois.device)
-    for l, f in enumerate(feats_nchw):
-        inds = torch.nonzero(lvl == l).squeeze(1)
-        if inds.numel() == 0:
-            continue
-        r = rois[inds].contiguous()
-        o = torch.empty((r.shape[0], c, output_size[0], output_size[1]), dtype=torch.float32, device=rois.device)
-        n, _, h, w = f.shape
-        _lib.check(_lib.load().glass_baseline_roi_align_rotated_d2(_ptr(f), n, c, h, w, _ptr(r), r.shape[0], float(scales[l]),
-                                                                   output_size[0], output_size[1], sampling_ratio, _ptr(o),
-                                                                   _stream()))
-        out[inds] = o
-    return out

@@ -153,16 +153,3 @@ def pack_stem_s2d(weight: torch.Tensor, scale, bias, device="cuda") -> PackedWei
     b[:cout] = bias.detach().float()
     wp, s = _pack_rows(w.reshape(w.shape[0], 256), s)
     return PackedWeight(wp.to(device), s.to(device), b.to(device), cout, 3, 7, 7, (2, 2), (3, 3), 64)
-
-
-def pack_stem(weight: torch.Tensor, scale, bias, kp: int = 192, device="cuda") -> PackedWeight:
-    """BasicStem conv1 [64,3,7,7] -> K = (r*7+s)*3 + c (matches glass_stem_im2col), zero padded to kp."""
-    cout = weight.shape[0]
-    w = torch.zeros((round_up(cout, 64), kp), dtype=torch.float32)
-    w[:cout, :147] = weight.detach().float().permute(0, 2, 3, 1).reshape(cout, 147)
-    s = torch.ones(w.shape[0])
-    b = torch.zeros(w.shape[0])
-    s[:cout] = scale
-    b[:cout] = bias
-    wp, s = _pack_rows(w, s)
-    return PackedWeight(wp.to(device), s.to(device), b.to(device), cout, 3, 7, 7, (2, 2), (3, 3), kp)

@@ -117,8 +117,10 @@ class ImageList:
     """Batch of images padded to a common size divisible by ``size_divisibility`` (d2 ImageList.from_tensors).
     ``pad_value`` lets the caller pad RAW pixels with the pixel mean so the normalised padding is exactly 0."""
 
-    def __init__(self, tensor: torch.Tensor, image_sizes: List[Tuple[int, int]]):
-        self.tensor, self.image_sizes = tensor, image_sizes
+    def __init__(self, tensor: torch.Tensor, image_sizes: List[Tuple[int, int]], normalized: bool = False):
+        # ``normalized``: the tensor already holds (x - mean) / std (what detectron2's preprocess_image produces); the B200
+        # modules built with a non-trivial pixel mean expect RAW pixels and refuse such a list (see d2_adapter.py)
+        self.tensor, self.image_sizes, self.normalized = tensor, image_sizes, normalized
 
     @staticmethod
     def from_tensors(tensors: Sequence[torch.Tensor], size_divisibility: int = 0, pad_value=0.0) -> "ImageList":

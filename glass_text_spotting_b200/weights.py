@@ -194,16 +194,41 @@ def required_keys(orientation: bool = True, mask: bool = False):
     return keys
 
 
-def load_checkpoint(path: str, mask: bool = False) -> Dict[str, torch.Tensor]:
+def _numpy_safe_globals():
+    """The globals a pickled numpy array needs (array reconstruction, dtypes): data constructors only."""
+    import numpy as np
+    out = [np.ndarray, np.dtype]
+    for mod in ("numpy._core.multiarray", "numpy.core.multiarray"):
+        try:
+            m = __import__(mod, fromlist=["_reconstruct"])
+            out += [m._reconstruct, m.scalar]
+        except Exception:
+            pass
+    out += [type(np.dtype(t)) for t in ("float32", "float64", "float16", "int64", "int32", "uint8", "bool")]
+    return list(dict.fromkeys(out))
+
+
+def load_checkpoint(path: str, mask: bool = False, allow_pickle: bool = False) -> Dict[str, torch.Tensor]:
     """What ``DetectionCheckpointer(model).load(path)`` does for a ``.pth`` file (glass/inference/glass_runner.py:58-60):
     read the ``"model"`` entry (or a bare state_dict), drop a DataParallel ``module.`` prefix, turn numpy arrays into
     tensors, and check that every parameter the inference path reads is there -- naming the missing ones instead of
     failing somewhere inside weight packing.  Keys the inference path does not read (training-only heads, mask head when
     ``mask`` is False, ``num_batches_tracked``) are dropped.  A checkpoint without ``box_predictor.orientation_pred``
-    (MODEL.ORIENTATION_ON false) is accepted."""
+    (MODEL.ORIENTATION_ON false) is accepted.
+
+    The file is read with ``weights_only=True`` (tensors, numpy arrays and plain containers only -- what released
+    detectron2 ``.pth`` checkpoints hold); a checkpoint that needs full unpickling (arbitrary code execution when the
+    file is untrusted) is refused unless ``allow_pickle=True`` is passed explicitly."""
     if not str(path).endswith((".pth", ".pt")):
         raise ValueError(f"{path}: only torch checkpoints (.pth) are supported; convert Caffe2 .pkl weights with detectron2")
-    ckpt = torch.load(path, map_location="cpu", weights_only=False)
+    try:
+        with torch.serialization.safe_globals(_numpy_safe_globals()):   # numpy arrays only construct data
+            ckpt = torch.load(path, map_location="cpu", weights_only=True)
+    except Exception as e:
+        if not allow_pickle:
+            raise RuntimeError(f"{path}: not loadable with weights_only=True ({type(e).__name__}: {str(e)[:200]}); if the file "
+                               "is trusted, pass allow_pickle=True") from e
+        ckpt = torch.load(path, map_location="cpu", weights_only=False)
     sd = ckpt["model"] if isinstance(ckpt, dict) and "model" in ckpt and isinstance(ckpt["model"], dict) else ckpt
     if not isinstance(sd, dict):
         raise ValueError(f"{path}: no state_dict found (expected a dict or a dict under 'model')")

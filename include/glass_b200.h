@@ -101,6 +101,11 @@ typedef struct {
    * (m_border 0) and re-zeroes the activation border afterwards (glass_zero_border). */
   int32_t a_col0;       /* first column of every k-block box inside the tensor row (multiple of 8) */
   int32_t a_inner;      /* inner extent of the tensor map in elements; 0 = k_per_tap (not grouped) */
+  /* Live M extent on the device (optional): only rows m < *m_count_dev * m_rows_per_count are computed.  The host sizes
+   * the launch for the worst case (m_imgs = capacity); the count -- e.g. the number of detected words, written by an
+   * earlier kernel of the same stream -- is read by the persistent grid itself, so no host round trip sizes the GEMM. */
+  const int32_t* m_count_dev;
+  int32_t m_rows_per_count;
 } GlassConvGemmParams;
 int glass_conv_gemm(const GlassConvGemmParams* p, void* stream);
 
@@ -117,13 +122,8 @@ int glass_unpack_nchw(const void* src_hi, const void* src_lo, int n, int c, int 
 int glass_nhwc_f32_to_nchw(const float* src, int n, int c, int h, int w, int ld, int border, float* dst,
                            void* stream);
 
-/* Stem im2col with fused (x - mean)/std (d2 GeneralizedRCNN.preprocess_image, called at
- * glass_rcnn.py:82; BasicStem conv 7x7 s2 p3): raw fp32 NCHW image [n,3,h,w] ->
- * split-fp16 rows [n*(h/2)*(w/2), kp] with k = (r*7+s)*3 + c, zero for k >= 147. */
-int glass_stem_im2col(const float* img, int n, int h, int w, const float* mean, const float* inv_std,
-                      void* dst_hi, void* dst_lo, int kp, void* stream);
-
-/* Stem pre-pass without an im2col matrix: raw fp32 NCHW [n,3,h,w] -> normalised space-to-depth map, split-fp16 NHWC
+/* Stem pre-pass with fused (x - mean)/std (d2 GeneralizedRCNN.preprocess_image, called at glass_rcnn.py:82), no im2col
+ * matrix: raw fp32 NCHW [n,3,h,w] -> normalised space-to-depth map, split-fp16 NHWC
  * [n, h/2+4, w/2+4, 16] with a 2-pixel zero border (pixel (Y,X), channel (dy*2+dx)*3+c = (img[c,2Y+dy,2X+dx]-mean)*inv_std;
  * channels 12..15 zero).  BasicStem's 7x7/s2/p3 conv (d2 resnet.py via configs/glass_pretrain.yaml:41-50) then runs as a
  * 4x4 stride-1 conv in glass_conv_gemm's compact-channel mode (a_ld = 16, 4 taps of one 64-wide k-block,
@@ -401,15 +401,6 @@ int glass_box_iou_rotated(const float* boxes1, int n1, const float* boxes2, int 
 int64_t glass_nms_rotated_all_workspace_bytes(int n);
 int glass_nms_rotated_all(const float* boxes, const int64_t* order, int n, float iou_thresh, int64_t* keep,
                           int32_t* keep_count, void* workspace, int64_t workspace_bytes, void* stream);
-
-/* ------------------------------------------------------------------------------------------
- * Benchmark baseline (NOT on the product path): detectron2 v0.6's GPU formulation of rotated RoIAlign restated --
- * fp32 NCHW, one thread per output element, one call per FPN level (ROIPooler).  Timed by bench.py --workload
- * roialign_512 next to glass_roi_align_rotated (BASELINE.json configs[2]: "HBM GB/s vs detectron2 CUDA op").
- * ------------------------------------------------------------------------------------------ */
-int glass_baseline_roi_align_rotated_d2(const float* input_nchw, int n, int channels, int height, int width,
-                                        const float* rois, int n_rois, float spatial_scale, int pooled_h, int pooled_w,
-                                        int sampling_ratio, float* out_nchw, void* stream);
 
 #ifdef __cplusplus
 }

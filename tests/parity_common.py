@@ -1,20 +1,52 @@
-"""Shared helpers for the GPU parity tests: seeded oracle construction (test infrastructure)."""
+"""Shared helpers for the GPU parity tests: seeded oracle construction and the tolerance check (test infrastructure).
+
+Tolerance (BASELINE.json north_star): ``|got - ref| <= atol + rtol * |ref|`` with rtol = 1e-3, atol = 1e-4 -- the LITERAL
+form, which is what ``close`` asserts by default.  A tap whose magnitude makes an absolute 1e-4 tighter than fp32
+arithmetic itself can promise (the CPU oracle's own rounding noise vs an fp64 evaluation reaches it,
+tests/test_oracle_noise_floor.py) may be checked with ``scaled=True``: the asserted bound then is
+``atol * max(1, max|ref|) + rtol * |ref|`` and the number of elements that miss the LITERAL bound is still counted,
+printed and recorded in ``REPORT`` (dumped to gpurun_out/parity_report.json by the tests' session hook) so the looser
+form never hides what the literal one would have said."""
+import json
+import os
+
 import torch
 from torch import nn
 
 RTOL, ATOL = 1e-3, 1e-4
 
+# every close() call of the session: name, elements, max abs error, scale, misses of the literal / scaled bound
+REPORT = []
+# GLASS_PARITY_REPORT_ONLY=1: record instead of asserting (one GPU call then shows every tap's status at once)
+REPORT_ONLY = os.environ.get("GLASS_PARITY_REPORT_ONLY", "0") == "1"
 
-def close(got: torch.Tensor, ref: torch.Tensor, name="", rtol=RTOL, atol=ATOL):
-    """north-star tolerance: |got-ref| <= atol*max(1,scale) + rtol*|ref| elementwise."""
+
+def close(got: torch.Tensor, ref: torch.Tensor, name="", rtol=RTOL, atol=ATOL, scaled: bool = False):
+    """Assert the north-star tolerance elementwise; returns the max abs error.  See the module docstring for ``scaled``."""
     got, ref = got.detach().cpu().float(), ref.detach().cpu().float()
     assert got.shape == ref.shape, (name, got.shape, ref.shape)
-    scale = max(ref.abs().max().item(), 1e-6)
+    scale = max(ref.abs().max().item(), 1e-6) if ref.numel() else 1.0
     err = (got - ref).abs()
-    tol = atol * max(scale, 1.0) + rtol * ref.abs()
-    bad = (err > tol).sum().item()
-    assert bad == 0, f"{name}: {bad}/{err.numel()} out of tolerance, max err {err.max().item():.3e}, scale {scale:.3e}"
-    return err.max().item()
+    bad_literal = int((err > atol + rtol * ref.abs()).sum().item())
+    bad_scaled = int((err > atol * max(scale, 1.0) + rtol * ref.abs()).sum().item())
+    max_err = err.max().item() if err.numel() else 0.0
+    rec = {"name": name, "numel": err.numel(), "max_err": max_err, "scale": scale, "rtol": rtol, "atol": atol,
+           "asserted": "scaled" if scaled else "literal", "literal_misses": bad_literal, "scaled_misses": bad_scaled}
+    REPORT.append(rec)
+    if scaled and bad_literal:
+        print(f"[parity] {name}: {bad_literal}/{err.numel()} elements miss the LITERAL atol {atol:g} "
+              f"(max err {max_err:.3e}, scale {scale:.3e}); asserted with atol*max(1,scale)")
+    bad = bad_scaled if scaled else bad_literal
+    if not REPORT_ONLY:
+        assert bad == 0, (f"{name}: {bad}/{err.numel()} out of tolerance ({rec['asserted']} atol), max err {max_err:.3e}, "
+                          f"scale {scale:.3e}")
+    return max_err
+
+
+def dump_report(path: str) -> None:
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    with open(path, "w") as f:
+        json.dump(REPORT, f, indent=1)
 
 
 @torch.no_grad()

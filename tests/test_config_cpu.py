@@ -120,3 +120,33 @@ def test_glass_rcnn_options_and_post_processor_selection():
     assert config.model_kwargs(cfg)["mask_inference"] is True
     with pytest.raises(NotImplementedError):
         config.load_config({"_BASE_": "x.yaml"})
+
+
+@pytest.mark.parametrize("path,value,needle", [
+    (("MODEL", "RPN", "PRE_NMS_TOPK_TEST"), 6000, "PRE_NMS_TOPK_TEST"),          # detectron2's default when the YAML omits it
+    (("MODEL", "RPN", "POST_NMS_TOPK_TEST"), 1000, "POST_NMS_TOPK_TEST"),
+    (("TEST", "DETECTIONS_PER_IMAGE"), 300, "DETECTIONS_PER_IMAGE"),
+    (("MODEL", "ROI_RECOGNIZER_HEAD", "MAX_WORD_LENGTH"), 80, "MAX_WORD_LENGTH"),
+    (("MODEL", "ROI_RECOGNIZER_HEAD", "POOLER_RESOLUTION_WIDTH"), 64, "POOLER_RESOLUTION_WIDTH"),
+])
+def test_kernel_limits_are_refused_by_key(path, value, needle):
+    """the kernels' hard numeric limits are validated with the offending key named, not discovered at the
+    first image as a C-side check or a bare assert."""
+    import copy
+    from glass_text_spotting_b200 import config
+    raw = copy.deepcopy(PRETRAIN_LIKE)
+    node = raw
+    for k in path[:-1]:
+        node = node.setdefault(k, {})
+    node[path[-1]] = value
+    with pytest.raises(config.UnsupportedConfig, match=needle):
+        config.model_kwargs(config.load_config(raw))
+
+
+def test_omitted_rpn_topk_inherits_d2_defaults_and_is_refused():
+    import copy
+    from glass_text_spotting_b200 import config
+    raw = copy.deepcopy(PRETRAIN_LIKE)
+    del raw["MODEL"]["RPN"]["PRE_NMS_TOPK_TEST"]
+    with pytest.raises(config.UnsupportedConfig, match="PRE_NMS_TOPK_TEST = 6000"):
+        config.check_supported(config.load_config(raw))

@@ -51,20 +51,6 @@ def test_maxpool_matches_torch(ops):
         assert torch.equal(got, ref), (k, s, p)
 
 
-def test_stem_im2col(ops):
-    from glass_text_spotting_b200 import packing
-    g = torch.Generator().manual_seed(2)
-    img = torch.randint(0, 256, (2, 3, 64, 96), generator=g).float()
-    mean, std = (103.53, 116.28, 123.675), (1.0, 1.0, 1.0)
-    w = torch.randn(64, 3, 7, 7, generator=g) * 0.05
-    cols = ops.stem_im2col(img.cuda(), mean, std)
-    pw = packing.pack_stem(w, torch.ones(64), torch.zeros(64))
-    out = ops.Act(2, 64, 32, 48)
-    ops.conv_gemm(cols[0], cols[1], cols.shape[1], 192, [0], pw, (2, 32, 48, 0), out=out)
-    ref = F.conv2d(img - torch.tensor(mean).view(1, 3, 1, 1), w, stride=2, padding=3)
-    _close(out.to_nchw(), ref, "stem")
-
-
 @pytest.mark.parametrize("shape", [(2, 64, 96), (1, 32, 160), (3, 96, 64)])
 def test_stem_space_to_depth(ops, shape):
     """The 7x7/s2/p3 stem as a 4x4/s1 conv over the normalised space-to-depth map (no im2col matrix), with a
@@ -333,20 +319,6 @@ def test_roi_align_rotated_split_input_matches_oracle(ops, cfg):
     _close(got.permute(0, 3, 1, 2), ref, cfg + "/f32")
     _close(out_act.to_nchw(), ref, cfg + "/split")
     assert out_act.buf[:, :, 0].abs().max().item() == 0  # the zero border is never written
-
-
-def test_d2_style_baseline_matches_oracle(ops):
-    """The benchmark's comparison arm (detectron2's thread-per-output NCHW formulation, csrc/baseline_d2.cu) computes the
-    same thing as the oracle -- otherwise the speed-up quoted against it would be meaningless."""
-    from oracle import d2_ops
-    g = torch.Generator().manual_seed(31)
-    sizes, scales = [64, 32, 16, 8, 4], [1 / 4, 1 / 8, 1 / 16, 1 / 32, 1 / 64]
-    feats = [torch.randn(1, 64, s, s, generator=g) for s in sizes]
-    rois = _random_rois(g, 64, img=256.0, batch=1)
-    rois[:, 3:5] *= 0.6
-    ref = d2_ops.roi_pooler(feats, [rois[:, 1:]], (7, 7), scales, 2)
-    got = ops.baseline_roi_pooler_d2([f.cuda() for f in feats], rois.cuda(), (7, 7), scales, 2)
-    _close(got, ref, "d2-style baseline")
 
 
 def test_image_roi_align_matches_oracle(ops):

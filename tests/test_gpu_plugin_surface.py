@@ -95,3 +95,35 @@ def test_checkpoint_without_orientation_head(model_and_inputs):
         assert not g.has("orientations") and "orientations" in w
         assert torch.equal(g.pred_boxes.tensor, w["pred_boxes"]) and torch.equal(g.scores, w["scores"])
         assert torch.equal(g.pred_text_prob, w["pred_text_prob"])
+
+
+def test_registry_adapters_reproduce_the_fused_model(glass_lib):
+    """d2_adapter: modules built BY NAME from a glass_pretrain.yaml-shaped cfg through (stub) detectron2 registries,
+    weights loaded afterwards (DetectionCheckpointer's order).  The fused meta-arch adapter must equal B200GlassRCNN bit
+    for bit; the three component adapters, driven the way d2's stock GeneralizedRCNN drives them (NORMALISED, zero-padded
+    images), must give the same detections (the normalisation happens in a different place, so the pixels differ in the
+    last bit)."""
+    from test_config_cpu import PRETRAIN_LIKE
+    from test_d2_adapter_cpu import _registries
+    from glass_text_spotting_b200 import d2_adapter as ad, weights
+    from glass_text_spotting_b200.modeling.glass_rcnn import B200GlassRCNN
+    sd = weights.random_state_dict(0)
+    g = torch.Generator().manual_seed(21)
+    inputs = [{"image": torch.randint(0, 256, (3, 200, 280), generator=g).float()},
+              {"image": torch.randint(0, 256, (3, 224, 256), generator=g).float()}]
+    regs = ad.register_all(**_registries(), generalized_rcnn=True)
+    want = B200GlassRCNN(sd, detections_per_image=100)(inputs)
+    model = ad.build_model(PRETRAIN_LIKE, regs)
+    model.load_state_dict(sd)
+    got = model(inputs)
+    comp = ad.ComponentRCNN(PRETRAIN_LIKE, regs)
+    comp.load_state_dict(sd)
+    got_c = comp.inference(inputs)
+    torch.cuda.synchronize()
+    for w, a, c in zip(want, got, got_c):
+        w, a = w["instances"], a["instances"]
+        assert len(w) == len(a) and len(w) > 0
+        assert torch.equal(w.pred_boxes.tensor, a.pred_boxes.tensor) and torch.equal(w.pred_text_prob, a.pred_text_prob)
+        assert len(c) == len(w)
+        assert (c.pred_boxes.tensor - w.pred_boxes.tensor).abs().max().item() < 1e-2
+        assert (c.pred_text_prob - w.pred_text_prob).abs().max().item() < 1e-3

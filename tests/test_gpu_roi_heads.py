@@ -118,9 +118,11 @@ def test_recognizer_branch_matches_oracle(glass_lib):
         close(taps["crops"].to_nchw()[sl], ot["local_crops"], f"img{i} crops")
         fused = taps["fused"].to_nchw()[sl]
         close(fused[:, 256:], ot["global_feats"], f"img{i} global_feats")
-        close(fused[:, :256], ot["local_feats"], f"img{i} local_feats")
-        close(taps["fusion_out"].to_nchw()[sl], ot["fusion_out"], f"img{i} fusion_out")
-        close(taps["recog_cnn"].to_nchw()[sl], ot["recog_cnn"], f"img{i} recog_cnn")
+        # free-running through the 31 convs of the local CNN (and everything after it from the device's own features):
+        # scale-relative atol, literal misses reported; the stage-wise literal checks are in test_gpu_fullsize_parity.py
+        close(fused[:, :256], ot["local_feats"], f"img{i} local_feats", scaled=True)
+        close(taps["fusion_out"].to_nchw()[sl], ot["fusion_out"], f"img{i} fusion_out", scaled=True)
+        close(taps["recog_cnn"].to_nchw()[sl], ot["recog_cnn"], f"img{i} recog_cnn", scaled=True)
         close(taps["encoder_out"].view(-1, 32, 256)[sl], ot["encoder_out"], f"img{i} encoder_out")
         steps = ot["decoder_steps"]
         close(taps["decoder_logits"][sl, :steps], ot["decoder_logits"][:, :steps], f"img{i} decoder_logits")

@@ -53,3 +53,18 @@ def test_load_checkpoint_d2_format(tmp_path):
         weights.load_checkpoint(str(p), mask=True)
     with pytest.raises(ValueError, match="pkl"):
         weights.load_checkpoint("R-50.pkl")
+
+
+def test_load_checkpoint_refuses_arbitrary_pickles(tmp_path):
+    """weights_only=True first; a file that needs full unpickling is refused unless opted in."""
+    import pytest
+    import torch
+    from glass_text_spotting_b200 import weights
+
+    class Evil:
+        def __reduce__(self):
+            return (print, ("arbitrary code ran",))
+    p = tmp_path / "evil.pth"
+    torch.save({"model": {"x": Evil()}}, str(p))
+    with pytest.raises(RuntimeError, match="allow_pickle=True"):
+        weights.load_checkpoint(str(p))
