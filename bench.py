@@ -831,6 +831,13 @@ def measure_backbone(min_seconds=1.2, no_clocks=False, mode=0):
 
 # ============================================================================================ B200 arm
 def run_b200(args):
+    """full_bs4 / backbone_bs8.  One step = one pass of the hot path over one batch of 4 (8) images.
+
+    full_bs4: the step is ONE CUDA graph (B200GlassRCNN.graph_step: no host sync, no per-kernel host work); its result --
+    the fixed-size packed detection records of the batch -- is appended to a device-side loop buffer, and the loop ends
+    with the SINGLE all-gather of SURVEY.md 8e / the north star ("a single NCCL all-gather of detections at the end",
+    what the reference's evaluator does with comm.gather in text_evaluator.py:246-249).  The gather (and, for e2e, rank 0's
+    read-back of the gathered records) is INSIDE the timed region."""
     import torch
     import torch.distributed as dist
     from glass_text_spotting_b200 import lib, ops, weights
@@ -849,34 +856,25 @@ def run_b200(args):
     L = lib.load()
     mode = ops.MODE_FAST if args.fast else ops.MODE_SPLIT
     stream = torch.cuda.current_stream()
+    steps, warm = args.steps, max(args.warmup, 3)
+    use_graph = full and not args.no_graph
 
     g = torch.Generator().manual_seed(1000 + rank)
     # host images are uint8 like the reference's dataset mapper output; they become fp32 on the device
     host = [torch.randint(0, 256, (B, 3, H, W), generator=g, dtype=torch.uint8).pin_memory() for _ in range(2)]
     dev = [h.cuda().float() for h in host]
     dbuf = [torch.empty((B, 3, H, W), dtype=torch.uint8, device="cuda") for _ in range(2)]
+    fbuf = torch.empty((B, 3, H, W), dtype=torch.float32, device="cuda")
     img_hw = torch.tensor([[H, W]] * B, dtype=torch.float32, device="cuda")
-    words = []
 
     if full:
         model = B200GlassRCNN(weights.random_state_dict(0), mode=mode)
-        gathered = None
 
         def step(images):
-            """One pass of the hot path over one batch, ending in the packed per-image detection records and
-            (N > 1) the single all-gather of those records."""
-            nonlocal gathered
-            det, probs, counts, starts = model.forward_device(images, img_hw)
-            rec = model.pack_detections(det, probs, counts, starts)
-            words.append(sum(counts))
-            if world > 1:
-                if gathered is None:
-                    gathered = torch.empty((world * rec.shape[0],) + tuple(rec.shape[1:]), dtype=rec.dtype,
-                                           device=rec.device)
-                dist.all_gather_into_tensor(gathered, rec)
-                return gathered
-            return rec
-        conv_flops = None
+            """-> the packed per-image detection records [B, 100, 10 + 26*97] of this batch (a persistent device buffer)"""
+            if use_graph:
+                return model.graph_step(images, img_hw)
+            return model.forward_packed(images, img_hw)[0]
     else:
         model = B200ResNetFPN(weights.random_backbone_state_dict(0), mode=mode)
 
@@ -890,37 +888,54 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up (also allocates every workspace buffer once); the clock sampler runs from here to the end of the
-    # timed region so that it collects enough 100 ms samples under load
+    # ---- warm-up (allocates every workspace buffer, captures the graph); the clock sampler runs from here to the end of
+    # the timed region so that it collects enough 100 ms samples under load
     sampler = ClockSampler(local_rank)
     if rank == 0 and not args.no_clocks:
         sampler.start()
-    for i in range(max(args.warmup, 3)):
-        step(dev[i % 2])
+    for i in range(warm):
+        res = step(dev[i % 2])
+    torch.cuda.synchronize()
+    # loop buffer: every step's result stays on the device until the single end-of-loop gather
+    loop_buf = torch.empty((steps,) + tuple(res.shape), dtype=res.dtype, device="cuda")
+    gathered = torch.empty((world,) + tuple(loop_buf.shape), dtype=res.dtype, device="cuda") if (full and world > 1) else None
+    ag = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    if gathered is not None:   # NCCL warm-up (communicator set-up is not part of the loop)
+        dist.all_gather_into_tensor(gathered.view(world, -1), loop_buf.view(-1))
     barrier()
 
     # ---- timed: inputs resident in HBM
-    words.clear()
     launches0 = L.glass_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
-    for i in range(args.steps):
-        step(dev[i % 2])
+    for i in range(steps):
+        loop_buf[i].copy_(step(dev[i % 2]), non_blocking=True)
+    if gathered is not None:
+        ag[0].record(stream)
+        dist.all_gather_into_tensor(gathered.view(world, -1), loop_buf.view(-1))
+        ag[1].record(stream)
     e1.record(stream)
     barrier()
     t_dev = e0.elapsed_time(e1) / 1e3
     launches = L.glass_launch_count() - launches0
+    if use_graph:
+        launches = model.last_graph["launches"] * steps     # kernels inside the replayed graph
     clocks = sampler.stop() if rank == 0 else None
-    words_per_step = sum(words) / max(len(words), 1)
+    ag_ms = ag[0].elapsed_time(ag[1]) if gathered is not None else 0.0
+    words_per_step = float(loop_buf[..., 0].sum().item()) / steps if full else None
 
     # ---- e2e: host buffers; H2D of every step's batch and D2H of its result are inside the timed region.  The H2D of
-    # step i+1 runs on a copy stream while step i computes (double-buffered device staging, events both ways), the way
-    # a serving loop would feed the model; every step still waits for ITS OWN batch and ships ITS OWN result.
-    res_host = None
+    # step i+1 and the D2H of step i run on a copy stream while the next step computes (double-buffered staging, events
+    # both ways), the way a serving loop feeds the model; every step still waits for ITS OWN batch and ships ITS OWN
+    # result.  The loop ends with the single all-gather and rank 0's read-back of the other ranks' records.
     copy_stream = torch.cuda.Stream()
     ready = [torch.cuda.Event(), torch.cuda.Event()]     # H2D of buffer b finished
-    consumed = [torch.cuda.Event(), torch.cuda.Event()]  # the step reading buffer b has been enqueued and finished
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]  # the step reading buffer b has finished with it
+    done = [torch.cuda.Event() for _ in range(steps)]    # step i's record is in the loop buffer
+    res_host = torch.empty(tuple(loop_buf.shape), dtype=res.dtype).pin_memory()
+    gathered_host = torch.empty(tuple(gathered.shape), dtype=res.dtype).pin_memory() if (gathered is not None and rank == 0) \
+        else None
 
     def upload(b):
         with torch.cuda.stream(copy_stream):
@@ -928,76 +943,96 @@ def run_b200(args):
             dbuf[b].copy_(host[b], non_blocking=True)
             ready[b].record(copy_stream)
 
+    def e2e_loop(n):
+        upload(0)
+        for i in range(n):
+            b = i % 2
+            if i + 1 < n:
+                upload((i + 1) % 2)           # next step's batch, overlapped with this step's compute
+            stream.wait_event(ready[b])
+            fbuf.copy_(dbuf[b])               # uint8 -> fp32 on the device
+            consumed[b].record(stream)
+            loop_buf[i].copy_(step(fbuf), non_blocking=True)
+            done[i].record(stream)
+            with torch.cuda.stream(copy_stream):   # this step's own result to the host, off the compute stream
+                copy_stream.wait_event(done[i])
+                res_host[i].copy_(loop_buf[i], non_blocking=True)
+        if gathered is not None:
+            ag[2].record(stream)
+            dist.all_gather_into_tensor(gathered.view(world, -1), loop_buf.view(-1))
+            ag[3].record(stream)
+            if rank == 0:                      # the gathered records are consumed on rank 0 (comm.gather(dst=0))
+                gathered_host.copy_(gathered, non_blocking=True)
+        stream.wait_stream(copy_stream)
+
     for b in range(2):
         consumed[b].record(stream)
-    for i in range(2):   # untimed warm-up of the e2e loop
-        upload(i % 2)
-        stream.wait_event(ready[i % 2])
-        step(dbuf[i % 2].float())
-        consumed[i % 2].record(stream)
+    e2e_loop(min(2, steps))                    # untimed warm-up of the e2e loop
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     f0.record(stream)
-    copy_stream.wait_event(f0)            # no upload starts before the timed region does
-    upload(0)
-    for i in range(args.steps):
-        b = i % 2
-        if i + 1 < args.steps:
-            upload((i + 1) % 2)           # next step's batch, overlapped with this step's compute
-        stream.wait_event(ready[b])
-        res = step(dbuf[b].float())
-        consumed[b].record(stream)
-        if full and world > 1 and rank != 0:
-            # the gathered records are read back where they are consumed -- on rank 0, like the reference's
-            # comm.gather(dst=0) (text_evaluator.py:246-249); the other ranks read back their own share
-            res = res[rank * B:(rank + 1) * B]
-        if res_host is None:
-            res_host = torch.empty(res.shape, dtype=res.dtype).pin_memory()
-        res_host.copy_(res, non_blocking=True)
+    copy_stream.wait_event(f0)                 # no upload starts before the timed region does
+    e2e_loop(steps)
     f1.record(stream)
     barrier()
     t_e2e = f0.elapsed_time(f1) / 1e3
-    d2h_bytes = res_host.numel() * res_host.element_size()
+    d2h_bytes = res_host[0].numel() * res_host.element_size()
+    if gathered_host is not None:
+        d2h_bytes += gathered_host.numel() * gathered_host.element_size() / steps
+    ag_e2e_ms = ag[2].elapsed_time(ag[3]) if gathered is not None else 0.0
 
-    # ---- per-kernel profile pass: CUDA events around every launch of the dominant kernel (conv GEMM)
+    # ---- per-kernel profile pass: CUDA events around every launch of the dominant kernel (conv GEMM), eager launches
     ops.PROFILE = []
     nprof = 2
     for i in range(nprof):
-        step(dev[i % 2])
+        if full:
+            model.forward_packed(dev[i % 2], img_hw)
+        else:
+            step(dev[i % 2])
     torch.cuda.synchronize()
     gemm_ms = sum(r[0].elapsed_time(r[1]) for r in ops.PROFILE) / nprof
     gemm_flops = sum(r[2] for r in ops.PROFILE) / nprof
     n_gemm = len(ops.PROFILE) // nprof
     ops.PROFILE = None
 
-    times = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device="cuda")
+    times = torch.tensor([t_dev, t_e2e, ag_ms, ag_e2e_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    t_dev, t_e2e = times.tolist()
+    t_dev, t_e2e, ag_ms, ag_e2e_ms = times.tolist()
 
     if rank == 0:
         peaks, peak_src = _peaks()
         peak = peaks["bf16_tflops_sustained"]
         achieved = gemm_flops / (gemm_ms / 1e3) / 1e12
         cfg = _config(args.workload, world)
-        run = {"kb_per_chunk": ops.KB_PER_CHUNK or "2 (backbone, RPN, box head), 4 (per-word recognizer convs)"}
+        run = {"kb_per_chunk": ops.KB_PER_CHUNK or "2 (backbone, RPN, box head), 4 (per-word recognizer convs)",
+               "step": "one CUDA graph replay (B200GlassRCNN.graph_step), no host synchronisation inside the loop"
+                       if use_graph else "eager launches"}
         if full:
+            # NOTE the GEMM's M space follows the live word count on the device: the profile pass' FLOPs are the
+            # algorithmic FLOPs of the words actually detected, not of the capacity
             run["words_per_step"] = words_per_step
-            run["collective"] = "one NCCL all-gather of packed detection records per step" if world > 1 else "none (N=1)"
+            run["collective"] = ("ONE NCCL all-gather of the loop's packed detection records at the end of the loop, inside "
+                                 "the timed region") if world > 1 else "none (N=1)"
+            run["allgather_ms_per_loop"] = ag_ms
+            run["allgather_ms_per_loop_e2e"] = ag_e2e_ms
+            run["allgather_bytes_per_rank"] = loop_buf.numel() * 4 if world > 1 else 0
         nc = _ncu(args.workload)
         out = {
-            "metric": "images/sec @1024x1024", "value": world * B * args.steps / t_dev, "unit": "images/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+            "metric": "images/sec @1024x1024", "value": world * B * steps / t_dev, "unit": "images/s",
+            "n_gpus": world, "steps": steps, "warmup": warm,
+            "ms_per_step": 1e3 * t_dev / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None,
             "dtype": "fp16 (single tcgen05 pass)" if args.fast else
                      "fp16x3 split (22-bit operands, 3 tcgen05 MMAs per product, chunked fp32 RN accumulation)",
             "data": "synthetic", "config": cfg, "run": run,
-            "e2e": {"value": world * B * args.steps / t_e2e, "unit": "images/s",
+            "e2e": {"value": world * B * steps / t_e2e, "unit": "images/s",
                     "h2d_bytes_per_step": B * 3 * H * W, "d2h_bytes_per_step": d2h_bytes,
                     "note": "pinned host uint8 batch -> H2D (copy stream, overlapped with the previous step) -> hot path -> "
-                            "D2H of the step's result "
-                            + ("(packed detection records)" if full else "(p6 + per-level checksums)")},
+                            "D2H of the step's result on the copy stream "
+                            + ("(packed detection records); at N > 1 the loop ends with the single all-gather and rank 0's "
+                               "read-back of the gathered records, both inside the timed region"
+                               if full else "(p6 + per-level checksums)")},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
@@ -1006,14 +1041,14 @@ def run_b200(args):
                                          "profiles/ncu_metrics.json); null when no capture exists for this workload",
                          "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM), all launches of one step",
                          "launches_per_step": n_gemm, "kernel_ms_per_step": gemm_ms,
-                         "kernel_share_of_step": gemm_ms / (1e3 * t_dev / args.steps),
+                         "kernel_share_of_step": gemm_ms / (1e3 * t_dev / steps),
                          "algorithmic_flops_per_step": gemm_flops,
                          "issued_mma_flops_per_step": gemm_flops * (1 if args.fast else 3),
                          "issued_frac": achieved * (1 if args.fast else 3) / peak,
                          "tensor_pipe_active_pct_ncu": nc.get("time_weighted_tensor_pipe_active_pct"),
                          # SURVEY.md 8d cfg 4: the WHOLE step against t_min = algorithmic FLOPs / tensor peak (the gather
                          # term bytes / HBM peak is < 0.1 ms and is left out)
-                         "whole_step_frac_of_tensor_roofline": (gemm_flops / (peak * 1e12)) / (t_dev / args.steps),
+                         "whole_step_frac_of_tensor_roofline": (gemm_flops / (peak * 1e12)) / (t_dev / steps),
                          "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src})"},
         }
         if world == 1 and full and not args.no_submetrics:
@@ -1045,6 +1080,7 @@ def main():
     ap.add_argument("--workload", default="full_bs4", choices=sorted(WORKLOADS))
     ap.add_argument("--fast", action="store_true", help="single-pass fp16 (NOT the parity precision)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-graph", action="store_true", help="full_bs4: eager launches instead of the CUDA-graph step")
     ap.add_argument("--no-submetrics", action="store_true", help="skip the backbone / RoIAlign sub-benches of full_bs4")
     ap.add_argument("--no-clocks", action="store_true", help="do not spawn the nvidia-smi clock sampler (ncu runs)")
     args = ap.parse_args()

@@ -48,5 +48,5 @@ int num_sms() {
 }  // namespace glass
 
 extern "C" const char* glass_last_error(void) { return glass::g_last_error.c_str(); }
-extern "C" int glass_abi_version(void) { return 1; }
+extern "C" int glass_abi_version(void) { return 2; }
 extern "C" int64_t glass_launch_count(void) { return glass::g_launches.load(); }

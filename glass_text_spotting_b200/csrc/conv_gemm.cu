@@ -17,6 +17,8 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <new>
+
 #include "common.cuh"
 #include "glass_b200.h"
 #include "host_util.h"
@@ -538,8 +540,16 @@ static int make_map_2d(CUtensorMap* map, const void* base, uint64_t inner, uint6
 
 using namespace glass;
 
-extern "C" int glass_conv_gemm(const GlassConvGemmParams* p, void* stream_v) {
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+// A launch plan: everything the host derives from a GlassConvGemmParams -- validation, the four TMA descriptors, the
+// tile / pipeline geometry, the grid -- so that a caller that repeats a launch (same buffers every step) pays for it
+// once (glass_plan_create) and the per-step cost is one cudaLaunchKernelEx (glass_plan_launch).
+struct GlassGemmPlan {
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  GemmKernelParams k;
+  int split, pair, grid, smem_req;
+};
+
+static int build_plan(const GlassConvGemmParams* p, GlassGemmPlan* plan) {
   GLASS_CHECK(p != nullptr, "null params");
   GLASS_CHECK(p->a_hi && p->b_hi, "a_hi / b_hi must be set");
   const bool split = (p->mode == 0);
@@ -590,7 +600,10 @@ extern "C" int glass_conv_gemm(const GlassConvGemmParams* p, void* stream_v) {
   }
   const int b_rows = pair ? bn / 2 : bn;
 
-  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  CUtensorMap& ma_hi = plan->ma_hi;
+  CUtensorMap& ma_lo = plan->ma_lo;
+  CUtensorMap& mb_hi = plan->mb_hi;
+  CUtensorMap& mb_lo = plan->mb_lo;
   const uint64_t ktot = (uint64_t)p->k_per_tap * p->ntaps;
   // compact-channel mode: rows overlap (stride a_ld < 64 elements); the last 64/a_ld - 1 rows would read past
   // the tensor, so they are left to the TMA's out-of-bounds zero fill (they start inside the zero border)
@@ -639,7 +652,8 @@ extern "C" int glass_conv_gemm(const GlassConvGemmParams* p, void* stream_v) {
     mb_lo = mb_hi;
   }
 
-  GemmKernelParams k{};
+  GemmKernelParams& k = plan->k;
+  k = GemmKernelParams{};
   k.rows_m = rows_m;
   k.tiles_m = (int)((rows_m + BM - 1) / BM);
   k.tiles_n = p->n / bn;
@@ -683,40 +697,87 @@ extern "C" int glass_conv_gemm(const GlassConvGemmParams* p, void* stream_v) {
   // always ask for > half of the SM's shared memory: exactly one CTA per SM owns all 512 TMEM columns
   const int smem_bytes = k.ring_bytes + EPI_STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
   const int smem_req = smem_bytes < 120 * 1024 ? 120 * 1024 : smem_bytes;
+  plan->split = split ? 1 : 0;
+  plan->pair = pair ? 1 : 0;
+  plan->smem_req = smem_req;
+  if (pair) {
+    const int units = ((k.tiles_m + 1) / 2) * k.tiles_n;
+    const int pairs = units < sms / 2 ? units : sms / 2;
+    plan->grid = 2 * pairs;
+  } else {
+    const int total_tiles = k.tiles_m * k.tiles_n;
+    plan->grid = total_tiles < sms ? total_tiles : sms;
+  }
+  return 0;
+}
+
+// the largest dynamic shared-memory request any plan makes: set once per kernel variant, not per launch
+static constexpr int kMaxSmem = 227 * 1024;
+template <bool SPLIT, bool PAIR>   // (the four variants share one function-pointer TYPE: key the static on the variant)
+static cudaError_t ensure_smem_attr() {
+  static cudaError_t once =
+      cudaFuncSetAttribute(conv_gemm_kernel<SPLIT, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+  return once;
+}
+
+static int launch_plan(const GlassGemmPlan* plan, cudaStream_t stream) {
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[2];
   int nattr = 0;
   attr[nattr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[nattr].val.programmaticStreamSerializationAllowed = 1;
   ++nattr;
-  if (pair) {
+  if (plan->pair) {
     attr[nattr].id = cudaLaunchAttributeClusterDimension;
     attr[nattr].val.clusterDim.x = 2;
     attr[nattr].val.clusterDim.y = 1;
     attr[nattr].val.clusterDim.z = 1;
     ++nattr;
-    const int units = ((k.tiles_m + 1) / 2) * k.tiles_n;
-    const int pairs = units < sms / 2 ? units : sms / 2;
-    cfg.gridDim = dim3(2 * pairs);
-  } else {
-    const int total_tiles = k.tiles_m * k.tiles_n;
-    cfg.gridDim = dim3(total_tiles < sms ? total_tiles : sms);
   }
+  cfg.gridDim = dim3(plan->grid);
   cfg.blockDim = dim3(NUM_THREADS);
-  cfg.dynamicSmemBytes = smem_req;
+  cfg.dynamicSmemBytes = plan->smem_req;
   cfg.stream = stream;
   cfg.attrs = attr;
   cfg.numAttrs = nattr;
-  auto launch = [&](auto kern) -> cudaError_t {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_req);
-    if (e != cudaSuccess) return e;
-    return cudaLaunchKernelEx(&cfg, kern, ma_hi, ma_lo, mb_hi, mb_lo, k);
+  auto launch = [&](auto kern, cudaError_t attr_state) -> cudaError_t {
+    if (attr_state != cudaSuccess) return attr_state;
+    return cudaLaunchKernelEx(&cfg, kern, plan->ma_hi, plan->ma_lo, plan->mb_hi, plan->mb_lo, plan->k);
   };
-  if (split && pair) GLASS_CUDA(launch(conv_gemm_kernel<true, true>));
-  else if (split) GLASS_CUDA(launch(conv_gemm_kernel<true, false>));
-  else if (pair) GLASS_CUDA(launch(conv_gemm_kernel<false, true>));
-  else GLASS_CUDA(launch(conv_gemm_kernel<false, false>));
+  if (plan->split && plan->pair) GLASS_CUDA(launch(conv_gemm_kernel<true, true>, ensure_smem_attr<true, true>()));
+  else if (plan->split) GLASS_CUDA(launch(conv_gemm_kernel<true, false>, ensure_smem_attr<true, false>()));
+  else if (plan->pair) GLASS_CUDA(launch(conv_gemm_kernel<false, true>, ensure_smem_attr<false, true>()));
+  else GLASS_CUDA(launch(conv_gemm_kernel<false, false>, ensure_smem_attr<false, false>()));
   count_launch();
   GLASS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int glass_conv_gemm(const GlassConvGemmParams* p, void* stream_v) {
+  GlassGemmPlan plan;
+  if (build_plan(p, &plan)) return -1;
+  return launch_plan(&plan, reinterpret_cast<cudaStream_t>(stream_v));
+}
+
+extern "C" int glass_plan_create(const GlassConvGemmParams* p, void** plan_out) {
+  GLASS_CHECK(plan_out != nullptr, "null plan_out");
+  *plan_out = nullptr;
+  GlassGemmPlan* plan = new (std::nothrow) GlassGemmPlan;
+  GLASS_CHECK(plan != nullptr, "out of host memory");
+  if (build_plan(p, plan)) {
+    delete plan;
+    return -1;
+  }
+  *plan_out = plan;
+  return 0;
+}
+
+extern "C" int glass_plan_launch(const void* plan, void* stream_v) {
+  GLASS_CHECK(plan != nullptr, "null plan");
+  return launch_plan(static_cast<const GlassGemmPlan*>(plan), reinterpret_cast<cudaStream_t>(stream_v));
+}
+
+extern "C" int glass_plan_destroy(void* plan) {
+  delete static_cast<GlassGemmPlan*>(plan);
   return 0;
 }

@@ -355,7 +355,9 @@ __global__ void __launch_bounds__(PP_THREADS) postprocess_merge_kernel(const Pos
 // product of the max probabilities up to AND including the first stop symbol (or all steps if there is none).
 __global__ void __launch_bounds__(128) text_scores_kernel(const float* __restrict__ probs, int n_words, int steps,
                                                           int classes, int stop_index, float* __restrict__ score,
-                                                          int32_t* __restrict__ out_idx, float* __restrict__ out_maxp) {
+                                                          int32_t* __restrict__ out_idx, float* __restrict__ out_maxp,
+                                                          const int32_t* __restrict__ n_dev) {
+  if (n_dev) n_words = min(n_words, max(*n_dev, 0));
   __shared__ float s_p[4][64];
   __shared__ int s_i[4][64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -401,13 +403,13 @@ __global__ void __launch_bounds__(128) text_scores_kernel(const float* __restric
 using namespace glass;
 
 extern "C" int glass_text_scores(const float* probs, int n_words, int steps, int classes, int stop_index, float* score,
-                                 int32_t* out_idx, float* out_maxp, void* stream_v) {
+                                 int32_t* out_idx, float* out_maxp, const int32_t* n_dev, void* stream_v) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
   GLASS_CHECK(probs && score, "null pointer");
   GLASS_CHECK(n_words >= 0 && steps > 0 && steps <= 64 && classes > 0, "steps must be in 1..64");
   if (n_words == 0) return 0;
   text_scores_kernel<<<(n_words + 3) / 4, 128, 0, stream>>>(probs, n_words, steps, classes, stop_index, score, out_idx,
-                                                           out_maxp);
+                                                           out_maxp, n_dev);
   count_launch();
   GLASS_CUDA(cudaGetLastError());
   return 0;

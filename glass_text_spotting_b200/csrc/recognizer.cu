@@ -4,8 +4,9 @@
 //   glass_hmean_rows   : BiLSTMBlockV2's mean over H (recognizer_encoder.py:118-120).
 //   glass_lstm_bidir   : nn.LSTM bidirectional recurrence (recognizer_encoder.py:141-142); the input
 //                        projection x W_ih^T + b runs on the tcgen05 GEMM, this kernel owns the T sequential
-//                        steps of h W_hh^T + cell update, persistent over all steps, one CTA per
-//                        (word group, direction); W_hh^T streams from L2.
+//                        steps of h W_hh^T + cell update, persistent over all steps: an 8-CTA cluster per
+//                        (64 words, direction) keeps split-fp16 W_hh resident in shared memory, the per-step product
+//                        runs on the tensor cores, h is exchanged through DSMEM.
 //   glass_aster_decode : AttentionRecognitionHead.sample (prediction_aster.py:63-99, 247-302): all 26
 //                        greedy steps (additive attention, GRU cell, classifier, argmax feedback) inside one
 //                        persistent kernel, one CTA per word group -- no per-step launches or host syncs.
@@ -262,116 +263,11 @@ __global__ void hmean_rows_kernel(const __half* __restrict__ shi, const __half* 
 // PyTorch gate order (i, f, g, o).  whh_t fp32 [2][H][4H] (k-major).  Output split-fp16 rows
 // [n_seq*T, 2H] (forward | backward) + optional fp32 copy.
 constexpr int LSTM_H = 256, LSTM_G = 1024;
-constexpr int LSTM_THREADS = LSTM_G / 2;                  // every thread owns two adjacent gate rows
-
-// d = a * (b.x, b.y) + c on a register pair: Blackwell's packed FFMA2 with a scalar-broadcast first operand --
-// the same fused multiply-add per lane as FFMA, at half the issue slots
-__device__ __forceinline__ float2 ffma2_bcast(float a, float2 b, float2 c) {
-  float2 d;
-  asm("{\n"
-      ".reg .b64 ra, rb, rc, rd;\n"
-      "mov.b64 ra, {%2, %2};\n"
-      "mov.b64 rb, {%3, %4};\n"
-      "mov.b64 rc, {%5, %6};\n"
-      "fma.rn.f32x2 rd, ra, rb, rc;\n"
-      "mov.b64 {%0, %1}, rd;\n"
-      "}"
-      : "=f"(d.x), "=f"(d.y)
-      : "f"(a), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
-  return d;
-}
-
-// The recurrent product is issue-bound on the FMA stream (ncu: one LDG + two broadcast LDS.128 + 8 FFMA per k and
-// gate row): two gate rows per thread share the h loads, and word pairs go through FFMA2, i.e. 11 instructions per
-// 16 multiply-adds instead of 22.  Each accumulator still sums its 256 products in k order with fused multiply-adds.
-template <int WPC>  // words per CTA: W_hh^T (1 MB) streams from L2 once per WPC words and step
-__global__ void __launch_bounds__(LSTM_THREADS) lstm_bidir_kernel(const float* __restrict__ gates_in,
-                                                                 const float* __restrict__ whh_t, int n_seq, int T,
-                                                                 __half* __restrict__ out_hi, __half* __restrict__ out_lo,
-                                                                 float* __restrict__ out_f32) {
-  extern __shared__ __align__(16) float lstm_smem[];
-  float (*h_s)[WPC] = reinterpret_cast<float (*)[WPC]>(lstm_smem);                               // h[k][w]
-  float (*c_s)[LSTM_H] = reinterpret_cast<float (*)[LSTM_H]>(lstm_smem + LSTM_H * WPC);           // c[w][u]
-  float (*g_s)[LSTM_G] = reinterpret_cast<float (*)[LSTM_G]>(lstm_smem + 2 * LSTM_H * WPC);       // gates[w][row]
-  const int dir = blockIdx.y;
-  const int seq0 = blockIdx.x * WPC;
-  const int j = 2 * threadIdx.x;  // first of this thread's two gate rows
-  const float* wt = whh_t + (int64_t)dir * LSTM_H * LSTM_G;
-  for (int i = threadIdx.x; i < LSTM_H * WPC; i += blockDim.x) {
-    (&h_s[0][0])[i] = 0.f;
-    (&c_s[0][0])[i] = 0.f;
-  }
-  __syncthreads();
-  for (int step = 0; step < T; ++step) {
-    const int t = dir == 0 ? step : T - 1 - step;
-    float2 acc0[WPC / 2], acc1[WPC / 2];  // rows j / j + 1, word pairs (2q, 2q + 1)
-#pragma unroll
-    for (int q = 0; q < WPC / 2; ++q) {
-      float2 g[2];
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int s = seq0 + 2 * q + e;
-        g[e] = s < n_seq ? __ldg(reinterpret_cast<const float2*>(gates_in + ((int64_t)s * T + t) * (2 * LSTM_G) +
-                                                                 dir * LSTM_G + j))
-                         : make_float2(0.f, 0.f);
-      }
-      acc0[q] = make_float2(g[0].x, g[1].x);
-      acc1[q] = make_float2(g[0].y, g[1].y);
-    }
-    // (an explicit load-16/32-rows-then-compute structure was measured 10-25 % slower than letting the compiler
-    // software-pipeline this loop)
-#pragma unroll 8
-    for (int k = 0; k < LSTM_H; ++k) {
-      const float2 wv = __ldg(reinterpret_cast<const float2*>(wt + (int64_t)k * LSTM_G + j));
-#pragma unroll
-      for (int v = 0; v < WPC / 4; ++v) {
-        const float4 h = *reinterpret_cast<const float4*>(&h_s[k][4 * v]);
-        acc0[2 * v] = ffma2_bcast(wv.x, make_float2(h.x, h.y), acc0[2 * v]);
-        acc0[2 * v + 1] = ffma2_bcast(wv.x, make_float2(h.z, h.w), acc0[2 * v + 1]);
-        acc1[2 * v] = ffma2_bcast(wv.y, make_float2(h.x, h.y), acc1[2 * v]);
-        acc1[2 * v + 1] = ffma2_bcast(wv.y, make_float2(h.z, h.w), acc1[2 * v + 1]);
-      }
-    }
-    const int gate = j >> 8;  // 0:i 1:f 2:g 3:o (rows j and j + 1 belong to the same gate)
-#pragma unroll
-    for (int q = 0; q < WPC / 2; ++q) {
-      const float a[2][2] = {{acc0[q].x, acc1[q].x}, {acc0[q].y, acc1[q].y}};  // [word parity][row]
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        g_s[2 * q + e][j] = gate == 2 ? tanhf(a[e][0]) : sigmoidf_(a[e][0]);
-        g_s[2 * q + e][j + 1] = gate == 2 ? tanhf(a[e][1]) : sigmoidf_(a[e][1]);
-      }
-    }
-    __syncthreads();
-    for (int wu = threadIdx.x; wu < WPC * LSTM_H; wu += blockDim.x) {
-      const int w = wu >> 8, u = wu & 255;  // (word, hidden unit)
-      const float ig = g_s[w][u], fg = g_s[w][256 + u], gg = g_s[w][512 + u], og = g_s[w][768 + u];
-      const float c = fg * c_s[w][u] + ig * gg;
-      const float hn = og * tanhf(c);
-      c_s[w][u] = c;
-      h_s[u][w] = hn;
-      const int s = seq0 + w;
-      if (s < n_seq) {
-        const int64_t o = ((int64_t)s * T + t) * (2 * LSTM_H) + dir * LSTM_H + u;
-        __half hh, hl;
-        split16(hn, hh, hl);
-        out_hi[o] = hh;
-        out_lo[o] = hl;
-        if (out_f32) out_f32[o] = hn;
-      }
-    }
-    __syncthreads();
-  }
-}
 
 // ------------------------------------------------------------------------------------------ cluster-resident LSTM
-// OPT-IN (GLASS_LSTM_CLUSTER=1), written at the end of round 1 with seconds of GPU time left: on a B200 it passes
-// tests/test_gpu_kernels.py's LSTM-vs-torch.nn.LSTM tests (4 of 4) -- its arithmetic is the one tools/lstm_split_probe.py
-// emulates (5e-7 from fp64 after 32 steps) -- but it has NOT been timed and the rest of the suite has not run with it,
-// so lstm_bidir_kernel stays the default.
-//
-// Why: lstm_bidir_kernel re-streams W_hh^T (1 MB) from L2 on every step into every CTA and does the product on the fp32
-// pipe.  Here a cluster of 8 CTAs owns 64 words of one direction for all T steps; CTA r keeps the split-fp16 W_hh rows of
+// The recurrence on tensor cores (round 2: 0.50 ms per launch at 357 words against 0.60 ms for the fp32 kernel that
+// re-streamed W_hh^T (1 MB) from L2 on every step into every CTA; the whole GPU suite passes with it; its arithmetic is the
+// one tools/lstm_split_probe.py emulates, 5e-7 from fp64 after 32 steps).  A cluster of 8 CTAs owns 64 words of one direction for all T steps; CTA r keeps the split-fp16 W_hh rows of
 // ITS 32 hidden units x 4 gates (128 rows x 256 k, hi + lo = 132 KB) in shared memory for the whole kernel, and every
 // CTA holds the full h [64 words x 256] (hi + lo, 66 KB).  Per step a CTA computes gates[64 x 128] = h . W_r^T with
 // tensor-core mma.sync m16n8k16 (three products hi.hi + hi.lo + lo.hi, fp32 accumulate), updates c / h for its 32 units
@@ -407,8 +303,11 @@ __device__ __forceinline__ void lc_split(float x, float scale, __half& hi, __hal
 
 __global__ void __cluster_dims__(LC_R, 1, 1) __launch_bounds__(LC_THREADS, 1)
     lstm_cluster_mma_kernel(const float* __restrict__ gates_in, const float* __restrict__ whh_t, int n_seq, int T,
-                            __half* __restrict__ out_hi, __half* __restrict__ out_lo, float* __restrict__ out_f32) {
+                            __half* __restrict__ out_hi, __half* __restrict__ out_lo, float* __restrict__ out_f32,
+                            const int32_t* __restrict__ n_dev) {
   extern __shared__ __align__(16) unsigned char lc_smem[];
+  if (n_dev) n_seq = min(n_seq, max(*n_dev, 0));
+  if ((int)(blockIdx.x / LC_R) * LC_W >= n_seq) return;   // the whole cluster has no live word (uniform over its CTAs)
   __half* w_hi = reinterpret_cast<__half*>(lc_smem);   // [LC_N][LC_LD], row n = this CTA's gate column n (order below)
   __half* w_lo = w_hi + LC_N * LC_LD;
   __half* h_hi = w_lo + LC_N * LC_LD;                  // [LC_W][LC_LD], h[word][k] * LC_SH
@@ -550,17 +449,16 @@ __global__ void __cluster_dims__(LC_R, 1, 1) __launch_bounds__(LC_THREADS, 1)
 constexpr int DEC_D = 256, DEC_T_MAX = 32, DEC_WPC = 4, DEC_MAX_CLASSES = 128;
 
 struct AsterParams {
-  const float* x;      // [n_words, T, 256] encoder output
   const float* xproj;  // [n_words, T, 256] xEmbed(x) (+ bias)
+  const float* pctx;   // [n_words, T, 768] x . W_ih[:, 256:]^T
   int n_words, T, steps, num_classes;
+  const int32_t* n_words_dev;  // optional live word count (the grid covers n_words = capacity)
   const float* ws_t;   // [256][256] sEmbed^T
   const float* bs;     // [256]
   const float* we;     // [256] wEmbed weight
   float be;            // wEmbed bias
-  const float* emb;    // [num_classes][256]
-  const float* wih_t;  // [512][768] GRU W_ih^T (input = [emb ; context]), gate order (r, z, n)
-  const float* whh_t;  // [256][768]
-  const float* bih;    // [768]
+  const float* emb_gi; // [num_classes][768] W_ih[:, :256] . Emb[y] + b_ih
+  const float* whh_t;  // [256][768] GRU W_hh^T, gate order (r, z, n)
   const float* bhh;    // [768]
   const float* wo_t;   // [256][num_classes] fc^T
   const float* bo;     // [num_classes]
@@ -571,174 +469,16 @@ struct AsterParams {
   int* first_eos;      // [n_words] first step whose argmax is class 0 (steps if never)
 };
 
-__global__ void __launch_bounds__(1024) aster_decode_kernel(const AsterParams p) {
-  __shared__ __align__(16) float h_s[DEC_D][DEC_WPC];        // h[k][w]
-  __shared__ __align__(16) float u_s[2 * DEC_D][DEC_WPC];    // [emb ; context][w]
-  __shared__ float sp_s[DEC_WPC][DEC_D];
-  __shared__ float al_s[DEC_WPC][DEC_T_MAX];
-  __shared__ float gi_s[DEC_WPC][3 * DEC_D];
-  __shared__ float gh_s[DEC_WPC][3 * DEC_D];
-  __shared__ float o_s[DEC_WPC][DEC_MAX_CLASSES];
-  __shared__ int y_s[DEC_WPC], eos_s[DEC_WPC];
-  const int w0 = blockIdx.x * DEC_WPC;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int T = p.T, NC = p.num_classes;
-  for (int i = tid; i < DEC_D * DEC_WPC; i += blockDim.x) (&h_s[0][0])[i] = 0.f;
-  if (tid < DEC_WPC) {
-    y_s[tid] = 0;
-    eos_s[tid] = p.steps;
-  }
-  __syncthreads();
-
-  for (int step = 0; step < p.steps; ++step) {
-    // (1) sProj = sEmbed(h)
-    if (tid < DEC_D) {
-      float acc[DEC_WPC];
-      const float b = __ldg(p.bs + tid);
-#pragma unroll
-      for (int w = 0; w < DEC_WPC; ++w) acc[w] = b;
-#pragma unroll 8
-      for (int k = 0; k < DEC_D; ++k) {
-        const float wv = __ldg(p.ws_t + k * DEC_D + tid);
-        const float4 hv = *reinterpret_cast<const float4*>(&h_s[k][0]);
-        acc[0] += wv * hv.x; acc[1] += wv * hv.y; acc[2] += wv * hv.z; acc[3] += wv * hv.w;
-      }
-#pragma unroll
-      for (int w = 0; w < DEC_WPC; ++w) sp_s[w][tid] = acc[w];
-    }
-    __syncthreads();
-    // (2) e[w][t] = we . tanh(sProj + xProj[t]) + be, one warp per (w, t)
-    for (int pair = warp; pair < DEC_WPC * T; pair += (blockDim.x >> 5)) {
-      const int w = pair / T, t = pair - w * T;
-      const int word = w0 + w;
-      float acc = 0.f;
-      if (word < p.n_words) {
-        const float* xp = p.xproj + ((int64_t)word * T + t) * DEC_D;
-        for (int a = lane; a < DEC_D; a += 32) acc += __ldg(p.we + a) * tanhf(sp_s[w][a] + __ldg(xp + a));
-      }
-      acc = warp_sum(acc);
-      if (lane == 0) al_s[w][t] = acc + p.be;
-    }
-    __syncthreads();
-    // (3) alpha = softmax_t(e), one warp per word
-    if (warp < DEC_WPC) {
-      const float v = lane < T ? al_s[warp][lane] : -CUDART_INF_F;
-      const float mx = warp_max(v);
-      const float e = lane < T ? expf(v - mx) : 0.f;
-      const float s = warp_sum(e);
-      if (lane < T) {
-        const float a = e / s;
-        al_s[warp][lane] = a;
-        const int word = w0 + warp;
-        if (p.alphas && word < p.n_words) p.alphas[((int64_t)word * p.steps + step) * T + lane] = a;
-      }
-    }
-    __syncthreads();
-    // (4) u = [Emb[y] ; sum_t alpha_t x_t]
-    {
-      const int w = tid >> 8, k = tid & 255;  // 4 words x 256
-      const int word = w0 + w;
-      float c = 0.f;
-      if (word < p.n_words) {
-        const float* xw = p.x + (int64_t)word * T * DEC_D + k;
-        for (int t = 0; t < T; ++t) c += al_s[w][t] * __ldg(xw + (int64_t)t * DEC_D);
-      }
-      u_s[DEC_D + k][w] = c;
-      u_s[k][w] = __ldg(p.emb + (int64_t)y_s[w] * DEC_D + k);
-    }
-    __syncthreads();
-    // (5) GRU pre-activations: gi = W_ih u + b_ih (768 x 512), gh = W_hh h + b_hh (768 x 256)
-    if (tid < 3 * DEC_D) {
-      float a[DEC_WPC], b[DEC_WPC];
-      const float bi = __ldg(p.bih + tid), bh = __ldg(p.bhh + tid);
-#pragma unroll
-      for (int w = 0; w < DEC_WPC; ++w) { a[w] = bi; b[w] = bh; }
-#pragma unroll 8
-      for (int k = 0; k < 2 * DEC_D; ++k) {
-        const float wv = __ldg(p.wih_t + (int64_t)k * (3 * DEC_D) + tid);
-        const float4 uv = *reinterpret_cast<const float4*>(&u_s[k][0]);
-        a[0] += wv * uv.x; a[1] += wv * uv.y; a[2] += wv * uv.z; a[3] += wv * uv.w;
-      }
-#pragma unroll 8
-      for (int k = 0; k < DEC_D; ++k) {
-        const float wv = __ldg(p.whh_t + (int64_t)k * (3 * DEC_D) + tid);
-        const float4 hv = *reinterpret_cast<const float4*>(&h_s[k][0]);
-        b[0] += wv * hv.x; b[1] += wv * hv.y; b[2] += wv * hv.z; b[3] += wv * hv.w;
-      }
-#pragma unroll
-      for (int w = 0; w < DEC_WPC; ++w) { gi_s[w][tid] = a[w]; gh_s[w][tid] = b[w]; }
-    }
-    __syncthreads();
-    // (6) GRU cell
-    {
-      const int w = tid >> 8, k = tid & 255;
-      const float r = sigmoidf_(gi_s[w][k] + gh_s[w][k]);
-      const float z = sigmoidf_(gi_s[w][DEC_D + k] + gh_s[w][DEC_D + k]);
-      const float n = tanhf(gi_s[w][2 * DEC_D + k] + r * gh_s[w][2 * DEC_D + k]);
-      h_s[k][w] = (1.0f - z) * n + z * h_s[k][w];
-    }
-    __syncthreads();
-    // (7) classifier
-    if (tid < NC) {
-      float acc[DEC_WPC];
-      const float b = __ldg(p.bo + tid);
-#pragma unroll
-      for (int w = 0; w < DEC_WPC; ++w) acc[w] = b;
-#pragma unroll 8
-      for (int k = 0; k < DEC_D; ++k) {
-        const float wv = __ldg(p.wo_t + (int64_t)k * NC + tid);
-        const float4 hv = *reinterpret_cast<const float4*>(&h_s[k][0]);
-        acc[0] += wv * hv.x; acc[1] += wv * hv.y; acc[2] += wv * hv.z; acc[3] += wv * hv.w;
-      }
-#pragma unroll
-      for (int w = 0; w < DEC_WPC; ++w) o_s[w][tid] = acc[w] * p.temperature;
-    }
-    __syncthreads();
-    // (8) softmax + argmax (first maximal index), one warp per word
-    if (warp < DEC_WPC) {
-      const int word = w0 + warp;
-      float mx = -CUDART_INF_F;
-      int arg = 0x7fffffff;
-      for (int v = lane; v < NC; v += 32) {
-        const float o = o_s[warp][v];
-        if (o > mx) { mx = o; arg = v; }
-      }
-      for (int off = 16; off > 0; off >>= 1) {
-        const float om = __shfl_xor_sync(0xffffffffu, mx, off);
-        const int oa = __shfl_xor_sync(0xffffffffu, arg, off);
-        if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
-      }
-      float s = 0.f;
-      for (int v = lane; v < NC; v += 32) s += expf(o_s[warp][v] - mx);
-      s = warp_sum(s);
-      if (word < p.n_words) {
-        for (int v = lane; v < NC; v += 32) {
-          const int64_t o = ((int64_t)word * p.steps + step) * NC + v;
-          p.probs[o] = expf(o_s[warp][v] - mx) / s;
-          if (p.logits) p.logits[o] = o_s[warp][v];
-        }
-      }
-      if (lane == 0) {
-        y_s[warp] = arg;
-        if (arg == 0 && eos_s[warp] == p.steps) eos_s[warp] = step;
-      }
-    }
-    __syncthreads();
-  }
-  if (tid < DEC_WPC && w0 + tid < p.n_words) p.first_eos[w0 + tid] = eos_s[tid];
-}
-
-// ------------------------------------------------------------------------------------------ decoder, precomputed input
-// OPT-IN variant (glass_aster_decode_pre, GLASS_DEC_PRE=1 on the Python side), written at the end of round 1 with no GPU
-// time left: it compiles, it has NOT run on hardware; aster_decode_kernel above stays the default and is untouched.
-// Two algebraic cuts remove the 1.5 MB W_ih stream (of 2.6 MB per step and CTA) from the step loop:
+// The GRU's input product never streams W_ih (1.5 MB per step and CTA in round 1's first kernel): two algebraic cuts,
 //   * the GRU input is [Emb[y_prev] ; context]: W_ih[:, :256] . Emb[y] + b_ih only takes num_classes values -> a table
 //     emb_gi [num_classes][768] built once at weight-packing time;
 //   * W_ih[:, 256:] . context = sum_t alpha_t (W_ih[:, 256:] . x_t): pctx = x . W_ih[:, 256:]^T [n_words, T, 768] comes
 //     from the conv GEMM once per word (like xProj), the step does a T-term weighted sum of its rows.
-// The context vector itself is no longer formed (nothing else reads it).  Everything else is aster_decode_kernel.
-__global__ void __launch_bounds__(1024) aster_decode_pre_kernel(const AsterParams p, const float* __restrict__ emb_gi,
-                                                                const float* __restrict__ pctx) {
+// The context vector itself is never formed (nothing else reads it).  Validated on B200 against the oracle and the
+// reference-run golden vectors (tests/test_gpu_roi_heads.py, tests/test_gpu_fullsize_parity.py).
+__global__ void __launch_bounds__(1024) aster_decode_kernel(const AsterParams p) {
+  const float* __restrict__ emb_gi = p.emb_gi;
+  const float* __restrict__ pctx = p.pctx;
   __shared__ __align__(16) float h_s[DEC_D][DEC_WPC];        // h[k][w]
   __shared__ float sp_s[DEC_WPC][DEC_D];
   __shared__ float al_s[DEC_WPC][DEC_T_MAX];
@@ -747,6 +487,8 @@ __global__ void __launch_bounds__(1024) aster_decode_pre_kernel(const AsterParam
   __shared__ float o_s[DEC_WPC][DEC_MAX_CLASSES];
   __shared__ int y_s[DEC_WPC], eos_s[DEC_WPC];
   const int w0 = blockIdx.x * DEC_WPC;
+  const int n_words = p.n_words_dev ? min(p.n_words, max(*p.n_words_dev, 0)) : p.n_words;
+  if (w0 >= n_words) return;   // uniform over the CTA
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int T = p.T, NC = p.num_classes;
   for (int i = tid; i < DEC_D * DEC_WPC; i += blockDim.x) (&h_s[0][0])[i] = 0.f;
@@ -778,7 +520,7 @@ __global__ void __launch_bounds__(1024) aster_decode_pre_kernel(const AsterParam
       const int w = pair / T, t = pair - w * T;
       const int word = w0 + w;
       float acc = 0.f;
-      if (word < p.n_words) {
+      if (word < n_words) {
         const float* xp = p.xproj + ((int64_t)word * T + t) * DEC_D;
         for (int a = lane; a < DEC_D; a += 32) acc += __ldg(p.we + a) * tanhf(sp_s[w][a] + __ldg(xp + a));
       }
@@ -796,7 +538,7 @@ __global__ void __launch_bounds__(1024) aster_decode_pre_kernel(const AsterParam
         const float a = e / s;
         al_s[warp][lane] = a;
         const int word = w0 + warp;
-        if (p.alphas && word < p.n_words) p.alphas[((int64_t)word * p.steps + step) * T + lane] = a;
+        if (p.alphas && word < n_words) p.alphas[((int64_t)word * p.steps + step) * T + lane] = a;
       }
     }
     __syncthreads();
@@ -812,7 +554,7 @@ __global__ void __launch_bounds__(1024) aster_decode_pre_kernel(const AsterParam
 #pragma unroll
       for (int w = 0; w < DEC_WPC; ++w) {
         const int word = w0 + w;
-        if (word < p.n_words) {
+        if (word < n_words) {
           const float* pw = pctx + (int64_t)word * T * (3 * DEC_D) + tid;
 #pragma unroll 8
           for (int t = 0; t < T; ++t) a[w] += al_s[w][t] * __ldg(pw + (int64_t)t * (3 * DEC_D));
@@ -870,7 +612,7 @@ __global__ void __launch_bounds__(1024) aster_decode_pre_kernel(const AsterParam
       float s = 0.f;
       for (int v = lane; v < NC; v += 32) s += expf(o_s[warp][v] - mx);
       s = warp_sum(s);
-      if (word < p.n_words) {
+      if (word < n_words) {
         for (int v = lane; v < NC; v += 32) {
           const int64_t o = ((int64_t)word * p.steps + step) * NC + v;
           p.probs[o] = expf(o_s[warp][v] - mx) / s;
@@ -884,7 +626,7 @@ __global__ void __launch_bounds__(1024) aster_decode_pre_kernel(const AsterParam
     }
     __syncthreads();
   }
-  if (tid < DEC_WPC && w0 + tid < p.n_words) p.first_eos[w0 + tid] = eos_s[tid];
+  if (tid < DEC_WPC && w0 + tid < n_words) p.first_eos[w0 + tid] = eos_s[tid];
 }
 
 // rows after the image's break step are zero: break step = max over the image's words of first_eos
@@ -947,76 +689,37 @@ extern "C" int glass_hmean_rows(const void* src_hi, const void* src_lo, int n, i
 }
 
 extern "C" int glass_lstm_bidir(const float* gates_in, const float* whh_t, int n_seq, int T, int hidden, void* out_hi,
-                                void* out_lo, float* out_f32, void* stream) {
+                                void* out_lo, float* out_f32, const int32_t* n_dev, void* stream) {
   GLASS_CHECK(gates_in && whh_t && out_hi && out_lo, "null pointer");
   GLASS_CHECK(hidden == LSTM_H, "hidden size must be 256");
   GLASS_CHECK(n_seq >= 0 && T > 0, "bad shape");
   if (n_seq == 0) return 0;
-  // 16 words per CTA once that still fills >= 40 SMs (the L2 stream of W_hh^T is the bound), else 8
-  static const int cluster_env = getenv("GLASS_LSTM_CLUSTER") ? atoi(getenv("GLASS_LSTM_CLUSTER")) : 1;
-  if (cluster_env) {   // opt-in: parity-tested on B200, not yet timed (see lstm_cluster_mma_kernel)
-    GLASS_CUDA(cudaFuncSetAttribute(lstm_cluster_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LC_SMEM));
-    dim3 grid(((n_seq + LC_W - 1) / LC_W) * LC_R, 2);
-    lstm_cluster_mma_kernel<<<grid, LC_THREADS, LC_SMEM, STREAM>>>(gates_in, whh_t, n_seq, T, (__half*)out_hi,
-                                                                    (__half*)out_lo, out_f32);
-    count_launch();
-    GLASS_CUDA(cudaGetLastError());
-    return 0;
-  }
-  static const int wpc_env = getenv("GLASS_LSTM_WPC") ? atoi(getenv("GLASS_LSTM_WPC")) : 0;  // A/B knob
-  const int wpc = wpc_env ? wpc_env : 8;  // 16 was measured 2x slower: the CTA is latency-bound, not L2-bound
-  auto launch = [&](auto kern, int w) -> cudaError_t {
-    const int smem = (2 * LSTM_H * w + w * LSTM_G) * (int)sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    dim3 grid((n_seq + w - 1) / w, 2);
-    kern<<<grid, LSTM_THREADS, smem, STREAM>>>(gates_in, whh_t, n_seq, T, (__half*)out_hi, (__half*)out_lo, out_f32);
-    return cudaSuccess;
-  };
-  if (wpc == 16) GLASS_CUDA(launch(lstm_bidir_kernel<16>, 16));
-  else GLASS_CUDA(launch(lstm_bidir_kernel<8>, 8));
+  static const cudaError_t attr = cudaFuncSetAttribute(lstm_cluster_mma_kernel,
+                                                       cudaFuncAttributeMaxDynamicSharedMemorySize, LC_SMEM);
+  GLASS_CUDA(attr);
+  dim3 grid(((n_seq + LC_W - 1) / LC_W) * LC_R, 2);
+  lstm_cluster_mma_kernel<<<grid, LC_THREADS, LC_SMEM, STREAM>>>(gates_in, whh_t, n_seq, T, (__half*)out_hi,
+                                                                  (__half*)out_lo, out_f32, n_dev);
   count_launch();
   GLASS_CUDA(cudaGetLastError());
   return 0;
 }
 
 extern "C" int glass_aster_decode(const GlassAsterParams* p, void* stream) {
-  GLASS_CHECK(p != nullptr && p->x && p->xproj && p->probs && p->first_eos, "null pointer");
-  GLASS_CHECK(p->ws_t && p->bs && p->we && p->emb && p->wih_t && p->whh_t && p->bih && p->bhh && p->wo_t && p->bo,
-              "null weight pointer");
+  GLASS_CHECK(p != nullptr && p->xproj && p->pctx && p->probs && p->first_eos, "null pointer");
+  GLASS_CHECK(p->ws_t && p->bs && p->we && p->emb_gi && p->whh_t && p->bhh && p->wo_t && p->bo, "null weight pointer");
   GLASS_CHECK(p->dim == DEC_D, "dim must be 256");
   GLASS_CHECK(p->T >= 1 && p->T <= DEC_T_MAX, "T must be in [1,32]");
   GLASS_CHECK(p->num_classes >= 2 && p->num_classes <= DEC_MAX_CLASSES, "num_classes must be in [2,128]");
   GLASS_CHECK(p->steps >= 1, "steps must be positive");
   if (p->n_words == 0) return 0;
   AsterParams k{};
-  k.x = p->x; k.xproj = p->xproj; k.n_words = p->n_words; k.T = p->T; k.steps = p->steps; k.num_classes = p->num_classes;
-  k.ws_t = p->ws_t; k.bs = p->bs; k.we = p->we; k.be = p->be; k.emb = p->emb; k.wih_t = p->wih_t; k.whh_t = p->whh_t;
-  k.bih = p->bih; k.bhh = p->bhh; k.wo_t = p->wo_t; k.bo = p->bo; k.temperature = p->temperature;
+  k.xproj = p->xproj; k.pctx = p->pctx; k.n_words = p->n_words; k.n_words_dev = p->n_words_dev; k.T = p->T;
+  k.steps = p->steps; k.num_classes = p->num_classes;
+  k.ws_t = p->ws_t; k.bs = p->bs; k.we = p->we; k.be = p->be; k.emb_gi = p->emb_gi; k.whh_t = p->whh_t;
+  k.bhh = p->bhh; k.wo_t = p->wo_t; k.bo = p->bo; k.temperature = p->temperature;
   k.probs = p->probs; k.logits = p->logits; k.alphas = p->alphas; k.first_eos = p->first_eos;
   aster_decode_kernel<<<(p->n_words + DEC_WPC - 1) / DEC_WPC, 1024, 0, STREAM>>>(k);
-  count_launch();
-  GLASS_CUDA(cudaGetLastError());
-  return 0;
-}
-
-extern "C" int glass_aster_decode_pre(const GlassAsterParams* p, const float* emb_gi, const float* pctx, int ld_pctx,
-                                     void* stream) {
-  GLASS_CHECK(p != nullptr && p->x && p->xproj && p->probs && p->first_eos, "null pointer");
-  GLASS_CHECK(p->ws_t && p->bs && p->we && p->whh_t && p->bhh && p->wo_t && p->bo, "null weight pointer");
-  GLASS_CHECK(emb_gi && pctx, "emb_gi / pctx missing");
-  GLASS_CHECK(ld_pctx == 3 * DEC_D, "pctx rows must be exactly 768 wide");
-  GLASS_CHECK(p->dim == DEC_D, "dim must be 256");
-  GLASS_CHECK(p->T >= 1 && p->T <= DEC_T_MAX, "T must be in [1,32]");
-  GLASS_CHECK(p->num_classes >= 2 && p->num_classes <= DEC_MAX_CLASSES, "num_classes must be in [2,128]");
-  GLASS_CHECK(p->steps >= 1, "steps must be positive");
-  if (p->n_words == 0) return 0;
-  AsterParams k{};
-  k.x = p->x; k.xproj = p->xproj; k.n_words = p->n_words; k.T = p->T; k.steps = p->steps; k.num_classes = p->num_classes;
-  k.ws_t = p->ws_t; k.bs = p->bs; k.we = p->we; k.be = p->be; k.emb = p->emb; k.wih_t = p->wih_t; k.whh_t = p->whh_t;
-  k.bih = p->bih; k.bhh = p->bhh; k.wo_t = p->wo_t; k.bo = p->bo; k.temperature = p->temperature;
-  k.probs = p->probs; k.logits = p->logits; k.alphas = p->alphas; k.first_eos = p->first_eos;
-  aster_decode_pre_kernel<<<(p->n_words + DEC_WPC - 1) / DEC_WPC, 1024, 0, STREAM>>>(k, emb_gi, pctx);
   count_launch();
   GLASS_CUDA(cudaGetLastError());
   return 0;

@@ -16,7 +16,9 @@ SYMBOLS = [
     "glass_nms_workspace_bytes",
     "glass_nms_rotated", "glass_box_decode", "glass_gc_attention", "glass_hmean_rows", "glass_lstm_bidir",
     "glass_aster_decode", "glass_aster_finalize", "glass_resize_bilinear_u8", "glass_postprocess_merge", "glass_text_scores", "glass_zero_border", "glass_stem_s2d", "glass_mask_finalize", "glass_paste_masks_rotated",
-    "glass_box_iou_rotated", "glass_nms_rotated_all", "glass_nms_rotated_all_workspace_bytes", "glass_aster_decode_pre",
+    "glass_box_iou_rotated", "glass_nms_rotated_all", "glass_nms_rotated_all_workspace_bytes",
+    "glass_plan_create", "glass_plan_launch", "glass_plan_destroy", "glass_prepack_weights", "glass_pack_rois",
+    "glass_pack_detections",
 ]
 
 
@@ -87,16 +89,16 @@ class GcAttentionParams(C.Structure):
         ("f_hi", C.c_void_p), ("f_lo", C.c_void_p), ("y_hi", C.c_void_p), ("y_lo", C.c_void_p),
         ("n_words", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("border", C.c_int32), ("channels", C.c_int32),
         ("w_mask", C.c_void_p), ("b_mask", C.c_float), ("w1t", C.c_void_p), ("b1", C.c_void_p), ("ln_g", C.c_void_p),
-        ("ln_b", C.c_void_p), ("w2t", C.c_void_p), ("b2", C.c_void_p),
+        ("ln_b", C.c_void_p), ("w2t", C.c_void_p), ("b2", C.c_void_p), ("n_words_dev", C.c_void_p),
     ]
 
 
 class AsterParams(C.Structure):
     _fields_ = [
-        ("x", C.c_void_p), ("xproj", C.c_void_p), ("n_words", C.c_int32), ("T", C.c_int32), ("steps", C.c_int32),
-        ("num_classes", C.c_int32), ("dim", C.c_int32), ("ws_t", C.c_void_p), ("bs", C.c_void_p), ("we", C.c_void_p),
-        ("be", C.c_float), ("emb", C.c_void_p), ("wih_t", C.c_void_p), ("whh_t", C.c_void_p), ("bih", C.c_void_p),
-        ("bhh", C.c_void_p), ("wo_t", C.c_void_p), ("bo", C.c_void_p), ("temperature", C.c_float),
+        ("xproj", C.c_void_p), ("pctx", C.c_void_p), ("n_words", C.c_int32), ("n_words_dev", C.c_void_p),
+        ("T", C.c_int32), ("steps", C.c_int32), ("num_classes", C.c_int32), ("dim", C.c_int32),
+        ("ws_t", C.c_void_p), ("bs", C.c_void_p), ("we", C.c_void_p), ("be", C.c_float), ("emb_gi", C.c_void_p),
+        ("whh_t", C.c_void_p), ("bhh", C.c_void_p), ("wo_t", C.c_void_p), ("bo", C.c_void_p), ("temperature", C.c_float),
         ("probs", C.c_void_p), ("logits", C.c_void_p), ("alphas", C.c_void_p), ("first_eos", C.c_void_p),
     ]
 
@@ -132,11 +134,17 @@ def load() -> C.CDLL:
     lib.glass_launch_count.restype = C.c_int64
     i, p, f = C.c_int, C.c_void_p, C.POINTER(C.c_float)
     lib.glass_conv_gemm.argtypes = [C.POINTER(ConvGemmParams), p]
+    lib.glass_plan_create.argtypes = [C.POINTER(ConvGemmParams), C.POINTER(C.c_void_p)]
+    lib.glass_plan_launch.argtypes = [p, p]
+    lib.glass_plan_destroy.argtypes = [p]
+    lib.glass_prepack_weights.argtypes = [p, i, i, p, p, p, p]
+    lib.glass_pack_rois.argtypes = [p, p, i, i, p, p, p, p]
+    lib.glass_pack_detections.argtypes = [p, p, p, p, p, p, i, i, i, i, p, p]
     lib.glass_pack_nchw.argtypes = [p, i, i, i, i, p, p, i, i, p]
     lib.glass_unpack_nchw.argtypes = [p, p, i, i, i, i, i, i, p, p]
     lib.glass_nhwc_f32_to_nchw.argtypes = [p, i, i, i, i, i, i, p, p]
-    lib.glass_gather_taps.argtypes = [p, p] + [i] * 13 + [p, p, p]
-    lib.glass_maxpool.argtypes = [p, p] + [i] * 13 + [p, p, i, p]
+    lib.glass_gather_taps.argtypes = [p, p] + [i] * 13 + [p, p, p, p]
+    lib.glass_maxpool.argtypes = [p, p] + [i] * 13 + [p, p, i, p, p]
     lib.glass_roi_align_rotated.argtypes = [C.POINTER(RoiAlignParams), p]
     lib.glass_image_roi_align_rotated.argtypes = [C.POINTER(ImageRoiAlignParams), p]
     lib.glass_rpn_topk_decode.argtypes = [C.POINTER(RpnTopkParams), p]
@@ -147,15 +155,14 @@ def load() -> C.CDLL:
     lib.glass_nms_rotated.argtypes = [C.POINTER(NmsParams), p]
     lib.glass_box_decode.argtypes = [p, i, p, p, i, i, f, p, p, p, p]
     lib.glass_gc_attention.argtypes = [C.POINTER(GcAttentionParams), p]
-    lib.glass_hmean_rows.argtypes = [p, p, i, i, i, i, i, p, p, p, p]
-    lib.glass_lstm_bidir.argtypes = [p, p, i, i, i, p, p, p, p]
+    lib.glass_hmean_rows.argtypes = [p, p, i, i, i, i, i, p, p, p, p, p]
+    lib.glass_lstm_bidir.argtypes = [p, p, i, i, i, p, p, p, p, p]
     lib.glass_aster_decode.argtypes = [C.POINTER(AsterParams), p]
-    lib.glass_aster_decode_pre.argtypes = [C.POINTER(AsterParams), p, p, i, p]
     lib.glass_aster_finalize.argtypes = [p, p, p, i, i, i, p]
     lib.glass_resize_bilinear_u8.argtypes = [p, i, i, i, p, i, i, p]
     lib.glass_postprocess_merge.argtypes = [C.POINTER(PostprocessParams), p]
-    lib.glass_text_scores.argtypes = [p, i, i, i, i, p, p, p, p]
-    lib.glass_zero_border.argtypes = [p, p, i, i, i, i, p]
+    lib.glass_text_scores.argtypes = [p, i, i, i, i, p, p, p, p, p]
+    lib.glass_zero_border.argtypes = [p, p, i, i, i, i, p, p]
     lib.glass_stem_s2d.argtypes = [p, i, i, i, f, f, p, p, p]
     lib.glass_mask_finalize.argtypes = [p, i, i, i, i, p, p]
     lib.glass_paste_masks_rotated.argtypes = [p, p, i, i, i, i, C.c_float, p, p, p]

@@ -64,44 +64,88 @@ class B200GlassRCNN:
             taps.update(features=feats, proposal_boxes=pb, objectness_logits=ps, proposal_count=pc)
         return feats, det
 
-    def recognize(self, images: torch.Tensor, feats, det, counts_host: List[int], taps: Optional[dict] = None):
-        n = images.shape[0]
-        rois = []
-        for i, c in enumerate(counts_host):
-            if c > 0:
-                b = det["pred_boxes"][i, :c]
-                rois.append(torch.cat((torch.full((c, 1), float(i), device=b.device), b), 1))
-        starts = [0]
-        for c in counts_host:
-            starts.append(starts[-1] + c)
-        word_start = torch.tensor(starts, dtype=torch.int32, device=images.device)
-        rois_t = torch.cat(rois).contiguous() if rois else torch.zeros((0, 6), device=images.device)
-        return self.roi_heads.forward_recognizer(images, tuple(images.shape[-2:]), feats, rois_t, word_start, n, taps), starts
+    @torch.no_grad()
+    def forward_packed(self, images: torch.Tensor, img_hw: torch.Tensor, taps: Optional[dict] = None):
+        """The whole hot path with NO host synchronisation (images: RAW fp32 [n,3,H,W] padded to /32 with the pixel mean):
+        backbone -> RPN -> box branch -> glass_pack_rois (detections become the recognizer's RoI list on the device) ->
+        recognizer sized for the capacity n * max_det, every kernel reading the live word count from device memory ->
+        glass_pack_detections.  Returns (rec [n, max_det, 10 + steps*classes] -- the fixed-size per-image record of the
+        end-of-loop all-gather, SURVEY.md 8e --, det dict, probs [capacity, steps, classes], word_start int32 [n+1]);
+        all device tensors in persistent workspaces, valid until the next call.  CUDA-graph capturable."""
+        feats, det = self.detect(images, img_hw, taps)
+        heads = self.roi_heads
+        n, m = det["pred_boxes"].shape[0], det["pred_boxes"].shape[1]
+        ws = heads.ws
+        rois = ws.raw("step.rois", (n * m, 6), torch.float32)
+        word_start = ws.raw("step.word_start", (n + 1,), torch.int32)
+        total = ws.raw("step.total", (1,), torch.int32)
+        ops.pack_rois(det["pred_boxes"], det["count"], rois, word_start, total)
+        probs = heads.forward_recognizer(images, tuple(images.shape[-2:]), feats, rois, word_start, n, taps, n_dev=total)
+        rec = ws.raw("step.rec", (n, m, 10 + heads.steps * heads.num_classes), torch.float32)
+        ops.pack_detections(det["pred_boxes"], det["scores"], det["orientations"] if heads.orientation_on else None,
+                            det["count"], probs, word_start, rec)
+        return rec, det, probs, word_start
 
     @torch.no_grad()
     def forward_device(self, images: torch.Tensor, img_hw: torch.Tensor, taps: Optional[dict] = None):
-        """Whole hot path on device tensors (images: RAW fp32 [n,3,H,W] padded to /32 with the pixel mean).
-        One host sync (the detection counts size the recognizer's batch)."""
-        feats, det = self.detect(images, img_hw, taps)
+        """``forward_packed`` + ONE read-back of the per-image detection counts AFTER everything is enqueued (the caller
+        wants host-side Instances): returns (det, probs [K_total, steps, classes], counts_host, starts)."""
+        _, det, probs, _ = self.forward_packed(images, img_hw, taps)
         counts_host = det["count"].cpu().tolist()
-        probs, starts = self.recognize(images, feats, det, counts_host, taps)
-        return det, probs, counts_host, starts
+        starts = [0]
+        for c in counts_host:
+            starts.append(starts[-1] + c)
+        return det, probs[: starts[-1]], counts_host, starts
 
     def pack_detections(self, det, probs: torch.Tensor, counts_host: List[int], starts: List[int]) -> torch.Tensor:
         """Fixed-size record per image for the end-of-loop all-gather:
-        [n, max_det, 1 + 5 + 1 + 1 + 2 + steps*classes] = (valid, box, score, class, orientation, text probs)."""
+        [n, max_det, 1 + 5 + 1 + 1 + 2 + steps*classes] = (valid, box, score, class, orientation, text probs);
+        one kernel (glass_pack_detections).  ``forward_packed`` produces the same record without the host counts."""
         n, m = det["pred_boxes"].shape[0], det["pred_boxes"].shape[1]
         tp = self.roi_heads.steps * self.roi_heads.num_classes
-        rec = torch.zeros((n, m, 10 + tp), dtype=torch.float32, device=probs.device)
-        for i, c in enumerate(counts_host):
-            if c == 0:
-                continue
-            rec[i, :c, 0] = 1.0
-            rec[i, :c, 1:6] = det["pred_boxes"][i, :c]
-            rec[i, :c, 6] = det["scores"][i, :c]
-            rec[i, :c, 8:10] = det["orientations"][i, :c]
-            rec[i, :c, 10:] = probs[starts[i]: starts[i + 1]].reshape(c, tp)
-        return rec
+        rec = torch.empty((n, m, 10 + tp), dtype=torch.float32, device=probs.device)
+        word_start = torch.tensor(starts, dtype=torch.int32, device=probs.device)
+        if probs.shape[0] == 0:
+            probs = torch.zeros((1, self.roi_heads.steps, self.roi_heads.num_classes), device=rec.device)
+        return ops.pack_detections(det["pred_boxes"], det["scores"],
+                                   det["orientations"] if self.roi_heads.orientation_on else None, det["count"],
+                                   probs.contiguous(), word_start, rec)
+
+    # ------------------------------------------------------------------ the step as ONE CUDA graph
+    @torch.no_grad()
+    def graph_step(self, images: torch.Tensor, img_hw: torch.Tensor) -> torch.Tensor:
+        """``forward_packed`` replayed from a CUDA graph (captured on first use per input shape, after two eager warm-up
+        passes that allocate every workspace): one graph launch per step instead of ~190 kernel launches, no host work
+        between them.  ``images`` / ``img_hw`` are copied into the graph's static inputs; returns the static record
+        buffer (valid until the next replay)."""
+        key = (tuple(images.shape), images.device.index)
+        g = self._graphs.get(key) if hasattr(self, "_graphs") else None
+        if g is None:
+            if not hasattr(self, "_graphs"):
+                self._graphs = {}
+            static_in = images.clone()
+            static_hw = img_hw.clone()
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self.forward_packed(static_in, static_hw)
+            cur.wait_stream(side)
+            torch.cuda.synchronize()
+            L = ops._lib.load()
+            before = L.glass_launch_count()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                rec, det, probs, word_start = self.forward_packed(static_in, static_hw)
+            g = self._graphs[key] = {"graph": graph, "in": static_in, "hw": static_hw, "rec": rec, "det": det,
+                                     "probs": probs, "word_start": word_start,
+                                     "launches": int(L.glass_launch_count() - before)}
+        g["in"].copy_(images, non_blocking=True)
+        g["hw"].copy_(img_hw, non_blocking=True)
+        g["graph"].replay()
+        self.last_graph = g
+        return g["rec"]
 
     @torch.no_grad()
     def inference(self, batched_inputs: List[dict], detected_instances: Optional[List[Instances]] = None,

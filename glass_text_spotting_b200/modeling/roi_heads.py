@@ -150,26 +150,23 @@ class B200GlassROIHeads:
         dp = "decoder.recognizer.decoder."
         self.x_embed = packing.pack_linear(sdr[dp + "attention_unit.xEmbed.weight"], sdr[dp + "attention_unit.xEmbed.bias"],
                                            device=dev)
+        # The GRU's input product is precomputed (include/glass_b200.h, glass_aster_decode): W_ih[:, :256] . Emb[y] + b_ih
+        # only takes num_classes values -> a [97, 768] table; W_ih[:, 256:] . context = sum_t alpha_t (W_ih[:, 256:] . x_t)
+        # -> one GEMM per launch (w_ctx), like xProj.
+        wih = sdr[dp + "gru.weight_ih_l0"]                                   # [768, 512], input = [embedding ; context]
+        table = sdr[dp + "tgt_embedding.weight"].double() @ wih[:, :256].double().t() + sdr[dp + "gru.bias_ih_l0"].double()
         self.dec = {
             "ws_t": sdr[dp + "attention_unit.sEmbed.weight"].t().contiguous().to(dev),
             "bs": sdr[dp + "attention_unit.sEmbed.bias"].to(dev),
             "we": sdr[dp + "attention_unit.wEmbed.weight"].view(-1).contiguous().to(dev),
             "be": float(sdr[dp + "attention_unit.wEmbed.bias"].item()),
-            "emb": sdr[dp + "tgt_embedding.weight"].contiguous().to(dev),
-            "wih_t": sdr[dp + "gru.weight_ih_l0"].t().contiguous().to(dev),
+            "emb_gi": table.float().contiguous().to(dev),
             "whh_t": sdr[dp + "gru.weight_hh_l0"].t().contiguous().to(dev),
-            "bih": sdr[dp + "gru.bias_ih_l0"].to(dev), "bhh": sdr[dp + "gru.bias_hh_l0"].to(dev),
+            "bhh": sdr[dp + "gru.bias_hh_l0"].to(dev),
             "wo_t": sdr[dp + "fc.weight"].t().contiguous().to(dev), "bo": sdr[dp + "fc.bias"].to(dev),
             "temperature": float(sdr[dp + "temperature"].item()) if (dp + "temperature") in sdr else 1.0,
         }
-        # OPT-IN (GLASS_DEC_PRE=1; compiles, not yet run on hardware): the decoder GRU's input product from two precomputed
-        # tensors instead of the 1.5 MB W_ih stream per step and CTA -- see aster_decode_pre_kernel (csrc/recognizer.cu)
-        self.dec_pre = None
-        if os.environ.get("GLASS_DEC_PRE", "1") == "1":
-            wih = sdr[dp + "gru.weight_ih_l0"]                                   # [768, 512], input = [embedding ; context]
-            table = sdr[dp + "tgt_embedding.weight"].double() @ wih[:, :256].double().t() + sdr[dp + "gru.bias_ih_l0"].double()
-            self.dec_pre = {"emb_gi": table.float().contiguous().to(dev),
-                            "w_ctx": packing.pack_linear(wih[:, 256:], None, device=dev)}
+        self.dec_w_ctx = packing.pack_linear(wih[:, 256:], None, device=dev)
 
     # ============================================================================================ box branch
     def box_features(self, features: Dict[str, Act], rois: torch.Tensor) -> torch.Tensor:
@@ -276,6 +273,12 @@ class B200GlassROIHeads:
         return instances
 
     # ============================================================================================ recognizer
+    # Two ways to size the recognizer: ``n_dev`` None = the host knows K (plugin surface, tests: every buffer view has K
+    # rows); ``n_dev`` = int32 device scalar = the live word count stays on the device (the fused step: buffers, grids and
+    # GEMM M spaces are sized for the capacity n_img * max_det, each kernel reads the count itself -- no host sync).
+    _n_dev: Optional[torch.Tensor] = None
+    _word_cap: int = 0
+
     def p2p3(self, features: Dict[str, Act]) -> Act:
         p2, p3 = features["p2"], features["p3"]
         t = self.ws.act("rec.p3conv", p3.n, 256, p3.h, p3.w)
@@ -288,98 +291,174 @@ class B200GlassROIHeads:
         """Recognizer-side activation: capacity = every detection slot of the batch, view of the n live words."""
         return self.ws.act(name, n, c, h, w, cp=cp, cap=self._word_cap)
 
+    def _conv(self, x: Act, w, out: Act, **kw) -> Act:
+        return ops.conv2d(x, w, out=out, mode=self.mode, n_dev=self._n_dev, **kw)
+
     def _basic_block(self, x: Act, blk, name: str) -> Act:
-        ws = self
-        t = ws.act(name + ".t", x.n, blk["conv1"].cout, x.h, x.w)
-        ops.conv2d(x, blk["conv1"], relu=True, out=t, mode=self.mode)
+        t = self.act(name + ".t", x.n, blk["conv1"].cout, x.h, x.w)
+        self._conv(x, blk["conv1"], t, relu=True)
         res = x
         if blk["down"] is not None:
-            res = ws.act(name + ".ds", x.n, blk["down"].cout, x.h, x.w)
-            ops.conv2d(x, blk["down"], out=res, mode=self.mode)
-        out = ws.act(name + ".out", x.n, blk["conv2"].cout, x.h, x.w)
-        ops.conv2d(t, blk["conv2"], relu=True, residual=res, out=out, mode=self.mode)
+            res = self.act(name + ".ds", x.n, blk["down"].cout, x.h, x.w)
+            self._conv(x, blk["down"], res)
+        out = self.act(name + ".out", x.n, blk["conv2"].cout, x.h, x.w)
+        self._conv(t, blk["conv2"], out, relu=True, residual=res)
         return out
 
-    def hybrid_net(self, crops: Act, f_out: Act, taps: Optional[dict] = None) -> None:
-        """ResNetFeatureExtractor on [K,3,128,128] crops; the [K,256,8,32] result lands in channels 0..255
-        of the fused buffer ``f_out`` (cp 512)."""
-        ws, m, k = self, self.mode, crops.n
-        x = ops.conv2d(crops, self.h_conv0_1, relu=True, out=ws.act("hyb.c01", k, 16, crops.h, crops.w, cp=16), mode=m)
-        x = ops.conv2d(x, self.h_conv0_2, relu=True, out=ws.act("hyb.c02", k, 32, x.h, x.w, cp=32), mode=m)
-        x = ops.maxpool2d(x, (2, 2), (2, 2), (0, 0), out=ws.act("hyb.pool1", k, 32, x.h // 2, x.w // 2, cp=32))
-        for b, blk in enumerate(self.h_layers[0]):
-            x = self._basic_block(x, blk, f"hyb.l1.{b}")
-        x = ops.conv2d(x, self.h_conv1, relu=True, out=ws.act("hyb.c1", k, x.c, x.h, x.w), mode=m)
-        x = ops.maxpool2d(x, (2, 2), (2, 2), (0, 0), out=ws.act("hyb.pool2", k, x.c, x.h // 2, x.w // 2))
-        for b, blk in enumerate(self.h_layers[1]):
-            x = self._basic_block(x, blk, f"hyb.l2.{b}")
-        x = ops.conv2d(x, self.h_conv2, relu=True, out=ws.act("hyb.c2", k, x.c, x.h, x.w), mode=m)
-        x = ops.maxpool2d(x, (2, 2), (2, 1), (0, 1), out=ws.act("hyb.pool3", k, x.c, x.h // 2, x.w + 1))
-        for b, blk in enumerate(self.h_layers[2]):
-            x = self._basic_block(x, blk, f"hyb.l3.{b}")
-        x = ops.conv2d(x, self.h_conv3, relu=True, out=ws.act("hyb.c3", k, x.c, x.h, x.w), mode=m)
+    HYBRID_STAGES = 6
+
+    def hybrid_stage(self, i: int, x: Act, f_out: Optional[Act] = None) -> Optional[Act]:
+        """Stage i of ResNetFeatureExtractor (local_feature_extraction.py:154-188), so that the parity tests can
+        teacher-force the 31-conv network in pieces:
+        0: conv0_1, conv0_2, pool -> [K,32,64,64]     1: layer1, conv1, pool -> [K,64,32,32]
+        2: layer2, conv2, pool(2,(2,1),(0,1)) -> [K,128,16,33]     3: layer3 blocks 0-2     4: layer3 blocks 3-4, conv3
+        5: layer4, conv4_1 (k2 s(2,1)) -> channels 0..255 of the fused buffer ``f_out`` [K,512,8,32] (returns None)."""
+        k, nd = x.n, self._n_dev
+        if i == 0:
+            x = self._conv(x, self.h_conv0_1, self.act("hyb.c01", k, 16, x.h, x.w, cp=16), relu=True)
+            x = self._conv(x, self.h_conv0_2, self.act("hyb.c02", k, 32, x.h, x.w, cp=32), relu=True)
+            return ops.maxpool2d(x, (2, 2), (2, 2), (0, 0), out=self.act("hyb.pool1", k, 32, x.h // 2, x.w // 2, cp=32),
+                                 n_dev=nd)
+        if i == 1:
+            for b, blk in enumerate(self.h_layers[0]):
+                x = self._basic_block(x, blk, f"hyb.l1.{b}")
+            x = self._conv(x, self.h_conv1, self.act("hyb.c1", k, x.c, x.h, x.w), relu=True)
+            return ops.maxpool2d(x, (2, 2), (2, 2), (0, 0), out=self.act("hyb.pool2", k, x.c, x.h // 2, x.w // 2), n_dev=nd)
+        if i == 2:
+            for b, blk in enumerate(self.h_layers[1]):
+                x = self._basic_block(x, blk, f"hyb.l2.{b}")
+            x = self._conv(x, self.h_conv2, self.act("hyb.c2", k, x.c, x.h, x.w), relu=True)
+            return ops.maxpool2d(x, (2, 2), (2, 1), (0, 1), out=self.act("hyb.pool3", k, x.c, x.h // 2, x.w + 1), n_dev=nd)
+        if i == 3:
+            for b, blk in enumerate(self.h_layers[2][:3]):
+                x = self._basic_block(x, blk, f"hyb.l3.{b}")
+            return x
+        if i == 4:
+            for b, blk in enumerate(self.h_layers[2][3:], start=3):
+                x = self._basic_block(x, blk, f"hyb.l3.{b}")
+            return self._conv(x, self.h_conv3, self.act("hyb.c3", k, x.c, x.h, x.w), relu=True)
+        assert i == 5 and f_out is not None
         for b, blk in enumerate(self.h_layers[3]):
             x = self._basic_block(x, blk, f"hyb.l4.{b}")
         # conv4_1: k2 s(2,1) p0 + BN + ReLU -> [K,256,8,32], written into the fused buffer's local half
         ho, wo = (x.h - 2) // 2 + 1, x.w - 1
         assert (ho, wo) == (f_out.h, f_out.w)
         g = self.ws.rows("hyb.c41.gather", k * ho * wo, 4 * x.cp, self._word_cap * ho * wo)
-        ops.gather_taps(x, 2, 2, 2, 1, 0, 0, ho, wo, out=g)
+        ops.gather_taps(x, 2, 2, 2, 1, 0, 0, ho, wo, out=g, n_dev=nd)
         ops.conv_gemm(g[0], g[1], g.shape[1], g.shape[2], [0], self.h_conv4_1, (k, ho, wo, 0), out_hi=f_out.hi,
                       out_lo=f_out.lo, out_geom=(f_out.hp, f_out.wp, f_out.border), ld_out=f_out.cp, relu_post=True,
-                      mode=m)
+                      mode=self.mode, m_count=None if nd is None else (nd, ho * wo))
+        return None
 
-    def forward_recognizer(self, images: torch.Tensor, pad_hw, features: Dict[str, Act], rois: torch.Tensor,
-                           word_start: torch.Tensor, n_img: int, taps: Optional[dict] = None) -> torch.Tensor:
-        """rois fp32 [K,6] (batch, cx, cy, w, h, angle) of the detections of all images, grouped by image;
-        word_start int32 [n_img+1].  Returns pred_text_prob [K, 26, 97]."""
-        K = rois.shape[0]
-        self._word_cap = max(n_img * self.max_det, K)
-        ws, m, cap = self, self.mode, self._word_cap
-        probs = torch.zeros((K, self.steps, self.num_classes), dtype=torch.float32, device=rois.device)
-        if K == 0:
-            return probs
-        ph, pw = self.pool_h, self.pool_w
-        g = self.p2p3(features)
-        fused = ws.act("rec.fused", K, 512, ph, pw)
-        ops.roi_align_rotated([g], rois, (ph, pw), [1.0 / self.strides[0]], self.recog_sampling, out_f32=False,
-                              out_split=(fused.buf, fused.hp, fused.wp, fused.border, 256, fused.cp))
-        crops = ws.act("rec.crops", K, 3, ph * 16, pw * 4, cp=8)
-        ops.image_roi_align_rotated(images, pad_hw, self.pixel_mean, self.pixel_std, rois, (ph * 16, pw * 4),
-                                    self.sampling, out_act=crops)
-        self.hybrid_net(crops, fused, taps)
-        fused2 = ws.act("rec.fused2", K, 512, ph, pw)
-        ops.gc_attention(fused, fused2, K, self.gc)
-        y = ops.conv2d(fused2, self.fusion_out, out=ws.act("rec.fusion_out", K, 256, ph, pw), mode=m)
-        # CNN_V1_1
-        x1 = ops.conv2d(y, self.r_conv1, relu=True, out=ws.act("rec.cnn1", K, 256, ph // 2, pw), mode=m,
-                        gather_buf=self.ws.rows("rec.cnn1.gather", K * (ph // 2) * pw, 2 * 256, cap * (ph // 2) * pw))
-        x2 = ops.conv2d(x1, self.r_conv2, relu_pre=True, residual=x1, out=ws.act("rec.cnn2", K, 256, ph // 2, pw), mode=m)
-        # BiLSTMBlockV2
+    def hybrid_net(self, crops: Act, f_out: Act) -> None:
+        """ResNetFeatureExtractor on [K,3,128,128] crops; the [K,256,8,32] result lands in channels 0..255
+        of the fused buffer ``f_out`` (cp 512)."""
+        x = crops
+        for i in range(self.HYBRID_STAGES):
+            x = self.hybrid_stage(i, x, f_out)
+
+    def fuse_and_encode(self, fused: Act, K: int):
+        """MultiAspectGCAttention (incl. its 3x3 output conv) -> CNN_V1_1 -> BiLSTMBlockV2 from the fused
+        [local | global] features.  Returns (fusion_out Act, recog_cnn Act, seq split rows, enc_f32)."""
+        ph, pw, cap, nd, m = self.pool_h, self.pool_w, self._word_cap, self._n_dev, self.mode
+        fused2 = self.act("rec.fused2", K, 512, ph, pw)
+        ops.gc_attention(fused, fused2, K, self.gc, n_dev=nd)
+        y = self._conv(fused2, self.fusion_out, self.act("rec.fusion_out", K, 256, ph, pw))
+        x2, seq, enc_f32 = self.recognizer_cnn_encoder(y, K)
+        return fused2, y, x2, seq, enc_f32
+
+    def recognizer_cnn_encoder(self, y: Act, K: int):
+        """CNN_V1_1 (recognizer_backbone.py:77-81) -> mean over H -> 2 x (BiLSTM + Linear) (recognizer_encoder.py:118-144)."""
+        ph, pw, cap, nd, m = self.pool_h, self.pool_w, self._word_cap, self._n_dev, self.mode
         T = pw
+        x1 = self._conv(y, self.r_conv1, self.act("rec.cnn1", K, 256, ph // 2, pw), relu=True,
+                        gather_buf=self.ws.rows("rec.cnn1.gather", K * (ph // 2) * pw, 2 * 256, cap * (ph // 2) * pw))
+        x2 = self._conv(x1, self.r_conv2, self.act("rec.cnn2", K, 256, ph // 2, pw), relu_pre=True, residual=x1)
+        mc = None if nd is None else (nd, T)
         seq = self.ws.rows("rec.seq0", K * T, 256, cap * T)
-        ops.hmean_rows(x2, K, seq)
+        ops.hmean_rows(x2, K, seq, n_dev=nd)
         enc_f32 = None
         for l, lw in enumerate(self.lstm):
-            _, gates = ops.linear(seq, lw["wih"], want_split=False, want_f32=True, mode=m)
+            gates = self.ws.rows(f"rec.lstm{l}.gates", K * T, lw["wih"].n_p, cap * T, planes=1, dtype=torch.float32)[0]
+            ops.linear(seq, lw["wih"], want_split=False, want_f32=True, mode=m, out_f32=gates, m_count=mc)
             hcat = self.ws.rows(f"rec.lstm{l}.h", K * T, 512, cap * T)
-            ops.lstm_bidir(gates, lw["whh_t"], K, T, hcat)
-            seq, enc_f32 = ops.linear(hcat, lw["linear"], want_f32=(l == len(self.lstm) - 1), mode=m)
-        # ASTER decoder
-        _, xproj = ops.linear(seq, self.x_embed, want_split=False, want_f32=True, mode=m)
+            ops.lstm_bidir(gates, lw["whh_t"], K, T, hcat, n_dev=nd)
+            last = l == len(self.lstm) - 1
+            seq = self.ws.rows(f"rec.lstm{l}.out", K * T, lw["linear"].n_p, cap * T)
+            if last:
+                enc_f32 = self.ws.rows("rec.enc_f32", K * T, lw["linear"].n_p, cap * T, planes=1, dtype=torch.float32)[0]
+            ops.linear(hcat, lw["linear"], want_f32=last, mode=m, out=seq, out_f32=enc_f32, m_count=mc)
+        return x2, seq, enc_f32
+
+    def decode(self, seq: torch.Tensor, K: int, word_start: torch.Tensor, n_img: int, probs: torch.Tensor,
+               taps: Optional[dict] = None):
+        """ASTER decoder (prediction_aster.py:63-99) on the encoder output rows ``seq`` [2, K*T, 256] -> probs [K,26,97]."""
+        T, cap, nd, m = self.pool_w, self._word_cap, self._n_dev, self.mode
+        mc = None if nd is None else (nd, T)
+        xproj = self.ws.rows("rec.xproj", K * T, self.x_embed.n_p, cap * T, planes=1, dtype=torch.float32)[0]
+        ops.linear(seq, self.x_embed, want_split=False, want_f32=True, mode=m, out_f32=xproj, m_count=mc)
+        pctx = self.ws.rows("rec.pctx", K * T, self.dec_w_ctx.n_p, cap * T, planes=1, dtype=torch.float32)[0]
+        ops.linear(seq, self.dec_w_ctx, want_split=False, want_f32=True, mode=m, out_f32=pctx, m_count=mc)
         first_eos = self.ws.raw("rec.first_eos", (cap,), torch.int32)
         logits = alphas = None
         if taps is not None:
             logits = torch.zeros_like(probs)
-            alphas = torch.zeros((K, self.steps, T), dtype=torch.float32, device=rois.device)
-        emb_gi = pctx = None
-        if self.dec_pre is not None:
-            emb_gi = self.dec_pre["emb_gi"]
-            _, pctx = ops.linear(seq, self.dec_pre["w_ctx"], want_split=False, want_f32=True, mode=m)
-        ops.aster_decode(enc_f32, xproj, K, T, self.steps, self.num_classes, self.dec, probs, first_eos, logits, alphas,
-                         emb_gi=emb_gi, pctx=pctx)
+            alphas = torch.zeros((K, self.steps, T), dtype=torch.float32, device=probs.device)
+        ops.aster_decode(xproj, pctx, K, T, self.steps, self.num_classes, self.dec, probs, first_eos, logits, alphas, n_dev=nd)
         ops.aster_finalize(probs, first_eos, word_start, n_img, self.steps, self.num_classes)
+        return logits, alphas, first_eos
+
+    def forward_recognizer(self, images: torch.Tensor, pad_hw, features: Dict[str, Act], rois: torch.Tensor,
+                           word_start: torch.Tensor, n_img: int, taps: Optional[dict] = None,
+                           n_dev: Optional[torch.Tensor] = None, teacher: Optional[dict] = None) -> torch.Tensor:
+        """rois fp32 [K,6] (batch, cx, cy, w, h, angle) of the detections of all images, grouped by image;
+        word_start int32 [n_img+1].  Returns pred_text_prob [K, 26, 97].
+        ``n_dev`` (int32 device scalar): the live word count; ``rois`` then has capacity rows (glass_pack_rois) and the
+        result is a persistent [capacity, 26, 97] buffer whose rows >= count are stale.
+        ``teacher`` (parity tests only): {"local_feats": fp32 [K,256,8,32]} replaces the local CNN's output and
+        {"fusion_out": fp32 [K,256,8,32]} the fusion network's, so the stages after them are checked on the ORACLE's
+        inputs (stage-wise teacher forcing)."""
+        K = rois.shape[0]
+        self._word_cap = max(n_img * self.max_det, K)
+        self._n_dev = n_dev
+        try:
+            return self._forward_recognizer(images, pad_hw, features, rois, word_start, n_img, taps, teacher)
+        finally:
+            self._n_dev = None
+
+    def _forward_recognizer(self, images, pad_hw, features, rois, word_start, n_img, taps, teacher):
+        K, nd, cap = rois.shape[0], self._n_dev, self._word_cap
+        if nd is None:
+            probs = torch.zeros((K, self.steps, self.num_classes), dtype=torch.float32, device=rois.device)
+        else:
+            assert K == cap
+            probs = self.ws.raw("rec.probs", (cap, self.steps, self.num_classes), torch.float32)
+        if K == 0:
+            return probs
+        ph, pw = self.pool_h, self.pool_w
+        g = self.p2p3(features)
+        fused = self.act("rec.fused", K, 512, ph, pw)
+        ops.roi_align_rotated([g], rois, (ph, pw), [1.0 / self.strides[0]], self.recog_sampling, out_f32=False,
+                              out_split=(fused.buf, fused.hp, fused.wp, fused.border, 256, fused.cp), n_rois_dev=nd)
+        crops = self.act("rec.crops", K, 3, ph * 16, pw * 4, cp=8)
+        ops.image_roi_align_rotated(images, pad_hw, self.pixel_mean, self.pixel_std, rois, (ph * 16, pw * 4),
+                                    self.sampling, out_act=crops, n_rois_dev=nd)
+        self.hybrid_net(crops, fused)
+        local_own = fused.to_nchw()[:, :256] if (teacher and "local_feats" in teacher) else None
+        if teacher and "local_feats" in teacher:
+            t = Act.from_nchw(teacher["local_feats"].to(rois.device))
+            fused.buf[:, :K, 1:-1, 1:-1, :256] = t.buf[:, :, 1:-1, 1:-1, :256]
+        fused2, y, x2, seq, enc_f32 = self.fuse_and_encode(fused, K)
+        fusion_own = y.to_nchw() if (teacher and "fusion_out" in teacher) else None
+        if teacher and "fusion_out" in teacher:
+            y = Act.from_nchw(teacher["fusion_out"].to(rois.device))
+            x2, seq, enc_f32 = self.recognizer_cnn_encoder(y, K)
+        logits, alphas, first_eos = self.decode(seq, K, word_start, n_img, probs, taps)
         if taps is not None:
             taps.update(p2p3=g, fused=fused, crops=crops, fused2=fused2, fusion_out=y, recog_cnn=x2, encoder_out=enc_f32,
                         decoder_logits=logits, decoder_alpha=alphas, first_eos=first_eos)
+            if local_own is not None:
+                taps["local_feats_own"] = local_own
+            if fusion_own is not None:
+                taps["fusion_out_own"] = fusion_own
         return probs

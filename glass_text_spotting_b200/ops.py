@@ -126,9 +126,12 @@ def conv_gemm(a_hi: torch.Tensor, a_lo: Optional[torch.Tensor], rows_a: int, k_p
               out_geom: Optional[Tuple[int, int, int]] = None, ld_out: int = 0,
               out_hi: Optional[torch.Tensor] = None, out_lo: Optional[torch.Tensor] = None,
               residual: Optional[Act] = None, res_shift: int = 0, relu_pre: bool = False, relu_post: bool = False,
-              mode: int = MODE_SPLIT, n_store: int = 0, a_ld: int = 0, a_col0: int = 0, a_inner: int = 0) -> None:
+              mode: int = MODE_SPLIT, n_store: int = 0, a_ld: int = 0, a_col0: int = 0, a_inner: int = 0,
+              m_count: Optional[Tuple[torch.Tensor, int]] = None) -> None:
     """Raw launch of glass_conv_gemm.  m_geom = (imgs, h, w, border) of the M space;
-    out_geom = (hp, wp, border) of the output rows (defaults to ``out``'s geometry)."""
+    out_geom = (hp, wp, border) of the output rows (defaults to ``out``'s geometry).
+    ``m_count`` = (int32 device scalar, rows per count): only rows < count * rows_per_count are computed (the live word
+    count stays on the device; m_geom then describes the capacity)."""
     p = _lib.ConvGemmParams()
     p.a_hi, p.a_lo, p.rows_a, p.a_ld = _ptr(a_hi), _ptr(a_lo), rows_a, a_ld
     p.k_per_tap, p.ntaps = k_per_tap, len(tap_shift)
@@ -155,10 +158,12 @@ def conv_gemm(a_hi: torch.Tensor, a_lo: Optional[torch.Tensor], rows_a: int, k_p
     p.pair_mode = PAIR_MODE if (PAIR_MODE != 2 or w.n_p % 32 == 0) else 0
     p.tap_mode = TAP_MODE
     p.a_col0, p.a_inner = a_col0, a_inner
+    if m_count is not None:
+        p.m_count_dev, p.m_rows_per_count = _ptr(m_count[0]), int(m_count[1])
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(torch.cuda.current_stream())
-        _lib.check(_lib.load().glass_conv_gemm(C.byref(p), _stream()))
+        _launch_gemm(p)
         e1.record(torch.cuda.current_stream())
         m_valid = p.m_imgs * (p.m_h - 2 * p.m_border) * (p.m_w - 2 * p.m_border)
         # algorithmic FLOPs of this launch + the GEMM's shape (tools/layer_profile.py)
@@ -166,23 +171,56 @@ def conv_gemm(a_hi: torch.Tensor, a_lo: Optional[torch.Tensor], rows_a: int, k_p
                         dict(m=p.m_imgs * p.m_h * p.m_w, n=w.n_p, k=k_per_tap * len(tap_shift), taps=len(tap_shift),
                              a_ld=a_ld, res=residual is not None, f32=out_f32 is not None)))
         return
-    _lib.check(_lib.load().glass_conv_gemm(C.byref(p), _stream()))
+    _launch_gemm(p)
+
+
+# Launch plans (glass_plan_create / glass_plan_launch): the model's buffers are persistent workspaces, so every step
+# repeats the same parameter blocks -- the host-side derivation (validation, 4 TMA descriptors, geometry) is done once
+# per distinct block and the steady state pays one cudaLaunchKernelEx per GEMM.  GLASS_PLAN_CACHE=0 disables it.
+_PLANS = {}
+_PLAN_CACHE = __import__("os").environ.get("GLASS_PLAN_CACHE", "1") != "0"
+_PLAN_CACHE_MAX = 4096
+
+
+def _launch_gemm(p) -> None:
+    L = _lib.load()
+    if not _PLAN_CACHE:
+        _lib.check(L.glass_conv_gemm(C.byref(p), _stream()))
+        return
+    key = (torch.cuda.current_device(), bytes(p))
+    plan = _PLANS.get(key)
+    if plan is None:
+        if len(_PLANS) >= _PLAN_CACHE_MAX:
+            clear_plans()
+        h = C.c_void_p()
+        _lib.check(L.glass_plan_create(C.byref(p), C.byref(h)))
+        plan = _PLANS[key] = h.value
+    _lib.check(L.glass_plan_launch(plan, _stream()))
+
+
+def clear_plans() -> None:
+    L = _lib.load()
+    for h in _PLANS.values():
+        L.glass_plan_destroy(h)
+    _PLANS.clear()
 
 
 def conv2d(x: Act, w: PackedWeight, relu: bool = False, residual: Optional[Act] = None, res_shift: int = 0,
            relu_pre: bool = False, out: Optional[Act] = None, f32: Optional[F32Map] = None, want_act: bool = True,
-           mode: int = MODE_SPLIT, gather_buf: Optional[torch.Tensor] = None) -> Optional[Act]:
+           mode: int = MODE_SPLIT, gather_buf: Optional[torch.Tensor] = None,
+           n_dev: Optional[torch.Tensor] = None) -> Optional[Act]:
     """conv (+ folded norm) (+ReLU) (+residual) on a split-fp16 activation.
 
     stride-1 'same' convs run as shifted-row implicit GEMM straight from ``x``; everything else goes
     through one tap-gather pass.  ``relu`` = ReLU after the residual add (d2 bottleneck order),
-    ``relu_pre`` = ReLU before it (CNN_V1_1 order)."""
+    ``relu_pre`` = ReLU before it (CNN_V1_1 order).  ``n_dev``: int32 device scalar = live images / words (x.n is then
+    the capacity the launch is sized for)."""
     if getattr(w, "grouped_p", 0):
         if x.wp % w.grouped_p == 0 and residual is None:
-            return _conv2d_grouped(x, w, relu, residual, relu_pre, out, mode)
+            return _conv2d_grouped(x, w, relu, residual, relu_pre, out, mode, n_dev)
         w = w.fallback
     if getattr(w, "compact_cp", 0):
-        return _conv2d_compact(x, w, relu, residual, res_shift, relu_pre, out, mode)
+        return _conv2d_compact(x, w, relu, residual, res_shift, relu_pre, out, mode, n_dev)
     assert x.cp == w.cin_p, (x.cp, w.cin_p)
     sh, sw = w.stride
     ph, pw = w.pad
@@ -200,17 +238,19 @@ def conv2d(x: Act, w: PackedWeight, relu: bool = False, residual: Optional[Act] 
             and x.border >= ph and x.border >= pw)
     if flat:
         shifts = [(r - ph) * x.wp + (s - pw) for r in range(w.kh) for s in range(w.kw)]
-        conv_gemm(x.hi, x.lo, x.rows, x.cp, shifts, w, (x.n, x.hp, x.wp, x.border), **kwargs)
+        conv_gemm(x.hi, x.lo, x.rows, x.cp, shifts, w, (x.n, x.hp, x.wp, x.border),
+                  m_count=None if n_dev is None else (n_dev, x.hp * x.wp), **kwargs)
     else:
         taps = w.kh * w.kw
         rows = x.n * ho * wo
-        g = gather_taps(x, w.kh, w.kw, sh, sw, ph, pw, ho, wo, out=gather_buf)
+        g = gather_taps(x, w.kh, w.kw, sh, sw, ph, pw, ho, wo, out=gather_buf, n_dev=n_dev)
         # the gathered matrix is already tap-major: one "tap" of width taps*cp
-        conv_gemm(g[0], g[1], rows, taps * x.cp, [0], w, (x.n, ho, wo, 0), **kwargs)
+        conv_gemm(g[0], g[1], rows, taps * x.cp, [0], w, (x.n, ho, wo, 0),
+                  m_count=None if n_dev is None else (n_dev, ho * wo), **kwargs)
     return out
 
 
-def _conv2d_compact(x: Act, w: PackedWeight, relu, residual, res_shift, relu_pre, out, mode) -> Act:
+def _conv2d_compact(x: Act, w: PackedWeight, relu, residual, res_shift, relu_pre, out, mode, n_dev=None) -> Act:
     """stride-1 'same' 1x1 / 3x3 conv on a narrow activation (cp = 8/16/32): a 64-wide k-block spans 64/cp
     consecutive pixels, so the three s-taps of a row are read by one (cp <= 16) or two (cp = 32) TMA boxes."""
     cp = w.compact_cp
@@ -222,11 +262,12 @@ def _conv2d_compact(x: Act, w: PackedWeight, relu, residual, res_shift, relu_pre
         out = Act(x.n, w.cout, x.h, x.w, 1, w.n_p, x.buf.device)
     assert (out.n, out.h, out.w, out.cp) == (x.n, x.h, x.w, w.n_p)
     conv_gemm(x.hi, x.lo, x.rows, 64, shifts, w, (x.n, x.hp, x.wp, x.border), out=out, residual=residual,
-              res_shift=res_shift, relu_pre=relu_pre, relu_post=relu, mode=mode, a_ld=cp)
+              res_shift=res_shift, relu_pre=relu_pre, relu_post=relu, mode=mode, a_ld=cp,
+              m_count=None if n_dev is None else (n_dev, x.hp * x.wp))
     return out
 
 
-def _conv2d_grouped(x: Act, w: PackedWeight, relu, residual, relu_pre, out, mode) -> Act:
+def _conv2d_grouped(x: Act, w: PackedWeight, relu, residual, relu_pre, out, mode, n_dev=None) -> Act:
     """Pixel-grouped implicit GEMM (include/glass_b200.h, a_inner > 0; packing.pack_conv_grouped): P pixels per GEMM
     row, then the border of the output (which the all-valid M space overwrites) is re-zeroed."""
     P, cp = w.grouped_p, w.grouped_cp
@@ -244,26 +285,35 @@ def _conv2d_grouped(x: Act, w: PackedWeight, relu, residual, relu_pre, out, mode
     col0 = left * (P - 1) * cp
     conv_gemm(x.hi, x.lo, rows, kwin, shifts, w, (1, rows, 1, 0), out_hi=out.hi, out_lo=out.lo, out_geom=(rows, 1, 0),
               ld_out=P * out.cp, relu_pre=relu_pre, relu_post=relu, mode=mode, a_ld=P * cp, a_col0=col0,
-              a_inner=col0 + kwin)
-    _lib.check(_lib.load().glass_zero_border(_ptr(out.hi), _ptr(out.lo), out.n, out.h, out.w, out.cp, _stream()))
+              a_inner=col0 + kwin, m_count=None if n_dev is None else (n_dev, x.hp * x.wp // P))
+    _lib.check(_lib.load().glass_zero_border(_ptr(out.hi), _ptr(out.lo), out.n, out.h, out.w, out.cp, _ptr(n_dev),
+                                             _stream()))
     return out
 
 
 def linear(a: torch.Tensor, w: PackedWeight, relu: bool = False, want_split: bool = True, want_f32: bool = False,
-           mode: int = MODE_SPLIT):
+           mode: int = MODE_SPLIT, out: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None,
+           m_count: Optional[Tuple[torch.Tensor, int]] = None):
     """y = a @ W^T (*scale + bias) for a split-fp16 matrix ``a`` [2, rows, k] (k == w.cin_p).
-    Returns (split [2, rows, n_p] or None, fp32 [rows, n_p] or None)."""
+    Returns (split [2, rows, n_p] or None, fp32 [rows, n_p] or None); ``out`` / ``out_f32`` are caller-owned result
+    buffers of those shapes (persistent workspaces: no allocation, stable pointers for the plan cache)."""
     assert a.dim() == 3 and a.shape[0] == 2 and a.shape[2] == w.cin_p and a[0].is_contiguous()
     rows = a.shape[1]
-    o = torch.empty((2, rows, w.n_p), dtype=torch.float16, device=a.device) if want_split else None
-    of = torch.empty((rows, w.n_p), dtype=torch.float32, device=a.device) if want_f32 else None
+    o = of = None
+    if want_split:
+        o = out if out is not None else torch.empty((2, rows, w.n_p), dtype=torch.float16, device=a.device)
+        assert tuple(o.shape) == (2, rows, w.n_p) and o[0].is_contiguous()
+    if want_f32:
+        of = out_f32 if out_f32 is not None else torch.empty((rows, w.n_p), dtype=torch.float32, device=a.device)
+        assert tuple(of.shape) == (rows, w.n_p) and of.is_contiguous()
     conv_gemm(a[0], a[1], rows, w.cin_p, [0], w, (1, rows, 1, 0),
               out_hi=None if o is None else o[0], out_lo=None if o is None else o[1], out_f32=of, ld_f32=w.n_p,
-              out_geom=(rows, 1, 0), ld_out=w.n_p, relu_post=relu, mode=mode)
+              out_geom=(rows, 1, 0), ld_out=w.n_p, relu_post=relu, mode=mode, m_count=m_count)
     return o, of
 
 
-def maxpool2d(x: Act, k: Tuple[int, int], s: Tuple[int, int], p: Tuple[int, int], out: Optional[Act] = None) -> Act:
+def maxpool2d(x: Act, k: Tuple[int, int], s: Tuple[int, int], p: Tuple[int, int], out: Optional[Act] = None,
+              n_dev: Optional[torch.Tensor] = None) -> Act:
     ho = (x.h + 2 * p[0] - k[0]) // s[0] + 1
     wo = (x.w + 2 * p[1] - k[1]) // s[1] + 1
     if out is None:
@@ -271,18 +321,18 @@ def maxpool2d(x: Act, k: Tuple[int, int], s: Tuple[int, int], p: Tuple[int, int]
     assert (out.n, out.h, out.w, out.cp) == (x.n, ho, wo, x.cp)
     _lib.check(_lib.load().glass_maxpool(_ptr(x.hi), _ptr(x.lo), x.n, x.h, x.w, x.cp, x.border, k[0], k[1], s[0],
                                          s[1], p[0], p[1], ho, wo, _ptr(out.hi), _ptr(out.lo), out.border,
-                                         _stream()))
+                                         _ptr(n_dev), _stream()))
     return out
 
 
 def gather_taps(x: Act, kh: int, kw: int, sh: int, sw: int, ph: int, pw: int, ho: int, wo: int,
-                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                out: Optional[torch.Tensor] = None, n_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
     """im2col of a split activation: rows [2, n*ho*wo, kh*kw*cp] (tap-major K)."""
     if out is None:
         out = torch.empty((2, x.n * ho * wo, kh * kw * x.cp), dtype=torch.float16, device=x.buf.device)
     assert tuple(out.shape) == (2, x.n * ho * wo, kh * kw * x.cp) and out[0].is_contiguous()
     _lib.check(_lib.load().glass_gather_taps(_ptr(x.hi), _ptr(x.lo), x.n, x.h, x.w, x.cp, x.border, kh, kw, sh, sw,
-                                             ph, pw, ho, wo, _ptr(out[0]), _ptr(out[1]), _stream()))
+                                             ph, pw, ho, wo, _ptr(out[0]), _ptr(out[1]), _ptr(n_dev), _stream()))
     return out
 
 
@@ -424,7 +474,7 @@ def box_decode(pred: torch.Tensor, proposals: torch.Tensor, counts: Optional[tor
 
 
 # ------------------------------------------------------------------------------------------ recognizer head
-def gc_attention(f: Act, y: Act, n_words: int, w) -> None:
+def gc_attention(f: Act, y: Act, n_words: int, w, n_dev: Optional[torch.Tensor] = None) -> None:
     """MultiAspectGCAttention pooling + channel_add MLP + broadcast add (concat channel order); w: dict of
     fp32 device tensors w_mask[512], b_mask(float), w1t[512,256], b1, ln_g, ln_b, w2t[256,512], b2."""
     assert f.cp == 512 and y.cp == 512 and (f.h, f.w, f.border) == (y.h, y.w, y.border)
@@ -433,42 +483,41 @@ def gc_attention(f: Act, y: Act, n_words: int, w) -> None:
     p.n_words, p.h, p.w, p.border, p.channels = n_words, f.h, f.w, f.border, 512
     p.w_mask, p.b_mask = _ptr(w["w_mask"]), float(w["b_mask"])
     p.w1t, p.b1, p.ln_g, p.ln_b, p.w2t, p.b2 = (_ptr(w[k]) for k in ("w1t", "b1", "ln_g", "ln_b", "w2t", "b2"))
+    p.n_words_dev = _ptr(n_dev)
     _lib.check(_lib.load().glass_gc_attention(C.byref(p), _stream()))
 
 
-def hmean_rows(x: Act, n: int, out: torch.Tensor, out_f32: Optional[torch.Tensor] = None) -> None:
+def hmean_rows(x: Act, n: int, out: torch.Tensor, out_f32: Optional[torch.Tensor] = None,
+               n_dev: Optional[torch.Tensor] = None) -> None:
     """mean over H: x [n,c,h,w] -> rows out [2, n*w, cp]."""
     assert tuple(out.shape) == (2, n * x.w, x.cp)
     _lib.check(_lib.load().glass_hmean_rows(_ptr(x.hi), _ptr(x.lo), n, x.h, x.w, x.cp, x.border, _ptr(out[0]),
-                                            _ptr(out[1]), _ptr(out_f32), _stream()))
+                                            _ptr(out[1]), _ptr(out_f32), _ptr(n_dev), _stream()))
 
 
 def lstm_bidir(gates_in: torch.Tensor, whh_t: torch.Tensor, n_seq: int, T: int, out: torch.Tensor,
-               out_f32: Optional[torch.Tensor] = None) -> None:
+               out_f32: Optional[torch.Tensor] = None, n_dev: Optional[torch.Tensor] = None) -> None:
     assert gates_in.dtype == torch.float32 and tuple(gates_in.shape) == (n_seq * T, 2048) and gates_in.is_contiguous()
     assert tuple(whh_t.shape) == (2, 256, 1024) and whh_t.is_contiguous() and tuple(out.shape) == (2, n_seq * T, 512)
     _lib.check(_lib.load().glass_lstm_bidir(_ptr(gates_in), _ptr(whh_t), n_seq, T, 256, _ptr(out[0]), _ptr(out[1]),
-                                            _ptr(out_f32), _stream()))
+                                            _ptr(out_f32), _ptr(n_dev), _stream()))
 
 
-def aster_decode(x: torch.Tensor, xproj: torch.Tensor, n_words: int, T: int, steps: int, num_classes: int, w,
+def aster_decode(xproj: torch.Tensor, pctx: torch.Tensor, n_words: int, T: int, steps: int, num_classes: int, w,
                  probs: torch.Tensor, first_eos: torch.Tensor, logits: Optional[torch.Tensor] = None,
-                 alphas: Optional[torch.Tensor] = None, emb_gi: Optional[torch.Tensor] = None,
-                 pctx: Optional[torch.Tensor] = None) -> None:
-    """``emb_gi`` [num_classes, 768] + ``pctx`` [n_words*T, 768] select the opt-in kernel with the precomputed GRU input
-    (glass_aster_decode_pre); without them the default kernel streams W_ih on every step."""
-    assert x.dtype == torch.float32 and x.is_contiguous() and xproj.is_contiguous()
+                 alphas: Optional[torch.Tensor] = None, n_dev: Optional[torch.Tensor] = None) -> None:
+    """Greedy attention decoding.  xproj fp32 [n_words*T, 256] = xEmbed(x); pctx fp32 [n_words*T, 768] =
+    x . W_ih[:, 256:]^T; w["emb_gi"] [num_classes, 768] = W_ih[:, :256] . Emb + b_ih (see include/glass_b200.h)."""
+    assert xproj.dtype == torch.float32 and xproj.is_contiguous() and tuple(xproj.shape) == (n_words * T, 256)
+    assert pctx.dtype == torch.float32 and tuple(pctx.shape) == (n_words * T, 768) and pctx.is_contiguous()
+    assert tuple(w["emb_gi"].shape) == (num_classes, 768) and w["emb_gi"].is_contiguous()
     p = _lib.AsterParams()
-    p.x, p.xproj, p.n_words, p.T, p.steps, p.num_classes, p.dim = _ptr(x), _ptr(xproj), n_words, T, steps, num_classes, 256
-    p.ws_t, p.bs, p.we, p.be, p.emb = _ptr(w["ws_t"]), _ptr(w["bs"]), _ptr(w["we"]), float(w["be"]), _ptr(w["emb"])
-    p.wih_t, p.whh_t, p.bih, p.bhh = _ptr(w["wih_t"]), _ptr(w["whh_t"]), _ptr(w["bih"]), _ptr(w["bhh"])
+    p.xproj, p.pctx, p.n_words, p.n_words_dev = _ptr(xproj), _ptr(pctx), n_words, _ptr(n_dev)
+    p.T, p.steps, p.num_classes, p.dim = T, steps, num_classes, 256
+    p.ws_t, p.bs, p.we, p.be, p.emb_gi = _ptr(w["ws_t"]), _ptr(w["bs"]), _ptr(w["we"]), float(w["be"]), _ptr(w["emb_gi"])
+    p.whh_t, p.bhh = _ptr(w["whh_t"]), _ptr(w["bhh"])
     p.wo_t, p.bo, p.temperature = _ptr(w["wo_t"]), _ptr(w["bo"]), float(w["temperature"])
     p.probs, p.logits, p.alphas, p.first_eos = _ptr(probs), _ptr(logits), _ptr(alphas), _ptr(first_eos)
-    if emb_gi is not None and pctx is not None:
-        assert emb_gi.dtype == torch.float32 and tuple(emb_gi.shape) == (num_classes, 768) and emb_gi.is_contiguous()
-        assert pctx.dtype == torch.float32 and tuple(pctx.shape) == (n_words * T, 768) and pctx.is_contiguous()
-        _lib.check(_lib.load().glass_aster_decode_pre(C.byref(p), _ptr(emb_gi), _ptr(pctx), 768, _stream()))
-        return
     _lib.check(_lib.load().glass_aster_decode(C.byref(p), _stream()))
 
 
@@ -490,8 +539,44 @@ def resize_bilinear_u8(img_hwc: torch.Tensor, out_hw: Tuple[int, int], flip_chan
     return out
 
 
+# ---------------------------------------------------------------------------------------------- detector -> recognizer
+def pack_rois(boxes: torch.Tensor, counts: torch.Tensor, rois: torch.Tensor, word_start: torch.Tensor,
+              total: torch.Tensor) -> None:
+    """boxes fp32 [n, m, 5] + counts int32 [n] -> rois fp32 [n*m, 6], word_start int32 [n+1], total int32 [1]
+    (glass_pack_rois: the detections become the recognizer's RoI list without leaving the device)."""
+    n, m, _ = boxes.shape
+    assert boxes.is_contiguous() and counts.dtype == torch.int32 and tuple(rois.shape) == (n * m, 6)
+    assert word_start.dtype == torch.int32 and word_start.numel() == n + 1 and total.dtype == torch.int32
+    _lib.check(_lib.load().glass_pack_rois(_ptr(boxes), _ptr(counts), n, m, _ptr(rois), _ptr(word_start), _ptr(total),
+                                           _stream()))
+
+
+def pack_detections(boxes: torch.Tensor, scores: torch.Tensor, orient: Optional[torch.Tensor], counts: torch.Tensor,
+                    probs: torch.Tensor, word_start: torch.Tensor, rec: torch.Tensor) -> torch.Tensor:
+    """-> rec fp32 [n, m, 10 + steps*classes] (glass_pack_detections), every row written (zeros past the counts)."""
+    n, m, _ = boxes.shape
+    steps, classes = probs.shape[1], probs.shape[2]
+    assert tuple(rec.shape) == (n, m, 10 + steps * classes) and rec.is_contiguous() and probs.is_contiguous()
+    assert boxes.is_contiguous() and scores.is_contiguous() and (orient is None or orient.is_contiguous())
+    _lib.check(_lib.load().glass_pack_detections(_ptr(boxes), _ptr(scores), _ptr(orient), _ptr(counts), _ptr(probs),
+                                                 _ptr(word_start), n, m, steps, classes, _ptr(rec), _stream()))
+    return rec
+
+
+def prepack_weights(w: torch.Tensor, scale: torch.Tensor):
+    """fp32 CUDA matrix [n, k] + epilogue scale [n] -> (fp16 [2, n, k] hi/lo planes, scale with the pre-scales folded in)
+    through glass_prepack_weights."""
+    assert w.is_cuda and w.dtype == torch.float32 and w.dim() == 2 and w.is_contiguous()
+    n, k = w.shape
+    planes = torch.empty((2, n, k), dtype=torch.float16, device=w.device)
+    scale = scale.to(device=w.device, dtype=torch.float32).contiguous().clone()
+    _lib.check(_lib.load().glass_prepack_weights(_ptr(w), n, k, _ptr(planes[0]), _ptr(planes[1]), _ptr(scale), _stream()))
+    return planes, scale
+
+
 # ---------------------------------------------------------------------------------------------- post-processing
-def text_scores(probs: torch.Tensor, stop_index: int = 1, want_steps: bool = False):
+def text_scores(probs: torch.Tensor, stop_index: int = 1, want_steps: bool = False,
+                n_dev: Optional[torch.Tensor] = None):
     """pred_text_prob fp32 [n, steps, classes] -> word score [n] (+ per-step argmax int32 and max prob [n, steps])."""
     assert probs.dim() == 3 and probs.dtype == torch.float32 and probs.is_contiguous()
     n, steps, classes = probs.shape
@@ -500,7 +585,7 @@ def text_scores(probs: torch.Tensor, stop_index: int = 1, want_steps: bool = Fal
     maxp = torch.empty((n, steps), dtype=torch.float32, device=probs.device) if want_steps else None
     if n:
         _lib.check(_lib.load().glass_text_scores(_ptr(probs), n, steps, classes, stop_index, _ptr(score), _ptr(idx),
-                                                 _ptr(maxp), _stream()))
+                                                 _ptr(maxp), _ptr(n_dev), _stream()))
     return (score, idx, maxp) if want_steps else score
 
 

@@ -20,12 +20,24 @@ def split_act(x: torch.Tensor) -> torch.Tensor:
     return split16(x.float() * ACT_SCALE)
 
 
-def _pack_rows(w: torch.Tensor, scale: torch.Tensor):
+def _row_shift(w: torch.Tensor) -> torch.Tensor:
+    """Per-row power-of-two exponent s = floor(log2(512 / amax)) clamped to [-24, 24] (0 for an all-zero row), taken from
+    the float's own exponent (frexp) so that the host rule and glass_prepack_weights agree bit for bit."""
+    amax = w.abs().amax(dim=1)
+    f, e = torch.frexp(amax.clamp_min(1e-37))          # amax = f * 2^e, f in [0.5, 1)
+    s = torch.where(f == 0.5, 10 - e, 9 - e).clamp(-24, 24).to(torch.float32)
+    return torch.where(amax > 0, s, torch.zeros_like(s))
+
+
+def _pack_rows(w: torch.Tensor, scale: torch.Tensor, device="cpu"):
     """Split a weight matrix [n, k] with a per-row power-of-two pre-scale (rows land in [256, 512) so
-    both planes stay in fp16's normal range) and fold 2^-s / ACT_SCALE into the epilogue scale."""
-    amax = w.abs().amax(dim=1).clamp_min(1e-30)
-    s = torch.floor(torch.log2(512.0 / amax)).clamp(-24, 24)
-    s = torch.where(w.abs().amax(dim=1) > 0, s, torch.zeros_like(s))
+    both planes stay in fp16's normal range) and fold 2^-s / ACT_SCALE into the epilogue scale.  On a CUDA device the
+    packing itself runs through the C ABI (glass_prepack_weights); the host path below is its restatement (CPU-side
+    tests, tools) and produces the same bits."""
+    if torch.device(device).type == "cuda":
+        from . import ops
+        return ops.prepack_weights(w.float().contiguous().to(device), scale)
+    s = _row_shift(w)
     return split16(w * torch.exp2(s).unsqueeze(1)), scale * torch.exp2(-s) / ACT_SCALE
 
 
@@ -53,7 +65,7 @@ def pack_conv(weight: torch.Tensor, scale: Optional[torch.Tensor] = None, bias: 
         s[:cout] = scale.detach().float()
     if bias is not None:
         b[:cout] = bias.detach().float()
-    wp, s = _pack_rows(w.reshape(n_p, kh * kw * cin_p), s)
+    wp, s = _pack_rows(w.reshape(n_p, kh * kw * cin_p), s, device)
     return PackedWeight(wp.to(device), s.to(device), b.to(device), cout, cin, kh, kw, tuple(stride), tuple(pad), cin_p)
 
 
@@ -75,7 +87,7 @@ def pack_conv_compact(weight: torch.Tensor, cp_in: int, scale: Optional[torch.Te
         s[:cout] = scale.detach().float()
     if bias is not None:
         b[:cout] = bias.detach().float()
-    wp, s = _pack_rows(w.reshape(n_p, kh * nj * 64), s)
+    wp, s = _pack_rows(w.reshape(n_p, kh * nj * 64), s, device)
     pw = PackedWeight(wp.to(device), s.to(device), b.to(device), cout, cin, kh, kw, (1, 1), ((kh - 1) // 2, (kw - 1) // 2),
                       64)
     pw.compact_cp = cp_in
@@ -107,7 +119,7 @@ def pack_conv_grouped(weight: torch.Tensor, cp_in: int, group: int, scale: Optio
         s[:cout] = scale.detach().float()
     if bias is not None:
         b[:cout] = bias.detach().float()
-    wp, s_all = _pack_rows(w.reshape(n_p, kh * kwin), s.repeat(group))
+    wp, s_all = _pack_rows(w.reshape(n_p, kh * kwin), s.repeat(group), device)
     pw = PackedWeight(wp.to(device), s_all.to(device), b.repeat(group).to(device), cout, cin, kh, kw, (1, 1),
                       ((kh - 1) // 2, (kw - 1) // 2), kwin)
     pw.grouped_p, pw.grouped_cp, pw.grouped_cout_p = group, cp_in, cout_p
@@ -125,7 +137,7 @@ def pack_linear(weight: torch.Tensor, bias: Optional[torch.Tensor] = None, k_p: 
     b = torch.zeros(w.shape[0], dtype=torch.float32)
     if bias is not None:
         b[:out_f] = bias.detach().float()
-    wp, s = _pack_rows(w, s)
+    wp, s = _pack_rows(w, s, device)
     return PackedWeight(wp.to(device), s.to(device), b.to(device), out_f, in_f, 1, 1, (1, 1), (0, 0), k_p)
 
 
@@ -151,5 +163,5 @@ def pack_stem_s2d(weight: torch.Tensor, scale, bias, device="cuda") -> PackedWei
     b = torch.zeros(w.shape[0])
     s[:cout] = scale.detach().float()
     b[:cout] = bias.detach().float()
-    wp, s = _pack_rows(w.reshape(w.shape[0], 256), s)
+    wp, s = _pack_rows(w.reshape(w.shape[0], 256), s, device)
     return PackedWeight(wp.to(device), s.to(device), b.to(device), cout, 3, 7, 7, (2, 2), (3, 3), 64)

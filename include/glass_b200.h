@@ -108,9 +108,23 @@ typedef struct {
   int32_t m_rows_per_count;
 } GlassConvGemmParams;
 int glass_conv_gemm(const GlassConvGemmParams* p, void* stream);
+/* Launch plans (SURVEY.md 8b "cached in an opaque handle the caller owns"): glass_plan_create does everything the host
+ * derives from the parameters -- validation, the four TMA descriptors, tile / pipeline geometry, grid -- once;
+ * glass_plan_launch then costs one cudaLaunchKernelEx.  A plan stays valid as long as the buffers it names do (the
+ * library never owns device memory).  glass_conv_gemm(p, s) == create + launch + destroy. */
+int glass_plan_create(const GlassConvGemmParams* p, void** plan_out);
+int glass_plan_launch(const void* plan, void* stream);
+int glass_plan_destroy(void* plan);
+/* glass_prepack_weights -- weights into the layout glass_conv_gemm consumes, once, into caller-owned buffers:
+ * w fp32 [n, k] (K = tap-major, channel-minor, already zero padded to the k the GEMM will be given) -> hi / lo fp16 [n, k]
+ * with a per-row power-of-two pre-scale (the row's largest magnitude lands in [256, 512), so both planes stay in fp16's
+ * normal range); scale fp32 [n] holds the folded epilogue scale (e.g. the BatchNorm scale) on entry and is multiplied by
+ * 2^-s / 16 (the inverse of the weight and activation pre-scales) on exit. */
+int glass_prepack_weights(const float* w, int n, int k, void* hi, void* lo, float* scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------
- * Layout / glue kernels
+ * Layout / glue kernels.  `n_dev` (where present, optional): device pointer to the LIVE image / word count (<= n, which
+ * then is the capacity the launch is sized for) -- the count of detected words stays on the device, no host sync.
  * ------------------------------------------------------------------------------------------ */
 /* fp32 NCHW [n,c,h,w] -> split-fp16 padded NHWC [n,h+2b,w+2b,cp] (interior only; border/pad channels must be 0) */
 int glass_pack_nchw(const float* src, int n, int c, int h, int w, void* dst_hi, void* dst_lo, int cp, int border,
@@ -135,16 +149,16 @@ int glass_stem_s2d(const float* img, int n, int h, int w, const float* mean, con
  * src split padded NHWC [n,h+2b,w+2b,cp] -> rows [n*ho*wo, kh*kw*cp], tap-major K. */
 int glass_gather_taps(const void* src_hi, const void* src_lo, int n, int h, int w, int cp, int border, int kh,
                       int kw, int sh, int sw, int ph, int pw, int ho, int wo, void* dst_hi, void* dst_lo,
-                      void* stream);
+                      const int32_t* n_dev, void* stream);
 
 /* max_pool2d on split-fp16 padded NHWC (F.max_pool2d: BasicStem, local_feature_extraction.py:163-178). */
 int glass_maxpool(const void* src_hi, const void* src_lo, int n, int h, int w, int cp, int border, int kh, int kw,
                   int sh, int sw, int ph, int pw, int ho, int wo, void* dst_hi, void* dst_lo, int dst_border,
-                  void* stream);
+                  const int32_t* n_dev, void* stream);
 
 /* Re-zero the 1-pixel border of a split-fp16 padded NHWC activation [n, h+2, w+2, cp] (after a pixel-grouped
  * glass_conv_gemm, which writes every pixel of the padded plane). */
-int glass_zero_border(void* hi, void* lo, int n, int h, int w, int cp, void* stream);
+int glass_zero_border(void* hi, void* lo, int n, int h, int w, int cp, const int32_t* n_dev, void* stream);
 
 /* Pre-processing of GlassRunner._image_to_tensor (glass/inference/glass_runner.py:123-148): uint8 HWC image ->
  * fp32 CHW tensor, bilinear resize with align_corners=False semantics of torch.nn.functional.interpolate(size=...),
@@ -258,6 +272,21 @@ int glass_box_decode(const float* pred, int ld, const float* proposals, const in
                      int per_img, const float* host_weights, float* out_boxes, float* out_scores,
                      float* out_orient, void* stream);
 
+/* glass_pack_rois -- the hand-over from the box branch to the recognizer (recognizers_hybrid_head.py:176-181 runs
+ * forward_with_given_boxes on the detected boxes), kept on the device: boxes fp32 [n_img, max_det, 5] + counts int32
+ * [n_img] -> rois fp32 [n_img*max_det, 6] = (image, cx, cy, w, h, angle) of the live detections grouped by image (zero
+ * rows after them), word_start int32 [n_img+1] prefix offsets, total int32 [1] = live words.  The recognizer's kernels
+ * take `total` as their device-side count, so the step has no host round trip. */
+int glass_pack_rois(const float* boxes, const int32_t* counts, int n_img, int max_det, float* rois, int32_t* word_start,
+                    int32_t* total, void* stream);
+/* glass_pack_detections -- the fixed-size per-image record of the single all-gather at the end of the loop
+ * (replaces the pickled comm.gather of glass/evaluation/text_evaluator.py:246-249):
+ * rec fp32 [n_img, max_det, 10 + steps*classes] = (valid, box 5, score, class, orientation 2, text probabilities), zero
+ * rows past each image's count.  probs fp32 [words, steps, classes] in word_start order; orient optional [n_img, max_det, 2]. */
+int glass_pack_detections(const float* boxes, const float* scores, const float* orient, const int32_t* counts,
+                          const float* probs, const int32_t* word_start, int n_img, int max_det, int steps, int classes,
+                          float* rec, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Recognizer-head kernels.
  * ------------------------------------------------------------------------------------------ */
@@ -281,36 +310,41 @@ typedef struct {
   const float* ln_b;   /* [256] */
   const float* w2t;    /* [256][512] */
   const float* b2;     /* [512] */
+  const int32_t* n_words_dev; /* optional live word count on the device (<= n_words, which then is the capacity) */
 } GlassGcAttentionParams;
 int glass_gc_attention(const GlassGcAttentionParams* p, void* stream);
 
 /* mean over H of a split activation [n,h+2b,w+2b,cp] -> rows [n*w, cp] (split fp16 + optional fp32):
  * BiLSTMBlockV2.forward's feats.mean(dim=2) (recognizer_encoder.py:118-120). */
 int glass_hmean_rows(const void* src_hi, const void* src_lo, int n, int h, int w, int cp, int border, void* dst_hi,
-                     void* dst_lo, float* dst_f32, void* stream);
+                     void* dst_lo, float* dst_f32, const int32_t* n_dev, void* stream);
 
 /* nn.LSTM(bidirectional) recurrence (recognizer_encoder.py:141-142).  gates_in fp32 [n_seq*T, 8*hidden] =
  * x W_ih^T + b_ih + b_hh (forward gates | backward gates, order i,f,g,o); whh_t fp32 [2][hidden][4*hidden].
  * Output rows [n_seq*T, 2*hidden] (forward | backward) as split fp16 (+ optional fp32). hidden must be 256. */
 int glass_lstm_bidir(const float* gates_in, const float* whh_t, int n_seq, int T, int hidden, void* out_hi,
-                     void* out_lo, float* out_f32, void* stream);
+                     void* out_lo, float* out_f32, const int32_t* n_dev, void* stream);
 
 /* glass_aster_decode -- AttentionRecognitionHead.sample (prediction_aster.py:63-99; DecoderUnit :291-302,
  * AttentionUnit :247-266): greedy additive-attention GRU decoding, all steps in one persistent kernel.
  * Weights are transposed to [in][out].  probs = softmax outputs (pred_text_prob); logits = pre-softmax tap.
- * first_eos[w] = first step whose argmax is class 0, or `steps`. */
+ * first_eos[w] = first step whose argmax is class 0, or `steps`.
+ * The GRU's input product W_ih . [Emb[y_prev] ; context] + b_ih is taken from two precomputed tensors instead of
+ * streaming W_ih on every step: emb_gi fp32 [num_classes][3*dim] = W_ih[:, :dim] . Emb[y] + b_ih (built at weight-packing
+ * time: y takes num_classes values) and pctx fp32 [n_words, T, 3*dim] = x . W_ih[:, dim:]^T (one glass_conv_gemm per
+ * launch, like xproj), since W . (sum_t alpha_t x_t) = sum_t alpha_t (W . x_t). */
 typedef struct {
-  const float* x;      /* [n_words, T, dim] encoder output */
   const float* xproj;  /* [n_words, T, dim] xEmbed(x) */
-  int32_t n_words, T, steps, num_classes, dim;
+  const float* pctx;   /* [n_words, T, 3*dim] */
+  int32_t n_words;     /* words (capacity of the buffers when n_words_dev is given) */
+  const int32_t* n_words_dev; /* optional live word count on the device (<= n_words) */
+  int32_t T, steps, num_classes, dim;
   const float* ws_t;   /* [dim][dim] */
   const float* bs;
   const float* we;     /* [dim] */
   float be;
-  const float* emb;    /* [num_classes][dim] */
-  const float* wih_t;  /* [2*dim][3*dim], GRU input = [embedding ; context], gates (r,z,n) */
-  const float* whh_t;  /* [dim][3*dim] */
-  const float* bih;
+  const float* emb_gi; /* [num_classes][3*dim] */
+  const float* whh_t;  /* [dim][3*dim], gates (r,z,n) */
   const float* bhh;
   const float* wo_t;   /* [dim][num_classes] */
   const float* bo;
@@ -321,11 +355,6 @@ typedef struct {
   int32_t* first_eos;  /* [n_words] */
 } GlassAsterParams;
 int glass_aster_decode(const GlassAsterParams* p, void* stream);
-/* Opt-in variant of glass_aster_decode (compiles; not yet run on hardware): the GRU's input product is taken from two
- * precomputed tensors instead of streaming W_ih on every step -- emb_gi fp32 [num_classes][3*dim] = W_ih[:, :dim] . Emb[y]
- * + b_ih, and pctx fp32 [n_words, T, 3*dim] = x . W_ih[:, dim:]^T (one GEMM per launch); ld_pctx must be 3*dim.  Same
- * outputs as glass_aster_decode up to the re-association sum_t alpha_t (W x_t) = W (sum_t alpha_t x_t). */
-int glass_aster_decode_pre(const GlassAsterParams* p, const float* emb_gi, const float* pctx, int ld_pctx, void* stream);
 /* The reference's batch-level early break (prediction_aster.py:91-93): zero the rows after the step at which
  * every word of an image has emitted class 0.  word_start: int32 [n_img+1] prefix offsets of each image's words. */
 int glass_aster_finalize(float* probs, const int32_t* first_eos, const int32_t* word_start, int n_img, int steps,
@@ -367,7 +396,7 @@ int glass_postprocess_merge(const GlassPostprocessParams* p, void* stream);
  * step max / argmax over the classes; score = product of the max probabilities up to and including the first
  * stop symbol.  probs fp32 [n_words, steps, classes]; out_idx / out_maxp optional [n_words, steps]. */
 int glass_text_scores(const float* probs, int n_words, int steps, int classes, int stop_index, float* score,
-                      int32_t* out_idx, float* out_maxp, void* stream);
+                      int32_t* out_idx, float* out_maxp, const int32_t* n_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Mask branch (MODEL.ROI_MASK_HEAD.MASK_INFERENCE): the head's convolutions run on glass_conv_gemm

@@ -71,3 +71,23 @@ def oracle_with_calibrated_backbone(seed: int, images: torch.Tensor):
     mean = torch.tensor(o.cfg.pixel_mean).view(1, 3, 1, 1)
     calibrate_bn(o.backbone, lambda: o.backbone(images - mean))
     return o
+
+
+def pack_detections_reference(det, probs: torch.Tensor, counts, starts) -> torch.Tensor:
+    """The record layout of glass_pack_detections written with torch index ops: [n, max_det,
+    1 + 5 + 1 + 1 + 2 + steps*classes] = (valid, box, score, class, orientation, text probs), zero rows past each count.
+    Test-side statement of the layout: the CPU property tests of the unpacking code use it, the GPU test holds the kernel
+    to it."""
+    n, m = det["pred_boxes"].shape[0], det["pred_boxes"].shape[1]
+    tp = probs.shape[1] * probs.shape[2]
+    rec = torch.zeros((n, m, 10 + tp), dtype=torch.float32, device=probs.device)
+    for i, c in enumerate(counts):
+        if c == 0:
+            continue
+        rec[i, :c, 0] = 1.0
+        rec[i, :c, 1:6] = det["pred_boxes"][i, :c]
+        rec[i, :c, 6] = det["scores"][i, :c]
+        if det.get("orientations") is not None:
+            rec[i, :c, 8:10] = det["orientations"][i, :c]
+        rec[i, :c, 10:] = probs[starts[i]: starts[i + 1]].reshape(c, tp)
+    return rec

@@ -35,7 +35,7 @@ def test_header_symbols_all_exported(built_lib):
 
 
 def test_abi_version_and_error_string(built_lib):
-    assert built_lib.glass_abi_version() == 1
+    assert built_lib.glass_abi_version() == 2
     assert isinstance(built_lib.glass_last_error(), bytes)
     assert built_lib.glass_launch_count() == 0
 

@@ -36,8 +36,9 @@ def test_full_inference_matches_oracle(glass_lib):
     assert (d.min(0).values < 5e-2).float().mean().item() >= 0.9
     # detections: same count, boxes / scores close (matched by order)
     assert len(got) == len(want["pred_boxes"]) == K
-    close(got.pred_boxes.tensor, want["pred_boxes"], "pred_boxes", rtol=5e-3, atol=5e-3)
-    close(got.scores, want["scores"], "scores", rtol=5e-3, atol=1e-4)
+    # free-running boxes: rtol 1e-3 with the scale-relative atol (coordinates up to ~600 px; literal misses are reported)
+    close(got.pred_boxes.tensor, want["pred_boxes"], "e2e pred_boxes (free-running)", scaled=True)
+    close(got.scores, want["scores"], "e2e scores (free-running)")
     assert got.pred_text_prob.shape == (K, 26, 97)
     rows = got.pred_text_prob.sum(-1).cpu()
     assert ((rows - 1).abs() < 1e-4).logical_or(rows == 0).all()   # softmax rows, or zero after the early break
@@ -48,4 +49,4 @@ def test_full_inference_matches_oracle(glass_lib):
     ws = torch.tensor([0, len(det_boxes)], dtype=torch.int32).cuda()
     il = model.preprocess_image([{"image": img}])
     probs = model.roi_heads.forward_recognizer(il.tensor, tuple(il.tensor.shape[-2:]), mt["features"], rois, ws, 1)
-    close(probs, t["pred_text_prob"], "pred_text_prob (teacher-forced boxes)", rtol=1e-2, atol=2e-3)
+    close(probs, t["pred_text_prob"], "e2e pred_text_prob (teacher-forced boxes, own pyramid)", atol=1e-5)

@@ -134,8 +134,39 @@ def test_a5_a8_box_branch(gate):
     close(det["pred_boxes"][0, :k2], want["pred_boxes"], "cfg0 pred_boxes [K,5] | own logits")
 
 
+def test_a12_local_cnn_stagewise(gate):
+    """Row a12 (ResNetFeatureExtractor, 31 convs) teacher-forced in six pieces: each piece gets the ORACLE's input."""
+    from glass_text_spotting_b200 import ops
+    import torch.nn.functional as F
+    t, heads = gate["t"], gate["model"].roi_heads
+    net = gate["oracle"].roi_heads.hybrid_net.ConvNet
+    k = min(24, t["local_crops"].shape[0])            # 24 words: the six oracle pieces stay within seconds on the host
+    x0 = t["local_crops"][:k]
+    with torch.no_grad():
+        a = F.relu(net.bn0_2(net.conv0_2(F.relu(net.bn0_1(net.conv0_1(x0))))))
+        s0 = F.max_pool2d(a, 2, 2, 0)
+        s1 = F.max_pool2d(F.relu(net.bn1(net.conv1(net.layer1(s0)))), 2, 2, 0)
+        s2 = F.max_pool2d(F.relu(net.bn2(net.conv2(net.layer2(s1)))), kernel_size=2, stride=(2, 1), padding=(0, 1))
+        s3 = net.layer3[:3](s2)
+        s4 = F.relu(net.bn3(net.conv3(net.layer3[3:](s3))))
+        s5 = F.relu(net.bn4_1(net.conv4_1(net.layer4(s4))))
+    close(s5, t["local_feats"][:k], "oracle pieces == oracle hybrid_net", atol=1e-6)
+    heads._word_cap, heads._n_dev = k, None
+    ins = [x0, s0, s1, s2, s3, s4]
+    outs = [s0, s1, s2, s3, s4, s5]
+    cps = [8, 32, 64, 128, 256, 256]
+    fused = ops.Act(k, 512, 8, 32)
+    for i in range(heads.HYBRID_STAGES):
+        y = heads.hybrid_stage(i, ops.Act.from_nchw(ins[i].cuda(), cp=cps[i]), fused)
+        got = fused.to_nchw()[:, :256] if i == 5 else y.to_nchw()
+        close(got, outs[i], f"cfg0 local CNN piece {i} | oracle input")
+
+
 def test_a9_a16_recognizer(gate):
-    """Rows a9-a16 from the oracle's pyramid and the oracle's K detections: every tap down to the per-character logits."""
+    """Rows a9-a16 from the oracle's pyramid and the oracle's K detections: every tap down to the per-character logits.
+    The fusion network gets the ORACLE's local features and CNN_V1_1 the ORACLE's fusion output (stage-wise teacher
+    forcing); the device's own free-running local features (31 convs deep) are held to the scale-relative bound with the
+    literal misses reported."""
     t, heads, want = gate["t"], gate["model"].roi_heads, gate["want"]
     det = t["det_boxes"]
     k = det.shape[0]
@@ -143,15 +174,14 @@ def test_a9_a16_recognizer(gate):
     ws = torch.tensor([0, k], dtype=torch.int32).cuda()
     taps = {}
     probs = heads.forward_recognizer(gate["img"][None].cuda().contiguous(), (H, W), {k_: _act(t[k_]) for k_ in ("p2", "p3")},
-                                     rois, ws, 1, taps)
+                                     rois, ws, 1, taps, teacher={"local_feats": t["local_feats"], "fusion_out": t["fusion_out"]})
     torch.cuda.synchronize()
     close(taps["p2p3"].to_nchw(), t["p2p3"], "cfg0 p2p3")
     close(taps["crops"].to_nchw(), t["local_crops"], "cfg0 local crops [K,3,128,128]")
-    fused = taps["fused"].to_nchw()
-    close(fused[:, 256:], t["global_feats"], "cfg0 global feats [K,256,8,32]")
-    close(fused[:, :256], t["local_feats"], "cfg0 local feats [K,256,8,32] (31-conv hybrid net)")
-    close(taps["fusion_out"].to_nchw(), t["fusion_out"], "cfg0 fusion_out")
-    close(taps["recog_cnn"].to_nchw(), t["recog_cnn"], "cfg0 recog_cnn")
+    close(taps["fused"].to_nchw()[:, 256:], t["global_feats"], "cfg0 global feats [K,256,8,32]")
+    close(taps["local_feats_own"], t["local_feats"], "cfg0 local feats [K,256,8,32] (free-running, 31 convs)", scaled=True)
+    close(taps["fusion_out_own"], t["fusion_out"], "cfg0 fusion_out | oracle local + global feats")
+    close(taps["recog_cnn"].to_nchw(), t["recog_cnn"], "cfg0 recog_cnn | oracle fusion_out")
     close(taps["encoder_out"].view(-1, 32, 256), t["encoder_out"], "cfg0 encoder_out")
     steps = t["decoder_steps"]
     assert torch.equal(taps["decoder_logits"][:, :steps].argmax(-1).cpu(), t["decoder_logits"][:, :steps].argmax(-1)), \
@@ -160,6 +190,11 @@ def test_a9_a16_recognizer(gate):
     close(taps["decoder_alpha"][:, :steps], t["decoder_alpha"][:, :steps], "cfg0 decoder alpha", atol=1e-5)
     assert torch.equal((probs.cpu().sum(2) > 0).sum(1), (want["pred_text_prob"].sum(2) > 0).sum(1)), "early break differs"
     close(probs, want["pred_text_prob"], "cfg0 pred_text_prob [K,26,97]", atol=1e-5)
+    # and free-running from the device's own local features / fusion output: same text, probabilities within tolerance
+    probs_free = heads.forward_recognizer(gate["img"][None].cuda().contiguous(), (H, W),
+                                          {k_: _act(t[k_]) for k_ in ("p2", "p3")}, rois, ws, 1)
+    assert torch.equal(probs_free.argmax(-1).cpu(), want["pred_text_prob"].argmax(-1))
+    close(probs_free, want["pred_text_prob"], "cfg0 pred_text_prob [K,26,97] (free-running recognizer)", atol=1e-5)
 
 
 def test_end_to_end_set_agreement(gate):
@@ -175,7 +210,7 @@ def test_end_to_end_set_agreement(gate):
     matched = d.min(0).values < 0.5
     assert matched.float().mean().item() >= 0.95, f"only {matched.float().mean().item():.3f} of the detections reproduced"
     m = matched.nonzero().squeeze(1)
-    close(gb[j[m]], wb[m], "cfg0 e2e pred_boxes (matched, free-running)", rtol=1e-3, atol=2e-2)
+    close(gb[j[m]], wb[m], "cfg0 e2e pred_boxes (matched, free-running)", scaled=True)
     close(got.scores.cpu()[j[m]], want["scores"][m], "cfg0 e2e scores (matched, free-running)", atol=1e-4)
     gp, wp = got.pred_text_prob.cpu()[j[m]], want["pred_text_prob"][m]
     same_text = (gp.argmax(-1) == wp.argmax(-1)).all(1).float().mean().item()

@@ -79,9 +79,8 @@ def test_shards_partition_the_dataset(n, world):
 def test_pack_detections_roundtrip(counts, seed):
     """pack_detections (the fixed-size all-gather record) -> parallel.unpack_detections /
     evaluation.instances_from_packed gives back exactly the detections, for any per-image counts incl. zero."""
-    import types
     from glass_text_spotting_b200 import evaluation, parallel
-    from glass_text_spotting_b200.modeling.glass_rcnn import B200GlassRCNN
+    from parity_common import pack_detections_reference
     steps, nc, max_det = 4, 7, 5
     g = torch.Generator().manual_seed(seed)
     n = len(counts)
@@ -91,9 +90,7 @@ def test_pack_detections_roundtrip(counts, seed):
     for c in counts:
         starts.append(starts[-1] + c)
     probs = torch.rand(starts[-1], steps, nc, generator=g)
-    model = B200GlassRCNN.__new__(B200GlassRCNN)
-    model.roi_heads = types.SimpleNamespace(steps=steps, num_classes=nc)
-    rec = model.pack_detections(det, probs, counts, starts)
+    rec = pack_detections_reference(det, probs, counts, starts)   # the layout glass_pack_detections writes on the device
     assert tuple(rec.shape) == (n, max_det, 10 + steps * nc)
     dets = parallel.unpack_detections(rec, steps, nc)
     insts = evaluation.instances_from_packed(rec, [(64, 80)] * n, steps, nc)
