@@ -812,7 +812,7 @@ def measure_backbone(min_seconds=1.2, no_clocks=False, mode=0):
         model(dev[i % 2])
     torch.cuda.synchronize()
     gemm_ms = sum(r[0].elapsed_time(r[1]) for r in ops.PROFILE) / 2
-    gemm_flops = sum(r[2] for r in ops.PROFILE) / 2
+    gemm_flops = sum(ops.profile_flops(r) for r in ops.PROFILE) / 2
     ops.PROFILE = None
     peaks, src = _peaks()
     peak = peaks["bf16_tflops_sustained"]
@@ -991,7 +991,7 @@ def run_b200(args):
             step(dev[i % 2])
     torch.cuda.synchronize()
     gemm_ms = sum(r[0].elapsed_time(r[1]) for r in ops.PROFILE) / nprof
-    gemm_flops = sum(r[2] for r in ops.PROFILE) / nprof
+    gemm_flops = sum(ops.profile_flops(r) for r in ops.PROFILE) / nprof
     n_gemm = len(ops.PROFILE) // nprof
     ops.PROFILE = None
 

@@ -106,6 +106,19 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// Explicit shared-state-space vector accesses.  A pointer derived from the dynamic shared-memory base through integer
+// arithmetic (the 1024-byte alignment of the operand ring) loses its state space: the compiler then emits GENERIC
+// LD.E / ST.E, which go through the L1TEX address path and sit on the long scoreboard (ncu, round 2: those were the
+// hottest stall sites of the GEMM epilogue).  These force LDS / STS.
+__device__ __forceinline__ void sts_f4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

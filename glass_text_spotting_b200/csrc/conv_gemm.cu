@@ -352,7 +352,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     const int c_begin = part * cbase + min(part, crem);
     const int c_end = c_begin + cbase + (part < crem ? 1 : 0);
     const bool has_res = p.res_hi != nullptr;
-    float* stage = stage_base + e * 512;
+    const uint32_t stage = smem_u32(stage_base) + (uint32_t)e * 2048u;   // this warp's 32 rows x 16 fp32 staging block
     const int chunks_per_tile = (kblocks + p.kb_per_chunk - 1) / p.kb_per_chunk;
     uint32_t chunk = 0;  // mirrors the MMA warp's running chunk counter
     for (int unit = worker; unit < num_units; unit += num_workers) {
@@ -450,8 +450,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
               const int phys = jj ^ ((lane >> 1) & 3);
-              *reinterpret_cast<float4*>(stage + lane * 16 + phys * 4) =
-                  make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
+              sts_f4(stage + (uint32_t)(lane * 16 + phys * 4) * 4u, v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
             }
           }
           __syncwarp();
@@ -465,8 +464,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             const long long res_row_r = __shfl_sync(0xffffffffu, (long long)res_row, R);
             if (valid_r && n < p.n_store) {
               const int sw = (R >> 1) & 3;
-              const float4 a = *reinterpret_cast<const float4*>(stage + R * 16 + (((2 * cg) ^ sw) * 4));
-              const float4 b = *reinterpret_cast<const float4*>(stage + R * 16 + (((2 * cg + 1) ^ sw) * 4));
+              const float4 a = lds_f4(stage + (uint32_t)(R * 16 + (((2 * cg) ^ sw) * 4)) * 4u);
+              const float4 b = lds_f4(stage + (uint32_t)(R * 16 + (((2 * cg + 1) ^ sw) * 4)) * 4u);
               float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
               if (has_res) {
                 const uint4 rh = __ldg(reinterpret_cast<const uint4*>(p.res_hi + res_row_r * p.ld_out + n));

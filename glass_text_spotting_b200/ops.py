@@ -166,12 +166,25 @@ def conv_gemm(a_hi: torch.Tensor, a_lo: Optional[torch.Tensor], rows_a: int, k_p
         _launch_gemm(p)
         e1.record(torch.cuda.current_stream())
         m_valid = p.m_imgs * (p.m_h - 2 * p.m_border) * (p.m_w - 2 * p.m_border)
-        # algorithmic FLOPs of this launch + the GEMM's shape (tools/layer_profile.py)
+        # algorithmic FLOPs of this launch + the GEMM's shape (tools/layer_profile.py).  With a device-side M count the
+        # launch is sized for the capacity but computes only the live rows: the FLOPs are scaled by live / capacity when
+        # the profile is read (profile_flops), after the stream has been synchronised.
+        live = None
+        if m_count is not None:
+            live = (m_count[0], float(m_count[1]) / float(p.m_imgs * p.m_h * p.m_w))
         PROFILE.append((e0, e1, 2.0 * m_valid * getattr(w, "grouped_p", 1) * w.cout * w.cin * w.kh * w.kw,
                         dict(m=p.m_imgs * p.m_h * p.m_w, n=w.n_p, k=k_per_tap * len(tap_shift), taps=len(tap_shift),
-                             a_ld=a_ld, res=residual is not None, f32=out_f32 is not None)))
+                             a_ld=a_ld, res=residual is not None, f32=out_f32 is not None), live))
         return
     _launch_gemm(p)
+
+
+def profile_flops(rec) -> float:
+    """Algorithmic FLOPs of one PROFILE record (call after a synchronise): capacity FLOPs x the live fraction of M."""
+    flops, live = rec[2], rec[4]
+    if live is None:
+        return flops
+    return flops * min(1.0, float(live[0].item()) * live[1])
 
 
 # Launch plans (glass_plan_create / glass_plan_launch): the model's buffers are persistent workspaces, so every step

@@ -35,7 +35,7 @@ n = len(prof) // REP
 rows = []
 for i in range(n):
     ms = sum(prof[r * n + i][0].elapsed_time(prof[r * n + i][1]) for r in range(REP)) / REP
-    rows.append((i, prof[i][3], ms, prof[i][2]))
+    rows.append((i, prof[i][3], ms, ops.profile_flops(prof[i])))
 tot = sum(r[2] for r in rows)
 print(f"# {wl}: {n} conv_gemm launches, {tot:.3f} ms, {sum(r[3] for r in rows) / tot / 1e9:.1f} TFLOP/s algorithmic")
 print("idx      M      N      K taps a_ld res f32     ms   alg_TF  iss_TF  share")
