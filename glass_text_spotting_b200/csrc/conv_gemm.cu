@@ -67,16 +67,24 @@ struct GemmKernelParams {
   // live M extent on the device: rows_m = min(rows_m, *m_count_dev * m_rows_per_count) (detections of this step)
   const int32_t* m_count_dev;
   int32_t m_rows_per_count;
+  int32_t tma_res;  // TMA epilogue: the residual tile is TMA-loaded into the staging boxes (same geometry as the output)
 };
 
 // PAIR = true: two CTAs of a cluster (one TPC) cooperate through tcgen05 cta_group::2 -- an M = 256 tile pair
 // shares ONE weight tile, each CTA staging only half of it (N/2 rows), which halves the dominant L2->SMEM
 // traffic of the wide layers.  The leader (even) CTA issues the MMAs for both; each CTA keeps its own 128 rows
 // of the accumulator in its own TMEM and runs its own epilogue.
-template <bool SPLIT, bool PAIR>
+// TMAEPI = true (flat layers: the output plane IS the M space, split-fp16 output, bn a multiple of 64): the epilogue warps
+// only do TMEM -> registers -> folded norm / ReLU / residual -> fp16 hi/lo into two 128-row x 64-column SWIZZLE_128B
+// boxes in shared memory; one thread then issues cp.async.bulk.tensor STORES of the boxes, and the residual tile arrives
+// by a TMA LOAD into the same boxes (added in place).  No per-row address arithmetic, no transposing shuffles, fully
+// coalesced 128-byte rows.  Border rows of the padded plane are written as the zeros they already are.
+template <bool SPLIT, bool PAIR, bool TMAEPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                 const __grid_constant__ CUtensorMap map_o_hi, const __grid_constant__ CUtensorMap map_o_lo,
+                 const __grid_constant__ CUtensorMap map_r_hi, const __grid_constant__ CUtensorMap map_r_lo,
                  const GemmKernelParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages x (A_hi, A_lo?, B_hi, B_lo?)] then barriers
@@ -90,6 +98,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   uint64_t* a_full_bar = bars + 2 * MAX_STAGES + 2 * MAX_ACC_BUFS;                  // [MAX_A_STAGES]
   uint64_t* a_empty_bar = bars + 2 * MAX_STAGES + 2 * MAX_ACC_BUFS + MAX_A_STAGES;  // [MAX_A_STAGES]
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 2 * MAX_ACC_BUFS + 2 * MAX_A_STAGES);
+  uint64_t* res_bar = bars + 2 * MAX_STAGES + 2 * MAX_ACC_BUFS + 2 * MAX_A_STAGES + 1;   // TMA epilogue: residual boxes landed
 
   // Programmatic dependent launch: let the next kernel of the stream start its prologue as soon as SMs free up
   // (it blocks at its own griddepcontrol.wait until this grid has completed and flushed).
@@ -112,6 +121,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       tma_prefetch_desc(&map_a_lo);
       tma_prefetch_desc(&map_b_lo);
     }
+    if (TMAEPI) {
+      tma_prefetch_desc(&map_o_hi);
+      tma_prefetch_desc(&map_o_lo);
+      if (p.tma_res) {
+        tma_prefetch_desc(&map_r_hi);
+        tma_prefetch_desc(&map_r_lo);
+      }
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < MAX_STAGES; ++i) {
@@ -126,6 +143,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       mbar_init(&tmem_full_bar[i], 1);
       mbar_init(&tmem_empty_bar[i], PAIR ? 2 * EPI_WARPS : EPI_WARPS);  // one arrive per epilogue warp (of both CTAs)
     }
+    mbar_init(res_bar, 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -337,7 +355,169 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     }
   } else if (warp >= 4) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
-    // ===================================================== epilogue (8 warps)
+    if constexpr (TMAEPI) {
+      // ===================================================== epilogue through TMA (16 warps)
+      // warp e = warp-4: TMEM lane quadrant q = e & 3 -> tile rows 32q..32q+31 (one per lane); sub = e >> 2 -> the
+      // 16-column chunk `sub` of every 64-column PART of the tile.  The tile is finished part by part through ONE pair
+      // of staging boxes (hi / lo, 16 KB each, the 32 KB the classic epilogue uses as its transpose stage).
+      const int e = warp - 4;
+      const int q = e & 3;
+      const int sub = e >> 2;
+      const int row_in_tile = q * 32 + lane;
+      const int plane = p.m_h * p.m_w;
+      const int parts = p.bn >> 6;
+      const bool has_res = p.tma_res != 0;
+      const bool issuer = threadIdx.x == 128;   // warp 4, lane 0: issues the TMA stores / residual loads
+      const uint32_t box_hi = smem_u32(stage_base), box_lo = box_hi + 16384u;
+      // this thread's two 16-byte chunks of its 128-byte box row (SWIZZLE_128B: chunk index ^ (row & 7))
+      const uint32_t row_off = (uint32_t)row_in_tile * 128u;
+      const uint32_t off0 = row_off + (uint32_t)(((2 * sub) ^ (lane & 7)) << 4);
+      const uint32_t off1 = row_off + (uint32_t)(((2 * sub + 1) ^ (lane & 7)) << 4);
+      const int chunks_per_tile = (kblocks + p.kb_per_chunk - 1) / p.kb_per_chunk;
+      uint32_t chunk = 0, res_phase = 0;
+      auto unit_origin = [&](int unit, int& m0, int& n0) {
+        const int um = unit / p.tiles_n;
+        const int tn = unit - um * p.tiles_n;
+        m0 = (PAIR ? um * 2 + (int)rank : um) * BM;
+        n0 = tn * p.bn;
+      };
+      if (has_res && issuer && worker < num_units) {   // the first tile's first residual part: no dependence on the MMA
+        int m0, n0;
+        unit_origin(worker, m0, n0);
+        mbar_arrive_expect_tx(res_bar, 32768u);
+        tma_load_2d(stage_base, &map_r_hi, res_bar, n0, m0);
+        tma_load_2d(reinterpret_cast<uint8_t*>(stage_base) + 16384, &map_r_lo, res_bar, n0, m0);
+      }
+      for (int unit = worker; unit < num_units; unit += num_workers) {
+        int m0, n0;
+        unit_origin(unit, m0, n0);
+        const int64_t m = (int64_t)m0 + row_in_tile;
+        bool valid = m < rows_m;
+        if (valid) {
+          const int rem = (int)(m % plane);
+          const int yy = rem / p.m_w;
+          const int xx = rem - yy * p.m_w;
+          valid = (yy >= p.m_border) && (xx >= p.m_border) && (yy < p.m_h - p.m_border) && (xx < p.m_w - p.m_border);
+        }
+        // ---- drain every accumulation chunk of this tile from TMEM into fp32 registers (round-to-nearest adds)
+        float accv[MAX_CHUNKS_PER_WARP][16];
+        const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+        for (int g = 0; g < chunks_per_tile; ++g, ++chunk) {
+          const uint32_t buf = chunk % (uint32_t)p.acc_bufs;
+          mbar_wait(&tmem_full_bar[buf], (chunk / (uint32_t)p.acc_bufs) & 1u);
+          tcgen05_fence_after();
+          const uint32_t t_row = tmem_base + buf * (uint32_t)p.acc_cols + lane_sel;
+#pragma unroll
+          for (int pt = 0; pt < MAX_CHUNKS_PER_WARP; ++pt) {
+            if (pt < parts) {
+              uint32_t r[16];
+              tmem_ld_32x32b_x16(t_row + (uint32_t)(pt * 64 + sub * 16), r);
+              tmem_ld_wait();
+              if (g == 0) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) accv[pt][j] = __uint_as_float(r[j]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) accv[pt][j] += __uint_as_float(r[j]);
+              }
+            }
+          }
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (PAIR) mbar_arrive_remote(&tmem_empty_bar[buf], 0u);
+            else mbar_arrive(&tmem_empty_bar[buf]);
+          }
+        }
+        // ---- part by part: math in registers -> staging boxes -> TMA store.  All arithmetic runs in the STORAGE scale
+        // (kActScale * y, a power of two: the same bits as scaling at the end): y16 = D * (16 scale) + 16 bias; the
+        // residual planes already hold 16 r.
+#pragma unroll
+        for (int pt = 0; pt < MAX_CHUNKS_PER_WARP; ++pt) {
+          if (pt < parts) {
+            const int n = n0 + pt * 64 + sub * 16;
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              float4 s4 = make_float4(kActScale, kActScale, kActScale, kActScale);
+              if (p.scale != nullptr) {
+                s4 = __ldg(reinterpret_cast<const float4*>(p.scale + n + j));
+                s4.x *= kActScale; s4.y *= kActScale; s4.z *= kActScale; s4.w *= kActScale;
+              }
+              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.bias != nullptr) {
+                b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+                b4.x *= kActScale; b4.y *= kActScale; b4.z *= kActScale; b4.w *= kActScale;
+              }
+              // one fused multiply-add per element, like the direct-store epilogue (same bits: the factor 16 is exact)
+              v[j] = fmaf(accv[pt][j], s4.x, b4.x); v[j + 1] = fmaf(accv[pt][j + 1], s4.y, b4.y);
+              v[j + 2] = fmaf(accv[pt][j + 2], s4.z, b4.z); v[j + 3] = fmaf(accv[pt][j + 3], s4.w, b4.w);
+            }
+            if (p.relu_pre) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (has_res) {
+              mbar_wait(res_bar, res_phase);   // this part's residual boxes have landed in the staging boxes
+              res_phase ^= 1u;
+              const uint4 rh0 = lds_u4(box_hi + off0), rh1 = lds_u4(box_hi + off1);
+              const uint4 rl0 = lds_u4(box_lo + off0), rl1 = lds_u4(box_lo + off1);
+              const uint32_t aw[8] = {rh0.x, rh0.y, rh0.z, rh0.w, rh1.x, rh1.y, rh1.z, rh1.w};
+              const uint32_t bw[8] = {rl0.x, rl0.y, rl0.z, rl0.w, rl1.x, rl1.y, rl1.z, rl1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float2 rv = unpack16x2_scaled(aw[j], bw[j]);
+                v[2 * j] += rv.x;
+                v[2 * j + 1] += rv.y;
+              }
+            }
+            if (p.relu_post) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            uint32_t hw[8], lw[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)   // border rows / rows past the M extent: zeros
+              split16x2_scaled(valid ? v[2 * j] : 0.f, valid ? v[2 * j + 1] : 0.f, hw[j], lw[j]);
+            if (!has_res) {
+              // boxes free?  (the issuer waits for the previous part's stores to have READ them only now, after this
+              // part's math: the store's shared-memory reads overlap the arithmetic)
+              if (issuer) tma_store_wait_read();
+              named_bar_sync(2, 32 * EPI_WARPS);
+            }
+            sts_u4(box_hi + off0, make_uint4(hw[0], hw[1], hw[2], hw[3]));
+            sts_u4(box_hi + off1, make_uint4(hw[4], hw[5], hw[6], hw[7]));
+            sts_u4(box_lo + off0, make_uint4(lw[0], lw[1], lw[2], lw[3]));
+            sts_u4(box_lo + off1, make_uint4(lw[4], lw[5], lw[6], lw[7]));
+            fence_proxy_async_smem();
+            named_bar_sync(1, 32 * EPI_WARPS);   // the boxes are complete
+            if (issuer) {
+              tma_store_2d(&map_o_hi, box_hi, n0 + pt * 64, m0);
+              tma_store_2d(&map_o_lo, box_lo, n0 + pt * 64, m0);
+              tma_store_commit();
+              if (has_res) {
+                // the next residual part goes into the same boxes as soon as the stores have read them; the other
+                // threads cannot touch the boxes before it has landed (they wait on res_bar), so no second barrier
+                tma_store_wait_read();
+                int rm0 = m0, rn0 = n0 + (pt + 1) * 64;
+                bool more = pt + 1 < parts;
+                if (!more && unit + num_workers < num_units) {   // first part of this CTA's next tile
+                  unit_origin(unit + num_workers, rm0, rn0);
+                  more = true;
+                }
+                if (more) {
+                  mbar_arrive_expect_tx(res_bar, 32768u);
+                  tma_load_2d(stage_base, &map_r_hi, res_bar, rn0, rm0);
+                  tma_load_2d(reinterpret_cast<uint8_t*>(stage_base) + 16384, &map_r_lo, res_bar, rn0, rm0);
+                }
+              }
+            }
+          }
+        }
+      }
+      if (issuer) tma_store_wait_all();
+    } else {
+    // ===================================================== epilogue (16 warps, direct stores)
     // warp e = warp-4: TMEM lane quadrant q = e & 3 (== warp % 4, the tcgen05.ld lane rule), column half
     // e >> 2.  Each thread owns one output row of the tile and walks its half of the 16-column chunks.
     // The residual does not depend on the MMA, so its loads run two chunks ahead (and, for the first
@@ -429,19 +609,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             float v[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = accv[ci][j];
-            if (p.scale != nullptr) {
 #pragma unroll
-              for (int j = 0; j < 16; j += 4) {
-                const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + n + j));
-                v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
-              }
-            }
-            if (p.bias != nullptr) {
-#pragma unroll
-              for (int j = 0; j < 16; j += 4) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
-                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-              }
+            for (int j = 0; j < 16; j += 4) {   // folded norm: ONE fused multiply-add per element (y = D * scale + bias)
+              float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.scale != nullptr) s4 = __ldg(reinterpret_cast<const float4*>(p.scale + n + j));
+              if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+              v[j] = fmaf(v[j], s4.x, b4.x); v[j + 1] = fmaf(v[j + 1], s4.y, b4.y);
+              v[j + 2] = fmaf(v[j + 2], s4.z, b4.z); v[j + 3] = fmaf(v[j + 3], s4.w, b4.w);
             }
             if (p.relu_pre) {
 #pragma unroll
@@ -507,6 +681,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         }
       }
     }
+    }  // classic epilogue
   }
 
   tcgen05_fence_before();
@@ -544,8 +719,9 @@ using namespace glass;
 // once (glass_plan_create) and the per-step cost is one cudaLaunchKernelEx (glass_plan_launch).
 struct GlassGemmPlan {
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  CUtensorMap mo_hi, mo_lo, mr_hi, mr_lo;   // TMA epilogue: output / residual boxes (64 columns x 128 rows)
   GemmKernelParams k;
-  int split, pair, grid, smem_req;
+  int split, pair, tma_epi, grid, smem_req;
 };
 
 static int build_plan(const GlassConvGemmParams* p, GlassGemmPlan* plan) {
@@ -691,6 +867,31 @@ static int build_plan(const GlassConvGemmParams* p, GlassGemmPlan* plan) {
   k.ld_out = p->ld_out; k.ld_f32 = p->ld_f32; k.n_store = n_store;
   k.m_count_dev = p->m_count_dev;
   k.m_rows_per_count = p->m_rows_per_count;
+
+  // TMA epilogue: flat layers only -- the output (and residual) plane IS the M space, so tile rows are contiguous
+  // tensor rows and one 2-D box per 64 columns covers them
+  static const int tma_env = getenv("GLASS_TMA_EPI") ? atoi(getenv("GLASS_TMA_EPI")) : 1;
+  const bool flat_out = split && p->out_hi && p->out_lo && !p->out_f32 && p->out_hp == p->m_h && p->out_wp == p->m_w &&
+                        p->out_border == p->m_border && n_store == p->n && bn % 64 == 0 && p->ld_out >= p->n;
+  const bool flat_res = !p->res_hi || (p->res_shift == 0 && p->res_hp == p->m_h && p->res_wp == p->m_w &&
+                                       p->res_border == p->m_border);
+  bool tma_epi = flat_out && flat_res && tma_env != 0 && p->epi_mode != 1;
+  if (p->epi_mode == 2) GLASS_CHECK(flat_out && flat_res, "epi_mode 2 (TMA epilogue) needs a flat split-fp16 output (and residual)");
+  plan->tma_epi = tma_epi ? 1 : 0;
+  k.tma_res = (tma_epi && p->res_hi) ? 1 : 0;
+  if (tma_epi) {
+    if (make_map_2d(&plan->mo_hi, p->out_hi, p->n, rows_m, BK, BM, p->ld_out)) return -1;
+    if (make_map_2d(&plan->mo_lo, p->out_lo, p->n, rows_m, BK, BM, p->ld_out)) return -1;
+    if (p->res_hi) {
+      if (make_map_2d(&plan->mr_hi, p->res_hi, p->n, rows_m, BK, BM, p->ld_out)) return -1;
+      if (make_map_2d(&plan->mr_lo, p->res_lo, p->n, rows_m, BK, BM, p->ld_out)) return -1;
+    } else {
+      plan->mr_hi = plan->mo_hi;
+      plan->mr_lo = plan->mo_lo;
+    }
+  } else {
+    plan->mo_hi = plan->mo_lo = plan->mr_hi = plan->mr_lo = ma_hi;   // unused by the classic epilogue
+  }
   if (p->m_count_dev) GLASS_CHECK(p->m_rows_per_count > 0, "m_count_dev needs m_rows_per_count > 0");
 
   // always ask for > half of the SM's shared memory: exactly one CTA per SM owns all 512 TMEM columns
@@ -712,11 +913,19 @@ static int build_plan(const GlassConvGemmParams* p, GlassGemmPlan* plan) {
 
 // the largest dynamic shared-memory request any plan makes: set once per kernel variant, not per launch
 static constexpr int kMaxSmem = 227 * 1024;
-template <bool SPLIT, bool PAIR>   // (the four variants share one function-pointer TYPE: key the static on the variant)
+template <bool SPLIT, bool PAIR, bool TMAEPI>   // (the variants share one function-pointer TYPE: key the static on the variant)
 static cudaError_t ensure_smem_attr() {
-  static cudaError_t once =
-      cudaFuncSetAttribute(conv_gemm_kernel<SPLIT, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+  static cudaError_t once = cudaFuncSetAttribute(conv_gemm_kernel<SPLIT, PAIR, TMAEPI>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
   return once;
+}
+
+template <bool SPLIT, bool PAIR, bool TMAEPI>
+static cudaError_t launch_variant(const cudaLaunchConfig_t* cfg, const GlassGemmPlan* plan) {
+  cudaError_t e = ensure_smem_attr<SPLIT, PAIR, TMAEPI>();
+  if (e != cudaSuccess) return e;
+  return cudaLaunchKernelEx(cfg, conv_gemm_kernel<SPLIT, PAIR, TMAEPI>, plan->ma_hi, plan->ma_lo, plan->mb_hi, plan->mb_lo,
+                            plan->mo_hi, plan->mo_lo, plan->mr_hi, plan->mr_lo, plan->k);
 }
 
 static int launch_plan(const GlassGemmPlan* plan, cudaStream_t stream) {
@@ -739,14 +948,15 @@ static int launch_plan(const GlassGemmPlan* plan, cudaStream_t stream) {
   cfg.stream = stream;
   cfg.attrs = attr;
   cfg.numAttrs = nattr;
-  auto launch = [&](auto kern, cudaError_t attr_state) -> cudaError_t {
-    if (attr_state != cudaSuccess) return attr_state;
-    return cudaLaunchKernelEx(&cfg, kern, plan->ma_hi, plan->ma_lo, plan->mb_hi, plan->mb_lo, plan->k);
-  };
-  if (plan->split && plan->pair) GLASS_CUDA(launch(conv_gemm_kernel<true, true>, ensure_smem_attr<true, true>()));
-  else if (plan->split) GLASS_CUDA(launch(conv_gemm_kernel<true, false>, ensure_smem_attr<true, false>()));
-  else if (plan->pair) GLASS_CUDA(launch(conv_gemm_kernel<false, true>, ensure_smem_attr<false, true>()));
-  else GLASS_CUDA(launch(conv_gemm_kernel<false, false>, ensure_smem_attr<false, false>()));
+  const int v = (plan->split ? 4 : 0) | (plan->pair ? 2 : 0) | (plan->tma_epi ? 1 : 0);
+  switch (v) {
+    case 7: GLASS_CUDA((launch_variant<true, true, true>(&cfg, plan))); break;
+    case 6: GLASS_CUDA((launch_variant<true, true, false>(&cfg, plan))); break;
+    case 5: GLASS_CUDA((launch_variant<true, false, true>(&cfg, plan))); break;
+    case 4: GLASS_CUDA((launch_variant<true, false, false>(&cfg, plan))); break;
+    case 2: GLASS_CUDA((launch_variant<false, true, false>(&cfg, plan))); break;
+    default: GLASS_CUDA((launch_variant<false, false, false>(&cfg, plan))); break;   // (the TMA epilogue needs split output)
+  }
   count_launch();
   GLASS_CUDA(cudaGetLastError());
   return 0;

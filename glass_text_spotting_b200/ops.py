@@ -21,6 +21,8 @@ KB_PER_CHUNK = int(__import__("os").environ.get("GLASS_KB_PER_CHUNK", "0"))
 PAIR_MODE = int(__import__("os").environ.get("GLASS_PAIR_MODE", "0"))
 # 0 = auto (3x3 convs stage one activation block per tap row), 1 = every tap loads its own tile
 TAP_MODE = int(__import__("os").environ.get("GLASS_TAP_MODE", "0"))
+# 0 = auto (TMA-store epilogue for flat layers), 1 = direct-store epilogue everywhere, 2 = insist on TMA (tests)
+EPI_MODE = int(__import__("os").environ.get("GLASS_EPI_MODE", "0"))
 
 # bench.py's per-kernel timing: when a list, every conv_gemm launch appends (start event, end event, algorithmic FLOPs)
 PROFILE = None
@@ -157,6 +159,7 @@ def conv_gemm(a_hi: torch.Tensor, a_lo: Optional[torch.Tensor], rows_a: int, k_p
     p.kb_per_chunk = KB_PER_CHUNK or getattr(w, "kb_per_chunk", 0)   # env override > per-weight choice > library default
     p.pair_mode = PAIR_MODE if (PAIR_MODE != 2 or w.n_p % 32 == 0) else 0
     p.tap_mode = TAP_MODE
+    p.epi_mode = EPI_MODE
     p.a_col0, p.a_inner = a_col0, a_inner
     if m_count is not None:
         p.m_count_dev, p.m_rows_per_count = _ptr(m_count[0]), int(m_count[1])

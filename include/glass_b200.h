@@ -106,6 +106,10 @@ typedef struct {
    * earlier kernel of the same stream -- is read by the persistent grid itself, so no host round trip sizes the GEMM. */
   const int32_t* m_count_dev;
   int32_t m_rows_per_count;
+  /* Epilogue: 0 = auto (TMA stores + TMA-loaded residual whenever the layer is "flat": split-fp16 output whose padded
+   * plane is the M space itself, n a multiple of 64 per tile, residual -- if any -- of the same geometry; direct stores
+   * otherwise), 1 = direct stores, 2 = TMA (error if not eligible).  Both epilogues produce the same bits. */
+  int32_t epi_mode;
 } GlassConvGemmParams;
 int glass_conv_gemm(const GlassConvGemmParams* p, void* stream);
 /* Launch plans (SURVEY.md 8b "cached in an opaque handle the caller owns"): glass_plan_create does everything the host

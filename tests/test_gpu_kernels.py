@@ -336,3 +336,33 @@ def test_image_roi_align_matches_oracle(ops):
                                       out_act=act)
     _close(got, ref, "image_pooler/f32")
     _close(act.to_nchw(), ref, "image_pooler/split")
+
+
+@pytest.mark.parametrize("cin,cout,k,res,relu,n_img,hw", [
+    (64, 256, 1, True, True, 8, (56, 72)),      # res2 conv3: HBM-bound, CTA pairs, 4 parts per tile
+    (64, 256, 1, False, False, 8, (56, 72)),    # shortcut: no residual
+    (256, 64, 1, False, True, 4, (40, 56)),     # one part per tile
+    (128, 512, 1, True, True, 2, (24, 40)),     # two N tiles
+    (128, 128, 3, True, True, 3, (16, 33)),     # 3x3 (tap-row mode) + residual, odd plane
+    (64, 64, 3, False, True, 1, (7, 9)),        # tiny: a single partial tile
+])
+def test_tma_epilogue_equals_direct_store_epilogue(ops, monkeypatch, cin, cout, k, res, relu, n_img, hw):
+    """The TMA-store epilogue (staging boxes + cp.async.bulk.tensor stores, TMA-loaded residual) writes the same bits as
+    the direct-store epilogue, never touches pad channels, and leaves the zero border zero."""
+    from glass_text_spotting_b200 import packing
+    g = torch.Generator().manual_seed(cin + cout + k)
+    x = ops.Act.from_nchw(torch.randn(n_img, cin, *hw, generator=g).cuda())
+    w = packing.pack_conv(torch.randn(cout, cin, k, k, generator=g) * 0.05, torch.rand(cout, generator=g) + 0.5,
+                          torch.randn(cout, generator=g), (1, 1), (k // 2, k // 2))
+    r = ops.Act.from_nchw(torch.randn(n_img, cout, *hw, generator=g).cuda()) if res else None
+    outs = []
+    for mode in (1, 2):
+        monkeypatch.setattr(ops, "EPI_MODE", mode)
+        o = ops.Act(n_img, cout, hw[0], hw[1])
+        ops.conv2d(x, w, relu=relu, residual=r, out=o)
+        torch.cuda.synchronize()
+        outs.append(o.buf.clone())
+    assert torch.equal(outs[0], outs[1])
+    b = outs[1]
+    assert b[:, :, 0].abs().max().item() == 0 and b[:, :, -1].abs().max().item() == 0
+    assert b[:, :, :, 0].abs().max().item() == 0 and b[:, :, :, -1].abs().max().item() == 0
