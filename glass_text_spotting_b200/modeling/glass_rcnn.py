@@ -56,13 +56,18 @@ class B200GlassRCNN:
         return ImageList.from_tensors(imgs, self.backbone.size_divisibility, pad_value=self.pixel_mean)
 
     # ------------------------------------------------------------------ dense + decision stages on device
+    _side = None
+
     def detect(self, images: torch.Tensor, img_hw: torch.Tensor, taps: Optional[dict] = None):
         feats = self.backbone(images)
+        return feats, self.detect_from_features(feats, img_hw, taps)
+
+    def detect_from_features(self, feats, img_hw: torch.Tensor, taps: Optional[dict] = None):
         pb, ps, pi, pc = self.proposal_generator.forward_device(feats, img_hw)
         det = self.roi_heads.forward_box(feats, pb, pc, img_hw, taps)
         if taps is not None:
             taps.update(features=feats, proposal_boxes=pb, objectness_logits=ps, proposal_count=pc)
-        return feats, det
+        return det
 
     @torch.no_grad()
     def forward_packed(self, images: torch.Tensor, img_hw: torch.Tensor, taps: Optional[dict] = None):
@@ -72,15 +77,27 @@ class B200GlassRCNN:
         glass_pack_detections.  Returns (rec [n, max_det, 10 + steps*classes] -- the fixed-size per-image record of the
         end-of-loop all-gather, SURVEY.md 8e --, det dict, probs [capacity, steps, classes], word_start int32 [n+1]);
         all device tensors in persistent workspaces, valid until the next call.  CUDA-graph capturable."""
-        feats, det = self.detect(images, img_hw, taps)
         heads = self.roi_heads
+        # P2P3Fusion (two full-GPU 1x1 GEMMs) depends only on the pyramid: forked onto a side stream, it fills the SMs
+        # that the latency-bound middle of the detector (per-level top-k, the two rotated NMS passes, the 400-row FC head)
+        # leaves idle; joined before the recognizer's pooler reads it.  Capturable: the fork / join become graph edges.
+        feats = self.backbone(images)
+        cur = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            gmap = heads.p2p3(feats)
+        det = self.detect_from_features(feats, img_hw, taps)
+        cur.wait_stream(self._side)
         n, m = det["pred_boxes"].shape[0], det["pred_boxes"].shape[1]
         ws = heads.ws
         rois = ws.raw("step.rois", (n * m, 6), torch.float32)
         word_start = ws.raw("step.word_start", (n + 1,), torch.int32)
         total = ws.raw("step.total", (1,), torch.int32)
         ops.pack_rois(det["pred_boxes"], det["count"], rois, word_start, total)
-        probs = heads.forward_recognizer(images, tuple(images.shape[-2:]), feats, rois, word_start, n, taps, n_dev=total)
+        probs = heads.forward_recognizer(images, tuple(images.shape[-2:]), feats, rois, word_start, n, taps, n_dev=total,
+                                         gmap=gmap)
         rec = ws.raw("step.rec", (n, m, 10 + heads.steps * heads.num_classes), torch.float32)
         ops.pack_detections(det["pred_boxes"], det["scores"], det["orientations"] if heads.orientation_on else None,
                             det["count"], probs, word_start, rec)

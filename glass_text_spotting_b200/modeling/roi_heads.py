@@ -410,7 +410,8 @@ class B200GlassROIHeads:
 
     def forward_recognizer(self, images: torch.Tensor, pad_hw, features: Dict[str, Act], rois: torch.Tensor,
                            word_start: torch.Tensor, n_img: int, taps: Optional[dict] = None,
-                           n_dev: Optional[torch.Tensor] = None, teacher: Optional[dict] = None) -> torch.Tensor:
+                           n_dev: Optional[torch.Tensor] = None, teacher: Optional[dict] = None,
+                           gmap: Optional[Act] = None) -> torch.Tensor:
         """rois fp32 [K,6] (batch, cx, cy, w, h, angle) of the detections of all images, grouped by image;
         word_start int32 [n_img+1].  Returns pred_text_prob [K, 26, 97].
         ``n_dev`` (int32 device scalar): the live word count; ``rois`` then has capacity rows (glass_pack_rois) and the
@@ -422,11 +423,11 @@ class B200GlassROIHeads:
         self._word_cap = max(n_img * self.max_det, K)
         self._n_dev = n_dev
         try:
-            return self._forward_recognizer(images, pad_hw, features, rois, word_start, n_img, taps, teacher)
+            return self._forward_recognizer(images, pad_hw, features, rois, word_start, n_img, taps, teacher, gmap)
         finally:
             self._n_dev = None
 
-    def _forward_recognizer(self, images, pad_hw, features, rois, word_start, n_img, taps, teacher):
+    def _forward_recognizer(self, images, pad_hw, features, rois, word_start, n_img, taps, teacher, gmap=None):
         K, nd, cap = rois.shape[0], self._n_dev, self._word_cap
         if nd is None:
             probs = torch.zeros((K, self.steps, self.num_classes), dtype=torch.float32, device=rois.device)
@@ -436,7 +437,7 @@ class B200GlassROIHeads:
         if K == 0:
             return probs
         ph, pw = self.pool_h, self.pool_w
-        g = self.p2p3(features)
+        g = gmap if gmap is not None else self.p2p3(features)   # (the fused step computes it on a side stream)
         fused = self.act("rec.fused", K, 512, ph, pw)
         ops.roi_align_rotated([g], rois, (ph, pw), [1.0 / self.strides[0]], self.recog_sampling, out_f32=False,
                               out_split=(fused.buf, fused.hp, fused.wp, fused.border, 256, fused.cp), n_rois_dev=nd)
