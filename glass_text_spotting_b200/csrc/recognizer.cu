@@ -25,7 +25,15 @@
 
 namespace glass {
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+// Gate non-linearities of the recurrent kernels.  ex2.approx-based exponential (2 ulp) + approximate division: absolute
+// error ~2e-7 on outputs in [-1, 1] -- three orders below the parity tolerance (atol 1e-4) -- at ~8 instructions instead
+// of ~35 for the exact expf / tanhf / division sequences, which dominated the issue slots of the decoder's attention
+// energies (32768 tanh per step and CTA) and of the LSTM cell update.
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanhf_(float x) {
+  const float e = __expf(2.0f * x);              // inf for large x -> 1 - 0; 0 for very negative x -> 1 - 2
+  return 1.0f - __fdividef(2.0f, e + 1.0f);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -400,10 +408,10 @@ __global__ void __cluster_dims__(LC_R, 1, 1) __launch_bounds__(LC_THREADS, 1)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const float ig = sigmoidf_(acc[i][0][2 * e + 0] * kInv), fg = sigmoidf_(acc[i][0][2 * e + 1] * kInv);
-        const float gg = tanhf(acc[i][1][2 * e + 0] * kInv), og = sigmoidf_(acc[i][1][2 * e + 1] * kInv);
+        const float gg = tanhf_(acc[i][1][2 * e + 0] * kInv), og = sigmoidf_(acc[i][1][2 * e + 1] * kInv);
         const float c = fg * cst[i][e] + ig * gg;
         cst[i][e] = c;
-        hn[i][e] = og * tanhf(c);
+        hn[i][e] = og * tanhf_(c);
       }
     if (step + 1 < T) load_gates(step + 1);   // in flight across the barriers
 
@@ -445,6 +453,23 @@ __global__ void __cluster_dims__(LC_R, 1, 1) __launch_bounds__(LC_THREADS, 1)
   }
 }
 
+// d = a * (b.x, b.y) + c on a register pair: Blackwell's packed FFMA2 with a scalar-broadcast first operand --
+// the same fused multiply-add per lane as FFMA, at half the issue slots
+__device__ __forceinline__ float2 ffma2_bcast(float a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n"
+      ".reg .b64 ra, rb, rc, rd;\n"
+      "mov.b64 ra, {%2, %2};\n"
+      "mov.b64 rb, {%3, %4};\n"
+      "mov.b64 rc, {%5, %6};\n"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n"
+      "mov.b64 {%0, %1}, rd;\n"
+      "}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+
 // ------------------------------------------------------------------------------------------ ASTER decoder
 constexpr int DEC_D = 256, DEC_T_MAX = 32, DEC_WPC = 4, DEC_MAX_CLASSES = 128;
 
@@ -477,13 +502,22 @@ struct AsterParams {
 // The context vector itself is never formed (nothing else reads it).  Validated on B200 against the oracle and the
 // reference-run golden vectors (tests/test_gpu_roi_heads.py, tests/test_gpu_fullsize_parity.py).
 __global__ void __launch_bounds__(1024) aster_decode_kernel(const AsterParams p) {
+  // Per step (all 1024 threads busy in every matvec phase; the kernel is bound by streaming ~1.5 MB of weights and
+  // per-word projections from L2 per step and CTA):
+  //   A  sProj = sEmbed(h) (256 columns) and gh = W_hh h + b_hh (768 columns) in ONE pass over h: thread = column
+  //   B  e[w][t] = we . tanh(sProj[w] + xProj[w][t]) + be, a warp per (word, t)
+  //   C  alpha = softmax_t(e)
+  //   D  thread = (word, hidden unit): gi = emb_gi[y] + sum_t alpha_t pctx[t] for its three gates, then the GRU cell in
+  //      registers -- no shared-memory round trip for gi
+  //   E  classifier with an 8-way split of k (8 x 128 threads), partial sums combined in a fixed order
+  //   F  softmax + argmax (first maximal index)
   const float* __restrict__ emb_gi = p.emb_gi;
   const float* __restrict__ pctx = p.pctx;
   __shared__ __align__(16) float h_s[DEC_D][DEC_WPC];        // h[k][w]
   __shared__ float sp_s[DEC_WPC][DEC_D];
-  __shared__ float al_s[DEC_WPC][DEC_T_MAX];
-  __shared__ float gi_s[DEC_WPC][3 * DEC_D];
   __shared__ float gh_s[DEC_WPC][3 * DEC_D];
+  __shared__ float al_s[DEC_WPC][DEC_T_MAX];
+  __shared__ float part_s[8][DEC_WPC][DEC_MAX_CLASSES];
   __shared__ float o_s[DEC_WPC][DEC_MAX_CLASSES];
   __shared__ int y_s[DEC_WPC], eos_s[DEC_WPC];
   const int w0 = blockIdx.x * DEC_WPC;
@@ -497,38 +531,50 @@ __global__ void __launch_bounds__(1024) aster_decode_kernel(const AsterParams p)
     eos_s[tid] = p.steps;
   }
   __syncthreads();
+  // phase A's column of this thread: sEmbed^T [256][256] for tid < 256, W_hh^T [256][768] after it
+  const bool a_sproj = tid < DEC_D;
+  const float* a_w = a_sproj ? p.ws_t + tid : p.whh_t + (tid - DEC_D);
+  const int a_ld = a_sproj ? DEC_D : 3 * DEC_D;
+  const float a_bias = a_sproj ? __ldg(p.bs + tid) : __ldg(p.bhh + (tid - DEC_D));
 
   for (int step = 0; step < p.steps; ++step) {
-    // (1) sProj = sEmbed(h)
-    if (tid < DEC_D) {
+    // (A) everything that is a product with h
+    {
       float acc[DEC_WPC];
-      const float b = __ldg(p.bs + tid);
 #pragma unroll
-      for (int w = 0; w < DEC_WPC; ++w) acc[w] = b;
-#pragma unroll 8
-      for (int k = 0; k < DEC_D; ++k) {
-        const float wv = __ldg(p.ws_t + k * DEC_D + tid);
+      for (int w = 0; w < DEC_WPC; ++w) acc[w] = a_bias;
+      float2 acc01 = make_float2(acc[0], acc[1]), acc23 = make_float2(acc[2], acc[3]);
+#pragma unroll 16
+      for (int k = 0; k < DEC_D; ++k) {   // one weight load + one broadcast LDS.128 + two packed FFMA2 per k
+        const float wv = __ldg(a_w + (int64_t)k * a_ld);
         const float4 hv = *reinterpret_cast<const float4*>(&h_s[k][0]);
-        acc[0] += wv * hv.x; acc[1] += wv * hv.y; acc[2] += wv * hv.z; acc[3] += wv * hv.w;
+        acc01 = ffma2_bcast(wv, make_float2(hv.x, hv.y), acc01);
+        acc23 = ffma2_bcast(wv, make_float2(hv.z, hv.w), acc23);
       }
+      acc[0] = acc01.x; acc[1] = acc01.y; acc[2] = acc23.x; acc[3] = acc23.y;
+      if (a_sproj) {
 #pragma unroll
-      for (int w = 0; w < DEC_WPC; ++w) sp_s[w][tid] = acc[w];
+        for (int w = 0; w < DEC_WPC; ++w) sp_s[w][tid] = acc[w];
+      } else {
+#pragma unroll
+        for (int w = 0; w < DEC_WPC; ++w) gh_s[w][tid - DEC_D] = acc[w];
+      }
     }
     __syncthreads();
-    // (2) e[w][t] = we . tanh(sProj + xProj[t]) + be, one warp per (w, t)
+    // (B) e[w][t] = we . tanh(sProj + xProj[t]) + be, one warp per (w, t)
     for (int pair = warp; pair < DEC_WPC * T; pair += (blockDim.x >> 5)) {
       const int w = pair / T, t = pair - w * T;
       const int word = w0 + w;
       float acc = 0.f;
       if (word < n_words) {
         const float* xp = p.xproj + ((int64_t)word * T + t) * DEC_D;
-        for (int a = lane; a < DEC_D; a += 32) acc += __ldg(p.we + a) * tanhf(sp_s[w][a] + __ldg(xp + a));
+        for (int a = lane; a < DEC_D; a += 32) acc += __ldg(p.we + a) * tanhf_(sp_s[w][a] + __ldg(xp + a));
       }
       acc = warp_sum(acc);
       if (lane == 0) al_s[w][t] = acc + p.be;
     }
     __syncthreads();
-    // (3) alpha = softmax_t(e), one warp per word
+    // (C) alpha = softmax_t(e), one warp per word
     if (warp < DEC_WPC) {
       const float v = lane < T ? al_s[warp][lane] : -CUDART_INF_F;
       const float mx = warp_max(v);
@@ -542,60 +588,57 @@ __global__ void __launch_bounds__(1024) aster_decode_kernel(const AsterParams p)
       }
     }
     __syncthreads();
-    // (4+5) GRU pre-activations: gi = emb_gi[y] + sum_t alpha_t pctx[t] (768), gh = W_hh h + b_hh (768 x 256)
-    if (tid < 3 * DEC_D) {
-      float a[DEC_WPC], b[DEC_WPC];
-      const float bh = __ldg(p.bhh + tid);
-#pragma unroll
-      for (int w = 0; w < DEC_WPC; ++w) {
-        a[w] = __ldg(emb_gi + (int64_t)y_s[w] * (3 * DEC_D) + tid);
-        b[w] = bh;
-      }
-#pragma unroll
-      for (int w = 0; w < DEC_WPC; ++w) {
-        const int word = w0 + w;
-        if (word < n_words) {
-          const float* pw = pctx + (int64_t)word * T * (3 * DEC_D) + tid;
+    // (D) GRU: gi = emb_gi[y] + sum_t alpha_t pctx[t] (three gates of one unit), cell update in registers
+    {
+      const int w = tid >> 8, k = tid & 255;   // 4 words x 256 units
+      const int word = w0 + w;
+      const float* eg = emb_gi + (int64_t)y_s[w] * (3 * DEC_D) + k;
+      float gr = __ldg(eg), gz = __ldg(eg + DEC_D), gn = __ldg(eg + 2 * DEC_D);
+      if (word < n_words) {
+        const float* pw = pctx + (int64_t)word * T * (3 * DEC_D) + k;
 #pragma unroll 8
-          for (int t = 0; t < T; ++t) a[w] += al_s[w][t] * __ldg(pw + (int64_t)t * (3 * DEC_D));
+        for (int t = 0; t < T; ++t) {
+          const float a = al_s[w][t];
+          const float* pt = pw + (int64_t)t * (3 * DEC_D);
+          gr += a * __ldg(pt);
+          gz += a * __ldg(pt + DEC_D);
+          gn += a * __ldg(pt + 2 * DEC_D);
         }
       }
-#pragma unroll 8
-      for (int k = 0; k < DEC_D; ++k) {
-        const float wv = __ldg(p.whh_t + (int64_t)k * (3 * DEC_D) + tid);
-        const float4 hv = *reinterpret_cast<const float4*>(&h_s[k][0]);
-        b[0] += wv * hv.x; b[1] += wv * hv.y; b[2] += wv * hv.z; b[3] += wv * hv.w;
-      }
-#pragma unroll
-      for (int w = 0; w < DEC_WPC; ++w) { gi_s[w][tid] = a[w]; gh_s[w][tid] = b[w]; }
+      const float r = sigmoidf_(gr + gh_s[w][k]);
+      const float z = sigmoidf_(gz + gh_s[w][DEC_D + k]);
+      const float n = tanhf_(gn + r * gh_s[w][2 * DEC_D + k]);
+      h_s[k][w] = (1.0f - z) * n + z * h_s[k][w];   // (only this thread touches h[k][w] in this phase)
     }
     __syncthreads();
-    // (6) GRU cell
+    // (E) classifier, k split 8 ways: slice ks covers k in [32 ks, 32 ks + 32)
     {
-      const int w = tid >> 8, k = tid & 255;
-      const float r = sigmoidf_(gi_s[w][k] + gh_s[w][k]);
-      const float z = sigmoidf_(gi_s[w][DEC_D + k] + gh_s[w][DEC_D + k]);
-      const float n = tanhf(gi_s[w][2 * DEC_D + k] + r * gh_s[w][2 * DEC_D + k]);
-      h_s[k][w] = (1.0f - z) * n + z * h_s[k][w];
-    }
-    __syncthreads();
-    // (7) classifier
-    if (tid < NC) {
-      float acc[DEC_WPC];
-      const float b = __ldg(p.bo + tid);
-#pragma unroll
-      for (int w = 0; w < DEC_WPC; ++w) acc[w] = b;
+      const int out = tid & 127, ks = tid >> 7;
+      if (out < NC) {
+        float acc[DEC_WPC] = {0.f, 0.f, 0.f, 0.f};
+        const float* wo = p.wo_t + (int64_t)(ks * 32) * NC + out;
 #pragma unroll 8
-      for (int k = 0; k < DEC_D; ++k) {
-        const float wv = __ldg(p.wo_t + (int64_t)k * NC + tid);
-        const float4 hv = *reinterpret_cast<const float4*>(&h_s[k][0]);
-        acc[0] += wv * hv.x; acc[1] += wv * hv.y; acc[2] += wv * hv.z; acc[3] += wv * hv.w;
-      }
+        for (int k = 0; k < 32; ++k) {
+          const float wv = __ldg(wo + (int64_t)k * NC);
+          const float4 hv = *reinterpret_cast<const float4*>(&h_s[ks * 32 + k][0]);
+          acc[0] += wv * hv.x; acc[1] += wv * hv.y; acc[2] += wv * hv.z; acc[3] += wv * hv.w;
+        }
 #pragma unroll
-      for (int w = 0; w < DEC_WPC; ++w) o_s[w][tid] = acc[w] * p.temperature;
+        for (int w = 0; w < DEC_WPC; ++w) part_s[ks][w][out] = acc[w];
+      }
     }
     __syncthreads();
-    // (8) softmax + argmax (first maximal index), one warp per word
+    if (tid < DEC_WPC * 128) {
+      const int w = tid >> 7, out = tid & 127;
+      if (out < NC) {
+        float acc = __ldg(p.bo + out);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) acc += part_s[ks][w][out];
+        o_s[w][out] = acc * p.temperature;
+      }
+    }
+    __syncthreads();
+    // (F) softmax + argmax (first maximal index), one warp per word
     if (warp < DEC_WPC) {
       const int word = w0 + warp;
       float mx = -CUDART_INF_F;
