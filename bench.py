@@ -469,8 +469,10 @@ def run_postprocess(args):
 
 def run_totaltext(args):
     """BASELINE.json configs[4]: the evaluation loop of tools/eval_glass.py / GlassRunner on synthetic images, image-sharded
-    over the ranks, ending in ONE all-gather of fixed-size per-image records.  Reports end-to-end
-    images/s and the all-gather time separately (CUDA events around it)."""
+    over the ranks: uint8 images -> device resize to 1200 (glass_finetune_totaltext.yaml MIN_SIZE_TEST) -> pad 1216 ->
+    full GLASS inference (one CUDA graph, no host sync) -> word scores -> device post-processor -> 24 KB/image records kept
+    in a device-side loop buffer -> ONE all-gather at the end of the loop (the reference's evaluator gathers
+    once, glass/evaluation/text_evaluator.py:246-249).  Reports end-to-end images/s and the all-gather time (CUDA events)."""
     import torch
     import torch.distributed as dist
     from glass_text_spotting_b200 import lib, ops, weights
@@ -494,6 +496,8 @@ def run_totaltext(args):
     model = B200GlassRCNN(weights.random_state_dict(0))
     post = B200PostProcessor()
     m = model.roi_heads.max_det
+    steps_t, nc = model.roi_heads.steps, model.roi_heads.num_classes
+    steps, warm = args.steps, max(args.warmup, 3)
     g = torch.Generator().manual_seed(2000 + rank)
     host = [torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8).pin_memory() for _ in range(2)]
     dev = [h.cuda() for h in host]
@@ -501,42 +505,37 @@ def run_totaltext(args):
     padded = torch.empty((B, 3, ph, pw), dtype=torch.float32, device="cuda")
     padded[:] = torch.tensor(PIXEL_MEAN, device="cuda").view(1, 3, 1, 1)   # mean padding normalises to exactly 0
     img_hw = torch.tensor([[nh, nw]] * B, dtype=torch.float32, device="cuda")
-    ts_pad = torch.zeros((B, m), dtype=torch.float32, device="cuda")
-    steps_t = model.roi_heads.steps
+    slot = torch.arange(m, device="cuda", dtype=torch.int64).view(1, m)
     rec = torch.zeros((B, m, 8 + 2 * steps_t), dtype=torch.float32, device="cuda")
-    gathered = torch.empty((world * B,) + tuple(rec.shape[1:]), dtype=rec.dtype, device="cuda") if world > 1 else None
-    ag_events, survivors, words = [], [], []
+    use_graph = not args.no_graph
 
     def step(images_u8):
+        """One loop iteration, no host synchronisation anywhere: -> rec [B, m, 8 + 2*steps] = (box 5, score, original
+        index, valid) + per-step argmax and its probability of the words that survive the post-processor."""
         for i in range(B):
             padded[i, :, :nh, :nw] = ops.resize_bilinear_u8(images_u8[i], (nh, nw), flip_channels=False)
-        det, probs, counts, starts = model.forward_device(padded, img_hw)
-        ts, tidx, tmax = ops.text_scores(probs, 1, want_steps=True)
-        ts_pad.zero_()
-        for i, c in enumerate(counts):
-            ts_pad[i, :c] = ts[starts[i]: starts[i + 1]]
+        if use_graph:
+            model.graph_step(padded, img_hw)
+            gs = model.last_graph
+            det, probs, word_start = gs["det"], gs["probs"], gs["word_start"]
+        else:
+            _, det, probs, word_start = model.forward_packed(padded, img_hw)
+        total = word_start[B:B + 1]
+        ts, tidx, tmax = ops.text_scores(probs, 1, want_steps=True, n_dev=total)
+        # word w of image i sits at row word_start[i] + w of the compacted word list
+        widx = (word_start[:B].long().view(B, 1) + slot).clamp_(max=probs.shape[0] - 1)
+        live = slot < det["count"].long().view(B, 1)
+        ts_pad = torch.where(live, ts[widx], torch.zeros((), device="cuda"))
         boxes = det["pred_boxes"].clone()
         boxes[:, :, :4] *= 1.0 / scale                       # back to the original image (glass_runner.py:100-101)
-        r = post.batch(boxes.contiguous(), det["scores"].contiguous(), det["count"], ts_pad)
-        # per-image record: (box 5, score, original index, valid) + per-step argmax and its probability
-        rec.zero_()
+        r = post.batch(boxes.contiguous(), det["scores"].contiguous(), det["count"], ts_pad.contiguous())
+        kept = r["index"] >= 0
+        sel = word_start[:B].long().view(B, 1) + r["index"].clamp(min=0).long()
         rec[:, :, 0:5], rec[:, :, 5], rec[:, :, 6] = r["boxes"], r["scores"], r["index"].float()
-        rec[:, :, 7] = (r["index"] >= 0).float()
-        for i, c in enumerate(counts):
-            if c:
-                sel = r["index"][i].clamp(min=0).long() + starts[i]
-                rec[i, :, 8:8 + steps_t] = tidx[sel].float()
-                rec[i, :, 8 + steps_t:] = tmax[sel]
-        survivors.append(r["count"])
-        words.append(sum(counts))
-        if world > 1:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            dist.all_gather_into_tensor(gathered, rec)
-            e1.record(stream)
-            ag_events.append((e0, e1))
-            return gathered
-        return rec
+        rec[:, :, 7] = kept.float()
+        rec[:, :, 8:8 + steps_t] = torch.where(kept.unsqueeze(-1), tidx[sel].float(), torch.zeros((), device="cuda"))
+        rec[:, :, 8 + steps_t:] = torch.where(kept.unsqueeze(-1), tmax[sel], torch.zeros((), device="cuda"))
+        return rec, r["count"], total
 
     def barrier():
         if world > 1:
@@ -546,65 +545,84 @@ def run_totaltext(args):
     sampler = ClockSampler(local_rank)
     if rank == 0 and not args.no_clocks:
         sampler.start()
-    warm = max(args.warmup, 3)
     for i in range(warm):
         step(dev[i % 2])
+    torch.cuda.synchronize()
+    loop_buf = torch.empty((steps,) + tuple(rec.shape), dtype=rec.dtype, device="cuda")
+    stats = torch.zeros((steps, 2), dtype=torch.float32, device="cuda")     # (survivors, words) per step
+    gathered = torch.empty((world,) + tuple(loop_buf.shape), dtype=rec.dtype, device="cuda") if world > 1 else None
+    if gathered is not None:
+        dist.all_gather_into_tensor(gathered.view(world, -1), loop_buf.view(-1))   # NCCL warm-up
+    ag = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     barrier()
-    ag_events.clear(); survivors.clear(); words.clear()
+
+    def loop(src, e2e):
+        for i in range(steps):
+            if e2e:
+                dbuf[i % 2].copy_(host[i % 2], non_blocking=True)
+            r, cnt, total = step(dbuf[i % 2] if e2e else src[i % 2])
+            loop_buf[i].copy_(r, non_blocking=True)
+            stats[i, 0] = cnt.float().mean()
+            stats[i, 1] = total.float()[0]
+        if gathered is not None:
+            ag[2 if e2e else 0].record(stream)
+            dist.all_gather_into_tensor(gathered.view(world, -1), loop_buf.view(-1))
+            ag[3 if e2e else 1].record(stream)
+
     launches0 = L.glass_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
-    for i in range(args.steps):
-        step(dev[i % 2])
+    loop(dev, False)
     e1.record(stream)
     barrier()
     t_dev = e0.elapsed_time(e1) / 1e3
     launches = L.glass_launch_count() - launches0
+    if use_graph:
+        launches += model.last_graph["launches"] * steps
     clocks = sampler.stop() if rank == 0 else None
-    ag_ms = sum(a.elapsed_time(b) for a, b in ag_events) / max(len(ag_events), 1) if ag_events else 0.0
-    kept = torch.stack(survivors).float().mean().item() if survivors else 0.0
-    words_per_step = sum(words) / max(len(words), 1)
-    # e2e: pinned host uint8 batch -> H2D -> loop body -> D2H of the (gathered) records
-    res_host = None
+    kept_mean, words_per_step = stats.mean(0).tolist()
+    # e2e: pinned host uint8 batch -> H2D -> loop body -> (end of loop) all-gather -> D2H of the records on rank 0
+    out_host = torch.empty(tuple((gathered if gathered is not None else loop_buf).shape), dtype=rec.dtype).pin_memory()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     f0.record(stream)
-    for i in range(args.steps):
-        dbuf[i % 2].copy_(host[i % 2], non_blocking=True)
-        res = step(dbuf[i % 2])
-        if res_host is None:
-            res_host = torch.empty(res.shape, dtype=res.dtype).pin_memory()
-        res_host.copy_(res, non_blocking=True)
+    loop(None, True)
+    if rank == 0:
+        out_host.copy_(gathered if gathered is not None else loop_buf, non_blocking=True)
     f1.record(stream)
     barrier()
     t_e2e = f0.elapsed_time(f1) / 1e3
-    times = torch.tensor([t_dev, t_e2e, ag_ms], dtype=torch.float64, device="cuda")
+    ag_ms = ag[0].elapsed_time(ag[1]) if gathered is not None else 0.0
+    ag_e2e_ms = ag[2].elapsed_time(ag[3]) if gathered is not None else 0.0
+    times = torch.tensor([t_dev, t_e2e, ag_ms, ag_e2e_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    t_dev, t_e2e, ag_ms = times.tolist()
+    t_dev, t_e2e, ag_ms, ag_e2e_ms = times.tolist()
     if rank == 0:
+        cfg = _config("totaltext_loop", world)
+        cfg.update(model_input=[ph, pw], scale_ratio=scale, config_file="configs/glass_finetune_totaltext.yaml geometry")
         print(json.dumps({
-            "metric": "images/sec @1024x1024 (TotalText-shape eval loop)", "value": world * B * args.steps / t_dev,
-            "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
-            "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": "images/sec @1024x1024 (TotalText-shape eval loop)", "value": world * B * steps / t_dev,
+            "unit": "images/s", "n_gpus": world, "steps": steps, "warmup": warm,
+            "ms_per_step": 1e3 * t_dev / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "fp16x3 split (22-bit operands, 3 tcgen05 MMAs per product, chunked fp32 RN accumulation)",
-            "data": "synthetic",
-            "config": {"workload": wl["desc"], "global_batch": world * B, "parallelism": f"image-sharded x{world}",
-                       "model_input": [ph, pw], "scale_ratio": scale,
-                       "l2": "inputs rotated between 2 batches; per-step working set >> 126 MB L2",
-                       "weights": "random init (seeded), BatchNorm folded",
-                       "words_recognized_per_step": words_per_step,
-                       "words_after_postprocess_per_image": kept,
-                       "note": "random weights give word scores far below TEXT_THRESHOLD 0.25, so the (faithful) "
-                               "post-processor drops nearly everything; its merge loop is exercised by the "
-                               "postprocess_bs4 workload",
-                       "allgather_ms_per_step": ag_ms, "allgather_bytes_per_rank": rec.numel() * 4,
-                       "collective": "one NCCL all-gather of 24 KB/image records per step" if world > 1 else "none (N=1)"},
-            "e2e": {"value": world * B * args.steps / t_e2e, "unit": "images/s", "h2d_bytes_per_step": B * H * W * 3,
-                    "d2h_bytes_per_step": res_host.numel() * 4,
-                    "note": "pinned host uint8 HWC batch -> H2D -> resize/pad -> hot path -> post-processor -> "
-                            "(all-gather) -> D2H of the records"},
+            "data": "synthetic", "config": cfg,
+            "run": {"words_recognized_per_step": words_per_step, "words_after_postprocess_per_image": kept_mean,
+                    "note": "random weights give word scores far below TEXT_THRESHOLD 0.25, so the (faithful) "
+                            "post-processor drops nearly everything; its merge loop is exercised by the "
+                            "postprocess_bs4 workload",
+                    "step": "resize x4 -> one CUDA graph replay -> text scores -> device post-processor -> record; no "
+                            "host synchronisation inside the loop" if use_graph else "eager launches",
+                    "collective": "ONE NCCL all-gather of the loop's 24 KB/image records at the end of the loop, inside the "
+                                  "timed region" if world > 1 else "none (N=1)",
+                    "allgather_ms_per_loop": ag_ms, "allgather_ms_per_loop_e2e": ag_e2e_ms,
+                    "allgather_ms_per_step": ag_ms / steps,
+                    "allgather_bytes_per_rank": loop_buf.numel() * 4 if world > 1 else 0},
+            "e2e": {"value": world * B * steps / t_e2e, "unit": "images/s", "h2d_bytes_per_step": B * H * W * 3,
+                    "d2h_bytes_per_step": out_host.numel() * 4 / steps,
+                    "note": "pinned host uint8 HWC batch -> H2D -> resize/pad -> hot path -> post-processor -> records; the "
+                            "loop ends with the single all-gather and rank 0's D2H of all records, inside the timed region"},
             "gpu_launches": launches, "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": None, "peak": None, "unit": "TFLOP/s", "frac": None,
                          "traffic": None, "kernel": "conv_gemm_kernel (see the full_bs4 workload for its roofline line)"}}))

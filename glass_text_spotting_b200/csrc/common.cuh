@@ -217,6 +217,13 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, ui
       : "memory");
 }
 
+// pull a tensor box into L2 ahead of the TMA load that will want it
+__device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+
 // TMA store (shared -> global, bulk async-group completion) and its fences
 __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(

@@ -67,6 +67,7 @@ struct GemmKernelParams {
   // live M extent on the device: rows_m = min(rows_m, *m_count_dev * m_rows_per_count) (detections of this step)
   const int32_t* m_count_dev;
   int32_t m_rows_per_count;
+  int32_t* sat_count;  // debug: counts outputs beyond the split-fp16 storage range (|16 y| > 60000), or nullptr
   int32_t tma_res;  // TMA epilogue: the residual tile is TMA-loaded into the staging boxes (same geometry as the output)
 };
 
@@ -475,6 +476,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
             }
+            if (p.sat_count != nullptr && valid) {   // debug only (GLASS_DEBUG_SAT): silent saturation made visible
+              int over = 0;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) over += fabsf(v[j]) > 60000.f;
+              if (over) atomicAdd(p.sat_count, over);
+            }
             uint32_t hw[8], lw[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j)   // border rows / rows past the M extent: zeros
@@ -662,6 +669,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                 o[1] = make_float4(v[4], v[5], v[6], v[7]);
               }
               if (p.out_hi != nullptr) {
+                if (p.sat_count != nullptr) {   // debug only (GLASS_DEBUG_SAT)
+                  int over = 0;
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) over += fabsf(v[j]) * kActScale > 60000.f;
+                  if (over) atomicAdd(p.sat_count, over);
+                }
                 uint32_t hw[4], lw[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -867,6 +880,7 @@ static int build_plan(const GlassConvGemmParams* p, GlassGemmPlan* plan) {
   k.ld_out = p->ld_out; k.ld_f32 = p->ld_f32; k.n_store = n_store;
   k.m_count_dev = p->m_count_dev;
   k.m_rows_per_count = p->m_rows_per_count;
+  k.sat_count = p->sat_count;
 
   // TMA epilogue: flat layers only -- the output (and residual) plane IS the M space, so tile rows are contiguous
   // tensor rows and one 2-D box per 64 columns covers them

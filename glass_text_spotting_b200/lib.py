@@ -34,7 +34,7 @@ class ConvGemmParams(C.Structure):
         ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("out_f32", C.c_void_p),
         ("out_hp", C.c_int32), ("out_wp", C.c_int32), ("out_border", C.c_int32),
         ("ld_out", C.c_int32), ("ld_f32", C.c_int32), ("n_store", C.c_int32), ("kb_per_chunk", C.c_int32), ("pair_mode", C.c_int32), ("tap_mode", C.c_int32),
-        ("a_col0", C.c_int32), ("a_inner", C.c_int32), ("m_count_dev", C.c_void_p), ("m_rows_per_count", C.c_int32), ("epi_mode", C.c_int32),
+        ("a_col0", C.c_int32), ("a_inner", C.c_int32), ("m_count_dev", C.c_void_p), ("m_rows_per_count", C.c_int32), ("epi_mode", C.c_int32), ("sat_count", C.c_void_p),
     ]
 
 

@@ -21,6 +21,12 @@ from .roi_heads import B200GlassROIHeads
 from .rpn import B200RotatedRPN
 
 
+# where P2P3Fusion is forked onto a side stream: 0 = not at all (default: a same-box A/B on B200 showed no gain --
+# 167.5 / 167.5 / 167.7 images/s -- the persistent GEMMs do not slip in beside the latency-bound detector kernels),
+# 1 = after the backbone, 2 = after the RPN head's convs
+_FORK = int(__import__("os").environ.get("GLASS_FORK", "0"))
+
+
 class B200GlassRCNN:
     """``filter_small_boxes`` / ``inflate_ratio`` are GlassRCNN's ``_postprocess`` options
     (glass_rcnn.py:43-50: cfg.POST_PROCESSING.MIN_BOX_DIMENSION / INFLATE_RATIO; the three fine-tune configs set
@@ -82,14 +88,27 @@ class B200GlassRCNN:
         # that the latency-bound middle of the detector (per-level top-k, the two rotated NMS passes, the 400-row FC head)
         # leaves idle; joined before the recognizer's pooler reads it.  Capturable: the fork / join become graph edges.
         feats = self.backbone(images)
+        rpn = self.proposal_generator
         cur = torch.cuda.current_stream()
         if self._side is None:
             self._side = torch.cuda.Stream()
-        self._side.wait_stream(cur)
-        with torch.cuda.stream(self._side):
-            gmap = heads.p2p3(feats)
-        det = self.detect_from_features(feats, img_hw, taps)
-        cur.wait_stream(self._side)
+        fork = _FORK
+
+        def side_p2p3():
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                return heads.p2p3(feats)
+        gmap = side_p2p3() if fork == 1 else None
+        preds = rpn.head(feats)
+        if fork == 2:
+            gmap = side_p2p3()
+        boxes, scores = rpn.topk_decode(preds)
+        pb, ps, pi, pc = rpn.select(boxes, scores, img_hw)
+        det = heads.forward_box(feats, pb, pc, img_hw, taps)
+        if taps is not None:
+            taps.update(features=feats, proposal_boxes=pb, objectness_logits=ps, proposal_count=pc)
+        if gmap is not None:
+            cur.wait_stream(self._side)
         n, m = det["pred_boxes"].shape[0], det["pred_boxes"].shape[1]
         ws = heads.ws
         rois = ws.raw("step.rois", (n * m, 6), torch.float32)

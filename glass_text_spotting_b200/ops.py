@@ -24,6 +24,29 @@ TAP_MODE = int(__import__("os").environ.get("GLASS_TAP_MODE", "0"))
 # 0 = auto (TMA-store epilogue for flat layers), 1 = direct-store epilogue everywhere, 2 = insist on TMA (tests)
 EPI_MODE = int(__import__("os").environ.get("GLASS_EPI_MODE", "0"))
 
+# GLASS_DEBUG_SAT=1: every GEMM counts the outputs that saturate the split-fp16 storage range (|y| > 3750) into one device
+# counter, read with saturation_count() -- a checkpoint with a hot activation then shows up instead of degrading silently
+DEBUG_SAT = __import__("os").environ.get("GLASS_DEBUG_SAT", "0") == "1"
+_SAT = {}
+
+
+def _sat_counter() -> torch.Tensor:
+    dev = torch.cuda.current_device()
+    if dev not in _SAT:
+        _SAT[dev] = torch.zeros((1,), dtype=torch.int32, device=f"cuda:{dev}")
+    return _SAT[dev]
+
+
+def saturation_count(reset: bool = False) -> int:
+    """Outputs clamped by the split-fp16 storage format since the last reset (only counted under GLASS_DEBUG_SAT=1 /
+    ops.DEBUG_SAT = True)."""
+    c = _sat_counter()
+    v = int(c.item())
+    if reset:
+        c.zero_()
+    return v
+
+
 # bench.py's per-kernel timing: when a list, every conv_gemm launch appends (start event, end event, algorithmic FLOPs)
 PROFILE = None
 
@@ -160,6 +183,8 @@ def conv_gemm(a_hi: torch.Tensor, a_lo: Optional[torch.Tensor], rows_a: int, k_p
     p.pair_mode = PAIR_MODE if (PAIR_MODE != 2 or w.n_p % 32 == 0) else 0
     p.tap_mode = TAP_MODE
     p.epi_mode = EPI_MODE
+    if DEBUG_SAT:
+        p.sat_count = _ptr(_sat_counter())
     p.a_col0, p.a_inner = a_col0, a_inner
     if m_count is not None:
         p.m_count_dev, p.m_rows_per_count = _ptr(m_count[0]), int(m_count[1])

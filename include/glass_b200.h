@@ -110,6 +110,10 @@ typedef struct {
    * plane is the M space itself, n a multiple of 64 per tile, residual -- if any -- of the same geometry; direct stores
    * otherwise), 1 = direct stores, 2 = TMA (error if not eligible).  Both epilogues produce the same bits. */
   int32_t epi_mode;
+  /* Debug (optional, NULL in production): device counter incremented by the number of stored outputs whose storage value
+   * 16*y lies beyond +-60000, i.e. that SATURATE in the split-fp16 format (|y| > 3750).  BatchNorm-normalised networks stay
+   * far inside; an uncalibrated checkpoint may not -- this makes the otherwise silent clamp visible. */
+  int32_t* sat_count;
 } GlassConvGemmParams;
 int glass_conv_gemm(const GlassConvGemmParams* p, void* stream);
 /* Launch plans (SURVEY.md 8b "cached in an opaque handle the caller owns"): glass_plan_create does everything the host

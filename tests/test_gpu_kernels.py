@@ -366,3 +366,20 @@ def test_tma_epilogue_equals_direct_store_epilogue(ops, monkeypatch, cin, cout, 
     b = outs[1]
     assert b[:, :, 0].abs().max().item() == 0 and b[:, :, -1].abs().max().item() == 0
     assert b[:, :, :, 0].abs().max().item() == 0 and b[:, :, :, -1].abs().max().item() == 0
+
+
+def test_saturation_counter_debug_flag(ops, monkeypatch):
+    """the split-fp16 storage clamps |y| > 3750 silently; under the debug flag the GEMM counts such outputs."""
+    from glass_text_spotting_b200 import packing
+    g = torch.Generator().manual_seed(5)
+    x = ops.Act.from_nchw(torch.randn(1, 64, 12, 16, generator=g).cuda())
+    w = torch.randn(64, 64, 1, 1, generator=g) * 0.1
+    monkeypatch.setattr(ops, "DEBUG_SAT", True)
+    ops.saturation_count(reset=True)
+    for mode in (1, 2):
+        monkeypatch.setattr(ops, "EPI_MODE", mode)
+        ops.conv2d(x, packing.pack_conv(w))
+        assert ops.saturation_count() == 0
+        hot = packing.pack_conv(w, torch.full((64,), 1.0), torch.cat((torch.tensor([5000.0, -9000.0]), torch.zeros(62))))
+        ops.conv2d(x, hot)
+        assert ops.saturation_count(reset=True) == 2 * 12 * 16      # two hot channels at every pixel
