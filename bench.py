@@ -649,9 +649,11 @@ def _roialign_glass_shapes(rois_d, flush, reps: int = 10):
         ops.roi_align_rotated([gmap], rois_d, (8, 32), [0.25], 0, out_f32=False,
                               out_split=(fused.buf, fused.hp, fused.wp, fused.border, 256, fused.cp))
 
+    img4 = torch.empty((1, 1024, 1024, 4), dtype=torch.float32, device="cuda")
+
     def img():
         ops.image_roi_align_rotated(image, (1024, 1024), (103.530, 116.280, 123.675), (1.0, 1.0, 1.0), rois_d, (128, 128), 2,
-                                    out_act=crops)
+                                    out_act=crops, workspace=img4)
 
     r = rois_d.cpu()
     area = (r[:, 3].clamp(max=1024) * r[:, 4].clamp(max=1024)).sum().item()      # px^2 on the image

@@ -349,30 +349,61 @@ struct ImgRoiKernelParams {
   __half* out_hi;
   __half* out_lo;
   int out_border, ld_out;
+  const float4* img4;   // optional: the NORMALISED image as pixel-interleaved float4 (c0, c1, c2, 0) [n, h, w]
 };
 
+// raw fp32 NCHW [n,3,h,w] -> normalised pixel-interleaved float4 [n,h,w] ((x - mean) * inv_std, the fp32 operation the
+// pooler would otherwise repeat for every tap): one 16-byte load per bilinear tap instead of three scalar ones
+__global__ void image_to_nhwc4_kernel(const float* __restrict__ img, int n, int h, int w, float m0, float m1, float m2,
+                                      float is0, float is1, float is2, float4* __restrict__ out) {
+  const int64_t plane = (int64_t)h * w, total = (int64_t)n * plane;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / plane, r = i - b * plane;
+    const float* f = img + b * 3 * plane + r;
+    out[i] = make_float4((__ldg(f) - m0) * is0, (__ldg(f + plane) - m1) * is1, (__ldg(f + 2 * plane) - m2) * is2, 0.f);
+  }
+}
+
+// One CTA = one RoI x a block of IMG_ROWS output rows.  The per-RoI constants -- above all the correctly rounded
+// sine / cosine, which are DOUBLE-precision library calls -- are computed ONCE per CTA by one thread (round 1's kernel
+// evaluated them in every one of the 16384 bins of a crop: the fp64 pipe, not memory, was its bound), then every thread
+// walks its bins with the reference's fp32 arithmetic, operation for operation.
+constexpr int IMG_ROWS = 8;
 __global__ void __launch_bounds__(256) image_roi_align_rotated_kernel(const ImgRoiKernelParams p) {
   const int n_rois = p.n_rois_dev ? min(*p.n_rois_dev, p.n_rois) : p.n_rois;
-  const int bins = p.ph * p.pw;
-  const int64_t total = (int64_t)n_rois * bins;
-  const int H = p.h_pad, W = p.w_pad;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int roi_idx = (int)(i / bins);
-    const int bin = (int)(i - (int64_t)roi_idx * bins);
-    const int bph = bin / p.pw, bpw = bin - bph * p.pw;
+  const int row_blocks = (p.ph + IMG_ROWS - 1) / IMG_ROWS;
+  const int roi_idx = blockIdx.x / row_blocks;
+  if (roi_idx >= n_rois) return;
+  const int row0 = (blockIdx.x - roi_idx * row_blocks) * IMG_ROWS;
+  __shared__ float s_c[10];   // batch, cw, chh, rw, rh, sn, cs
+  if (threadIdx.x == 0) {
     const float* roi = p.rois + (int64_t)roi_idx * 6;
-    const int batch = (int)roi[0];
-    const float cw = roi[1] - 0.5f, chh = roi[2] - 0.5f;
-    const float rw = roi[3], rh = roi[4];
     const float theta = (float)((double)roi[5] * 3.14159265358979323846 / 180.0);
-    const float sn = (float)sin((double)theta), cs = (float)cos((double)theta);
-    const float bsh = rh / (float)p.ph, bsw = rw / (float)p.pw;
-    const int gh = p.sampling > 0 ? p.sampling : (int)ceilf(rh / (float)p.ph);
-    const int gw = p.sampling > 0 ? p.sampling : (int)ceilf(rw / (float)p.pw);
-    const float count = (float)max(gh * gw, 1);
-    const float sh0 = -rh / 2.0f, sw0 = -rw / 2.0f;
-    const float* f = p.img + (int64_t)batch * 3 * p.h * p.w;
-    const int64_t cstride = (int64_t)p.h * p.w;
+    s_c[0] = roi[0];
+    s_c[1] = roi[1] - 0.5f;
+    s_c[2] = roi[2] - 0.5f;
+    s_c[3] = roi[3];
+    s_c[4] = roi[4];
+    s_c[5] = (float)sin((double)theta);
+    s_c[6] = (float)cos((double)theta);
+  }
+  __syncthreads();
+  const int batch = (int)s_c[0];
+  const float cw = s_c[1], chh = s_c[2], rw = s_c[3], rh = s_c[4], sn = s_c[5], cs = s_c[6];
+  const int H = p.h_pad, W = p.w_pad;
+  const int bins = p.ph * p.pw;
+  const float bsh = rh / (float)p.ph, bsw = rw / (float)p.pw;
+  const int gh = p.sampling > 0 ? p.sampling : (int)ceilf(rh / (float)p.ph);
+  const int gw = p.sampling > 0 ? p.sampling : (int)ceilf(rw / (float)p.pw);
+  const float count = (float)max(gh * gw, 1);
+  const float sh0 = -rh / 2.0f, sw0 = -rw / 2.0f;
+  const float* f = p.img + (int64_t)batch * 3 * p.h * p.w;
+  const float4* f4 = p.img4 ? p.img4 + (int64_t)batch * p.h * p.w : nullptr;
+  const int64_t cstride = (int64_t)p.h * p.w;
+  const int rows = min(IMG_ROWS, p.ph - row0);
+  for (int i = threadIdx.x; i < rows * p.pw; i += blockDim.x) {
+    const int bph = row0 + i / p.pw, bpw = i % p.pw;
+    const int bin = bph * p.pw + bpw;
     float acc[3] = {0.f, 0.f, 0.f};
     for (int iy = 0; iy < gh; ++iy) {
       const float yy = sh0 + bph * bsh + ((float)iy + .5f) * bsh / (float)gh;
@@ -391,14 +422,25 @@ __global__ void __launch_bounds__(256) image_roi_align_rotated_kernel(const ImgR
         const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
         const bool in1 = yl < p.h && xl < p.w, in2 = yl < p.h && xh < p.w;
         const bool in3 = yh < p.h && xl < p.w, in4 = yh < p.h && xh < p.w;
+        if (f4 != nullptr) {   // pre-normalised float4 pixels: same values, one vector load per tap
+          const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 a = in1 ? __ldg(f4 + (int64_t)yl * p.w + xl) : z4;
+          const float4 b = in2 ? __ldg(f4 + (int64_t)yl * p.w + xh) : z4;
+          const float4 cc = in3 ? __ldg(f4 + (int64_t)yh * p.w + xl) : z4;
+          const float4 d = in4 ? __ldg(f4 + (int64_t)yh * p.w + xh) : z4;
+          acc[0] += w1 * a.x + w2 * b.x + w3 * cc.x + w4 * d.x;
+          acc[1] += w1 * a.y + w2 * b.y + w3 * cc.y + w4 * d.y;
+          acc[2] += w1 * a.z + w2 * b.z + w3 * cc.z + w4 * d.z;
+        } else {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float* fc = f + c * cstride;
-          const float a = in1 ? (__ldg(fc + (int64_t)yl * p.w + xl) - p.mean[c]) * p.inv_std[c] : 0.f;
-          const float b = in2 ? (__ldg(fc + (int64_t)yl * p.w + xh) - p.mean[c]) * p.inv_std[c] : 0.f;
-          const float cc = in3 ? (__ldg(fc + (int64_t)yh * p.w + xl) - p.mean[c]) * p.inv_std[c] : 0.f;
-          const float d = in4 ? (__ldg(fc + (int64_t)yh * p.w + xh) - p.mean[c]) * p.inv_std[c] : 0.f;
-          acc[c] += w1 * a + w2 * b + w3 * cc + w4 * d;
+          for (int c = 0; c < 3; ++c) {
+            const float* fc = f + c * cstride;
+            const float a = in1 ? (__ldg(fc + (int64_t)yl * p.w + xl) - p.mean[c]) * p.inv_std[c] : 0.f;
+            const float b = in2 ? (__ldg(fc + (int64_t)yl * p.w + xh) - p.mean[c]) * p.inv_std[c] : 0.f;
+            const float cc = in3 ? (__ldg(fc + (int64_t)yh * p.w + xl) - p.mean[c]) * p.inv_std[c] : 0.f;
+            const float d = in4 ? (__ldg(fc + (int64_t)yh * p.w + xh) - p.mean[c]) * p.inv_std[c] : 0.f;
+            acc[c] += w1 * a + w2 * b + w3 * cc + w4 * d;
+          }
         }
       }
     }
@@ -500,10 +542,22 @@ extern "C" int glass_image_roi_align_rotated(const GlassImageRoiAlignParams* p, 
   k.ph = p->pooled_h; k.pw = p->pooled_w; k.sampling = p->sampling_ratio;
   k.out_f32 = p->out_f32; k.out_hi = (__half*)p->out_hi; k.out_lo = (__half*)p->out_lo;
   k.out_border = p->out_border; k.ld_out = p->ld_out;
-  const int64_t total = (int64_t)p->n_rois * p->pooled_h * p->pooled_w;
-  int64_t blocks = (total + 255) / 256;
-  const int64_t cap = (int64_t)num_sms() * 32;
-  if (blocks > cap) blocks = cap;
+  k.img4 = nullptr;
+  if (p->workspace != nullptr) {   // normalise once per pixel into the caller's workspace, then gather float4 taps
+    const int64_t need = (int64_t)p->n * p->h * p->w * 16;
+    GLASS_CHECK(p->workspace_bytes >= need, "image pooler workspace too small (n*h*w*16 bytes)");
+    GLASS_CHECK((reinterpret_cast<uintptr_t>(p->workspace) & 15) == 0, "workspace must be 16-byte aligned");
+    const int64_t px = (int64_t)p->n * p->h * p->w;
+    int64_t nb = (px + 255) / 256;
+    if (nb > (int64_t)num_sms() * 16) nb = (int64_t)num_sms() * 16;
+    image_to_nhwc4_kernel<<<(int)nb, 256, 0, stream>>>(p->img, p->n, p->h, p->w, p->mean[0], p->mean[1], p->mean[2],
+                                                       p->inv_std[0], p->inv_std[1], p->inv_std[2],
+                                                       reinterpret_cast<float4*>(p->workspace));
+    count_launch();
+    k.img4 = reinterpret_cast<const float4*>(p->workspace);
+  }
+  const int64_t blocks = (int64_t)p->n_rois * ((p->pooled_h + IMG_ROWS - 1) / IMG_ROWS);
+  GLASS_CHECK(blocks < ((int64_t)1 << 31), "too many RoIs");
   image_roi_align_rotated_kernel<<<(int)blocks, 256, 0, stream>>>(k);
   count_launch();
   GLASS_CUDA(cudaGetLastError());

@@ -60,7 +60,7 @@ class ImageRoiAlignParams(C.Structure):
         ("rois", C.c_void_p), ("n_rois_dev", C.c_void_p), ("n_rois", C.c_int32),
         ("pooled_h", C.c_int32), ("pooled_w", C.c_int32), ("sampling_ratio", C.c_int32),
         ("out_f32", C.c_void_p), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p),
-        ("out_border", C.c_int32), ("ld_out", C.c_int32),
+        ("out_border", C.c_int32), ("ld_out", C.c_int32), ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
     ]
 
 

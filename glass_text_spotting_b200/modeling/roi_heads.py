@@ -442,8 +442,9 @@ class B200GlassROIHeads:
         ops.roi_align_rotated([g], rois, (ph, pw), [1.0 / self.strides[0]], self.recog_sampling, out_f32=False,
                               out_split=(fused.buf, fused.hp, fused.wp, fused.border, 256, fused.cp), n_rois_dev=nd)
         crops = self.act("rec.crops", K, 3, ph * 16, pw * 4, cp=8)
+        img4 = self.ws.raw("rec.img_nhwc4", (images.shape[0], images.shape[2], images.shape[3], 4), torch.float32)
         ops.image_roi_align_rotated(images, pad_hw, self.pixel_mean, self.pixel_std, rois, (ph * 16, pw * 4),
-                                    self.sampling, out_act=crops, n_rois_dev=nd)
+                                    self.sampling, out_act=crops, n_rois_dev=nd, workspace=img4)
         self.hybrid_net(crops, fused)
         local_own = fused.to_nchw()[:, :256] if (teacher and "local_feats" in teacher) else None
         if teacher and "local_feats" in teacher:

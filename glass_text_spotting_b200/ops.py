@@ -429,7 +429,9 @@ def roi_align_rotated(feats: List, rois: torch.Tensor, output_size: Tuple[int, i
 
 def image_roi_align_rotated(img: torch.Tensor, pad_hw: Tuple[int, int], mean, std, rois: torch.Tensor,
                             output_size: Tuple[int, int], sampling_ratio: int, out_f32: bool = False,
-                            out_act: Optional[Act] = None, n_rois_dev: Optional[torch.Tensor] = None):
+                            out_act: Optional[Act] = None, n_rois_dev: Optional[torch.Tensor] = None,
+                            workspace: Optional[torch.Tensor] = None):
+    """``workspace``: optional uint8 / float32 CUDA scratch of n*h*w*16 bytes (see include/glass_b200.h)."""
     n, c, h, w = img.shape
     assert c == 3 and img.dtype == torch.float32 and img.is_contiguous()
     p = _lib.ImageRoiAlignParams()
@@ -446,6 +448,8 @@ def image_roi_align_rotated(img: torch.Tensor, pad_hw: Tuple[int, int], mean, st
     if out_act is not None:
         assert (out_act.h, out_act.w) == tuple(output_size) and out_act.n >= rois.shape[0]
         p.out_hi, p.out_lo, p.out_border, p.ld_out = _ptr(out_act.hi), _ptr(out_act.lo), out_act.border, out_act.cp
+    if workspace is not None:
+        p.workspace, p.workspace_bytes = _ptr(workspace), workspace.numel() * workspace.element_size()
     _lib.check(_lib.load().glass_image_roi_align_rotated(C.byref(p), _stream()))
     return out
 

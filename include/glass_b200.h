@@ -219,6 +219,11 @@ typedef struct {
   void* out_hi;   /* optional split fp16 [n_rois, ph+2b, pw+2b, ld_out], channels 0..2 */
   void* out_lo;
   int32_t out_border, ld_out;
+  /* optional scratch, n*h*w*16 bytes, 16-byte aligned: the image is normalised ONCE per pixel into pixel-interleaved
+   * float4 there and the gather reads one 16-byte vector per bilinear tap (same values, a third of the loads); NULL =
+   * gather from the planar image, normalising every tap */
+  void* workspace;
+  int64_t workspace_bytes;
 } GlassImageRoiAlignParams;
 int glass_image_roi_align_rotated(const GlassImageRoiAlignParams* p, void* stream);
 

@@ -336,6 +336,12 @@ def test_image_roi_align_matches_oracle(ops):
                                       out_act=act)
     _close(got, ref, "image_pooler/f32")
     _close(act.to_nchw(), ref, "image_pooler/split")
+    # the pre-normalised float4 path (workspace given) gathers the same values: bit-identical
+    ws = torch.empty((1, 200, 232, 4), dtype=torch.float32, device="cuda")
+    act2 = ops.Act(6, 3, 128, 128)
+    got2 = ops.image_roi_align_rotated(img.cuda(), (224, 256), mean, std, rois.cuda(), (128, 128), 2, out_f32=True,
+                                       out_act=act2, workspace=ws)
+    assert torch.equal(got2, got) and torch.equal(act2.buf, act.buf)
 
 
 @pytest.mark.parametrize("cin,cout,k,res,relu,n_img,hw", [
