@@ -291,7 +291,8 @@ constexpr int LC_LD = LSTM_H + 8;        // shared-memory row stride in halfs: 5
 constexpr int LC_THREADS = 256;          // 8 warps: warp w owns gate columns [16w, 16w + 16) = 4 hidden units
 constexpr float LC_SW = 64.f;            // power-of-two pre-scales of the fp16 split (weights, h)
 constexpr float LC_SH = 1024.f;
-constexpr int LC_SMEM = (2 * LC_N + 2 * LC_W) * LC_LD * (int)sizeof(__half);   // 202,752 B
+constexpr int LC_SLD = LC_U + 8;         // row stride of the local slice stage in halfs (80 B: conflict-free 16-byte rows)
+constexpr int LC_SMEM = ((2 * LC_N + 2 * LC_W) * LC_LD + 2 * LC_W * LC_SLD) * (int)sizeof(__half);   // 212,992 B
 
 __device__ __forceinline__ void lc_ldsm_x4(uint32_t (&r)[4], const __half* p) {
   const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
@@ -302,6 +303,16 @@ __device__ __forceinline__ void lc_mma(float (&d)[4], const uint32_t (&a)[4], ui
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// 16-byte store into the shared memory of CTA `rank` of this cluster at the same offset as local address `addr`
+__device__ __forceinline__ void lc_st_cluster_u4(uint32_t addr, uint32_t rank, uint4 v) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n"
+      "st.shared::cluster.v4.b32 [ra], {%2, %3, %4, %5};\n"
+      "}\n" ::"r"(addr), "r"(rank), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+      : "memory");
 }
 __device__ __forceinline__ void lc_split(float x, float scale, __half& hi, __half& lo) {
   const float v = x * scale;
@@ -320,6 +331,8 @@ __global__ void __cluster_dims__(LC_R, 1, 1) __launch_bounds__(LC_THREADS, 1)
   __half* w_lo = w_hi + LC_N * LC_LD;
   __half* h_hi = w_lo + LC_N * LC_LD;                  // [LC_W][LC_LD], h[word][k] * LC_SH
   __half* h_lo = h_hi + LC_W * LC_LD;
+  __half* s_hi = h_lo + LC_W * LC_LD;                  // [LC_W][LC_SLD] this CTA's new h slice (hi), staged before the push
+  __half* s_lo = s_hi + LC_W * LC_SLD;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int dir = blockIdx.y;
@@ -415,7 +428,10 @@ __global__ void __cluster_dims__(LC_R, 1, 1) __launch_bounds__(LC_THREADS, 1)
       }
     if (step + 1 < T) load_gates(step + 1);   // in flight across the barriers
 
-    cluster.barrier_wait();     // every CTA of the cluster has finished reading h_{t-1}: it may be overwritten
+    // ---- new h slice [64 words x 32 units] of this CTA: staged in LOCAL shared memory first (and written to global
+    // memory), then pushed to the 8 CTAs of the cluster with 16-byte shared::cluster stores, one peer per warp.  (The
+    // first version scattered 8-byte stores to 4 different peers per instruction straight from the registers: ncu put
+    // 43 % of the kernel's stall samples there.)
     const int kcol = rank * LC_U + 4 * warp;   // the quad (q = 0..3) holds units kcol .. kcol + 3 of the same 8 words
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -424,20 +440,15 @@ __global__ void __cluster_dims__(LC_R, 1, 1) __launch_bounds__(LC_THREADS, 1)
         float v[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[j] = __shfl_sync(0xffffffffu, hn[i][e], (lane & ~3) + j);
-        __half hh[4], hl[4];
+        const int wrow = 16 * i + g + 8 * e;
+        if (q == (i & 3)) {                      // one lane of the quad stages the quad's 4 units of this word ...
+          __half hh[4], hl[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) lc_split(v[j], LC_SH, hh[j], hl[j]);
-        const uint2 ph = make_uint2(pack16x2(hh[0], hh[1]), pack16x2(hh[2], hh[3]));
-        const uint2 pl = make_uint2(pack16x2(hl[0], hl[1]), pack16x2(hl[2], hl[3]));
-        const int off = (16 * i + g + 8 * e) * LC_LD + kcol;
-#pragma unroll
-        for (int pr = 0; pr < 2; ++pr) {       // lane q of the quad serves peers 2q and 2q + 1
-          const unsigned peer = 2 * q + pr;
-          *reinterpret_cast<uint2*>(cluster.map_shared_rank(h_hi, peer) + off) = ph;
-          *reinterpret_cast<uint2*>(cluster.map_shared_rank(h_lo, peer) + off) = pl;
-        }
-        if (i == q) {                            // and stores m-tile q's two words to global memory
-          const int word = seq0 + 16 * i + g + 8 * e;
+          for (int j = 0; j < 4; ++j) lc_split(v[j], LC_SH, hh[j], hl[j]);
+          const int so = wrow * LC_SLD + 4 * warp;
+          *reinterpret_cast<uint2*>(s_hi + so) = make_uint2(pack16x2(hh[0], hh[1]), pack16x2(hh[2], hh[3]));
+          *reinterpret_cast<uint2*>(s_lo + so) = make_uint2(pack16x2(hl[0], hl[1]), pack16x2(hl[2], hl[3]));
+          const int word = seq0 + wrow;          // ... and stores them to global memory
           if (word < n_seq) {
             const int64_t o = ((int64_t)word * T + t) * (2 * LSTM_H) + dir * LSTM_H + kcol;
             __half oh[4], ol[4];
@@ -449,6 +460,20 @@ __global__ void __cluster_dims__(LC_R, 1, 1) __launch_bounds__(LC_THREADS, 1)
           }
         }
       }
+    __syncthreads();            // the local slice is complete
+    cluster.barrier_wait();     // every CTA of the cluster has finished reading h_{t-1}: it may be overwritten
+    {
+      // warp w -> peer w: 64 rows x (4 chunks of 8 units) x 2 planes = 512 chunks of 16 bytes, 16 per lane
+      const uint32_t peer = (uint32_t)warp;
+#pragma unroll 4
+      for (int c = lane; c < 2 * LC_W * 4; c += 32) {
+        const int plane = c >> 8, row = (c & 255) >> 2, ch = c & 3;
+        const __half* src = (plane ? s_lo : s_hi) + row * LC_SLD + ch * 8;
+        __half* dst = (plane ? h_lo : h_hi) + row * LC_LD + rank * LC_U + ch * 8;
+        const uint4 v = *reinterpret_cast<const uint4*>(src);
+        lc_st_cluster_u4(smem_u32(dst), peer, v);
+      }
+    }
     cluster.sync();             // all slices of h_t have landed in every CTA (also keeps peers alive until the last write)
   }
 }
