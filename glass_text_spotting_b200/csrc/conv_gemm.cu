@@ -35,7 +35,7 @@ static constexpr int A_BLOCK_BYTES = A_BLOCK_ROWS * BK * 2;  // 17408 = 17 x 102
 static constexpr int MAX_A_STAGES = 4;
 static constexpr int EPI_WARPS = 16;
 static constexpr int NUM_THREADS = 128 + 32 * EPI_WARPS;  // 4 control warps + 16 epilogue warps
-static constexpr int MAX_STAGES = 8;
+static constexpr int MAX_STAGES = 12;
 static constexpr int EPI_STAGE_BYTES = EPI_WARPS * 2048;  // per epilogue warp: 32 rows x 16 fp32 columns
 static constexpr int MAX_CHUNKS_PER_WARP = 4;  // 256 columns / 16 per chunk / 4 column parts
 
@@ -50,6 +50,10 @@ struct GemmKernelParams {
   // s-taps are addressed by advancing the UMMA descriptor start by s rows (the 128B swizzle is a function of the
   // absolute shared-memory address, verified by tools/probes/umma_rowoffset_probe.cu); weights stream per tap.
   int32_t group3, a_stages, a_stage_bytes, b_stages, b_stage_bytes, ring_bytes;
+  // resident weights (tap-row mode, one N tile, all k-blocks of the weight tile fit the ring: the 64-channel 3x3 convs):
+  // the weight tile is loaded ONCE per CTA and every M tile re-uses it -- those layers were bound by re-streaming it from
+  // L2 for every tile (74 KB per tile beside 104 KB of activations)
+  int32_t resident_b;
   int32_t kb_per_chunk;  // k-blocks accumulated inside the tensor core before a drain to registers
   int32_t acc_cols, acc_bufs;  // TMEM accumulator ring: acc_bufs buffers of acc_cols columns (acc_cols * acc_bufs = 512)
   int32_t m_h, m_w, m_border;
@@ -208,16 +212,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
               aphase ^= 1;
             }
             for (int sx = 0; sx < 3; ++sx) {
-              mbar_wait(&empty_bar[bs], bphase ^ 1);
-              uint8_t* sb = b_ring + (size_t)bs * p.b_stage_bytes;
-              if (leader) mbar_arrive_expect_tx(&full_bar[bs], (uint32_t)p.b_stage_bytes * (PAIR ? 2u : 1u));
-              const int kw = ((3 * r + sx) * p.kblocks_per_tap + kb) * BK;
-              if (PAIR) {
-                tma_load_2d_pair(sb, &map_b_hi, &full_bar[bs], kw, n0);
-                if (SPLIT) tma_load_2d_pair(sb + p.b_tile_bytes, &map_b_lo, &full_bar[bs], kw, n0);
-              } else {
-                tma_load_2d(sb, &map_b_hi, &full_bar[bs], kw, n0);
-                if (SPLIT) tma_load_2d(sb + p.b_tile_bytes, &map_b_lo, &full_bar[bs], kw, n0);
+              if (!(p.resident_b && unit != worker)) {   // resident weights: loaded by this CTA's first tile only
+                mbar_wait(&empty_bar[bs], bphase ^ 1);
+                uint8_t* sb = b_ring + (size_t)bs * p.b_stage_bytes;
+                if (leader) mbar_arrive_expect_tx(&full_bar[bs], (uint32_t)p.b_stage_bytes * (PAIR ? 2u : 1u));
+                const int kw = ((3 * r + sx) * p.kblocks_per_tap + kb) * BK;
+                if (PAIR) {
+                  tma_load_2d_pair(sb, &map_b_hi, &full_bar[bs], kw, n0);
+                  if (SPLIT) tma_load_2d_pair(sb + p.b_tile_bytes, &map_b_lo, &full_bar[bs], kw, n0);
+                } else {
+                  tma_load_2d(sb, &map_b_hi, &full_bar[bs], kw, n0);
+                  if (SPLIT) tma_load_2d(sb + p.b_tile_bytes, &map_b_lo, &full_bar[bs], kw, n0);
+                }
               }
               if (++bs == p.b_stages) {
                 bs = 0;
@@ -306,7 +312,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
               mbar_wait(&a_full_bar[as], aphase);
               a_block = smem_u32(smem) + (uint32_t)(as * p.a_stage_bytes);
             }
-            mbar_wait(&full_bar[stage], phase);
+            if (!(p.resident_b && unit != worker)) mbar_wait(&full_bar[stage], phase);   // (resident: landed with the first tile)
             sa_hi = a_block + (uint32_t)(sx * BK * 2);  // descriptor start advanced by sx rows of 128 bytes
             sa_lo = sa_hi + A_BLOCK_BYTES;
             sb_hi = b_ring + (uint32_t)(stage * p.b_stage_bytes);
@@ -337,7 +343,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                 mma(d_tmem, da_hi + koff, db_hi + koff, acc_flag);
               }
             }
-            commit(&empty_bar[stage]);  // frees the (weight) slot in both CTAs when these MMAs retire
+            if (!p.resident_b) commit(&empty_bar[stage]);  // frees the (weight) slot in both CTAs when these MMAs retire
             if (a_done) commit(&a_empty_bar[as]);  // all three s-taps have consumed the activation block
             if (chunk_done) commit(&tmem_full_bar[chunk % (uint32_t)p.acc_bufs]);  // -> the epilogue(s) drain it
           }
@@ -820,7 +826,19 @@ static int build_plan(const GlassConvGemmParams* p, GlassGemmPlan* plan) {
   for (int r = 0; r < 3 && group3; ++r)
     group3 = p->tap_shift[3 * r + 1] == p->tap_shift[3 * r] + 1 && p->tap_shift[3 * r + 2] == p->tap_shift[3 * r] + 2;
   int a_stages = 2, b_stages = 0;
+  bool resident_b = false;
   if (group3) {
+    static const int res_env = getenv("GLASS_RESIDENT_B") ? atoi(getenv("GLASS_RESIDENT_B")) : 1;
+    const int kblocks_all = p->ntaps * (p->k_per_tap / BK);
+    if (res_env && p->n == bn && kblocks_all <= MAX_STAGES &&
+        kblocks_all * b_stage_bytes + 2 * A_BLOCK_BYTES * split_mul <= smem_budget) {
+      resident_b = true;
+      b_stages = kblocks_all;
+      a_stages = (smem_budget - b_stages * b_stage_bytes) / (A_BLOCK_BYTES * split_mul);
+      if (a_stages > MAX_A_STAGES) a_stages = MAX_A_STAGES;
+    }
+  }
+  if (group3 && !resident_b) {
     b_stages = (smem_budget - a_stages * A_BLOCK_BYTES * split_mul) / b_stage_bytes;
     if (b_stages > MAX_STAGES) {
       b_stages = MAX_STAGES;
@@ -859,6 +877,7 @@ static int build_plan(const GlassConvGemmParams* p, GlassGemmPlan* plan) {
   k.a_stages = a_stages;
   k.a_stage_bytes = A_BLOCK_BYTES * split_mul;
   k.b_stages = b_stages;
+  k.resident_b = (group3 && resident_b) ? 1 : 0;
   k.b_stage_bytes = b_stage_bytes;
   k.ring_bytes = group3 ? a_stages * k.a_stage_bytes + b_stages * b_stage_bytes : k.num_stages * k.stage_bytes;
   // default: drain every 2 k-blocks (split) / 4 (single pass): a drain reads the whole 128 x BN fp32 tile from TMEM
