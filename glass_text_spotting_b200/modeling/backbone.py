@@ -19,6 +19,9 @@ PIXEL_MEAN = (103.530, 116.280, 123.675)
 PIXEL_STD = (1.0, 1.0, 1.0)
 
 
+GROUPED64 = os.environ.get("GLASS_GROUPED64", "1") != "0"
+
+
 def _conv_bn(sd: Dict[str, torch.Tensor], prefix: str, stride=(1, 1), pad=(0, 0), device="cuda"):
     w = sd[prefix + ".weight"]
     if prefix + ".norm.weight" in sd:
@@ -27,7 +30,13 @@ def _conv_bn(sd: Dict[str, torch.Tensor], prefix: str, stride=(1, 1), pad=(0, 0)
                                       conv_bias=sd.get(prefix + ".bias"))
     else:
         scale, bias = None, sd.get(prefix + ".bias")
-    return packing.pack_conv(w, scale, bias, stride, pad, device=device)
+    pw = packing.pack_conv(w, scale, bias, stride, pad, device=device)
+    if GROUPED64 and tuple(w.shape[1:]) == (64, 3, 3) and w.shape[0] == 64 and tuple(stride) == (1, 1):
+        # res2's 64 -> 64 3x3 convs: two pixels per GEMM row (see roi_heads.py: N = 64 tiles starve the tensor pipe)
+        g = packing.pack_conv_grouped(w, 64, 2, scale, bias, device=device)
+        g.fallback = pw
+        return g
+    return pw
 
 
 class Workspace:

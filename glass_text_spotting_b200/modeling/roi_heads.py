@@ -71,10 +71,18 @@ class B200GlassROIHeads:
         # pixels per GEMM row for the narrow layers (ops._conv2d_grouped); the padded crop width must divide:
         # conv0_1 / conv0_2 see 130-wide planes (P = 5 / 2), layer1.0 66-wide ones (P = 2).  GLASS_GROUPED=0: compact mode
         grouped = os.environ.get("GLASS_GROUPED", "1") != "0"
+        grouped64 = os.environ.get("GLASS_GROUPED64", "1") != "0"
         group_of = {8: 5, 16: 2, 32: 2}
 
-        def cb(conv, bn, stride=(1, 1), pad=(1, 1), compact_cp=0):
+        def cb(conv, bn, stride=(1, 1), pad=(1, 1), compact_cp=0, pair64=False):
             s, b = _bn_fold(sd, hp + bn)
+            if pair64 and grouped64:
+                # 64 -> 64 channel 3x3 convs: N = 64 tiles are bound by fetching the A operand from shared memory (34 %
+                # tensor-pipe activity, ncu); with two pixels per GEMM row the tile is 128 wide (K window 4 pixels x 64
+                # channels per tap row, 1.33x the MACs at twice the pipe activity)
+                pw = packing.pack_conv_grouped(sd[hp + conv + ".weight"], 64, 2, s, b, device=dev)
+                pw.fallback = packing.pack_conv(sd[hp + conv + ".weight"], s, b, stride, pad, device=dev)
+                return pw
             if compact_cp and grouped:
                 pw = packing.pack_conv_grouped(sd[hp + conv + ".weight"], compact_cp, group_of[compact_cp], s, b,
                                                device=dev)
@@ -93,13 +101,13 @@ class B200GlassROIHeads:
             for b in range(nblk):
                 q = f"layer{li}.{b}."
                 narrow = 32 if (li == 1 and b == 0) else 0  # layer1.0 reads the 32-channel activation
-                blk = {"conv1": cb(q + "conv1", q + "bn1", compact_cp=narrow), "conv2": cb(q + "conv2", q + "bn2"),
-                       "down": None}
+                blk = {"conv1": cb(q + "conv1", q + "bn1", compact_cp=narrow),
+                       "conv2": cb(q + "conv2", q + "bn2", pair64=(li == 1)), "down": None}
                 if hp + q + "downsample.0.weight" in sd:
                     blk["down"] = cb(q + "downsample.0", q + "downsample.1", pad=(0, 0), compact_cp=narrow)
                 blocks.append(blk)
             self.h_layers.append(blocks)
-        self.h_conv1, self.h_conv2, self.h_conv3 = cb("conv1", "bn1"), cb("conv2", "bn2"), cb("conv3", "bn3")
+        self.h_conv1, self.h_conv2, self.h_conv3 = cb("conv1", "bn1", pair64=True), cb("conv2", "bn2"), cb("conv3", "bn3")
         self.h_conv4_1 = cb("conv4_1", "bn4_1", stride=(2, 1), pad=(0, 0))
 
         # ---- fusion_net = MultiAspectGCAttention; channel interleave folded into the weights (concat order)

@@ -152,7 +152,8 @@ def conv_gemm(a_hi: torch.Tensor, a_lo: Optional[torch.Tensor], rows_a: int, k_p
               out_hi: Optional[torch.Tensor] = None, out_lo: Optional[torch.Tensor] = None,
               residual: Optional[Act] = None, res_shift: int = 0, relu_pre: bool = False, relu_post: bool = False,
               mode: int = MODE_SPLIT, n_store: int = 0, a_ld: int = 0, a_col0: int = 0, a_inner: int = 0,
-              m_count: Optional[Tuple[torch.Tensor, int]] = None) -> None:
+              m_count: Optional[Tuple[torch.Tensor, int]] = None, res_geom: Optional[Tuple[int, int, int]] = None,
+              valid_pixels: Optional[int] = None) -> None:
     """Raw launch of glass_conv_gemm.  m_geom = (imgs, h, w, border) of the M space;
     out_geom = (hp, wp, border) of the output rows (defaults to ``out``'s geometry).
     ``m_count`` = (int32 device scalar, rows per count): only rows < count * rows_per_count are computed (the live word
@@ -172,10 +173,13 @@ def conv_gemm(a_hi: torch.Tensor, a_lo: Optional[torch.Tensor], rows_a: int, k_p
         ld_out = out.cp
     if residual is not None:
         p.res_hi, p.res_lo = _ptr(residual.hi), _ptr(residual.lo)
-        p.res_hp, p.res_wp, p.res_border, p.res_shift = residual.hp, residual.wp, residual.border, res_shift
-        if ld_out == 0:
-            ld_out = residual.cp
-        assert residual.cp == ld_out, "residual and output must share the channel stride"
+        if res_geom is not None:   # the residual's memory seen in another row geometry (pixel-grouped rows)
+            p.res_hp, p.res_wp, p.res_border, p.res_shift = res_geom[0], res_geom[1], res_geom[2], res_shift
+        else:
+            p.res_hp, p.res_wp, p.res_border, p.res_shift = residual.hp, residual.wp, residual.border, res_shift
+            if ld_out == 0:
+                ld_out = residual.cp
+            assert residual.cp == ld_out, "residual and output must share the channel stride"
     p.out_hi, p.out_lo, p.out_f32 = _ptr(out_hi), _ptr(out_lo), _ptr(out_f32)
     p.out_hp, p.out_wp, p.out_border = out_geom
     p.ld_out, p.ld_f32, p.n_store = ld_out, ld_f32, n_store
@@ -194,6 +198,8 @@ def conv_gemm(a_hi: torch.Tensor, a_lo: Optional[torch.Tensor], rows_a: int, k_p
         _launch_gemm(p)
         e1.record(torch.cuda.current_stream())
         m_valid = p.m_imgs * (p.m_h - 2 * p.m_border) * (p.m_w - 2 * p.m_border)
+        if valid_pixels is not None:     # pixel-grouped launches: the M space is groups of padded pixels
+            m_valid = valid_pixels / getattr(w, "grouped_p", 1)
         # algorithmic FLOPs of this launch + the GEMM's shape (tools/layer_profile.py).  With a device-side M count the
         # launch is sized for the capacity but computes only the live rows: the FLOPs are scaled by live / capacity when
         # the profile is read (profile_flops), after the stream has been synchronised.
@@ -257,7 +263,7 @@ def conv2d(x: Act, w: PackedWeight, relu: bool = False, residual: Optional[Act] 
     ``relu_pre`` = ReLU before it (CNN_V1_1 order).  ``n_dev``: int32 device scalar = live images / words (x.n is then
     the capacity the launch is sized for)."""
     if getattr(w, "grouped_p", 0):
-        if x.wp % w.grouped_p == 0 and residual is None:
+        if x.wp % w.grouped_p == 0 and res_shift == 0:
             return _conv2d_grouped(x, w, relu, residual, relu_pre, out, mode, n_dev)
         w = w.fallback
     if getattr(w, "compact_cp", 0):
@@ -310,13 +316,15 @@ def _conv2d_compact(x: Act, w: PackedWeight, relu, residual, res_shift, relu_pre
 
 def _conv2d_grouped(x: Act, w: PackedWeight, relu, residual, relu_pre, out, mode, n_dev=None) -> Act:
     """Pixel-grouped implicit GEMM (include/glass_b200.h, a_inner > 0; packing.pack_conv_grouped): P pixels per GEMM
-    row, then the border of the output (which the all-valid M space overwrites) is re-zeroed."""
+    row, then the border of the output (which the all-valid M space overwrites) is re-zeroed.  A residual of the output's
+    own geometry is read through the same grouped row view (its zero border adds nothing to the rows re-zeroed anyway)."""
     P, cp = w.grouped_p, w.grouped_cp
-    assert residual is None, "grouped convs have no residual input"
     assert x.cp == cp and x.border == 1 and x.wp % P == 0 and x.rows % P == 0, (x.cp, cp, x.wp, P)
     if out is None:
         out = Act(x.n, w.cout, x.h, x.w, 1, w.grouped_cout_p, x.buf.device)
     assert (out.n, out.h, out.w, out.cp, out.border) == (x.n, x.h, x.w, w.grouped_cout_p, 1)
+    if residual is not None:
+        assert (residual.n, residual.h, residual.w, residual.cp, residual.border) == (out.n, out.h, out.w, out.cp, 1)
     rows = x.rows // P
     kwin = w.cin_p  # K per tap row (window, padded to 64)
     left = 1 if w.kw == 3 else 0
@@ -326,7 +334,8 @@ def _conv2d_grouped(x: Act, w: PackedWeight, relu, residual, relu_pre, out, mode
     col0 = left * (P - 1) * cp
     conv_gemm(x.hi, x.lo, rows, kwin, shifts, w, (1, rows, 1, 0), out_hi=out.hi, out_lo=out.lo, out_geom=(rows, 1, 0),
               ld_out=P * out.cp, relu_pre=relu_pre, relu_post=relu, mode=mode, a_ld=P * cp, a_col0=col0,
-              a_inner=col0 + kwin, m_count=None if n_dev is None else (n_dev, x.hp * x.wp // P))
+              a_inner=col0 + kwin, m_count=None if n_dev is None else (n_dev, x.hp * x.wp // P),
+              residual=residual, res_geom=(rows, 1, 0), valid_pixels=x.n * x.h * x.w)
     _lib.check(_lib.load().glass_zero_border(_ptr(out.hi), _ptr(out.lo), out.n, out.h, out.w, out.cp, _ptr(n_dev),
                                              _stream()))
     return out

@@ -174,6 +174,38 @@ def test_conv_gemm_pixel_grouped(ops, case):
     assert b[:, :, :, 0].abs().max().item() == 0 and b[:, :, :, -1].abs().max().item() == 0
 
 
+@pytest.mark.parametrize("res", [False, True])
+def test_conv_gemm_pixel_pairs_64_channels(ops, res):
+    """The 64 -> 64 channel 3x3 convs as pixel-pair GEMMs (N = 128 tiles), incl. the residual read through the same grouped
+    row view and the device-side word count."""
+    from glass_text_spotting_b200 import packing
+    g = torch.Generator().manual_seed(64 + res)
+    x = torch.randn(5, 64, 14, 22, generator=g)
+    r = torch.randn(5, 64, 14, 22, generator=g)
+    wt = torch.randn(64, 64, 3, 3, generator=g) / math.sqrt(64 * 9)
+    scale = 1.0 + 0.1 * torch.randn(64, generator=g)
+    bias = 0.1 * torch.randn(64, generator=g)
+    pw = packing.pack_conv_grouped(wt, 64, 2, scale, bias)
+    pw.fallback = packing.pack_conv(wt, scale, bias, (1, 1), (1, 1))
+    a = ops.Act.from_nchw(x.cuda())
+    ra = ops.Act.from_nchw(r.cuda()) if res else None
+    out = ops.conv2d(a, pw, relu=True, residual=ra)
+    ref = F.conv2d(x, wt, padding=1) * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)
+    ref = F.relu(ref + r) if res else F.relu(ref)
+    _close(out.to_nchw(), ref, f"pairs64 res={res}")
+    b = out.buf
+    assert b[:, :, 0].abs().max().item() == 0 and b[:, :, -1].abs().max().item() == 0
+    assert b[:, :, :, 0].abs().max().item() == 0 and b[:, :, :, -1].abs().max().item() == 0
+    # same launch sized for 5 words with 3 live ones
+    out2 = ops.Act(5, 64, 14, 22)
+    ops.conv2d(a, pw, relu=True, residual=ra, out=out2, n_dev=torch.tensor([3], dtype=torch.int32).cuda())
+    assert torch.equal(out2.to_nchw()[:3], out.to_nchw()[:3])
+    # odd padded width: falls back to the plain tap-row GEMM
+    x3 = torch.randn(1, 64, 9, 11, generator=g)
+    o3 = ops.conv2d(ops.Act.from_nchw(x3.cuda()), pw, relu=True)
+    _close(o3.to_nchw(), F.relu(F.conv2d(x3, wt, padding=1) * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)), "fallback")
+
+
 def test_conv_gemm_fast_mode_is_fp16_grade(ops):
     from glass_text_spotting_b200 import packing
     g = torch.Generator().manual_seed(5)
