@@ -97,8 +97,8 @@ class AsterParams(C.Structure):
     _fields_ = [
         ("xproj", C.c_void_p), ("pctx", C.c_void_p), ("n_words", C.c_int32), ("n_words_dev", C.c_void_p),
         ("T", C.c_int32), ("steps", C.c_int32), ("num_classes", C.c_int32), ("dim", C.c_int32),
-        ("ws_t", C.c_void_p), ("bs", C.c_void_p), ("we", C.c_void_p), ("be", C.c_float), ("emb_gi", C.c_void_p),
-        ("whh_t", C.c_void_p), ("bhh", C.c_void_p), ("wo_t", C.c_void_p), ("bo", C.c_void_p), ("temperature", C.c_float),
+        ("wh_frag", C.c_void_p), ("bh", C.c_void_p), ("we", C.c_void_p), ("be", C.c_float), ("emb_gi", C.c_void_p),
+        ("wo_t", C.c_void_p), ("bo", C.c_void_p), ("temperature", C.c_float),
         ("probs", C.c_void_p), ("logits", C.c_void_p), ("alphas", C.c_void_p), ("first_eos", C.c_void_p),
     ]
 

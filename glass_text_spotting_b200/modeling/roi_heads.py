@@ -163,14 +163,14 @@ class B200GlassROIHeads:
         # -> one GEMM per launch (w_ctx), like xProj.
         wih = sdr[dp + "gru.weight_ih_l0"]                                   # [768, 512], input = [embedding ; context]
         table = sdr[dp + "tgt_embedding.weight"].double() @ wih[:, :256].double().t() + sdr[dp + "gru.bias_ih_l0"].double()
+        wh_frag, bh = packing.pack_decoder_h_weights(sdr[dp + "attention_unit.sEmbed.weight"],
+                                                     sdr[dp + "attention_unit.sEmbed.bias"],
+                                                     sdr[dp + "gru.weight_hh_l0"], sdr[dp + "gru.bias_hh_l0"], device=dev)
         self.dec = {
-            "ws_t": sdr[dp + "attention_unit.sEmbed.weight"].t().contiguous().to(dev),
-            "bs": sdr[dp + "attention_unit.sEmbed.bias"].to(dev),
+            "wh_frag": wh_frag, "bh": bh,
             "we": sdr[dp + "attention_unit.wEmbed.weight"].view(-1).contiguous().to(dev),
             "be": float(sdr[dp + "attention_unit.wEmbed.bias"].item()),
             "emb_gi": table.float().contiguous().to(dev),
-            "whh_t": sdr[dp + "gru.weight_hh_l0"].t().contiguous().to(dev),
-            "bhh": sdr[dp + "gru.bias_hh_l0"].to(dev),
             "wo_t": sdr[dp + "fc.weight"].t().contiguous().to(dev), "bo": sdr[dp + "fc.bias"].to(dev),
             "temperature": float(sdr[dp + "temperature"].item()) if (dp + "temperature") in sdr else 1.0,
         }

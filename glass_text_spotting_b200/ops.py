@@ -568,8 +568,8 @@ def aster_decode(xproj: torch.Tensor, pctx: torch.Tensor, n_words: int, T: int, 
     p = _lib.AsterParams()
     p.xproj, p.pctx, p.n_words, p.n_words_dev = _ptr(xproj), _ptr(pctx), n_words, _ptr(n_dev)
     p.T, p.steps, p.num_classes, p.dim = T, steps, num_classes, 256
-    p.ws_t, p.bs, p.we, p.be, p.emb_gi = _ptr(w["ws_t"]), _ptr(w["bs"]), _ptr(w["we"]), float(w["be"]), _ptr(w["emb_gi"])
-    p.whh_t, p.bhh = _ptr(w["whh_t"]), _ptr(w["bhh"])
+    assert w["wh_frag"].dtype == torch.int32 and w["wh_frag"].numel() == 64 * 16 * 2 * 32 * 4 and w["bh"].numel() == 1024
+    p.wh_frag, p.bh, p.we, p.be, p.emb_gi = _ptr(w["wh_frag"]), _ptr(w["bh"]), _ptr(w["we"]), float(w["be"]), _ptr(w["emb_gi"])
     p.wo_t, p.bo, p.temperature = _ptr(w["wo_t"]), _ptr(w["bo"]), float(w["temperature"])
     p.probs, p.logits, p.alphas, p.first_eos = _ptr(probs), _ptr(logits), _ptr(alphas), _ptr(first_eos)
     _lib.check(_lib.load().glass_aster_decode(C.byref(p), _stream()))

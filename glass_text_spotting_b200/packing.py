@@ -165,3 +165,21 @@ def pack_stem_s2d(weight: torch.Tensor, scale, bias, device="cuda") -> PackedWei
     b[:cout] = bias.detach().float()
     wp, s = _pack_rows(w.reshape(w.shape[0], 256), s, device)
     return PackedWeight(wp.to(device), s.to(device), b.to(device), cout, 3, 7, 7, (2, 2), (3, 3), 64)
+
+
+DEC_SW = 64.0   # == DEC_SW in csrc/recognizer.cu: power-of-two pre-scale of the decoder's fp16-split weights
+
+
+def pack_decoder_h_weights(ws: torch.Tensor, bs: torch.Tensor, whh: torch.Tensor, bhh: torch.Tensor, device="cuda"):
+    """The decoder's products with the hidden state -- sEmbed [256, 256] and GRU W_hh [768, 256] (nn.Linear / nn.GRU
+    layout [out, in]) -- as ONE 1024 x 256 matrix in the fragment order of mma.sync.m16n8k16's A operand, split into fp16
+    hi / lo planes of DEC_SW * w (include/glass_b200.h, GlassAsterParams.wh_frag).  Returns (int32 [64,16,2,32,4], fp32
+    bias [1024])."""
+    w = torch.cat((ws.detach().float(), whh.detach().float()), 0)            # [1024, 256]
+    assert tuple(w.shape) == (1024, 256)
+    planes = split16(w * DEC_SW)                                             # fp16 [2, 1024, 256]
+    # dims: plane, m-tile (64), r2 (row g / g + 8), g (8), k-step (16), c2 (k 2q.. / 2q + 8..), q (4), e (2 halfs)
+    f = planes.view(2, 64, 2, 8, 16, 2, 4, 2).permute(1, 4, 0, 3, 6, 5, 2, 7).contiguous()   # mt, ks, plane, g, q, c2, r2, e
+    frag = f.view(64, 16, 2, 32, 4, 2).view(torch.int32).view(64, 16, 2, 32, 4)
+    bias = torch.cat((bs.detach().float(), bhh.detach().float()), 0)
+    return frag.contiguous().to(device), bias.contiguous().to(device)

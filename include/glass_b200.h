@@ -352,13 +352,15 @@ typedef struct {
   int32_t n_words;     /* words (capacity of the buffers when n_words_dev is given) */
   const int32_t* n_words_dev; /* optional live word count on the device (<= n_words) */
   int32_t T, steps, num_classes, dim;
-  const float* ws_t;   /* [dim][dim] */
-  const float* bs;
+  /* [sEmbed ; W_hh] (4*dim x dim: every product with the hidden state) as mma.sync m16n8k16 A FRAGMENTS of its split-fp16
+   * planes (weights x 64): uint4 [4*dim/16 m-tiles][dim/16 k-steps][2 planes hi, lo][32 lanes], lane (g = lane / 4,
+   * q = lane % 4) holding {(row g, k 2q..2q+1), (row g+8, same k), (row g, k 2q+8..2q+9), (row g+8, same k)} of its tile
+   * (packing.pack_decoder_h_weights).  The step streams them from L2 in this order: 512 contiguous bytes per warp load. */
+  const void* wh_frag;
+  const float* bh;     /* [4*dim] sEmbed bias | b_hh */
   const float* we;     /* [dim] */
   float be;
   const float* emb_gi; /* [num_classes][3*dim] */
-  const float* whh_t;  /* [dim][3*dim], gates (r,z,n) */
-  const float* bhh;
   const float* wo_t;   /* [dim][num_classes] */
   const float* bo;
   float temperature;

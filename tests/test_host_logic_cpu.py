@@ -188,3 +188,21 @@ def test_glass_rcnn_module_signatures_match_the_reference_call_sites():
     assert list(inspect.signature(B200GlassROIHeads.forward_with_given_boxes).parameters) == ["self", "images", "features", "instances"]
     assert list(inspect.signature(B200GlassRCNN.inference).parameters)[:4] == ["self", "batched_inputs", "detected_instances", "do_postprocess"]
     assert B200GlassRCNN.__call__ is B200GlassRCNN.forward and B200GlassROIHeads.__call__ is B200GlassROIHeads.forward
+
+
+def test_decoder_fragment_packing_matches_the_mma_operand_layout():
+    """packing.pack_decoder_h_weights: register `reg` of lane (g, q) of (m-tile, k-step, plane) must hold
+    (row g + 8*(reg & 1), k = 2q + 8*(reg >> 1) + {0, 1}) of its 16 x 16 tile -- mma.sync.m16n8k16's A operand."""
+    import random
+    from glass_text_spotting_b200 import packing
+    g = torch.Generator().manual_seed(0)
+    ws, whh = torch.randn(256, 256, generator=g) * 0.06, torch.randn(768, 256, generator=g) * 0.06
+    frag, bias = packing.pack_decoder_h_weights(ws, torch.ones(256), whh, torch.zeros(768), device="cpu")
+    assert frag.dtype == torch.int32 and tuple(frag.shape) == (64, 16, 2, 32, 4) and bias[:256].eq(1).all() and bias[256:].eq(0).all()
+    planes = packing.split16(torch.cat((ws, whh), 0) * packing.DEC_SW)
+    f16 = frag.view(torch.float16).view(64, 16, 2, 32, 4, 2)
+    rnd = random.Random(1)
+    for _ in range(3000):
+        mt, ks, pl, lane, reg, e = (rnd.randrange(n) for n in (64, 16, 2, 32, 4, 2))
+        row, k = mt * 16 + (lane >> 2) + 8 * (reg & 1), ks * 16 + 2 * (lane & 3) + 8 * (reg >> 1) + e
+        assert f16[mt, ks, pl, lane, reg, e] == planes[pl, row, k]
