@@ -32,6 +32,12 @@ int fail(const std::string& msg);  // sets last error, returns -1
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Plane geometry code carried by every `border` argument of the ABI (include/glass_b200.h): low byte = LEADING zero rows /
+// columns of a padded plane; GLASS_BORDER_SHARED set = no trailing ones (the next row's / plane's leading border serves as
+// the trailing border of this one).
+#define GLASS_BORDER_LO(code) ((code) & 0xff)
+#define GLASS_BORDER_HI(code) (((code) & GLASS_BORDER_SHARED) ? 0 : ((code) & 0xff))
+
 #ifdef __CUDACC__
 // ---------------------------------------------------------------- small utilities
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

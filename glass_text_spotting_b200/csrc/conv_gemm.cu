@@ -57,6 +57,7 @@ struct GemmKernelParams {
   int32_t kb_per_chunk;  // k-blocks accumulated inside the tensor core before a drain to registers
   int32_t acc_cols, acc_bufs;  // TMEM accumulator ring: acc_bufs buffers of acc_cols columns (acc_cols * acc_bufs = 512)
   int32_t m_h, m_w, m_border;
+  int32_t m_border_hi;  // trailing border rows / columns of the M-space planes (0 for shared-border planes)
   const float* scale;
   const float* bias;
   int32_t relu_pre, relu_post;
@@ -404,7 +405,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           const int rem = (int)(m % plane);
           const int yy = rem / p.m_w;
           const int xx = rem - yy * p.m_w;
-          valid = (yy >= p.m_border) && (xx >= p.m_border) && (yy < p.m_h - p.m_border) && (xx < p.m_w - p.m_border);
+          valid = (yy >= p.m_border) && (xx >= p.m_border) && (yy < p.m_h - p.m_border_hi) && (xx < p.m_w - p.m_border_hi);
         }
         // ---- drain every accumulation chunk of this tile from TMEM into fp32 registers (round-to-nearest adds)
         float accv[MAX_CHUNKS_PER_WARP][16];
@@ -562,7 +563,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         const int yy = rem / p.m_w;
         const int xx = rem - yy * p.m_w;
         const int y = yy - p.m_border, x = xx - p.m_border;
-        valid = (y >= 0) && (x >= 0) && (yy < p.m_h - p.m_border) && (xx < p.m_w - p.m_border);
+        valid = (y >= 0) && (x >= 0) && (yy < p.m_h - p.m_border_hi) && (xx < p.m_w - p.m_border_hi);
         out_row = ((int64_t)img * p.out_hp + y + p.out_border) * p.out_wp + x + p.out_border;
         res_row = ((int64_t)img * p.res_hp + (y >> p.res_shift) + p.res_border) * p.res_wp + (x >> p.res_shift) +
                   p.res_border;
@@ -768,7 +769,8 @@ static int build_plan(const GlassConvGemmParams* p, GlassGemmPlan* plan) {
   }
   GLASS_CHECK(rows_m > 0 && rows_m < (int64_t)1 << 31, "bad M space");
   GLASS_CHECK(p->rows_a > 0 && p->rows_a < (int64_t)1 << 31, "bad rows_a");
-  GLASS_CHECK(p->m_border >= 0 && 2 * p->m_border < p->m_h && 2 * p->m_border < p->m_w, "bad m_border");
+  const int m_b = GLASS_BORDER_LO(p->m_border), m_bh = GLASS_BORDER_HI(p->m_border);
+  GLASS_CHECK(p->m_border >= 0 && m_b + m_bh < p->m_h && m_b + m_bh < p->m_w, "bad m_border");
   GLASS_CHECK(p->out_hi || p->out_f32, "no output requested");
   const int n_store = p->n_store > 0 ? p->n_store : p->n;
   GLASS_CHECK(n_store <= p->n, "n_store > n");
@@ -889,13 +891,13 @@ static int build_plan(const GlassConvGemmParams* p, GlassGemmPlan* plan) {
     const int v = atoi(e);
     if (v >= 2 && v <= k.acc_bufs) k.acc_bufs = v;
   }
-  k.m_h = p->m_h; k.m_w = p->m_w; k.m_border = p->m_border;
+  k.m_h = p->m_h; k.m_w = p->m_w; k.m_border = m_b; k.m_border_hi = m_bh;
   k.scale = p->scale; k.bias = p->bias;
   k.relu_pre = p->relu_pre; k.relu_post = p->relu_post;
   k.res_hi = (const __half*)p->res_hi; k.res_lo = (const __half*)p->res_lo;
-  k.res_hp = p->res_hp; k.res_wp = p->res_wp; k.res_border = p->res_border; k.res_shift = p->res_shift;
+  k.res_hp = p->res_hp; k.res_wp = p->res_wp; k.res_border = GLASS_BORDER_LO(p->res_border); k.res_shift = p->res_shift;
   k.out_hi = (__half*)p->out_hi; k.out_lo = (__half*)p->out_lo; k.out_f32 = p->out_f32;
-  k.out_hp = p->out_hp; k.out_wp = p->out_wp; k.out_border = p->out_border;
+  k.out_hp = p->out_hp; k.out_wp = p->out_wp; k.out_border = GLASS_BORDER_LO(p->out_border);
   k.ld_out = p->ld_out; k.ld_f32 = p->ld_f32; k.n_store = n_store;
   k.m_count_dev = p->m_count_dev;
   k.m_rows_per_count = p->m_rows_per_count;

@@ -24,7 +24,8 @@ __global__ void pack_nchw_kernel(const float* __restrict__ src, int n, int c, in
                                  int border) {
   const int groups = (c + 7) / 8;
   const int64_t total = (int64_t)n * groups * h * w;
-  const int hp = h + 2 * border, wp = w + 2 * border;
+  const int hp = h + GLASS_BORDER_LO(border) + GLASS_BORDER_HI(border), wp = w + GLASS_BORDER_LO(border) + GLASS_BORDER_HI(border);
+  border = GLASS_BORDER_LO(border);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int x = (int)(i % w);
     int64_t t = i / w;
@@ -54,7 +55,8 @@ __global__ void pack_nchw_kernel(const float* __restrict__ src, int n, int c, in
 __global__ void unpack_nchw_kernel(const __half* __restrict__ shi, const __half* __restrict__ slo,
                                    int n, int c, int h, int w, int cp, int border, float* __restrict__ dst) {
   const int64_t total = (int64_t)n * c * h * w;
-  const int hp = h + 2 * border, wp = w + 2 * border;
+  const int hp = h + GLASS_BORDER_LO(border) + GLASS_BORDER_HI(border), wp = w + GLASS_BORDER_LO(border) + GLASS_BORDER_HI(border);
+  border = GLASS_BORDER_LO(border);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int x = (int)(i % w);
     int64_t t = i / w;
@@ -70,7 +72,8 @@ __global__ void unpack_nchw_kernel(const __half* __restrict__ shi, const __half*
 __global__ void nhwc_f32_to_nchw_kernel(const float* __restrict__ src, int n, int c, int h, int w, int ld,
                                         int border, float* __restrict__ dst) {
   const int64_t total = (int64_t)n * c * h * w;
-  const int hp = h + 2 * border, wp = w + 2 * border;
+  const int hp = h + GLASS_BORDER_LO(border) + GLASS_BORDER_HI(border), wp = w + GLASS_BORDER_LO(border) + GLASS_BORDER_HI(border);
+  border = GLASS_BORDER_LO(border);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int x = (int)(i % w);
     int64_t t = i / w;
@@ -91,7 +94,8 @@ __global__ void gather_taps_kernel(const uint4* __restrict__ shi, const uint4* _
   if (n_dev) n = min(n, max(*n_dev, 0));  // live image / word count left on the device by an earlier kernel
   const int taps = kh * kw;
   const int64_t total = (int64_t)n * ho * wo * taps * cv;
-  const int hp = h + 2 * border, wp = w + 2 * border;
+  const int hp = h + GLASS_BORDER_LO(border) + GLASS_BORDER_HI(border), wp = w + GLASS_BORDER_LO(border) + GLASS_BORDER_HI(border);
+  border = GLASS_BORDER_LO(border);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % cv);
     int64_t t = i / cv;
@@ -184,8 +188,10 @@ __global__ void maxpool_kernel(const uint4* __restrict__ shi, const uint4* __res
                                const int32_t* __restrict__ n_dev) {
   if (n_dev) n = min(n, max(*n_dev, 0));
   const int64_t total = (int64_t)n * ho * wo * cv;
-  const int hp = h + 2 * border, wp = w + 2 * border;
-  const int dhp = ho + 2 * dborder, dwp = wo + 2 * dborder;
+  const int hp = h + GLASS_BORDER_LO(border) + GLASS_BORDER_HI(border), wp = w + GLASS_BORDER_LO(border) + GLASS_BORDER_HI(border);
+  border = GLASS_BORDER_LO(border);
+  const int dhp = ho + GLASS_BORDER_LO(dborder) + GLASS_BORDER_HI(dborder), dwp = wo + GLASS_BORDER_LO(dborder) + GLASS_BORDER_HI(dborder);
+  dborder = GLASS_BORDER_LO(dborder);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % cv);
     const int64_t pix = i / cv;

@@ -77,14 +77,15 @@ __global__ void __launch_bounds__(256) gc_attention_kernel(const GcParams p) {
   float* tvec = hid + GC_HID;           // [512]
   __shared__ float red[2];
   const int word = blockIdx.x;
-  const int hp = p.h + 2 * p.border, wp = p.w + 2 * p.border;
+  const int hp = p.h + GLASS_BORDER_LO(p.border) + GLASS_BORDER_HI(p.border);
+  const int wp = p.w + GLASS_BORDER_LO(p.border) + GLASS_BORDER_HI(p.border);
   const int64_t base = (int64_t)word * hp * wp * GC_C;
   const int tid = threadIdx.x;
 
   // phase 1: mask logits, one position per thread (loops when P > blockDim)
   for (int pos = tid; pos < P; pos += blockDim.x) {
     const int y = pos / p.w, x = pos - y * p.w;
-    const int64_t off = base + ((int64_t)(y + p.border) * wp + x + p.border) * GC_C;
+    const int64_t off = base + ((int64_t)(y + GLASS_BORDER_LO(p.border)) * wp + x + GLASS_BORDER_LO(p.border)) * GC_C;
     float m[GC_HEADS];
 #pragma unroll
     for (int hh = 0; hh < GC_HEADS; ++hh) m[hh] = 0.f;
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(256) gc_attention_kernel(const GcParams p) {
 #pragma unroll 4
     for (int pos = quarter * per; pos < pos_end; ++pos) {
       const int y = pos / p.w, x = pos - y * p.w;
-      const int64_t off = base + ((int64_t)(y + p.border) * wp + x + p.border) * GC_C + f;
+      const int64_t off = base + ((int64_t)(y + GLASS_BORDER_LO(p.border)) * wp + x + GLASS_BORDER_LO(p.border)) * GC_C + f;
       const uint4 a = __ldg(reinterpret_cast<const uint4*>(p.f_hi + off));
       const uint4 b = __ldg(reinterpret_cast<const uint4*>(p.f_lo + off));
       const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(256) gc_attention_kernel(const GcParams p) {
   for (int i = tid; i < P * (GC_C / 8); i += blockDim.x) {
     const int pos = i / (GC_C / 8), f = 8 * (i - pos * (GC_C / 8));
     const int y = pos / p.w, x = pos - y * p.w;
-    const int64_t off = base + ((int64_t)(y + p.border) * wp + x + p.border) * GC_C + f;
+    const int64_t off = base + ((int64_t)(y + GLASS_BORDER_LO(p.border)) * wp + x + GLASS_BORDER_LO(p.border)) * GC_C + f;
     const uint4 a = __ldg(reinterpret_cast<const uint4*>(p.f_hi + off));
     const uint4 b = __ldg(reinterpret_cast<const uint4*>(p.f_lo + off));
     const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
@@ -237,7 +238,8 @@ __global__ void hmean_rows_kernel(const __half* __restrict__ shi, const __half* 
   if (n_dev) n = min(n, max(*n_dev, 0));
   const int cpairs = cp / 2;
   const int64_t total = (int64_t)n * w * cpairs;
-  const int hp = h + 2 * border, wp = w + 2 * border;
+  const int hp = h + GLASS_BORDER_LO(border) + GLASS_BORDER_HI(border), wp = w + GLASS_BORDER_LO(border) + GLASS_BORDER_HI(border);
+  border = GLASS_BORDER_LO(border);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = 2 * (int)(i % cpairs);
     const int64_t t = i / cpairs;

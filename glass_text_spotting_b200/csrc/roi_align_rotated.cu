@@ -496,7 +496,7 @@ extern "C" int glass_roi_align_rotated(const GlassRoiAlignParams* p, void* strea
   k.rois = p->rois; k.n_rois_dev = p->n_rois_dev; k.n_rois = p->n_rois;
   k.ph = p->pooled_h; k.pw = p->pooled_w; k.sampling = p->sampling_ratio;
   k.out_f32 = p->out_f32; k.out_hi = (__half*)p->out_hi; k.out_lo = (__half*)p->out_lo;
-  k.out_hp = p->out_hp; k.out_wp = p->out_wp; k.out_border = p->out_border; k.out_coff = p->out_coff;
+  k.out_hp = p->out_hp; k.out_wp = p->out_wp; k.out_border = GLASS_BORDER_LO(p->out_border); k.out_coff = p->out_coff;
   k.ld_out = p->ld_out;
   const int64_t warps = (int64_t)p->n_rois * p->pooled_h * p->pooled_w;
   int64_t blocks = (warps + 7) / 8;

@@ -48,15 +48,17 @@ class Workspace:
         self._acts: Dict[str, Act] = {}
         self._raw: Dict[str, torch.Tensor] = {}
 
-    def act(self, name: str, n: int, c: int, h: int, w: int, cp: Optional[int] = None, cap: int = 0) -> Act:
+    def act(self, name: str, n: int, c: int, h: int, w: int, cp: Optional[int] = None, cap: int = 0,
+            shared: bool = False) -> Act:
         """Activation buffer ``name`` for n images; allocated (zeroed) once with capacity max(n, cap) images and
-        handed out as a view of the first n, so a varying n (detected words) never re-allocates or re-zeroes."""
+        handed out as a view of the first n, so a varying n (detected words) never re-allocates or re-zeroes.
+        ``shared``: shared-border planes (ops.Act)."""
         a = self._acts.get(name)
         cp = cp if cp is not None else ops.round_up(c, 64)
-        if a is None or (a.c, a.h, a.w, a.cp) != (c, h, w, cp) or a.buf.shape[1] < n:
-            a = Act(max(n, cap), c, h, w, 1, cp, self.device)
+        if a is None or (a.c, a.h, a.w, a.cp, a.shared) != (c, h, w, cp, shared) or a.buf.shape[1] < n + (1 if shared else 0):
+            a = Act(max(n, cap), c, h, w, 1, cp, self.device, shared=shared)
             self._acts[name] = a
-        return a if a.n == n else Act(n, c, h, w, 1, cp, self.device, buf=a.buf)
+        return a if a.n == n else Act(n, c, h, w, 1, cp, self.device, buf=a.buf, shared=shared)
 
     def raw(self, name: str, shape, dtype=torch.float16, zero: bool = False) -> torch.Tensor:
         t = self._raw.get(name)

@@ -17,6 +17,9 @@ from ..structures import ImageList, Instances, RotatedBoxes
 from .backbone import Workspace, _conv_bn
 
 
+SHARED_PLANES = os.environ.get("GLASS_SHARED", "1") != "0"
+
+
 def _bn_fold(sd, prefix):
     return packing.fold_bn(sd[prefix + ".weight"], sd[prefix + ".bias"], sd[prefix + ".running_mean"],
                            sd[prefix + ".running_var"])
@@ -295,21 +298,24 @@ class B200GlassROIHeads:
         ops.conv2d(p2, self.p2p3_conv1, residual=t, res_shift=1, out=g, mode=self.mode)
         return g
 
-    def act(self, name: str, n: int, c: int, h: int, w: int, cp: Optional[int] = None) -> Act:
-        """Recognizer-side activation: capacity = every detection slot of the batch, view of the n live words."""
-        return self.ws.act(name, n, c, h, w, cp=cp, cap=self._word_cap)
+    def act(self, name: str, n: int, c: int, h: int, w: int, cp: Optional[int] = None, shared: bool = False) -> Act:
+        """Recognizer-side activation: capacity = every detection slot of the batch, view of the n live words.
+        ``shared`` = shared-border planes: the small maps of the recognizer's tail (16x33, 8x32, 4x32) pay 16-20 % of their
+        GEMM rows for the zero ring of a fully padded plane, 8-12 % with one shared zero row / column (GLASS_SHARED=0: off)."""
+        return self.ws.act(name, n, c, h, w, cp=cp, cap=self._word_cap, shared=shared and SHARED_PLANES)
 
     def _conv(self, x: Act, w, out: Act, **kw) -> Act:
         return ops.conv2d(x, w, out=out, mode=self.mode, n_dev=self._n_dev, **kw)
 
     def _basic_block(self, x: Act, blk, name: str) -> Act:
-        t = self.act(name + ".t", x.n, blk["conv1"].cout, x.h, x.w)
+        sh = x.shared
+        t = self.act(name + ".t", x.n, blk["conv1"].cout, x.h, x.w, shared=sh)
         self._conv(x, blk["conv1"], t, relu=True)
         res = x
         if blk["down"] is not None:
-            res = self.act(name + ".ds", x.n, blk["down"].cout, x.h, x.w)
+            res = self.act(name + ".ds", x.n, blk["down"].cout, x.h, x.w, shared=sh)
             self._conv(x, blk["down"], res)
-        out = self.act(name + ".out", x.n, blk["conv2"].cout, x.h, x.w)
+        out = self.act(name + ".out", x.n, blk["conv2"].cout, x.h, x.w, shared=sh)
         self._conv(t, blk["conv2"], out, relu=True, residual=res)
         return out
 
@@ -336,7 +342,8 @@ class B200GlassROIHeads:
             for b, blk in enumerate(self.h_layers[1]):
                 x = self._basic_block(x, blk, f"hyb.l2.{b}")
             x = self._conv(x, self.h_conv2, self.act("hyb.c2", k, x.c, x.h, x.w), relu=True)
-            return ops.maxpool2d(x, (2, 2), (2, 1), (0, 1), out=self.act("hyb.pool3", k, x.c, x.h // 2, x.w + 1), n_dev=nd)
+            return ops.maxpool2d(x, (2, 2), (2, 1), (0, 1), out=self.act("hyb.pool3", k, x.c, x.h // 2, x.w + 1, shared=True),
+                                 n_dev=nd)   # from here on: shared-border planes
         if i == 3:
             for b, blk in enumerate(self.h_layers[2][:3]):
                 x = self._basic_block(x, blk, f"hyb.l3.{b}")
@@ -344,7 +351,7 @@ class B200GlassROIHeads:
         if i == 4:
             for b, blk in enumerate(self.h_layers[2][3:], start=3):
                 x = self._basic_block(x, blk, f"hyb.l3.{b}")
-            return self._conv(x, self.h_conv3, self.act("hyb.c3", k, x.c, x.h, x.w), relu=True)
+            return self._conv(x, self.h_conv3, self.act("hyb.c3", k, x.c, x.h, x.w, shared=x.shared), relu=True)
         assert i == 5 and f_out is not None
         for b, blk in enumerate(self.h_layers[3]):
             x = self._basic_block(x, blk, f"hyb.l4.{b}")
@@ -354,7 +361,7 @@ class B200GlassROIHeads:
         g = self.ws.rows("hyb.c41.gather", k * ho * wo, 4 * x.cp, self._word_cap * ho * wo)
         ops.gather_taps(x, 2, 2, 2, 1, 0, 0, ho, wo, out=g, n_dev=nd)
         ops.conv_gemm(g[0], g[1], g.shape[1], g.shape[2], [0], self.h_conv4_1, (k, ho, wo, 0), out_hi=f_out.hi,
-                      out_lo=f_out.lo, out_geom=(f_out.hp, f_out.wp, f_out.border), ld_out=f_out.cp, relu_post=True,
+                      out_lo=f_out.lo, out_geom=(f_out.hp, f_out.wp, f_out.border_code), ld_out=f_out.cp, relu_post=True,
                       mode=self.mode, m_count=None if nd is None else (nd, ho * wo))
         return None
 
@@ -369,9 +376,9 @@ class B200GlassROIHeads:
         """MultiAspectGCAttention (incl. its 3x3 output conv) -> CNN_V1_1 -> BiLSTMBlockV2 from the fused
         [local | global] features.  Returns (fusion_out Act, recog_cnn Act, seq split rows, enc_f32)."""
         ph, pw, cap, nd, m = self.pool_h, self.pool_w, self._word_cap, self._n_dev, self.mode
-        fused2 = self.act("rec.fused2", K, 512, ph, pw)
+        fused2 = self.act("rec.fused2", K, 512, ph, pw, shared=fused.shared)
         ops.gc_attention(fused, fused2, K, self.gc, n_dev=nd)
-        y = self._conv(fused2, self.fusion_out, self.act("rec.fusion_out", K, 256, ph, pw))
+        y = self._conv(fused2, self.fusion_out, self.act("rec.fusion_out", K, 256, ph, pw, shared=fused.shared))
         x2, seq, enc_f32 = self.recognizer_cnn_encoder(y, K)
         return fused2, y, x2, seq, enc_f32
 
@@ -379,9 +386,9 @@ class B200GlassROIHeads:
         """CNN_V1_1 (recognizer_backbone.py:77-81) -> mean over H -> 2 x (BiLSTM + Linear) (recognizer_encoder.py:118-144)."""
         ph, pw, cap, nd, m = self.pool_h, self.pool_w, self._word_cap, self._n_dev, self.mode
         T = pw
-        x1 = self._conv(y, self.r_conv1, self.act("rec.cnn1", K, 256, ph // 2, pw), relu=True,
+        x1 = self._conv(y, self.r_conv1, self.act("rec.cnn1", K, 256, ph // 2, pw, shared=True), relu=True,
                         gather_buf=self.ws.rows("rec.cnn1.gather", K * (ph // 2) * pw, 2 * 256, cap * (ph // 2) * pw))
-        x2 = self._conv(x1, self.r_conv2, self.act("rec.cnn2", K, 256, ph // 2, pw), relu_pre=True, residual=x1)
+        x2 = self._conv(x1, self.r_conv2, self.act("rec.cnn2", K, 256, ph // 2, pw, shared=True), relu_pre=True, residual=x1)
         mc = None if nd is None else (nd, T)
         seq = self.ws.rows("rec.seq0", K * T, 256, cap * T)
         ops.hmean_rows(x2, K, seq, n_dev=nd)
@@ -446,9 +453,9 @@ class B200GlassROIHeads:
             return probs
         ph, pw = self.pool_h, self.pool_w
         g = gmap if gmap is not None else self.p2p3(features)   # (the fused step computes it on a side stream)
-        fused = self.act("rec.fused", K, 512, ph, pw)
+        fused = self.act("rec.fused", K, 512, ph, pw, shared=True)
         ops.roi_align_rotated([g], rois, (ph, pw), [1.0 / self.strides[0]], self.recog_sampling, out_f32=False,
-                              out_split=(fused.buf, fused.hp, fused.wp, fused.border, 256, fused.cp), n_rois_dev=nd)
+                              out_split=(fused.buf, fused.hp, fused.wp, fused.border_code, 256, fused.cp), n_rois_dev=nd)
         crops = self.act("rec.crops", K, 3, ph * 16, pw * 4, cp=8)
         img4 = self.ws.raw("rec.img_nhwc4", (images.shape[0], images.shape[2], images.shape[3], 4), torch.float32)
         ops.image_roi_align_rotated(images, pad_hw, self.pixel_mean, self.pixel_std, rois, (ph * 16, pw * 4),
@@ -457,11 +464,11 @@ class B200GlassROIHeads:
         local_own = fused.to_nchw()[:, :256] if (teacher and "local_feats" in teacher) else None
         if teacher and "local_feats" in teacher:
             t = Act.from_nchw(teacher["local_feats"].to(rois.device))
-            fused.buf[:, :K, 1:-1, 1:-1, :256] = t.buf[:, :, 1:-1, 1:-1, :256]
+            fused.interior()[..., :256] = t.interior()[..., :256]
         fused2, y, x2, seq, enc_f32 = self.fuse_and_encode(fused, K)
         fusion_own = y.to_nchw() if (teacher and "fusion_out" in teacher) else None
         if teacher and "fusion_out" in teacher:
-            y = Act.from_nchw(teacher["fusion_out"].to(rois.device))
+            y = Act.from_nchw(teacher["fusion_out"].to(rois.device), shared=y.shared)
             x2, seq, enc_f32 = self.recognizer_cnn_encoder(y, K)
         logits, alphas, first_eos = self.decode(seq, K, word_start, n_img, probs, taps)
         if taps is not None:

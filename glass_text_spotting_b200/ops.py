@@ -67,27 +67,40 @@ def round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
+BORDER_SHARED = 0x100   # == GLASS_BORDER_SHARED (include/glass_b200.h)
+
+
 class Act:
     """An fp32 activation [n,c,h,w] stored as split-fp16 padded NHWC (see include/glass_b200.h).
 
-    ``buf`` is one fp16 tensor [2, n, h+2b, w+2b, cp]: plane 0 = hi, plane 1 = lo.  Borders and pad
-    channels are zero and are never written by any kernel.
+    ``buf`` is one fp16 tensor [2, n(+1), hp, wp, cp]: plane 0 = hi, plane 1 = lo.  Borders and pad
+    channels are zero and are never written with anything but zeros by any kernel.
+
+    ``shared`` = shared-border planes (GLASS_BORDER_SHARED): only LEADING zero rows / columns, hp = h + border,
+    wp = w + border; a row's right neighbour is the next row's leading zero column and the row below a plane is the next
+    plane's leading zero row, so the buffer carries one more (all-zero) plane after the last image.
     """
 
     def __init__(self, n: int, c: int, h: int, w: int, border: int = 1, cp: Optional[int] = None,
-                 device="cuda", buf: Optional[torch.Tensor] = None):
-        self.n, self.c, self.h, self.w, self.border = n, c, h, w, border
+                 device="cuda", buf: Optional[torch.Tensor] = None, shared: bool = False):
+        self.n, self.c, self.h, self.w, self.border, self.shared = n, c, h, w, border, shared
         self.cp = cp if cp is not None else round_up(c, 64)
         assert self.cp % 8 == 0 and self.cp >= c
-        self.hp, self.wp = h + 2 * border, w + 2 * border
-        shape = (2, n, self.hp, self.wp, self.cp)
+        hi = 0 if shared else border
+        self.hp, self.wp = h + border + hi, w + border + hi
+        shape = (2, n + (1 if shared else 0), self.hp, self.wp, self.cp)
         if buf is None:
             buf = torch.zeros(shape, dtype=torch.float16, device=device)
         else:
             # ``buf`` may have spare capacity along n (Workspace): this Act is then a view of its first n images
-            assert buf.dtype == torch.float16 and buf.is_contiguous() and buf.shape[0] == 2 and buf.shape[1] >= n \
+            assert buf.dtype == torch.float16 and buf.is_contiguous() and buf.shape[0] == 2 and buf.shape[1] >= shape[1] \
                 and tuple(buf.shape[2:]) == shape[2:]
         self.buf = buf
+
+    @property
+    def border_code(self) -> int:
+        """the `border` argument of the C ABI for this activation's planes"""
+        return self.border | (BORDER_SHARED if self.shared else 0)
 
     @property
     def hi(self) -> torch.Tensor:
@@ -101,18 +114,23 @@ class Act:
     def rows(self) -> int:
         return self.n * self.hp * self.wp
 
+    def interior(self) -> torch.Tensor:
+        """[2, n, h, w, cp] view of the pixels (tests)"""
+        b = self.border
+        return self.buf[:, : self.n, b: b + self.h, b: b + self.w]
+
     @staticmethod
-    def from_nchw(x: torch.Tensor, border: int = 1, cp: Optional[int] = None) -> "Act":
+    def from_nchw(x: torch.Tensor, border: int = 1, cp: Optional[int] = None, shared: bool = False) -> "Act":
         n, c, h, w = x.shape
-        a = Act(n, c, h, w, border, cp, x.device)
+        a = Act(n, c, h, w, border, cp, x.device, shared=shared)
         x = x.contiguous().float()
-        _lib.check(_lib.load().glass_pack_nchw(_ptr(x), n, c, h, w, _ptr(a.hi), _ptr(a.lo), a.cp, border, _stream()))
+        _lib.check(_lib.load().glass_pack_nchw(_ptr(x), n, c, h, w, _ptr(a.hi), _ptr(a.lo), a.cp, a.border_code, _stream()))
         return a
 
     def to_nchw(self) -> torch.Tensor:
         out = torch.empty((self.n, self.c, self.h, self.w), dtype=torch.float32, device=self.buf.device)
         _lib.check(_lib.load().glass_unpack_nchw(_ptr(self.hi), _ptr(self.lo), self.n, self.c, self.h, self.w,
-                                                 self.cp, self.border, _ptr(out), _stream()))
+                                                 self.cp, self.border_code, _ptr(out), _stream()))
         return out
 
 
@@ -169,14 +187,14 @@ def conv_gemm(a_hi: torch.Tensor, a_lo: Optional[torch.Tensor], rows_a: int, k_p
     p.relu_pre, p.relu_post = int(relu_pre), int(relu_post)
     if out is not None:
         out_hi, out_lo = out.hi, out.lo
-        out_geom = (out.hp, out.wp, out.border)
+        out_geom = (out.hp, out.wp, out.border_code)
         ld_out = out.cp
     if residual is not None:
         p.res_hi, p.res_lo = _ptr(residual.hi), _ptr(residual.lo)
         if res_geom is not None:   # the residual's memory seen in another row geometry (pixel-grouped rows)
             p.res_hp, p.res_wp, p.res_border, p.res_shift = res_geom[0], res_geom[1], res_geom[2], res_shift
         else:
-            p.res_hp, p.res_wp, p.res_border, p.res_shift = residual.hp, residual.wp, residual.border, res_shift
+            p.res_hp, p.res_wp, p.res_border, p.res_shift = residual.hp, residual.wp, residual.border_code, res_shift
             if ld_out == 0:
                 ld_out = residual.cp
             assert residual.cp == ld_out, "residual and output must share the channel stride"
@@ -197,7 +215,9 @@ def conv_gemm(a_hi: torch.Tensor, a_lo: Optional[torch.Tensor], rows_a: int, k_p
         e0.record(torch.cuda.current_stream())
         _launch_gemm(p)
         e1.record(torch.cuda.current_stream())
-        m_valid = p.m_imgs * (p.m_h - 2 * p.m_border) * (p.m_w - 2 * p.m_border)
+        b_lo = p.m_border & 0xff
+        b_hi = 0 if (p.m_border & BORDER_SHARED) else b_lo
+        m_valid = p.m_imgs * (p.m_h - b_lo - b_hi) * (p.m_w - b_lo - b_hi)
         if valid_pixels is not None:     # pixel-grouped launches: the M space is groups of padded pixels
             m_valid = valid_pixels / getattr(w, "grouped_p", 1)
         # algorithmic FLOPs of this launch + the GEMM's shape (tools/layer_profile.py).  With a device-side M count the
@@ -263,7 +283,7 @@ def conv2d(x: Act, w: PackedWeight, relu: bool = False, residual: Optional[Act] 
     ``relu_pre`` = ReLU before it (CNN_V1_1 order).  ``n_dev``: int32 device scalar = live images / words (x.n is then
     the capacity the launch is sized for)."""
     if getattr(w, "grouped_p", 0):
-        if x.wp % w.grouped_p == 0 and res_shift == 0:
+        if x.wp % w.grouped_p == 0 and res_shift == 0 and not x.shared:
             return _conv2d_grouped(x, w, relu, residual, relu_pre, out, mode, n_dev)
         w = w.fallback
     if getattr(w, "compact_cp", 0):
@@ -274,10 +294,10 @@ def conv2d(x: Act, w: PackedWeight, relu: bool = False, residual: Optional[Act] 
     ho = (x.h + 2 * ph - w.kh) // sh + 1
     wo = (x.w + 2 * pw - w.kw) // sw + 1
     if want_act and out is None:
-        out = Act(x.n, w.cout, ho, wo, 1, w.n_p, x.buf.device)
+        out = Act(x.n, w.cout, ho, wo, 1, w.n_p, x.buf.device, shared=x.shared)
     if out is not None:
         assert (out.n, out.h, out.w, out.cp) == (x.n, ho, wo, w.n_p)
-    geom = (out.hp, out.wp, out.border) if out is not None else (f32.hp, f32.wp, f32.border)
+    geom = (out.hp, out.wp, out.border_code) if out is not None else (f32.hp, f32.wp, f32.border)
     kwargs = dict(out=out, out_f32=None if f32 is None else f32.buf, ld_f32=0 if f32 is None else f32.ld,
                   out_geom=geom, residual=residual, res_shift=res_shift, relu_pre=relu_pre, relu_post=relu,
                   mode=mode)
@@ -285,7 +305,9 @@ def conv2d(x: Act, w: PackedWeight, relu: bool = False, residual: Optional[Act] 
             and x.border >= ph and x.border >= pw)
     if flat:
         shifts = [(r - ph) * x.wp + (s - pw) for r in range(w.kh) for s in range(w.kw)]
-        conv_gemm(x.hi, x.lo, x.rows, x.cp, shifts, w, (x.n, x.hp, x.wp, x.border),
+        if out is not None:
+            assert out.shared == x.shared, "a flat conv keeps its input's plane geometry"
+        conv_gemm(x.hi, x.lo, x.rows, x.cp, shifts, w, (x.n, x.hp, x.wp, x.border_code),
                   m_count=None if n_dev is None else (n_dev, x.hp * x.wp), **kwargs)
     else:
         taps = w.kh * w.kw
@@ -301,7 +323,7 @@ def _conv2d_compact(x: Act, w: PackedWeight, relu, residual, res_shift, relu_pre
     """stride-1 'same' 1x1 / 3x3 conv on a narrow activation (cp = 8/16/32): a 64-wide k-block spans 64/cp
     consecutive pixels, so the three s-taps of a row are read by one (cp <= 16) or two (cp = 32) TMA boxes."""
     cp = w.compact_cp
-    assert x.cp == cp and w.stride == (1, 1) and x.border >= w.pad[0] and (w.kh, w.kw) in ((1, 1), (3, 3))
+    assert x.cp == cp and w.stride == (1, 1) and x.border >= w.pad[0] and (w.kh, w.kw) in ((1, 1), (3, 3)) and not x.shared
     ppk = 64 // cp
     nj = (w.kw + ppk - 1) // ppk
     shifts = [(r - w.pad[0]) * x.wp - w.pad[1] + j * ppk for r in range(w.kh) for j in range(nj)]
@@ -319,7 +341,7 @@ def _conv2d_grouped(x: Act, w: PackedWeight, relu, residual, relu_pre, out, mode
     row, then the border of the output (which the all-valid M space overwrites) is re-zeroed.  A residual of the output's
     own geometry is read through the same grouped row view (its zero border adds nothing to the rows re-zeroed anyway)."""
     P, cp = w.grouped_p, w.grouped_cp
-    assert x.cp == cp and x.border == 1 and x.wp % P == 0 and x.rows % P == 0, (x.cp, cp, x.wp, P)
+    assert x.cp == cp and x.border == 1 and not x.shared and x.wp % P == 0 and x.rows % P == 0, (x.cp, cp, x.wp, P)
     if out is None:
         out = Act(x.n, w.cout, x.h, x.w, 1, w.grouped_cout_p, x.buf.device)
     assert (out.n, out.h, out.w, out.cp, out.border) == (x.n, x.h, x.w, w.grouped_cout_p, 1)
@@ -367,10 +389,10 @@ def maxpool2d(x: Act, k: Tuple[int, int], s: Tuple[int, int], p: Tuple[int, int]
     ho = (x.h + 2 * p[0] - k[0]) // s[0] + 1
     wo = (x.w + 2 * p[1] - k[1]) // s[1] + 1
     if out is None:
-        out = Act(x.n, x.c, ho, wo, 1, x.cp, x.buf.device)
+        out = Act(x.n, x.c, ho, wo, 1, x.cp, x.buf.device, shared=x.shared)
     assert (out.n, out.h, out.w, out.cp) == (x.n, ho, wo, x.cp)
-    _lib.check(_lib.load().glass_maxpool(_ptr(x.hi), _ptr(x.lo), x.n, x.h, x.w, x.cp, x.border, k[0], k[1], s[0],
-                                         s[1], p[0], p[1], ho, wo, _ptr(out.hi), _ptr(out.lo), out.border,
+    _lib.check(_lib.load().glass_maxpool(_ptr(x.hi), _ptr(x.lo), x.n, x.h, x.w, x.cp, x.border_code, k[0], k[1], s[0],
+                                         s[1], p[0], p[1], ho, wo, _ptr(out.hi), _ptr(out.lo), out.border_code,
                                          _ptr(n_dev), _stream()))
     return out
 
@@ -381,7 +403,7 @@ def gather_taps(x: Act, kh: int, kw: int, sh: int, sw: int, ph: int, pw: int, ho
     if out is None:
         out = torch.empty((2, x.n * ho * wo, kh * kw * x.cp), dtype=torch.float16, device=x.buf.device)
     assert tuple(out.shape) == (2, x.n * ho * wo, kh * kw * x.cp) and out[0].is_contiguous()
-    _lib.check(_lib.load().glass_gather_taps(_ptr(x.hi), _ptr(x.lo), x.n, x.h, x.w, x.cp, x.border, kh, kw, sh, sw,
+    _lib.check(_lib.load().glass_gather_taps(_ptr(x.hi), _ptr(x.lo), x.n, x.h, x.w, x.cp, x.border_code, kh, kw, sh, sw,
                                              ph, pw, ho, wo, _ptr(out[0]), _ptr(out[1]), _ptr(n_dev), _stream()))
     return out
 
@@ -531,10 +553,10 @@ def box_decode(pred: torch.Tensor, proposals: torch.Tensor, counts: Optional[tor
 def gc_attention(f: Act, y: Act, n_words: int, w, n_dev: Optional[torch.Tensor] = None) -> None:
     """MultiAspectGCAttention pooling + channel_add MLP + broadcast add (concat channel order); w: dict of
     fp32 device tensors w_mask[512], b_mask(float), w1t[512,256], b1, ln_g, ln_b, w2t[256,512], b2."""
-    assert f.cp == 512 and y.cp == 512 and (f.h, f.w, f.border) == (y.h, y.w, y.border)
+    assert f.cp == 512 and y.cp == 512 and (f.h, f.w, f.border_code) == (y.h, y.w, y.border_code)
     p = _lib.GcAttentionParams()
     p.f_hi, p.f_lo, p.y_hi, p.y_lo = _ptr(f.hi), _ptr(f.lo), _ptr(y.hi), _ptr(y.lo)
-    p.n_words, p.h, p.w, p.border, p.channels = n_words, f.h, f.w, f.border, 512
+    p.n_words, p.h, p.w, p.border, p.channels = n_words, f.h, f.w, f.border_code, 512
     p.w_mask, p.b_mask = _ptr(w["w_mask"]), float(w["b_mask"])
     p.w1t, p.b1, p.ln_g, p.ln_b, p.w2t, p.b2 = (_ptr(w[k]) for k in ("w1t", "b1", "ln_g", "ln_b", "w2t", "b2"))
     p.n_words_dev = _ptr(n_dev)
@@ -545,7 +567,7 @@ def hmean_rows(x: Act, n: int, out: torch.Tensor, out_f32: Optional[torch.Tensor
                n_dev: Optional[torch.Tensor] = None) -> None:
     """mean over H: x [n,c,h,w] -> rows out [2, n*w, cp]."""
     assert tuple(out.shape) == (2, n * x.w, x.cp)
-    _lib.check(_lib.load().glass_hmean_rows(_ptr(x.hi), _ptr(x.lo), n, x.h, x.w, x.cp, x.border, _ptr(out[0]),
+    _lib.check(_lib.load().glass_hmean_rows(_ptr(x.hi), _ptr(x.lo), n, x.h, x.w, x.cp, x.border_code, _ptr(out[0]),
                                             _ptr(out[1]), _ptr(out_f32), _ptr(n_dev), _stream()))
 
 

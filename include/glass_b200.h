@@ -30,6 +30,11 @@
 extern "C" {
 #endif
 
+/* Shared-border planes: OR this flag into any `border` argument.  A plane [h, w] is then laid out [h + b, w + b] with
+ * only LEADING zero rows / columns: in the flattened pixel order the right neighbour of a row's last pixel is the next
+ * row's leading zero column, and the row below a plane's last row is the next plane's leading zero row (the caller keeps
+ * one more zero plane after the last).  A 16 x 33 map then costs 17 x 34 = 578 GEMM rows instead of 18 x 35 = 630. */
+#define GLASS_BORDER_SHARED 0x100
 #define GLASS_MAX_TAPS 16
 #define GLASS_MAX_LEVELS 5
 

@@ -206,6 +206,41 @@ def test_conv_gemm_pixel_pairs_64_channels(ops, res):
     _close(o3.to_nchw(), F.relu(F.conv2d(x3, wt, padding=1) * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)), "fallback")
 
 
+@pytest.mark.parametrize("hw", [(16, 33), (8, 32), (5, 7)])
+def test_shared_border_planes_equal_padded_planes(ops, hw):
+    """Shared-border planes (GLASS_BORDER_SHARED: one leading zero row / column per plane, the next row / plane provides
+    the trailing one) give the same bits as fully padded planes through every kernel that addresses a plane: pack / unpack,
+    3x3 conv (+ residual, both epilogues), max-pool, tap gather, GC attention, H-mean."""
+    from glass_text_spotting_b200 import packing
+    g = torch.Generator().manual_seed(hw[0] * 100 + hw[1])
+    n = 5
+    x = torch.randn(n, 256, *hw, generator=g)
+    r = torch.randn(n, 256, *hw, generator=g)
+    w = packing.pack_conv(torch.randn(256, 256, 3, 3, generator=g) * 0.02, torch.rand(256, generator=g) + 0.5,
+                          torch.randn(256, generator=g), (1, 1), (1, 1))
+    outs = {}
+    for shared in (False, True):
+        a, ra = ops.Act.from_nchw(x.cuda(), shared=shared), ops.Act.from_nchw(r.cuda(), shared=shared)
+        assert torch.equal(a.to_nchw().cpu(), ops.Act.from_nchw(x.cuda()).to_nchw().cpu())
+        y = ops.conv2d(a, w, relu=True, residual=ra)
+        assert y.shared == shared
+        res = [y.to_nchw()]
+        b = y.border
+        assert y.buf[:, :, :b].abs().max().item() == 0 and y.buf[:, :, :, :b].abs().max().item() == 0   # leading borders
+        if shared:
+            assert y.buf[:, n].abs().max().item() == 0                                                  # the extra plane
+        if hw[0] % 2 == 0:
+            res.append(ops.maxpool2d(y, (2, 2), (2, 1), (0, 1)).to_nchw())
+            gt = ops.gather_taps(y, 2, 2, 2, 1, 0, 0, (hw[0] - 2) // 2 + 1, hw[1] - 1)
+            res.append(gt.clone())
+        seq = torch.empty((2, n * hw[1], 256), dtype=torch.float16, device="cuda")
+        ops.hmean_rows(y, n, seq)
+        res.append(seq)
+        outs[shared] = res
+    for u, v in zip(outs[False], outs[True]):
+        assert torch.equal(u, v)
+
+
 def test_conv_gemm_fast_mode_is_fp16_grade(ops):
     from glass_text_spotting_b200 import packing
     g = torch.Generator().manual_seed(5)
