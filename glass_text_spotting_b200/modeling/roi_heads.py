@@ -337,11 +337,12 @@ class B200GlassROIHeads:
             for b, blk in enumerate(self.h_layers[0]):
                 x = self._basic_block(x, blk, f"hyb.l1.{b}")
             x = self._conv(x, self.h_conv1, self.act("hyb.c1", k, x.c, x.h, x.w), relu=True)
-            return ops.maxpool2d(x, (2, 2), (2, 2), (0, 0), out=self.act("hyb.pool2", k, x.c, x.h // 2, x.w // 2), n_dev=nd)
+            return ops.maxpool2d(x, (2, 2), (2, 2), (0, 0), out=self.act("hyb.pool2", k, x.c, x.h // 2, x.w // 2, shared=True),
+                                 n_dev=nd)   # from here on: shared-border planes (32x32: 1089 GEMM rows instead of 1156)
         if i == 2:
             for b, blk in enumerate(self.h_layers[1]):
                 x = self._basic_block(x, blk, f"hyb.l2.{b}")
-            x = self._conv(x, self.h_conv2, self.act("hyb.c2", k, x.c, x.h, x.w), relu=True)
+            x = self._conv(x, self.h_conv2, self.act("hyb.c2", k, x.c, x.h, x.w, shared=x.shared), relu=True)
             return ops.maxpool2d(x, (2, 2), (2, 1), (0, 1), out=self.act("hyb.pool3", k, x.c, x.h // 2, x.w + 1, shared=True),
                                  n_dev=nd)   # from here on: shared-border planes
         if i == 3:

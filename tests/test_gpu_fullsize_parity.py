@@ -157,8 +157,8 @@ def test_a12_local_cnn_stagewise(gate):
     cps = [8, 32, 64, 128, 256, 256]
     fused = ops.Act(k, 512, 8, 32, shared=True)
     for i in range(heads.HYBRID_STAGES):
-        # (from the third max-pool on the activations live in shared-border planes, like in the model)
-        y = heads.hybrid_stage(i, ops.Act.from_nchw(ins[i].cuda(), cp=cps[i], shared=(i >= 3)), fused)
+        # (from the second max-pool on the activations live in shared-border planes, like in the model)
+        y = heads.hybrid_stage(i, ops.Act.from_nchw(ins[i].cuda(), cp=cps[i], shared=(i >= 2)), fused)
         got = fused.to_nchw()[:, :256] if i == 5 else y.to_nchw()
         close(got, outs[i], f"cfg0 local CNN piece {i} | oracle input")
 
