@@ -290,7 +290,7 @@ constexpr int LC_U = LSTM_H / LC_R;      // hidden units per CTA (32)
 constexpr int LC_N = 4 * LC_U;           // gate rows per CTA (128)
 constexpr int LC_W = 64;                 // words per cluster
 constexpr int LC_LD = LSTM_H + 8;        // shared-memory row stride in halfs: 528 B, conflict-free for ldmatrix
-constexpr int LC_THREADS = 256;          // 8 warps: warp w owns gate columns [16w, 16w + 16) = 4 hidden units
+constexpr int LC_THREADS = 512;          // 16 warps: column group w & 7 owns gate columns [16w, 16w + 16) = 4 hidden units; w >> 3 = word half
 constexpr float LC_SW = 64.f;            // power-of-two pre-scales of the fp16 split (weights, h)
 constexpr float LC_SH = 1024.f;
 constexpr int LC_SLD = LC_U + 8;         // row stride of the local slice stage in halfs (80 B: conflict-free 16-byte rows)
@@ -339,7 +339,9 @@ __global__ void __cluster_dims__(LC_R, 1, 1) __launch_bounds__(LC_THREADS, 1)
   const int rank = (int)cluster.block_rank();
   const int dir = blockIdx.y;
   const int seq0 = (blockIdx.x / LC_R) * LC_W;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+  const int tid = threadIdx.x, lane = tid & 31, g = lane >> 2, q = lane & 3;
+  // 16 warps: warp = column group (16 gate columns = 4 hidden units), mh = which half of the 64 words (m-tiles 2 mh, 2 mh + 1)
+  const int warp = (tid >> 5) & 7, mh = tid >> 8;
   const float* wt = whh_t + (int64_t)dir * LSTM_H * LSTM_G;   // [k][gate row]
 
   // column n of this CTA: warp n/16, 8-wide tile (n%16)/8, column c = n%8 inside it -> gate = 2*tile + (c&1),
@@ -360,20 +362,20 @@ __global__ void __cluster_dims__(LC_R, 1, 1) __launch_bounds__(LC_THREADS, 1)
 
   const int unit = rank * LC_U + 4 * warp + q;                 // the hidden unit this thread updates
   const float kScale = LC_SW * LC_SH, kInv = 1.0f / (LC_SW * LC_SH);
-  float cst[4][2];                                             // cell state of (word = 16i + g + 8e, unit)
-  float gnext[4][2][4];                                        // next step's input-projection gates (i, f, g, o)
+  float cst[2][2];                                             // cell state of (word = 16 (2 mh + i) + g + 8e, unit)
+  float gnext[2][2][4];                                        // next step's input-projection gates (i, f, g, o)
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
     for (int e = 0; e < 2; ++e) cst[i][e] = 0.f;
 
   auto load_gates = [&](int step) {
     const int t = dir == 0 ? step : T - 1 - step;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int word = seq0 + 16 * i + g + 8 * e;
+        const int word = seq0 + 16 * (2 * mh + i) + g + 8 * e;
         const float* base = gates_in + ((int64_t)word * T + t) * (2 * LSTM_G) + dir * LSTM_G + unit;
 #pragma unroll
         for (int gt = 0; gt < 4; ++gt) gnext[i][e][gt] = word < n_seq ? __ldg(base + gt * LSTM_H) : 0.f;
@@ -383,9 +385,9 @@ __global__ void __cluster_dims__(LC_R, 1, 1) __launch_bounds__(LC_THREADS, 1)
 
   for (int step = 0; step < T; ++step) {
     const int t = dir == 0 ? step : T - 1 - step;
-    float acc[4][2][4];   // [m-tile i][n-tile][d0..d3]: d0/d1 = word 16i+g, columns 2q / 2q+1; d2/d3 = word 16i+g+8
+    float acc[2][2][4];   // [m-tile 2 mh + i][n-tile][d0..d3]: d0/d1 = word 16 m + g, columns 2q / 2q+1; d2/d3 = word + 8
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         acc[i][0][2 * e + 0] = gnext[i][e][0] * kScale;   // i
@@ -402,9 +404,9 @@ __global__ void __cluster_dims__(LC_R, 1, 1) __launch_bounds__(LC_THREADS, 1)
       lc_ldsm_x4(bh, w_hi + brow * LC_LD + bcol);
       lc_ldsm_x4(bl, w_lo + brow * LC_LD + bcol);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 2; ++i) {
         uint32_t ah[4], al[4];
-        const int aoff = (16 * i + (lane & 15)) * LC_LD + k0 + (lane >> 4) * 8;
+        const int aoff = (16 * (2 * mh + i) + (lane & 15)) * LC_LD + k0 + (lane >> 4) * 8;
         lc_ldsm_x4(ah, h_hi + aoff);
         lc_ldsm_x4(al, h_lo + aoff);
         lc_mma(acc[i][0], ah, bh[0], bh[1]);
@@ -417,9 +419,9 @@ __global__ void __cluster_dims__(LC_R, 1, 1) __launch_bounds__(LC_THREADS, 1)
     }
     cluster.barrier_arrive();   // this CTA has finished reading h_{t-1}
 
-    float hn[4][2];
+    float hn[2][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const float ig = sigmoidf_(acc[i][0][2 * e + 0] * kInv), fg = sigmoidf_(acc[i][0][2 * e + 1] * kInv);
@@ -436,14 +438,14 @@ __global__ void __cluster_dims__(LC_R, 1, 1) __launch_bounds__(LC_THREADS, 1)
     // 43 % of the kernel's stall samples there.)
     const int kcol = rank * LC_U + 4 * warp;   // the quad (q = 0..3) holds units kcol .. kcol + 3 of the same 8 words
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         float v[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[j] = __shfl_sync(0xffffffffu, hn[i][e], (lane & ~3) + j);
-        const int wrow = 16 * i + g + 8 * e;
-        if (q == (i & 3)) {                      // one lane of the quad stages the quad's 4 units of this word ...
+        const int wrow = 16 * (2 * mh + i) + g + 8 * e;
+        if (q == 2 * i + e) {                      // one lane of the quad stages the quad's 4 units of this word ...
           __half hh[4], hl[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) lc_split(v[j], LC_SH, hh[j], hl[j]);
@@ -465,11 +467,11 @@ __global__ void __cluster_dims__(LC_R, 1, 1) __launch_bounds__(LC_THREADS, 1)
     __syncthreads();            // the local slice is complete
     cluster.barrier_wait();     // every CTA of the cluster has finished reading h_{t-1}: it may be overwritten
     {
-      // warp w -> peer w: 64 rows x (4 chunks of 8 units) x 2 planes = 512 chunks of 16 bytes, 16 per lane
+      // warps (w, mh) -> peer w, plane mh: 64 rows x 4 chunks of 8 units = 256 chunks of 16 bytes, 8 per lane
       const uint32_t peer = (uint32_t)warp;
 #pragma unroll 4
-      for (int c = lane; c < 2 * LC_W * 4; c += 32) {
-        const int plane = c >> 8, row = (c & 255) >> 2, ch = c & 3;
+      for (int c = lane; c < LC_W * 4; c += 32) {
+        const int plane = mh, row = c >> 2, ch = c & 3;
         const __half* src = (plane ? s_lo : s_hi) + row * LC_SLD + ch * 8;
         __half* dst = (plane ? h_lo : h_hi) + row * LC_LD + rank * LC_U + ch * 8;
         const uint4 v = *reinterpret_cast<const uint4*>(src);
