@@ -240,6 +240,12 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t smem_src
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // the source shared memory of every committed store has been READ (it may be overwritten)
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... of all but the newest `pending` committed groups (pending in 0..2)
+__device__ __forceinline__ void tma_store_wait_read_but(int pending) {
+  if (pending <= 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  else if (pending == 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+  else asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+}
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // generic-proxy writes to shared memory become visible to the async proxy (TMA)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

@@ -37,6 +37,8 @@ static constexpr int EPI_WARPS = 16;
 static constexpr int NUM_THREADS = 128 + 32 * EPI_WARPS;  // 4 control warps + 16 epilogue warps
 static constexpr int MAX_STAGES = 12;
 static constexpr int EPI_STAGE_BYTES = EPI_WARPS * 2048;  // per epilogue warp: 32 rows x 16 fp32 columns
+static constexpr int EPI_BOX_BYTES = 2 * BM * BK * 2;      // TMA epilogue: one pair (hi, lo) of 128-row x 64-column boxes
+static constexpr int MAX_EPI_BOXES = 3;
 static constexpr int MAX_CHUNKS_PER_WARP = 4;  // 256 columns / 16 per chunk / 4 column parts
 
 struct GemmKernelParams {
@@ -74,6 +76,10 @@ struct GemmKernelParams {
   int32_t m_rows_per_count;
   int32_t* sat_count;  // debug: counts outputs beyond the split-fp16 storage range (|16 y| > 60000), or nullptr
   int32_t tma_res;  // TMA epilogue: the residual tile is TMA-loaded into the staging boxes (same geometry as the output)
+  // TMA epilogue: a ring of epi_boxes pairs of staging boxes (32 KB each; epi_bytes in all).  One pair serialises
+  // residual load -> arithmetic -> store read per 64-column part (HBM latency exposed: the K <= 256 layers with a residual
+  // ran at 0.55-0.6 of the copy bandwidth); with three, two residual loads and a store are in flight behind the arithmetic.
+  int32_t epi_boxes, epi_bytes;
 };
 
 // PAIR = true: two CTAs of a cluster (one TPC) cooperate through tcgen05 cta_group::2 -- an M = 256 tile pair
@@ -96,7 +102,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   // carve: [stages x (A_hi, A_lo?, B_hi, B_lo?)] then barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* stage_base = reinterpret_cast<float*>(smem + (size_t)p.ring_bytes);  // epilogue staging, 2 KB per warp
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.ring_bytes + EPI_STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.ring_bytes + (size_t)p.epi_bytes);
   uint64_t* full_bar = bars;                      // [MAX_STAGES]
   uint64_t* empty_bar = bars + MAX_STAGES;        // [MAX_STAGES]
   uint64_t* tmem_full_bar = bars + 2 * MAX_STAGES;   // [MAX_ACC_BUFS]
@@ -104,7 +110,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   uint64_t* a_full_bar = bars + 2 * MAX_STAGES + 2 * MAX_ACC_BUFS;                  // [MAX_A_STAGES]
   uint64_t* a_empty_bar = bars + 2 * MAX_STAGES + 2 * MAX_ACC_BUFS + MAX_A_STAGES;  // [MAX_A_STAGES]
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 2 * MAX_ACC_BUFS + 2 * MAX_A_STAGES);
-  uint64_t* res_bar = bars + 2 * MAX_STAGES + 2 * MAX_ACC_BUFS + 2 * MAX_A_STAGES + 1;   // TMA epilogue: residual boxes landed
+  uint64_t* res_bar = bars + 2 * MAX_STAGES + 2 * MAX_ACC_BUFS + 2 * MAX_A_STAGES + 1;   // [MAX_EPI_BOXES] residual boxes landed
 
   // Programmatic dependent launch: let the next kernel of the stream start its prologue as soon as SMs free up
   // (it blocks at its own griddepcontrol.wait until this grid has completed and flushed).
@@ -149,7 +155,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       mbar_init(&tmem_full_bar[i], 1);
       mbar_init(&tmem_empty_bar[i], PAIR ? 2 * EPI_WARPS : EPI_WARPS);  // one arrive per epilogue warp (of both CTAs)
     }
-    mbar_init(res_bar, 1);
+    for (int i = 0; i < MAX_EPI_BOXES; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -366,8 +372,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     if constexpr (TMAEPI) {
       // ===================================================== epilogue through TMA (16 warps)
       // warp e = warp-4: TMEM lane quadrant q = e & 3 -> tile rows 32q..32q+31 (one per lane); sub = e >> 2 -> the
-      // 16-column chunk `sub` of every 64-column PART of the tile.  The tile is finished part by part through ONE pair
-      // of staging boxes (hi / lo, 16 KB each, the 32 KB the classic epilogue uses as its transpose stage).
+      // 16-column chunk `sub` of every 64-column PART of the tile.  The tile is finished part by part through a ring
+      // of p.epi_boxes pairs of staging boxes (hi / lo, 16 KB each; one pair = the 32 KB the classic epilogue uses as
+      // its transpose stage).
       const int e = warp - 4;
       const int q = e & 3;
       const int sub = e >> 2;
@@ -376,25 +383,42 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       const int parts = p.bn >> 6;
       const bool has_res = p.tma_res != 0;
       const bool issuer = threadIdx.x == 128;   // warp 4, lane 0: issues the TMA stores / residual loads
-      const uint32_t box_hi = smem_u32(stage_base), box_lo = box_hi + 16384u;
+      const uint32_t boxes = smem_u32(stage_base);   // ring of p.epi_boxes pairs: hi box at + 32 KB * b, lo box 16 KB behind it
       // this thread's two 16-byte chunks of its 128-byte box row (SWIZZLE_128B: chunk index ^ (row & 7))
       const uint32_t row_off = (uint32_t)row_in_tile * 128u;
       const uint32_t off0 = row_off + (uint32_t)(((2 * sub) ^ (lane & 7)) << 4);
       const uint32_t off1 = row_off + (uint32_t)(((2 * sub + 1) ^ (lane & 7)) << 4);
       const int chunks_per_tile = (kblocks + p.kb_per_chunk - 1) / p.kb_per_chunk;
-      uint32_t chunk = 0, res_phase = 0;
+      uint32_t chunk = 0;
+      const int nb = p.epi_boxes;
+      const int ahead = nb > 1 ? nb - 1 : 1;   // residual loads run `ahead` parts in front of the arithmetic
+      int box = 0;                             // ring position of the current part
+      uint32_t box_phase = 0;                  // parity of res_bar[box] for the current lap
       auto unit_origin = [&](int unit, int& m0, int& n0) {
         const int um = unit / p.tiles_n;
         const int tn = unit - um * p.tiles_n;
         m0 = (PAIR ? um * 2 + (int)rank : um) * BM;
         n0 = tn * p.bn;
       };
-      if (has_res && issuer && worker < num_units) {   // the first tile's first residual part: no dependence on the MMA
-        int m0, n0;
-        unit_origin(worker, m0, n0);
-        mbar_arrive_expect_tx(res_bar, 32768u);
-        tma_load_2d(stage_base, &map_r_hi, res_bar, n0, m0);
-        tma_load_2d(reinterpret_cast<uint8_t*>(stage_base) + 16384, &map_r_lo, res_bar, n0, m0);
+      // issuer only: the part the next residual load is for, and the box it goes to
+      int la_unit = worker, la_pt = 0, la_box = 0;
+      auto res_load_next = [&]() {
+        if (la_unit < num_units) {
+          int rm0, rn0;
+          unit_origin(la_unit, rm0, rn0);
+          uint8_t* dst = reinterpret_cast<uint8_t*>(stage_base) + (size_t)la_box * EPI_BOX_BYTES;
+          mbar_arrive_expect_tx(&res_bar[la_box], (uint32_t)EPI_BOX_BYTES);
+          tma_load_2d(dst, &map_r_hi, &res_bar[la_box], rn0 + la_pt * 64, rm0);
+          tma_load_2d(dst + EPI_BOX_BYTES / 2, &map_r_lo, &res_bar[la_box], rn0 + la_pt * 64, rm0);
+        }
+        if (++la_pt == parts) {
+          la_pt = 0;
+          la_unit += num_workers;
+        }
+        if (++la_box == nb) la_box = 0;
+      };
+      if (has_res && issuer) {   // the first parts' residuals: no dependence on the MMA
+        for (int i = 0; i < ahead; ++i) res_load_next();
       }
       for (int unit = worker; unit < num_units; unit += num_workers) {
         int m0, n0;
@@ -465,9 +489,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
             }
+            const uint32_t box_hi = boxes + (uint32_t)box * (uint32_t)EPI_BOX_BYTES, box_lo = box_hi + (uint32_t)(EPI_BOX_BYTES / 2);
             if (has_res) {
-              mbar_wait(res_bar, res_phase);   // this part's residual boxes have landed in the staging boxes
-              res_phase ^= 1u;
+              mbar_wait(&res_bar[box], box_phase);   // this part's residual has landed in its pair of boxes
               const uint4 rh0 = lds_u4(box_hi + off0), rh1 = lds_u4(box_hi + off1);
               const uint4 rl0 = lds_u4(box_lo + off0), rl1 = lds_u4(box_lo + off1);
               const uint32_t aw[8] = {rh0.x, rh0.y, rh0.z, rh0.w, rh1.x, rh1.y, rh1.z, rh1.w};
@@ -493,9 +517,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
 #pragma unroll
             for (int j = 0; j < 8; ++j)   // border rows / rows past the M extent: zeros
               split16x2_scaled(valid ? v[2 * j] : 0.f, valid ? v[2 * j + 1] : 0.f, hw[j], lw[j]);
-            if (!has_res) {
-              // boxes free?  (the issuer waits for the previous part's stores to have READ them only now, after this
-              // part's math: the store's shared-memory reads overlap the arithmetic)
+            if (!has_res && nb == 1) {
+              // single pair, no residual: the boxes are free once the previous part's stores have READ them (the issuer
+              // waits only now, after this part's math: the store's shared-memory reads overlap the arithmetic)
               if (issuer) tma_store_wait_read();
               named_bar_sync(2, 32 * EPI_WARPS);
             }
@@ -504,27 +528,25 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             sts_u4(box_lo + off0, make_uint4(lw[0], lw[1], lw[2], lw[3]));
             sts_u4(box_lo + off1, make_uint4(lw[4], lw[5], lw[6], lw[7]));
             fence_proxy_async_smem();
-            named_bar_sync(1, 32 * EPI_WARPS);   // the boxes are complete
+            // ring without residual: the NEXT part's pair was last read by the store nb - 1 parts back; the issuer makes
+            // sure of that before it joins the barrier, so passing the barrier also means "the next pair is free"
+            if (!has_res && nb > 1 && issuer) tma_store_wait_read_but(nb - 2);
+            named_bar_sync(1, 32 * EPI_WARPS);   // this pair of boxes is complete
             if (issuer) {
               tma_store_2d(&map_o_hi, box_hi, n0 + pt * 64, m0);
               tma_store_2d(&map_o_lo, box_lo, n0 + pt * 64, m0);
               tma_store_commit();
               if (has_res) {
-                // the next residual part goes into the same boxes as soon as the stores have read them; the other
-                // threads cannot touch the boxes before it has landed (they wait on res_bar), so no second barrier
-                tma_store_wait_read();
-                int rm0 = m0, rn0 = n0 + (pt + 1) * 64;
-                bool more = pt + 1 < parts;
-                if (!more && unit + num_workers < num_units) {   // first part of this CTA's next tile
-                  unit_origin(unit + num_workers, rm0, rn0);
-                  more = true;
-                }
-                if (more) {
-                  mbar_arrive_expect_tx(res_bar, 32768u);
-                  tma_load_2d(stage_base, &map_r_hi, res_bar, rn0, rm0);
-                  tma_load_2d(reinterpret_cast<uint8_t*>(stage_base) + 16384, &map_r_lo, res_bar, rn0, rm0);
-                }
+                // the residual `ahead` parts on goes into the pair the PREVIOUS part's stores are reading (this part's
+                // own pair when the ring has one); the other threads cannot touch a pair before its residual has landed
+                // (they wait on res_bar), so no second barrier
+                tma_store_wait_read_but(nb > 1 ? 1 : 0);
+                res_load_next();
               }
+            }
+            if (++box == nb) {
+              box = 0;
+              box_phase ^= 1u;
             }
           }
         }
@@ -758,6 +780,15 @@ static int build_plan(const GlassConvGemmParams* p, GlassGemmPlan* plan) {
     GLASS_CHECK(p->n % 128 == 0, "n > 256 must be a multiple of 128");
     bn = (p->n % 256 == 0) ? 256 : 128;
   }
+  {   // A/B knob: 128-wide tiles for the 1x1 layers with lo..hi k-blocks ("GLASS_BN128_KB=lo,hi")
+    static const char* e = getenv("GLASS_BN128_KB");
+    if (e != nullptr && bn == 256 && p->ntaps == 1) {
+      int lo = 0, hi = -1;
+      sscanf(e, "%d,%d", &lo, &hi);
+      const int kb = p->k_per_tap / BK;
+      if (kb >= lo && kb <= hi) bn = 128;
+    }
+  }
   const int64_t rows_m = (int64_t)p->m_imgs * p->m_h * p->m_w;
   // Small-M GEMMs (the box head's FCs: 400 rows x 2048 columns x K = 12544; the RPN head on p5 / p6) would occupy a
   // fraction of the 148 SMs with 256-wide tiles, and each of those CTAs is bound by its own TMA feed: narrower tiles
@@ -820,9 +851,35 @@ static int build_plan(const GlassConvGemmParams* p, GlassGemmPlan* plan) {
     GLASS_CHECK(p->rows_a > BK / a_ld, "too few rows for compact mode");
     a_rows = (uint64_t)p->rows_a - (uint64_t)(BK / a_ld) + 1;
   }
-  // tap-row mode for 3x3 'same' convs (taps ordered (r, s), s-taps = consecutive rows): one 136-row block per tap row
+  // TMA epilogue: flat layers only -- the output (and residual) plane IS the M space, so tile rows are contiguous
+  // tensor rows and one 2-D box per 64 columns covers them
+  static const int tma_env = getenv("GLASS_TMA_EPI") ? atoi(getenv("GLASS_TMA_EPI")) : 1;
+  const bool flat_out = split && p->out_hi && p->out_lo && !p->out_f32 && p->out_hp == p->m_h && p->out_wp == p->m_w &&
+                        p->out_border == p->m_border && n_store == p->n && bn % 64 == 0 && p->ld_out >= p->n;
+  const bool flat_res = !p->res_hi || (p->res_shift == 0 && p->res_hp == p->m_h && p->res_wp == p->m_w &&
+                                       p->res_border == p->m_border);
+  bool tma_epi = flat_out && flat_res && tma_env != 0 && p->epi_mode != 1;
+  if (p->epi_mode == 2) GLASS_CHECK(flat_out && flat_res, "epi_mode 2 (TMA epilogue) needs a flat split-fp16 output (and residual)");
+  // staging ring of the TMA epilogue: the layers with at most 4 k-blocks (1x1 convs with K <= 256: HBM-bound) trade
+  // pipeline stages they do not need for two more pairs of boxes (one more without a residual)
   const int split_mul = split ? 2 : 1;
-  const int smem_budget = 227 * 1024 - EPI_STAGE_BYTES - 1024 /*align slack*/ - 512 /*barriers*/;
+  int epi_boxes = 1;
+  if (tma_epi) {
+    static const int nb_small = getenv("GLASS_EPI_BOXES_SMALLK") ? atoi(getenv("GLASS_EPI_BOXES_SMALLK")) : 0;
+    static const int nb_big = getenv("GLASS_EPI_BOXES") ? atoi(getenv("GLASS_EPI_BOXES")) : 1;
+    static const int small_kb = getenv("GLASS_EPI_SMALLK") ? atoi(getenv("GLASS_EPI_SMALLK")) : 4;
+    const int kblocks_all = p->ntaps * (p->k_per_tap / BK);
+    if (kblocks_all <= small_kb) epi_boxes = nb_small > 0 ? nb_small : (p->res_hi ? 3 : 2);
+    else epi_boxes = p->res_hi ? nb_big : 1;
+    if (epi_boxes < 1) epi_boxes = 1;
+    if (epi_boxes > MAX_EPI_BOXES) epi_boxes = MAX_EPI_BOXES;
+    // never at the price of a ring below two stages
+    const int stage_b = (A_TILE_BYTES + (pair ? bn / 2 : bn) * BK * 2) * split_mul;
+    while (epi_boxes > 1 && (227 * 1024 - epi_boxes * EPI_BOX_BYTES - 1536) / stage_b < 2) --epi_boxes;
+  }
+  const int epi_bytes = tma_epi ? epi_boxes * EPI_BOX_BYTES : EPI_STAGE_BYTES;
+  // tap-row mode for 3x3 'same' convs (taps ordered (r, s), s-taps = consecutive rows): one 136-row block per tap row
+  const int smem_budget = 227 * 1024 - epi_bytes - 1024 /*align slack*/ - 512 /*barriers*/;
   const int b_stage_bytes = b_rows * BK * 2 * split_mul;
   bool group3 = p->ntaps == 9 && a_ld == p->k_per_tap && p->tap_mode != 1 && !grouped;
   for (int r = 0; r < 3 && group3; ++r)
@@ -903,17 +960,10 @@ static int build_plan(const GlassConvGemmParams* p, GlassGemmPlan* plan) {
   k.m_rows_per_count = p->m_rows_per_count;
   k.sat_count = p->sat_count;
 
-  // TMA epilogue: flat layers only -- the output (and residual) plane IS the M space, so tile rows are contiguous
-  // tensor rows and one 2-D box per 64 columns covers them
-  static const int tma_env = getenv("GLASS_TMA_EPI") ? atoi(getenv("GLASS_TMA_EPI")) : 1;
-  const bool flat_out = split && p->out_hi && p->out_lo && !p->out_f32 && p->out_hp == p->m_h && p->out_wp == p->m_w &&
-                        p->out_border == p->m_border && n_store == p->n && bn % 64 == 0 && p->ld_out >= p->n;
-  const bool flat_res = !p->res_hi || (p->res_shift == 0 && p->res_hp == p->m_h && p->res_wp == p->m_w &&
-                                       p->res_border == p->m_border);
-  bool tma_epi = flat_out && flat_res && tma_env != 0 && p->epi_mode != 1;
-  if (p->epi_mode == 2) GLASS_CHECK(flat_out && flat_res, "epi_mode 2 (TMA epilogue) needs a flat split-fp16 output (and residual)");
   plan->tma_epi = tma_epi ? 1 : 0;
   k.tma_res = (tma_epi && p->res_hi) ? 1 : 0;
+  k.epi_boxes = epi_boxes;
+  k.epi_bytes = epi_bytes;
   if (tma_epi) {
     if (make_map_2d(&plan->mo_hi, p->out_hi, p->n, rows_m, BK, BM, p->ld_out)) return -1;
     if (make_map_2d(&plan->mo_lo, p->out_lo, p->n, rows_m, BK, BM, p->ld_out)) return -1;
@@ -930,7 +980,7 @@ static int build_plan(const GlassConvGemmParams* p, GlassGemmPlan* plan) {
   if (p->m_count_dev) GLASS_CHECK(p->m_rows_per_count > 0, "m_count_dev needs m_rows_per_count > 0");
 
   // always ask for > half of the SM's shared memory: exactly one CTA per SM owns all 512 TMEM columns
-  const int smem_bytes = k.ring_bytes + EPI_STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
+  const int smem_bytes = k.ring_bytes + epi_bytes + 1024 /*align slack*/ + 512 /*barriers*/;
   const int smem_req = smem_bytes < 120 * 1024 ? 120 * 1024 : smem_bytes;
   plan->split = split ? 1 : 0;
   plan->pair = pair ? 1 : 0;

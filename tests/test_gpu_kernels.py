@@ -418,6 +418,10 @@ def test_image_roi_align_matches_oracle(ops):
     (128, 512, 1, True, True, 2, (24, 40)),     # two N tiles
     (128, 128, 3, True, True, 3, (16, 33)),     # 3x3 (tap-row mode) + residual, odd plane
     (64, 64, 3, False, True, 1, (7, 9)),        # tiny: a single partial tile
+    (128, 512, 1, True, True, 8, (56, 72)),     # ring of three box pairs wrapping over ~4 tiles x 4 parts per CTA
+    (64, 192, 1, True, False, 8, (56, 72)),     # three parts per tile: ring position differs from tile to tile
+    (64, 128, 1, False, True, 8, (56, 72)),     # no residual: ring of two pairs, two parts per tile
+    (256, 256, 1, True, True, 8, (56, 72)),     # four k-blocks (the FPN laterals' shape)
 ])
 def test_tma_epilogue_equals_direct_store_epilogue(ops, monkeypatch, cin, cout, k, res, relu, n_img, hw):
     """The TMA-store epilogue (staging boxes + cp.async.bulk.tensor stores, TMA-loaded residual) writes the same bits as
