@@ -131,9 +131,9 @@ class B200GlassROIHeads:
 
         # ---- accumulation chunk of the per-word convs (the MMA-bound 3/4 of the step): 4 k-blocks between TMEM drains
         # instead of the library's 2.  relL2 vs fp64 9e-7 instead of 5e-7 per GEMM (an fp32 CPU GEMM:
-        # 3.0-3.6e-7); the stage-wise parity tests and the reference-golden test of this branch hold at 4, the free-running
-        # random-weight BACKBONE test does not (its res5/p5 amplify rounding noise ~4x per stage), so the backbone, RPN and
-        # box head keep 2.  GLASS_KB_PER_CHUNK overrides both.
+        # 3.0-3.6e-7); the stage-wise parity tests and the reference-golden test of this branch hold at 4, and so do the
+        # shallow heads (box head, P2P3, RPN, FPN); only the bottom-up ResNet body keeps 2 (res4 | oracle res3 reaches
+        # 1.8e-4 at 4).  GLASS_KB_PER_CHUNK overrides all of them.
         def _chunked(pw):
             pw.kb_per_chunk = recognizer_kb_per_chunk
             if getattr(pw, "fallback", None) is not None:
@@ -149,6 +149,8 @@ class B200GlassROIHeads:
         self.r_conv2 = _conv_bn(sdr, "backbone.conv2", (1, 1), (1, 1), dev)
         _chunked(self.r_conv1)
         _chunked(self.r_conv2)
+        for pw in (self.fc1, self.fc2, self.predictor, self.p2p3_conv1, self.p2p3_conv2):
+            _chunked(pw)
         self.lstm = []
         for l in range(2):
             q = f"encoder.bilsm_stack.{l}."
@@ -178,6 +180,8 @@ class B200GlassROIHeads:
             "temperature": float(sdr[dp + "temperature"].item()) if (dp + "temperature") in sdr else 1.0,
         }
         self.dec_w_ctx = packing.pack_linear(wih[:, 256:], None, device=dev)
+        for pw in [self.x_embed, self.dec_w_ctx] + [lw[k] for lw in self.lstm for k in ("wih", "linear")]:
+            _chunked(pw)
 
     # ============================================================================================ box branch
     def box_features(self, features: Dict[str, Act], rois: torch.Tensor) -> torch.Tensor:

@@ -47,6 +47,8 @@ class B200RotatedRPN:
         w = torch.cat((sd["objectness_logits.weight"], sd["anchor_deltas.weight"]), 0)   # [A + 5A, 256, 1, 1]
         b = torch.cat((sd["objectness_logits.bias"], sd["anchor_deltas.bias"]), 0)
         self.pred = packing.pack_conv(w, None, b, (1, 1), (0, 0), n_align=16, device=device)
+        # two layers on top of the pyramid: 4 k-blocks per accumulation chunk (logits within 6e-7 of the oracle's)
+        self.conv.kb_per_chunk = self.pred.kb_per_chunk = 4
         self.ws = Workspace(device)
         self._streams = None
 
