@@ -1025,7 +1025,7 @@ def run_b200(args):
         peak = peaks["bf16_tflops_sustained"]
         achieved = gemm_flops / (gemm_ms / 1e3) / 1e12
         cfg = _config(args.workload, world)
-        run = {"kb_per_chunk": ops.KB_PER_CHUNK or "2 (bottom-up ResNet body), 4 (FPN, RPN, box head, recognizer)",
+        run = {"kb_per_chunk": ops.KB_PER_CHUNK or "2 (bottom-up ResNet body), 4 (FPN, RPN, box head, P2P3), 6 (per-word recognizer convs)",
                "step": "one CUDA graph replay (B200GlassRCNN.graph_step), no host synchronisation inside the loop"
                        if use_graph else "eager launches"}
         if full:

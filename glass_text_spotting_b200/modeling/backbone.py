@@ -123,7 +123,7 @@ class B200ResNetFPN:
         # drains hold the literal tolerance with a factor 8 to spare (p2..p6 | oracle res2..res5: 1.2e-5); the bottom-up
         # body stays at the library's 2 (res4's six bottlenecks reach 1.8e-4 at 4: tests/test_gpu_fullsize_parity.py)
         for pw in list(self.lateral.values()) + list(self.output.values()):
-            pw.kb_per_chunk = fpn_kb_per_chunk
+            pw.kb_per_chunk = int(os.environ.get("GLASS_KB_HEADS", fpn_kb_per_chunk))
         self.ws = Workspace(device)
 
     # ------------------------------------------------------------------------------------------

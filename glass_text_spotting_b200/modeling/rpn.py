@@ -9,6 +9,8 @@ apply_deltas, per-level top-k, clip, batched rotated NMS and the final top-k all
 import math
 from typing import Dict, List, Sequence, Tuple
 
+import os
+
 import torch
 
 from .. import ops, packing
@@ -48,7 +50,7 @@ class B200RotatedRPN:
         b = torch.cat((sd["objectness_logits.bias"], sd["anchor_deltas.bias"]), 0)
         self.pred = packing.pack_conv(w, None, b, (1, 1), (0, 0), n_align=16, device=device)
         # two layers on top of the pyramid: 4 k-blocks per accumulation chunk (logits within 6e-7 of the oracle's)
-        self.conv.kb_per_chunk = self.pred.kb_per_chunk = 4
+        self.conv.kb_per_chunk = self.pred.kb_per_chunk = int(os.environ.get("GLASS_KB_HEADS", 4))
         self.ws = Workspace(device)
         self._streams = None
 

@@ -30,7 +30,10 @@ def close(got: torch.Tensor, ref: torch.Tensor, name="", rtol=RTOL, atol=ATOL, s
     bad_literal = int((err > atol + rtol * ref.abs()).sum().item())
     bad_scaled = int((err > atol * max(scale, 1.0) + rtol * ref.abs()).sum().item())
     max_err = err.max().item() if err.numel() else 0.0
+    # the worst error as a fraction of the literal bound (1.0 = at the bound): the margin a pass was made with
+    worst = (err / (atol + rtol * ref.abs())).max().item() if err.numel() else 0.0
     rec = {"name": name, "numel": err.numel(), "max_err": max_err, "scale": scale, "rtol": rtol, "atol": atol,
+           "worst_over_literal_bound": worst,
            "asserted": "scaled" if scaled else "literal", "literal_misses": bad_literal, "scaled_misses": bad_scaled}
     REPORT.append(rec)
     if scaled and bad_literal:
