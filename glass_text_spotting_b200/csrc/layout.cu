@@ -89,11 +89,15 @@ __global__ void nhwc_f32_to_nchw_kernel(const float* __restrict__ src, int n, in
 // ------------------------------------------------------------------ generic tap gather
 __global__ void gather_taps_kernel(const uint4* __restrict__ shi, const uint4* __restrict__ slo, int n, int h, int w,
                                    int cv /*cp/8*/, int border, int kh, int kw, int sh, int sw, int ph, int pw,
-                                   int ho, int wo, uint4* __restrict__ dhi, uint4* __restrict__ dlo,
+                                   int ho, int wo, uint4* __restrict__ dhi, uint4* __restrict__ dlo, int dst_border,
                                    const int32_t* __restrict__ n_dev) {
   if (n_dev) n = min(n, max(*n_dev, 0));  // live image / word count left on the device by an earlier kernel
   const int taps = kh * kw;
   const int64_t total = (int64_t)n * ho * wo * taps * cv;
+  // destination rows: dense [n, ho, wo], or the positions of a padded / shared-border plane of the OUTPUT geometry (the
+  // GEMM's M space then is the output plane itself: TMA-store epilogue; border rows are never written)
+  const int dlo_b = GLASS_BORDER_LO(dst_border);
+  const int hpo = ho + dlo_b + GLASS_BORDER_HI(dst_border), wpo = wo + dlo_b + GLASS_BORDER_HI(dst_border);
   const int hp = h + GLASS_BORDER_LO(border) + GLASS_BORDER_HI(border), wp = w + GLASS_BORDER_LO(border) + GLASS_BORDER_HI(border);
   border = GLASS_BORDER_LO(border);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -112,8 +116,9 @@ __global__ void gather_taps_kernel(const uint4* __restrict__ shi, const uint4* _
       vh = __ldg(shi + row * cv + c);
       vl = __ldg(slo + row * cv + c);
     }
-    dhi[i] = vh;
-    dlo[i] = vl;
+    const int64_t o = dst_border == 0 ? i : ((((int64_t)b * hpo + y + dlo_b) * wpo + x + dlo_b) * taps + tap) * cv + c;
+    dhi[o] = vh;
+    dlo[o] = vl;
   }
 }
 
@@ -335,14 +340,14 @@ extern "C" int glass_stem_s2d(const float* img, int n, int h, int w, const float
 
 extern "C" int glass_gather_taps(const void* src_hi, const void* src_lo, int n, int h, int w, int cp, int border,
                                  int kh, int kw, int sh, int sw, int ph, int pw, int ho, int wo, void* dst_hi,
-                                 void* dst_lo, const int32_t* n_dev, void* stream) {
+                                 void* dst_lo, int dst_border, const int32_t* n_dev, void* stream) {
   GLASS_CHECK(src_hi && src_lo && dst_hi && dst_lo, "null pointer");
   GLASS_CHECK(n > 0 && h > 0 && w > 0 && cp % 8 == 0 && kh > 0 && kw > 0 && sh > 0 && sw > 0 && ho > 0 && wo > 0,
               "bad shape");
   const int64_t total = (int64_t)n * ho * wo * kh * kw * (cp / 8);
   gather_taps_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>((const uint4*)src_hi, (const uint4*)src_lo, n, h, w,
                                                                cp / 8, border, kh, kw, sh, sw, ph, pw, ho, wo,
-                                                               (uint4*)dst_hi, (uint4*)dst_lo, n_dev);
+                                                               (uint4*)dst_hi, (uint4*)dst_lo, dst_border, n_dev);
   count_launch();
   GLASS_CUDA(cudaGetLastError());
   return 0;

@@ -143,7 +143,7 @@ def load() -> C.CDLL:
     lib.glass_pack_nchw.argtypes = [p, i, i, i, i, p, p, i, i, p]
     lib.glass_unpack_nchw.argtypes = [p, p, i, i, i, i, i, i, p, p]
     lib.glass_nhwc_f32_to_nchw.argtypes = [p, i, i, i, i, i, i, p, p]
-    lib.glass_gather_taps.argtypes = [p, p] + [i] * 13 + [p, p, p, p]
+    lib.glass_gather_taps.argtypes = [p, p] + [i] * 13 + [p, p, i, p, p]
     lib.glass_maxpool.argtypes = [p, p] + [i] * 13 + [p, p, i, p, p]
     lib.glass_roi_align_rotated.argtypes = [C.POINTER(RoiAlignParams), p]
     lib.glass_image_roi_align_rotated.argtypes = [C.POINTER(ImageRoiAlignParams), p]

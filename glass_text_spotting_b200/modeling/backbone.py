@@ -68,12 +68,13 @@ class Workspace:
         return t
 
     def rows(self, name: str, rows: int, width: int, cap_rows: int = 0, planes: int = 2,
-             dtype=torch.float16) -> torch.Tensor:
+             dtype=torch.float16, zero: bool = False) -> torch.Tensor:
         """Row-matrix buffer [planes, rows, width] as a view of a buffer with capacity max(rows, cap_rows) rows
         (each plane's prefix is contiguous)."""
         t = self._raw.get(name)
         if t is None or t.shape[0] != planes or t.shape[2] != width or t.dtype != dtype or t.shape[1] < rows:
-            t = torch.empty((planes, max(rows, cap_rows), width), dtype=dtype, device=self.device)
+            t = (torch.zeros if zero else torch.empty)((planes, max(rows, cap_rows), width), dtype=dtype,
+                                                       device=self.device)
             self._raw[name] = t
         return t[:, :rows]
 
@@ -128,8 +129,12 @@ class B200ResNetFPN:
 
     # ------------------------------------------------------------------------------------------
     def _gemm_rows(self, g: torch.Tensor, w, n, ho, wo, out: Act, relu: bool):
-        ops.conv_gemm(g[0], g[1], g.shape[1], g.shape[2], [0], w, (n, ho, wo, 0), out=out, relu_post=relu,
-                      mode=self.mode)
+        """1x1 conv over gathered rows; rows in the order of ``out``'s padded plane make the GEMM flat (TMA epilogue)."""
+        if g.shape[1] == out.rows:
+            geom = (n, out.hp, out.wp, out.border_code)
+        else:
+            geom = (n, ho, wo, 0)
+        ops.conv_gemm(g[0], g[1], g.shape[1], g.shape[2], [0], w, geom, out=out, relu_post=relu, mode=self.mode)
 
     def _bottleneck(self, x: Act, blk, name: str) -> Act:
         ws, n = self.ws, x.n
@@ -147,8 +152,9 @@ class B200ResNetFPN:
                 ops.conv2d(x, blk["shortcut"], out=sc, mode=self.mode)
         else:
             # STRIDE_IN_1X1: conv1 and the shortcut read the same stride-2 subsampled pixels -> gather once
-            g = ws.raw(f"{name}.gather", (2, n * ho * wo, x.cp))
-            ops.gather_taps(x, 1, 1, s, s, 0, 0, ho, wo, g)
+            db = t1.border_code if ops.GATHER_PADDED else 0   # rows in the order of the padded output planes
+            g = ws.raw(f"{name}.gather", (2, ops.gather_rows(n, ho, wo, db), x.cp), zero=True)
+            ops.gather_taps(x, 1, 1, s, s, 0, 0, ho, wo, g, dst_border=db)
             self._gemm_rows(g, c1, n, ho, wo, t1, True)
             sc = ws.act(f"{name}.sc", n, c3.cout, ho, wo)
             self._gemm_rows(g, blk["shortcut"], n, ho, wo, sc, False)

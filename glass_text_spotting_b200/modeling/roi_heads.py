@@ -367,11 +367,15 @@ class B200GlassROIHeads:
         # conv4_1: k2 s(2,1) p0 + BN + ReLU -> [K,256,8,32], written into the fused buffer's local half
         ho, wo = (x.h - 2) // 2 + 1, x.w - 1
         assert (ho, wo) == (f_out.h, f_out.w)
-        g = self.ws.rows("hyb.c41.gather", k * ho * wo, 4 * x.cp, self._word_cap * ho * wo)
-        ops.gather_taps(x, 2, 2, 2, 1, 0, 0, ho, wo, out=g, n_dev=nd)
-        ops.conv_gemm(g[0], g[1], g.shape[1], g.shape[2], [0], self.h_conv4_1, (k, ho, wo, 0), out_hi=f_out.hi,
+        # rows gathered in the order of the fused buffer's planes: the GEMM is flat and stores through TMA
+        db = f_out.border_code if ops.GATHER_PADDED else 0
+        per_word = ops.gather_rows(1, ho, wo, db)
+        g = self.ws.rows("hyb.c41.gather", k * per_word, 4 * x.cp, self._word_cap * per_word, zero=True)
+        ops.gather_taps(x, 2, 2, 2, 1, 0, 0, ho, wo, out=g, n_dev=nd, dst_border=db)
+        geom = (k, f_out.hp, f_out.wp, db) if db else (k, ho, wo, 0)
+        ops.conv_gemm(g[0], g[1], g.shape[1], g.shape[2], [0], self.h_conv4_1, geom, out_hi=f_out.hi,
                       out_lo=f_out.lo, out_geom=(f_out.hp, f_out.wp, f_out.border_code), ld_out=f_out.cp, relu_post=True,
-                      mode=self.mode, m_count=None if nd is None else (nd, ho * wo))
+                      mode=self.mode, m_count=None if nd is None else (nd, per_word))
         return None
 
     def hybrid_net(self, crops: Act, f_out: Act) -> None:
@@ -395,8 +399,10 @@ class B200GlassROIHeads:
         """CNN_V1_1 (recognizer_backbone.py:77-81) -> mean over H -> 2 x (BiLSTM + Linear) (recognizer_encoder.py:118-144)."""
         ph, pw, cap, nd, m = self.pool_h, self.pool_w, self._word_cap, self._n_dev, self.mode
         T = pw
-        x1 = self._conv(y, self.r_conv1, self.act("rec.cnn1", K, 256, ph // 2, pw, shared=True), relu=True,
-                        gather_buf=self.ws.rows("rec.cnn1.gather", K * (ph // 2) * pw, 2 * 256, cap * (ph // 2) * pw))
+        x1o = self.act("rec.cnn1", K, 256, ph // 2, pw, shared=True)
+        per_word = ops.gather_rows(1, ph // 2, pw, x1o.border_code if ops.GATHER_PADDED else 0)
+        x1 = self._conv(y, self.r_conv1, x1o, relu=True,
+                        gather_buf=self.ws.rows("rec.cnn1.gather", K * per_word, 2 * 256, cap * per_word, zero=True))
         x2 = self._conv(x1, self.r_conv2, self.act("rec.cnn2", K, 256, ph // 2, pw, shared=True), relu_pre=True, residual=x1)
         mc = None if nd is None else (nd, T)
         seq = self.ws.rows("rec.seq0", K * T, 256, cap * T)

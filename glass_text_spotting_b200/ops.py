@@ -17,6 +17,8 @@ ACT_SCALE = 16.0  # == kActScale in csrc/common.cuh: split planes hold ACT_SCALE
 
 # k-blocks (64 wide) accumulated inside the tensor core between drains to fp32 registers (0 = library default)
 KB_PER_CHUNK = int(__import__("os").environ.get("GLASS_KB_PER_CHUNK", "0"))
+# strided convs gather into the row order of their padded output plane (flat GEMM, TMA-store epilogue); 0 = dense rows
+GATHER_PADDED = int(__import__("os").environ.get("GLASS_GATHER_PADDED", "1"))
 # 0 = auto, 1 = never pair CTAs, 2 = always use tcgen05 cta_group::2 CTA pairs (when the tile width allows)
 PAIR_MODE = int(__import__("os").environ.get("GLASS_PAIR_MODE", "0"))
 # 0 = auto (3x3 convs stage one activation block per tap row), 1 = every tap loads its own tile
@@ -311,11 +313,20 @@ def conv2d(x: Act, w: PackedWeight, relu: bool = False, residual: Optional[Act] 
                   m_count=None if n_dev is None else (n_dev, x.hp * x.wp), **kwargs)
     else:
         taps = w.kh * w.kw
-        rows = x.n * ho * wo
-        g = gather_taps(x, w.kh, w.kw, sh, sw, ph, pw, ho, wo, out=gather_buf, n_dev=n_dev)
+        # a split-fp16 output plane: gather into ITS row order, so that the GEMM is flat (TMA-store epilogue); a caller's
+        # dense gather buffer or an fp32 output keep the dense M space
+        db = out.border_code if (out is not None and f32 is None and GATHER_PADDED) else 0
+        if gather_buf is not None and gather_buf.shape[1] != gather_rows(x.n, ho, wo, db):
+            db = 0
+        rows = gather_rows(x.n, ho, wo, db)
+        g = gather_taps(x, w.kh, w.kw, sh, sw, ph, pw, ho, wo, out=gather_buf, n_dev=n_dev, dst_border=db)
         # the gathered matrix is already tap-major: one "tap" of width taps*cp
-        conv_gemm(g[0], g[1], rows, taps * x.cp, [0], w, (x.n, ho, wo, 0),
-                  m_count=None if n_dev is None else (n_dev, ho * wo), **kwargs)
+        if db:
+            conv_gemm(g[0], g[1], rows, taps * x.cp, [0], w, (x.n, out.hp, out.wp, db),
+                      m_count=None if n_dev is None else (n_dev, out.hp * out.wp), **kwargs)
+        else:
+            conv_gemm(g[0], g[1], rows, taps * x.cp, [0], w, (x.n, ho, wo, 0),
+                      m_count=None if n_dev is None else (n_dev, ho * wo), **kwargs)
     return out
 
 
@@ -397,14 +408,26 @@ def maxpool2d(x: Act, k: Tuple[int, int], s: Tuple[int, int], p: Tuple[int, int]
     return out
 
 
+def gather_rows(n: int, ho: int, wo: int, dst_border: int = 0) -> int:
+    """Rows of the gathered matrix: dense n*ho*wo, or the rows of the padded / shared-border OUTPUT planes."""
+    lo, hi = (dst_border & 0xFF), (0 if dst_border & BORDER_SHARED else dst_border & 0xFF)
+    return n * (ho + lo + hi) * (wo + lo + hi)
+
+
 def gather_taps(x: Act, kh: int, kw: int, sh: int, sw: int, ph: int, pw: int, ho: int, wo: int,
-                out: Optional[torch.Tensor] = None, n_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """im2col of a split activation: rows [2, n*ho*wo, kh*kw*cp] (tap-major K)."""
+                out: Optional[torch.Tensor] = None, n_dev: Optional[torch.Tensor] = None,
+                dst_border: int = 0) -> torch.Tensor:
+    """im2col of a split activation: rows [2, n*ho*wo, kh*kw*cp] (tap-major K); with ``dst_border`` (the border code of
+    the conv's OUTPUT plane) the row of output pixel (y, x) sits at that plane's flattened position, so that the GEMM's M
+    space is the output plane and the layer finishes through the TMA-store epilogue (border rows are not written: whatever
+    they hold is multiplied and thrown away, the epilogue writes zeros there)."""
+    rows = gather_rows(x.n, ho, wo, dst_border)
     if out is None:
-        out = torch.empty((2, x.n * ho * wo, kh * kw * x.cp), dtype=torch.float16, device=x.buf.device)
-    assert tuple(out.shape) == (2, x.n * ho * wo, kh * kw * x.cp) and out[0].is_contiguous()
+        out = torch.zeros((2, rows, kh * kw * x.cp), dtype=torch.float16, device=x.buf.device)
+    assert tuple(out.shape) == (2, rows, kh * kw * x.cp) and out[0].is_contiguous(), (tuple(out.shape), rows)
     _lib.check(_lib.load().glass_gather_taps(_ptr(x.hi), _ptr(x.lo), x.n, x.h, x.w, x.cp, x.border_code, kh, kw, sh, sw,
-                                             ph, pw, ho, wo, _ptr(out[0]), _ptr(out[1]), _ptr(n_dev), _stream()))
+                                             ph, pw, ho, wo, _ptr(out[0]), _ptr(out[1]), dst_border, _ptr(n_dev),
+                                             _stream()))
     return out
 
 

@@ -159,10 +159,13 @@ int glass_stem_s2d(const float* img, int n, int h, int w, const float* mean, con
                    void* dst_lo, void* stream);
 
 /* Generic tap gather (im2col) for strided / odd-shaped convs:
- * src split padded NHWC [n,h+2b,w+2b,cp] -> rows [n*ho*wo, kh*kw*cp], tap-major K. */
+ * src split padded NHWC [n,h+2b,w+2b,cp] -> rows of kh*kw*cp elements, tap-major K.  dst_border = 0: dense rows
+ * [n*ho*wo]; otherwise a border code (GLASS_BORDER_SHARED allowed) of the OUTPUT plane: the row of output pixel (y, x)
+ * sits at that plane's flattened position, border rows are left untouched -- the GEMM's M space is then the output
+ * plane itself and the layer finishes through the TMA-store epilogue. */
 int glass_gather_taps(const void* src_hi, const void* src_lo, int n, int h, int w, int cp, int border, int kh,
                       int kw, int sh, int sw, int ph, int pw, int ho, int wo, void* dst_hi, void* dst_lo,
-                      const int32_t* n_dev, void* stream);
+                      int dst_border, const int32_t* n_dev, void* stream);
 
 /* max_pool2d on split-fp16 padded NHWC (F.max_pool2d: BasicStem, local_feature_extraction.py:163-178). */
 int glass_maxpool(const void* src_hi, const void* src_lo, int n, int h, int w, int cp, int border, int kh, int kw,

@@ -445,6 +445,34 @@ def test_tma_epilogue_equals_direct_store_epilogue(ops, monkeypatch, cin, cout, 
     assert b[:, :, :, 0].abs().max().item() == 0 and b[:, :, :, -1].abs().max().item() == 0
 
 
+@pytest.mark.parametrize("cin,cout,k,stride,pad,hw,shared", [
+    (256, 128, 1, (2, 2), (0, 0), (48, 64), False),     # res3 conv1: stride in the 1x1
+    (256, 512, 1, (2, 2), (0, 0), (48, 64), False),     # its shortcut: two N tiles
+    (256, 256, 2, (2, 1), (0, 0), (16, 33), True),      # conv4_1: k2 s(2,1) into shared-border planes
+    (256, 256, 2, (2, 1), (0, 0), (8, 32), True),       # CNN_V1_1 conv1's shape
+])
+def test_strided_conv_gathers_into_the_output_plane_order(ops, monkeypatch, cin, cout, k, stride, pad, hw, shared):
+    """Strided convs gather their taps into the row order of the padded OUTPUT plane, which makes the GEMM flat (TMA-store
+    epilogue); same bits as the dense gather + direct-store epilogue, zero border untouched."""
+    from glass_text_spotting_b200 import packing
+    g = torch.Generator().manual_seed(cin + cout + k)
+    n = 5
+    x = ops.Act.from_nchw(torch.randn(n, cin, *hw, generator=g).cuda(), shared=shared)
+    w = packing.pack_conv(torch.randn(cout, cin, k, k, generator=g) * 0.05, torch.rand(cout, generator=g) + 0.5,
+                          torch.randn(cout, generator=g), stride, pad)
+    ho, wo = (hw[0] + 2 * pad[0] - k) // stride[0] + 1, (hw[1] + 2 * pad[1] - k) // stride[1] + 1
+    outs = []
+    for padded in (0, 1):
+        monkeypatch.setattr(ops, "GATHER_PADDED", padded)
+        o = ops.Act(n, cout, ho, wo, shared=shared)
+        ops.conv2d(x, w, relu=True, out=o)
+        torch.cuda.synchronize()
+        outs.append(o.buf.clone())
+    assert torch.equal(outs[0], outs[1])
+    b = outs[1]
+    assert b[:, :, 0].abs().max().item() == 0 and b[:, :, :, 0].abs().max().item() == 0
+
+
 def test_saturation_counter_debug_flag(ops, monkeypatch):
     """the split-fp16 storage clamps |y| > 3750 silently; under the debug flag the GEMM counts such outputs."""
     from glass_text_spotting_b200 import packing
