@@ -123,13 +123,18 @@ __global__ void gather_taps_kernel(const uint4* __restrict__ shi, const uint4* _
 }
 
 // ------------------------------------------------------------------ stem: normalise + space-to-depth
-// raw fp32 NCHW [n,3,h,w] -> split-fp16 NHWC [n, h/2+4, w/2+4, 16] with a 2-pixel zero border: pixel (Y, X) holds
+// raw fp32 NCHW [n,3,h,w] -> split-fp16 NHWC [n, h/2+2b, w/2+2b, 16] with a b-pixel zero border: pixel (Y, X) holds
 // channel (dy*2+dx)*3 + c = (img[c, 2Y+dy, 2X+dx] - mean[c]) * inv_std[c]; channels 12..15 are zero.  The 7x7/s2/p3
 // stem conv then is a 4x4 stride-1 conv over this map (taps Y-2..Y+1, X-2..X+1), i.e. 4 k-blocks of 4 pixels x 16
 // channels in the GEMM's compact-channel mode -- no 192-wide im2col matrix is materialised (805 MB at bs = 4).
+// b = 1 is enough although the taps reach 2 pixels up / left: in the flattened pixel order the cell left of a row's left
+// border IS the previous row's right border, and the row above an image's top border IS the previous image's bottom
+// border (before the first image: the TMA's out-of-bounds zeros) -- and with b = 1 the map has the geometry of the conv's
+// output plane, i.e. the GEMM is flat and stores through TMA.
 __global__ void stem_s2d_kernel(const float* __restrict__ img, int n, int h, int w, float m0, float m1, float m2,
-                                float is0, float is1, float is2, uint4* __restrict__ dhi, uint4* __restrict__ dlo) {
-  const int ho = h / 2, wo = w / 2, hp = ho + 4, wp = wo + 4;
+                                float is0, float is1, float is2, uint4* __restrict__ dhi, uint4* __restrict__ dlo,
+                                int border) {
+  const int ho = h / 2, wo = w / 2, hp = ho + 2 * border, wp = wo + 2 * border;
   const int64_t total = (int64_t)n * ho * wo;
   const float mean[3] = {m0, m1, m2}, istd[3] = {is0, is1, is2};
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -157,7 +162,7 @@ __global__ void stem_s2d_kernel(const float* __restrict__ img, int n, int h, int
       hw[j] = pack16x2(h0, h1);
       lw[j] = pack16x2(l0, l1);
     }
-    const int64_t o = ((((int64_t)b * hp + y + 2) * wp) + x + 2) * 2;  // 2 x uint4 per 16-channel pixel
+    const int64_t o = ((((int64_t)b * hp + y + border) * wp) + x + border) * 2;  // 2 x uint4 per 16-channel pixel
     dhi[o] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
     dhi[o + 1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
     dlo[o] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
@@ -326,13 +331,15 @@ extern "C" int glass_nhwc_f32_to_nchw(const float* src, int n, int c, int h, int
 }
 
 extern "C" int glass_stem_s2d(const float* img, int n, int h, int w, const float* mean, const float* inv_std,
-                              void* dst_hi, void* dst_lo, void* stream) {
+                              void* dst_hi, void* dst_lo, int border, void* stream) {
   GLASS_CHECK(img && mean && inv_std && dst_hi && dst_lo, "null pointer");
+  GLASS_CHECK(border == 1 || border == 2, "border must be 1 or 2");
   GLASS_CHECK(n > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0, "image size must be even");
   GLASS_CHECK((reinterpret_cast<uintptr_t>(img) & 7) == 0, "image must be 8-byte aligned");
   const int64_t total = (int64_t)n * (h / 2) * (w / 2);
   stem_s2d_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>(img, n, h, w, mean[0], mean[1], mean[2], inv_std[0],
-                                                            inv_std[1], inv_std[2], (uint4*)dst_hi, (uint4*)dst_lo);
+                                                            inv_std[1], inv_std[2], (uint4*)dst_hi, (uint4*)dst_lo,
+                                                            border);
   count_launch();
   GLASS_CUDA(cudaGetLastError());
   return 0;

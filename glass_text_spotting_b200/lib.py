@@ -163,7 +163,7 @@ def load() -> C.CDLL:
     lib.glass_postprocess_merge.argtypes = [C.POINTER(PostprocessParams), p]
     lib.glass_text_scores.argtypes = [p, i, i, i, i, p, p, p, p, p]
     lib.glass_zero_border.argtypes = [p, p, i, i, i, i, p, p]
-    lib.glass_stem_s2d.argtypes = [p, i, i, i, f, f, p, p, p]
+    lib.glass_stem_s2d.argtypes = [p, i, i, i, f, f, p, p, i, p]
     lib.glass_mask_finalize.argtypes = [p, i, i, i, i, p, p]
     lib.glass_paste_masks_rotated.argtypes = [p, p, i, i, i, i, C.c_float, p, p, p]
     lib.glass_box_iou_rotated.argtypes = [p, i, p, i, i, p, p]

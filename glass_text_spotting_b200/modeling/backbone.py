@@ -19,6 +19,7 @@ PIXEL_MEAN = (103.530, 116.280, 123.675)
 PIXEL_STD = (1.0, 1.0, 1.0)
 
 
+STEM_BORDER = int(os.environ.get("GLASS_STEM_BORDER", "1"))
 GROUPED64 = os.environ.get("GLASS_GROUPED64", "1") != "0"
 
 
@@ -175,11 +176,16 @@ class B200ResNetFPN:
         s1 = ws.act("stem.conv", n, 64, h // 2, w // 2)
         # normalise + space-to-depth, then the 7x7/s2 conv as a 4x4/s1 conv: 4 compact-channel k-blocks (one per
         # s2d row Y-2..Y+1, each spanning the 4 pixels X-2..X+1 of 16 channels) straight from the 17 MB/image map
-        hp2, wp2 = h // 2 + 4, w // 2 + 4
+        # The map carries a ONE-pixel zero border although the taps reach two pixels up / left: in the flattened order the
+        # cell left of a row's left border is the previous row's right border and the row above the top border is the
+        # previous image's bottom border (TMA zero fill before the first image).  It then has the geometry of the output
+        # plane: the GEMM is flat and stores through TMA (STEM_BORDER = 2: the round-1 layout, direct stores).
+        sb = STEM_BORDER
+        hp2, wp2 = h // 2 + 2 * sb, w // 2 + 2 * sb
         s2d = ws.raw("stem.s2d", (2, n, hp2, wp2, 16), zero=True)
         ops.stem_s2d(images, self.pixel_mean, self.pixel_std, out=s2d)
         shifts = [(i - 2) * wp2 - 2 for i in range(4)]
-        ops.conv_gemm(s2d[0], s2d[1], n * hp2 * wp2, 64, shifts, self.stem_s2d, (n, hp2, wp2, 2), out=s1,
+        ops.conv_gemm(s2d[0], s2d[1], n * hp2 * wp2, 64, shifts, self.stem_s2d, (n, hp2, wp2, sb), out=s1,
                       relu_post=True, mode=self.mode, a_ld=16)
         x = ws.act("stem.pool", n, 64, h // 4, w // 4)
         ops.maxpool2d(s1, (3, 3), (2, 2), (1, 1), out=x)

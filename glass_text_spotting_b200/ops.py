@@ -432,14 +432,16 @@ def gather_taps(x: Act, kh: int, kw: int, sh: int, sw: int, ph: int, pw: int, ho
 
 
 def stem_s2d(img: torch.Tensor, mean: Sequence[float], std: Sequence[float], out: torch.Tensor) -> torch.Tensor:
-    """raw fp32 NCHW [n,3,h,w] -> normalised space-to-depth map, split planes [2, n, h/2+4, w/2+4, 16] (2-pixel zero
-    border, which must already be zero in ``out``)."""
+    """raw fp32 NCHW [n,3,h,w] -> normalised space-to-depth map, split planes [2, n, h/2+2b, w/2+2b, 16] (b-pixel zero
+    border, b = 1 or 2 read off ``out``'s shape, which must already be zero in ``out``)."""
     n, c, h, w = img.shape
     assert c == 3 and img.dtype == torch.float32 and img.is_contiguous()
-    assert tuple(out.shape) == (2, n, h // 2 + 4, w // 2 + 4, 16) and out.dtype == torch.float16 and out.is_contiguous()
+    border = (out.shape[2] - h // 2) // 2
+    assert border in (1, 2) and tuple(out.shape) == (2, n, h // 2 + 2 * border, w // 2 + 2 * border, 16)
+    assert out.dtype == torch.float16 and out.is_contiguous()
     m = (C.c_float * 3)(*[float(v) for v in mean])
     s = (C.c_float * 3)(*[1.0 / float(v) for v in std])
-    _lib.check(_lib.load().glass_stem_s2d(_ptr(img), n, h, w, m, s, _ptr(out[0]), _ptr(out[1]), _stream()))
+    _lib.check(_lib.load().glass_stem_s2d(_ptr(img), n, h, w, m, s, _ptr(out[0]), _ptr(out[1]), border, _stream()))
     return out
 
 

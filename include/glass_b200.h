@@ -151,12 +151,15 @@ int glass_nhwc_f32_to_nchw(const float* src, int n, int c, int h, int w, int ld,
 
 /* Stem pre-pass with fused (x - mean)/std (d2 GeneralizedRCNN.preprocess_image, called at glass_rcnn.py:82), no im2col
  * matrix: raw fp32 NCHW [n,3,h,w] -> normalised space-to-depth map, split-fp16 NHWC
- * [n, h/2+4, w/2+4, 16] with a 2-pixel zero border (pixel (Y,X), channel (dy*2+dx)*3+c = (img[c,2Y+dy,2X+dx]-mean)*inv_std;
+ * [n, h/2+2b, w/2+2b, 16] with a b-pixel zero border, b = 1 or 2 (pixel (Y,X), channel (dy*2+dx)*3+c = (img[c,2Y+dy,2X+dx]-mean)*inv_std;
  * channels 12..15 zero).  BasicStem's 7x7/s2/p3 conv (d2 resnet.py via configs/glass_pretrain.yaml:41-50) then runs as a
  * 4x4 stride-1 conv in glass_conv_gemm's compact-channel mode (a_ld = 16, 4 taps of one 64-wide k-block,
- * packing.pack_stem_s2d).  The destination's border must be zero (allocate it zeroed once; only the interior is written). */
+ * packing.pack_stem_s2d).  The destination's border must be zero (allocate it zeroed once; only the interior is written).
+ * b = 1 suffices for the 2-pixel reach of the taps (flattened order: the cell left of a row's left border is the previous
+ * row's right border, the row above the top border is the previous image's bottom border) and gives the map the geometry
+ * of the conv's output plane, so that the GEMM is flat (TMA-store epilogue). */
 int glass_stem_s2d(const float* img, int n, int h, int w, const float* mean, const float* inv_std, void* dst_hi,
-                   void* dst_lo, void* stream);
+                   void* dst_lo, int border, void* stream);
 
 /* Generic tap gather (im2col) for strided / odd-shaped convs:
  * src split padded NHWC [n,h+2b,w+2b,cp] -> rows of kh*kw*cp elements, tap-major K.  dst_border = 0: dense rows

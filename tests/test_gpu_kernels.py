@@ -51,10 +51,13 @@ def test_maxpool_matches_torch(ops):
         assert torch.equal(got, ref), (k, s, p)
 
 
+@pytest.mark.parametrize("sb", [1, 2])
 @pytest.mark.parametrize("shape", [(2, 64, 96), (1, 32, 160), (3, 96, 64)])
-def test_stem_space_to_depth(ops, shape):
+def test_stem_space_to_depth(ops, shape, sb):
     """The 7x7/s2/p3 stem as a 4x4/s1 conv over the normalised space-to-depth map (no im2col matrix), with a
-    non-trivial std and folded scale / bias; borders of the map (2 pixels) stay zero."""
+    non-trivial std and folded scale / bias; borders of the map stay zero.  Border 1 (the product's layout: the map has the
+    output plane's geometry, flat GEMM, TMA stores; the taps' 2-pixel reach wraps onto neighbouring border cells) and
+    border 2 (direct stores) must agree bit for bit -- checked through the same reference."""
     from glass_text_spotting_b200 import packing
     n, h, w_ = shape
     g = torch.Generator().manual_seed(n * 1000 + h)
@@ -63,14 +66,14 @@ def test_stem_space_to_depth(ops, shape):
     wt = torch.randn(64, 3, 7, 7, generator=g) * 0.05
     scale = 1.0 + 0.1 * torch.randn(64, generator=g)
     bias = 0.1 * torch.randn(64, generator=g)
-    hp2, wp2 = h // 2 + 4, w_ // 2 + 4
+    hp2, wp2 = h // 2 + 2 * sb, w_ // 2 + 2 * sb
     s2d = torch.zeros((2, n, hp2, wp2, 16), dtype=torch.float16, device="cuda")
     ops.stem_s2d(img.cuda(), mean, std, out=s2d)
-    assert s2d[:, :, :2].abs().max().item() == 0 and s2d[:, :, :, -2:].abs().max().item() == 0
+    assert s2d[:, :, :sb].abs().max().item() == 0 and s2d[:, :, :, -sb:].abs().max().item() == 0
     assert s2d[..., 12:].abs().max().item() == 0
     pw = packing.pack_stem_s2d(wt, scale, bias)
     out = ops.Act(n, 64, h // 2, w_ // 2)
-    ops.conv_gemm(s2d[0], s2d[1], n * hp2 * wp2, 64, [(i - 2) * wp2 - 2 for i in range(4)], pw, (n, hp2, wp2, 2),
+    ops.conv_gemm(s2d[0], s2d[1], n * hp2 * wp2, 64, [(i - 2) * wp2 - 2 for i in range(4)], pw, (n, hp2, wp2, sb),
                   out=out, relu_post=True, a_ld=16)
     x = (img - torch.tensor(mean).view(1, 3, 1, 1)) / torch.tensor(std).view(1, 3, 1, 1)
     ref = F.relu(F.conv2d(x, wt, stride=2, padding=3) * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1))
