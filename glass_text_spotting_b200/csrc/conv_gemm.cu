@@ -57,7 +57,8 @@ struct GemmKernelParams {
   // L2 for every tile (74 KB per tile beside 104 KB of activations)
   int32_t resident_b;
   int32_t kb_per_chunk;  // k-blocks accumulated inside the tensor core before a drain to registers
-  int32_t acc_cols, acc_bufs;  // TMEM accumulator ring: acc_bufs buffers of acc_cols columns (acc_cols * acc_bufs = 512)
+  int32_t acc_cols, acc_bufs;  // TMEM accumulator ring: acc_bufs (a power of two) buffers of acc_cols columns (product <= 512)
+  int32_t acc_shift;           // log2(acc_bufs): ring position / lap parity by mask and shift (no runtime division per chunk)
   int32_t m_h, m_w, m_border;
   int32_t m_border_hi;  // trailing border rows / columns of the M-space planes (0 for shared-border planes)
   const float* scale;
@@ -197,7 +198,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       uint32_t aphase = 0, bphase = 0;
       uint8_t* b_ring = smem + (size_t)p.a_stages * p.a_stage_bytes;
       for (int unit = worker; unit < num_units; unit += num_workers) {
-        const int um = unit / p.tiles_n;
+        const int um = p.tiles_n == 1 ? unit : unit / p.tiles_n;
         const int tn = unit - um * p.tiles_n;
         const int m0 = (PAIR ? um * 2 + (int)rank : um) * BM;
         const int n0 = tn * p.bn + (int)rank * b_rows;
@@ -244,7 +245,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       for (int unit = worker; unit < num_units; unit += num_workers) {
-        const int um = unit / p.tiles_n;
+        const int um = p.tiles_n == 1 ? unit : unit / p.tiles_n;
         const int tn = unit - um * p.tiles_n;
         const int m0 = (PAIR ? um * 2 + (int)rank : um) * BM;
         const int n0 = tn * p.bn + (int)rank * b_rows;  // this CTA's half of the weight tile
@@ -305,8 +306,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           const int kin = kb % p.kb_per_chunk;  // position inside the accumulation chunk
           if (kin == 0) {
             // a new chunk starts from zero in the next TMEM buffer once the epilogue has drained it
-            const uint32_t buf = chunk % (uint32_t)p.acc_bufs;
-            mbar_wait(&tmem_empty_bar[buf], ((chunk / (uint32_t)p.acc_bufs) & 1u) ^ 1u);
+            const uint32_t buf = chunk & (uint32_t)(p.acc_bufs - 1);
+            mbar_wait(&tmem_empty_bar[buf], ((chunk >> p.acc_shift) & 1u) ^ 1u);
             tcgen05_fence_after();
             d_tmem = tmem_base + buf * (uint32_t)p.acc_cols;
           }
@@ -352,7 +353,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             }
             if (!p.resident_b) commit(&empty_bar[stage]);  // frees the (weight) slot in both CTAs when these MMAs retire
             if (a_done) commit(&a_empty_bar[as]);  // all three s-taps have consumed the activation block
-            if (chunk_done) commit(&tmem_full_bar[chunk % (uint32_t)p.acc_bufs]);  // -> the epilogue(s) drain it
+            if (chunk_done) commit(&tmem_full_bar[chunk & (uint32_t)(p.acc_bufs - 1)]);  // -> the epilogue(s) drain it
           }
           __syncwarp();
           if (a_done && ++as == p.a_stages) {
@@ -395,7 +396,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       int box = 0;                             // ring position of the current part
       uint32_t box_phase = 0;                  // parity of res_bar[box] for the current lap
       auto unit_origin = [&](int unit, int& m0, int& n0) {
-        const int um = unit / p.tiles_n;
+        const int um = p.tiles_n == 1 ? unit : unit / p.tiles_n;
         const int tn = unit - um * p.tiles_n;
         m0 = (PAIR ? um * 2 + (int)rank : um) * BM;
         n0 = tn * p.bn;
@@ -425,18 +426,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         unit_origin(unit, m0, n0);
         const int64_t m = (int64_t)m0 + row_in_tile;
         bool valid = m < rows_m;
-        if (valid) {
-          const int rem = (int)(m % plane);
-          const int yy = rem / p.m_w;
-          const int xx = rem - yy * p.m_w;
+        if (valid && (p.m_border | p.m_border_hi) != 0) {   // (planes without a border: every row is a pixel)
+          const uint32_t rem = (uint32_t)m % (uint32_t)plane;   // rows_m < 2^31 (checked by the host): 32-bit division
+          const int yy = (int)(rem / (uint32_t)p.m_w);
+          const int xx = (int)rem - yy * p.m_w;
           valid = (yy >= p.m_border) && (xx >= p.m_border) && (yy < p.m_h - p.m_border_hi) && (xx < p.m_w - p.m_border_hi);
         }
         // ---- drain every accumulation chunk of this tile from TMEM into fp32 registers (round-to-nearest adds)
         float accv[MAX_CHUNKS_PER_WARP][16];
         const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
         for (int g = 0; g < chunks_per_tile; ++g, ++chunk) {
-          const uint32_t buf = chunk % (uint32_t)p.acc_bufs;
-          mbar_wait(&tmem_full_bar[buf], (chunk / (uint32_t)p.acc_bufs) & 1u);
+          const uint32_t buf = chunk & (uint32_t)(p.acc_bufs - 1);
+          mbar_wait(&tmem_full_bar[buf], (chunk >> p.acc_shift) & 1u);
           tcgen05_fence_after();
           const uint32_t t_row = tmem_base + buf * (uint32_t)p.acc_cols + lane_sel;
 #pragma unroll
@@ -572,7 +573,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     const int chunks_per_tile = (kblocks + p.kb_per_chunk - 1) / p.kb_per_chunk;
     uint32_t chunk = 0;  // mirrors the MMA warp's running chunk counter
     for (int unit = worker; unit < num_units; unit += num_workers) {
-      const int um = unit / p.tiles_n;
+      const int um = p.tiles_n == 1 ? unit : unit / p.tiles_n;
       const int tn = unit - um * p.tiles_n;
       const int tm = PAIR ? um * 2 + (int)rank : um;
       const int n0 = tn * p.bn;
@@ -580,8 +581,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       bool valid = m < rows_m;
       int64_t out_row = 0, res_row = 0;
       if (valid) {
-        const int img = (int)(m / plane);
-        const int rem = (int)(m - (int64_t)img * plane);
+        const int img = (int)((uint32_t)m / (uint32_t)plane);   // rows_m < 2^31 (checked by the host): 32-bit division
+        const int rem = (int)((uint32_t)m - (uint32_t)img * (uint32_t)plane);
         const int yy = rem / p.m_w;
         const int xx = rem - yy * p.m_w;
         const int y = yy - p.m_border, x = xx - p.m_border;
@@ -604,8 +605,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       float accv[MAX_CHUNKS_PER_WARP][16];
       const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
       for (int g = 0; g < chunks_per_tile; ++g, ++chunk) {
-        const uint32_t buf = chunk % (uint32_t)p.acc_bufs;
-        mbar_wait(&tmem_full_bar[buf], (chunk / (uint32_t)p.acc_bufs) & 1u);
+        const uint32_t buf = chunk & (uint32_t)(p.acc_bufs - 1);
+        mbar_wait(&tmem_full_bar[buf], (chunk >> p.acc_shift) & 1u);
         tcgen05_fence_after();
         const uint32_t t_row = tmem_base + buf * (uint32_t)p.acc_cols + lane_sel;
 #pragma unroll
@@ -855,7 +856,8 @@ static int build_plan(const GlassConvGemmParams* p, GlassGemmPlan* plan) {
   // tensor rows and one 2-D box per 64 columns covers them
   static const int tma_env = getenv("GLASS_TMA_EPI") ? atoi(getenv("GLASS_TMA_EPI")) : 1;
   const bool flat_out = split && p->out_hi && p->out_lo && !p->out_f32 && p->out_hp == p->m_h && p->out_wp == p->m_w &&
-                        p->out_border == p->m_border && n_store == p->n && bn % 64 == 0 && p->ld_out >= p->n;
+                        p->out_border == p->m_border && bn % 64 == 0 && p->ld_out >= n_store &&
+                        (n_store == p->n || !p->res_hi);   // pad columns (n_store < n): clipped by the TMA store
   const bool flat_res = !p->res_hi || (p->res_shift == 0 && p->res_hp == p->m_h && p->res_wp == p->m_w &&
                                        p->res_border == p->m_border);
   bool tma_epi = flat_out && flat_res && tma_env != 0 && p->epi_mode != 1;
@@ -944,10 +946,11 @@ static int build_plan(const GlassConvGemmParams* p, GlassGemmPlan* plan) {
   k.kb_per_chunk = p->kb_per_chunk > 0 ? p->kb_per_chunk : (split ? 2 : 4);
   k.acc_cols = bn <= 64 ? 64 : (bn <= 128 ? 128 : 256);
   k.acc_bufs = TMEM_COLS / k.acc_cols;  // narrow tiles get a deeper ring: the chunk hand-shake latency hides behind it
-  if (const char* e = getenv("GLASS_ACC_BUFS")) {  // tuning / A-B knob
+  if (const char* e = getenv("GLASS_ACC_BUFS")) {  // tuning / A-B knob (rounded down to a power of two)
     const int v = atoi(e);
-    if (v >= 2 && v <= k.acc_bufs) k.acc_bufs = v;
+    if (v >= 2 && v <= k.acc_bufs) k.acc_bufs = v >= 8 ? 8 : (v >= 4 ? 4 : 2);
   }
+  k.acc_shift = k.acc_bufs == 8 ? 3 : (k.acc_bufs == 4 ? 2 : 1);
   k.m_h = p->m_h; k.m_w = p->m_w; k.m_border = m_b; k.m_border_hi = m_bh;
   k.scale = p->scale; k.bias = p->bias;
   k.relu_pre = p->relu_pre; k.relu_post = p->relu_post;
@@ -965,8 +968,8 @@ static int build_plan(const GlassConvGemmParams* p, GlassGemmPlan* plan) {
   k.epi_boxes = epi_boxes;
   k.epi_bytes = epi_bytes;
   if (tma_epi) {
-    if (make_map_2d(&plan->mo_hi, p->out_hi, p->n, rows_m, BK, BM, p->ld_out)) return -1;
-    if (make_map_2d(&plan->mo_lo, p->out_lo, p->n, rows_m, BK, BM, p->ld_out)) return -1;
+    if (make_map_2d(&plan->mo_hi, p->out_hi, n_store, rows_m, BK, BM, p->ld_out)) return -1;
+    if (make_map_2d(&plan->mo_lo, p->out_lo, n_store, rows_m, BK, BM, p->ld_out)) return -1;
     if (p->res_hi) {
       if (make_map_2d(&plan->mr_hi, p->res_hi, p->n, rows_m, BK, BM, p->ld_out)) return -1;
       if (make_map_2d(&plan->mr_lo, p->res_lo, p->n, rows_m, BK, BM, p->ld_out)) return -1;

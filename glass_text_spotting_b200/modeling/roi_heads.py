@@ -87,8 +87,10 @@ class B200GlassROIHeads:
                 pw.fallback = packing.pack_conv(sd[hp + conv + ".weight"], s, b, stride, pad, device=dev)
                 return pw
             if compact_cp and grouped:
+                # (rows padded to a multiple of 64 columns -- 5 pixels x 16 channels = 80 -> 128 -- so that the layer
+                # qualifies for the TMA-store epilogue; the store clips the pad columns)
                 pw = packing.pack_conv_grouped(sd[hp + conv + ".weight"], compact_cp, group_of[compact_cp], s, b,
-                                               device=dev)
+                                               device=dev, n_align=64)
                 # crop sizes whose padded width is not a multiple of the group fall back to the compact mode
                 pw.fallback = packing.pack_conv_compact(sd[hp + conv + ".weight"], compact_cp, s, b, device=dev)
                 return pw

@@ -368,7 +368,8 @@ def _conv2d_grouped(x: Act, w: PackedWeight, relu, residual, relu_pre, out, mode
     conv_gemm(x.hi, x.lo, rows, kwin, shifts, w, (1, rows, 1, 0), out_hi=out.hi, out_lo=out.lo, out_geom=(rows, 1, 0),
               ld_out=P * out.cp, relu_pre=relu_pre, relu_post=relu, mode=mode, a_ld=P * cp, a_col0=col0,
               a_inner=col0 + kwin, m_count=None if n_dev is None else (n_dev, x.hp * x.wp // P),
-              residual=residual, res_geom=(rows, 1, 0), valid_pixels=x.n * x.h * x.w)
+              residual=residual, res_geom=(rows, 1, 0), valid_pixels=x.n * x.h * x.w,
+              n_store=w.grouped_n_store if w.grouped_n_store != w.n_p else 0)
     _lib.check(_lib.load().glass_zero_border(_ptr(out.hi), _ptr(out.lo), out.n, out.h, out.w, out.cp, _ptr(n_dev),
                                              _stream()))
     return out

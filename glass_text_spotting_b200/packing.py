@@ -95,12 +95,14 @@ def pack_conv_compact(weight: torch.Tensor, cp_in: int, scale: Optional[torch.Te
 
 
 def pack_conv_grouped(weight: torch.Tensor, cp_in: int, group: int, scale: Optional[torch.Tensor] = None,
-                      bias: Optional[torch.Tensor] = None, device="cuda") -> PackedWeight:
+                      bias: Optional[torch.Tensor] = None, device="cuda", n_align: int = 16) -> PackedWeight:
     """Pixel-grouped packing of a stride-1 'same' conv (1x1 or 3x3) on a narrow activation (cp_in channels per pixel):
     one GEMM row = ``group`` consecutive pixels, K per tap row = the window of group + kw - 1 pixels (zero padded to a
     multiple of 64), weights = the block-Toeplitz matrix [group * cout_p, kh * Kwin] whose row (p, co) holds
     weight[co, :, r, s] at window pixel p + s.  Output row = group * cout_p contiguous elements = the NHWC rows of the
-    group's pixels, so cout_p (cout rounded up to 16) must be the output activation's channel stride."""
+    group's pixels, so cout_p (cout rounded up to 16) must be the output activation's channel stride.  ``n_align`` pads
+    the weight rows with zeros (5 pixels x 16 channels = 80 -> 128: a tile width the TMA-store epilogue takes; the store
+    clips the pad columns, ``grouped_n_store`` = the real row width)."""
     cout, cin, kh, kw = weight.shape
     assert cin <= cp_in and cp_in % 8 == 0 and (kh, kw) in ((1, 1), (3, 3)) and group >= 1
     cout_p = round_up(cout, 16)
@@ -112,17 +114,22 @@ def pack_conv_grouped(weight: torch.Tensor, cp_in: int, group: int, scale: Optio
     for p in range(group):
         for s_ in range(kw):
             w[p, :cout, :, p + s_, :cin] = wt[:, :, s_, :]
-    n_p = group * cout_p
+    n_real = group * cout_p
+    n_p = round_up(n_real, n_align)
     s = torch.ones(cout_p, dtype=torch.float32)
     b = torch.zeros(cout_p, dtype=torch.float32)
     if scale is not None:
         s[:cout] = scale.detach().float()
     if bias is not None:
         b[:cout] = bias.detach().float()
-    wp, s_all = _pack_rows(w.reshape(n_p, kh * kwin), s.repeat(group), device)
-    pw = PackedWeight(wp.to(device), s_all.to(device), b.repeat(group).to(device), cout, cin, kh, kw, (1, 1),
+    rows = torch.zeros((n_p, kh * kwin), dtype=torch.float32)
+    rows[:n_real] = w.reshape(n_real, kh * kwin)
+    s_rows, b_rows = torch.ones(n_p, dtype=torch.float32), torch.zeros(n_p, dtype=torch.float32)
+    s_rows[:n_real], b_rows[:n_real] = s.repeat(group), b.repeat(group)
+    wp, s_all = _pack_rows(rows, s_rows, device)
+    pw = PackedWeight(wp.to(device), s_all.to(device), b_rows.to(device), cout, cin, kh, kw, (1, 1),
                       ((kh - 1) // 2, (kw - 1) // 2), kwin)
-    pw.grouped_p, pw.grouped_cp, pw.grouped_cout_p = group, cp_in, cout_p
+    pw.grouped_p, pw.grouped_cp, pw.grouped_cout_p, pw.grouped_n_store = group, cp_in, cout_p, n_real
     return pw
 
 
