@@ -384,11 +384,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       const int parts = p.bn >> 6;
       const bool has_res = p.tma_res != 0;
       const bool issuer = threadIdx.x == 128;   // warp 4, lane 0: issues the TMA stores / residual loads
-      const uint32_t boxes = smem_u32(stage_base);   // ring of p.epi_boxes pairs: hi box at + 32 KB * b, lo box 16 KB behind it
+      // Everything below is addressed through 32-bit shared-space addresses derived from ONE laundered base, and the
+      // per-thread offsets are laundered too: left to itself the compiler re-derived them from %tid / the generic smem
+      // pointer (cvta) at every use inside the register-starved part loop -- ~300 of the ~550 warp instructions per part.
+      const uint32_t sbase = opaque_u32(smem_u32(smem));
+      const uint32_t boxes = sbase + (uint32_t)p.ring_bytes;   // ring of p.epi_boxes pairs: hi box at + 32 KB * b, lo box 16 KB behind it
+      const uint32_t bars_a = boxes + (uint32_t)p.epi_bytes;
+      const uint32_t tmem_full_a = bars_a + 8u * (2 * MAX_STAGES);
+      const uint32_t tmem_empty_a = tmem_full_a + 8u * MAX_ACC_BUFS;
+      const uint32_t res_bar_a = bars_a + 8u * (2 * MAX_STAGES + 2 * MAX_ACC_BUFS + 2 * MAX_A_STAGES + 1);
       // this thread's two 16-byte chunks of its 128-byte box row (SWIZZLE_128B: chunk index ^ (row & 7))
       const uint32_t row_off = (uint32_t)row_in_tile * 128u;
-      const uint32_t off0 = row_off + (uint32_t)(((2 * sub) ^ (lane & 7)) << 4);
-      const uint32_t off1 = row_off + (uint32_t)(((2 * sub + 1) ^ (lane & 7)) << 4);
+      const uint32_t off0 = opaque_u32(row_off + (uint32_t)(((2 * sub) ^ (lane & 7)) << 4));
+      const uint32_t off1 = opaque_u32(row_off + (uint32_t)(((2 * sub + 1) ^ (lane & 7)) << 4));
+      const uint32_t col_off = opaque_u32((uint32_t)sub * 16u);   // first of this thread's 16 columns inside a part
       const int chunks_per_tile = (kblocks + p.kb_per_chunk - 1) / p.kb_per_chunk;
       uint32_t chunk = 0;
       const int nb = p.epi_boxes;
@@ -407,10 +416,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         if (la_unit < num_units) {
           int rm0, rn0;
           unit_origin(la_unit, rm0, rn0);
-          uint8_t* dst = reinterpret_cast<uint8_t*>(stage_base) + (size_t)la_box * EPI_BOX_BYTES;
-          mbar_arrive_expect_tx(&res_bar[la_box], (uint32_t)EPI_BOX_BYTES);
-          tma_load_2d(dst, &map_r_hi, &res_bar[la_box], rn0 + la_pt * 64, rm0);
-          tma_load_2d(dst + EPI_BOX_BYTES / 2, &map_r_lo, &res_bar[la_box], rn0 + la_pt * 64, rm0);
+          const uint32_t dst = boxes + (uint32_t)la_box * (uint32_t)EPI_BOX_BYTES;
+          const uint32_t bar = res_bar_a + 8u * (uint32_t)la_box;
+          mbar_arrive_expect_tx_a(bar, (uint32_t)EPI_BOX_BYTES);
+          tma_load_2d_a(dst, &map_r_hi, bar, rn0 + la_pt * 64, rm0);
+          tma_load_2d_a(dst + (uint32_t)(EPI_BOX_BYTES / 2), &map_r_lo, bar, rn0 + la_pt * 64, rm0);
         }
         if (++la_pt == parts) {
           la_pt = 0;
@@ -437,14 +447,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
         for (int g = 0; g < chunks_per_tile; ++g, ++chunk) {
           const uint32_t buf = chunk & (uint32_t)(p.acc_bufs - 1);
-          mbar_wait(&tmem_full_bar[buf], (chunk >> p.acc_shift) & 1u);
+          mbar_wait_a(tmem_full_a + 8u * buf, (chunk >> p.acc_shift) & 1u);
           tcgen05_fence_after();
-          const uint32_t t_row = tmem_base + buf * (uint32_t)p.acc_cols + lane_sel;
+          const uint32_t t_row = tmem_base + buf * (uint32_t)p.acc_cols + lane_sel + col_off;
 #pragma unroll
           for (int pt = 0; pt < MAX_CHUNKS_PER_WARP; ++pt) {
             if (pt < parts) {
               uint32_t r[16];
-              tmem_ld_32x32b_x16(t_row + (uint32_t)(pt * 64 + sub * 16), r);
+              tmem_ld_32x32b_x16(t_row + (uint32_t)(pt * 64), r);
               tmem_ld_wait();
               if (g == 0) {
 #pragma unroll
@@ -458,8 +468,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) {
-            if (PAIR) mbar_arrive_remote(&tmem_empty_bar[buf], 0u);
-            else mbar_arrive(&tmem_empty_bar[buf]);
+            if (PAIR) mbar_arrive_remote_a(tmem_empty_a + 8u * buf, 0u);
+            else mbar_arrive_a(tmem_empty_a + 8u * buf);
           }
         }
         // ---- part by part: math in registers -> staging boxes -> TMA store.  All arithmetic runs in the STORAGE scale
@@ -468,23 +478,28 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
 #pragma unroll
         for (int pt = 0; pt < MAX_CHUNKS_PER_WARP; ++pt) {
           if (pt < parts) {
-            const int n = n0 + pt * 64 + sub * 16;
+            const uint32_t n = (uint32_t)(n0 + pt * 64) + col_off;
             float v[16];
+            // y16 = 16 (D scale + bias): one fused multiply-add per element like the direct-store epilogue, then the exact
+            // power-of-two factor (the same bits as fma(D, 16 scale, 16 bias), half the multiplies)
+            if (p.scale != nullptr && p.bias != nullptr) {
+              const float4* sp = reinterpret_cast<const float4*>(p.scale + n);
+              const float4* bp = reinterpret_cast<const float4*>(p.bias + n);
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              float4 s4 = make_float4(kActScale, kActScale, kActScale, kActScale);
-              if (p.scale != nullptr) {
-                s4 = __ldg(reinterpret_cast<const float4*>(p.scale + n + j));
-                s4.x *= kActScale; s4.y *= kActScale; s4.z *= kActScale; s4.w *= kActScale;
+              for (int j = 0; j < 16; j += 4) {
+                const float4 s4 = __ldg(sp + (j >> 2)), b4 = __ldg(bp + (j >> 2));
+                v[j] = fmaf(accv[pt][j], s4.x, b4.x) * kActScale; v[j + 1] = fmaf(accv[pt][j + 1], s4.y, b4.y) * kActScale;
+                v[j + 2] = fmaf(accv[pt][j + 2], s4.z, b4.z) * kActScale; v[j + 3] = fmaf(accv[pt][j + 3], s4.w, b4.w) * kActScale;
               }
-              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (p.bias != nullptr) {
-                b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
-                b4.x *= kActScale; b4.y *= kActScale; b4.z *= kActScale; b4.w *= kActScale;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.scale != nullptr) s4 = __ldg(reinterpret_cast<const float4*>(p.scale + n + j));
+                if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+                v[j] = fmaf(accv[pt][j], s4.x, b4.x) * kActScale; v[j + 1] = fmaf(accv[pt][j + 1], s4.y, b4.y) * kActScale;
+                v[j + 2] = fmaf(accv[pt][j + 2], s4.z, b4.z) * kActScale; v[j + 3] = fmaf(accv[pt][j + 3], s4.w, b4.w) * kActScale;
               }
-              // one fused multiply-add per element, like the direct-store epilogue (same bits: the factor 16 is exact)
-              v[j] = fmaf(accv[pt][j], s4.x, b4.x); v[j + 1] = fmaf(accv[pt][j + 1], s4.y, b4.y);
-              v[j + 2] = fmaf(accv[pt][j + 2], s4.z, b4.z); v[j + 3] = fmaf(accv[pt][j + 3], s4.w, b4.w);
             }
             if (p.relu_pre) {
 #pragma unroll
@@ -492,7 +507,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             }
             const uint32_t box_hi = boxes + (uint32_t)box * (uint32_t)EPI_BOX_BYTES, box_lo = box_hi + (uint32_t)(EPI_BOX_BYTES / 2);
             if (has_res) {
-              mbar_wait(&res_bar[box], box_phase);   // this part's residual has landed in its pair of boxes
+              mbar_wait_a(res_bar_a + 8u * (uint32_t)box, box_phase);   // this part's residual has landed in its pair of boxes
               const uint4 rh0 = lds_u4(box_hi + off0), rh1 = lds_u4(box_hi + off1);
               const uint4 rl0 = lds_u4(box_lo + off0), rl1 = lds_u4(box_lo + off1);
               const uint32_t aw[8] = {rh0.x, rh0.y, rh0.z, rh0.w, rh1.x, rh1.y, rh1.z, rh1.w};
