@@ -9,6 +9,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <string>
 
@@ -31,6 +32,38 @@ int fail(const std::string& msg);  // sets last error, returns -1
   } while (0)
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+#ifdef __CUDACC__
+// Programmatic dependent launch along the step's chain of ~170 launches.  The GEMM launches carry the
+// programmatic-stream-serialization attribute (conv_gemm.cu); every other kernel of the chain starts with pdl_prologue(),
+// whose griddepcontrol.launch_dependents lets a GEMM that FOLLOWS it be scheduled -- barrier init, TMEM allocation,
+// descriptor prefetch -- while this kernel still runs, instead of after it has drained (+3 % end to end, also inside a CUDA
+// graph).  Giving the small kernels the attribute as well (GLASS_PDL_ALL=1: their CTAs park at griddepcontrol.wait beside
+// the running GEMM) was measured slower (191 vs 197 images/s), so by default they launch plainly.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     Args&&... args) {
+  static const bool on = getenv("GLASS_PDL_ALL") && atoi(getenv("GLASS_PDL_ALL")) != 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = on ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+// First statement of such a kernel: let the NEXT kernel of the stream be scheduled as this one's CTAs retire, then (a
+// no-op unless this launch itself is programmatic) wait until the PREVIOUS one has completed and its writes are visible.
+// Nothing written by an earlier kernel (device-side counts included) may be read before it.
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+#endif
 
 // Plane geometry code carried by every `border` argument of the ABI (include/glass_b200.h): low byte = LEADING zero rows /
 // columns of a padded plane; GLASS_BORDER_SHARED set = no trailing ones (the next row's / plane's leading border serves as

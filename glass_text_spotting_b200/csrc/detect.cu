@@ -83,6 +83,7 @@ constexpr int RPN_HIST0_BITS = 12, RPN_HIST0_BINS = 1 << RPN_HIST0_BITS;
 // Pass 0, many CTAs per image: gather the strided logits into a dense key array and histogram the top 12 bits
 // (sign, exponent, 3 mantissa bits: fine enough that the later passes only touch a few thousand candidates).
 __global__ void __launch_bounds__(256) rpn_keys_kernel(const RpnTopkKernelParams p) {
+  pdl_prologue();
   __shared__ unsigned int hist[RPN_HIST0_BINS];
   const int img = blockIdx.y;
   const int npix = p.h * p.w;
@@ -105,6 +106,7 @@ __global__ void __launch_bounds__(256) rpn_keys_kernel(const RpnTopkKernelParams
 
 // Passes 1..3 + compaction + sort + decode, one CTA per image, over the dense keys (coalesced).
 __global__ void __launch_bounds__(1024) rpn_topk_decode_kernel(const RpnTopkKernelParams p) {
+  pdl_prologue();
   __shared__ unsigned int hist[RPN_HIST0_BINS];
   __shared__ unsigned int coarse[32];
   __shared__ unsigned int s_prefix, s_mask, s_remaining, s_cnt_gt, s_cnt_eq;
@@ -299,6 +301,7 @@ constexpr int NMS_CHUNK = 64;
 constexpr int NMS_MAX_KEEP = 128;
 
 __global__ void __launch_bounds__(1024) nms_rotated_kernel(const NmsKernelParams p) {
+  pdl_prologue();
   extern __shared__ unsigned long long keys[];  // [sort_n]
   __shared__ float scratch[32];
   __shared__ RBox kept[NMS_MAX_KEEP];
@@ -426,6 +429,7 @@ __global__ void box_decode_kernel(const float* __restrict__ pred, int ld, const 
                                   const int* __restrict__ counts, int n_img, int per_img, float w0, float w1,
                                   float w2, float w3, float w4, float* __restrict__ out_boxes,
                                   float* __restrict__ out_scores, float* __restrict__ out_orient) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_img * per_img) return;
   const int img = i / per_img, r = i - img * per_img;
@@ -539,7 +543,7 @@ extern "C" int glass_nms_rotated(const GlassNmsParams* p, void* stream_v) {
   k.ws_boxes = reinterpret_cast<float*>(ws + (size_t)p->n_img * p->m * sizeof(RBox));
   const int smem = sort_n * (int)sizeof(unsigned long long);
   GLASS_CUDA(cudaFuncSetAttribute(nms_rotated_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
-  nms_rotated_kernel<<<p->n_img, 1024, smem, stream>>>(k);
+  GLASS_CUDA(launch_pdl(nms_rotated_kernel, dim3(p->n_img), dim3(1024), smem, stream, k));
   count_launch();
   GLASS_CUDA(cudaGetLastError());
   return 0;
@@ -552,10 +556,10 @@ extern "C" int glass_box_decode(const float* pred, int ld, const float* proposal
   GLASS_CHECK(pred && proposals && host_weights && out_boxes && out_scores && out_orient, "null pointer");
   GLASS_CHECK(ld >= 11 && n_img > 0 && per_img > 0, "bad shape");
   const int total = n_img * per_img;
-  box_decode_kernel<<<(total + 127) / 128, 128, 0, stream>>>(pred, ld, proposals, counts, n_img, per_img,
+  GLASS_CUDA(launch_pdl(box_decode_kernel, dim3((total + 127) / 128), dim3(128), 0, stream, pred, ld, proposals, counts, n_img, per_img,
                                                             host_weights[0], host_weights[1], host_weights[2],
                                                             host_weights[3], host_weights[4], out_boxes, out_scores,
-                                                            out_orient);
+                                                            out_orient));
   count_launch();
   GLASS_CUDA(cudaGetLastError());
   return 0;

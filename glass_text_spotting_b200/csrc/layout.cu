@@ -91,6 +91,7 @@ __global__ void gather_taps_kernel(const uint4* __restrict__ shi, const uint4* _
                                    int cv /*cp/8*/, int border, int kh, int kw, int sh, int sw, int ph, int pw,
                                    int ho, int wo, uint4* __restrict__ dhi, uint4* __restrict__ dlo, int dst_border,
                                    const int32_t* __restrict__ n_dev) {
+  pdl_prologue();
   if (n_dev) n = min(n, max(*n_dev, 0));  // live image / word count left on the device by an earlier kernel
   const int taps = kh * kw;
   const int64_t total = (int64_t)n * ho * wo * taps * cv;
@@ -134,6 +135,7 @@ __global__ void gather_taps_kernel(const uint4* __restrict__ shi, const uint4* _
 __global__ void stem_s2d_kernel(const float* __restrict__ img, int n, int h, int w, float m0, float m1, float m2,
                                 float is0, float is1, float is2, uint4* __restrict__ dhi, uint4* __restrict__ dlo,
                                 int border) {
+  pdl_prologue();
   const int ho = h / 2, wo = w / 2, hp = ho + 2 * border, wp = wo + 2 * border;
   const int64_t total = (int64_t)n * ho * wo;
   const float mean[3] = {m0, m1, m2}, istd[3] = {is0, is1, is2};
@@ -173,6 +175,7 @@ __global__ void stem_s2d_kernel(const float* __restrict__ img, int n, int h, int
 // ------------------------------------------------------------------ border re-zero (border = 1)
 __global__ void zero_border_kernel(uint4* __restrict__ hi, uint4* __restrict__ lo, int n, int hp, int wp, int cv,
                                    const int32_t* __restrict__ n_dev) {
+  pdl_prologue();
   if (n_dev) n = min(n, max(*n_dev, 0));
   const int per_img = 2 * wp + 2 * (hp - 2);
   const int64_t total = (int64_t)n * per_img * cv;
@@ -196,6 +199,7 @@ __global__ void maxpool_kernel(const uint4* __restrict__ shi, const uint4* __res
                                int cv, int border, int kh, int kw, int sh, int sw, int ph, int pw, int ho, int wo,
                                uint4* __restrict__ dhi, uint4* __restrict__ dlo, int dborder,
                                const int32_t* __restrict__ n_dev) {
+  pdl_prologue();
   if (n_dev) n = min(n, max(*n_dev, 0));
   const int64_t total = (int64_t)n * ho * wo * cv;
   const int hp = h + GLASS_BORDER_LO(border) + GLASS_BORDER_HI(border), wp = w + GLASS_BORDER_LO(border) + GLASS_BORDER_HI(border);
@@ -337,9 +341,9 @@ extern "C" int glass_stem_s2d(const float* img, int n, int h, int w, const float
   GLASS_CHECK(n > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0, "image size must be even");
   GLASS_CHECK((reinterpret_cast<uintptr_t>(img) & 7) == 0, "image must be 8-byte aligned");
   const int64_t total = (int64_t)n * (h / 2) * (w / 2);
-  stem_s2d_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>(img, n, h, w, mean[0], mean[1], mean[2], inv_std[0],
+  GLASS_CUDA(launch_pdl(stem_s2d_kernel, dim3(grid_for(total, 256)), dim3(256), 0, STREAM, img, n, h, w, mean[0], mean[1], mean[2], inv_std[0],
                                                             inv_std[1], inv_std[2], (uint4*)dst_hi, (uint4*)dst_lo,
-                                                            border);
+                                                            border));
   count_launch();
   GLASS_CUDA(cudaGetLastError());
   return 0;
@@ -352,9 +356,9 @@ extern "C" int glass_gather_taps(const void* src_hi, const void* src_lo, int n, 
   GLASS_CHECK(n > 0 && h > 0 && w > 0 && cp % 8 == 0 && kh > 0 && kw > 0 && sh > 0 && sw > 0 && ho > 0 && wo > 0,
               "bad shape");
   const int64_t total = (int64_t)n * ho * wo * kh * kw * (cp / 8);
-  gather_taps_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>((const uint4*)src_hi, (const uint4*)src_lo, n, h, w,
+  GLASS_CUDA(launch_pdl(gather_taps_kernel, dim3(grid_for(total, 256)), dim3(256), 0, STREAM, (const uint4*)src_hi, (const uint4*)src_lo, n, h, w,
                                                                cp / 8, border, kh, kw, sh, sw, ph, pw, ho, wo,
-                                                               (uint4*)dst_hi, (uint4*)dst_lo, dst_border, n_dev);
+                                                               (uint4*)dst_hi, (uint4*)dst_lo, dst_border, n_dev));
   count_launch();
   GLASS_CUDA(cudaGetLastError());
   return 0;
@@ -365,7 +369,7 @@ extern "C" int glass_zero_border(void* hi, void* lo, int n, int h, int w, int cp
   GLASS_CHECK(n > 0 && h > 0 && w > 0 && cp > 0 && cp % 8 == 0, "bad shape");
   const int hp = h + 2, wp = w + 2;
   const int64_t total = (int64_t)n * (2 * wp + 2 * (hp - 2)) * (cp / 8);
-  zero_border_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>((uint4*)hi, (uint4*)lo, n, hp, wp, cp / 8, n_dev);
+  GLASS_CUDA(launch_pdl(zero_border_kernel, dim3(grid_for(total, 256)), dim3(256), 0, STREAM, (uint4*)hi, (uint4*)lo, n, hp, wp, cp / 8, n_dev));
   count_launch();
   GLASS_CUDA(cudaGetLastError());
   return 0;
@@ -378,9 +382,9 @@ extern "C" int glass_maxpool(const void* src_hi, const void* src_lo, int n, int 
   GLASS_CHECK(n > 0 && h > 0 && w > 0 && cp % 8 == 0 && kh > 0 && kw > 0 && sh > 0 && sw > 0 && ho > 0 && wo > 0,
               "bad shape");
   const int64_t total = (int64_t)n * ho * wo * (cp / 8);
-  maxpool_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>((const uint4*)src_hi, (const uint4*)src_lo, n, h, w,
+  GLASS_CUDA(launch_pdl(maxpool_kernel, dim3(grid_for(total, 256)), dim3(256), 0, STREAM, (const uint4*)src_hi, (const uint4*)src_lo, n, h, w,
                                                            cp / 8, border, kh, kw, sh, sw, ph, pw, ho, wo,
-                                                           (uint4*)dst_hi, (uint4*)dst_lo, dst_border, n_dev);
+                                                           (uint4*)dst_hi, (uint4*)dst_lo, dst_border, n_dev));
   count_launch();
   GLASS_CUDA(cudaGetLastError());
   return 0;

@@ -18,6 +18,7 @@ namespace glass {
 __global__ void __launch_bounds__(256) pack_rois_kernel(const float* __restrict__ boxes, const int32_t* __restrict__ counts,
                                                         int n_img, int max_det, float* __restrict__ rois,
                                                         int32_t* __restrict__ word_start, int32_t* __restrict__ total) {
+  pdl_prologue();
   extern __shared__ int32_t s_start[];   // [n_img + 1]
   if (threadIdx.x == 0) {
     int acc = 0;
@@ -54,6 +55,7 @@ __global__ void __launch_bounds__(128) pack_detections_kernel(const float* __res
                                                               const float* __restrict__ probs,
                                                               const int32_t* __restrict__ word_start, int max_det, int tp,
                                                               float* __restrict__ rec) {
+  pdl_prologue();
   const int img = blockIdx.x / max_det, j = blockIdx.x - img * max_det;
   const int64_t row = (int64_t)blockIdx.x * (10 + tp);
   const bool live = j < min(max(counts[img], 0), max_det);
@@ -121,7 +123,7 @@ extern "C" int glass_pack_rois(const float* boxes, const int32_t* counts, int n_
                                int32_t* word_start, int32_t* total, void* stream) {
   GLASS_CHECK(boxes && counts && rois && word_start && total, "null pointer");
   GLASS_CHECK(n_img > 0 && n_img <= 4096 && max_det > 0, "bad shape (n_img <= 4096)");
-  pack_rois_kernel<<<1, 256, (n_img + 1) * sizeof(int32_t), STREAM>>>(boxes, counts, n_img, max_det, rois, word_start, total);
+  GLASS_CUDA(launch_pdl(pack_rois_kernel, dim3(1), dim3(256), (n_img + 1) * sizeof(int32_t), STREAM, boxes, counts, n_img, max_det, rois, word_start, total));
   count_launch();
   GLASS_CUDA(cudaGetLastError());
   return 0;
@@ -132,8 +134,8 @@ extern "C" int glass_pack_detections(const float* boxes, const float* scores, co
                                      int classes, float* rec, void* stream) {
   GLASS_CHECK(boxes && scores && counts && probs && word_start && rec, "null pointer");
   GLASS_CHECK(n_img > 0 && max_det > 0 && steps > 0 && classes > 0, "bad shape");
-  pack_detections_kernel<<<n_img * max_det, 128, 0, STREAM>>>(boxes, scores, orient, counts, probs, word_start, max_det,
-                                                              steps * classes, rec);
+  GLASS_CUDA(launch_pdl(pack_detections_kernel, dim3(n_img * max_det), dim3(128), 0, STREAM, boxes, scores, orient, counts, probs, word_start, max_det,
+                                                              steps * classes, rec));
   count_launch();
   GLASS_CUDA(cudaGetLastError());
   return 0;

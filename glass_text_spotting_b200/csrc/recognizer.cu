@@ -68,6 +68,7 @@ struct GcParams {
 };
 
 __global__ void __launch_bounds__(256) gc_attention_kernel(const GcParams p) {
+  pdl_prologue();
   if (p.n_words_dev && (int)blockIdx.x >= *p.n_words_dev) return;
   extern __shared__ float sm[];
   const int P = p.h * p.w;              // positions (256)
@@ -235,6 +236,7 @@ __global__ void __launch_bounds__(256) gc_attention_kernel(const GcParams p) {
 __global__ void hmean_rows_kernel(const __half* __restrict__ shi, const __half* __restrict__ slo, int n, int h, int w,
                                   int cp, int border, __half* __restrict__ dhi, __half* __restrict__ dlo,
                                   float* __restrict__ df32, const int32_t* __restrict__ n_dev) {
+  pdl_prologue();
   if (n_dev) n = min(n, max(*n_dev, 0));
   const int cpairs = cp / 2;
   const int64_t total = (int64_t)n * w * cpairs;
@@ -326,6 +328,7 @@ __global__ void __cluster_dims__(LC_R, 1, 1) __launch_bounds__(LC_THREADS, 1)
     lstm_cluster_mma_kernel(const float* __restrict__ gates_in, const float* __restrict__ whh_t, int n_seq, int T,
                             __half* __restrict__ out_hi, __half* __restrict__ out_lo, float* __restrict__ out_f32,
                             const int32_t* __restrict__ n_dev) {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char lc_smem[];
   if (n_dev) n_seq = min(n_seq, max(*n_dev, 0));
   if ((int)(blockIdx.x / LC_R) * LC_W >= n_seq) return;   // the whole cluster has no live word (uniform over its CTAs)
@@ -530,6 +533,7 @@ struct AsterParams {
 // The context vector itself is never formed (nothing else reads it).  Validated on B200 against the oracle and the
 // reference-run golden vectors (tests/test_gpu_roi_heads.py, tests/test_gpu_fullsize_parity.py).
 __global__ void __launch_bounds__(1024) aster_decode_kernel(const AsterParams p) {
+  pdl_prologue();
   // Per step (all 1024 threads busy in every matvec phase; the kernel is bound by streaming ~1.5 MB of weights and
   // per-word projections from L2 per step and CTA):
   //   A  sProj = sEmbed(h) (256 columns) and gh = W_hh h + b_hh (768 columns) in ONE pass over h: thread = column
@@ -743,6 +747,7 @@ __global__ void __launch_bounds__(1024) aster_decode_kernel(const AsterParams p)
 // rows after the image's break step are zero: break step = max over the image's words of first_eos
 __global__ void aster_finalize_kernel(float* __restrict__ probs, const int* __restrict__ first_eos,
                                       const int* __restrict__ word_start, int n_img, int steps, int nc) {
+  pdl_prologue();
   const int img = blockIdx.x;
   const int a = word_start[img], b = word_start[img + 1];
   __shared__ int s_break;
@@ -778,7 +783,7 @@ extern "C" int glass_gc_attention(const GlassGcAttentionParams* p, void* stream)
   k.w2t = p->w2t; k.b2 = p->b2;
   k.n_words_dev = p->n_words_dev;
   const int smem = (GC_HEADS * p->h * p->w + GC_C + GC_HID + GC_C) * (int)sizeof(float);
-  gc_attention_kernel<<<p->n_words, 256, smem, STREAM>>>(k);
+  GLASS_CUDA(launch_pdl(gc_attention_kernel, dim3(p->n_words), dim3(256), smem, STREAM, k));
   count_launch();
   GLASS_CUDA(cudaGetLastError());
   return 0;
@@ -792,8 +797,8 @@ extern "C" int glass_hmean_rows(const void* src_hi, const void* src_lo, int n, i
   const int64_t total = (int64_t)n * w * (cp / 2);
   int64_t blocks = (total + 255) / 256;
   if (blocks > (int64_t)num_sms() * 16) blocks = (int64_t)num_sms() * 16;
-  hmean_rows_kernel<<<(int)blocks, 256, 0, STREAM>>>((const __half*)src_hi, (const __half*)src_lo, n, h, w, cp, border,
-                                                     (__half*)dst_hi, (__half*)dst_lo, dst_f32, n_dev);
+  GLASS_CUDA(launch_pdl(hmean_rows_kernel, dim3((int)blocks), dim3(256), 0, STREAM, (const __half*)src_hi, (const __half*)src_lo, n, h, w, cp, border,
+                                                     (__half*)dst_hi, (__half*)dst_lo, dst_f32, n_dev));
   count_launch();
   GLASS_CUDA(cudaGetLastError());
   return 0;
@@ -809,8 +814,8 @@ extern "C" int glass_lstm_bidir(const float* gates_in, const float* whh_t, int n
                                                        cudaFuncAttributeMaxDynamicSharedMemorySize, LC_SMEM);
   GLASS_CUDA(attr);
   dim3 grid(((n_seq + LC_W - 1) / LC_W) * LC_R, 2);
-  lstm_cluster_mma_kernel<<<grid, LC_THREADS, LC_SMEM, STREAM>>>(gates_in, whh_t, n_seq, T, (__half*)out_hi,
-                                                                  (__half*)out_lo, out_f32, n_dev);
+  GLASS_CUDA(launch_pdl(lstm_cluster_mma_kernel, dim3(grid), dim3(LC_THREADS), LC_SMEM, STREAM, gates_in, whh_t, n_seq, T, (__half*)out_hi,
+                                                                  (__half*)out_lo, out_f32, n_dev));
   count_launch();
   GLASS_CUDA(cudaGetLastError());
   return 0;
@@ -831,7 +836,7 @@ extern "C" int glass_aster_decode(const GlassAsterParams* p, void* stream) {
   k.wh_frag = reinterpret_cast<const uint4*>(p->wh_frag); k.bh = p->bh; k.we = p->we; k.be = p->be; k.emb_gi = p->emb_gi;
   k.wo_t = p->wo_t; k.bo = p->bo; k.temperature = p->temperature;
   k.probs = p->probs; k.logits = p->logits; k.alphas = p->alphas; k.first_eos = p->first_eos;
-  aster_decode_kernel<<<(p->n_words + DEC_WPC - 1) / DEC_WPC, 1024, 0, STREAM>>>(k);
+  GLASS_CUDA(launch_pdl(aster_decode_kernel, dim3((p->n_words + DEC_WPC - 1) / DEC_WPC), dim3(1024), 0, STREAM, k));
   count_launch();
   GLASS_CUDA(cudaGetLastError());
   return 0;
@@ -841,7 +846,7 @@ extern "C" int glass_aster_finalize(float* probs, const int32_t* first_eos, cons
                                     int steps, int num_classes, void* stream) {
   GLASS_CHECK(probs && first_eos && word_start, "null pointer");
   GLASS_CHECK(n_img > 0 && steps > 0 && num_classes > 0, "bad shape");
-  aster_finalize_kernel<<<n_img, 256, 0, STREAM>>>(probs, first_eos, word_start, n_img, steps, num_classes);
+  GLASS_CUDA(launch_pdl(aster_finalize_kernel, dim3(n_img), dim3(256), 0, STREAM, probs, first_eos, word_start, n_img, steps, num_classes));
   count_launch();
   GLASS_CUDA(cudaGetLastError());
   return 0;

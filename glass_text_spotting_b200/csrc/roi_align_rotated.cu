@@ -54,6 +54,7 @@ __device__ __forceinline__ float4 load4(const void* base, const void* base_lo, i
 
 template <int NV, bool SPLIT_IN>  // float4 vectors per lane: channels <= 128*NV
 __global__ void __launch_bounds__(256) roi_align_rotated_kernel(const RoiKernelParams p) {
+  pdl_prologue();
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n_rois = p.n_rois_dev ? min(*p.n_rois_dev, p.n_rois) : p.n_rois;
@@ -214,6 +215,7 @@ static constexpr int kBinsPerWarp = 4;  // default consecutive bins per warp tas
 
 template <int S>  // S = 2: the sampling grid is 2 x 2 (all four samples' loads are in flight together); 0: generic
 __global__ void __launch_bounds__(256, 2) roi_align_rotated_split8_kernel(const RoiKernelParams p) {
+  pdl_prologue();
   // One warp per task of kBinsPerWarp consecutive output bins (a warp per whole row of bins was measured slower:
   // too few warps in flight); the grid is NOT persistent so that the block scheduler balances the tail.
   const int lane = threadIdx.x & 31;
@@ -356,6 +358,7 @@ struct ImgRoiKernelParams {
 // pooler would otherwise repeat for every tap): one 16-byte load per bilinear tap instead of three scalar ones
 __global__ void image_to_nhwc4_kernel(const float* __restrict__ img, int n, int h, int w, float m0, float m1, float m2,
                                       float is0, float is1, float is2, float4* __restrict__ out) {
+  pdl_prologue();
   const int64_t plane = (int64_t)h * w, total = (int64_t)n * plane;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t b = i / plane, r = i - b * plane;
@@ -370,6 +373,7 @@ __global__ void image_to_nhwc4_kernel(const float* __restrict__ img, int n, int 
 // walks its bins with the reference's fp32 arithmetic, operation for operation.
 constexpr int IMG_ROWS = 8;
 __global__ void __launch_bounds__(256) image_roi_align_rotated_kernel(const ImgRoiKernelParams p) {
+  pdl_prologue();
   const int n_rois = p.n_rois_dev ? min(*p.n_rois_dev, p.n_rois) : p.n_rois;
   const int row_blocks = (p.ph + IMG_ROWS - 1) / IMG_ROWS;
   const int roi_idx = blockIdx.x / row_blocks;
