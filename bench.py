@@ -989,9 +989,14 @@ def run_b200(args):
             if i + 1 < n:
                 upload((i + 1) % 2)           # next step's batch, overlapped with this step's compute
             stream.wait_event(ready[b])
-            fbuf.copy_(dbuf[b])               # uint8 -> fp32 on the device
-            consumed[b].record(stream)
-            loop_buf[i].copy_(step(fbuf), non_blocking=True)
+            if full and use_graph:
+                # uint8 -> fp32 happens in the copy into the graph's static input (one pass over the batch)
+                loop_buf[i].copy_(step(dbuf[b]), non_blocking=True)
+                consumed[b].record(stream)
+            else:
+                fbuf.copy_(dbuf[b])           # uint8 -> fp32 on the device
+                consumed[b].record(stream)
+                loop_buf[i].copy_(step(fbuf), non_blocking=True)
             done[i].record(stream)
             with torch.cuda.stream(copy_stream):   # this step's own result to the host, off the compute stream
                 copy_stream.wait_event(done[i])

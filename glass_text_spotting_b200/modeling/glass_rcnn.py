@@ -152,14 +152,14 @@ class B200GlassRCNN:
     def graph_step(self, images: torch.Tensor, img_hw: torch.Tensor) -> torch.Tensor:
         """``forward_packed`` replayed from a CUDA graph (captured on first use per input shape, after two eager warm-up
         passes that allocate every workspace): one graph launch per step instead of ~190 kernel launches, no host work
-        between them.  ``images`` / ``img_hw`` are copied into the graph's static inputs; returns the static record
-        buffer (valid until the next replay)."""
+        between them.  ``images`` (fp32, or uint8: converted by the copy) / ``img_hw`` are copied into the graph's static
+        inputs; returns the static record buffer (valid until the next replay)."""
         key = (tuple(images.shape), images.device.index)
         g = self._graphs.get(key) if hasattr(self, "_graphs") else None
         if g is None:
             if not hasattr(self, "_graphs"):
                 self._graphs = {}
-            static_in = images.clone()
+            static_in = images.float().clone()
             static_hw = img_hw.clone()
             cur = torch.cuda.current_stream()
             side = torch.cuda.Stream()
