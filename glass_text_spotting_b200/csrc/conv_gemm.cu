@@ -836,6 +836,44 @@ static int build_plan(const GlassConvGemmParams* p, GlassGemmPlan* plan) {
   GLASS_CHECK(sms > 0, "no CUDA device");
   const int tiles_m_all = (int)((rows_m + BM - 1) / BM);
   bool pair = (bn % 32 == 0) && bn >= 64 && (int64_t)tiles_m_all * (p->n / bn) >= sms;
+  // Small layers (a handful of tile rounds: res5, the p5 / p6 ends of FPN and RPN): the rule above can land just past a
+  // round boundary -- 37 M tiles x 4 N tiles = 76 pair units on 74 pairs = TWO rounds where 148 single tiles fill the 148
+  // SMs in one.  For them the tile width and the pairing are chosen together by rounds x (tile width / the width's
+  // measured MMA efficiency: 0.34 / 0.62 / 0.90 at 64 / 128 / 256 columns), pairs 3 % ahead for their shared weight tile.
+  static const int tile_model = getenv("GLASS_TILE_MODEL") ? atoi(getenv("GLASS_TILE_MODEL")) : 1;
+  if (tile_model && p->pair_mode != 2) {
+    auto rounds = [&](int w, bool pr) {
+      const int64_t um = pr ? (tiles_m_all + 1) / 2 : tiles_m_all;
+      const int64_t units = um * (p->n / w);
+      const int workers = pr ? sms / 2 : sms;
+      return (int)((units + workers - 1) / workers);
+    };
+    auto cost = [&](int w, bool pr) {
+      const double eff = w >= 256 ? 0.90 : (w >= 128 ? 0.62 + (w - 128) * (0.28 / 128.0) : 0.34 + (w - 64) * (0.28 / 64.0));
+      return rounds(w, pr) * (w / (eff > 0.1 ? eff : 0.1)) * (pr ? 0.97 : 1.0);
+    };
+    if (rounds(bn, pair) <= 3) {
+      int best_bn = bn;
+      bool best_pair = pair;
+      double best = cost(bn, pair);
+      int w = p->n > 256 ? ((p->n % 256 == 0) ? 256 : 128) : p->n;   // widest admissible tile, then its halvings
+      for (;;) {
+        for (int pr = 0; pr < 2; ++pr) {
+          if (pr && (p->pair_mode == 1 || w % 32 != 0 || w < 64)) continue;
+          const double c = cost(w, pr != 0);
+          if (c < best - 1e-9) {
+            best = c;
+            best_bn = w;
+            best_pair = pr != 0;
+          }
+        }
+        if (!(w > 64 && w % 2 == 0 && (w / 2) % 16 == 0 && p->n % (w / 2) == 0)) break;
+        w /= 2;
+      }
+      bn = best_bn;
+      pair = best_pair;
+    }
+  }
   if (p->pair_mode == 1) pair = false;
   if (p->pair_mode == 2) {
     GLASS_CHECK(bn % 32 == 0, "pair mode needs a tile width that is a multiple of 32");
