@@ -206,3 +206,17 @@ def test_decoder_fragment_packing_matches_the_mma_operand_layout():
         mt, ks, pl, lane, reg, e = (rnd.randrange(n) for n in (64, 16, 2, 32, 4, 2))
         row, k = mt * 16 + (lane >> 2) + 8 * (reg & 1), ks * 16 + 2 * (lane & 3) + 8 * (reg >> 1) + e
         assert f16[mt, ks, pl, lane, reg, e] == planes[pl, row, k]
+
+
+def test_gather_rows_follow_the_output_plane():
+    """ops.gather_rows: dense rows, the rows of padded planes, and of shared-border planes (only leading borders)."""
+    from glass_text_spotting_b200 import ops
+    assert ops.gather_rows(3, 8, 32, 0) == 3 * 8 * 32
+    assert ops.gather_rows(3, 8, 32, 1) == 3 * 10 * 34
+    assert ops.gather_rows(3, 8, 32, 1 | ops.BORDER_SHARED) == 3 * 9 * 33
+    a = ops.Act.__new__(ops.Act)   # geometry only: no device memory needed for the row count
+    for shared in (False, True):
+        a.n, a.h, a.w, a.border, a.shared = 5, 16, 33, 1, shared
+        hp = 16 + (1 if shared else 2)
+        wp = 33 + (1 if shared else 2)
+        assert ops.gather_rows(5, 16, 33, a.border | (ops.BORDER_SHARED if shared else 0)) == 5 * hp * wp
