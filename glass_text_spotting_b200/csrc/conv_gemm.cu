@@ -796,15 +796,6 @@ static int build_plan(const GlassConvGemmParams* p, GlassGemmPlan* plan) {
     GLASS_CHECK(p->n % 128 == 0, "n > 256 must be a multiple of 128");
     bn = (p->n % 256 == 0) ? 256 : 128;
   }
-  {   // A/B knob: 128-wide tiles for the 1x1 layers with lo..hi k-blocks ("GLASS_BN128_KB=lo,hi")
-    static const char* e = getenv("GLASS_BN128_KB");
-    if (e != nullptr && bn == 256 && p->ntaps == 1) {
-      int lo = 0, hi = -1;
-      sscanf(e, "%d,%d", &lo, &hi);
-      const int kb = p->k_per_tap / BK;
-      if (kb >= lo && kb <= hi) bn = 128;
-    }
-  }
   const int64_t rows_m = (int64_t)p->m_imgs * p->m_h * p->m_w;
   // Small-M GEMMs (the box head's FCs: 400 rows x 2048 columns x K = 12544; the RPN head on p5 / p6) would occupy a
   // fraction of the 148 SMs with 256-wide tiles, and each of those CTAs is bound by its own TMA feed: narrower tiles
